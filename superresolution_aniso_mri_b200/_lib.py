@@ -1,0 +1,73 @@
+"""ctypes binding of libaesr_b200.so (C-ABI declared in include/aesr_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing, or the device is not a compute-capability
+10.x GPU, every operator raises ``RuntimeError`` -- loudly, never a silent eager-PyTorch substitute.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libaesr_b200.so")
+
+_lib = None
+_initialised_devices = set()
+
+_SIGNATURES = {
+    "aesr_init": (c_int, [c_int]),
+    "aesr_last_error": (c_char_p, []),
+    "aesr_sm_count": (c_int, []),
+    "aesr_launch_count": (c_int64, []),
+    "aesr_pack_conv3x3_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "aesr_conv3x3_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
+    "aesr_e0_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "aesr_head_fwd": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_size_t,
+                              c_int, c_void_p]),
+    "aesr_place_slices": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "aesr_lerp_latents": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                  c_int, c_void_p]),
+}
+
+
+def exported_symbols():
+    """Names every entry point include/aesr_b200.h declares (used by the symbol-export test)."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Load the shared library (no GPU needed for this step)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "aesr_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU / eager fallback." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError here = header / library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().aesr_last_error()
+        raise RuntimeError("aesr_b200 %s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def lib_for_device(device_index: int):
+    """Library handle with ``aesr_init(device)`` done (checks sm_100a, resolves the TMA encoder)."""
+    lib = load()
+    if device_index not in _initialised_devices:
+        check(lib.aesr_init(int(device_index)), "init")
+        _initialised_devices.add(device_index)
+    return lib
+
+
+def launch_count() -> int:
+    return int(load().aesr_launch_count())

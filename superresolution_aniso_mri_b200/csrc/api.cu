@@ -1,0 +1,268 @@
+// extern "C" entry points of libaesr_b200.so (declared in include/aesr_b200.h).
+// Host-side glue only: argument validation, TMA descriptor encoding, grid sizing, launches.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/aesr_b200.h"
+#include "conv3x3_tc.cuh"
+#include "elementwise.cuh"
+
+using namespace aesr;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+std::once_flag g_init_once;
+int g_init_status = AESR_ERR_CUDA;
+int g_sm_count = 0;
+int g_max_smem_optin = 0;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_tiled = nullptr;
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) return fail(AESR_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+int check_launch(const char* what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(AESR_ERR_CUDA, "%s launch: %s", what, cudaGetErrorString(e));
+    return AESR_OK;
+}
+
+void do_init(int device) {
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        g_init_status = fail(AESR_ERR_CUDA, "no usable CUDA device %d: %s", device,
+                             cudaGetErrorString(cudaGetLastError()));
+        return;
+    }
+    if (prop.major != 10) {
+        g_init_status = fail(AESR_ERR_ARCH, "aesr_b200 needs a compute-capability 10.x (B200, sm_100a) device, got %d.%d (%s); "
+                             "there is no fallback path", prop.major, prop.minor, prop.name);
+        return;
+    }
+    g_sm_count = prop.multiProcessorCount;
+    g_max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+        g_init_status = fail(AESR_ERR_CUDA, "cannot resolve cuTensorMapEncodeTiled from the driver");
+        return;
+    }
+    g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+    g_init_status = AESR_OK;
+}
+
+int ensure_init() {
+    if (g_init_status != AESR_OK) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return aesr_init(dev);
+    }
+    return AESR_OK;
+}
+
+// NHWC bf16 activation [N,H,W,C] viewed as a 4-D tensor {C, W, H, N}; box = {KC, 8, 16, 1}.
+int make_act_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int KC) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, CONV_TILE_W, CONV_TILE_H, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(AESR_ERR_CUDA, "cuTensorMapEncodeTiled(activation) failed: %d", (int)r);
+    return AESR_OK;
+}
+
+// packed weights bf16 [9*Cout rows][Cin]; box = {KC, BN}.
+int make_wgt_tmap(CUtensorMap* m, const void* ptr, int rows, int Cin, int KC, int BN) {
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
+    cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(AESR_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    return AESR_OK;
+}
+
+__global__ void pack_conv3x3_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
+                                           int Cin, int transpose_flip) {
+    const int total = 9 * Cout * Cin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        // destination index: [tap][row][col]
+        int tap, row, col;
+        if (!transpose_flip) {
+            col = i % Cin; row = (i / Cin) % Cout; tap = i / (Cin * Cout);
+            out[i] = __float2bfloat16_rn(w[(static_cast<size_t>(row) * Cin + col) * 9 + tap]);
+        } else {
+            // dgrad: dX = conv(dY, W') with W'[tap][ci][co] = W[co][ci][8 - tap]
+            col = i % Cout; row = (i / Cout) % Cin; tap = i / (Cin * Cout);
+            out[i] = __float2bfloat16_rn(w[(static_cast<size_t>(col) * Cin + row) * 9 + (8 - tap)]);
+        }
+    }
+}
+
+template <int KC>
+int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
+    using S = ConvSmem<KC>;
+    int stages = CONV_MAX_STAGES;
+    while (stages > 2 && S::total_bytes(p.BN, stages) > g_max_smem_optin) --stages;
+    ConvParams q = p;
+    q.num_stages = stages;
+    const int smem = S::total_bytes(p.BN, stages);
+    static int configured_smem = 0;
+    if (smem > configured_smem) {
+        CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem_optin));
+        configured_smem = g_max_smem_optin;
+    }
+    const int grid = p.num_tiles < g_sm_count ? p.num_tiles : g_sm_count;
+    conv3x3_tc_kernel<KC><<<grid, CONV_THREADS, smem, stream>>>(tx, tw, q);
+    return check_launch("conv3x3_tc");
+}
+
+}  // namespace
+
+extern "C" {
+
+int aesr_init(int device) {
+    std::call_once(g_init_once, do_init, device);
+    if (g_init_status != AESR_OK) return g_init_status;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(AESR_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    return AESR_OK;
+}
+
+const char* aesr_last_error(void) { return g_err; }
+int aesr_sm_count(void) { return g_sm_count; }
+int64_t aesr_launch_count(void) { return g_launches.load(); }
+
+int aesr_pack_conv3x3_weight(const float* w, void* packed, int Cout, int Cin, int transpose_flip, void* stream) {
+    if (!w || !packed || Cout <= 0 || Cin <= 0) return fail(AESR_ERR_INVALID, "pack_conv3x3_weight: bad arguments");
+    const int total = 9 * Cout * Cin;
+    pack_conv3x3_weight_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        w, static_cast<__nv_bfloat16*>(packed), Cout, Cin, transpose_flip);
+    return check_launch("pack_conv3x3_weight");
+}
+
+int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, const float* scale, const float* shift,
+                     void* out, void* out2, const void* mul_src, float* stats, int N, int H, int W, int Cin, int Cout,
+                     int act, float slope, int out_mode, int mul_mode, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!x || !w_packed || !out) return fail(AESR_ERR_INVALID, "conv3x3_fwd: null tensor");
+    if (N <= 0 || H <= 0 || W <= 0) return fail(AESR_ERR_INVALID, "conv3x3_fwd: empty shape N=%d H=%d W=%d", N, H, W);
+    if (Cin % 32 != 0 || Cin < 32 || Cin > 512 || (Cin > 32 && Cin % 64 != 0))
+        return fail(AESR_ERR_INVALID, "conv3x3_fwd: Cin=%d unsupported (32, 64, 128, 256, 512)", Cin);
+    if (Cout % 32 != 0 || Cout < 32 || Cout > 512) return fail(AESR_ERR_INVALID, "conv3x3_fwd: Cout=%d unsupported", Cout);
+    if ((scale == nullptr) != (shift == nullptr)) return fail(AESR_ERR_INVALID, "conv3x3_fwd: scale/shift must come together");
+    if (out_mode < 0 || out_mode > 4) return fail(AESR_ERR_INVALID, "conv3x3_fwd: out_mode=%d", out_mode);
+    if (out_mode == AESR_OUT_SAME_MAXPOOL2 && !out2) return fail(AESR_ERR_INVALID, "conv3x3_fwd: maxpool needs out2");
+    if (mul_mode != AESR_MUL_NONE && !mul_src) return fail(AESR_ERR_INVALID, "conv3x3_fwd: mul_mode without mul_src");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(out)) & 15)
+        return fail(AESR_ERR_INVALID, "conv3x3_fwd: tensors must be 16-byte aligned");
+
+    ConvParams p{};
+    p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
+    p.BN = Cout <= 256 ? Cout : 256;
+    if (Cout % p.BN != 0) return fail(AESR_ERR_INVALID, "conv3x3_fwd: Cout=%d not a multiple of the N tile %d", Cout, p.BN);
+    p.tiles_x = (W + CONV_TILE_W - 1) / CONV_TILE_W;
+    p.tiles_y = (H + CONV_TILE_H - 1) / CONV_TILE_H;
+    p.n_blocks = Cout / p.BN;
+    p.num_tiles = N * p.tiles_x * p.tiles_y * p.n_blocks;
+    p.bias = bias; p.scale = scale; p.shift = shift; p.slope = slope; p.act = act; p.out_mode = out_mode;
+    p.out = out; p.out2 = out2; p.mul_src = static_cast<const __nv_bfloat16*>(mul_src); p.mul_mode = mul_mode;
+    p.stats = stats;
+
+    const int KC = (Cin >= 64) ? 64 : 32;
+    CUtensorMap tx, tw;
+    rc = make_act_tmap(&tx, x, N, H, W, Cin, KC);
+    if (rc != AESR_OK) return rc;
+    rc = make_wgt_tmap(&tw, w_packed, 9 * Cout, Cin, KC, p.BN);
+    if (rc != AESR_OK) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return KC == 64 ? launch_conv<64>(tx, tw, p, s) : launch_conv<32>(tx, tw, p, s);
+}
+
+int aesr_e0_fwd(const float* x, const float* w, const float* b, void* out, int N, int H, int W, int C, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!x || !w || !b || !out || N <= 0 || H <= 0 || W <= 0 || C % 8 != 0)
+        return fail(AESR_ERR_INVALID, "e0_fwd: bad arguments");
+    const size_t total = static_cast<size_t>(N) * (H + 2) * (W + 2) * (C / 8);
+    const int block = 256;
+    size_t grid = (total + block - 1) / block;
+    const size_t cap = static_cast<size_t>(g_sm_count) * 16;
+    if (grid > cap) grid = cap;
+    e0_conv1x1_pad1_kernel<<<static_cast<int>(grid), block, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, w, b, static_cast<__nv_bfloat16*>(out), N, H, W, C);
+    return check_launch("e0_conv1x1_pad1");
+}
+
+int aesr_head_fwd(const void* in, const float* w9c, float bias, float* out, const int* out_index, int N, int H, int W,
+                  int C, size_t out_image_stride, int apply_sigmoid, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!in || !w9c || !out || N <= 0 || H <= 0 || W <= 0) return fail(AESR_ERR_INVALID, "head_fwd: bad arguments");
+    if (C != 32) return fail(AESR_ERR_INVALID, "head_fwd: C=%d unsupported (32)", C);
+    const size_t total = static_cast<size_t>(N) * H * W;
+    const int block = 128;
+    size_t grid = (total + block - 1) / block;
+    const size_t cap = static_cast<size_t>(g_sm_count) * 32;
+    if (grid > cap) grid = cap;
+    head_conv3x3_sigmoid_kernel<32><<<static_cast<int>(grid), block, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(in), w9c, bias, out, out_index, N, H, W, out_image_stride, apply_sigmoid);
+    return check_launch("head_conv3x3_sigmoid");
+}
+
+int aesr_lerp_latents(const float* z, const int* ia, const int* ib, const float* wa, const float* wb, void* out_nhwc,
+                      float* out_nchw, int M, int C, int HW, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!z || !ia || !ib || !wa || !wb || !out_nhwc || C <= 0 || HW <= 0) return fail(AESR_ERR_INVALID, "lerp_latents: bad arguments");
+    if (M == 0) return AESR_OK;
+    if (M < 0 || M > 65535) return fail(AESR_ERR_INVALID, "lerp_latents: M=%d out of range (1..65535 per call)", M);
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, M), block(32, 8);
+    lerp_nchw_to_nhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        z, ia, ib, wa, wb, static_cast<__nv_bfloat16*>(out_nhwc), out_nchw, C, HW);
+    return check_launch("lerp_nchw_to_nhwc");
+}
+
+int aesr_place_slices(const float* src, float* dst, const int* out_index, int N, int HW, int do_clamp, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!src || !dst || HW <= 0) return fail(AESR_ERR_INVALID, "place_slices: bad arguments");
+    if (N == 0) return AESR_OK;
+    if (N < 0 || N > 65535) return fail(AESR_ERR_INVALID, "place_slices: N=%d out of range (1..65535 per call)", N);
+    const int block = 256;
+    int gx = ((HW >> 2) + block - 1) / block;
+    if (gx < 1) gx = 1;
+    if (gx > 64) gx = 64;
+    place_slices_kernel<<<dim3(gx, N), block, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, out_index, N, HW, do_clamp);
+    return check_launch("place_slices");
+}
+
+}  // extern "C"

@@ -1,0 +1,164 @@
+// Memory-bound kernels around the tensor-core convs: network head/tail convs with 1 input or 1 output channel
+// (CUDA cores, nothing for a tensor core to do there), latent interpolation + layout change, and the
+// image-domain utilities.  All coalesced / 16-byte vectorised; grids sized from the problem, no smem unless it buys
+// coalescing (the NCHW <-> NHWC transposes).
+#pragma once
+#include "common.cuh"
+
+namespace aesr {
+
+// ---------------------------------------------------------------------------------------------------------------
+// enc.0 : Conv2d(1, C, kernel 1, padding 1)   (networks/acai_vanilla.py:51)
+// x fp32 [N,1,H,W]  ->  out bf16 NHWC [N,H+2,W+2,C];  out = w[c] * xpad + b[c]  (ring pixels = bias)
+// one thread = one output pixel x 8 channels (one 16-byte store)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void e0_conv1x1_pad1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                       const float* __restrict__ b, __nv_bfloat16* __restrict__ out, int N, int H,
+                                       int W, int C) {
+    const int Ho = H + 2, Wo = W + 2;
+    const int groups = C >> 3;
+    const size_t total = static_cast<size_t>(N) * Ho * Wo * groups;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % groups);
+        const size_t pix = i / groups;
+        const int xo = static_cast<int>(pix % Wo);
+        const int yo = static_cast<int>((pix / Wo) % Ho);
+        const int n = static_cast<int>(pix / (static_cast<size_t>(Wo) * Ho));
+        const int yi = yo - 1, xi = xo - 1;
+        const float xv = (yi >= 0 && yi < H && xi >= 0 && xi < W)
+                             ? __ldg(x + (static_cast<size_t>(n) * H + yi) * W + xi) : 0.f;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(__ldg(w + g * 8 + j), xv, __ldg(b + g * 8 + j));
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dec.14 + dec.15 : Conv2d(C, 1, 3, padding 1) + Sigmoid  (networks/acai_vanilla.py:98), C = 32
+// in bf16 NHWC [N,H,W,32] -> out fp32 [N,1,H,W] (clamped to [0,1] like generate_hr_volumes.py:67; a no-op after
+// the sigmoid).  Optionally also writes the pre-sigmoid logit (training backward).
+// One thread per output pixel; the 3x3x32 filter sits in shared memory as fp32.
+// ---------------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void head_conv3x3_sigmoid_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w /*[9][C]*/,
+                                            float bias, float* __restrict__ out, const int* __restrict__ out_index,
+                                            int N, int H, int W, size_t out_image_stride, int apply_sigmoid) {
+    __shared__ float sw[9 * C];
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const size_t total = static_cast<size_t>(N) * H * W;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(i % W);
+        const int y = static_cast<int>((i / W) % H);
+        const int n = static_cast<int>(i / (static_cast<size_t>(W) * H));
+        float acc = bias;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int yy = y + dy - 1;
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const int xx = x + dx - 1;
+                if (xx < 0 || xx >= W) continue;
+                const uint4* src = reinterpret_cast<const uint4*>(
+                    in + ((static_cast<size_t>(n) * H + yy) * W + xx) * C);
+                const float* wt = sw + (dy * 3 + dx) * C;
+#pragma unroll
+                for (int j4 = 0; j4 < C / 8; ++j4) {
+                    const uint4 m = __ldg(src + j4);
+                    const uint32_t u[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        acc = fmaf(bf16_lo(u[k]), wt[j4 * 8 + k * 2], acc);
+                        acc = fmaf(bf16_hi(u[k]), wt[j4 * 8 + k * 2 + 1], acc);
+                    }
+                }
+            }
+        }
+        float r = acc;
+        if (apply_sigmoid) {
+            r = 1.f / (1.f + __expf(-acc));
+            r = fminf(fmaxf(r, 0.f), 1.f);
+        }
+        const size_t slot = out_index ? static_cast<size_t>(__ldg(out_index + n)) : static_cast<size_t>(n);
+        out[slot * out_image_stride + static_cast<size_t>(y) * W + x] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// latent interpolation + layout change
+//   z    fp32 NCHW [*, C, HW]  (public latent layout)
+//   out  bf16 NHWC [M, HW, C]  (decoder input), optionally also fp32 NCHW [M, C, HW] (the public z_mix)
+//   out[m] = wa[m] * z[ia[m]] + wb[m] * z[ib[m]]   -- three separately rounded fp32 ops (mul, mul, add), exactly
+//   what `alpha * latent_1 + (1 - alpha) * latent_2` does in torch (generate_hr_volumes.py:88); ib[m] < 0 => copy.
+// 32 pixels x 32 channels per block through a padded smem tile: reads coalesced along pixels, writes along channels.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void lerp_nchw_to_nhwc_kernel(const float* __restrict__ z, const int* __restrict__ ia,
+                                         const int* __restrict__ ib, const float* __restrict__ wa,
+                                         const float* __restrict__ wb, __nv_bfloat16* __restrict__ out_nhwc,
+                                         float* __restrict__ out_nchw, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int m = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int a = ia[m], b = ib[m];
+    const float fa = wa[m], fb = (b >= 0) ? wb[m] : 0.f;
+    const float* za = z + static_cast<size_t>(a) * C * HW;
+    const float* zb = z + static_cast<size_t>(b >= 0 ? b : a) * C * HW;
+    for (int cy = threadIdx.y; cy < 32; cy += blockDim.y) {
+        const int c = c0 + cy, p = p0 + threadIdx.x;
+        float v = 0.f;
+        if (c < C && p < HW) {
+            const size_t off = static_cast<size_t>(c) * HW + p;
+            if (b >= 0) v = __fadd_rn(__fmul_rn(fa, za[off]), __fmul_rn(fb, zb[off]));
+            else v = za[off];
+            if (out_nchw) out_nchw[static_cast<size_t>(m) * C * HW + off] = v;
+        }
+        tile[cy][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int py = threadIdx.y; py < 32; py += blockDim.y) {
+        const int p = p0 + py, c = c0 + threadIdx.x;
+        if (p < HW && c < C)
+            out_nhwc[(static_cast<size_t>(m) * HW + p) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][py]);
+    }
+}
+
+}  // namespace aesr
+
+namespace aesr {
+
+// ---------------------------------------------------------------------------------------------------------------
+// kept (original) slices of the HR volume: dst[out_index[n]] = clamp(src[n], 0, 1)   (generate_hr_volumes.py:44,58-67)
+// fp32 images of HW pixels, float4 vectorised when HW % 4 == 0.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void place_slices_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                    const int* __restrict__ out_index, int N, int HW, int do_clamp) {
+    const int n = blockIdx.y;
+    const size_t slot = out_index ? static_cast<size_t>(out_index[n]) : static_cast<size_t>(n);
+    const float* s = src + static_cast<size_t>(n) * HW;
+    float* d = dst + slot * HW;
+    if ((HW & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(s);
+        float4* d4 = reinterpret_cast<float4*>(d);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (HW >> 2); i += gridDim.x * blockDim.x) {
+            float4 v = __ldg(s4 + i);
+            if (do_clamp) {
+                v.x = fminf(fmaxf(v.x, 0.f), 1.f); v.y = fminf(fmaxf(v.y, 0.f), 1.f);
+                v.z = fminf(fmaxf(v.z, 0.f), 1.f); v.w = fminf(fmaxf(v.w, 0.f), 1.f);
+            }
+            d4[i] = v;
+        }
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+            float v = __ldg(s + i);
+            if (do_clamp) v = fminf(fmaxf(v, 0.f), 1.f);
+            d[i] = v;
+        }
+    }
+}
+
+}  // namespace aesr

@@ -1,0 +1,161 @@
+"""Volume synthesis: encode the low-resolution slices, interpolate latents at every alpha, decode the in-between slices.
+
+Drop-in for ``generate_hr_volumes.create_super_volume / latent_space_interp`` (generate_hr_volumes.py:12-101) and the
+evaluation twin ``evaluate/common.create_super_volume`` (evaluate/common.py:134-235), with the reference's result
+(slice order, lerp weights, clamp) but the minimal work: every slice is encoded ONCE (the reference re-encodes both
+neighbours for every alpha), all (pair, alpha) latents are blended and decoded as one batch, and each synthesized slice
+is written by the decoder's last kernel straight to its position ``i*(A+1)+1+k`` of a preallocated volume (the
+reference builds it with an O(Z^2) chain of torch.cat).  Eval-mode BatchNorm is per-sample, so batching differently
+from the reference cannot change a value.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def interp_weights(alpha_range: Sequence[float]):
+    """fp32 weights exactly as torch forms them from a float64 python scalar: w_hi = fp32(alpha) multiplies the LATER
+    slice, w_lo = fp32(1 - alpha) (subtraction in float64) the earlier one (generate_hr_volumes.py:50,88)."""
+    a = np.asarray(alpha_range, dtype=np.float64)
+    return a.astype(np.float32), (1.0 - a).astype(np.float32)
+
+
+def _model_of(trainer_or_model, use_sr_model: bool = True):
+    m = trainer_or_model
+    if hasattr(m, "_use_sr_model"):
+        return m._use_sr_model(use_sr_model)
+    return getattr(m, "model", m)
+
+
+def pair_plan(num_slices: int, num_alphas: int, w_hi: np.ndarray, w_lo: np.ndarray, device, slice_offset: int = 0,
+              out_offset: int = 0):
+    """Index / weight tables for all (pair i, alpha k) problems of one volume, m = i*A + k:
+    out[i*(A+1)+1+k] = dec(w_hi[k] * z[i+1] + w_lo[k] * z[i])."""
+    Z, A = num_slices, num_alphas
+    i = np.repeat(np.arange(Z - 1, dtype=np.int64), A)
+    k = np.tile(np.arange(A, dtype=np.int64), Z - 1)
+    ia = (i + 1 + slice_offset).astype(np.int32)
+    ib = (i + slice_offset).astype(np.int32)
+    out_idx = (i * (A + 1) + 1 + k + out_offset).astype(np.int32)
+    return ia, ib, w_hi[k].astype(np.float32), w_lo[k].astype(np.float32), out_idx
+
+
+@torch.no_grad()
+def synthesize_volumes(model, volumes: torch.Tensor, alpha_range: Sequence[float], use_original: bool = True,
+                       decode_chunk: int = 128, encode_chunk: int = 256, out: Optional[torch.Tensor] = None
+                       ) -> torch.Tensor:
+    """Batched synthesis of V independent volumes.  volumes: [V,Z,H,W] fp32 (device) -> [V,(Z-1)(A+1)+1,H,W] fp32.
+
+    ``decode_chunk`` / ``encode_chunk`` bound the slices per kernel launch so that inter-layer activations
+    (<= 1 MiB bf16 per 128x128 slice and layer) stay resident in the 126 MB L2 between producer and consumer."""
+    assert volumes.dim() == 4 and volumes.is_cuda
+    V, Z, H, W = volumes.shape
+    A = len(alpha_range)
+    dev = volumes.device
+    w_hi, w_lo = interp_weights(alpha_range)
+    Zo = (Z - 1) * (A + 1) + 1
+    vol = volumes.float().contiguous()
+    if out is None:
+        out = torch.empty((V, Zo, H, W), dtype=torch.float32, device=dev)
+    flat_in = vol.view(V * Z, 1, H, W)
+    # ---- encode every slice once
+    z_parts, rec_parts = [], []
+    for s in range(0, V * Z, encode_chunk):
+        z_parts.append(model.encode_eval(flat_in[s:s + encode_chunk]))
+    z = z_parts[0] if len(z_parts) == 1 else torch.cat(z_parts, dim=0)
+    # ---- kept slices: originals (clamped, generate_hr_volumes.py:44,67) or reconstructions
+    idx = torch.arange(V * Z, dtype=torch.int32, device=dev)
+    if use_original:
+        oi = ((idx // Z) * Zo + (idx % Z) * (A + 1)).to(torch.int32)
+        ops.place_slices(flat_in, out, oi, clamp=True)
+    else:
+        neg = torch.full((V * Z,), -1, dtype=torch.int32, device=dev)
+        one = torch.ones(V * Z, dtype=torch.float32, device=dev)
+        oi = ((idx // Z) * Zo + (idx % Z) * (A + 1)).to(torch.int32)
+        for s in range(0, V * Z, decode_chunk):
+            e = min(s + decode_chunk, V * Z)
+            a = ops.lerp_latents(z, idx[s:e], neg[s:e], one[s:e], one[s:e])
+            model.decode_nhwc_eval(a, out=out, out_image_stride=H * W, out_index=oi[s:e].contiguous())
+    if A == 0 or Z < 2:
+        return out
+    # ---- all (volume, pair, alpha) lerp+decode problems
+    plans = [pair_plan(Z, A, w_hi, w_lo, dev, slice_offset=v * Z, out_offset=v * Zo) for v in range(V)]
+    ia, ib, wa, wb, oi = (torch.from_numpy(np.concatenate([p[j] for p in plans])).to(dev, non_blocking=True)
+                          for j in range(5))
+    M = ia.numel()
+    for s in range(0, M, decode_chunk):
+        e = min(s + decode_chunk, M)
+        a = ops.lerp_latents(z, ia[s:e], ib[s:e], wa[s:e], wb[s:e])
+        model.decode_nhwc_eval(a, out=out, out_image_stride=H * W, out_index=oi[s:e])
+    return out
+
+
+@torch.no_grad()
+def latent_space_interp(alpha, trainer, img1, img2, device="cuda", with_labels=False, hierarchical=False) -> dict:
+    """generate_hr_volumes.py:72-101 / kwatsch/img_interpolation.py:57-89 (same signature and return dict)."""
+    if with_labels or hierarchical:
+        raise NotImplementedError("aesr_b200: label / hierarchical latents belong to other model families")
+    model = _model_of(trainer)
+    img1 = img1.float().to(device)
+    img2 = img2.float().to(device)
+    n = img1.shape[0]
+    z = model.encode_eval(torch.cat([img1, img2], dim=0))
+    hi, lo = interp_weights([float(alpha)])
+    ia = torch.arange(n, dtype=torch.int32, device=z.device)
+    a = ops.lerp_latents(z, ia, ia + n, torch.full((n,), float(hi[0]), device=z.device),
+                         torch.full((n,), float(lo[0]), device=z.device))
+    img = model.decode_nhwc_eval(a)
+    return {"inter_image": img.detach().cpu(), "inter_label": None}
+
+
+@torch.no_grad()
+def create_super_volume(trainer, images: torch.Tensor, alpha_range, use_original: bool = False, labels=None) -> dict:
+    """generate_hr_volumes.py:12-69: images [Z,1,H,W] or [Z,H,W] -> {'upsampled_image': [(Z-1)(A+1)+1,H,W] (CPU)}."""
+    if labels is not None:
+        raise NotImplementedError("aesr_b200: label volumes belong to the multi-channel model family")
+    model = _model_of(trainer)
+    if images.dim() == 4:
+        images = images[:, 0]
+    dev = next(model.parameters()).device
+    vol = images.float().to(dev).unsqueeze(0)
+    # the final torch.clamp(0, 1) of the reference (:67) is applied inside the kernels that write `out`
+    out = synthesize_volumes(model, vol, alpha_range, use_original=use_original)[0]
+    return {"upsampled_image": out.cpu(), "upsampled_labels": None}
+
+
+@torch.no_grad()
+def create_super_volume_eval(trainer, images: torch.Tensor, alpha_range=None, use_original: bool = False,
+                             hierarchical: bool = False, downsample_steps: Optional[int] = None,
+                             generate_inbetween_slices: bool = False, train_patch_size=None, feature_dict=None,
+                             labels=None) -> dict:
+    """evaluate/common.py:134-235: optional slice dropping images[::d] after trimming (Z-1) % d tail slices, tail
+    re-appended untouched."""
+    if labels is not None or hierarchical:
+        raise NotImplementedError("aesr_b200: labels / hierarchical latents are out of scope")
+    if generate_inbetween_slices and downsample_steps is None:
+        downsample_steps = int(len(alpha_range) + 1)
+    orig_images, orig_num = None, images.shape[0]
+    if downsample_steps is not None or generate_inbetween_slices:
+        orig_images = images.clone()
+        if (orig_num - 1) % downsample_steps != 0:
+            images = images[:-((orig_num - 1) % downsample_steps)]
+        images = images[::downsample_steps]
+    if alpha_range is None:
+        alpha_range = [0.25, 0.5, 0.75]
+    res = create_super_volume(trainer, images, alpha_range, use_original=use_original)
+    new_volume = res["upsampled_image"]
+    if generate_inbetween_slices and (orig_num - 1) % downsample_steps != 0:
+        remain = (orig_num - 1) % downsample_steps
+        tail = orig_images[-remain:].float().cpu()
+        if tail.dim() == 4:
+            tail = tail[:, 0]
+        new_volume = torch.cat([new_volume, torch.clamp(tail, 0, 1.)])
+    n_alpha = len(alpha_range)
+    pred_alphas = torch.cat([torch.FloatTensor([a]).expand(images.shape[0] - 1) for a in alpha_range]) \
+        if n_alpha else None
+    return {"upsampled_image": new_volume, "upsampled_labels": None, "pred_alphas": pred_alphas}
