@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched HR-volume synthesis (encode -> interpolate latents -> decode).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one process per GPU)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port) on host cores
+
+One "step" = one pass of the hot path over one batch of synthetic volumes: V ACDC-shaped volumes [10,128,128] per GPU,
+num_interpolations = 6 (the generate_hr_volumes.py default) -> V*54 synthesized slices per GPU per step.  The metric
+is BASELINE.json's "synthesized HR slices/sec"; `value` has the inputs resident in HBM, `e2e` goes through the public
+host-buffer API (pinned host volumes in, HR volumes back to pinned host memory, copies inside the timed region).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "synthesized_hr_slices_per_sec"
+Z, SIZE, NI = 10, 128, 6
+# algorithmic conv FLOPs (2*MAC) of the reference's formulation, per image (ACDC scales=2 @128^2)
+ENC_GMAC, DEC_GMAC = 0.7722, 0.3822
+
+
+def flops_per_step(V: int) -> float:
+    """Minimal-work count: every slice encoded once, every synthesized slice decoded once."""
+    return 2e9 * (V * Z * ENC_GMAC + V * (Z - 1) * NI * DEC_GMAC)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm (CPU)
+def cpu_synthesis_rate(sample_volumes: int, repeats: int):
+    """The reference's algorithm for the path (generate_hr_volumes.create_super_volume as written: both neighbours
+    re-encoded for every alpha) restated in oracle/aesr_oracle.py, on all host threads torch will use."""
+    from oracle import aesr_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    args = O.default_args(SIZE, 32)
+    state = O.init_state(args, seed=892372)
+    ar = O.alpha_range_for(NI)
+    vols = [O.synthetic_volume(Z, SIZE, seed=1 + i) for i in range(sample_volumes)]
+    O.create_super_volume(state, args, vols[0], ar, use_original=True)        # warm-up
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for v in vols:
+            O.create_super_volume(state, args, v, ar, use_original=True)
+        best = min(best, time.perf_counter() - t0)
+    return sample_volumes * (Z - 1) * NI / best, torch.get_num_threads(), best
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 2
+    t0 = time.perf_counter()
+    for _ in range(a.warmup):
+        cpu_synthesis_rate(1, 1)
+    rates = []
+    for _ in range(a.steps):
+        r, cores, _ = cpu_synthesis_rate(sample, 1)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    value = float(np.mean(rates))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sample * (Z - 1) * NI / value,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ACDC-shaped volumes [10,128,128], num_interpolations=6, ae_combined scales=2 "
+                                   "(width 128, latent_width 32, latent 128)", "sample": "%d volumes per step" % sample},
+            "cpu_baseline": {"value": value, "unit": "slices/s", "cores": cores, "kind": "port",
+                             "sample": "%d volumes (%d synthesized slices) per step, %d steps, oracle port of "
+                                       "generate_hr_volumes.create_super_volume" % (sample, sample * 54, a.steps)},
+            "e2e": {"value": value, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": wall}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- this repo's arm (GPU)
+def run_ours(a):
+    import torch.distributed as dist
+    from oracle import aesr_oracle as O          # synthetic inputs / seeded weights only (never computes on this arm)
+    from superresolution_aniso_mri_b200 import _lib, ops, synthesis
+    from superresolution_aniso_mri_b200.networks.acai_vanilla import VanillaACAI
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200 GPU; there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from superresolution_aniso_mri_b200 import build
+    if rank == 0:
+        build.build_library()
+    if world > 1:
+        dist.barrier()
+    V = a.volumes
+    args = O.default_args(SIZE, 32)
+    margs = dict(args)
+    margs["device"] = str(dev)
+    torch.manual_seed(892372)
+    model = VanillaACAI(margs)
+    model.load_state_dict(O.calibrated_state(args))      # seeded synthetic checkpoint with O(1) activations
+    model.eval()
+    ar = O.alpha_range_for(NI)
+    g = torch.Generator().manual_seed(100 + rank)
+    host_in = torch.rand(V, Z, SIZE, SIZE, generator=g).pin_memory()
+    dev_in = host_in.to(dev)
+    Zo = (Z - 1) * (NI + 1) + 1
+    dev_out = torch.empty(V, Zo, SIZE, SIZE, device=dev)
+    host_out = torch.empty(V, Zo, SIZE, SIZE).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)          # 256 MB > 126 MB L2
+
+    def step_device():
+        synthesis.synthesize_volumes(model, dev_in, ar, use_original=True, out=dev_out,
+                                     decode_chunk=a.chunk, encode_chunk=a.chunk)
+
+    pipe = synthesis.HostPipeline(model, V, Z, SIZE, SIZE, ar, groups=a.groups, chunk=a.chunk)
+
+    def step_host():
+        pipe.run(host_in, host_out)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(step_fn, steps, flush_l2):
+        """K steps, device timing with CUDA events on the launching stream, L2 flushed between steps."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for s in range(steps):
+            if flush_l2:
+                flush.zero_()
+            ev[s][0].record()
+            step_fn()
+            ev[s][1].record()
+        barrier()
+        ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms_total = timed(step_device, a.steps, True)
+    launches = (_lib.launch_count() - l0)
+    clocks = sampler.stop() if sampler else None
+    slices_per_step = world * V * (Z - 1) * NI
+    value = slices_per_step * a.steps / (ms_total * 1e-3)
+
+    # ---- e2e: pinned host volumes -> HR volumes in pinned host memory, H2D/D2H inside the timed region
+    for _ in range(max(a.warmup, 3)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for _ in range(a.steps):
+        step_host()
+    e_end.record()
+    barrier()
+    e2e_ms = torch.tensor([e_start.elapsed_time(e_end)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = slices_per_step * a.steps / (float(e2e_ms.item()) * 1e-3)
+    _ = time.perf_counter() - t0
+
+    # ---- roofline of the dominant kernel family (tcgen05 conv3x3), timed per launch with CUDA events, untimed pass
+    roof = None
+    if rank == 0:
+        peaks = load_peaks()
+        ops.TIMING = []
+        step_device()
+        torch.cuda.synchronize()
+        conv_ms = sum(e0.elapsed_time(e1) for name, e0, e1, fl in ops.TIMING if name == "conv3x3")
+        conv_fl = sum(fl for name, e0, e1, fl in ops.TIMING if name == "conv3x3")
+        n_conv = sum(1 for t in ops.TIMING if t[0] == "conv3x3")
+        all_ms = sum(e0.elapsed_time(e1) for name, e0, e1, fl in ops.TIMING)
+        ops.TIMING = None
+        ach = conv_fl / (conv_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "conv3x3_halo_kernel (tcgen05, all %d launches of a step)" % n_conv,
+                "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" % peaks["source"],
+                "conv_ms_per_step": conv_ms, "all_kernels_ms_per_step": all_ms,
+                "conv_share_of_kernel_time": conv_ms / all_ms if all_ms else None,
+                "algorithmic_gflop_per_step": conv_fl / 1e9}
+
+    if rank == 0:
+        cpu_rate, cores, cpu_t = cpu_synthesis_rate(a.cpu_sample, 3)
+        line = {"metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f16" if ops.DEFAULT_DTYPE == torch.float16 else "bf16",
+                "data": "synthetic",
+                "config": {"workload": "batched HR volume generation: %d ACDC-shaped volumes [10,128,128] per GPU per "
+                                       "step, num_interpolations=6 -> %d synthesized slices/GPU/step; ae_combined "
+                                       "scales=2 (width 128, latent_width 32, latent 128), seeded synthetic checkpoint"
+                                       % (V, V * 54),
+                           "volumes_per_gpu": V, "chunk": a.chunk, "l2": "256 MB flush buffer written between steps",
+                           "accumulate": "fp32 (TMEM)", "sharding": "volumes over ranks, no collective"},
+                "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": host_in.numel() * 4,
+                        "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": float(e2e_ms.item()) / a.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+                "cpu_baseline": {"value": cpu_rate, "unit": "slices/s", "cores": cores, "kind": "port",
+                                 "sample": "%d volumes (%d synthesized slices), best of 3, %.2f s; oracle port of "
+                                           "generate_hr_volumes.create_super_volume (re-encodes per alpha like the "
+                                           "reference)" % (a.cpu_sample, a.cpu_sample * 54, cpu_t)}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--volumes", type=int, default=64, help="volumes per GPU per step")
+    ap.add_argument("--chunk", type=int, default=256, help="slices per kernel launch")
+    ap.add_argument("--groups", type=int, default=4, help="e2e: volume groups pipelined over copy/compute streams")
+    ap.add_argument("--cpu-sample", type=int, default=4, dest="cpu_sample")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

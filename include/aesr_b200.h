@@ -12,7 +12,8 @@
  *   - stream-ordered: work is enqueued on `stream` (a cudaStream_t passed as void*), nothing synchronises.
  *   - return value: 0 on success, negative error code otherwise; aesr_last_error() gives the message.
  *   - thread-compatible: no global mutable state besides the once-initialised driver entry point.
- *   - activations are NHWC bf16 internally; the public tensors (images, latents) are NCHW fp32.
+ *   - activations are NHWC 16-bit internally (dtype: AESR_DT_BF16 or AESR_DT_FP16, fp32 accumulation);
+ *     the public tensors (images, latents) are NCHW fp32.
  *   - no CPU fallback: aesr_init fails with AESR_ERR_ARCH unless the device is compute capability 10.x.
  */
 #ifndef AESR_B200_H
@@ -31,21 +32,30 @@ extern "C" {
 #define AESR_ERR_ARCH (-3)
 #define AESR_ERR_WORKSPACE (-4)
 
+/* 16-bit storage format of internal activations / packed filters */
+#define AESR_DT_BF16 0
+#define AESR_DT_FP16 1
+
 /* activation fused into the conv epilogue */
 #define AESR_ACT_NONE 0
 #define AESR_ACT_LEAKY 1 /* nn.LeakyReLU(slope)   networks/acai_vanilla.py:17,55-56 */
 #define AESR_ACT_RELU 2  /* nn.ReLU               lpips/pretrained_networks.py:107-116 (VGG16 features) */
 
 /* output stage fused into the conv epilogue */
-#define AESR_OUT_SAME 0          /* NHWC bf16 [N,H,W,Cout] */
+#define AESR_OUT_SAME 0          /* NHWC 16-bit [N,H,W,Cout] */
 #define AESR_OUT_AVGPOOL2 1      /* nn.AvgPool2d(2) (floor)            networks/acai_vanilla.py:59  */
 #define AESR_OUT_UP2 2           /* nn.Upsample(scale_factor=2) nearest networks/acai_vanilla.py:92  */
-#define AESR_OUT_NCHW_F32 3      /* public latent: NCHW fp32 (+ optional NHWC bf16 copy in out2) */
+#define AESR_OUT_NCHW_F32 3      /* public latent: NCHW fp32 (+ optional NHWC 16-bit copy in out2) */
 #define AESR_OUT_SAME_MAXPOOL2 4 /* full-res tap + nn.MaxPool2d(2) in out2  (VGG16 slices) */
 
 #define AESR_MUL_NONE 0
 #define AESR_MUL_LEAKY_GRAD 1 /* dgrad epilogue: multiply by LeakyReLU'(mul_src) */
 #define AESR_MUL_RELU_GRAD 2  /* dgrad epilogue: multiply by ReLU'(mul_src) */
+
+/* conv kernel selection (aesr_conv3x3_fwd `algo`): AUTO picks HALO whenever the filter bank fits in shared memory */
+#define AESR_ALGO_AUTO 0
+#define AESR_ALGO_HALO 1   /* one TMA halo load per tile, nine row-shifted UMMA descriptors, resident filters */
+#define AESR_ALGO_STREAM 2 /* one (A, B) TMA pair per filter tap */
 
 /* Select device, verify compute capability 10.x, resolve cuTensorMapEncodeTiled.  Idempotent. */
 int aesr_init(int device);
@@ -54,42 +64,50 @@ int aesr_sm_count(void);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 int64_t aesr_launch_count(void);
 
-/* fp32 [Cout,Cin,3,3] (nn.Conv2d.weight layout) -> bf16 [9][Cout][Cin] (forward) or, with transpose_flip != 0,
- * bf16 [9 (taps mirrored)][Cin][Cout] (the data-gradient conv).  Replaces cuDNN's internal filter transforms. */
-int aesr_pack_conv3x3_weight(const float* w, void* packed_bf16, int Cout, int Cin, int transpose_flip, void* stream);
+/* fp32 [Cout,Cin,3,3] (nn.Conv2d.weight layout) -> 16-bit [9][Cout][Cin] (forward) or, with transpose_flip != 0,
+ * [9 (taps mirrored)][Cin][Cout] (the data-gradient conv).  Replaces cuDNN's internal filter transforms. */
+int aesr_pack_conv3x3_weight(const float* w, void* packed, int Cout, int Cin, int transpose_flip, int dtype,
+                             void* stream);
 
 /* 3x3 / pad 1 / stride 1 convolution, implicit GEMM on tcgen05 tensor cores with TMA operand loads.
  * Replaces nn.Conv2d(k,k,3,padding=1) + activation (+ eval BatchNorm2d affine) (+ AvgPool2d / Upsample) of
  * networks/acai_vanilla.py:55-59,68-70,87-92,96 and the VGG16 convs of lpips/pretrained_networks.py:107-116.
- *   x        NHWC bf16 [N,H,W,Cin],  Cin  in {32,64,128,256,512}
- *   w_packed bf16 [9][Cout][Cin],    Cout multiple of 32
+ *   x        NHWC 16-bit [N,H,W,Cin],  Cin  in {32,64,128,256,512}
+ *   w_packed 16-bit [9][Cout][Cin],    Cout multiple of 32
  *   y = act(conv(x) + bias) [* act'(mul_src)] ; stats += {sum y, sum y^2} per channel ; y = y*scale + shift ; out stage
  *   bias/scale/shift/out2/mul_src/stats may be NULL. */
 int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, const float* scale, const float* shift,
                      void* out, void* out2, const void* mul_src, float* stats, int N, int H, int W, int Cin, int Cout,
-                     int act, float slope, int out_mode, int mul_mode, void* stream);
+                     int act, float slope, int out_mode, int mul_mode, int dtype, int algo, void* stream);
 
-/* enc.0: nn.Conv2d(1, C, 1, padding=1) (networks/acai_vanilla.py:51).  x fp32 [N,1,H,W] -> NHWC bf16 [N,H+2,W+2,C]. */
-int aesr_e0_fwd(const float* x, const float* w, const float* b, void* out, int N, int H, int W, int C, void* stream);
+/* enc.0: nn.Conv2d(1, C, 1, padding=1) (networks/acai_vanilla.py:51).  x fp32 [N,1,H,W] -> NHWC 16-bit [N,H+2,W+2,C]. */
+int aesr_e0_fwd(const float* x, const float* w, const float* b, void* out, int N, int H, int W, int C, int dtype,
+                void* stream);
 
 /* dec.14/15: nn.Conv2d(C, 1, 3, padding=1) + nn.Sigmoid (networks/acai_vanilla.py:98) + clamp(0,1)
- * (generate_hr_volumes.py:67).  in NHWC bf16 [N,H,W,C] (C = 32), w9c fp32 [9][C]; image n is written at
+ * (generate_hr_volumes.py:67).  in NHWC 16-bit [N,H,W,C] (C = 32), w9c fp32 [9][C]; image n is written at
  * out + (out_index ? out_index[n] : n) * out_image_stride (floats), so synthesized slices land directly at their
  * position i*(A+1)+1+k inside the HR volume (generate_hr_volumes.py:58-60) without a concat pass. */
 int aesr_head_fwd(const void* in, const float* w9c, float bias, float* out, const int* out_index, int N, int H, int W,
-                  int C, size_t out_image_stride, int apply_sigmoid, void* stream);
+                  int C, size_t out_image_stride, int apply_sigmoid, int dtype, void* stream);
 
 /* Latent interpolation (generate_hr_volumes.py:88, kwatsch/cardiac/trainer_ae.py:173,
- * kwatsch/brain/trainer_ae.py:265-266) fused with the NCHW fp32 -> NHWC bf16 layout change:
+ * kwatsch/brain/trainer_ae.py:265-266) fused with the NCHW fp32 -> NHWC 16-bit layout change:
  *   out[m] = wa[m] * z[ia[m]] + wb[m] * z[ib[m]]  (three separately rounded fp32 ops; ib[m] < 0: plain copy)
- *   z fp32 [*,C,HW]; ia/ib int32 [M]; wa/wb fp32 [M]; out_nhwc bf16 [M,HW,C]; out_nchw fp32 [M,C,HW] or NULL. */
+ *   z fp32 [*,C,HW]; ia/ib int32 [M]; wa/wb fp32 [M]; out_nhwc 16-bit [M,HW,C]; out_nchw fp32 [M,C,HW] or NULL. */
 int aesr_lerp_latents(const float* z, const int* ia, const int* ib, const float* wa, const float* wb, void* out_nhwc,
-                      float* out_nchw, int M, int C, int HW, void* stream);
+                      float* out_nchw, int M, int C, int HW, int dtype, void* stream);
 
 /* Kept (non-synthesized) slices of the HR volume: dst[out_index[n]] = clamp(src[n], 0, 1)
  * (generate_hr_volumes.py:44,58-67: `recon_volume = images`, the torch.cat chain, the final torch.clamp).
  * src fp32 [N,HW], dst fp32 [*,HW], out_index int32 [N] or NULL (identity).  N <= 65535 per call. */
 int aesr_place_slices(const float* src, float* dst, const int* out_index, int N, int HW, int do_clamp, void* stream);
+
+/* DIAGNOSTIC (not on the product path): one 16x8 tile of a 64->64 bf16 conv computed from a single TMA halo load with
+ * row-shifted UMMA descriptors; used by tools/gpu_diag.py to establish what the hardware's swizzle addressing does.
+ * out fp32 [128][64] raw accumulators. */
+int aesr_probe_halo_conv(const void* x, const void* w_packed, float* out, int N, int H, int W, int x0, int y0, int n,
+                         int pitch, int variant, void* stream);
 
 #ifdef __cplusplus
 }

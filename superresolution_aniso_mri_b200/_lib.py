@@ -14,26 +14,25 @@ LIB_PATH = os.path.join(_HERE, "lib", "libaesr_b200.so")
 
 _lib = None
 _initialised_devices = set()
+P, I, F = c_void_p, c_int, c_float
 
 _SIGNATURES = {
-    "aesr_init": (c_int, [c_int]),
+    "aesr_init": (I, [I]),
     "aesr_last_error": (c_char_p, []),
-    "aesr_sm_count": (c_int, []),
+    "aesr_sm_count": (I, []),
     "aesr_launch_count": (c_int64, []),
-    "aesr_pack_conv3x3_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "aesr_conv3x3_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p]),
-    "aesr_e0_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "aesr_head_fwd": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_size_t,
-                              c_int, c_void_p]),
-    "aesr_place_slices": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
-    "aesr_lerp_latents": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                  c_int, c_void_p]),
+    "aesr_pack_conv3x3_weight": (I, [P, P, I, I, I, I, P]),
+    "aesr_conv3x3_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, F, I, I, I, I, P]),
+    "aesr_e0_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
+    "aesr_head_fwd": (I, [P, P, F, P, P, I, I, I, I, c_size_t, I, I, P]),
+    "aesr_lerp_latents": (I, [P, P, P, P, P, P, P, I, I, I, I, P]),
+    "aesr_place_slices": (I, [P, P, P, I, I, I, P]),
+    "aesr_probe_halo_conv": (I, [P, P, P, I, I, I, I, I, I, I, I, P]),
 }
 
 
 def exported_symbols():
-    """Names every entry point include/aesr_b200.h declares (used by the symbol-export test)."""
+    """Names of every entry point include/aesr_b200.h declares (checked by tests/test_cabi.py)."""
     return sorted(_SIGNATURES)
 
 

@@ -9,6 +9,7 @@
 #include "../../include/aesr_b200.h"
 #include "conv3x3_tc.cuh"
 #include "elementwise.cuh"
+#include "probe.cuh"
 
 using namespace aesr;
 
@@ -34,9 +35,9 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-#define CUDA_TRY(expr)                                                                         \
-    do {                                                                                       \
-        cudaError_t _e = (expr);                                                               \
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
         if (_e != cudaSuccess) return fail(AESR_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
     } while (0)
 
@@ -55,7 +56,8 @@ void do_init(int device) {
         return;
     }
     if (prop.major != 10) {
-        g_init_status = fail(AESR_ERR_ARCH, "aesr_b200 needs a compute-capability 10.x (B200, sm_100a) device, got %d.%d (%s); "
+        g_init_status = fail(AESR_ERR_ARCH,
+                             "aesr_b200 needs a compute-capability 10.x (B200, sm_100a) device, got %d.%d (%s); "
                              "there is no fallback path", prop.major, prop.minor, prop.name);
         return;
     }
@@ -81,11 +83,12 @@ int ensure_init() {
     return AESR_OK;
 }
 
-// NHWC bf16 activation [N,H,W,C] viewed as a 4-D tensor {C, W, H, N}; box = {KC, 8, 16, 1}.
-int make_act_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int KC) {
+// NHWC 16-bit activation [N,H,W,C] viewed as a 4-D tensor {C, W, H, N}; box = {KC, box_w, box_h, 1}.
+// (bf16 and fp16 are both plain 2-byte copies for TMA; out-of-bounds elements are zero-filled.)
+int make_act_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int KC, int box_w, int box_h) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)KC, CONV_TILE_W, CONV_TILE_H, 1};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -95,7 +98,7 @@ int make_act_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, i
     return AESR_OK;
 }
 
-// packed weights bf16 [9*Cout rows][Cin]; box = {KC, BN}.
+// packed weights 16-bit [9*Cout rows][Cin]; box = {KC, BN}.
 int make_wgt_tmap(CUtensorMap* m, const void* ptr, int rows, int Cin, int KC, int BN) {
     cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
@@ -109,39 +112,92 @@ int make_wgt_tmap(CUtensorMap* m, const void* ptr, int rows, int Cin, int KC, in
     return AESR_OK;
 }
 
-__global__ void pack_conv3x3_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
-                                           int Cin, int transpose_flip) {
+template <bool FP16>
+__global__ void pack_conv3x3_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cout, int Cin,
+                                           int transpose_flip) {
     const int total = 9 * Cout * Cin;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        // destination index: [tap][row][col]
-        int tap, row, col;
+        int tap, row, col;     // destination index: [tap][row][col]
+        float v;
         if (!transpose_flip) {
             col = i % Cin; row = (i / Cin) % Cout; tap = i / (Cin * Cout);
-            out[i] = __float2bfloat16_rn(w[(static_cast<size_t>(row) * Cin + col) * 9 + tap]);
+            v = w[(static_cast<size_t>(row) * Cin + col) * 9 + tap];
         } else {
             // dgrad: dX = conv(dY, W') with W'[tap][ci][co] = W[co][ci][8 - tap]
             col = i % Cout; row = (i / Cout) % Cin; tap = i / (Cin * Cout);
-            out[i] = __float2bfloat16_rn(w[(static_cast<size_t>(col) * Cin + row) * 9 + (8 - tap)]);
+            v = w[(static_cast<size_t>(col) * Cin + row) * 9 + (8 - tap)];
         }
+        out[i] = cvt16_t<FP16>(v);
     }
 }
 
+template <typename K>
+int set_max_smem(K kernel, int* configured) {
+    if (!*configured) {
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem_optin));
+        *configured = 1;
+    }
+    return AESR_OK;
+}
+
 template <int KC>
-int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
-    using S = ConvSmem<KC>;
+int launch_stream(const void* x, const void* w, ConvParams p, cudaStream_t stream) {
+    using S = StreamSmem<KC>;
+    p.BN = p.Cout <= 256 ? p.Cout : 256;
+    if (p.Cout % p.BN != 0) return fail(AESR_ERR_INVALID, "conv3x3_fwd: Cout=%d not a multiple of %d", p.Cout, p.BN);
+    p.n_blocks = p.Cout / p.BN;
+    p.num_tiles = p.N * p.tiles_x * p.tiles_y * p.n_blocks;
     int stages = CONV_MAX_STAGES;
     while (stages > 2 && S::total_bytes(p.BN, stages) > g_max_smem_optin) --stages;
-    ConvParams q = p;
-    q.num_stages = stages;
-    const int smem = S::total_bytes(p.BN, stages);
-    static int configured_smem = 0;
-    if (smem > configured_smem) {
-        CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem_optin));
-        configured_smem = g_max_smem_optin;
-    }
+    p.num_stages = stages;
+    CUtensorMap tx, tw;
+    int rc = make_act_tmap(&tx, x, p.N, p.H, p.W, p.Cin, KC, CONV_TILE_W, CONV_TILE_H);
+    if (rc != AESR_OK) return rc;
+    rc = make_wgt_tmap(&tw, w, 9 * p.Cout, p.Cin, KC, p.BN);
+    if (rc != AESR_OK) return rc;
+    static int configured = 0;
+    rc = set_max_smem(conv3x3_stream_kernel<KC>, &configured);
+    if (rc != AESR_OK) return rc;
     const int grid = p.num_tiles < g_sm_count ? p.num_tiles : g_sm_count;
-    conv3x3_tc_kernel<KC><<<grid, CONV_THREADS, smem, stream>>>(tx, tw, q);
-    return check_launch("conv3x3_tc");
+    conv3x3_stream_kernel<KC><<<grid, CONV_THREADS, S::total_bytes(p.BN, stages), stream>>>(tx, tw, p);
+    return check_launch("conv3x3_stream");
+}
+
+// largest N tile (multiple of 32 dividing Cout, <= 256) whose resident filter bank + >= 2 halo stages fit; 0 = none
+template <int KC>
+int halo_pick_bn(int Cin, int Cout) {
+    using S = HaloSmem<KC>;
+    for (int bn = Cout <= 256 ? Cout : 256; bn >= 32; bn -= 32) {
+        if (Cout % bn != 0) continue;
+        if (S::total_bytes(bn, Cin, 2) <= g_max_smem_optin) return bn;
+    }
+    return 0;
+}
+
+template <int KC>
+int launch_halo(const void* x, const void* w, ConvParams p, cudaStream_t stream) {
+    using S = HaloSmem<KC>;
+    p.BN = halo_pick_bn<KC>(p.Cin, p.Cout);
+    if (p.BN == 0) return fail(AESR_ERR_INVALID, "conv3x3_fwd: filter bank %dx%d does not fit the halo kernel", p.Cout, p.Cin);
+    p.n_blocks = p.Cout / p.BN;
+    const int sp_tiles = p.N * p.tiles_x * p.tiles_y;
+    p.num_tiles = sp_tiles * p.n_blocks;
+    int stages = CONV_MAX_STAGES;
+    while (stages > 2 && S::total_bytes(p.BN, p.Cin, stages) > g_max_smem_optin) --stages;
+    p.num_stages = stages;
+    CUtensorMap tx, tw;
+    int rc = make_act_tmap(&tx, x, p.N, p.H, p.W, p.Cin, KC, HALO_W, HALO_H);
+    if (rc != AESR_OK) return rc;
+    rc = make_wgt_tmap(&tw, w, 9 * p.Cout, p.Cin, KC, p.BN);
+    if (rc != AESR_OK) return rc;
+    static int configured = 0;
+    rc = set_max_smem(conv3x3_halo_kernel<KC>, &configured);
+    if (rc != AESR_OK) return rc;
+    int per_nb = g_sm_count / p.n_blocks;
+    if (per_nb < 1) per_nb = 1;
+    if (per_nb > sp_tiles) per_nb = sp_tiles;
+    conv3x3_halo_kernel<KC><<<per_nb * p.n_blocks, CONV_THREADS, S::total_bytes(p.BN, p.Cin, stages), stream>>>(tx, tw, p);
+    return check_launch("conv3x3_halo");
 }
 
 }  // namespace
@@ -160,17 +216,21 @@ const char* aesr_last_error(void) { return g_err; }
 int aesr_sm_count(void) { return g_sm_count; }
 int64_t aesr_launch_count(void) { return g_launches.load(); }
 
-int aesr_pack_conv3x3_weight(const float* w, void* packed, int Cout, int Cin, int transpose_flip, void* stream) {
+int aesr_pack_conv3x3_weight(const float* w, void* packed, int Cout, int Cin, int transpose_flip, int dtype,
+                             void* stream) {
     if (!w || !packed || Cout <= 0 || Cin <= 0) return fail(AESR_ERR_INVALID, "pack_conv3x3_weight: bad arguments");
     const int total = 9 * Cout * Cin;
-    pack_conv3x3_weight_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        w, static_cast<__nv_bfloat16*>(packed), Cout, Cin, transpose_flip);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == AESR_DT_FP16)
+        pack_conv3x3_weight_kernel<true><<<(total + 255) / 256, 256, 0, s>>>(w, static_cast<uint16_t*>(packed), Cout, Cin, transpose_flip);
+    else
+        pack_conv3x3_weight_kernel<false><<<(total + 255) / 256, 256, 0, s>>>(w, static_cast<uint16_t*>(packed), Cout, Cin, transpose_flip);
     return check_launch("pack_conv3x3_weight");
 }
 
 int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, const float* scale, const float* shift,
                      void* out, void* out2, const void* mul_src, float* stats, int N, int H, int W, int Cin, int Cout,
-                     int act, float slope, int out_mode, int mul_mode, void* stream) {
+                     int act, float slope, int out_mode, int mul_mode, int dtype, int algo, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!x || !w_packed || !out) return fail(AESR_ERR_INVALID, "conv3x3_fwd: null tensor");
@@ -182,32 +242,34 @@ int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, con
     if (out_mode < 0 || out_mode > 4) return fail(AESR_ERR_INVALID, "conv3x3_fwd: out_mode=%d", out_mode);
     if (out_mode == AESR_OUT_SAME_MAXPOOL2 && !out2) return fail(AESR_ERR_INVALID, "conv3x3_fwd: maxpool needs out2");
     if (mul_mode != AESR_MUL_NONE && !mul_src) return fail(AESR_ERR_INVALID, "conv3x3_fwd: mul_mode without mul_src");
+    if (dtype != AESR_DT_BF16 && dtype != AESR_DT_FP16) return fail(AESR_ERR_INVALID, "conv3x3_fwd: dtype=%d", dtype);
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(out)) & 15)
         return fail(AESR_ERR_INVALID, "conv3x3_fwd: tensors must be 16-byte aligned");
 
     ConvParams p{};
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-    p.BN = Cout <= 256 ? Cout : 256;
-    if (Cout % p.BN != 0) return fail(AESR_ERR_INVALID, "conv3x3_fwd: Cout=%d not a multiple of the N tile %d", Cout, p.BN);
     p.tiles_x = (W + CONV_TILE_W - 1) / CONV_TILE_W;
     p.tiles_y = (H + CONV_TILE_H - 1) / CONV_TILE_H;
-    p.n_blocks = Cout / p.BN;
-    p.num_tiles = N * p.tiles_x * p.tiles_y * p.n_blocks;
+    p.fp16 = (dtype == AESR_DT_FP16);
     p.bias = bias; p.scale = scale; p.shift = shift; p.slope = slope; p.act = act; p.out_mode = out_mode;
-    p.out = out; p.out2 = out2; p.mul_src = static_cast<const __nv_bfloat16*>(mul_src); p.mul_mode = mul_mode;
+    p.out = out; p.out2 = out2; p.mul_src = static_cast<const uint16_t*>(mul_src); p.mul_mode = mul_mode;
     p.stats = stats;
 
-    const int KC = (Cin >= 64) ? 64 : 32;
-    CUtensorMap tx, tw;
-    rc = make_act_tmap(&tx, x, N, H, W, Cin, KC);
-    if (rc != AESR_OK) return rc;
-    rc = make_wgt_tmap(&tw, w_packed, 9 * Cout, Cin, KC, p.BN);
-    if (rc != AESR_OK) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    return KC == 64 ? launch_conv<64>(tx, tw, p, s) : launch_conv<32>(tx, tw, p, s);
+    const int KC = (Cin >= 64) ? 64 : 32;
+    bool halo = false;
+    if (algo != AESR_ALGO_STREAM) {
+        const int bn = (KC == 64) ? halo_pick_bn<64>(Cin, Cout) : halo_pick_bn<32>(Cin, Cout);
+        halo = bn > 0;
+        if (!halo && algo == AESR_ALGO_HALO)
+            return fail(AESR_ERR_INVALID, "conv3x3_fwd: filter bank %dx%d too large for AESR_ALGO_HALO", Cout, Cin);
+    }
+    if (halo) return KC == 64 ? launch_halo<64>(x, w_packed, p, s) : launch_halo<32>(x, w_packed, p, s);
+    return KC == 64 ? launch_stream<64>(x, w_packed, p, s) : launch_stream<32>(x, w_packed, p, s);
 }
 
-int aesr_e0_fwd(const float* x, const float* w, const float* b, void* out, int N, int H, int W, int C, void* stream) {
+int aesr_e0_fwd(const float* x, const float* w, const float* b, void* out, int N, int H, int W, int C, int dtype,
+                void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!x || !w || !b || !out || N <= 0 || H <= 0 || W <= 0 || C % 8 != 0)
@@ -217,13 +279,16 @@ int aesr_e0_fwd(const float* x, const float* w, const float* b, void* out, int N
     size_t grid = (total + block - 1) / block;
     const size_t cap = static_cast<size_t>(g_sm_count) * 16;
     if (grid > cap) grid = cap;
-    e0_conv1x1_pad1_kernel<<<static_cast<int>(grid), block, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, w, b, static_cast<__nv_bfloat16*>(out), N, H, W, C);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == AESR_DT_FP16)
+        e0_conv1x1_pad1_kernel<true><<<static_cast<int>(grid), block, 0, s>>>(x, w, b, static_cast<uint16_t*>(out), N, H, W, C);
+    else
+        e0_conv1x1_pad1_kernel<false><<<static_cast<int>(grid), block, 0, s>>>(x, w, b, static_cast<uint16_t*>(out), N, H, W, C);
     return check_launch("e0_conv1x1_pad1");
 }
 
 int aesr_head_fwd(const void* in, const float* w9c, float bias, float* out, const int* out_index, int N, int H, int W,
-                  int C, size_t out_image_stride, int apply_sigmoid, void* stream) {
+                  int C, size_t out_image_stride, int apply_sigmoid, int dtype, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!in || !w9c || !out || N <= 0 || H <= 0 || W <= 0) return fail(AESR_ERR_INVALID, "head_fwd: bad arguments");
@@ -233,21 +298,28 @@ int aesr_head_fwd(const void* in, const float* w9c, float bias, float* out, cons
     size_t grid = (total + block - 1) / block;
     const size_t cap = static_cast<size_t>(g_sm_count) * 32;
     if (grid > cap) grid = cap;
-    head_conv3x3_sigmoid_kernel<32><<<static_cast<int>(grid), block, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(in), w9c, bias, out, out_index, N, H, W, out_image_stride, apply_sigmoid);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint16_t* in16 = static_cast<const uint16_t*>(in);
+    if (dtype == AESR_DT_FP16)
+        head_conv3x3_sigmoid_kernel<32, true><<<static_cast<int>(grid), block, 0, s>>>(in16, w9c, bias, out, out_index, N, H, W, out_image_stride, apply_sigmoid);
+    else
+        head_conv3x3_sigmoid_kernel<32, false><<<static_cast<int>(grid), block, 0, s>>>(in16, w9c, bias, out, out_index, N, H, W, out_image_stride, apply_sigmoid);
     return check_launch("head_conv3x3_sigmoid");
 }
 
 int aesr_lerp_latents(const float* z, const int* ia, const int* ib, const float* wa, const float* wb, void* out_nhwc,
-                      float* out_nchw, int M, int C, int HW, void* stream) {
+                      float* out_nchw, int M, int C, int HW, int dtype, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!z || !ia || !ib || !wa || !wb || !out_nhwc || C <= 0 || HW <= 0) return fail(AESR_ERR_INVALID, "lerp_latents: bad arguments");
     if (M == 0) return AESR_OK;
     if (M < 0 || M > 65535) return fail(AESR_ERR_INVALID, "lerp_latents: M=%d out of range (1..65535 per call)", M);
     dim3 grid((HW + 31) / 32, (C + 31) / 32, M), block(32, 8);
-    lerp_nchw_to_nhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-        z, ia, ib, wa, wb, static_cast<__nv_bfloat16*>(out_nhwc), out_nchw, C, HW);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == AESR_DT_FP16)
+        lerp_nchw_to_nhwc_kernel<true><<<grid, block, 0, s>>>(z, ia, ib, wa, wb, static_cast<uint16_t*>(out_nhwc), out_nchw, C, HW);
+    else
+        lerp_nchw_to_nhwc_kernel<false><<<grid, block, 0, s>>>(z, ia, ib, wa, wb, static_cast<uint16_t*>(out_nhwc), out_nchw, C, HW);
     return check_launch("lerp_nchw_to_nhwc");
 }
 
@@ -263,6 +335,22 @@ int aesr_place_slices(const float* src, float* dst, const int* out_index, int N,
     if (gx > 64) gx = 64;
     place_slices_kernel<<<dim3(gx, N), block, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, out_index, N, HW, do_clamp);
     return check_launch("place_slices");
+}
+
+int aesr_probe_halo_conv(const void* x, const void* w_packed, float* out, int N, int H, int W, int x0, int y0, int n,
+                         int pitch, int variant, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (pitch != 10 && pitch != 16) return fail(AESR_ERR_INVALID, "probe: pitch must be 10 or 16");
+    CUtensorMap tx, tw;
+    rc = make_act_tmap(&tx, x, N, H, W, 64, 64, pitch, 18);
+    if (rc != AESR_OK) return rc;
+    rc = make_wgt_tmap(&tw, w_packed, 9 * 64, 64, 64, 64);
+    if (rc != AESR_OK) return rc;
+    const int smem = 1024 + 36864 + 73728 + 64;
+    CUDA_TRY(cudaFuncSetAttribute(halo_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    halo_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(tx, tw, out, x0, y0, n, pitch, variant);
+    return check_launch("halo_probe");
 }
 
 }  // extern "C"

@@ -137,6 +137,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
            ((M >> 4) << 24);
 }
 
+// 16-bit operands: fp16 (format 0) or bf16 (format 1), fp32 accumulate.
+__host__ __device__ constexpr uint32_t make_idesc_16(uint32_t M, uint32_t N, int fp16) {
+    const uint32_t fmt = fp16 ? 0u : 1u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------

@@ -1,20 +1,42 @@
 // Memory-bound kernels around the tensor-core convs: network head/tail convs with 1 input or 1 output channel
 // (CUDA cores, nothing for a tensor core to do there), latent interpolation + layout change, and the
 // image-domain utilities.  All coalesced / 16-byte vectorised; grids sized from the problem, no smem unless it buys
-// coalescing (the NCHW <-> NHWC transposes).
+// coalescing (the NCHW <-> NHWC transposes).  FP16 template flag = 16-bit activation format (fp16 or bf16).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace aesr {
 
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack2_t(float lo, float hi) {
+    if (FP16) {
+        __half2 h = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+    return pack_bf16x2(lo, hi);
+}
+template <bool FP16>
+__device__ __forceinline__ float2 unpack2_t(uint32_t u) {
+    if (FP16) return __half22float2(*reinterpret_cast<__half2*>(&u));
+    return make_float2(bf16_lo(u), bf16_hi(u));
+}
+template <bool FP16>
+__device__ __forceinline__ uint16_t cvt16_t(float v) {
+    if (FP16) return __half_as_ushort(__float2half_rn(v));
+    return __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // enc.0 : Conv2d(1, C, kernel 1, padding 1)   (networks/acai_vanilla.py:51)
-// x fp32 [N,1,H,W]  ->  out bf16 NHWC [N,H+2,W+2,C];  out = w[c] * xpad + b[c]  (ring pixels = bias)
+// x fp32 [N,1,H,W]  ->  out 16-bit NHWC [N,H+2,W+2,C];  out = w[c] * xpad + b[c]  (ring pixels = bias)
 // one thread = one output pixel x 8 channels (one 16-byte store)
 // ---------------------------------------------------------------------------------------------------------------
+template <bool FP16>
 __global__ void e0_conv1x1_pad1_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                       const float* __restrict__ b, __nv_bfloat16* __restrict__ out, int N, int H,
-                                       int W, int C) {
+                                       const float* __restrict__ b, uint16_t* __restrict__ out, int N, int H, int W,
+                                       int C) {
     const int Ho = H + 2, Wo = W + 2;
     const int groups = C >> 3;
     const size_t total = static_cast<size_t>(N) * Ho * Wo * groups;
@@ -31,19 +53,19 @@ __global__ void e0_conv1x1_pad1_kernel(const float* __restrict__ x, const float*
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = fmaf(__ldg(w + g * 8 + j), xv, __ldg(b + g * 8 + j));
-        reinterpret_cast<uint4*>(out)[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(pack2_t<FP16>(v[0], v[1]), pack2_t<FP16>(v[2], v[3]),
+                                                      pack2_t<FP16>(v[4], v[5]), pack2_t<FP16>(v[6], v[7]));
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // dec.14 + dec.15 : Conv2d(C, 1, 3, padding 1) + Sigmoid  (networks/acai_vanilla.py:98), C = 32
-// in bf16 NHWC [N,H,W,32] -> out fp32 [N,1,H,W] (clamped to [0,1] like generate_hr_volumes.py:67; a no-op after
-// the sigmoid).  Optionally also writes the pre-sigmoid logit (training backward).
+// in 16-bit NHWC [N,H,W,32] -> out fp32 image n at out + slot(n) * stride, clamped to [0,1] like
+// generate_hr_volumes.py:67 (a no-op after the sigmoid).  apply_sigmoid = 0 writes the raw logit.
 // One thread per output pixel; the 3x3x32 filter sits in shared memory as fp32.
 // ---------------------------------------------------------------------------------------------------------------
-template <int C>
-__global__ void head_conv3x3_sigmoid_kernel(const __nv_bfloat16* __restrict__ in, const float* __restrict__ w /*[9][C]*/,
+template <int C, bool FP16>
+__global__ void head_conv3x3_sigmoid_kernel(const uint16_t* __restrict__ in, const float* __restrict__ w /*[9][C]*/,
                                             float bias, float* __restrict__ out, const int* __restrict__ out_index,
                                             int N, int H, int W, size_t out_image_stride, int apply_sigmoid) {
     __shared__ float sw[9 * C];
@@ -73,8 +95,9 @@ __global__ void head_conv3x3_sigmoid_kernel(const __nv_bfloat16* __restrict__ in
                     const uint32_t u[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        acc = fmaf(bf16_lo(u[k]), wt[j4 * 8 + k * 2], acc);
-                        acc = fmaf(bf16_hi(u[k]), wt[j4 * 8 + k * 2 + 1], acc);
+                        const float2 f = unpack2_t<FP16>(u[k]);
+                        acc = fmaf(f.x, wt[j4 * 8 + k * 2], acc);
+                        acc = fmaf(f.y, wt[j4 * 8 + k * 2 + 1], acc);
                     }
                 }
             }
@@ -92,14 +115,15 @@ __global__ void head_conv3x3_sigmoid_kernel(const __nv_bfloat16* __restrict__ in
 // ---------------------------------------------------------------------------------------------------------------
 // latent interpolation + layout change
 //   z    fp32 NCHW [*, C, HW]  (public latent layout)
-//   out  bf16 NHWC [M, HW, C]  (decoder input), optionally also fp32 NCHW [M, C, HW] (the public z_mix)
+//   out  16-bit NHWC [M, HW, C]  (decoder input), optionally also fp32 NCHW [M, C, HW] (the public z_mix)
 //   out[m] = wa[m] * z[ia[m]] + wb[m] * z[ib[m]]   -- three separately rounded fp32 ops (mul, mul, add), exactly
 //   what `alpha * latent_1 + (1 - alpha) * latent_2` does in torch (generate_hr_volumes.py:88); ib[m] < 0 => copy.
 // 32 pixels x 32 channels per block through a padded smem tile: reads coalesced along pixels, writes along channels.
 // ---------------------------------------------------------------------------------------------------------------
+template <bool FP16>
 __global__ void lerp_nchw_to_nhwc_kernel(const float* __restrict__ z, const int* __restrict__ ia,
                                          const int* __restrict__ ib, const float* __restrict__ wa,
-                                         const float* __restrict__ wb, __nv_bfloat16* __restrict__ out_nhwc,
+                                         const float* __restrict__ wb, uint16_t* __restrict__ out_nhwc,
                                          float* __restrict__ out_nchw, int C, int HW) {
     __shared__ float tile[32][33];
     const int m = blockIdx.z;
@@ -123,13 +147,9 @@ __global__ void lerp_nchw_to_nhwc_kernel(const float* __restrict__ z, const int*
     for (int py = threadIdx.y; py < 32; py += blockDim.y) {
         const int p = p0 + py, c = c0 + threadIdx.x;
         if (p < HW && c < C)
-            out_nhwc[(static_cast<size_t>(m) * HW + p) * C + c] = __float2bfloat16_rn(tile[threadIdx.x][py]);
+            out_nhwc[(static_cast<size_t>(m) * HW + p) * C + c] = cvt16_t<FP16>(tile[threadIdx.x][py]);
     }
 }
-
-}  // namespace aesr
-
-namespace aesr {
 
 // ---------------------------------------------------------------------------------------------------------------
 // kept (original) slices of the HR volume: dst[out_index[n]] = clamp(src[n], 0, 1)   (generate_hr_volumes.py:44,58-67)

@@ -1,0 +1,69 @@
+// Hardware probe (diagnostic entry point, not on the product path): does a tcgen05 shared-memory descriptor whose
+// start address is shifted by whole 128-byte rows inside a TMA-written, 128B-swizzled halo tile address the right
+// data?  If yes, one halo load per tile can feed all 9 filter taps (no 9x re-fetch of the activation window).
+//
+// One CTA, one tile: Cin = 64, Cout = 64, 16x8 output pixels.  Halo tile = 18 rows x `pitch` pixels x 128 B.
+//   variant bit 0: set the descriptor's base-offset field to (start_address >> 7) & 7
+//   pitch = 10 (dense TMA box {64,10,18,1}) or 16 (box {64,16,18,1}: 8-row groups 1024-byte aligned)
+#pragma once
+#include "common.cuh"
+
+namespace aesr {
+
+__global__ void __launch_bounds__(128, 1)
+halo_probe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                  float* __restrict__ out /*[128][64]*/, int x0, int y0, int n, int pitch, int variant) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a_halo = smem;                       // 18 * 16 * 128 = 36864 B max
+    uint8_t* b_all = smem + 36864;                // 9 * 64 * 128 = 73728 B
+    uint64_t* bar = reinterpret_cast<uint64_t*>(b_all + 73728);
+    uint64_t* done_bar = bar + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_ptr, 64);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bar, 18 * pitch * 128 + 9 * 64 * 128);
+        tma_load_4d(a_halo, &tmap_x, bar, 0, x0 - 1, y0 - 1, n);
+        for (int tap = 0; tap < 9; ++tap) tma_load_2d(b_all + tap * 8192, &tmap_w, bar, 0, tap * 64);
+        mbar_wait(bar, 0);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc_bf16(128, 64);
+        for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap % 3;
+            const uint32_t a_addr = smem_u32(a_halo) + (dy * pitch + dx) * 128;
+            uint64_t a_desc = make_smem_desc(a_addr, pitch * 128, UMMA_LAYOUT_SW128);
+            if (variant & 1) a_desc |= static_cast<uint64_t>((a_addr >> 7) & 7) << 49;
+            const uint64_t b_desc = make_smem_desc(smem_u32(b_all + tap * 8192), 1024, UMMA_LAYOUT_SW128);
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (tap | k) != 0);
+        }
+        umma_commit(done_bar);
+    }
+    __syncwarp();
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, raw);
+        tmem_ld_wait();
+        for (int j = 0; j < 32; ++j) out[row * 64 + c0 + j] = __uint_as_float(raw[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 64);
+    }
+}
+
+}  // namespace aesr

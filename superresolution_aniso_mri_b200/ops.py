@@ -4,6 +4,7 @@ PyTorch is plumbing here: it owns the device memory and the stream; all arithmet
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -13,7 +14,45 @@ from . import _lib
 ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
 OUT_SAME, OUT_AVGPOOL2, OUT_UP2, OUT_NCHW_F32, OUT_SAME_MAXPOOL2 = 0, 1, 2, 3, 4
 MUL_NONE, MUL_LEAKY_GRAD, MUL_RELU_GRAD = 0, 1, 2
+ALGO_AUTO, ALGO_HALO, ALGO_STREAM = 0, 1, 2
+DT_BF16, DT_FP16 = 0, 1
 LEAKY_SLOPE = 0.01
+
+# 16-bit storage format of internal activations / packed filters.  fp16 (10-bit mantissa, fp32 accumulate) is the
+# default for inference: 8x smaller rounding error than bf16 at the same tensor-core rate; BatchNorm keeps activations
+# far inside the fp16 range.  AESR_ACT_DTYPE=bf16 switches globally.
+DEFAULT_DTYPE = torch.bfloat16 if os.environ.get("AESR_ACT_DTYPE", "fp16").lower() == "bf16" else torch.float16
+
+
+# Per-launch device timing for bench.py's roofline pass: when a list, every wrapper appends
+# (kernel family, start event, end event, algorithmic FLOPs).  None (default) = no events, no overhead.
+TIMING = None
+
+
+class _timed:
+    def __init__(self, name: str, flops: float = 0.0):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if TIMING is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if TIMING is not None:
+            self.e1.record()
+            TIMING.append((self.name, self.e0, self.e1, self.flops))
+        return False
+
+
+def dt_code(dtype: torch.dtype) -> int:
+    if dtype == torch.float16:
+        return DT_FP16
+    if dtype == torch.bfloat16:
+        return DT_BF16
+    raise RuntimeError("aesr_b200: internal activations are fp16 or bf16, got %s" % dtype)
 
 
 def _dev(t: torch.Tensor):
@@ -31,15 +70,17 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def pack_conv3x3_weight(w: torch.Tensor, transpose_flip: bool = False) -> torch.Tensor:
-    """fp32 [Cout,Cin,3,3] -> bf16 [9,Cout,Cin] (or [9,Cin,Cout] with mirrored taps for the data-gradient conv)."""
+def pack_conv3x3_weight(w: torch.Tensor, transpose_flip: bool = False, dtype: Optional[torch.dtype] = None
+                        ) -> torch.Tensor:
+    """fp32 [Cout,Cin,3,3] -> 16-bit [9,Cout,Cin] (or [9,Cin,Cout] with mirrored taps for the data-gradient conv)."""
     lib = _dev(w)
+    dtype = dtype or DEFAULT_DTYPE
     w = w.detach().contiguous().float()
     cout, cin = w.shape[0], w.shape[1]
     shape = (9, cin, cout) if transpose_flip else (9, cout, cin)
-    out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
-    _lib.check(lib.aesr_pack_conv3x3_weight(w.data_ptr(), out.data_ptr(), cout, cin, int(transpose_flip), _stream(w)),
-               "pack_conv3x3_weight")
+    out = torch.empty(shape, dtype=dtype, device=w.device)
+    _lib.check(lib.aesr_pack_conv3x3_weight(w.data_ptr(), out.data_ptr(), cout, cin, int(transpose_flip),
+                                            dt_code(dtype), _stream(w)), "pack_conv3x3_weight")
     return out
 
 
@@ -57,67 +98,75 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
             slope: float = LEAKY_SLOPE, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
             out_mode: int = OUT_SAME, out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
             want_out2: bool = False, mul_src: Optional[torch.Tensor] = None, mul_mode: int = MUL_NONE,
-            stats: Optional[torch.Tensor] = None):
-    """x NHWC bf16 [N,H,W,Cin]; w_packed bf16 [9,Cout,Cin].  Returns out (and out2 when the mode produces one)."""
+            stats: Optional[torch.Tensor] = None, algo: int = ALGO_AUTO):
+    """x NHWC 16-bit [N,H,W,Cin]; w_packed same dtype [9,Cout,Cin].  Returns out (and out2 when the mode has one)."""
     lib = _dev(x)
-    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.dim() == 4
+    assert x.is_contiguous() and x.dim() == 4 and x.dtype == w_packed.dtype
     n, h, w, cin = x.shape
     cout = w_packed.shape[1]
-    assert w_packed.shape == (9, cout, cin) and w_packed.dtype == torch.bfloat16 and w_packed.is_contiguous()
+    assert w_packed.shape == (9, cout, cin) and w_packed.is_contiguous()
     if out is None:
         out = torch.empty(conv_out_shape(n, h, w, cout, out_mode),
-                          dtype=torch.float32 if out_mode == OUT_NCHW_F32 else torch.bfloat16, device=x.device)
+                          dtype=torch.float32 if out_mode == OUT_NCHW_F32 else x.dtype, device=x.device)
     if out2 is None and (out_mode == OUT_SAME_MAXPOOL2 or (out_mode == OUT_NCHW_F32 and want_out2)):
         shp = (n, h // 2, w // 2, cout) if out_mode == OUT_SAME_MAXPOOL2 else (n, h, w, cout)
-        out2 = torch.empty(shp, dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.aesr_conv3x3_fwd(x.data_ptr(), w_packed.data_ptr(), _ptr(bias), _ptr(scale), _ptr(shift),
-                                    out.data_ptr(), _ptr(out2), _ptr(mul_src), _ptr(stats), n, h, w, cin, cout,
-                                    int(act), float(slope), int(out_mode), int(mul_mode), _stream(x)), "conv3x3_fwd")
+        out2 = torch.empty(shp, dtype=x.dtype, device=x.device)
+    with _timed("conv3x3", 2.0 * n * h * w * 9 * cin * cout):
+        _lib.check(lib.aesr_conv3x3_fwd(x.data_ptr(), w_packed.data_ptr(), _ptr(bias), _ptr(scale), _ptr(shift),
+                                        out.data_ptr(), _ptr(out2), _ptr(mul_src), _ptr(stats), n, h, w, cin, cout,
+                                        int(act), float(slope), int(out_mode), int(mul_mode), dt_code(x.dtype),
+                                        int(algo), _stream(x)), "conv3x3_fwd")
     return (out, out2) if out2 is not None else out
 
 
-def e0(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """enc.0: x fp32 [N,1,H,W] -> NHWC bf16 [N,H+2,W+2,C]."""
+def e0(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """enc.0: x fp32 [N,1,H,W] -> NHWC 16-bit [N,H+2,W+2,C]."""
     lib = _dev(x)
+    dtype = dtype or DEFAULT_DTYPE
     assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 1
     n, _, h, wd = x.shape
     c = w.numel()
-    out = torch.empty((n, h + 2, wd + 2, c), dtype=torch.bfloat16, device=x.device)
-    _lib.check(lib.aesr_e0_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, h, wd, c, _stream(x)),
-               "e0_fwd")
+    out = torch.empty((n, h + 2, wd + 2, c), dtype=dtype, device=x.device)
+    with _timed("e0", 2.0 * n * (h + 2) * (wd + 2) * c):
+        _lib.check(lib.aesr_e0_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, h, wd, c,
+                                   dt_code(dtype), _stream(x)), "e0_fwd")
     return out
 
 
 def head(a: torch.Tensor, w9c: torch.Tensor, bias: float, out: Optional[torch.Tensor] = None,
          out_image_stride: Optional[int] = None, sigmoid: bool = True,
          out_index: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dec.14 + sigmoid: NHWC bf16 [N,H,W,32] -> fp32 [N,1,H,W] (or image n -> out[out_index[n]])."""
+    """dec.14 + sigmoid: NHWC 16-bit [N,H,W,32] -> fp32 [N,1,H,W] (or image n -> out[out_index[n]])."""
     lib = _dev(a)
     n, h, w, c = a.shape
     if out is None:
         out = torch.empty((n, 1, h, w), dtype=torch.float32, device=a.device)
         out_image_stride = h * w
-    _lib.check(lib.aesr_head_fwd(a.data_ptr(), w9c.data_ptr(), float(bias), out.data_ptr(), _ptr(out_index), n, h, w, c,
-                                 int(out_image_stride), int(sigmoid), _stream(a)), "head_fwd")
+    with _timed("head", 2.0 * n * h * w * 9 * c):
+        _lib.check(lib.aesr_head_fwd(a.data_ptr(), w9c.data_ptr(), float(bias), out.data_ptr(), _ptr(out_index), n, h,
+                                     w, c, int(out_image_stride), int(sigmoid), dt_code(a.dtype), _stream(a)),
+                   "head_fwd")
     return out
 
 
 def lerp_latents(z: torch.Tensor, ia: torch.Tensor, ib: torch.Tensor, wa: torch.Tensor, wb: torch.Tensor,
-                 want_nchw: bool = False):
-    """out[m] = wa[m]*z[ia[m]] + wb[m]*z[ib[m]]; z fp32 NCHW -> NHWC bf16 [M,h,w,C] (+ fp32 NCHW z_mix)."""
+                 want_nchw: bool = False, dtype: Optional[torch.dtype] = None):
+    """out[m] = wa[m]*z[ia[m]] + wb[m]*z[ib[m]]; z fp32 NCHW -> NHWC 16-bit [M,h,w,C] (+ fp32 NCHW z_mix)."""
     lib = _dev(z)
+    dtype = dtype or DEFAULT_DTYPE
     assert z.dtype == torch.float32 and z.is_contiguous() and z.dim() == 4
     _, c, h, w = z.shape
     m = ia.numel()
-    out = torch.empty((m, h, w, c), dtype=torch.bfloat16, device=z.device)
+    out = torch.empty((m, h, w, c), dtype=dtype, device=z.device)
     out_nchw = torch.empty((m, c, h, w), dtype=torch.float32, device=z.device) if want_nchw else None
     done = 0
+    tm = _timed("lerp").__enter__()
     while done < m:                                  # gridDim.z limit
         cnt = min(m - done, 65535)
         _lib.check(lib.aesr_lerp_latents(z.data_ptr(), ia[done:].data_ptr(), ib[done:].data_ptr(),
                                          wa[done:].data_ptr(), wb[done:].data_ptr(), out[done:].data_ptr(),
-                                         _ptr(out_nchw[done:]) if want_nchw else None, cnt, c, h * w, _stream(z)),
-                   "lerp_latents")
+                                         out_nchw[done:].data_ptr() if want_nchw else None, cnt, c, h * w,
+                                         dt_code(dtype), _stream(z)), "lerp_latents")
         done += cnt
     return (out, out_nchw) if want_nchw else out
 

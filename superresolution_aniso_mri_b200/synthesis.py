@@ -95,6 +95,60 @@ def synthesize_volumes(model, volumes: torch.Tensor, alpha_range: Sequence[float
     return out
 
 
+class HostPipeline:
+    """Host-buffer entry point for batched synthesis: pinned host volumes [V,Z,H,W] in, HR volumes
+    [V,(Z-1)(A+1)+1,H,W] back in pinned host memory.  The V volumes are cut into groups; group g+1's host->device copy
+    and group g-1's device->host copy run on their own streams while group g computes (double-buffered staging)."""
+
+    def __init__(self, model, V, Z, H, W, alpha_range, groups: int = 4, chunk: int = 256):
+        self.model, self.ar, self.chunk = model, list(alpha_range), chunk
+        dev = next(model.parameters()).device
+        self.dev = dev
+        groups = max(1, min(groups, V))
+        self.bounds = [(g * V // groups, (g + 1) * V // groups) for g in range(groups)]
+        gmax = max(e - s for s, e in self.bounds)
+        A = len(self.ar)
+        Zo = (Z - 1) * (A + 1) + 1
+        self.d_in = [torch.empty(gmax, Z, H, W, device=dev) for _ in range(2)]
+        self.d_out = [torch.empty(gmax, Zo, H, W, device=dev) for _ in range(2)]
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.in_free = [torch.cuda.Event() for _ in range(2)]     # compute finished reading d_in[b]
+        self.out_free = [torch.cuda.Event() for _ in range(2)]    # copy-out finished reading d_out[b]
+        self.used = [False, False]
+
+    def run(self, host_in: torch.Tensor, host_out: torch.Tensor) -> None:
+        main = torch.cuda.current_stream(self.dev)
+        last_copy = None
+        for g, (s, e) in enumerate(self.bounds):
+            b = g & 1
+            n = e - s
+            with torch.cuda.stream(self.s_in):
+                if self.used[b]:
+                    self.s_in.wait_event(self.in_free[b])
+                self.d_in[b][:n].copy_(host_in[s:e], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(self.s_in)
+            main.wait_event(ready)
+            if self.used[b]:
+                main.wait_event(self.out_free[b])
+            synthesize_volumes(self.model, self.d_in[b][:n], self.ar, use_original=True, out=self.d_out[b][:n],
+                               decode_chunk=self.chunk, encode_chunk=self.chunk)
+            self.in_free[b].record(main)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(done)
+                host_out[s:e].copy_(self.d_out[b][:n], non_blocking=True)
+                self.out_free[b].record(self.s_out)
+            self.used[b] = True
+            last_copy = self.out_free[b]
+        # the call returns stream-ordered on the caller's stream: results are in host_out once `main` passes this point
+        if last_copy is not None:
+            for b in range(2):
+                if self.used[b]:
+                    main.wait_event(self.out_free[b])
+
+
 @torch.no_grad()
 def latent_space_interp(alpha, trainer, img1, img2, device="cuda", with_labels=False, hierarchical=False) -> dict:
     """generate_hr_volumes.py:72-101 / kwatsch/img_interpolation.py:57-89 (same signature and return dict)."""

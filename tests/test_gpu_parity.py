@@ -1,0 +1,300 @@
+"""GPU tier (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle / golden fixtures.
+
+Tolerances (BASELINE.json north_star): synthesized slices within max-abs 2e-2 on [0,1] intensities for the
+random-init checkpoint; PSNR / SSIM within 0.05 dB / 0.001; slice indexing, kept slices and interpolation weights
+bit-exact.  Internal activations are fp16 (fp32 accumulate), so per-kernel checks compare against torch fp32 on
+fp16-rounded operands with a tolerance of a few output ulps.  The 'calibrated' checkpoint (O(1) activations through
+all 13 layers, |gamma| up to 3) is a stress test beyond the spec'd random-init bar; its bounds are stated below.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import aesr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(cuda_lib):
+    return torch.device("cuda:0")
+
+
+def make_model(args, state, dev):
+    from superresolution_aniso_mri_b200.networks.acai_vanilla import VanillaACAI
+    margs = dict(args)
+    margs["device"] = str(dev)
+    m = VanillaACAI(margs)
+    m.load_state_dict(state)
+    return m.eval()
+
+
+# ------------------------------------------------------------------------------------------------ kernels
+CONV_CASES = [  # cin, cout, n, h, w, act, mode, affine
+    (32, 32, 1, 16, 8, 0, 0, False), (32, 32, 2, 130, 130, 1, 1, True), (32, 64, 2, 65, 65, 1, 0, False),
+    (64, 64, 2, 65, 65, 1, 1, True), (64, 128, 2, 32, 32, 1, 0, False), (128, 128, 2, 32, 32, 0, 3, False),
+    (128, 64, 3, 32, 32, 1, 0, False), (64, 64, 3, 32, 32, 1, 2, True), (64, 32, 2, 64, 64, 1, 0, False),
+    (32, 32, 2, 64, 64, 1, 2, True), (32, 32, 2, 128, 128, 1, 0, False), (64, 64, 1, 55, 55, 1, 1, True),
+    (128, 256, 1, 16, 16, 2, 0, False), (256, 256, 1, 16, 16, 2, 4, False), (512, 512, 1, 8, 8, 2, 0, False),
+    (64, 64, 1, 1, 1, 1, 0, False), (32, 32, 1, 3, 5, 1, 1, False), (64, 64, 149, 32, 32, 1, 0, False),
+]
+
+
+def conv_reference(x, wt, b, act, sc, sh, mode, dtype):
+    y = F.conv2d(x.float().permute(0, 3, 1, 2).cpu(), wt.to(dtype).float().cpu(), b.cpu(), padding=1)
+    if act == 1:
+        y = F.leaky_relu(y, 0.01)
+    elif act == 2:
+        y = F.relu(y)
+    if sc is not None:
+        y = y * sc.cpu()[None, :, None, None] + sh.cpu()[None, :, None, None]
+    if mode == 1:
+        y = F.avg_pool2d(y, 2)
+    elif mode == 2:
+        y = F.interpolate(y, scale_factor=2, mode="nearest")
+    return y
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3x3_vs_torch_fp32(dev, case, algo, dtype):
+    from superresolution_aniso_mri_b200 import ops
+    cin, cout, n, h, w, act, mode, affine = case
+    if algo == 1 and cin >= 512:
+        pytest.skip("512-channel filter banks do not fit the resident-filter kernel")
+    if dtype == torch.bfloat16 and (n > 3 or cin > 128):
+        pytest.skip("bf16 covered on the autoencoder shapes")
+    g = torch.Generator().manual_seed(cin * 7 + cout + h)
+    x = torch.randn(n, h, w, cin, generator=g).to(dtype).to(dev)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / np.sqrt(cin * 9)).to(dev)
+    b = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    sc = (torch.rand(cout, generator=g) + 0.5).to(dev) if affine else None
+    sh = (torch.randn(cout, generator=g) * 0.1).to(dev) if affine else None
+    res = ops.conv3x3(x, ops.pack_conv3x3_weight(wt, dtype=dtype), b, act=act, scale=sc, shift=sh, out_mode=mode,
+                      algo=algo)
+    want = conv_reference(x, wt, b, act, sc, sh, mode if mode != 4 else 0, dtype)
+    ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    tol = 4 * ulp * max(1.0, want.abs().max().item()) + 2e-4 * np.sqrt(cin * 9)
+    if mode == 3:
+        got = res.cpu()
+        tol = 2e-4 * np.sqrt(cin * 9)                 # fp32 output: only accumulation-order noise
+    elif mode == 4:
+        got = res[0].float().permute(0, 3, 1, 2).cpu()
+        got2 = res[1].float().permute(0, 3, 1, 2).cpu()
+        assert (got2 - F.max_pool2d(want, 2)).abs().max().item() <= tol
+    else:
+        got = res.float().permute(0, 3, 1, 2).cpu()
+    assert got.shape == want.shape
+    assert (got - want).abs().max().item() <= tol
+
+
+def test_conv3x3_dgrad_multiplier_and_stats(dev):
+    """Epilogue extras used by training: act'(mul_src) multiplier and per-channel sum / sum-of-squares."""
+    from superresolution_aniso_mri_b200 import ops
+    dt = torch.float16
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 33, 20, 64, generator=g).to(dt).to(dev)
+    wt = (torch.randn(64, 64, 3, 3, generator=g) / 24).to(dev)
+    b = (torch.randn(64, generator=g) * 0.1).to(dev)
+    src = torch.randn(2, 33, 20, 64, generator=g).to(dt).to(dev)
+    stats = torch.zeros(128, device=dev)
+    got = ops.conv3x3(x, ops.pack_conv3x3_weight(wt, dtype=dt), b, act=0, mul_src=src, mul_mode=1, stats=stats)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2).cpu(), wt.to(dt).float().cpu(), b.cpu(), padding=1)
+    y = y * torch.where(src.float().permute(0, 3, 1, 2).cpu() > 0, 1.0, 0.01)
+    assert (got.float().permute(0, 3, 1, 2).cpu() - y).abs().max().item() < 1e-2
+    assert torch.allclose(stats[:64].cpu(), y.sum(dim=(0, 2, 3)), rtol=2e-3, atol=5e-2)
+    assert torch.allclose(stats[64:].cpu(), (y * y).sum(dim=(0, 2, 3)), rtol=2e-3, atol=5e-2)
+
+
+def test_dgrad_weight_packing(dev):
+    """transpose_flip packing turns the forward kernel into the data-gradient conv."""
+    from superresolution_aniso_mri_b200 import ops
+    dt = torch.float16
+    g = torch.Generator().manual_seed(4)
+    wt = (torch.randn(64, 32, 3, 3, generator=g) / 17).to(dev)             # Cout=64, Cin=32
+    dy = torch.randn(2, 20, 24, 64, generator=g).to(dt).to(dev)
+    got = ops.conv3x3(dy, ops.pack_conv3x3_weight(wt, transpose_flip=True, dtype=dt), None)
+    want = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2).cpu(), wt.to(dt).float().cpu(), padding=1)
+    assert got.shape == (2, 20, 24, 32)
+    assert (got.float().permute(0, 3, 1, 2).cpu() - want).abs().max().item() < 1e-2
+
+
+def test_edge_kernels_e0_head_lerp_place(dev):
+    from superresolution_aniso_mri_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(3, 1, 20, 28, generator=g)
+    w0, b0 = torch.randn(32, generator=g), torch.randn(32, generator=g)
+    a0 = ops.e0(x.to(dev), w0.to(dev), b0.to(dev))
+    want = F.conv2d(x, w0.view(32, 1, 1, 1), b0, padding=1)
+    assert a0.shape == (3, 22, 30, 32)
+    assert (a0.float().permute(0, 3, 1, 2).cpu() - want).abs().max().item() < 4e-3
+    # head: 32 -> 1 conv + sigmoid, scattered into a larger volume
+    act = torch.randn(4, 12, 16, 32, generator=g).to(torch.float16)
+    wh, bh = torch.randn(1, 32, 3, 3, generator=g) / 17, 0.3
+    out = torch.full((7, 12, 16), -1.0, device=dev)
+    idx = torch.tensor([5, 0, 3, 6], dtype=torch.int32, device=dev)
+    ops.head(act.to(dev), wh[0].permute(1, 2, 0).reshape(9, 32).contiguous().to(dev), bh, out=out,
+             out_image_stride=12 * 16, out_index=idx)
+    ref = torch.sigmoid(F.conv2d(act.float().permute(0, 3, 1, 2), wh, torch.tensor([bh]), padding=1))[:, 0]
+    assert (out[idx.long()].cpu() - ref).abs().max().item() < 1e-5
+    assert torch.all(out[[1, 2, 4]] == -1.0)                     # untouched slots
+    # lerp: fp32 result bit-exact with torch's `alpha * z1 + (1 - alpha) * z2`
+    z = torch.randn(5, 128, 6, 6, generator=g)
+    ar = O.alpha_range_for(6)
+    hi, lo = O.interp_weights(ar)
+    ia = torch.tensor([1, 2, 3, 4, 1, 2], dtype=torch.int32)
+    ib = torch.tensor([0, 1, 2, 3, 0, -1], dtype=torch.int32)
+    nhwc, nchw = ops.lerp_latents(z.to(dev), ia.to(dev), ib.to(dev), torch.from_numpy(hi).to(dev),
+                                  torch.from_numpy(lo).to(dev), want_nchw=True)
+    for m in range(5):
+        ref_m = float(ar[m]) * z[ia[m]] + (1 - float(ar[m])) * z[ib[m]]
+        assert torch.equal(nchw[m].cpu(), ref_m), "interpolation must be bit-exact (alpha %d)" % m
+        assert torch.equal(nhwc[m].cpu(), ref_m.permute(1, 2, 0).to(torch.float16))
+    assert torch.equal(nchw[5].cpu(), z[2])                      # ib < 0: plain copy
+    # place_slices: clamp + scatter, odd sizes
+    src = torch.randn(3, 7, 9, generator=g)
+    dst = torch.zeros(5, 7, 9, device=dev)
+    ops.place_slices(src.to(dev), dst, torch.tensor([4, 0, 2], dtype=torch.int32, device=dev))
+    assert torch.equal(dst[[4, 0, 2]].cpu(), src.clamp(0, 1)) and torch.all(dst[[1, 3]] == 0)
+
+
+def test_invalid_arguments_raise(dev):
+    from superresolution_aniso_mri_b200 import ops
+    x = torch.zeros(1, 8, 8, 48, dtype=torch.float16, device=dev)
+    w = torch.zeros(9, 32, 48, dtype=torch.float16, device=dev)
+    with pytest.raises(RuntimeError, match="Cin=48"):
+        ops.conv3x3(x, w, None)
+    with pytest.raises(RuntimeError):
+        ops.e0(torch.zeros(1, 1, 4, 4), torch.zeros(32), torch.zeros(32))      # CPU tensor
+
+
+# ------------------------------------------------------------------------------------------------ network parity
+def test_random_init_checkpoint_meets_spec_tolerance(dev, golden):
+    """BASELINE north_star: identical synthetic inputs + random-init weights, max-abs 2e-2 on [0,1]."""
+    from superresolution_aniso_mri_b200 import synthesis
+    g = golden("infer_acdc.npz")
+    args = O.default_args(128, 32)
+    model = make_model(args, O.init_state(args, seed=892372), dev)
+    for vname, vol in (("uniform", O.synthetic_volume(10, 128, seed=1)), ("phantom", O.smooth_phantom(10, 128, seed=2))):
+        for ni in (6, 1):
+            got = synthesis.create_super_volume(model, vol, O.alpha_range_for(ni), use_original=True)["upsampled_image"]
+            key = "rnd_%s_ni%d" % (vname, ni)
+            assert got.shape == (9 * (ni + 1) + 1, 128, 128)
+            assert np.abs(got[:, ::4, ::4].numpy() - g[key + "_sub"]).max() < 2e-2
+            kept = np.arange(0, got.shape[0], ni + 1)
+            np.testing.assert_array_equal(got[kept][:, ::4, ::4].numpy(), g[key + "_sub"][kept])   # originals bit-exact
+            assert np.abs(got.double().sum(dim=(1, 2)).numpy() - g[key + "_slice_sum"]).max() < 2e-2 * 128 * 128
+
+
+def test_small_volume_against_golden_full_tensors(dev, golden):
+    from superresolution_aniso_mri_b200 import synthesis
+    g = golden("infer_small.npz")
+    args = O.default_args(64, 16)
+    model = make_model(args, O.calibrated_state(args), dev)
+    vol = 0.8 * O.smooth_phantom(4, 64, seed=2) + 0.2 * O.synthetic_volume(4, 64, seed=1)
+    z = model.encode(vol.to(dev)).cpu()
+    assert z.shape == (4, 128, 16, 16) and z.dtype == torch.float32
+    zr = torch.from_numpy(g["z"])
+    assert (z - zr).abs().max().item() < 0.03 * zr.abs().max().item()
+    rec = model(vol.to(dev)).cpu()
+    assert (rec - torch.from_numpy(g["recon"])).abs().max().item() < 6e-2
+    assert (rec - torch.from_numpy(g["recon"])).abs().mean().item() < 3e-3
+    for use_original, key in ((True, "hr"), (False, "hr_recon")):
+        got = synthesis.create_super_volume(model, vol, g["alpha_range"], use_original=use_original)["upsampled_image"]
+        want = torch.from_numpy(g[key])
+        assert got.shape == want.shape
+        assert (got - want).abs().max().item() < 6e-2 and (got - want).abs().mean().item() < 3e-3
+        if use_original:
+            assert torch.equal(got[::3], want[::3])
+
+
+def test_eval_twin_slice_dropping(dev, golden):
+    from superresolution_aniso_mri_b200 import synthesis
+    g = golden("infer_eval_twin.npz")
+    args = O.default_args(64, 16)
+    model = make_model(args, O.calibrated_state(args), dev)
+    vol11 = (0.8 * O.smooth_phantom(11, 64, seed=4) + 0.2 * O.synthetic_volume(11, 64, seed=3))[:, 0]
+    out = synthesis.create_super_volume_eval(model, vol11, O.alpha_range_for(2), use_original=False, downsample_steps=3,
+                                             generate_inbetween_slices=True)["upsampled_image"]
+    want = torch.from_numpy(g["hr"])
+    assert out.shape == want.shape == (11, 64, 64)
+    assert torch.equal(out[10], want[10])                        # trimmed tail slice re-appended untouched
+    assert (out - want).abs().max().item() < 6e-2 and (out - want).abs().mean().item() < 3e-3
+
+
+def test_calibrated_acdc_volume_psnr_ssim(dev, golden):
+    """Stress checkpoint, config 1: error statistics + PSNR/SSIM deltas (0.05 dB / 0.001) of the synthesized slices."""
+    from superresolution_aniso_mri_b200 import synthesis
+    args = O.default_args(128, 32)
+    st = O.calibrated_state(args)
+    model = make_model(args, st, dev)
+    vol = O.smooth_phantom(10, 128, seed=2)
+    ar = O.alpha_range_for(1)
+    want = O.create_super_volume(st, args, vol, ar, use_original=True)
+    got = synthesis.create_super_volume(model, vol, ar, use_original=True)["upsampled_image"]
+    g = golden("infer_acdc.npz")
+    np.testing.assert_array_equal(want[:, ::4, ::4].numpy(), g["cal_phantom_ni1_sub"])      # oracle == reference
+    d = (got - want).abs()
+    assert d.max().item() < 8e-2 and d.mean().item() < 3e-3
+    # image-quality metrics of the synthesized slices against a pseudo ground truth (mean of the neighbours)
+    synth = np.arange(1, 19, 2)
+    truth = (0.5 * (vol[:-1, 0] + vol[1:, 0])).numpy()
+    psnr_o = np.mean([O.psnr_slice(truth[i], want[s].numpy()) for i, s in enumerate(synth)])
+    psnr_g = np.mean([O.psnr_slice(truth[i], got[s].numpy()) for i, s in enumerate(synth)])
+    ssim_o = np.mean([O.ssim_slice(truth[i], want[s].numpy()) for i, s in enumerate(synth)])
+    ssim_g = np.mean([O.ssim_slice(truth[i], got[s].numpy()) for i, s in enumerate(synth)])
+    assert abs(psnr_o - psnr_g) < 0.05 and abs(ssim_o - ssim_g) < 1e-3
+
+
+def test_scales3_readme_literal_config(dev, golden):
+    from superresolution_aniso_mri_b200 import synthesis
+    g = golden("infer_acdc.npz")
+    args = O.default_args(128, 16)
+    model = make_model(args, O.calibrated_state(args), dev)
+    got = synthesis.create_super_volume(model, O.smooth_phantom(5, 128, seed=2), O.alpha_range_for(3),
+                                        use_original=True)["upsampled_image"]
+    d = np.abs(got[:, ::4, ::4].numpy() - g["cal_lw16_phantom_ni3_sub"])
+    assert got.shape == (17, 128, 128) and d.max() < 8e-2 and d.mean() < 4e-3
+
+
+def test_odd_sizes_and_batch_invariance_at_full_size(dev):
+    """Size-independent properties at BASELINE sizes: (i) batching V volumes == one at a time, bit-exact (eval BN is
+    per-sample); (ii) alpha -> 0 / 1 limits reproduce the reconstructions of the neighbouring slices;
+    (iii) non-multiple-of-tile inputs (OASIS eval 220 -> 222/111/55) run and agree with the oracle."""
+    from superresolution_aniso_mri_b200 import synthesis
+    args = O.default_args(128, 32)
+    model = make_model(args, O.calibrated_state(args), dev)
+    vols = torch.rand(6, 10, 128, 128, generator=torch.Generator().manual_seed(5)).to(dev)
+    ar = O.alpha_range_for(6)
+    batched = synthesis.synthesize_volumes(model, vols, ar, decode_chunk=100, encode_chunk=32)
+    for v in (0, 5):
+        single = synthesis.synthesize_volumes(model, vols[v:v + 1], ar)
+        assert torch.equal(batched[v], single[0])
+    lim = synthesis.synthesize_volumes(model, vols[:1], [0.0, 1.0], use_original=False)[0]
+    assert torch.equal(lim[1], lim[0]) and torch.equal(lim[2], lim[3])     # alpha=0 -> slice i, alpha=1 -> slice i+1
+    args220 = O.default_args(64, 16)
+    st = O.calibrated_state(args220)
+    m220 = make_model(args220, st, dev)
+    x = O.smooth_phantom(3, 220, seed=8)
+    with torch.no_grad():
+        want = O.decode(st, args220, O.encode(st, args220, x))
+    got = m220(x.to(dev)).cpu()
+    assert got.shape == want.shape == (3, 1, 220, 220)
+    assert (got - want).abs().max().item() < 8e-2 and (got - want).abs().mean().item() < 3e-3
+
+
+def test_host_pipeline_matches_device_path(dev):
+    from superresolution_aniso_mri_b200 import synthesis
+    args = O.default_args(128, 32)
+    model = make_model(args, O.calibrated_state(args), dev)
+    ar = O.alpha_range_for(6)
+    host_in = torch.rand(5, 10, 128, 128, generator=torch.Generator().manual_seed(6)).pin_memory()
+    host_out = torch.empty(5, 64, 128, 128).pin_memory()
+    pipe = synthesis.HostPipeline(model, 5, 10, 128, 128, ar, groups=3)
+    pipe.run(host_in, host_out)
+    pipe.run(host_in, host_out)                                   # buffer reuse across calls
+    torch.cuda.synchronize()
+    want = synthesis.synthesize_volumes(model, host_in.to(dev), ar).cpu()
+    assert torch.equal(host_out, want)
