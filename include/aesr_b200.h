@@ -88,7 +88,7 @@ int aesr_e0_fwd(const float* x, const float* w, const float* b, void* out, int N
  * (generate_hr_volumes.py:67).  in NHWC 16-bit [N,H,W,C] (C = 32), w9c fp32 [9][C]; image n is written at
  * out + (out_index ? out_index[n] : n) * out_image_stride (floats), so synthesized slices land directly at their
  * position i*(A+1)+1+k inside the HR volume (generate_hr_volumes.py:58-60) without a concat pass. */
-int aesr_head_fwd(const void* in, const float* w9c, float bias, float* out, const int* out_index, int N, int H, int W,
+int aesr_head_fwd(const void* in, const float* w9c, const float* bias, float* out, const int* out_index, int N, int H, int W,
                   int C, size_t out_image_stride, int apply_sigmoid, int dtype, void* stream);
 
 /* Latent interpolation (generate_hr_volumes.py:88, kwatsch/cardiac/trainer_ae.py:173,
@@ -102,6 +102,60 @@ int aesr_lerp_latents(const float* z, const int* ia, const int* ib, const float*
  * (generate_hr_volumes.py:44,58-67: `recon_volume = images`, the torch.cat chain, the final torch.clamp).
  * src fp32 [N,HW], dst fp32 [*,HW], out_index int32 [N] or NULL (identity).  N <= 65535 per call. */
 int aesr_place_slices(const float* src, float* dst, const int* out_index, int N, int HW, int do_clamp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training step (kwatsch/cardiac/trainer_ae.py:10-50, kwatsch/brain/trainer_ae.py:92-132).  Gradient tensors are
+ * ALWAYS bf16 NHWC (fp32 range); activations are `dtype`; reductions, parameters and optimizer state are fp32.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* nn.BatchNorm2d in train mode (networks/acai_vanilla.py:58,90).  stats[c] = sum a, stats[C+c] = sum a^2 over `count`
+ * positions (accumulated by aesr_conv3x3_fwd's epilogue).  Writes this pass' scale/shift (gamma/sqrt(var+eps), ...),
+ * mean, invstd, and updates running_mean/var (momentum, unbiased variance); running_* may be NULL. */
+int aesr_bn_finalize(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, float* scale, float* shift, float* mean_out,
+                     float* invstd_out, int C, void* stream);
+/* out = mode(a * scale + shift), mode 0 same / 1 AvgPool2d(2) / 2 Upsample(2) nearest; a, out NHWC `dtype`. */
+int aesr_bn_apply(const void* a, const float* scale, const float* shift, void* out, int N, int H, int W, int C, int mode,
+                  int dtype, void* stream);
+/* Backward of [LeakyReLU ->] BatchNorm(train) -> pool/upsample: dnext bf16 (gradient of the pooled / upsampled tensor),
+ * a = saved post-activation input of the BN; g_out bf16 [N,H,W,C] = gradient w.r.t. the producing conv's
+ * pre-activation output; dgamma / dbeta accumulated; sums = 2*C floats of scratch. */
+int aesr_bn_bwd(const void* dnext, const void* a, const float* mean, const float* invstd, const float* gamma,
+                float* sums, float slope, void* g_out, float* dgamma, float* dbeta, int N, int H, int W, int C, int mode,
+                int dtype, void* stream);
+/* F.mse_loss(a, b) (kwatsch/base_trainer.py:177): *loss_acc += mean((a-b)^2); d (optional) = grad_scale * 2 (a-b)/n. */
+int aesr_mse(const float* a, const float* b, size_t n, float* loss_acc, float* d, float grad_scale, void* stream);
+/* Backward of dec.14 + Sigmoid: g_in bf16 (includes LeakyReLU'(a_in)), dw9c[9*C] and dbias accumulated. */
+int aesr_head_bwd(const float* dout, const float* out, const void* a_in, const float* w9c, void* g_in, float* dw9c,
+                  float* dbias, int N, int H, int W, int C, float slope, int dtype, void* stream);
+/* Backward of enc.0 (1x1 conv, padding 1): dw[C], db[C] accumulated from g bf16 [N,H+2,W+2,C] and x fp32 [N,1,H,W]. */
+int aesr_e0_bwd(const void* g, const float* x, float* dw, float* db, int N, int H, int W, int C, void* stream);
+/* Weight gradient of a 3x3 conv: dW fp32 [Cout,Cin,3,3] += g^T * shifted(x), dbias[Cout] += sum g (dbias may be NULL).
+ * g bf16 [N,H,W,Cout], x `dtype` [N,H,W,Cin]. */
+int aesr_wgrad3x3(const void* g, const void* x, float* dW, float* dbias, int N, int H, int W, int Cin, int Cout, int dtype,
+                  void* stream);
+/* Backward of z_mix[b] = wa[b] z[b] + wb[b] z[B+b]: g_z[2B] = g_dec[2B] + {wa,wb}[b] * g_mix[b] (bf16 NHWC). */
+int aesr_mix_bwd(const void* g_dec, const void* g_mix, const float* wa, const float* wb, void* g_z, int B,
+                 size_t per_image, void* stream);
+/* torch.optim.Adam step over flat fp32 buffers (kwatsch/trainer_ae.py:29-30); `step` is the 1-based step count. */
+int aesr_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, void* stream);
+
+/* LPIPS-VGG v0.1 (lpips/perceptual.py:19-33, lpips/networks_basic.py:63-110, lpips/pretrained_networks.py:97-135). */
+/* conv1_1 with the input pipeline folded in: (2*img-1 if normalize), ScalingLayer 1->3 channels, conv 3->64, ReLU.
+ * img fp32 [N,1,H,W]; w fp32 [64,3,3,3]; shift3/scale3 HOST pointers to 3 floats; out NHWC `dtype` [N,H,W,64]. */
+int aesr_vgg_conv1_fwd(const float* img, const float* w, const float* b, void* out, int N, int H, int W,
+                       const float* shift3, const float* scale3, int normalize, int dtype, void* stream);
+/* its backward to the image: g bf16 [N,H,W,64] (ReLU' applied) -> dimg fp32 [N,1,H,W] * out_scale. */
+int aesr_vgg_conv1_bwd(const void* g, const float* w, float* dimg, int N, int H, int W, const float* scale3,
+                       int normalize, float out_scale, void* stream);
+/* MaxPool2d(2) backward + tap gradient + ReLU': g_out = relu'(a) * (route(d_pooled) + g_tap); d_pooled or g_tap may be NULL. */
+int aesr_maxpool_bwd(const void* a, const void* d_pooled, const void* g_tap, void* g_out, int N, int H, int W, int C,
+                     int dtype, void* stream);
+/* Distance head of one VGG tap: val[n] += spatial_mean(sum_c lin_c (f0_c - f1_c)^2) with f = o/(||o||+1e-10);
+ * if g1 != NULL also the gradient w.r.t. o1 (bf16), scaled by upstream[n].  o0, o1 NHWC `dtype` [N,HW,C]. */
+int aesr_lpips_head(const void* o0, const void* o1, const float* lin, float* val, const float* upstream, void* g1, int N,
+                    int HW, int C, int dtype, void* stream);
 
 /* DIAGNOSTIC (not on the product path): one 16x8 tile of a 64->64 bf16 conv computed from a single TMA halo load with
  * row-shifted UMMA descriptors; used by tools/gpu_diag.py to establish what the hardware's swizzle addressing does.

@@ -24,10 +24,24 @@ _SIGNATURES = {
     "aesr_pack_conv3x3_weight": (I, [P, P, I, I, I, I, P]),
     "aesr_conv3x3_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, F, I, I, I, I, P]),
     "aesr_e0_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
-    "aesr_head_fwd": (I, [P, P, F, P, P, I, I, I, I, c_size_t, I, I, P]),
+    "aesr_head_fwd": (I, [P, P, P, P, P, I, I, I, I, c_size_t, I, I, P]),
     "aesr_lerp_latents": (I, [P, P, P, P, P, P, P, I, I, I, I, P]),
     "aesr_place_slices": (I, [P, P, P, I, I, I, P]),
     "aesr_probe_halo_conv": (I, [P, P, P, I, I, I, I, I, I, I, I, P]),
+    # training step
+    "aesr_bn_finalize": (I, [P, F, P, P, P, P, F, F, P, P, P, P, I, P]),
+    "aesr_bn_apply": (I, [P, P, P, P, I, I, I, I, I, I, P]),
+    "aesr_bn_bwd": (I, [P, P, P, P, P, P, F, P, P, P, I, I, I, I, I, I, P]),
+    "aesr_mse": (I, [P, P, c_size_t, P, P, F, P]),
+    "aesr_head_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
+    "aesr_e0_bwd": (I, [P, P, P, P, I, I, I, I, P]),
+    "aesr_wgrad3x3": (I, [P, P, P, P, I, I, I, I, I, I, P]),
+    "aesr_mix_bwd": (I, [P, P, P, P, P, I, c_size_t, P]),
+    "aesr_adam_step": (I, [P, P, P, P, c_size_t, F, F, F, F, F, I, P]),
+    "aesr_vgg_conv1_fwd": (I, [P, P, P, P, I, I, I, P, P, I, I, P]),
+    "aesr_vgg_conv1_bwd": (I, [P, P, P, I, I, I, P, I, F, P]),
+    "aesr_maxpool_bwd": (I, [P, P, P, P, I, I, I, I, I, P]),
+    "aesr_lpips_head": (I, [P, P, P, P, P, P, I, I, I, I, P]),
 }
 
 

@@ -9,7 +9,9 @@
 #include "../../include/aesr_b200.h"
 #include "conv3x3_tc.cuh"
 #include "elementwise.cuh"
+#include "lpips_kernels.cuh"
 #include "probe.cuh"
+#include "train_kernels.cuh"
 
 using namespace aesr;
 
@@ -287,11 +289,11 @@ int aesr_e0_fwd(const float* x, const float* w, const float* b, void* out, int N
     return check_launch("e0_conv1x1_pad1");
 }
 
-int aesr_head_fwd(const void* in, const float* w9c, float bias, float* out, const int* out_index, int N, int H, int W,
+int aesr_head_fwd(const void* in, const float* w9c, const float* bias, float* out, const int* out_index, int N, int H, int W,
                   int C, size_t out_image_stride, int apply_sigmoid, int dtype, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
-    if (!in || !w9c || !out || N <= 0 || H <= 0 || W <= 0) return fail(AESR_ERR_INVALID, "head_fwd: bad arguments");
+    if (!in || !w9c || !bias || !out || N <= 0 || H <= 0 || W <= 0) return fail(AESR_ERR_INVALID, "head_fwd: bad arguments");
     if (C != 32) return fail(AESR_ERR_INVALID, "head_fwd: C=%d unsupported (32)", C);
     const size_t total = static_cast<size_t>(N) * H * W;
     const int block = 128;
@@ -354,3 +356,5 @@ int aesr_probe_halo_conv(const void* x, const void* w_packed, float* out, int N,
 }
 
 }  // extern "C"
+
+#include "api_train.cuh"

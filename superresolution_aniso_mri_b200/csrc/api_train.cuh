@@ -1,0 +1,212 @@
+// extern "C" entry points of the training-step kernels (included by api.cu; declared in include/aesr_b200.h).
+#pragma once
+
+namespace {
+inline int grid_for(size_t total, int block, int per_sm = 8) {
+    size_t g = (total + block - 1) / block;
+    const size_t cap = static_cast<size_t>(g_sm_count) * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+}  // namespace
+
+extern "C" {
+
+int aesr_bn_finalize(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, float* scale, float* shift, float* mean_out,
+                     float* invstd_out, int C, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!stats || !gamma || !beta || !scale || !shift || !mean_out || !invstd_out || C <= 0 || count <= 0)
+        return fail(AESR_ERR_INVALID, "bn_finalize: bad arguments");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        stats, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, mean_out, invstd_out, C);
+    return check_launch("bn_finalize");
+}
+
+int aesr_bn_apply(const void* a, const float* scale, const float* shift, void* out, int N, int H, int W, int C, int mode,
+                  int dtype, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!a || !scale || !shift || !out || C % 8 != 0 || mode < 0 || mode > 2) return fail(AESR_ERR_INVALID, "bn_apply: bad arguments");
+    const int Ho = mode == BN_POOL ? H / 2 : mode == BN_UP ? 2 * H : H, Wo = mode == BN_POOL ? W / 2 : mode == BN_UP ? 2 * W : W;
+    const size_t total = static_cast<size_t>(N) * Ho * Wo * (C / 8);
+    if (total == 0) return AESR_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == AESR_DT_FP16)
+        bn_apply_kernel<true><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(a), scale, shift, static_cast<uint16_t*>(out), N, H, W, C, mode);
+    else
+        bn_apply_kernel<false><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(a), scale, shift, static_cast<uint16_t*>(out), N, H, W, C, mode);
+    return check_launch("bn_apply");
+}
+
+int aesr_bn_bwd(const void* dnext, const void* a, const float* mean, const float* invstd, const float* gamma,
+                float* sums, float slope, void* g_out, float* dgamma, float* dbeta, int N, int H, int W, int C, int mode,
+                int dtype, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!dnext || !a || !mean || !invstd || !gamma || !sums || !g_out || !dgamma || !dbeta || C % 32 != 0 || mode < 0 || mode > 2)
+        return fail(AESR_ERR_INVALID, "bn_bwd: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t npix = static_cast<size_t>(N) * H * W;
+    CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), s));
+    int gx = static_cast<int>((npix + 63) / 64);
+    const int capx = g_sm_count * 8 / (C / 32);
+    if (gx > capx) gx = capx;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, C / 32), block(32, 8);
+    const size_t total = npix * C;
+    const float count = static_cast<float>(npix);
+    if (dtype == AESR_DT_FP16) {
+        bn_bwd_reduce_kernel<true><<<grid, block, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode);
+        bn_bwd_apply_kernel<true><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, slope, static_cast<uint16_t*>(g_out), dgamma, dbeta, N, H, W, C, mode);
+    } else {
+        bn_bwd_reduce_kernel<false><<<grid, block, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode);
+        bn_bwd_apply_kernel<false><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, slope, static_cast<uint16_t*>(g_out), dgamma, dbeta, N, H, W, C, mode);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return check_launch("bn_bwd");
+}
+
+int aesr_mse(const float* a, const float* b, size_t n, float* loss_acc, float* d, float grad_scale, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!a || !b || !loss_acc || n == 0) return fail(AESR_ERR_INVALID, "mse: bad arguments");
+    mse_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, 1.f / static_cast<float>(n), loss_acc, d, grad_scale);
+    return check_launch("mse");
+}
+
+int aesr_head_bwd(const float* dout, const float* out, const void* a_in, const float* w9c, void* g_in, float* dw9c,
+                  float* dbias, int N, int H, int W, int C, float slope, int dtype, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!dout || !out || !a_in || !w9c || !g_in || !dw9c || !dbias || C != 32) return fail(AESR_ERR_INVALID, "head_bwd: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t total = static_cast<size_t>(N) * H * W;
+    const uint16_t* a16 = static_cast<const uint16_t*>(a_in);
+    if (dtype == AESR_DT_FP16) {
+        head_bwd_data_kernel<32, true><<<grid_for(total, 128, 32), 128, 0, s>>>(dout, out, a16, w9c, static_cast<uint16_t*>(g_in), N, H, W, slope);
+        head_bwd_weight_kernel<32, true><<<grid_for(total * 32 / 8, 256, 8), 256, 0, s>>>(dout, out, a16, dw9c, dbias, N, H, W);
+    } else {
+        head_bwd_data_kernel<32, false><<<grid_for(total, 128, 32), 128, 0, s>>>(dout, out, a16, w9c, static_cast<uint16_t*>(g_in), N, H, W, slope);
+        head_bwd_weight_kernel<32, false><<<grid_for(total * 32 / 8, 256, 8), 256, 0, s>>>(dout, out, a16, dw9c, dbias, N, H, W);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return check_launch("head_bwd");
+}
+
+int aesr_e0_bwd(const void* g, const float* x, float* dw, float* db, int N, int H, int W, int C, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!g || !x || !dw || !db || C != 32) return fail(AESR_ERR_INVALID, "e0_bwd: bad arguments (C must be 32)");
+    const size_t total = static_cast<size_t>(N) * (H + 2) * (W + 2);
+    e0_bwd_kernel<<<grid_for(total * 32 / 16, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint16_t*>(g), x, dw, db, N, H, W, C);
+    return check_launch("e0_bwd");
+}
+
+int aesr_wgrad3x3(const void* g, const void* x, float* dW, float* dbias, int N, int H, int W, int Cin, int Cout, int dtype,
+                  void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!g || !x || !dW || Cin % 32 != 0 || Cout % 32 != 0) return fail(AESR_ERR_INVALID, "wgrad3x3: bad arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t npix = static_cast<size_t>(N) * H * W;
+    constexpr int CO_PER = 4;                       // 8 warps x 4 = 32 output channels per block
+    const int gy = Cin / 32, gz = Cout / 32;
+    int gx = g_sm_count * 4 / (gy * gz);
+    if (gx < 1) gx = 1;
+    if (static_cast<size_t>(gx) > npix) gx = static_cast<int>(npix);
+    dim3 grid(gx, gy, gz);
+    const uint16_t* g16 = static_cast<const uint16_t*>(g);
+    const uint16_t* x16 = static_cast<const uint16_t*>(x);
+    if (dtype == AESR_DT_FP16) wgrad3x3_kernel<true, CO_PER><<<grid, 256, 0, s>>>(g16, x16, dW, dbias, N, H, W, Cin, Cout);
+    else wgrad3x3_kernel<false, CO_PER><<<grid, 256, 0, s>>>(g16, x16, dW, dbias, N, H, W, Cin, Cout);
+    return check_launch("wgrad3x3");
+}
+
+int aesr_mix_bwd(const void* g_dec, const void* g_mix, const float* wa, const float* wb, void* g_z, int B,
+                 size_t per_image, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!g_dec || !g_mix || !wa || !wb || !g_z || B <= 0) return fail(AESR_ERR_INVALID, "mix_bwd: bad arguments");
+    mix_bwd_kernel<<<grid_for(2 * B * per_image, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint16_t*>(g_dec), static_cast<const uint16_t*>(g_mix), wa, wb, static_cast<uint16_t*>(g_z), B, per_image);
+    return check_launch("mix_bwd");
+}
+
+int aesr_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!p || !g || !m || !v || n == 0 || step < 1) return fail(AESR_ERR_INVALID, "adam_step: bad arguments");
+    const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+    const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+    adam_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2));
+    return check_launch("adam_step");
+}
+
+int aesr_vgg_conv1_fwd(const float* img, const float* w, const float* b, void* out, int N, int H, int W,
+                       const float* shift3, const float* scale3, int normalize, int dtype, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!img || !w || !b || !out || !shift3 || !scale3) return fail(AESR_ERR_INVALID, "vgg_conv1_fwd: bad arguments");
+    const size_t total = static_cast<size_t>(N) * H * W * 8;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == AESR_DT_FP16)
+        vgg_conv1_fwd_kernel<true><<<grid_for(total, 256, 8), 256, 0, s>>>(img, w, b, static_cast<uint16_t*>(out), N, H, W, shift3[0], shift3[1], shift3[2], scale3[0], scale3[1], scale3[2], normalize);
+    else
+        vgg_conv1_fwd_kernel<false><<<grid_for(total, 256, 8), 256, 0, s>>>(img, w, b, static_cast<uint16_t*>(out), N, H, W, shift3[0], shift3[1], shift3[2], scale3[0], scale3[1], scale3[2], normalize);
+    return check_launch("vgg_conv1_fwd");
+}
+
+int aesr_vgg_conv1_bwd(const void* g, const float* w, float* dimg, int N, int H, int W, const float* scale3,
+                       int normalize, float out_scale, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!g || !w || !dimg || !scale3) return fail(AESR_ERR_INVALID, "vgg_conv1_bwd: bad arguments");
+    const size_t total = static_cast<size_t>(N) * H * W;
+    vgg_conv1_bwd_kernel<<<grid_for(total * 32, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint16_t*>(g), w, dimg, N, H, W, scale3[0], scale3[1], scale3[2], normalize, out_scale);
+    return check_launch("vgg_conv1_bwd");
+}
+
+int aesr_maxpool_bwd(const void* a, const void* d_pooled, const void* g_tap, void* g_out, int N, int H, int W, int C,
+                     int dtype, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!a || !g_out || (!d_pooled && !g_tap)) return fail(AESR_ERR_INVALID, "maxpool_bwd: bad arguments");
+    const size_t total = static_cast<size_t>(N) * H * W * C;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == AESR_DT_FP16)
+        maxpool_bwd_kernel<true><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(a), static_cast<const uint16_t*>(d_pooled), static_cast<const uint16_t*>(g_tap), static_cast<uint16_t*>(g_out), N, H, W, C);
+    else
+        maxpool_bwd_kernel<false><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(a), static_cast<const uint16_t*>(d_pooled), static_cast<const uint16_t*>(g_tap), static_cast<uint16_t*>(g_out), N, H, W, C);
+    return check_launch("maxpool_bwd");
+}
+
+int aesr_lpips_head(const void* o0, const void* o1, const float* lin, float* val, const float* upstream, void* g1, int N,
+                    int HW, int C, int dtype, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!o0 || !o1 || !lin || (!val && !g1) || (g1 && !upstream)) return fail(AESR_ERR_INVALID, "lpips_head: bad arguments");
+    const size_t total = static_cast<size_t>(N) * HW;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint16_t* a = static_cast<const uint16_t*>(o0);
+    const uint16_t* b = static_cast<const uint16_t*>(o1);
+    const int grid = grid_for(total * 32, 256, 8);
+    if (val) {
+        if (dtype == AESR_DT_FP16) lpips_head_fwd_kernel<true><<<grid, 256, 0, s>>>(a, b, lin, val, N, HW, C);
+        else lpips_head_fwd_kernel<false><<<grid, 256, 0, s>>>(a, b, lin, val, N, HW, C);
+        int r2 = check_launch("lpips_head_fwd");
+        if (r2 != AESR_OK) return r2;
+    }
+    if (g1) {
+        if (dtype == AESR_DT_FP16) lpips_head_bwd_kernel<true><<<grid, 256, 0, s>>>(a, b, lin, upstream, static_cast<uint16_t*>(g1), N, HW, C);
+        else lpips_head_bwd_kernel<false><<<grid, 256, 0, s>>>(a, b, lin, upstream, static_cast<uint16_t*>(g1), N, HW, C);
+        return check_launch("lpips_head_bwd");
+    }
+    return AESR_OK;
+}
+
+}  // extern "C"

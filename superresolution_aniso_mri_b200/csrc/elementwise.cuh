@@ -66,7 +66,7 @@ __global__ void e0_conv1x1_pad1_kernel(const float* __restrict__ x, const float*
 // ---------------------------------------------------------------------------------------------------------------
 template <int C, bool FP16>
 __global__ void head_conv3x3_sigmoid_kernel(const uint16_t* __restrict__ in, const float* __restrict__ w /*[9][C]*/,
-                                            float bias, float* __restrict__ out, const int* __restrict__ out_index,
+                                            const float* __restrict__ bias_ptr, float* __restrict__ out, const int* __restrict__ out_index,
                                             int N, int H, int W, size_t out_image_stride, int apply_sigmoid) {
     __shared__ float sw[9 * C];
     for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[i] = w[i];
@@ -77,7 +77,7 @@ __global__ void head_conv3x3_sigmoid_kernel(const uint16_t* __restrict__ in, con
         const int x = static_cast<int>(i % W);
         const int y = static_cast<int>((i / W) % H);
         const int n = static_cast<int>(i / (static_cast<size_t>(W) * H));
-        float acc = bias;
+        float acc = __ldg(bias_ptr);
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
             const int yy = y + dy - 1;

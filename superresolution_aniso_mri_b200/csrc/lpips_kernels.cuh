@@ -1,0 +1,207 @@
+// LPIPS-VGG v0.1 pieces that are not 3x3 tensor-core convs (lpips/networks_basic.py:63-110, lpips/perceptual.py:19-33,
+// lpips/pretrained_networks.py:97-135): the input preparation fused into conv1_1 (1 -> 3 -> 64 channels on CUDA
+// cores), its backward, the max-pool backward, and the fused distance head forward / backward.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "train_kernels.cuh"
+
+namespace aesr {
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv1_1 with the LPIPS input pipeline folded in:
+//   u = 2*img - 1 (perceptual.py:30-31, normalize=True) ; v_c = (u - shift_c) / scale_c for c in 0..2
+//   (ScalingLayer, networks_basic.py:99-100: a 1-channel image broadcasts against the [1,3,1,1] buffers) ;
+//   y = ReLU(conv3x3(v, W[64,3,3,3]) + b), zero padding applies to v (after the scaling).
+// img fp32 [N,1,H,W] -> out 16-bit NHWC [N,H,W,64].  One thread = one pixel x 8 output channels.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool AF>
+__global__ void vgg_conv1_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][3][3][3]*/,
+                                     const float* __restrict__ b, uint16_t* __restrict__ out, int N, int H, int W,
+                                     float sh0, float sh1, float sh2, float sc0, float sc1, float sc2, int normalize) {
+    __shared__ float sw[64 * 27];
+    __shared__ float sb[64];
+    for (int i = threadIdx.x; i < 64 * 27; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) sb[i] = b[i];
+    __syncthreads();
+    const float shf[3] = {sh0, sh1, sh2}, scv[3] = {sc0, sc1, sc2};
+    const size_t total = static_cast<size_t>(N) * H * W * 8;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int grp = static_cast<int>(i & 7);
+        const size_t p = i >> 3;
+        const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+        const size_t nb = (p / (static_cast<size_t>(W) * H)) * H * W;
+        float v[3][9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+            const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            float u = in ? img[nb + static_cast<size_t>(yy) * W + xx] : 0.f;
+            if (normalize) u = 2.f * u - 1.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c][t] = in ? (u - shf[c]) / scv[c] : 0.f;
+        }
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int co = grp * 8 + j;
+            float acc = sb[co];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int t = 0; t < 9; ++t) acc = fmaf(sw[co * 27 + c * 9 + t], v[c][t], acc);
+            o[j] = fmaxf(acc, 0.f);
+        }
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(pack2_t<AF>(o[0], o[1]), pack2_t<AF>(o[2], o[3]),
+                                                      pack2_t<AF>(o[4], o[5]), pack2_t<AF>(o[6], o[7]));
+    }
+}
+
+// backward of the above w.r.t. the image: g bf16 [N,H,W,64] is dL/d(pre-ReLU conv1_1 output) (ReLU' already applied)
+//   dimg[p] = (normalize ? 2 : 1) * sum_c (1/scale_c) * sum_{tap,co} W[co][c][tap] * g[p - off(tap)][co]
+// One warp per pixel: lanes split the 64 output channels (2 each), shuffle-reduce.
+__global__ void vgg_conv1_bwd_kernel(const uint16_t* __restrict__ g, const float* __restrict__ w,
+                                     float* __restrict__ dimg, int N, int H, int W, float sc0, float sc1, float sc2,
+                                     int normalize, float out_scale) {
+    __shared__ float swe[9 * 64];          // effective 1-channel filter: sum_c W[co][c][tap] / scale_c
+    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) {
+        const int t = i / 64, co = i % 64;
+        swe[i] = w[co * 27 + 0 * 9 + t] / sc0 + w[co * 27 + 1 * 9 + t] / sc1 + w[co * 27 + 2 * 9 + t] / sc2;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t warp_id = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+    const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+    const size_t total = static_cast<size_t>(N) * H * W;
+    for (size_t p = warp_id; p < total; p += nwarps) {
+        const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+        const size_t nb = (p / (static_cast<size_t>(W) * H)) * H * W;
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const uint32_t u = *reinterpret_cast<const uint32_t*>(g + (nb + static_cast<size_t>(yy) * W + xx) * 64 + lane * 2);
+            acc = fmaf(swe[t * 64 + lane * 2], bf16_lo(u), acc);
+            acc = fmaf(swe[t * 64 + lane * 2 + 1], bf16_hi(u), acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) dimg[p] = acc * (normalize ? 2.f : 1.f) * out_scale;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// MaxPool2d(2) backward fused with the tap gradient and the ReLU' of the producing conv:
+//   g_out[y,x,c] = relu'(a) * ( first_argmax(a over its 2x2 window) ? d_pooled[y/2,x/2,c] : 0  +  g_tap[y,x,c] )
+// a: post-ReLU activation 16-bit [N,H,W,C]; d_pooled bf16 [N,H/2,W/2,C]; g_tap bf16 [N,H,W,C] or null.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool AF>
+__global__ void maxpool_bwd_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ d_pooled,
+                                   const uint16_t* __restrict__ g_tap, uint16_t* __restrict__ g_out, int N, int H,
+                                   int W, int C) {
+    const int Ho = H / 2, Wo = W / 2;
+    const size_t total = static_cast<size_t>(N) * H * W * C;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        const size_t p = i / C;
+        const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+        const int n = static_cast<int>(p / (static_cast<size_t>(W) * H));
+        const float av = a16_to_f<AF>(a[i]);
+        float gsum = g_tap ? bf16_to_f(g_tap[i]) : 0.f;
+        const int yo = y >> 1, xo = x >> 1;
+        if (d_pooled != nullptr && yo < Ho && xo < Wo) {
+            // torch picks the first maximum in window scan order (0,0),(0,1),(1,0),(1,1)
+            const uint16_t* base = a + ((static_cast<size_t>(n) * H + 2 * yo) * W + 2 * xo) * C + c;
+            const float w0 = a16_to_f<AF>(base[0]), w1 = a16_to_f<AF>(base[C]);
+            const float w2 = a16_to_f<AF>(base[static_cast<size_t>(W) * C]), w3 = a16_to_f<AF>(base[static_cast<size_t>(W) * C + C]);
+            int arg = 0;
+            float best = w0;
+            if (w1 > best) { best = w1; arg = 1; }
+            if (w2 > best) { best = w2; arg = 2; }
+            if (w3 > best) { best = w3; arg = 3; }
+            if (arg == ((y & 1) * 2 + (x & 1)))
+                gsum += bf16_to_f(d_pooled[((static_cast<size_t>(n) * Ho + yo) * Wo + xo) * C + c]);
+        }
+        g_out[i] = __bfloat16_as_ushort(__float2bfloat16_rn(av > 0.f ? gsum : 0.f));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LPIPS distance head of one tap (networks_basic.py:70-77 + lpips/common.py:12-14):
+//   f = o / (||o||_2 + 1e-10) over channels ; val[n] += (1/HW) * sum_px sum_c lin_c (f0_c - f1_c)^2
+// f0 = features of image set 0 (reference), f1 = set 1 (synthesized); both 16-bit NHWC [N,HW,C].  One warp per pixel.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool AF>
+__global__ void lpips_head_fwd_kernel(const uint16_t* __restrict__ o0, const uint16_t* __restrict__ o1,
+                                      const float* __restrict__ lin, float* __restrict__ val, int N, int HW, int C) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp_id = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+    const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+    const size_t total = static_cast<size_t>(N) * HW;
+    for (size_t p = warp_id; p < total; p += nwarps) {
+        const uint16_t* a = o0 + p * C;
+        const uint16_t* b = o1 + p * C;
+        float n0 = 0.f, n1 = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float x0 = a16_to_f<AF>(a[c]), x1 = a16_to_f<AF>(b[c]);
+            n0 = fmaf(x0, x0, n0);
+            n1 = fmaf(x1, x1, n1);
+        }
+        n0 = warp_sum(n0);
+        n1 = warp_sum(n1);
+        const float i0 = 1.f / (sqrtf(n0) + 1e-10f), i1 = 1.f / (sqrtf(n1) + 1e-10f);
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float d = a16_to_f<AF>(a[c]) * i0 - a16_to_f<AF>(b[c]) * i1;
+            acc = fmaf(lin[c] * d, d, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) atomicAdd(val + p / HW, acc / HW);
+    }
+}
+
+// backward w.r.t. o1:  with e_c = 2 lin_c (f1_c - f0_c), s = sum_c e_c o1_c, r = ||o1||, q = r + eps
+//   d val / d o1_j = e_j / q - o1_j * s / (r q^2)       ; times upstream[n] / HW.   Output bf16 NHWC.
+template <bool AF>
+__global__ void lpips_head_bwd_kernel(const uint16_t* __restrict__ o0, const uint16_t* __restrict__ o1,
+                                      const float* __restrict__ lin, const float* __restrict__ upstream /*[N]*/,
+                                      uint16_t* __restrict__ g1, int N, int HW, int C) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp_id = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+    const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+    const size_t total = static_cast<size_t>(N) * HW;
+    for (size_t p = warp_id; p < total; p += nwarps) {
+        const uint16_t* a = o0 + p * C;
+        const uint16_t* b = o1 + p * C;
+        float n0 = 0.f, n1 = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float x0 = a16_to_f<AF>(a[c]), x1 = a16_to_f<AF>(b[c]);
+            n0 = fmaf(x0, x0, n0);
+            n1 = fmaf(x1, x1, n1);
+        }
+        n0 = warp_sum(n0);
+        n1 = warp_sum(n1);
+        const float r = sqrtf(n1);
+        const float i0 = 1.f / (sqrtf(n0) + 1e-10f), q = r + 1e-10f, i1 = 1.f / q;
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float x1 = a16_to_f<AF>(b[c]);
+            const float e = 2.f * lin[c] * (x1 * i1 - a16_to_f<AF>(a[c]) * i0);
+            s = fmaf(e, x1, s);
+        }
+        s = warp_sum(s);
+        const float up = upstream[p / HW] / HW;
+        const float k = (r > 0.f) ? s / (r * q * q) : 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float x1 = a16_to_f<AF>(b[c]);
+            const float e = 2.f * lin[c] * (x1 * i1 - a16_to_f<AF>(a[c]) * i0);
+            g1[p * C + c] = __bfloat16_as_ushort(__float2bfloat16_rn(up * (e * i1 - x1 * k)));
+        }
+    }
+}
+
+}  // namespace aesr

@@ -1,0 +1,384 @@
+// Training-step kernels around the tensor-core convs (all memory-bound or tiny): train-mode BatchNorm forward /
+// backward fused with the pool / upsample that follows it, MSE, the 1-channel head / tail convs' backward, the
+// weight-gradient conv (CUDA-core version), the latent mix backward and the fused Adam update.
+//
+// dtypes: activations A16 = fp16 or bf16 (template flag AF: true = fp16), gradients are ALWAYS bf16 (fp32 range:
+// dL/dx of a mean-reduced loss is ~1e-6..1e-9, below fp16's normal range), reductions / parameters fp32.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "elementwise.cuh"
+
+namespace aesr {
+
+enum BnMode : int { BN_SAME = 0, BN_POOL = 1, BN_UP = 2 };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float bf16_to_f(uint16_t u) { return __uint_as_float(static_cast<uint32_t>(u) << 16); }
+template <bool AF>
+__device__ __forceinline__ float a16_to_f(uint16_t u) {
+    return AF ? __half2float(__ushort_as_half(u)) : bf16_to_f(u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// BatchNorm2d (training) -- networks/acai_vanilla.py:58,90.  The producing conv's epilogue accumulated
+// stats[c] = sum a, stats[C+c] = sum a^2 over the `count` = N*H*W positions of the batch.
+//   scale = gamma / sqrt(var_biased + eps), shift = beta - mean * scale          (normalisation of this pass)
+//   running_mean = (1-m) rm + m mean ; running_var = (1-m) rv + m var * count/(count-1)   (torch semantics)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mean = static_cast<double>(stats[c]) / count;
+    double var = static_cast<double>(stats[C + c]) / count - mean * mean;
+    if (var < 0) var = 0;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = gamma[c] * invstd;
+    scale[c] = sc;
+    shift[c] = beta[c] - static_cast<float>(mean) * sc;
+    mean_out[c] = static_cast<float>(mean);
+    invstd_out[c] = invstd;
+    if (running_mean != nullptr) {
+        const double unbiased = count > 1.f ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    }
+}
+
+// out = pool/up/same( a * scale + shift ): a [N,H,W,C] 16-bit -> out 16-bit.  One thread = 8 channels of one output px.
+template <bool AF>
+__global__ void bn_apply_kernel(const uint16_t* __restrict__ a, const float* __restrict__ scale,
+                                const float* __restrict__ shift, uint16_t* __restrict__ out, int N, int H, int W, int C,
+                                int mode) {
+    const int Ho = mode == BN_POOL ? H / 2 : mode == BN_UP ? 2 * H : H;
+    const int Wo = mode == BN_POOL ? W / 2 : mode == BN_UP ? 2 * W : W;
+    const int groups = C >> 3;
+    const size_t total = static_cast<size_t>(N) * Ho * Wo * groups;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % groups);
+        const size_t pix = i / groups;
+        const int xo = static_cast<int>(pix % Wo), yo = static_cast<int>((pix / Wo) % Ho);
+        const int n = static_cast<int>(pix / (static_cast<size_t>(Wo) * Ho));
+        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int taps = mode == BN_POOL ? 4 : 1;
+        for (int t = 0; t < taps; ++t) {
+            const int yi = mode == BN_POOL ? 2 * yo + (t >> 1) : mode == BN_UP ? (yo >> 1) : yo;
+            const int xi = mode == BN_POOL ? 2 * xo + (t & 1) : mode == BN_UP ? (xo >> 1) : xo;
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(a + ((static_cast<size_t>(n) * H + yi) * W + xi) * C) + g);
+            const uint32_t u[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack2_t<AF>(u[k]);
+                v[2 * k] += f.x;
+                v[2 * k + 1] += f.y;
+            }
+        }
+        const float inv = mode == BN_POOL ? 0.25f : 1.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j] * inv, __ldg(scale + g * 8 + j), __ldg(shift + g * 8 + j));
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(pack2_t<AF>(v[0], v[1]), pack2_t<AF>(v[2], v[3]),
+                                                      pack2_t<AF>(v[4], v[5]), pack2_t<AF>(v[6], v[7]));
+    }
+}
+
+// gradient w.r.t. the BN output at full resolution, derived from the gradient of the pooled / upsampled tensor
+__device__ __forceinline__ float bn_dy_at(const uint16_t* __restrict__ dnext, int mode, int n, int y, int x, int c,
+                                          int H, int W, int C) {
+    if (mode == BN_POOL) {
+        const int Ho = H / 2, Wo = W / 2, yo = y >> 1, xo = x >> 1;
+        if (yo >= Ho || xo >= Wo) return 0.f;        // row / column dropped by the floor of AvgPool2d(2)
+        return 0.25f * bf16_to_f(dnext[((static_cast<size_t>(n) * Ho + yo) * Wo + xo) * C + c]);
+    }
+    if (mode == BN_UP) {
+        const int Wo = 2 * W, Ho = 2 * H;
+        const uint16_t* p = dnext + ((static_cast<size_t>(n) * Ho + 2 * y) * Wo + 2 * x) * C + c;
+        return bf16_to_f(p[0]) + bf16_to_f(p[C]) + bf16_to_f(p[static_cast<size_t>(Wo) * C]) +
+               bf16_to_f(p[static_cast<size_t>(Wo) * C + C]);
+    }
+    return bf16_to_f(dnext[((static_cast<size_t>(n) * H + y) * W + x) * C + c]);
+}
+
+// pass 1: sums[c] += sum dy, sums[C+c] += sum dy * xhat   (xhat = (a - mean) * invstd)
+// block = 256 threads = 8 pixel-rows x 32 channel lanes; each block walks a strip of pixels for a 32-channel group.
+template <bool AF>
+__global__ void bn_bwd_reduce_kernel(const uint16_t* __restrict__ dnext, const uint16_t* __restrict__ a,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     float* __restrict__ sums, int N, int H, int W, int C, int mode) {
+    __shared__ float s1[8][32], s2[8][32];
+    const int c = blockIdx.y * 32 + threadIdx.x;
+    const size_t npix = static_cast<size_t>(N) * H * W;
+    const float mu = mean[c], is = invstd[c];
+    float a1 = 0.f, a2 = 0.f;
+    for (size_t p = blockIdx.x * 8 + threadIdx.y; p < npix; p += static_cast<size_t>(gridDim.x) * 8) {
+        const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+        const int n = static_cast<int>(p / (static_cast<size_t>(W) * H));
+        const float dy = bn_dy_at(dnext, mode, n, y, x, c, H, W, C);
+        const float xh = (a16_to_f<AF>(a[p * C + c]) - mu) * is;
+        a1 += dy;
+        a2 = fmaf(dy, xh, a2);
+    }
+    s1[threadIdx.y][threadIdx.x] = a1;
+    s2[threadIdx.y][threadIdx.x] = a2;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+#pragma unroll
+        for (int r = 1; r < 8; ++r) { a1 += s1[r][threadIdx.x]; a2 += s2[r][threadIdx.x]; }
+        atomicAdd(sums + c, a1);
+        atomicAdd(sums + C + c, a2);
+    }
+}
+
+// pass 2: g = gamma * invstd * (dy - S1/M - xhat * S2/M) * act'(a)   (act = LeakyReLU(slope): a > 0 ? 1 : slope)
+//         dgamma[c] += S2, dbeta[c] += S1 (done once, by block 0)
+template <bool AF>
+__global__ void bn_bwd_apply_kernel(const uint16_t* __restrict__ dnext, const uint16_t* __restrict__ a,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ sums, float count,
+                                    float slope, uint16_t* __restrict__ g_out, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int N, int H, int W, int C, int mode) {
+    const size_t total = static_cast<size_t>(N) * H * W * C;
+    if (blockIdx.x == 0)
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            atomicAdd(dgamma + c, sums[C + c]);
+            atomicAdd(dbeta + c, sums[c]);
+        }
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        const size_t p = i / C;
+        const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+        const int n = static_cast<int>(p / (static_cast<size_t>(W) * H));
+        const float dy = bn_dy_at(dnext, mode, n, y, x, c, H, W, C);
+        const float av = a16_to_f<AF>(a[i]);
+        const float xh = (av - mean[c]) * invstd[c];
+        float g = gamma[c] * invstd[c] * (dy - sums[c] / count - xh * sums[C + c] / count);
+        g *= av > 0.f ? 1.f : slope;
+        g_out[i] = __bfloat16_as_ushort(__float2bfloat16_rn(g));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// MSE (F.mse_loss(reduction='mean'), kwatsch/base_trainer.py:177): loss_acc += sum (a-b)^2 * inv_n (fp32 atomics),
+// optionally d = (a - b) * 2 * inv_n * grad_scale.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void mse_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n, float inv_n,
+                           float* __restrict__ loss_acc, float* __restrict__ d, float grad_scale) {
+    float acc = 0.f;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float diff = a[i] - b[i];
+        acc = fmaf(diff, diff, acc);
+        if (d) d[i] = diff * (2.f * inv_n * grad_scale);
+    }
+    acc = warp_sum(acc);
+    __shared__ float sm[32];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(loss_acc, v * inv_n);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// head (dec.14 + sigmoid) backward.  dlogit = dout * out * (1 - out).
+//   data:   g_in[p][c] = act'(a_in[p][c]) * sum_tap w[tap][c] * dlogit[p - off(tap)]          (bf16 out)
+//   weight: dW[tap][c] += sum_q dlogit[q] * a_in[q + off(tap)][c] ; dbias += sum_q dlogit[q]
+// ---------------------------------------------------------------------------------------------------------------
+template <int C, bool AF>
+__global__ void head_bwd_data_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                     const uint16_t* __restrict__ a_in, const float* __restrict__ w /*[9][C]*/,
+                                     uint16_t* __restrict__ g_in, int N, int H, int W, float slope) {
+    __shared__ float sw[9 * C];
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const size_t total = static_cast<size_t>(N) * H * W;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(i % W), y = static_cast<int>((i / W) % H);
+        const size_t nb = (i / (static_cast<size_t>(W) * H)) * H * W;
+        float dl[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            // forward tap t reads a[q + (t/3-1, t%3-1)]; pixel p receives from q = p - off(t)
+            const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
+            float v = 0.f;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                const size_t q = nb + static_cast<size_t>(yy) * W + xx;
+                const float o = out[q];
+                v = dout[q] * o * (1.f - o);
+            }
+            dl[t] = v;
+        }
+        const uint16_t* ap = a_in + i * C;
+        uint16_t* gp = g_in + i * C;
+#pragma unroll 4
+        for (int c = 0; c < C; ++c) {
+            float s = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) s = fmaf(sw[t * C + c], dl[t], s);
+            s *= a16_to_f<AF>(ap[c]) > 0.f ? 1.f : slope;
+            gp[c] = __bfloat16_as_ushort(__float2bfloat16_rn(s));
+        }
+    }
+}
+
+// one warp handles a strip of pixels; lane = channel (C = 32); 9 tap accumulators per lane.
+template <int C, bool AF>
+__global__ void head_bwd_weight_kernel(const float* __restrict__ dout, const float* __restrict__ out,
+                                       const uint16_t* __restrict__ a_in, float* __restrict__ dw /*[9][C]*/,
+                                       float* __restrict__ dbias, int N, int H, int W) {
+    static_assert(C == 32, "lane == channel");
+    const int lane = threadIdx.x & 31;
+    const size_t warp_id = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+    const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+    const size_t total = static_cast<size_t>(N) * H * W;
+    float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float accb = 0.f;
+    for (size_t q = warp_id; q < total; q += nwarps) {
+        const int x = static_cast<int>(q % W), y = static_cast<int>((q / W) % H);
+        const size_t nb = (q / (static_cast<size_t>(W) * H)) * H * W;
+        const float o = out[q];
+        const float dl = dout[q] * o * (1.f - o);
+        accb += dl;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+                acc[t] = fmaf(dl, a16_to_f<AF>(a_in[(nb + static_cast<size_t>(yy) * W + xx) * C + lane]), acc[t]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) atomicAdd(dw + lane * 9 + t, acc[t]);   // nn.Conv2d layout [1][C][3][3]
+    if (lane == 0) atomicAdd(dbias, accb);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// enc.0 backward: a0[p][c] = w0[c] * xpad[p] + b0[c]  =>  dw0[c] += sum_p g[p][c] * xpad[p], db0[c] += sum_p g[p][c]
+// g bf16 [N,H+2,W+2,C] (C = 32: lane = channel), x fp32 [N,1,H,W].
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void e0_bwd_kernel(const uint16_t* __restrict__ g, const float* __restrict__ x, float* __restrict__ dw,
+                              float* __restrict__ db, int N, int H, int W, int C) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp_id = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
+    const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+    const int Ho = H + 2, Wo = W + 2;
+    const size_t total = static_cast<size_t>(N) * Ho * Wo;
+    float aw = 0.f, ab = 0.f;
+    for (size_t p = warp_id; p < total; p += nwarps) {
+        const int xo = static_cast<int>(p % Wo), yo = static_cast<int>((p / Wo) % Ho);
+        const int n = static_cast<int>(p / (static_cast<size_t>(Wo) * Ho));
+        const int yi = yo - 1, xi = xo - 1;
+        const float xv = (yi >= 0 && yi < H && xi >= 0 && xi < W) ? x[(static_cast<size_t>(n) * H + yi) * W + xi] : 0.f;
+        const float gv = bf16_to_f(g[p * C + lane]);
+        aw = fmaf(gv, xv, aw);
+        ab += gv;
+    }
+    atomicAdd(dw + lane, aw);
+    atomicAdd(db + lane, ab);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradient of a 3x3 / pad 1 conv (CUDA cores, fp32 accumulate):
+//   dW[co][ci][tap] += sum_{n,y,x} g[n,y,x,co] * X[n, y+dy-1, x+dx-1, ci] ;  dbias[co] += sum g
+// g bf16 [N,H,W,Cout], X 16-bit [N,H,W,Cin].  Block = (32 ci) x (8 co groups): thread (tx, ty) owns input channel
+// ci0 + tx and the CO_PER output channels co0 + ty*CO_PER ..; it walks a strip of pixels with 9 taps in registers.
+// grid = (pixel strips, Cin/32, Cout/(8*CO_PER)); partial sums are atomically added to dW (fp32).
+// ---------------------------------------------------------------------------------------------------------------
+template <bool AF, int CO_PER>
+__global__ void __launch_bounds__(256)
+wgrad3x3_kernel(const uint16_t* __restrict__ g, const uint16_t* __restrict__ X, float* __restrict__ dW,
+                float* __restrict__ dbias, int N, int H, int W, int Cin, int Cout) {
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int ci = blockIdx.y * 32 + tx;
+    const int co0 = (blockIdx.z * 8 + ty) * CO_PER;
+    const size_t npix = static_cast<size_t>(N) * H * W;
+    float acc[CO_PER][9];
+    float accb[CO_PER];
+#pragma unroll
+    for (int j = 0; j < CO_PER; ++j) {
+        accb[j] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[j][t] = 0.f;
+    }
+    for (size_t p = blockIdx.x; p < npix; p += gridDim.x) {
+        const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+        const size_t nb = (p / (static_cast<size_t>(W) * H)) * H * W;
+        float gv[CO_PER];
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < CO_PER; ++j) {
+            gv[j] = bf16_to_f(__ldg(g + p * Cout + co0 + j));      // warp-uniform address: broadcast
+            accb[j] += gv[j];
+            any |= gv[j] != 0.f;
+        }
+        if (!any) continue;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+            const float xv = a16_to_f<AF>(__ldg(X + (nb + static_cast<size_t>(yy) * W + xx) * Cin + ci));
+#pragma unroll
+            for (int j = 0; j < CO_PER; ++j) acc[j][t] = fmaf(gv[j], xv, acc[j][t]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CO_PER; ++j) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) atomicAdd(dW + (static_cast<size_t>(co0 + j) * Cin + ci) * 9 + t, acc[j][t]);
+        if (blockIdx.y == 0 && tx == 0 && dbias) atomicAdd(dbias + co0 + j, accb[j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// latent-mix backward (kwatsch/cardiac/trainer_ae.py:173 / brain :265-266): z_mix[b] = wa[b] z[b] + wb[b] z[B+b]
+//   g_z[b]   = g_dec[b]   + wa[b] * g_mix[b]
+//   g_z[B+b] = g_dec[B+b] + wb[b] * g_mix[b]          all bf16 NHWC [., HW*C]
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void mix_bwd_kernel(const uint16_t* __restrict__ g_dec, const uint16_t* __restrict__ g_mix,
+                               const float* __restrict__ wa, const float* __restrict__ wb, uint16_t* __restrict__ g_z,
+                               int B, size_t per_image) {
+    const size_t total = 2 * static_cast<size_t>(B) * per_image;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int n = static_cast<int>(i / per_image);
+        const size_t r = i - static_cast<size_t>(n) * per_image;
+        const int b = n < B ? n : n - B;
+        const float w = n < B ? wa[b] : wb[b];
+        const float v = bf16_to_f(g_dec[i]) + w * bf16_to_f(g_mix[static_cast<size_t>(b) * per_image + r]);
+        g_z[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused Adam over flat fp32 buffers (torch.optim.Adam semantics, kwatsch/trainer_ae.py:29-30: L2-in-grad weight decay)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
+                            float bc1, float bc2_sqrt) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float gi = g[i];
+        const float pi = p[i];
+        if (wd != 0.f) gi = fmaf(wd, pi, gi);
+        const float mi = m[i] + (gi - m[i]) * (1.f - b1);          // exp_avg.lerp_(grad, 1 - beta1)
+        const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = pi - (lr / bc1) * (mi / denom);
+    }
+}
+
+}  // namespace aesr

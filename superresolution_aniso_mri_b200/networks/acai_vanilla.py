@@ -111,6 +111,9 @@ class _PackedCache:
     def __init__(self):
         self._store = {}
 
+    def clear(self):
+        self._store = {}
+
     def get(self, key, tensors, build):
         ver = tuple((t.data_ptr(), t._version) for t in tensors)
         hit = self._store.get(key)
@@ -148,19 +151,38 @@ class VanillaACAI(nn.Module):
     def forward(self, img):
         return self.decode(self.encode(img))
 
+    def _train_forward(self):
+        """Forward-only train-mode helper (batch-statistics BN, running stats updated).  Gradients are never built by
+        autograd here: optimisation goes through ``training.engine.TrainEngine.step`` (the trainers' ``train()``)."""
+        if getattr(self, "_tf", None) is None:
+            from ..training.engine import TrainForward
+            self._tf = TrainForward(self)
+        self._tf._pack_all()
+        return self._tf
+
+    def invalidate_cache(self):
+        """Parameters / BN buffers were updated in place by our kernels (no torch version bump): drop derived tensors."""
+        self._cache.clear()
+
+    @torch.no_grad()
     def encode(self, img):
-        if self.training and torch.is_grad_enabled():
-            from ..training import autograd_net
-            return autograd_net.encode_train(self, img)
         if self.training:
-            from ..training import autograd_net
-            return autograd_net.encode_train(self, img, need_grad=False)
+            z, _, _ = self._train_forward().encode_train(img.detach().float().contiguous(), save=False)
+            self.invalidate_cache()
+            return z
         return self.encode_eval(img)
 
+    @torch.no_grad()
     def decode(self, z):
         if self.training:
-            from ..training import autograd_net
-            return autograd_net.decode_train(self, z, need_grad=torch.is_grad_enabled())
+            z = z.detach().float().contiguous()
+            m = z.shape[0]
+            idx = torch.arange(m, dtype=torch.int32, device=z.device)
+            one = torch.ones(m, dtype=torch.float32, device=z.device)
+            z16 = ops.lerp_latents(z, idx, torch.full_like(idx, -1), one, one)
+            out, _ = self._train_forward().decode_train(z16, save=False)
+            self.invalidate_cache()
+            return out
         return self.decode_eval(z)
 
     # ------------------------------------------------------------------ eval-mode (inference) pipelines
@@ -179,7 +201,7 @@ class VanillaACAI(nn.Module):
         def build():
             with torch.no_grad():
                 return (conv.weight.detach()[0].permute(1, 2, 0).reshape(9, -1).contiguous().float(),
-                        float(conv.bias.detach()[0]))
+                        conv.bias.detach().float().contiguous())
         return self._cache.get(("head", id(conv)), [conv.weight, conv.bias], build)
 
     @torch.no_grad()

@@ -133,7 +133,7 @@ def e0(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, dtype: Optional[torch.
     return out
 
 
-def head(a: torch.Tensor, w9c: torch.Tensor, bias: float, out: Optional[torch.Tensor] = None,
+def head(a: torch.Tensor, w9c: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None,
          out_image_stride: Optional[int] = None, sigmoid: bool = True,
          out_index: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dec.14 + sigmoid: NHWC 16-bit [N,H,W,32] -> fp32 [N,1,H,W] (or image n -> out[out_index[n]])."""
@@ -143,7 +143,7 @@ def head(a: torch.Tensor, w9c: torch.Tensor, bias: float, out: Optional[torch.Te
         out = torch.empty((n, 1, h, w), dtype=torch.float32, device=a.device)
         out_image_stride = h * w
     with _timed("head", 2.0 * n * h * w * 9 * c):
-        _lib.check(lib.aesr_head_fwd(a.data_ptr(), w9c.data_ptr(), float(bias), out.data_ptr(), _ptr(out_index), n, h,
+        _lib.check(lib.aesr_head_fwd(a.data_ptr(), w9c.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(out_index), n, h,
                                      w, c, int(out_image_stride), int(sigmoid), dt_code(a.dtype), _stream(a)),
                    "head_fwd")
     return out

@@ -1,0 +1,287 @@
+"""Fused training step of the ae_combined autoencoder on the sm_100a kernels.
+
+One call = what ``AETrainerEndToEnd.train`` / ``AETrainerExtension1Brain.train`` do between ``x = batch['image']`` and
+``opt_ae.step()`` (kwatsch/cardiac/trainer_ae.py:10-36, kwatsch/brain/trainer_ae.py:92-118):
+
+    z      = enc(x)                    [2B]   train-mode BN (batch statistics, running stats updated)
+    out    = dec(z)                    [2B]
+    z_mix  = wa * z[:B] + wb * z[B:]   [B]    (0.5/0.5 cardiac, per-sample alphas brain)
+    s_mix  = dec(z_mix)                [B]    second decoder pass, its own BN statistics
+    z_ref  = enc(slice_between)        [B]    logged latent MSE only -- but it does update BN running stats
+    loss   = MSE(out, x) + w * mean_b LPIPS(slice_between, s_mix)
+    backward (dgrad + wgrad for the AE, dgrad only through VGG), Adam.
+
+No autograd: forward saves exactly the tensors the hand-written backward needs.  Parameters, gradients and Adam
+moments live in flat fp32 buffers (parameters are views), so the optimizer is ONE kernel and data-parallel training is
+ONE (two, overlapped) NCCL all-reduce(s) of the flat gradient buffer.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import ops, ops_train as T
+from ..networks.acai_vanilla import BatchNormHolder, ConvHolder, VanillaACAI
+
+SLOPE = 0.01
+
+
+class _ConvRec:
+    __slots__ = ("conv", "x_in", "prev", "bn")
+
+    def __init__(self, conv, x_in, prev, bn=None):
+        self.conv, self.x_in, self.prev, self.bn = conv, x_in, prev, bn
+
+
+class _BnRec:
+    __slots__ = ("bn", "a", "mean", "invstd", "mode")
+
+    def __init__(self, bn, a, mean, invstd, mode):
+        self.bn, self.a, self.mean, self.invstd, self.mode = bn, a, mean, invstd, mode
+
+
+class TrainForward:
+    """Train-mode (batch-statistics BatchNorm) forward passes; also what ``VanillaACAI.encode/decode`` run when the
+    module is in ``.train()`` mode outside the fused step (e.g. ``BaseTrainer.encode(x, eval=False)``)."""
+
+    def __init__(self, model: VanillaACAI, sync_bn: bool = False):
+        self.model = model
+        self.sync_bn = sync_bn
+        self.dev = next(model.parameters()).device
+        self.dtype = ops.DEFAULT_DTYPE
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.w_fwd, self.w_bwd = {}, {}
+
+
+class TrainEngine(TrainForward):
+    def __init__(self, model: VanillaACAI, optimizer: Optional[torch.optim.Adam] = None, sync_bn: bool = False):
+        super().__init__(model, sync_bn)
+        self.opt = optimizer
+        self.params = [p for p in model.parameters()]
+        self.step_count = 0
+        self._flatten()
+
+    # ------------------------------------------------------------------ flat parameter / gradient / moment buffers
+    def _flatten(self):
+        n = sum(p.numel() for p in self.params)
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=self.dev)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        self.flat_m = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        self.flat_v = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        self.grad: Dict[int, torch.Tensor] = {}
+        off = 0
+        self.offsets = []
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[off:off + k].view(p.shape)
+                self.grad[id(p)] = self.flat_g[off:off + k].view(p.shape)
+                self.offsets.append((off, k))
+                off += k
+        enc_params = sum(p.numel() for p in self.model.enc.parameters())
+        self.enc_numel = enc_params              # encoder parameters come first (module order)
+        self._bind_optimizer_state(adopt=True)
+
+    def _bind_optimizer_state(self, adopt: bool):
+        """Make opt.state[p]['exp_avg' / 'exp_avg_sq'] views of the flat moment buffers so that
+        ``opt.state_dict()`` stays a stock Adam state_dict (checkpoint layout of kwatsch/base_trainer.py:353-356)."""
+        if self.opt is None:
+            return
+        for p, (off, k) in zip(self.params, self.offsets):
+            st = self.opt.state[p]
+            if adopt and "exp_avg" in st:       # state loaded from a checkpoint: copy it into the flat buffers
+                self.flat_m[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                self.flat_v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                self.step_count = int(st["step"]) if "step" in st else self.step_count
+            st["exp_avg"] = self.flat_m[off:off + k].view(p.shape)
+            st["exp_avg_sq"] = self.flat_v[off:off + k].view(p.shape)
+            st["step"] = torch.tensor(float(self.step_count))
+
+    def reload_optimizer_state(self):
+        """Call after ``opt.load_state_dict`` (BaseTrainer.load)."""
+        self._bind_optimizer_state(adopt=True)
+
+    # ------------------------------------------------------------------ per-step derived tensors
+    def _pack_all(self):
+        self.w_fwd, self.w_bwd = {}, {}
+        for seq in (self.model.enc, self.model.dec):
+            for m in seq:
+                if isinstance(m, ConvHolder) and m.kernel_size == 3 and m.out_channels > 1:
+                    self.w_fwd[id(m)] = ops.pack_conv3x3_weight(m.weight, dtype=self.dtype)
+                    self.w_bwd[id(m)] = ops.pack_conv3x3_weight(m.weight, transpose_flip=True, dtype=T.GRAD_DTYPE)
+
+    def _bn_train(self, bn: BatchNormHolder, stats: torch.Tensor, count: int, update_running: bool = True):
+        if self.sync_bn and self.world > 1:
+            dist.all_reduce(stats)
+            count *= self.world
+        out = T.bn_finalize(stats, count, bn.weight, bn.bias, bn.running_mean if update_running else None,
+                            bn.running_var if update_running else None, bn.momentum, bn.eps)
+        if update_running:
+            bn.num_batches_tracked += 1
+        return out
+
+    # ------------------------------------------------------------------ forward passes (train mode)
+    def encode_train(self, x: torch.Tensor, save: bool = True):
+        enc, sc = self.model.enc, self.model.scales
+        n = x.shape[0]
+        recs: List[_ConvRec] = []
+        a = ops.e0(x, enc[0].weight.reshape(-1), enc[0].bias, dtype=self.dtype)
+        prev = "e0"
+        i = 1
+        for _ in range(sc):
+            c1, c2, bn = enc[i], enc[i + 2], enc[i + 4]
+            recs.append(_ConvRec(c1, a, prev))
+            a1 = ops.conv3x3(a, self.w_fwd[id(c1)], c1.bias, act=ops.ACT_LEAKY)
+            stats = torch.zeros(2 * c2.out_channels, dtype=torch.float32, device=self.dev)
+            a2 = ops.conv3x3(a1, self.w_fwd[id(c2)], c2.bias, act=ops.ACT_LEAKY, stats=stats)
+            scale, shift, mean, invstd = self._bn_train(bn, stats, n * a2.shape[1] * a2.shape[2])
+            a = T.bn_apply(a2, scale, shift, T.BN_POOL)
+            recs.append(_ConvRec(c2, a1, "leaky", _BnRec(bn, a2, mean, invstd, T.BN_POOL)))
+            prev = "bn"
+            i += 6
+        c1, c2 = enc[i], enc[i + 2]
+        recs.append(_ConvRec(c1, a, prev))
+        a1 = ops.conv3x3(a, self.w_fwd[id(c1)], c1.bias, act=ops.ACT_LEAKY)
+        recs.append(_ConvRec(c2, a1, "leaky"))
+        z, z16 = ops.conv3x3(a1, self.w_fwd[id(c2)], c2.bias, act=ops.ACT_NONE, out_mode=ops.OUT_NCHW_F32,
+                             want_out2=True)
+        return z, z16, (recs if save else None)
+
+    def decode_train(self, z16: torch.Tensor, save: bool = True):
+        dec, sc = self.model.dec, self.model.scales
+        n = z16.shape[0]
+        recs: List[_ConvRec] = []
+        a, prev = z16, "latent"
+        i = 0
+        for _ in range(sc):
+            c1, c2, bn = dec[i], dec[i + 2], dec[i + 4]
+            recs.append(_ConvRec(c1, a, prev))
+            a1 = ops.conv3x3(a, self.w_fwd[id(c1)], c1.bias, act=ops.ACT_LEAKY)
+            stats = torch.zeros(2 * c2.out_channels, dtype=torch.float32, device=self.dev)
+            a2 = ops.conv3x3(a1, self.w_fwd[id(c2)], c2.bias, act=ops.ACT_LEAKY, stats=stats)
+            scale, shift, mean, invstd = self._bn_train(bn, stats, n * a2.shape[1] * a2.shape[2])
+            a = T.bn_apply(a2, scale, shift, T.BN_UP)
+            recs.append(_ConvRec(c2, a1, "leaky", _BnRec(bn, a2, mean, invstd, T.BN_UP)))
+            prev = "bn"
+            i += 6
+        c1, head = dec[i], dec[i + 2]
+        recs.append(_ConvRec(c1, a, prev))
+        a1 = ops.conv3x3(a, self.w_fwd[id(c1)], c1.bias, act=ops.ACT_LEAKY)
+        w9c, hb = self.model._head_w(head)
+        out = ops.head(a1, w9c, hb, sigmoid=True)
+        return out, ((recs, a1, out, head, w9c) if save else None)
+
+    # ------------------------------------------------------------------ backward passes
+    def _backward_convs(self, recs: List[_ConvRec], g: torch.Tensor, x_img: Optional[torch.Tensor] = None):
+        """g: bf16 gradient w.r.t. the LAST conv's pre-activation output.  Returns the gradient w.r.t. the stage input
+        (latent for the decoder, nothing for the encoder whose first op is enc.0)."""
+        for k in range(len(recs) - 1, -1, -1):
+            r = recs[k]
+            T.wgrad3x3(g, r.x_in, self.grad[id(r.conv.weight)], self.grad[id(r.conv.bias)])
+            wt = self.w_bwd[id(r.conv)]
+            if r.prev == "leaky":
+                prev_rec = recs[k - 1]
+                if prev_rec.bn is not None:
+                    raise AssertionError("a conv fed by a BN'd tensor is tagged 'bn'")
+                g = ops.conv3x3(g, wt, None, mul_src=r.x_in, mul_mode=ops.MUL_LEAKY_GRAD, slope=SLOPE)
+            elif r.prev == "bn":
+                bnrec = recs[k - 1].bn
+                dnext = ops.conv3x3(g, wt, None)
+                g = T.bn_bwd(dnext, bnrec.a, bnrec.mean, bnrec.invstd, bnrec.bn.weight,
+                             self.grad[id(bnrec.bn.weight)], self.grad[id(bnrec.bn.bias)], bnrec.mode, SLOPE)
+            elif r.prev == "e0":
+                d_a0 = ops.conv3x3(g, wt, None)
+                e0 = self.model.enc[0]
+                T.e0_bwd(d_a0, x_img, self.grad[id(e0.weight)].view(-1), self.grad[id(e0.bias)])
+                return None
+            elif r.prev == "latent":
+                return ops.conv3x3(g, wt, None)
+        return None
+
+    def decode_backward(self, ctx, dout: torch.Tensor):
+        recs, a1, out, head, w9c = ctx
+        g = T.head_bwd(dout, out, a1, w9c, self.grad[id(head.weight)].view(-1), self.grad[id(head.bias)], SLOPE)
+        return self._backward_convs(recs, g)
+
+    # ------------------------------------------------------------------ the step
+    @torch.no_grad()
+    def step(self, image: torch.Tensor, slice_between: torch.Tensor, wa: torch.Tensor, wb: torch.Tensor,
+             lpips=None, ex_loss_weight: float = 0.0, combined: bool = True, do_update: bool = True,
+             lr: Optional[float] = None, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+             keep: bool = False) -> dict:
+        m = self.model
+        B = image.shape[0] // 2
+        x = image.detach().float().contiguous()
+        sb = slice_between.detach().float().contiguous()
+        self._pack_all()
+        self.flat_g.zero_()
+        scal = torch.zeros(4, dtype=torch.float32, device=self.dev)      # [mse_recon, latent_mse, spare, spare]
+
+        z, z16, enc_ctx = self.encode_train(x)
+        out, dec_ctx = self.decode_train(z16)
+        dout = T.mse(out, x, scal[0:1], want_grad=True)
+
+        idx = torch.arange(B, dtype=torch.int32, device=self.dev)
+        z16_mix, z_mix = ops.lerp_latents(z, idx, idx + B, wa, wb, want_nchw=True, dtype=self.dtype)
+        val = None
+        if combined:
+            s_mix, mix_ctx = self.decode_train(z16_mix)
+            z_ref, _, _ = self.encode_train(sb, save=False)               # logged only; updates BN running stats
+            T.mse(z_mix, z_ref, scal[1:2])
+            upstream = torch.full((B,), ex_loss_weight / B, dtype=torch.float32, device=self.dev)
+            val, d_smix = lpips.value_and_grad(sb, s_mix, upstream, normalize=True)
+        else:
+            s_mix = None
+            z_ref = m.encode_eval(sb)                                     # AEBaseTrainer: eval-mode encode (no_grad)
+            T.mse(z_mix, z_ref, scal[1:2])
+
+        # ---- backward
+        g_z = self.decode_backward(dec_ctx, dout)                         # [2B,h,w,latent] bf16
+        if combined:
+            g_mix = self.decode_backward(mix_ctx, d_smix)                 # [B,...]
+            g_z = T.mix_bwd(g_z, g_mix, wa, wb)
+        handle_dec = None
+        if self.world > 1:                                                # decoder grads are final: reduce them now
+            handle_dec = dist.all_reduce(self.flat_g[self.enc_numel:], op=dist.ReduceOp.AVG, async_op=True)
+        self._backward_convs(enc_ctx, g_z, x_img=x)
+        if self.world > 1:
+            dist.all_reduce(self.flat_g[:self.enc_numel], op=dist.ReduceOp.AVG)
+            handle_dec.wait()
+
+        if do_update:
+            self.step_count += 1
+            if lr is None:
+                lr = self.opt.param_groups[0]["lr"]
+            T.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr, betas[0], betas[1], eps, weight_decay,
+                        self.step_count)
+            if self.opt is not None:
+                for p in self.params:
+                    self.opt.state[p]["step"] = torch.tensor(float(self.step_count))
+
+        m.invalidate_cache()            # weights / BN buffers changed under the eval-path caches
+        res = {"scalars": scal, "lpips_per_image": val, "B": B, "ex_loss_weight": ex_loss_weight}
+        if keep:
+            res.update(reconstruction=out, s_between_mix=s_mix, z=z, z_mix=z_mix)
+        return res
+
+    @staticmethod
+    def logged_losses(res: dict) -> dict:
+        """One device->host read for all logged scalars (the reference does five .item() syncs per step)."""
+        scal = res["scalars"].tolist()
+        out = {"loss_ae_dist": scal[0], "loss_latent_1": scal[1]}
+        if res["lpips_per_image"] is not None:
+            extra = res["ex_loss_weight"] * float(res["lpips_per_image"].mean().item())
+            out["loss_ae_dist_extra"] = extra
+            out["loss_ae_extra"] = extra
+            out["loss_ae"] = scal[0] + extra
+        else:
+            out["loss_ae"] = scal[0]
+        return out
+
+
+# The forward-only helper shares the pass implementations with the engine (they only touch TrainForward state).
+for _name in ("_pack_all", "_bn_train", "encode_train", "decode_train"):
+    setattr(TrainForward, _name, getattr(TrainEngine, _name))

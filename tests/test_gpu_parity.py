@@ -135,7 +135,8 @@ def test_edge_kernels_e0_head_lerp_place(dev):
     wh, bh = torch.randn(1, 32, 3, 3, generator=g) / 17, 0.3
     out = torch.full((7, 12, 16), -1.0, device=dev)
     idx = torch.tensor([5, 0, 3, 6], dtype=torch.int32, device=dev)
-    ops.head(act.to(dev), wh[0].permute(1, 2, 0).reshape(9, 32).contiguous().to(dev), bh, out=out,
+    ops.head(act.to(dev), wh[0].permute(1, 2, 0).reshape(9, 32).contiguous().to(dev), torch.tensor([bh], device=dev),
+             out=out,
              out_image_stride=12 * 16, out_index=idx)
     ref = torch.sigmoid(F.conv2d(act.float().permute(0, 3, 1, 2), wh, torch.tensor([bh]), padding=1))[:, 0]
     assert (out[idx.long()].cpu() - ref).abs().max().item() < 1e-5

@@ -1,0 +1,158 @@
+"""GPU tier: the fused training step (forward + hand-written backward + Adam on the sm_100a kernels) against the CPU
+oracle (autograd) and the reference's own 200-step loss curve (tests/golden/train_acdc_200.npz, produced by
+``AETrainerEndToEnd.train`` of the unmodified reference on CPU).
+
+Tolerance (BASELINE.json north_star): training loss curves within 1 % over 200 steps.  Gradients are compared per
+parameter tensor by relative L2 error / cosine (activations fp16, gradient tensors bf16, fp32 accumulation)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import aesr_oracle as O
+from oracle.make_golden import acdc_batch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def lins():
+    d = np.load(os.path.join(ROOT, "superresolution_aniso_mri_b200", "data", "lpips_vgg_lin_v0_1.npz"))
+    return [torch.from_numpy(d["lin%d" % i]) for i in range(5)]
+
+
+def vgg_flat(seed=3):
+    return [t for pair in O.init_vgg(seed) for t in pair]
+
+
+def trainer_args(width=128, latent_width=32, dataset="ACDC", **over):
+    from networks.net_config import NetworkConfig
+    a = dict(NetworkConfig("ae_combined", dataset).architecture)
+    a.update(dataset=dataset, model="ae_combined", ae_class="VanillaACAI", width=width, latent_width=latent_width,
+             latent=128, depth=32, lr=1e-5, weight_decay=0.0, epochs=10, device="cuda:0", gpu_ids=[0],
+             ex_loss_weight1=0.05, use_percept_loss=False, use_loss_annealing=False, get_masks=False,
+             epoch_threshold=0, log_tensorboard=False, batch_size=12, _vgg_state=vgg_flat())
+    a.update(over)
+    return a
+
+
+def make_trainer(args, seed=892372):
+    from kwatsch.get_trainer import get_trainer_dynamic
+    torch.manual_seed(seed)
+    return get_trainer_dynamic(args)
+
+
+def test_lpips_forward_and_gradient(cuda_lib, golden):
+    from superresolution_aniso_mri_b200.lpips_b200 import PerceptualLoss
+    dev = torch.device("cuda:0")
+    g = golden("lpips_pins.npz")
+    lp = PerceptualLoss(vgg_state=vgg_flat(), device=dev)
+    gen = torch.Generator().manual_seed(21)
+    a = torch.rand(3, 1, 64, 64, generator=gen)
+    b = (a + 0.1 * torch.randn(3, 1, 64, 64, generator=gen)).clamp(0, 1)
+    got = lp(a.to(dev), b.to(dev), normalize=True).cpu()
+    assert got.shape == (3, 1, 1, 1)
+    np.testing.assert_allclose(got.numpy(), g["lpips"], rtol=2e-3)           # reference PerceptualLoss output
+    syn = b.clone().requires_grad_(True)
+    val = O.lpips_forward(O.init_vgg(3), lins(), syn, a, normalize=True).sum()
+    gref, = torch.autograd.grad(val, syn)
+    _, gg = lp.value_and_grad(a.to(dev), b.to(dev), torch.ones(3, device=dev))
+    rel = (gg.cpu() - gref).norm().item() / gref.norm().item()
+    assert rel < 0.08, rel
+
+
+@pytest.mark.parametrize("kind,brain", [("rnd", False), ("cal", True)])
+def test_step_gradients_match_oracle_autograd(cuda_lib, kind, brain):
+    from superresolution_aniso_mri_b200.lpips_b200 import PerceptualLoss
+    from superresolution_aniso_mri_b200.networks.acai_vanilla import VanillaACAI
+    from superresolution_aniso_mri_b200.training.engine import TrainEngine
+    dev = torch.device("cuda:0")
+    args = O.default_args(64, 16)
+    st = O.init_state(args, seed=892372) if kind == "rnd" else O.calibrated_state(args)
+    margs = dict(args)
+    margs["device"] = "cuda:0"
+    model = VanillaACAI(margs)
+    model.load_state_dict(st)
+    model.train()
+    lp = PerceptualLoss(vgg_state=vgg_flat(), device=dev)
+    eng = TrainEngine(model, None)
+    B = 4
+    img, sb = acdc_batch(0, B=B, size=64)
+    af = torch.tensor([[0.25], [0.5], [0.75], [0.5]]) if brain else None
+    at = (1 - af) if brain else None
+    wa = (af[:, 0] if brain else torch.full((B,), 0.5)).to(dev)
+    wb = (at[:, 0] if brain else torch.full((B,), 0.5)).to(dev)
+    st_o = {k: v.clone() for k, v in st.items()}
+    lg = O.train_step(st_o, args, None, img, sb, O.init_vgg(3), lins(), alpha_from=af, alpha_to=at,
+                      ex_loss_weight=0.05, return_grads=True)
+    res = eng.step(img.to(dev), sb.to(dev), wa, wb, lpips=lp, ex_loss_weight=0.05, do_update=False, keep=True)
+    logs = eng.logged_losses(res)
+    for k in ("loss_ae_dist", "loss_ae_dist_extra", "loss_latent_1", "loss_ae"):
+        assert abs(lg[k] - logs[k]) <= 2e-3 * abs(lg[k]) + 1e-9, (k, lg[k], logs[k])
+    for name, p in model.named_parameters():
+        gr, go = lg["grads"][name], eng.grad[id(p)].cpu()
+        rel = (go - gr).norm().item() / max(gr.norm().item(), 1e-30)
+        cos = torch.nn.functional.cosine_similarity(go.flatten(), gr.flatten(), dim=0).item()
+        assert rel < 0.2 and cos > 0.98, (name, rel, cos)
+    sd = model.state_dict()
+    for k in sd:                                                   # BN running statistics + counters (App. B item 7)
+        if "running" in k:
+            assert torch.allclose(sd[k].cpu(), st_o[k], rtol=2e-3, atol=2e-4), k
+        if "num_batches" in k:
+            assert int(sd[k]) == int(st_o[k]) == int(st[k]) + 2
+
+
+def test_acdc_200_step_loss_curve_within_1_percent(cuda_lib, golden):
+    """BASELINE config 2: B=12, 128x128, MSE + 0.05 LPIPS, Adam lr 1e-5, fixed cycle of 8 synthetic batches."""
+    g = golden("train_acdc_200.npz")
+    tr = make_trainer(trainer_args())
+    assert type(tr).__name__ == "AETrainerEndToEnd"
+    for s in range(200):
+        img, mid = acdc_batch(s % 8)
+        tr.train({"image": img, "slice_between": mid}, keep_predictions=False)
+    for key in ("loss_ae", "loss_ae_dist", "loss_ae_dist_extra"):
+        ours, ref = np.array(tr.losses[key]), g[key]
+        rel = np.abs(ours - ref) / np.abs(ref)
+        print(key, "max rel dev %.4f at step %d, mean %.4f" % (rel.max(), rel.argmax(), rel.mean()))
+        assert rel.max() < 0.01, (key, rel.max(), int(rel.argmax()))
+    assert tr.iters == 201 and int(tr.model.enc[5].num_batches_tracked) == 400
+
+
+def test_trainer_interface_checkpoint_roundtrip_and_validate(cuda_lib, tmp_path):
+    args = trainer_args(width=64, latent_width=16, dataset="dHCP", ex_loss_weight1=0.001, output_dir=str(tmp_path),
+                        dir_models=str(tmp_path))
+    tr = make_trainer(args)
+    assert type(tr).__name__ == "AETrainerExtension1Brain"
+    B = 4
+    img, mid = acdc_batch(1, B=B, size=64)
+    batch = {"image": img, "slice_between": mid, "alpha_from": torch.tensor([[0.25], [0.5], [0.75], [0.5]]),
+             "alpha_to": torch.tensor([[0.75], [0.5], [0.25], [0.5]])}
+    for _ in range(3):
+        tr.train(batch, keep_predictions=True)
+    assert set(tr.losses) >= {"loss_ae", "loss_ae_dist", "loss_ae_extra", "loss_ae_dist_extra", "loss_latent_1"}
+    assert tr.train_predictions["reconstruction"].shape == (2 * B, 1, 64, 64)
+    assert tr.train_predictions["slice_inbetween_mix"].shape == (B, 1, 64, 64)
+    fname = os.path.join(str(tmp_path), "3.models")
+    tr.save_models(fname, 3)
+    ck = torch.load(fname, map_location="cpu")
+    assert set(ck) == {"model_dict_ae", "optimizer_dict_ae", "epoch"}
+    assert set(ck["optimizer_dict_ae"]["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}       # stock Adam state
+    tr2 = make_trainer(dict(args), seed=1)
+    tr2.load(fname)
+    for k, v in tr.model.state_dict().items():
+        assert torch.equal(v, tr2.model.state_dict()[k]), k
+    assert tr2.engine.step_count == tr.engine.step_count == 3                  # Adam state restored into the flat buffers
+    assert torch.equal(tr2.engine.flat_m, tr.engine.flat_m) and torch.equal(tr2.engine.flat_v, tr.engine.flat_v)
+    tr.train(batch, keep_predictions=False)
+    tr2.train(batch, keep_predictions=False)
+    assert abs(tr.losses["loss_ae"][-1] - tr2.losses["loss_ae"][-1]) < 1e-5 * abs(tr.losses["loss_ae"][-1]) + 1e-9
+    # fp32 atomics make the weight-gradient sums order-dependent: allow a fraction of one lr-sized Adam step (1e-5)
+    assert torch.allclose(tr.model.enc[1].weight, tr2.model.enc[1].weight, rtol=0, atol=4e-6)
+    # eval-mode API used by the synthesis loops + validation bookkeeping
+    z = tr.encode(img, eval=True)
+    out = tr.decode(z, eval=True)
+    assert z.shape == (2 * B, 128, 16, 16) and out.shape == (2 * B, 1, 64, 64)
+    val = tr.validate(batch)
+    assert "loss_ae" in val and len(tr.losses_test["loss_ae_dist_extra"]) == 1
+    assert tr.model.training
