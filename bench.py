@@ -241,6 +241,9 @@ def run_ours(a):
         conv_fl = sum(fl for name, e0, e1, fl in ops.TIMING if name == "conv3x3")
         n_conv = sum(1 for t in ops.TIMING if t[0] == "conv3x3")
         all_ms = sum(e0.elapsed_time(e1) for name, e0, e1, fl in ops.TIMING)
+        kernel_ms = {}
+        for name, e0, e1, fl in ops.TIMING:
+            kernel_ms[name] = kernel_ms.get(name, 0.0) + e0.elapsed_time(e1)
         ops.TIMING = None
         ach = conv_fl / (conv_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv3x3_halo_kernel (tcgen05, all %d launches of a step)" % n_conv,
@@ -249,7 +252,9 @@ def run_ours(a):
                 "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" % peaks["source"],
                 "conv_ms_per_step": conv_ms, "all_kernels_ms_per_step": all_ms,
                 "conv_share_of_kernel_time": conv_ms / all_ms if all_ms else None,
-                "algorithmic_gflop_per_step": conv_fl / 1e9}
+                "algorithmic_gflop_per_step": conv_fl / 1e9, "kernel_ms": kernel_ms}
+
+    train = bench_train(a, dev, rank, world, barrier) if a.train else None
 
     if rank == 0:
         cpu_rate, cores, cpu_t = cpu_synthesis_rate(a.cpu_sample, 3)
@@ -270,9 +275,109 @@ def run_ours(a):
                                  "sample": "%d volumes (%d synthesized slices), best of 3, %.2f s; oracle port of "
                                            "generate_hr_volumes.create_super_volume (re-encodes per alpha like the "
                                            "reference)" % (a.cpu_sample, a.cpu_sample * 54, cpu_t)}}
+        if train is not None:
+            line["train"] = train
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+TRAIN_GFLOP_PER_STEP = 573.0      # ACDC B=12 step, reference formulation (2*MAC, convs only)
+
+
+def cpu_train_rate(steps: int = 2):
+    """The reference's train step (AETrainerEndToEnd.train restated in the oracle, autograd + Adam) on all host cores."""
+    from oracle import aesr_oracle as O
+    from oracle.make_golden import acdc_batch
+    torch.set_num_threads(os.cpu_count() or 1)
+    args = O.default_args(SIZE, 32)
+    st = O.init_state(args, seed=892372)
+    vgg = O.init_vgg(3)
+    d = np.load(os.path.join(ROOT, "superresolution_aniso_mri_b200", "data", "lpips_vgg_lin_v0_1.npz"))
+    lins = [torch.from_numpy(d["lin%d" % i]) for i in range(5)]
+    adam = O.AdamState(st, lr=1e-5)
+    img, mid = acdc_batch(0)
+    O.train_step(st, args, adam, img, mid, vgg, lins, ex_loss_weight=0.05)          # warm-up
+    t0 = time.perf_counter()
+    for s in range(steps):
+        O.train_step(st, args, adam, img, mid, vgg, lins, ex_loss_weight=0.05)
+    dt = (time.perf_counter() - t0) / steps
+    return 12.0 / dt, torch.get_num_threads(), dt
+
+
+def bench_train(a, dev, rank, world, barrier):
+    """BASELINE config 2: ACDC training step, B=12 per GPU (image [24,1,128,128] + slice_between [12,1,128,128]),
+    MSE + 0.05 * LPIPS-VGG (seeded random-init VGG16 + shipped lin heads), Adam lr 1e-5; weak scaling, gradients
+    averaged over ranks with NCCL.  samples/s, sample = one (from, to, between) triplet."""
+    import torch.distributed as dist
+    from oracle import aesr_oracle as O
+    from oracle.make_golden import acdc_batch
+    from networks.net_config import NetworkConfig
+    from kwatsch.get_trainer import get_trainer_dynamic
+    from superresolution_aniso_mri_b200 import ops
+    targs = dict(NetworkConfig("ae_combined", "ACDC").architecture)
+    targs.update(dataset="ACDC", model="ae_combined", ae_class="VanillaACAI", width=SIZE, latent_width=32, latent=128,
+                 depth=32, lr=1e-5, weight_decay=0.0, epochs=10, device=str(dev), gpu_ids=[dev.index or 0],
+                 ex_loss_weight1=0.05, use_percept_loss=False, use_loss_annealing=False, get_masks=False,
+                 epoch_threshold=0, log_tensorboard=False, batch_size=12,
+                 _vgg_state=[t for pair in O.init_vgg(3) for t in pair])
+    torch.manual_seed(892372)
+    tr = get_trainer_dynamic(targs)
+    host = [tuple(t.pin_memory() for t in acdc_batch(i + 8 * rank)) for i in range(8)]
+    devb = [(i.to(dev), m.to(dev)) for i, m in host]
+    wa = torch.full((12,), 0.5, device=dev)
+    eng, lp = tr.engine, tr.percept_criterion
+    steps = a.train_steps
+
+    def step_dev(s):
+        img, mid = devb[s % 8]
+        eng.step(img, mid, wa, wa, lpips=lp, ex_loss_weight=0.05, lr=1e-5)
+
+    def step_host(s):
+        img, mid = host[s % 8]
+        tr.train({"image": img, "slice_between": mid}, keep_predictions=False)
+
+    out = {}
+    for name, fn in (("device", step_dev), ("e2e", step_host)):
+        for s in range(3):
+            fn(s)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(steps):
+            fn(s)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        out[name] = float(ms.item())
+    if rank != 0:
+        return None
+    ops.TIMING = []
+    step_dev(0)
+    torch.cuda.synchronize()
+    agg = {}
+    for name, e0, e1, fl in ops.TIMING:
+        agg[name] = agg.get(name, 0.0) + e0.elapsed_time(e1)
+    ops.TIMING = None
+    cpu_rate, cores, cpu_dt = cpu_train_rate(2)
+    ms_step = out["device"] / steps
+    ach = TRAIN_GFLOP_PER_STEP / ms_step          # GFLOP / ms = TFLOP/s
+    peaks = load_peaks()
+    return {"metric": "train_samples_per_sec", "value": world * 12 * steps / (out["device"] * 1e-3), "unit": "samples/s",
+            "steps": steps, "ms_per_step": ms_step, "scaling": "weak", "dtype": "bf16",
+            "config": {"workload": "ACDC training step: B=12/GPU, 128x128, latent 128, MSE + 0.05*LPIPS-VGG, Adam 1e-5; "
+                                   "gradient all-reduce (NCCL, AVG) over ranks"},
+            "e2e": {"value": world * 12 * steps / (out["e2e"] * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": 36 * SIZE * SIZE * 4, "d2h_bytes_per_step": 16 + 48,
+                    "ms_per_step": out["e2e"] / steps},
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "note": "whole step (573 algorithmic GFLOP) over step time", "kernel_ms": agg},
+            "cpu_baseline": {"value": cpu_rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": "2 steps of B=12 after 1 warm-up, %.2f s/step, oracle port of "
+                                       "AETrainerEndToEnd.train (autograd + Adam)" % cpu_dt}}
 
 
 def main():
@@ -285,6 +390,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=256, help="slices per kernel launch")
     ap.add_argument("--groups", type=int, default=4, help="e2e: volume groups pipelined over copy/compute streams")
     ap.add_argument("--cpu-sample", type=int, default=4, dest="cpu_sample")
+    ap.add_argument("--no-train", action="store_false", dest="train", help="skip the training-step measurement")
+    ap.add_argument("--train-steps", type=int, default=30, dest="train_steps")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -98,6 +98,11 @@ int aesr_head_fwd(const void* in, const float* w9c, const float* bias, float* ou
 int aesr_lerp_latents(const float* z, const int* ia, const int* ib, const float* wa, const float* wb, void* out_nhwc,
                       float* out_nchw, int M, int C, int HW, int dtype, void* stream);
 
+/* All K alpha steps of P slice pairs (generate_hr_volumes.py:49-53 loops alphas around the whole encode/lerp/decode;
+ * here the two fp32 latents of a pair are read once): out[p*K+k] = wa[k] * z[pa[p]] + wb[k] * z[pb[p]], NHWC 16-bit. */
+int aesr_lerp_pairs(const float* z, const int* pa, const int* pb, const float* wa, const float* wb, void* out_nhwc,
+                    int P, int K, int C, int HW, int dtype, void* stream);
+
 /* Kept (non-synthesized) slices of the HR volume: dst[out_index[n]] = clamp(src[n], 0, 1)
  * (generate_hr_volumes.py:44,58-67: `recon_volume = images`, the torch.cat chain, the final torch.clamp).
  * src fp32 [N,HW], dst fp32 [*,HW], out_index int32 [N] or NULL (identity).  N <= 65535 per call. */
@@ -131,9 +136,10 @@ int aesr_head_bwd(const float* dout, const float* out, const void* a_in, const f
 /* Backward of enc.0 (1x1 conv, padding 1): dw[C], db[C] accumulated from g bf16 [N,H+2,W+2,C] and x fp32 [N,1,H,W]. */
 int aesr_e0_bwd(const void* g, const float* x, float* dw, float* db, int N, int H, int W, int C, void* stream);
 /* Weight gradient of a 3x3 conv: dW fp32 [Cout,Cin,3,3] += g^T * shifted(x), dbias[Cout] += sum g (dbias may be NULL).
- * g bf16 [N,H,W,Cout], x `dtype` [N,H,W,Cin]. */
+ * g bf16 [N,H,W,Cout], x `dtype` [N,H,W,Cin].  algo: 0 auto, 1 tcgen05 (pixels as the GEMM K dimension, MN-major
+ * operands straight from NHWC, channels in {32,64,128}), 2 CUDA cores. */
 int aesr_wgrad3x3(const void* g, const void* x, float* dW, float* dbias, int N, int H, int W, int Cin, int Cout, int dtype,
-                  void* stream);
+                  int algo, void* stream);
 /* Backward of z_mix[b] = wa[b] z[b] + wb[b] z[B+b]: g_z[2B] = g_dec[2B] + {wa,wb}[b] * g_mix[b] (bf16 NHWC). */
 int aesr_mix_bwd(const void* g_dec, const void* g_mix, const float* wa, const float* wb, void* g_z, int B,
                  size_t per_image, void* stream);

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "aesr_head_fwd": (I, [P, P, P, P, P, I, I, I, I, c_size_t, I, I, P]),
     "aesr_lerp_latents": (I, [P, P, P, P, P, P, P, I, I, I, I, P]),
     "aesr_place_slices": (I, [P, P, P, I, I, I, P]),
+    "aesr_lerp_pairs": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "aesr_probe_halo_conv": (I, [P, P, P, I, I, I, I, I, I, I, I, P]),
     # training step
     "aesr_bn_finalize": (I, [P, F, P, P, P, P, F, F, P, P, P, P, I, P]),
@@ -35,7 +36,7 @@ _SIGNATURES = {
     "aesr_mse": (I, [P, P, c_size_t, P, P, F, P]),
     "aesr_head_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
     "aesr_e0_bwd": (I, [P, P, P, P, I, I, I, I, P]),
-    "aesr_wgrad3x3": (I, [P, P, P, P, I, I, I, I, I, I, P]),
+    "aesr_wgrad3x3": (I, [P, P, P, P, I, I, I, I, I, I, I, P]),
     "aesr_mix_bwd": (I, [P, P, P, P, P, I, c_size_t, P]),
     "aesr_adam_step": (I, [P, P, P, P, c_size_t, F, F, F, F, F, I, P]),
     "aesr_vgg_conv1_fwd": (I, [P, P, P, P, I, I, I, P, P, I, I, P]),

@@ -12,6 +12,7 @@
 #include "lpips_kernels.cuh"
 #include "probe.cuh"
 #include "train_kernels.cuh"
+#include "wgrad_tc.cuh"
 
 using namespace aesr;
 
@@ -323,6 +324,22 @@ int aesr_lerp_latents(const float* z, const int* ia, const int* ib, const float*
     else
         lerp_nchw_to_nhwc_kernel<false><<<grid, block, 0, s>>>(z, ia, ib, wa, wb, static_cast<uint16_t*>(out_nhwc), out_nchw, C, HW);
     return check_launch("lerp_nchw_to_nhwc");
+}
+
+int aesr_lerp_pairs(const float* z, const int* pa, const int* pb, const float* wa, const float* wb, void* out_nhwc,
+                    int P, int K, int C, int HW, int dtype, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!z || !pa || !pb || !wa || !wb || !out_nhwc || C <= 0 || HW <= 0 || K <= 0) return fail(AESR_ERR_INVALID, "lerp_pairs: bad arguments");
+    if (P == 0) return AESR_OK;
+    if (P < 0 || P > 65535) return fail(AESR_ERR_INVALID, "lerp_pairs: P=%d out of range (1..65535 per call)", P);
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, P), block(32, 8);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == AESR_DT_FP16)
+        lerp_pairs_kernel<true><<<grid, block, 0, s>>>(z, pa, pb, wa, wb, static_cast<uint16_t*>(out_nhwc), K, C, HW);
+    else
+        lerp_pairs_kernel<false><<<grid, block, 0, s>>>(z, pa, pb, wa, wb, static_cast<uint16_t*>(out_nhwc), K, C, HW);
+    return check_launch("lerp_pairs");
 }
 
 int aesr_place_slices(const float* src, float* dst, const int* out_index, int N, int HW, int do_clamp, void* stream) {

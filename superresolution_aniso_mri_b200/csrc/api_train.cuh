@@ -106,12 +106,47 @@ int aesr_e0_bwd(const void* g, const float* x, float* dw, float* db, int N, int 
 }
 
 int aesr_wgrad3x3(const void* g, const void* x, float* dW, float* dbias, int N, int H, int W, int Cin, int Cout, int dtype,
-                  void* stream) {
+                  int algo, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!g || !x || !dW || Cin % 32 != 0 || Cout % 32 != 0) return fail(AESR_ERR_INVALID, "wgrad3x3: bad arguments");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t npix = static_cast<size_t>(N) * H * W;
+    const bool tc_ok = Cin <= 128 && Cout <= 128 && (Cin == 32 || Cin % 64 == 0) && (Cout == 32 || Cout % 64 == 0);
+    if (algo == 1 && !tc_ok) return fail(AESR_ERR_INVALID, "wgrad3x3: tensor-core path needs channels in {32,64,128}");
+    if (algo != 2 && tc_ok) {
+        WgradParams p{};
+        p.N = N; p.H = H; p.W = W; p.Cg = Cout; p.Cx = Cin;
+        p.tiles_x = (W + 7) / 8; p.tiles_y = (H + 15) / 16; p.num_tiles = N * p.tiles_x * p.tiles_y;
+        p.taps_per_group = Cin <= 32 ? 9 : Cin <= 64 ? 5 : 3;
+        p.num_groups = (9 + p.taps_per_group - 1) / p.taps_per_group;
+        int per = g_sm_count / p.num_groups;
+        if (per > p.num_tiles) per = p.num_tiles;
+        if (per < 1) per = 1;
+        p.ctas_per_group = per;
+        p.x_fp16 = (dtype == AESR_DT_FP16);
+        p.dW = dW;
+        CUtensorMap tg, tx;
+        rc = make_act_tmap(&tg, g, N, H, W, Cout, Cout < 64 ? 32 : 64, 8, 16);
+        if (rc != AESR_OK) return rc;
+        rc = make_act_tmap(&tx, x, N, H, W, Cin, Cin < 64 ? 32 : 64, 10, 18);
+        if (rc != AESR_OK) return rc;
+        static int configured = 0;
+        rc = set_max_smem(wgrad3x3_tc_kernel, &configured);
+        if (rc != AESR_OK) return rc;
+        wgrad3x3_tc_kernel<<<per * p.num_groups, WG_THREADS, wg_smem_bytes(Cout, Cin), s>>>(tg, tx, p);
+        rc = check_launch("wgrad3x3_tc");
+        if (rc != AESR_OK) return rc;
+        if (dbias) {
+            int gx = static_cast<int>((npix + 255) / 256);
+            const int cap = g_sm_count * 8 / (Cout / 32);
+            if (gx > cap) gx = cap;
+            if (gx < 1) gx = 1;
+            colsum_bf16_kernel<<<dim3(gx, Cout / 32), dim3(32, 8), 0, s>>>(static_cast<const uint16_t*>(g), dbias, npix, Cout);
+            return check_launch("colsum_bf16");
+        }
+        return AESR_OK;
+    }
     constexpr int CO_PER = 4;                       // 8 warps x 4 = 32 output channels per block
     const int gy = Cin / 32, gz = Cout / 32;
     int gx = g_sm_count * 4 / (gy * gz);

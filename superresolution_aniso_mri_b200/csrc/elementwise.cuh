@@ -151,6 +151,42 @@ __global__ void lerp_nchw_to_nhwc_kernel(const float* __restrict__ z, const int*
     }
 }
 
+// All K alpha steps of one slice pair in one pass (volume synthesis): the two fp32 latents are read ONCE and K blended
+// 16-bit NHWC latents are written, out[(p*K + k)] = wa[k] * z[pa[p]] + wb[k] * z[pb[p]]  (same three roundings).
+// Algorithmic bytes per pair: 2 * 4 * C*HW read + K * 2 * C*HW written (vs 8 B read per OUTPUT element unfused).
+template <bool FP16>
+__global__ void lerp_pairs_kernel(const float* __restrict__ z, const int* __restrict__ pa, const int* __restrict__ pb,
+                                  const float* __restrict__ wa, const float* __restrict__ wb,
+                                  uint16_t* __restrict__ out_nhwc, int K, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int p = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float* za = z + static_cast<size_t>(pa[p]) * C * HW;
+    const float* zb = z + static_cast<size_t>(pb[p]) * C * HW;
+    float va[4], vb[4];                              // blockDim.y == 8: 4 channel rows per thread
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int c = c0 + threadIdx.y + 8 * r, px = p0 + threadIdx.x;
+        const bool ok = c < C && px < HW;
+        va[r] = ok ? za[static_cast<size_t>(c) * HW + px] : 0.f;
+        vb[r] = ok ? zb[static_cast<size_t>(c) * HW + px] : 0.f;
+    }
+    for (int k = 0; k < K; ++k) {
+        const float fa = wa[k], fb = wb[k];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            tile[threadIdx.y + 8 * r][threadIdx.x] = __fadd_rn(__fmul_rn(fa, va[r]), __fmul_rn(fb, vb[r]));
+        __syncthreads();
+        uint16_t* o = out_nhwc + (static_cast<size_t>(p) * K + k) * HW * C;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int px = p0 + threadIdx.y + 8 * r, c = c0 + threadIdx.x;
+            if (px < HW && c < C) o[static_cast<size_t>(px) * C + c] = cvt16_t<FP16>(tile[threadIdx.x][threadIdx.y + 8 * r]);
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // kept (original) slices of the HR volume: dst[out_index[n]] = clamp(src[n], 0, 1)   (generate_hr_volumes.py:44,58-67)
 // fp32 images of HW pixels, float4 vectorised when HW % 4 == 0.

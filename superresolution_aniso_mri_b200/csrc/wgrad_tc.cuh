@@ -1,0 +1,193 @@
+// Weight gradient of the 3x3 / pad-1 conv on the tensor cores (tcgen05 + TMEM), pixels as the GEMM K dimension:
+//
+//     dW[co][ci][tap] = sum_{n,y,x} g[n,y,x,co] * X[n, y+dy-1, x+dx-1, ci]
+//
+// Both operands are NHWC, i.e. [pixel][channel] = "MN-major" for the MMA (channels contiguous, K = pixels strided by
+// one row): A = g tile (128 pixels x Cout), B = X halo (18x10 pixels x Cin) seen through a descriptor shifted by the
+// tap offset -- the same halo trick as the forward kernel, with the 8-pixel K groups strided by the halo pitch.  TMA
+// zero-fills out-of-image pixels of both operands (= the conv's zero padding / ragged tile edges).
+// A CTA walks its share of the pixel tiles and keeps accumulating into the SAME TMEM columns (one N-wide accumulator
+// per tap of its tap group); only at the very end the 4 epilogue warps add the partial dW to global memory with fp32
+// atomics.  M is always 128: for Cout < 128 the A descriptor's MN-block stride (LBO) is 0, so TMEM lanes >= Cout hold
+// duplicates that are simply not read back.
+#pragma once
+#include "common.cuh"
+
+namespace aesr {
+
+struct WgradParams {
+    int N, H, W, Cg, Cx;          // g: [N,H,W,Cg] bf16 (Cg = Cout), x: [N,H,W,Cx] 16-bit (Cx = Cin)
+    int tiles_x, tiles_y, num_tiles;
+    int taps_per_group, num_groups;
+    int ctas_per_group;
+    int x_fp16;                   // x operand format: 1 fp16, 0 bf16 (g is always bf16)
+    float* dW;                    // [Cg][Cx][9] fp32, accumulated
+};
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_STAGES = 2;
+
+__host__ __device__ constexpr int wg_g_chunk_bytes(int Cg) { return 128 * (Cg < 64 ? Cg : 64) * 2; }
+__host__ __device__ constexpr int wg_x_chunk_bytes(int Cx) {
+    return ((18 * 10 * (Cx < 64 ? Cx : 64) * 2 + 1023) / 1024) * 1024;
+}
+__host__ __device__ constexpr int wg_stage_bytes(int Cg, int Cx) {
+    return wg_g_chunk_bytes(Cg) * ((Cg + 63) / 64) + wg_x_chunk_bytes(Cx) * ((Cx + 63) / 64);
+}
+__host__ __device__ constexpr int wg_smem_bytes(int Cg, int Cx) { return 1024 + WG_STAGES * wg_stage_bytes(Cg, Cx) + 256; }
+
+// MN-major shared-memory descriptor: LBO = stride between 64-element (swizzle-row) blocks along M/N,
+// SBO = stride between groups of 8 K-rows.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                      uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(layout_type & 0x7) << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_constant__ CUtensorMap tmap_x,
+                   const WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int gKC = p.Cg < 64 ? p.Cg : 64, xKC = p.Cx < 64 ? p.Cx : 64;
+    const int g_chunks = (p.Cg + 63) / 64, x_chunks = (p.Cx + 63) / 64;
+    const int g_chunk_bytes = wg_g_chunk_bytes(p.Cg), x_chunk_bytes = wg_x_chunk_bytes(p.Cx);
+    const int g_bytes = g_chunk_bytes * g_chunks;
+    const int stage_bytes = wg_stage_bytes(p.Cg, p.Cx);
+    uint8_t* tail = smem + WG_STAGES * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* empty_bar = full_bar + WG_STAGES;
+    uint64_t* done_bar = empty_bar + WG_STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NN = p.Cx;                                   // MMA N (<= 128)
+    const int ncols = p.taps_per_group * NN;
+    const uint32_t tmem_cols = ncols <= 32 ? 32 : ncols <= 64 ? 64 : ncols <= 128 ? 128 : ncols <= 256 ? 256 : 512;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_g);
+        tma_prefetch_desc(&tmap_x);
+        for (int s = 0; s < WG_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(done_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_ptr, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int group = blockIdx.x / p.ctas_per_group;
+    const int first = blockIdx.x - group * p.ctas_per_group;
+    const int tap0 = group * p.taps_per_group;
+    const int ntaps = (9 - tap0) < p.taps_per_group ? (9 - tap0) : p.taps_per_group;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = first; t < p.num_tiles; t += p.ctas_per_group) {
+                const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+                const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* base = smem + stage * stage_bytes;
+                mbar_arrive_expect_tx(&full_bar[stage], 128 * p.Cg * 2 + 180 * p.Cx * 2);
+                for (int c = 0; c < g_chunks; ++c)
+                    tma_load_4d(base + c * g_chunk_bytes, &tmap_g, &full_bar[stage], c * 64, x0, y0, n);
+                for (int c = 0; c < x_chunks; ++c)
+                    tma_load_4d(base + g_bytes + c * x_chunk_bytes, &tmap_x, &full_bar[stage], c * 64, x0 - 1, y0 - 1, n);
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // idesc: D f32, A = bf16 (g), B = x format, both MN-major, M = 128, N = Cx
+            const uint32_t bfmt = p.x_fp16 ? 0u : 1u;
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (bfmt << 10) | (1u << 15) | (1u << 16) |
+                                   ((static_cast<uint32_t>(NN) >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t a_layout = gKC == 64 ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
+            const uint32_t b_layout = xKC == 64 ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
+            const uint32_t a_row = gKC * 2, b_row = xKC * 2;
+            const uint32_t a_lbo = g_chunks > 1 ? g_chunk_bytes : 0;     // Cout < 128: duplicate the block (rows unused)
+            const uint32_t b_lbo = x_chunks > 1 ? x_chunk_bytes : 0;
+            int stage = 0;
+            uint32_t phase = 0;
+            bool first_tile = true;
+            for (int t = first; t < p.num_tiles; t += p.ctas_per_group) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
+                const uint32_t b_base = a_base + g_bytes;
+                for (int tl = 0; tl < ntaps; ++tl) {
+                    const int tap = tap0 + tl, dy = tap / 3, dx = tap - dy * 3;
+                    for (int ks = 0; ks < 8; ++ks) {                     // K = 128 pixels = 8 x 16
+                        const uint64_t a_desc = make_smem_desc_mn(a_base + ks * 16 * a_row, a_lbo, 8 * a_row, a_layout);
+                        const uint64_t b_desc = make_smem_desc_mn(
+                            b_base + ((2 * ks + dy) * 10 + dx) * b_row, b_lbo, 10 * b_row, b_layout);
+                        umma_f16(tmem_base + tl * NN, a_desc, b_desc, idesc, (first_tile && ks == 0) ? 0u : 1u);
+                    }
+                }
+                umma_commit(&empty_bar[stage]);
+                first_tile = false;
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(done_bar);
+        }
+    } else {
+        // final epilogue: TMEM lane = output channel co, columns = [tap][ci]
+        mbar_wait(done_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int co = q * 32 + lane;
+        const bool has_tiles = first < p.num_tiles;
+        if (has_tiles) {
+            for (int tl = 0; tl < ntaps; ++tl) {
+                for (int c0 = 0; c0 < NN; c0 += 32) {
+                    uint32_t raw[32];
+                    tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tl * NN + c0, raw);
+                    tmem_ld_wait();
+                    if (co < p.Cg) {
+                        float* dst = p.dW + (static_cast<size_t>(co) * p.Cx + c0) * 9 + (tap0 + tl);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) atomicAdd(dst + j * 9, __uint_as_float(raw[j]));
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// dbias[c] += sum over pixels of g[p][c]  (g bf16 [P][C]); block = 32 channel lanes x 8 pixel rows.
+__global__ void colsum_bf16_kernel(const uint16_t* __restrict__ g, float* __restrict__ out, size_t P, int C) {
+    __shared__ float s[8][32];
+    const int c = blockIdx.y * 32 + threadIdx.x;
+    float acc = 0.f;
+    for (size_t p = blockIdx.x * 8 + threadIdx.y; p < P; p += static_cast<size_t>(gridDim.x) * 8)
+        acc += __uint_as_float(static_cast<uint32_t>(g[p * C + c]) << 16);
+    s[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+#pragma unroll
+        for (int r = 1; r < 8; ++r) acc += s[r][threadIdx.x];
+        atomicAdd(out + c, acc);
+    }
+}
+
+}  // namespace aesr

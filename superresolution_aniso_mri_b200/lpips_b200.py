@@ -48,7 +48,7 @@ class PerceptualLoss(nn.Module):
     """Same constructor / forward signature as the reference class; ``model='net-lin', net='vgg'`` only."""
 
     def __init__(self, model="net-lin", net="vgg", colorspace="rgb", spatial=False, use_gpu=True, gpu_ids=[0],
-                 vgg_state: Optional[List[torch.Tensor]] = None, device=None):
+                 vgg_state: Optional[List[torch.Tensor]] = None, device=None, act_dtype=None):
         super().__init__()
         if model != "net-lin" or net not in ("vgg", "vgg16") or spatial:
             raise NotImplementedError("aesr_b200 LPIPS: only model='net-lin', net='vgg', spatial=False are on the hot "
@@ -60,7 +60,7 @@ class PerceptualLoss(nn.Module):
         lins = np.load(_DATA)
         self.lins = nn.ParameterList([nn.Parameter(torch.from_numpy(lins["lin%d" % k]).reshape(-1).to(dev),
                                                    requires_grad=False) for k in range(5)])
-        self.dtype = ops.DEFAULT_DTYPE
+        self.dtype = act_dtype or ops.DEFAULT_DTYPE
         self._fwd_packed = None
         self._bwd_packed = None
 

@@ -171,6 +171,26 @@ def lerp_latents(z: torch.Tensor, ia: torch.Tensor, ib: torch.Tensor, wa: torch.
     return (out, out_nchw) if want_nchw else out
 
 
+def lerp_pairs(z: torch.Tensor, pa: torch.Tensor, pb: torch.Tensor, wa: torch.Tensor, wb: torch.Tensor,
+               dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """out[p*K + k] = wa[k]*z[pa[p]] + wb[k]*z[pb[p]]; z fp32 NCHW -> NHWC 16-bit [P*K,h,w,C] (latents read once)."""
+    lib = _dev(z)
+    dtype = dtype or DEFAULT_DTYPE
+    assert z.dtype == torch.float32 and z.is_contiguous() and z.dim() == 4
+    _, c, h, w = z.shape
+    p, k = pa.numel(), wa.numel()
+    out = torch.empty((p * k, h, w, c), dtype=dtype, device=z.device)
+    with _timed("lerp"):
+        done = 0
+        while done < p:
+            cnt = min(p - done, 65535)
+            _lib.check(lib.aesr_lerp_pairs(z.data_ptr(), pa[done:].data_ptr(), pb[done:].data_ptr(), wa.data_ptr(),
+                                           wb.data_ptr(), out[done * k:].data_ptr(), cnt, k, c, h * w, dt_code(dtype),
+                                           _stream(z)), "lerp_pairs")
+            done += cnt
+    return out
+
+
 def place_slices(src: torch.Tensor, dst: torch.Tensor, out_index: Optional[torch.Tensor], clamp: bool = True) -> None:
     """dst[out_index[n]] = clamp(src[n], 0, 1) for fp32 images; src [N,HW...] contiguous, dst [*,HW...] contiguous."""
     lib = _dev(src)

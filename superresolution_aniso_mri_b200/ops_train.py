@@ -78,7 +78,10 @@ def e0_bwd(g, x, dw, db):
                                _stream(g)), "e0_bwd")
 
 
-def wgrad3x3(g, x, dW, dbias: Optional[torch.Tensor]):
+WGRAD_ALGO = 0          # 0 auto (tensor cores when the channel counts allow), 1 tcgen05, 2 CUDA cores
+
+
+def wgrad3x3(g, x, dW, dbias: Optional[torch.Tensor], algo: Optional[int] = None):
     """dW [Cout,Cin,3,3] fp32 += ..., dbias [Cout] += ...; g bf16 [N,H,W,Cout], x 16-bit [N,H,W,Cin]."""
     lib = _dev(g)
     n, h, w, cout = g.shape
@@ -86,7 +89,8 @@ def wgrad3x3(g, x, dW, dbias: Optional[torch.Tensor]):
     assert g.dtype == GRAD_DTYPE and dW.shape == (cout, cin, 3, 3) and dW.is_contiguous()
     with _timed("wgrad3x3", 2.0 * n * h * w * 9 * cin * cout):
         _lib.check(lib.aesr_wgrad3x3(g.data_ptr(), x.data_ptr(), dW.data_ptr(), _ptr(dbias), n, h, w, cin, cout,
-                                     dt_code(x.dtype), _stream(g)), "wgrad3x3")
+                                     dt_code(x.dtype), WGRAD_ALGO if algo is None else int(algo), _stream(g)),
+                   "wgrad3x3")
 
 
 def mix_bwd(g_dec, g_mix, wa, wb):

@@ -84,14 +84,21 @@ def synthesize_volumes(model, volumes: torch.Tensor, alpha_range: Sequence[float
     if A == 0 or Z < 2:
         return out
     # ---- all (volume, pair, alpha) lerp+decode problems
-    plans = [pair_plan(Z, A, w_hi, w_lo, dev, slice_offset=v * Z, out_offset=v * Zo) for v in range(V)]
-    ia, ib, wa, wb, oi = (torch.from_numpy(np.concatenate([p[j] for p in plans])).to(dev, non_blocking=True)
-                          for j in range(5))
-    M = ia.numel()
-    for s in range(0, M, decode_chunk):
-        e = min(s + decode_chunk, M)
-        a = ops.lerp_latents(z, ia[s:e], ib[s:e], wa[s:e], wb[s:e])
-        model.decode_nhwc_eval(a, out=out, out_image_stride=H * W, out_index=oi[s:e])
+    #      pair q = v*(Z-1)+i blends z[v*Z+i+1] (weight w_hi[k]) and z[v*Z+i] (w_lo[k]); problem m = q*A + k lands at
+    #      out[v*Zo + i*(A+1) + 1 + k].  The two fp32 latents of a pair are read once for all A alphas.
+    q = np.arange(V * (Z - 1), dtype=np.int64)
+    v_of, i_of = q // (Z - 1), q % (Z - 1)
+    pa = torch.from_numpy((v_of * Z + i_of + 1).astype(np.int32)).to(dev, non_blocking=True)
+    pb = torch.from_numpy((v_of * Z + i_of).astype(np.int32)).to(dev, non_blocking=True)
+    oi_np = (v_of * Zo + i_of * (A + 1) + 1)[:, None] + np.arange(A, dtype=np.int64)[None, :]
+    oi = torch.from_numpy(oi_np.reshape(-1).astype(np.int32)).to(dev, non_blocking=True)
+    wa = torch.from_numpy(w_hi.astype(np.float32)).to(dev, non_blocking=True)
+    wb = torch.from_numpy(w_lo.astype(np.float32)).to(dev, non_blocking=True)
+    pairs_per_chunk = max(1, decode_chunk // A)
+    for s in range(0, V * (Z - 1), pairs_per_chunk):
+        e = min(s + pairs_per_chunk, V * (Z - 1))
+        a = ops.lerp_pairs(z, pa[s:e], pb[s:e], wa, wb)
+        model.decode_nhwc_eval(a, out=out, out_image_stride=H * W, out_index=oi[s * A:e * A])
     return out
 
 

@@ -46,18 +46,22 @@ class TrainForward:
     """Train-mode (batch-statistics BatchNorm) forward passes; also what ``VanillaACAI.encode/decode`` run when the
     module is in ``.train()`` mode outside the fused step (e.g. ``BaseTrainer.encode(x, eval=False)``)."""
 
-    def __init__(self, model: VanillaACAI, sync_bn: bool = False):
+    def __init__(self, model: VanillaACAI, sync_bn: bool = False, act_dtype: Optional[torch.dtype] = None):
         self.model = model
         self.sync_bn = sync_bn
         self.dev = next(model.parameters()).device
-        self.dtype = ops.DEFAULT_DTYPE
+        # Training activations are bf16 like the gradients: the tensor-core weight-gradient GEMM multiplies a gradient
+        # tile by an activation tile, and tcgen05 kind::f16 needs both operands in ONE 16-bit format (bf16 x fp16 is an
+        # illegal instruction -- measured); gradients need bf16's range (dL/dx ~ 1e-6..1e-9).
+        self.dtype = act_dtype or T.GRAD_DTYPE
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.w_fwd, self.w_bwd = {}, {}
 
 
 class TrainEngine(TrainForward):
-    def __init__(self, model: VanillaACAI, optimizer: Optional[torch.optim.Adam] = None, sync_bn: bool = False):
-        super().__init__(model, sync_bn)
+    def __init__(self, model: VanillaACAI, optimizer: Optional[torch.optim.Adam] = None, sync_bn: bool = False,
+                 act_dtype: Optional[torch.dtype] = None):
+        super().__init__(model, sync_bn, act_dtype)
         self.opt = optimizer
         self.params = [p for p in model.parameters()]
         self.step_count = 0
