@@ -254,6 +254,10 @@ int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, con
     p.tiles_x = (W + CONV_TILE_W - 1) / CONV_TILE_W;
     p.tiles_y = (H + CONV_TILE_H - 1) / CONV_TILE_H;
     p.fp16 = (dtype == AESR_DT_FP16);
+    {
+        static const int dbg = getenv("AESR_CONV_DEBUG") ? atoi(getenv("AESR_CONV_DEBUG")) : 0;   // profiling only
+        p.debug = dbg;
+    }
     p.bias = bias; p.scale = scale; p.shift = shift; p.slope = slope; p.act = act; p.out_mode = out_mode;
     p.out = out; p.out2 = out2; p.mul_src = static_cast<const uint16_t*>(mul_src); p.mul_mode = mul_mode;
     p.stats = stats;
@@ -303,6 +307,14 @@ int aesr_head_fwd(const void* in, const float* w9c, const float* bias, float* ou
     if (grid > cap) grid = cap;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const uint16_t* in16 = static_cast<const uint16_t*>(in);
+    if (N <= 65535) {        // shared-memory tiled kernel: one block per 16x16 output pixels of one image
+        dim3 tgrid((W + 15) / 16, (H + 15) / 16, N);
+        if (dtype == AESR_DT_FP16)
+            head_conv3x3_tiled_kernel<true><<<tgrid, 256, 0, s>>>(in16, w9c, bias, out, out_index, H, W, out_image_stride, apply_sigmoid);
+        else
+            head_conv3x3_tiled_kernel<false><<<tgrid, 256, 0, s>>>(in16, w9c, bias, out, out_index, H, W, out_image_stride, apply_sigmoid);
+        return check_launch("head_conv3x3_tiled");
+    }
     if (dtype == AESR_DT_FP16)
         head_conv3x3_sigmoid_kernel<32, true><<<static_cast<int>(grid), block, 0, s>>>(in16, w9c, bias, out, out_index, N, H, W, out_image_stride, apply_sigmoid);
     else

@@ -46,6 +46,7 @@ struct ConvParams {
     int tiles_x, tiles_y, n_blocks, num_tiles;   // num_tiles = spatial tiles (N * tiles_y * tiles_x) * n_blocks
     int num_stages;
     int fp16;               // 1: activations / weights are fp16, 0: bf16
+    int debug;              // profiling only (AESR_CONV_DEBUG): bit0 = skip the MMAs, bit1 = skip the activation TMA loads
     // epilogue
     const float* bias;      // [Cout] or null
     const float* scale;     // [Cout] or null: y = act(acc + bias) * scale + shift
@@ -66,7 +67,9 @@ constexpr int CONV_TILE_H = 16;
 constexpr int CONV_TILE_W = 8;
 constexpr int CONV_TILE_M = 128;
 constexpr int CONV_EPI_SETS = 4;                          // epilogue warp sets (4 warps = 128 TMEM lanes each)
-constexpr int CONV_THREADS = 64 + 128 * CONV_EPI_SETS;    // 576: TMA warp + MMA warp + 16 epilogue warps
+constexpr int CONV_ISSUERS = 2;                            // MMA-issuing threads (warps 1..CONV_ISSUERS)
+constexpr int CONV_FIRST_EPI_WARP = 1 + CONV_ISSUERS;      // warp 0 TMA, warps 1-2 MMA issuers, then the epilogue sets
+constexpr int CONV_THREADS = 32 * CONV_FIRST_EPI_WARP + 128 * CONV_EPI_SETS;   // 608
 constexpr int CONV_MAX_STAGES = 8;
 // TMEM accumulators in flight: one per epilogue set while they fit in the 512 columns
 __host__ __device__ constexpr int conv_num_acc(int BN) { return (CONV_EPI_SETS * BN <= 512) ? CONV_EPI_SETS : 512 / BN; }
@@ -185,12 +188,18 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
     uint16_t* out2_16 = static_cast<uint16_t*>(p.out2);
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t raw[32];
-        tmem_ld_32x32b_x32(t_addr + c0, raw);
-        tmem_ld_wait();
+        if (p.debug & 8) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) raw[j] = 0;
+        } else {
+            tmem_ld_32x32b_x32(t_addr + c0, raw);
+            tmem_ld_wait();
+        }
         if (c0 + 32 >= p.BN) {                  // accumulator fully read: hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(tmem_empty_bar);
         }
+        if (p.debug & 64) continue;
         float v[32];
         const int cg = t.n0 + c0;               // first global output channel of this chunk
         {
@@ -254,7 +263,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
             }
         }
         if (p.out_mode == OUT_SAME || p.out_mode == OUT_SAME_MAXPOOL2) {
-            if (inb) {
+            if (inb && !((p.debug & 4) && v[0] != 12345.f)) {
                 uint4* o4 = reinterpret_cast<uint4*>(
                     out16 + (static_cast<size_t>(n) * H * W + static_cast<size_t>(y) * W + x) * Cout + cg);
 #pragma unroll
@@ -370,59 +379,93 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                                 tap * p.Cout + nb * p.BN);
             int stage = 0;
             uint32_t phase = 0;
+            // tile coordinates advance incrementally (one producer thread: no div/mod per tile)
+            const int tiles_per_img = p.tiles_x * p.tiles_y;
+            int n = first / tiles_per_img, ty = (first % tiles_per_img) / p.tiles_x, tx = first % p.tiles_x;
+            const int dn = ctas_per_nb / tiles_per_img, dty = (ctas_per_nb % tiles_per_img) / p.tiles_x,
+                      dtx = ctas_per_nb % p.tiles_x;
             for (int sp = first; sp < sp_tiles; sp += ctas_per_nb) {
-                const TileCoord t = tile_coord(p, sp, nb);
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&bars.empty[stage], phase ^ 1);
-                    mbar_arrive_expect_tx(&bars.full[stage], S::A_BYTES);
-                    tma_load_4d(a_smem + stage * S::A_STAGE, &tmap_x, &bars.full[stage], kc * KC, t.x0 - 1, t.y0 - 1,
-                                t.n);
+                    if (p.debug & 2) {
+                        mbar_arrive(&bars.full[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&bars.full[stage], S::A_BYTES);
+                        tma_load_4d(a_smem + stage * S::A_STAGE, &tmap_x, &bars.full[stage], kc * KC,
+                                    tx * CONV_TILE_W - 1, ty * CONV_TILE_H - 1, n);
+                    }
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
+                tx += dtx;
+                if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
+                ty += dty;
+                if (ty >= p.tiles_y) { ty -= p.tiles_y; ++n; }
+                n += dn;
             }
         }
-    } else if (warp == 1) {
+    } else if (warp < CONV_FIRST_EPI_WARP) {
+        // CONV_ISSUERS MMA-issuing threads alternate tiles (issuer j takes this CTA's tiles j, j+2, ...).  A tile's
+        // barrier round trip (2 waits, 2 fences, 2 commits: ~760 cycles measured with everything else stubbed out) is
+        // serial in the issuing thread and the tensor-core queue is too shallow to cover it, so with ONE issuer a
+        // thin-layer tile costs overhead + MMA time (1900 cycles vs ~850 of MMA); with two, one thread feeds the tensor
+        // core while the other does its bookkeeping (1400 cycles; four issuers were slower again: register pressure at
+        // 672 threads).  Stages and accumulators are assigned by tile index: each thread steps them by two tiles.
+        const int issuer = warp - 1;
+        const int num_acc = conv_num_acc(p.BN);
         if (lane == 0 && active) {
             const uint32_t idesc = make_idesc_16(CONV_TILE_M, p.BN, p.fp16);
             int stage = 0;
             uint32_t phase = 0;
-            const int num_acc = conv_num_acc(p.BN);
-            int acc = 0;
+            int acc = issuer % num_acc;
             uint32_t acc_phase = 0;
+            for (int i = 0; i < issuer * kchunks; ++i)
+                if (++stage == num_stages) { stage = 0; phase ^= 1; }
             mbar_wait(bars.b_full, 0);
-            const uint32_t b_base = smem_u32(b_smem);
-            for (int sp = first; sp < sp_tiles; sp += ctas_per_nb) {
+            // Descriptors: only the 14-bit start-address field (bits 0..13 of the low word, address >> 4) changes
+            // between MMAs, so each MMA costs one 32-bit add per operand.
+            //   A rows: group g (output row g of the tile) starts at halo pixel (g + dy) * 10 + dx  =>  start address
+            //   advanced by (dy*10+dx) rows, 8-row group stride (SBO) = halo pitch.
+            const uint64_t a_tmpl = make_smem_desc(smem_u32(a_smem), HALO_W * ROW_BYTES, LAYOUT);
+            const uint64_t b_tmpl = make_smem_desc(smem_u32(b_smem), 8 * ROW_BYTES, LAYOUT);
+            const uint32_t a_hi = static_cast<uint32_t>(a_tmpl >> 32), b_hi = static_cast<uint32_t>(b_tmpl >> 32);
+            const uint32_t a_lo0 = static_cast<uint32_t>(a_tmpl), b_lo0 = static_cast<uint32_t>(b_tmpl);
+            const uint32_t b_blk16 = static_cast<uint32_t>(b_block) >> 4;
+            const uint32_t b_tap16 = b_blk16 * kchunks;
+            for (int sp = first + issuer * ctas_per_nb; sp < sp_tiles; sp += CONV_ISSUERS * ctas_per_nb) {
                 mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * p.BN;
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&bars.full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(a_smem + stage * S::A_STAGE);
+                    const uint32_t a_lo = a_lo0 + stage * (S::A_STAGE >> 4);
+                    uint32_t b_lo = b_lo0 + kc * b_blk16;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
-                        const int dy = tap / 3, dx = tap - dy * 3;
-                        // rows of the A operand: group g (output row g of the tile) starts at halo pixel
-                        // (g + dy) * 10 + dx  =>  start address shifted by (dy*10+dx) rows, group stride = halo pitch
-                        const uint64_t a_desc = make_smem_desc(a_base + (dy * HALO_W + dx) * ROW_BYTES,
-                                                               HALO_W * ROW_BYTES, LAYOUT);
-                        const uint64_t b_desc = make_smem_desc(b_base + (tap * kchunks + kc) * b_block, 8 * ROW_BYTES,
-                                                               LAYOUT);
+                        if ((p.debug & 1) && tap > 0) break;
+                        if (p.debug & 32) break;
+                        constexpr uint32_t kRow16 = ROW_BYTES >> 4;
+                        const uint32_t a_tap = a_lo + ((tap / 3) * HALO_W + (tap % 3)) * kRow16;
 #pragma unroll
                         for (int k = 0; k < KC / 16; ++k)
-                            umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kc | tap | k) != 0);
+                            umma_f16_split(d_tmem, a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
+                                           (tap | k) != 0 ? 1u : static_cast<uint32_t>(kc != 0));
+                        b_lo += b_tap16;
                     }
-                    umma_commit(&bars.empty[stage]);
+                    if (p.debug & 16) mbar_arrive(&bars.empty[stage]); else umma_commit(&bars.empty[stage]);
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&bars.tmem_full[acc]);
-                if (++acc == num_acc) { acc = 0; acc_phase ^= 1; }
+                if (p.debug & 32) mbar_arrive(&bars.tmem_full[acc]); else umma_commit(&bars.tmem_full[acc]);
+                acc += CONV_ISSUERS;                        // skip the other issuer's tile
+                if (acc >= num_acc) { acc -= num_acc; acc_phase ^= 1; }
+                for (int i = 0; i < (CONV_ISSUERS - 1) * kchunks; ++i)
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (active) {
         // epilogue set `eset` owns accumulator `eset`: it handles this CTA's tiles eset, eset + num_acc, ...
         const int num_acc = conv_num_acc(p.BN);
-        const int eset = (warp - 2) >> 2;
+        const int eset = (warp - CONV_FIRST_EPI_WARP) >> 2;
         if (eset < num_acc) {
             uint32_t acc_phase = 0;
             for (int sp = first + eset * ctas_per_nb; sp < sp_tiles; sp += ctas_per_nb * num_acc) {
@@ -500,6 +543,8 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             const int num_acc = conv_num_acc(p.BN);
             int acc = 0;
             uint32_t acc_phase = 0;
+            const uint64_t s_tmpl = make_smem_desc(smem_u32(smem), SBO, LAYOUT);
+            const uint32_t s_hi = static_cast<uint32_t>(s_tmpl >> 32), s_lo0 = static_cast<uint32_t>(s_tmpl);
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -507,12 +552,11 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(&bars.full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-                    const uint64_t a_desc = make_smem_desc(a_addr, SBO, LAYOUT);
-                    const uint64_t b_desc = make_smem_desc(a_addr + S::A_BYTES, SBO, LAYOUT);
+                    const uint32_t a_lo = s_lo0 + stage * (static_cast<uint32_t>(stage_bytes) >> 4);
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k)   // +32 bytes along K inside the swizzle row
-                        umma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        umma_f16_split(d_tmem, a_lo + 2 * k, s_hi, a_lo + (S::A_BYTES >> 4) + 2 * k, s_hi, idesc,
+                                       k != 0 ? 1u : static_cast<uint32_t>(kb != 0));
                     umma_commit(&bars.empty[stage]);
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
@@ -520,9 +564,9 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 if (++acc == num_acc) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else {
+    } else if (warp >= CONV_FIRST_EPI_WARP) {
         const int num_acc = conv_num_acc(p.BN);
-        const int eset = (warp - 2) >> 2;
+        const int eset = (warp - CONV_FIRST_EPI_WARP) >> 2;
         if (eset < num_acc) {
             uint32_t acc_phase = 0;
             for (int tile = blockIdx.x + eset * gridDim.x; tile < p.num_tiles; tile += gridDim.x * num_acc) {

@@ -112,6 +112,62 @@ __global__ void head_conv3x3_sigmoid_kernel(const uint16_t* __restrict__ in, con
     }
 }
 
+// Shared-memory tiled version of the same head conv: one block = 16x16 output pixels of one image.  The 18x18x32 input
+// window is staged once (coalesced 16-byte loads) with an 80-byte pixel pitch (64 B of channels + 16 B pad: the eight
+// lanes of an LDS.128 phase then hit eight distinct 4-bank groups), so each input byte is fetched from L2 ~1.27x instead
+// of 9x and the inner loop runs from conflict-free shared memory.
+template <bool FP16>
+__global__ void __launch_bounds__(256)
+head_conv3x3_tiled_kernel(const uint16_t* __restrict__ in, const float* __restrict__ w /*[9][32]*/,
+                          const float* __restrict__ bias_ptr, float* __restrict__ out,
+                          const int* __restrict__ out_index, int H, int W, size_t out_image_stride,
+                          int apply_sigmoid) {
+    constexpr int C = 32, TW = 16, TH = 16, PITCH = 80;
+    __shared__ __align__(16) uint8_t tile[(TH + 2) * (TW + 2) * PITCH];
+    __shared__ float sw[9 * C];
+    const int n = blockIdx.z, x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    for (int i = threadIdx.x; i < 9 * C; i += 256) sw[i] = w[i];
+    const uint16_t* img = in + static_cast<size_t>(n) * H * W * C;
+    for (int i = threadIdx.x; i < (TH + 2) * (TW + 2) * 4; i += 256) {
+        const int chunk = i & 3, px = i >> 2;
+        const int hx = px % (TW + 2), hy = px / (TW + 2);
+        const int gx = x0 + hx - 1, gy = y0 + hy - 1;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (gx >= 0 && gx < W && gy >= 0 && gy < H)
+            v = __ldg(reinterpret_cast<const uint4*>(img + (static_cast<size_t>(gy) * W + gx) * C) + chunk);
+        *reinterpret_cast<uint4*>(tile + px * PITCH + chunk * 16) = v;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int x = x0 + tx, y = y0 + ty;
+    float acc0 = __ldg(bias_ptr), acc1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+        const uint8_t* src = tile + ((ty + t / 3) * (TW + 2) + tx + t % 3) * PITCH;
+        const float* wt = sw + t * C;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+            const uint4 m = *reinterpret_cast<const uint4*>(src + j4 * 16);
+            const uint32_t u[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack2_t<FP16>(u[k]);
+                acc0 = fmaf(f.x, wt[j4 * 8 + k * 2], acc0);
+                acc1 = fmaf(f.y, wt[j4 * 8 + k * 2 + 1], acc1);
+            }
+        }
+    }
+    if (x < W && y < H) {
+        float r = acc0 + acc1;
+        if (apply_sigmoid) {
+            r = 1.f / (1.f + __expf(-r));
+            r = fminf(fmaxf(r, 0.f), 1.f);
+        }
+        const size_t slot = out_index ? static_cast<size_t>(__ldg(out_index + n)) : static_cast<size_t>(n);
+        out[slot * out_image_stride + static_cast<size_t>(y) * W + x] = r;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // latent interpolation + layout change
 //   z    fp32 NCHW [*, C, HW]  (public latent layout)

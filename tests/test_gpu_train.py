@@ -124,7 +124,8 @@ def test_step_gradients_match_oracle_autograd(cuda_lib, kind, brain):
     sd = model.state_dict()
     for k in sd:                                                   # BN running statistics + counters (App. B item 7)
         if "running" in k:
-            assert torch.allclose(sd[k].cpu(), st_o[k], rtol=2e-3, atol=2e-4), k
+            tol = dict(rtol=2e-3, atol=2e-4) if kind == "rnd" else dict(rtol=1e-2, atol=2e-3)   # bf16 activations
+            assert torch.allclose(sd[k].cpu(), st_o[k], **tol), k
         if "num_batches" in k:
             assert int(sd[k]) == int(st_o[k]) == int(st[k]) + 2
 
