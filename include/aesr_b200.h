@@ -163,6 +163,31 @@ int aesr_maxpool_bwd(const void* a, const void* d_pooled, const void* g_tap, voi
 int aesr_lpips_head(const void* o0, const void* o1, const float* lin, float* val, const float* upstream, void* g1, int N,
                     int HW, int C, int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Evaluation / data-path utilities (HBM-bound, one pass over the data)
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Per-slice SSIM / squared error / minimum of two fp32 volumes [Z,H,W] (evaluate/metrics.py:111-194, which calls
+ * scikit-image structural_similarity(im1, im2) / peak_signal_noise_ratio(true, test) per slice).  win = 7 (or 5),
+ * uniform window, sample covariance, K1 .01, K2 .03, border of (win-1)/2 cropped; data_range is the caller's choice
+ * (2.0 reproduces the reference's legacy float default, 1.0 the [0,1] images' true range).
+ * ssim_sum[z] = sum of S over the (H-win+1)(W-win+1) kept pixels; sqerr_sum[z] = sum (a-b)^2 over the slice;
+ * min_key[z] = order-preserving uint32 key of min(a) (key >= 0x80000000 <=> min >= 0).  Z <= 65535. */
+int aesr_ssim_psnr(const float* a, const float* b, int Z, int H, int W, int win, double data_range, double* ssim_sum,
+                   double* sqerr_sum, unsigned int* min_key, void* stream);
+
+/* np.percentile(x, (q_lo, q_hi)) ('linear', float64) by exact 3-pass radix select, then
+ * out = clip((x - p_lo) / (p_hi - p_lo), 0, 1) in float64 rounded once to fp32 (generate_hr_volumes.py:130-133,
+ * datasets/common.py:408-417).  out may be NULL (percentiles only -> lo_hi_out[2], device doubles, may be NULL). */
+size_t aesr_percentile_workspace_bytes(void);
+int aesr_percentile_normalize(const float* x, float* out, size_t n, double q_lo, double q_hi, void* workspace,
+                              size_t workspace_bytes, double* lo_hi_out, void* stream);
+
+/* Batched zero-pad + crop of fp32 images (datasets/shared_transforms.py AdjustToPatchSize :389-447, CenterCrop
+ * :297-363, RandomCrop :48-120): out[b,c,y,x] = in[b,c,y+top[b],x+left[b]] inside the source, 0 outside. */
+int aesr_pad_crop_gather(const float* in, float* out, const int* top, const int* left, int B, int C, int Hin, int Win,
+                         int Hout, int Wout, void* stream);
+
 /* DIAGNOSTIC (not on the product path): one 16x8 tile of a 64->64 bf16 conv computed from a single TMA halo load with
  * row-shifted UMMA descriptors; used by tools/gpu_diag.py to establish what the hardware's swizzle addressing does.
  * out fp32 [128][64] raw accumulators. */

@@ -43,6 +43,11 @@ _SIGNATURES = {
     "aesr_vgg_conv1_bwd": (I, [P, P, P, I, I, I, P, I, F, P]),
     "aesr_maxpool_bwd": (I, [P, P, P, P, I, I, I, I, I, P]),
     "aesr_lpips_head": (I, [P, P, P, P, P, P, I, I, I, I, P]),
+    # evaluation / data path
+    "aesr_ssim_psnr": (I, [P, P, I, I, I, I, ctypes.c_double, P, P, P, P]),
+    "aesr_percentile_workspace_bytes": (c_size_t, []),
+    "aesr_percentile_normalize": (I, [P, P, c_size_t, ctypes.c_double, ctypes.c_double, P, c_size_t, P, P]),
+    "aesr_pad_crop_gather": (I, [P, P, P, P, I, I, I, I, I, I, P]),
 }
 
 

@@ -9,6 +9,7 @@
 #include "../../include/aesr_b200.h"
 #include "conv3x3_tc.cuh"
 #include "elementwise.cuh"
+#include "eval_kernels.cuh"
 #include "lpips_kernels.cuh"
 #include "probe.cuh"
 #include "train_kernels.cuh"

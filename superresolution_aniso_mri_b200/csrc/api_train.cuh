@@ -244,4 +244,76 @@ int aesr_lpips_head(const void* o0, const void* o1, const float* lin, float* val
     return AESR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// evaluation / data-path utilities
+// ------------------------------------------------------------------------------------------------------------------
+int aesr_ssim_psnr(const float* a, const float* b, int Z, int H, int W, int win, double data_range, double* ssim_sum,
+                   double* sqerr_sum, unsigned int* min_key, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!a || !b || !ssim_sum || !sqerr_sum || !min_key || Z <= 0 || Z > 65535 || H < win || W < win)
+        return fail(AESR_ERR_INVALID, "ssim_psnr: bad arguments (Z<=65535, H,W >= win)");
+    if (win != 7 && win != 5) return fail(AESR_ERR_INVALID, "ssim_psnr: win must be 7 (default) or 5 (evaluate/metrics.py:151)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemsetAsync(ssim_sum, 0, Z * sizeof(double), s));
+    CUDA_TRY(cudaMemsetAsync(sqerr_sum, 0, Z * sizeof(double), s));
+    CUDA_TRY(cudaMemsetAsync(min_key, 0xFF, Z * sizeof(unsigned int), s));
+    const double c1 = (0.01 * data_range) * (0.01 * data_range), c2 = (0.03 * data_range) * (0.03 * data_range);
+    dim3 grid((W + 15) / 16, (H + 15) / 16, Z);
+    if (win == 7) ssim_psnr_kernel<7><<<grid, 256, 0, s>>>(a, b, H, W, c1, c2, ssim_sum, sqerr_sum, min_key);
+    else ssim_psnr_kernel<5><<<grid, 256, 0, s>>>(a, b, H, W, c1, c2, ssim_sum, sqerr_sum, min_key);
+    return check_launch("ssim_psnr");
+}
+
+size_t aesr_percentile_workspace_bytes(void) { return 256 + 4 * 2048 * sizeof(unsigned int) + 64; }
+
+int aesr_percentile_normalize(const float* x, float* out, size_t n, double q_lo, double q_hi, void* workspace,
+                              size_t workspace_bytes, double* lo_hi_out, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!x || !workspace || n == 0 || q_lo < 0 || q_hi > 100 || q_lo > q_hi) return fail(AESR_ERR_INVALID, "percentile_normalize: bad arguments");
+    if (workspace_bytes < aesr_percentile_workspace_bytes()) return fail(AESR_ERR_WORKSPACE, "percentile_normalize: workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    SelectState* st = reinterpret_cast<SelectState*>(ws);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(ws + 256);
+    double* lo_hi = reinterpret_cast<double*>(ws + 256 + 4 * 2048 * sizeof(unsigned int));
+    // numpy 'linear': virtual index q/100 * (n-1), neighbours floor / floor+1 (clamped)
+    SelectState h{};
+    const double vi[2] = {q_lo / 100.0 * static_cast<double>(n - 1), q_hi / 100.0 * static_cast<double>(n - 1)};
+    double frac[2];
+    for (int j = 0; j < 2; ++j) {
+        const double fl = floor(vi[j]);
+        frac[j] = vi[j] - fl;
+        const uint64_t k = static_cast<uint64_t>(fl);
+        h.rank[2 * j] = k;
+        h.rank[2 * j + 1] = (k + 1 < n) ? k + 1 : n - 1;
+    }
+    CUDA_TRY(cudaMemcpyAsync(st, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(hist, 0, 4 * 2048 * sizeof(unsigned int), s));
+    const int grid = grid_for(n, 256, 8);
+    select_hist_kernel<21, 11><<<grid, 256, 0, s>>>(x, n, st, 4, hist);
+    select_narrow_kernel<21, 11><<<1, 32, 0, s>>>(st, 4, hist, 0);
+    select_hist_kernel<10, 11><<<grid, 256, 0, s>>>(x, n, st, 4, hist);
+    select_narrow_kernel<10, 11><<<1, 32, 0, s>>>(st, 4, hist, 0);
+    select_hist_kernel<0, 10><<<grid, 256, 0, s>>>(x, n, st, 4, hist);
+    select_narrow_kernel<0, 10><<<1, 32, 0, s>>>(st, 4, hist, 1);
+    percentile_finish_kernel<<<1, 1, 0, s>>>(st, frac[0], frac[1], lo_hi);
+    g_launches.fetch_add(6, std::memory_order_relaxed);
+    if (lo_hi_out) CUDA_TRY(cudaMemcpyAsync(lo_hi_out, lo_hi, 2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (out) normalize_apply_kernel<<<grid, 256, 0, s>>>(x, out, n, lo_hi);
+    return check_launch("percentile_normalize");
+}
+
+int aesr_pad_crop_gather(const float* in, float* out, const int* top, const int* left, int B, int C, int Hin, int Win,
+                         int Hout, int Wout, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!in || !out || !top || !left || B <= 0 || B > 65535 || C <= 0 || C > 65535) return fail(AESR_ERR_INVALID, "pad_crop_gather: bad arguments");
+    int gx = (Hout * Wout + 255) / 256;
+    if (gx > 64) gx = 64;
+    pad_crop_gather_kernel<<<dim3(gx, C, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, top, left, C, Hin, Win, Hout, Wout);
+    return check_launch("pad_crop_gather");
+}
+
 }  // extern "C"

@@ -1,0 +1,157 @@
+"""Device-resident evaluation / data-path utilities: SSIM & PSNR per slice, percentile normalisation, pad / crop.
+
+Drop-ins for ``evaluate.metrics.compute_ssim_for_batch / compute_psnr_for_batch`` (evaluate/metrics.py:111-194),
+``generate_hr_volumes.normalize_img`` (:130-133) / ``datasets.common.rescale_intensities`` (:408-417) and the crop / pad
+transforms of ``datasets/shared_transforms.py`` (AdjustToPatchSize :389-447, CenterCrop :297-363, RandomCrop :48-120).
+The reference does these on the host (numpy / scikit-image, one Python call per slice); here each is one pass of a
+coalesced kernel over data that already sits in HBM after synthesis.
+
+SSIM caveat (parity unpinned): the reference calls scikit-image without ``data_range`` on float
+images, i.e. the legacy dtype range 2.0; ``data_range`` defaults to that and 1.0 can be passed for the images' true
+range.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ops import _dev, _stream
+
+
+def _as_dev_f32(x, device) -> torch.Tensor:
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    return x.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def original_slice_ids(num_slices: int, downsample_steps: int, conv_interpol: bool = False) -> np.ndarray:
+    """evaluate/metrics.py:29-45 (host index bookkeeping, bit-exact integer logic)."""
+    ids = np.arange(num_slices)
+    keep = None
+    if (num_slices - 1) % downsample_steps != 0:
+        r = (num_slices - 1) % downsample_steps
+        keep, ids = ids[-r:], ids[:-r]
+    if conv_interpol and ids.shape[0] % downsample_steps != 0:
+        r = ids.shape[0] % downsample_steps
+        keep = ids[-r:] if keep is None else np.concatenate((ids[-r:], keep))
+        ids = ids[:-r]
+    ids = ids[::downsample_steps]
+    return ids if keep is None else np.concatenate((ids, keep))
+
+
+def synth_slices_mask(orig_num_slices: int, downsample_steps: int):
+    """evaluate/quantitative_comparison.py:10-17: (reconstructed-slice mask, synthesized-slice mask)."""
+    n = ((orig_num_slices - 1) // downsample_steps) * downsample_steps + 1
+    s_mask = np.ones(n, dtype=bool)
+    s_mask[::downsample_steps] = False
+    return ~s_mask, s_mask
+
+
+def ssim_psnr_slices(true_vol, test_vol, win: int = 7, data_range: float = 2.0, device="cuda:0"):
+    """Per-slice SSIM and PSNR of two [Z,H,W] volumes -> (ssim[Z], psnr[Z]) float64 numpy arrays."""
+    a = _as_dev_f32(true_vol, device).squeeze()
+    b = _as_dev_f32(test_vol, device).squeeze()
+    if a.dim() == 2:
+        a, b = a[None], b[None]
+    assert a.shape == b.shape and a.dim() == 3
+    lib = _dev(a)
+    z, h, w = a.shape
+    ssim_sum = torch.empty(z, dtype=torch.float64, device=a.device)
+    sq = torch.empty(z, dtype=torch.float64, device=a.device)
+    mk = torch.empty(z, dtype=torch.int32, device=a.device)
+    _lib.check(lib.aesr_ssim_psnr(a.data_ptr(), b.data_ptr(), z, h, w, win, float(data_range), ssim_sum.data_ptr(),
+                                  sq.data_ptr(), mk.data_ptr(), _stream(a)), "ssim_psnr")
+    pad = (win - 1) // 2
+    ssim = ssim_sum.cpu().numpy() / ((h - 2 * pad) * (w - 2 * pad))
+    mse = sq.cpu().numpy() / (h * w)
+    min_nonneg = mk.cpu().numpy().view(np.uint32) >= np.uint32(0x80000000)     # order-preserving key of min(true)
+    rng = np.where(min_nonneg, 1.0, 2.0)               # skimage: float images, data_range 1 if min >= 0 else 2
+    with np.errstate(divide="ignore"):
+        psnr = 10 * np.log10(rng * rng / mse)
+    return ssim, psnr
+
+
+def compute_ssim_for_batch(l_images, l_reconstructions, eval_axis=0, normalize=False, downsample_steps=None,
+                           conv_interpol=False, data_range: float = 2.0, device="cuda:0"):
+    """evaluate/metrics.py:111-156 (eval_axis=0): mean SSIM over the non-original slices."""
+    if eval_axis != 0 or normalize:
+        raise NotImplementedError("aesr_b200: eval_axis != 0 / normalize=True are long-axis evaluation options "
+                                  "outside the hot path")
+    ssim, _ = ssim_psnr_slices(l_images, l_reconstructions, data_range=data_range, device=device)
+    skip = original_slice_ids(len(ssim), downsample_steps, conv_interpol) if downsample_steps else []
+    keep = np.setdiff1d(np.arange(len(ssim)), skip)
+    return float(np.mean(ssim[keep]))
+
+
+def compute_psnr_for_batch(l_images, l_reconstructions, eval_axis=0, normalize=False, downsample_steps=None,
+                           conv_interpol=False, device="cuda:0"):
+    """evaluate/metrics.py:159-194 (eval_axis=0): mean PSNR over the non-original slices, nan / inf dropped."""
+    if eval_axis != 0 or normalize:
+        raise NotImplementedError("aesr_b200: eval_axis != 0 / normalize=True are outside the hot path")
+    _, psnr = ssim_psnr_slices(l_images, l_reconstructions, device=device)
+    skip = original_slice_ids(len(psnr), downsample_steps, conv_interpol) if downsample_steps else []
+    keep = np.setdiff1d(np.arange(len(psnr)), skip)
+    vals = psnr[keep]
+    vals = vals[np.isfinite(vals)]
+    return float(np.mean(vals))
+
+
+def normalize_img(img, perc=(1, 99), device="cuda:0", return_percentiles: bool = False):
+    """generate_hr_volumes.py:130-133 on the device: exact np.percentile (linear) over the whole volume + clip."""
+    x = _as_dev_f32(img, device)
+    lib = _dev(x)
+    ws = torch.empty(int(lib.aesr_percentile_workspace_bytes()), dtype=torch.uint8, device=x.device)
+    out = torch.empty_like(x)
+    lo_hi = torch.empty(2, dtype=torch.float64, device=x.device)
+    _lib.check(lib.aesr_percentile_normalize(x.data_ptr(), out.data_ptr(), x.numel(), float(perc[0]), float(perc[1]),
+                                             ws.data_ptr(), ws.numel(), lo_hi.data_ptr(), _stream(x)),
+               "percentile_normalize")
+    return (out, lo_hi) if return_percentiles else out
+
+
+def rescale_intensities(im, percs=(0, 100), device="cuda:0"):
+    """datasets/common.py:408-417."""
+    return normalize_img(im, percs, device=device)
+
+
+def pad_crop(images, top, left, out_h: int, out_w: int, device="cuda:0") -> torch.Tensor:
+    """out[b,c,y,x] = images[b,c,y+top[b],x+left[b]] or 0 outside; images [B,C,H,W] fp32."""
+    x = _as_dev_f32(images, device)
+    lib = _dev(x)
+    b, c, h, w = x.shape
+    t = torch.as_tensor(np.broadcast_to(np.asarray(top, dtype=np.int32), (b,)).copy(), device=x.device)
+    l_ = torch.as_tensor(np.broadcast_to(np.asarray(left, dtype=np.int32), (b,)).copy(), device=x.device)
+    out = torch.empty((b, c, out_h, out_w), dtype=torch.float32, device=x.device)
+    _lib.check(lib.aesr_pad_crop_gather(x.data_ptr(), out.data_ptr(), t.data_ptr(), l_.data_ptr(), b, c, h, w, out_h,
+                                        out_w, _stream(x)), "pad_crop_gather")
+    return out
+
+
+def adjust_to_patch_size(images, patch: int, device="cuda:0") -> torch.Tensor:
+    """AdjustToPatchSize (shared_transforms.py:389-447): zero-pad up to >= patch, left = floor(d/2), right = ceil."""
+    h, w = images.shape[-2:]
+    dh, dw = max(patch - h, 0), max(patch - w, 0)
+    return pad_crop(images, -(dh // 2), -(dw // 2), h + dh, w + dw, device=device)
+
+
+def center_crop(images, patch: int, device="cuda:0") -> torch.Tensor:
+    """CenterCrop (shared_transforms.py:297-363): window int(h/2) +- int(P/2)."""
+    h, w = images.shape[-2:]
+    half = int(patch / 2)
+    return pad_crop(images, int(h / 2) - half, int(w / 2) - half, 2 * half, 2 * half, device=device)
+
+
+def random_crop(images, patch: int, rs: np.random.RandomState, device="cuda:0") -> torch.Tensor:
+    """RandomCrop (shared_transforms.py:48-120): one (top, left) per sample from rs.randint(0, h - P) (exclusive),
+    same window for all channels of the sample (the from / to / between triplet)."""
+    b, _, h, w = images.shape
+    if h == patch and w == patch:
+        return _as_dev_f32(images, device)
+    tops, lefts = [], []
+    for _ in range(b):
+        tops.append(rs.randint(0, h - patch))
+        lefts.append(rs.randint(0, w - patch))
+    return pad_crop(images, np.array(tops), np.array(lefts), patch, patch, device=device)

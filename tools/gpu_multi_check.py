@@ -1,0 +1,87 @@
+"""Multi-GPU checks, launched with torchrun (one process per GPU, NCCL):
+  (a) inference: volumes sharded over ranks, no collective -> bit-identical to the single-GPU result;
+  (b) training: global batch split over ranks (triplets co-located), SyncBN sums + gradient all-reduce (AVG) ->
+      same losses / parameters as the single-GPU step on the global batch, within tolerance."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import aesr_oracle as O  # noqa: E402
+from oracle.make_golden import acdc_batch  # noqa: E402
+from superresolution_aniso_mri_b200 import parallel as P, synthesis  # noqa: E402
+from superresolution_aniso_mri_b200.lpips_b200 import PerceptualLoss  # noqa: E402
+from superresolution_aniso_mri_b200.networks.acai_vanilla import VanillaACAI  # noqa: E402
+from superresolution_aniso_mri_b200.training.engine import TrainEngine  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+args = O.default_args(128, 32)
+
+
+def model_from(state, train=False):
+    margs = dict(args)
+    margs["device"] = str(dev)
+    m = VanillaACAI(margs)
+    m.load_state_dict(state)
+    return m.train() if train else m.eval()
+
+
+# ---------------------------------------------------------------- (a) inference sharding
+state = O.calibrated_state(args)
+model = model_from(state)
+vols = torch.rand(6, 10, 128, 128, generator=torch.Generator().manual_seed(5)).to(dev)
+ar = O.alpha_range_for(6)
+mine = synthesis.synthesize_volumes(model, P.shard_volumes(vols, rank, world), ar)
+parts = P.gather_volume_shards(mine, 6)
+if rank == 0:
+    full = synthesis.synthesize_volumes(model, vols, ar)
+    print("inference: sharded == single-GPU bit-exact:", bool(torch.equal(torch.cat(parts), full)), flush=True)
+
+# ---------------------------------------------------------------- (b) data-parallel training step(s)
+vgg = [t for pair in O.init_vgg(3) for t in pair]
+st0 = O.init_state(args, seed=892372)
+lp = PerceptualLoss(vgg_state=vgg, device=dev)
+steps = 3
+# single-GPU reference on the global batch (rank 0 only, no process group use: world forced to 1)
+ref_losses, ref_state = [], None
+if rank == 0:
+    m1 = model_from(st0, train=True)
+    e1 = TrainEngine(m1, None)
+    e1.world = 1
+    for s in range(steps):
+        img, mid = acdc_batch(s)
+        w = torch.full((12,), 0.5, device=dev)
+        res = e1.step(img.to(dev), mid.to(dev), w, w, lpips=lp, ex_loss_weight=0.05, lr=1e-5)
+        ref_losses.append(e1.logged_losses(res)["loss_ae"])
+    ref_state = {k: v.clone() for k, v in m1.state_dict().items()}
+dist.barrier()
+m2 = model_from(st0, train=True)
+e2 = TrainEngine(m2, None, sync_bn=True)
+dp_losses = []
+for s in range(steps):
+    img, mid = acdc_batch(s)
+    lb = P.shard_batch_pairs({"image": img, "slice_between": mid}, rank, world)
+    b = lb["slice_between"].shape[0]
+    w = torch.full((b,), 0.5, device=dev)
+    res = e2.step(lb["image"].to(dev), lb["slice_between"].to(dev), w, w, lpips=lp, ex_loss_weight=0.05, lr=1e-5)
+    t = torch.tensor([e2.logged_losses(res)["loss_ae"]], device=dev, dtype=torch.float64)
+    dist.all_reduce(t)                    # equal shard sizes: mean of per-rank means = global mean
+    dp_losses.append(float(t.item()) / world)
+if rank == 0:
+    print("training losses single:", ["%.6f" % v for v in ref_losses])
+    print("training losses DP x%d: %s" % (world, ["%.6f" % v for v in dp_losses]))
+    worst = max(abs(a - b) / abs(a) for a, b in zip(ref_losses, dp_losses))
+    sd = m2.state_dict()
+    pdiff = max((sd[k].float() - ref_state[k].float()).abs().max().item() for k in sd if sd[k].dtype.is_floating_point
+                and "running" not in k)
+    rdiff = max((sd[k].float() - ref_state[k].float()).abs().max().item() for k in sd if "running" in k)
+    print("max rel loss dev %.2e ; max |param diff| %.2e (lr 1e-5 x %d steps) ; max |running stat diff| %.2e"
+          % (worst, pdiff, steps, rdiff))
+    print("DP CHECK", "OK" if worst < 1e-2 and pdiff < 2.5e-5 and rdiff < 1e-3 else "FAILED", flush=True)
+dist.destroy_process_group()
