@@ -355,6 +355,7 @@ def bench_train(a, dev, rank, world, barrier):
     if rank != 0:
         return None
     ops.TIMING = []
+    eng.world = 1            # per-kernel timing pass on rank 0 alone: no collective (the other ranks have moved on)
     step_dev(0)
     torch.cuda.synchronize()
     agg = {}

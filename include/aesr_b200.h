@@ -124,10 +124,12 @@ int aesr_bn_apply(const void* a, const float* scale, const float* shift, void* o
                   int dtype, void* stream);
 /* Backward of [LeakyReLU ->] BatchNorm(train) -> pool/upsample: dnext bf16 (gradient of the pooled / upsampled tensor),
  * a = saved post-activation input of the BN; g_out bf16 [N,H,W,C] = gradient w.r.t. the producing conv's
- * pre-activation output; dgamma / dbeta accumulated; sums = 2*C floats of scratch. */
+ * pre-activation output; dgamma / dbeta accumulated; sums = 2*C floats of scratch.
+ * phase 0 = reduce + apply; 1 = reduce only (sums[c] = sum dy, sums[C+c] = sum dy*xhat); 2 = apply only -- a data-parallel
+ * caller all-reduces `sums` between 1 and 2 and passes the GLOBAL element count (`count` <= 0: local N*H*W). */
 int aesr_bn_bwd(const void* dnext, const void* a, const float* mean, const float* invstd, const float* gamma,
                 float* sums, float slope, void* g_out, float* dgamma, float* dbeta, int N, int H, int W, int C, int mode,
-                int dtype, void* stream);
+                int dtype, int phase, float count, void* stream);
 /* F.mse_loss(a, b) (kwatsch/base_trainer.py:177): *loss_acc += mean((a-b)^2); d (optional) = grad_scale * 2 (a-b)/n. */
 int aesr_mse(const float* a, const float* b, size_t n, float* loss_acc, float* d, float grad_scale, void* stream);
 /* Backward of dec.14 + Sigmoid: g_in bf16 (includes LeakyReLU'(a_in)), dw9c[9*C] and dbias accumulated. */

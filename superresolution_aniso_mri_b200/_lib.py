@@ -32,7 +32,7 @@ _SIGNATURES = {
     # training step
     "aesr_bn_finalize": (I, [P, F, P, P, P, P, F, F, P, P, P, P, I, P]),
     "aesr_bn_apply": (I, [P, P, P, P, I, I, I, I, I, I, P]),
-    "aesr_bn_bwd": (I, [P, P, P, P, P, P, F, P, P, P, I, I, I, I, I, I, P]),
+    "aesr_bn_bwd": (I, [P, P, P, P, P, P, F, P, P, P, I, I, I, I, I, I, I, F, P]),
     "aesr_mse": (I, [P, P, c_size_t, P, P, F, P]),
     "aesr_head_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
     "aesr_e0_bwd": (I, [P, P, P, P, I, I, I, I, P]),

@@ -189,6 +189,8 @@ int launch_halo(const void* x, const void* w, ConvParams p, cudaStream_t stream)
     int stages = CONV_MAX_STAGES;
     while (stages > 2 && S::total_bytes(p.BN, p.Cin, stages) > g_max_smem_optin) --stages;
     p.num_stages = stages;
+    // two issuers are only safe when neither can run a full stage ring ahead of the producer's fills (parity aliasing)
+    p.num_issuers = (stages > p.Cin / KC) ? CONV_ISSUERS : 1;
     CUtensorMap tx, tw;
     int rc = make_act_tmap(&tx, x, p.N, p.H, p.W, p.Cin, KC, HALO_W, HALO_H);
     if (rc != AESR_OK) return rc;

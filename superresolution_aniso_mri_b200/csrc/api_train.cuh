@@ -43,28 +43,34 @@ int aesr_bn_apply(const void* a, const float* scale, const float* shift, void* o
 
 int aesr_bn_bwd(const void* dnext, const void* a, const float* mean, const float* invstd, const float* gamma,
                 float* sums, float slope, void* g_out, float* dgamma, float* dbeta, int N, int H, int W, int C, int mode,
-                int dtype, void* stream) {
+                int dtype, int phase, float count, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!dnext || !a || !mean || !invstd || !gamma || !sums || !g_out || !dgamma || !dbeta || C % 32 != 0 || mode < 0 || mode > 2)
         return fail(AESR_ERR_INVALID, "bn_bwd: bad arguments");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t npix = static_cast<size_t>(N) * H * W;
-    CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), s));
+    const bool do_reduce = phase != 2, do_apply = phase != 1;
+    if (do_reduce) CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), s));
     int gx = static_cast<int>((npix + 63) / 64);
     const int capx = g_sm_count * 8 / (C / 32);
     if (gx > capx) gx = capx;
     if (gx < 1) gx = 1;
     dim3 grid(gx, C / 32), block(32, 8);
     const size_t total = npix * C;
-    const float count = static_cast<float>(npix);
+    if (count <= 0.f) count = static_cast<float>(npix);       // global-batch count in SyncBN mode
+    // phase 0: the apply kernel banks dgamma / dbeta from the (local) sums; phase 1 banks them right after the local
+    // reduce; phase 2 (sums all-reduced by the caller) must not bank them again.
+    float* dg_apply = phase == 0 ? dgamma : nullptr;
+    float* db_apply = phase == 0 ? dbeta : nullptr;
     if (dtype == AESR_DT_FP16) {
-        bn_bwd_reduce_kernel<true><<<grid, block, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode);
-        bn_bwd_apply_kernel<true><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, slope, static_cast<uint16_t*>(g_out), dgamma, dbeta, N, H, W, C, mode);
+        if (do_reduce) bn_bwd_reduce_kernel<true><<<grid, block, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode);
+        if (do_apply) bn_bwd_apply_kernel<true><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, slope, static_cast<uint16_t*>(g_out), dg_apply, db_apply, N, H, W, C, mode);
     } else {
-        bn_bwd_reduce_kernel<false><<<grid, block, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode);
-        bn_bwd_apply_kernel<false><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, slope, static_cast<uint16_t*>(g_out), dgamma, dbeta, N, H, W, C, mode);
+        if (do_reduce) bn_bwd_reduce_kernel<false><<<grid, block, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode);
+        if (do_apply) bn_bwd_apply_kernel<false><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, slope, static_cast<uint16_t*>(g_out), dg_apply, db_apply, N, H, W, C, mode);
     }
+    if (phase == 1) bn_bwd_accum_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, dgamma, dbeta, C);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return check_launch("bn_bwd");
 }

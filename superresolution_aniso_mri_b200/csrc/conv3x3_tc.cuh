@@ -45,6 +45,8 @@ struct ConvParams {
     int BN;                 // output channels per tile (multiple of 32, <= 256, divides Cout)
     int tiles_x, tiles_y, n_blocks, num_tiles;   // num_tiles = spatial tiles (N * tiles_y * tiles_x) * n_blocks
     int num_stages;
+    int num_issuers;        // MMA-issuing threads in use (halo kernel): 2 when the stage ring is deeper than one tile's
+                            // K-chunks, else 1 (an issuer one full ring ahead would alias the mbarrier phase parity)
     int fp16;               // 1: activations / weights are fp16, 0: bf16
     int debug;              // profiling only (AESR_CONV_DEBUG): bit0 = skip the MMAs, bit1 = skip the activation TMA loads
     // epilogue
@@ -412,7 +414,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         // 672 threads).  Stages and accumulators are assigned by tile index: each thread steps them by two tiles.
         const int issuer = warp - 1;
         const int num_acc = conv_num_acc(p.BN);
-        if (lane == 0 && active) {
+        const int n_iss = p.num_issuers;
+        if (lane == 0 && active && issuer < n_iss) {
             const uint32_t idesc = make_idesc_16(CONV_TILE_M, p.BN, p.fp16);
             int stage = 0;
             uint32_t phase = 0;
@@ -431,7 +434,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             const uint32_t a_lo0 = static_cast<uint32_t>(a_tmpl), b_lo0 = static_cast<uint32_t>(b_tmpl);
             const uint32_t b_blk16 = static_cast<uint32_t>(b_block) >> 4;
             const uint32_t b_tap16 = b_blk16 * kchunks;
-            for (int sp = first + issuer * ctas_per_nb; sp < sp_tiles; sp += CONV_ISSUERS * ctas_per_nb) {
+            for (int sp = first + issuer * ctas_per_nb; sp < sp_tiles; sp += n_iss * ctas_per_nb) {
                 mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * p.BN;
@@ -456,9 +459,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
                 if (p.debug & 32) mbar_arrive(&bars.tmem_full[acc]); else umma_commit(&bars.tmem_full[acc]);
-                acc += CONV_ISSUERS;                        // skip the other issuer's tile
+                acc += n_iss;                               // skip the other issuer's tile
                 if (acc >= num_acc) { acc -= num_acc; acc_phase ^= 1; }
-                for (int i = 0; i < (CONV_ISSUERS - 1) * kchunks; ++i)
+                for (int i = 0; i < (n_iss - 1) * kchunks; ++i)
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
         }

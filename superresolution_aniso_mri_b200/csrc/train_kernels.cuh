@@ -147,7 +147,7 @@ __global__ void bn_bwd_apply_kernel(const uint16_t* __restrict__ dnext, const ui
                                     float slope, uint16_t* __restrict__ g_out, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, int N, int H, int W, int C, int mode) {
     const size_t total = static_cast<size_t>(N) * H * W * C;
-    if (blockIdx.x == 0)
+    if (blockIdx.x == 0 && dgamma != nullptr)
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
             atomicAdd(dgamma + c, sums[C + c]);
             atomicAdd(dbeta + c, sums[c]);
@@ -164,6 +164,17 @@ __global__ void bn_bwd_apply_kernel(const uint16_t* __restrict__ dnext, const ui
         float g = gamma[c] * invstd[c] * (dy - sums[c] / count - xh * sums[C + c] / count);
         g *= av > 0.f ? 1.f : slope;
         g_out[i] = __bfloat16_as_ushort(__float2bfloat16_rn(g));
+    }
+}
+
+// SyncBN: dgamma / dbeta come from the LOCAL sums (the gradient all-reduce averages them over ranks), while the apply
+// pass uses the all-reduced sums.  This tiny kernel banks the local sums between the two.
+__global__ void bn_bwd_accum_kernel(const float* __restrict__ sums, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) {
+        dgamma[c] += sums[C + c];
+        dbeta[c] += sums[c];
     }
 }
 

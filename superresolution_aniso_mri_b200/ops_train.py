@@ -37,17 +37,28 @@ def bn_apply(a, scale, shift, mode):
     return out
 
 
-def bn_bwd(dnext, a, mean, invstd, gamma, dgamma, dbeta, mode, slope=0.01):
-    """dnext bf16 (grad of pooled / upsampled BN output), a saved activation -> g bf16 [N,H,W,C]."""
+def bn_bwd(dnext, a, mean, invstd, gamma, dgamma, dbeta, mode, slope=0.01, sync_world: int = 1):
+    """dnext bf16 (grad of pooled / upsampled BN output), a saved activation -> g bf16 [N,H,W,C].
+    sync_world > 1 (SyncBN parity mode): the per-channel sums are all-reduced between the reduce and apply kernels."""
     lib = _dev(a)
     n, h, w, c = a.shape
     assert dnext.dtype == GRAD_DTYPE and dnext.is_contiguous()
     g = torch.empty((n, h, w, c), dtype=GRAD_DTYPE, device=a.device)
     sums = torch.empty(2 * c, dtype=torch.float32, device=a.device)
-    with _timed("bn_bwd"):
+
+    def call(phase, count):
         _lib.check(lib.aesr_bn_bwd(dnext.data_ptr(), a.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
                                    sums.data_ptr(), float(slope), g.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), n,
-                                   h, w, c, mode, dt_code(a.dtype), _stream(a)), "bn_bwd")
+                                   h, w, c, mode, dt_code(a.dtype), phase, float(count), _stream(a)), "bn_bwd")
+    with _timed("bn_bwd"):
+        if sync_world > 1:
+            import torch.distributed as dist
+            call(1, 0)
+            dist.all_reduce(sums)
+            call(2, n * h * w * sync_world)
+            # dgamma / dbeta were accumulated from the GLOBAL sums on every rank; the gradient all-reduce averages them
+        else:
+            call(0, 0)
     return g
 
 

@@ -195,7 +195,8 @@ class TrainEngine(TrainForward):
                 bnrec = recs[k - 1].bn
                 dnext = ops.conv3x3(g, wt, None)
                 g = T.bn_bwd(dnext, bnrec.a, bnrec.mean, bnrec.invstd, bnrec.bn.weight,
-                             self.grad[id(bnrec.bn.weight)], self.grad[id(bnrec.bn.bias)], bnrec.mode, SLOPE)
+                             self.grad[id(bnrec.bn.weight)], self.grad[id(bnrec.bn.bias)], bnrec.mode, SLOPE,
+                             sync_world=self.world if self.sync_bn else 1)
             elif r.prev == "e0":
                 d_a0 = ops.conv3x3(g, wt, None)
                 e0 = self.model.enc[0]

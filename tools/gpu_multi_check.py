@@ -73,6 +73,17 @@ for s in range(steps):
     t = torch.tensor([e2.logged_losses(res)["loss_ae"]], device=dev, dtype=torch.float64)
     dist.all_reduce(t)                    # equal shard sizes: mean of per-rank means = global mean
     dp_losses.append(float(t.item()) / world)
+# diagnostics: (i) same global batch on every rank with SyncBN (must equal single), (ii) shards without SyncBN
+for tag, sync, shard in (("full-batch-on-each-rank+sync", True, False), ("sharded-nosync", False, True)):
+    m3 = model_from(st0, train=True)
+    e3 = TrainEngine(m3, None, sync_bn=sync)
+    img, mid = acdc_batch(0)
+    lb = P.shard_batch_pairs({"image": img, "slice_between": mid}, rank, world) if shard else {"image": img, "slice_between": mid}
+    b = lb["slice_between"].shape[0]
+    w = torch.full((b,), 0.5, device=dev)
+    res = e3.step(lb["image"].to(dev), lb["slice_between"].to(dev), w, w, lpips=lp, ex_loss_weight=0.05, lr=1e-5)
+    lg = e3.logged_losses(res)
+    print("rank %d %s: loss_ae %.6f dist %.6f extra %.6f" % (rank, tag, lg["loss_ae"], lg["loss_ae_dist"], lg["loss_ae_dist_extra"]), flush=True)
 if rank == 0:
     print("training losses single:", ["%.6f" % v for v in ref_losses])
     print("training losses DP x%d: %s" % (world, ["%.6f" % v for v in dp_losses]))
