@@ -94,5 +94,7 @@ if rank == 0:
     rdiff = max((sd[k].float() - ref_state[k].float()).abs().max().item() for k in sd if "running" in k)
     print("max rel loss dev %.2e ; max |param diff| %.2e (lr 1e-5 x %d steps) ; max |running stat diff| %.2e"
           % (worst, pdiff, steps, rdiff))
-    print("DP CHECK", "OK" if worst < 1e-2 and pdiff < 2.5e-5 and rdiff < 1e-3 else "FAILED", flush=True)
+    # parameters: Adam's first steps are sign-like (|update| ~ lr whatever the gradient size), so fp32-atomic ordering
+    # noise on near-zero gradients can flip an update: allow 2 * steps * lr.
+    print("DP CHECK", "OK" if worst < 1e-3 and pdiff < 2.05 * steps * 1e-5 and rdiff < 1e-3 else "FAILED", flush=True)
 dist.destroy_process_group()
