@@ -237,12 +237,12 @@ def run_ours(a):
         ops.TIMING = []
         step_device()
         torch.cuda.synchronize()
-        conv_ms = sum(e0.elapsed_time(e1) for name, e0, e1, fl in ops.TIMING if name == "conv3x3")
-        conv_fl = sum(fl for name, e0, e1, fl in ops.TIMING if name == "conv3x3")
+        conv_ms = sum(e0.elapsed_time(e1) for name, e0, e1, fl, _d in ops.TIMING if name == "conv3x3")
+        conv_fl = sum(fl for name, e0, e1, fl, _d in ops.TIMING if name == "conv3x3")
         n_conv = sum(1 for t in ops.TIMING if t[0] == "conv3x3")
-        all_ms = sum(e0.elapsed_time(e1) for name, e0, e1, fl in ops.TIMING)
+        all_ms = sum(e0.elapsed_time(e1) for name, e0, e1, fl, _d in ops.TIMING)
         kernel_ms = {}
-        for name, e0, e1, fl in ops.TIMING:
+        for name, e0, e1, fl, _d in ops.TIMING:
             kernel_ms[name] = kernel_ms.get(name, 0.0) + e0.elapsed_time(e1)
         ops.TIMING = None
         ach = conv_fl / (conv_ms * 1e-3) / 1e12
@@ -359,7 +359,7 @@ def bench_train(a, dev, rank, world, barrier):
     step_dev(0)
     torch.cuda.synchronize()
     agg = {}
-    for name, e0, e1, fl in ops.TIMING:
+    for name, e0, e1, fl, _d in ops.TIMING:
         agg[name] = agg.get(name, 0.0) + e0.elapsed_time(e1)
     ops.TIMING = None
     cpu_rate, cores, cpu_dt = cpu_train_rate(2)

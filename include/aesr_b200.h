@@ -47,6 +47,9 @@ extern "C" {
 #define AESR_OUT_UP2 2           /* nn.Upsample(scale_factor=2) nearest networks/acai_vanilla.py:92  */
 #define AESR_OUT_NCHW_F32 3      /* public latent: NCHW fp32 (+ optional NHWC 16-bit copy in out2) */
 #define AESR_OUT_SAME_MAXPOOL2 4 /* full-res tap + nn.MaxPool2d(2) in out2  (VGG16 slices) */
+#define AESR_OUT_SHUFFLE2 5      /* nn.Upsample(2) + the NEXT nn.Conv2d folded into one low-res conv with 4*C phase
+                                    channels (weights from aesr_pack_conv3x3_weight_up2fold) + depth-to-space store:
+                                    networks/acai_vanilla.py:92 followed by :87 / :96.  out NHWC 16-bit [N,2H,2W,Cout/4] */
 
 #define AESR_MUL_NONE 0
 #define AESR_MUL_LEAKY_GRAD 1 /* dgrad epilogue: multiply by LeakyReLU'(mul_src) */
@@ -79,6 +82,37 @@ int aesr_pack_conv3x3_weight(const float* w, void* packed, int Cout, int Cin, in
 int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, const float* scale, const float* shift,
                      void* out, void* out2, const void* mul_src, float* stats, int N, int H, int W, int Cin, int Cout,
                      int act, float slope, int out_mode, int mul_mode, int dtype, int algo, void* stream);
+
+/* Folded filter bank for AESR_OUT_SHUFFLE2: fp32 [Cout,Cin,3,3] -> 16-bit [9 low-res taps][4 phases][Cout][Cin],
+ * phase 2a+b = hi-res pixel (2y+a, 2x+b); each entry is the sum of the original taps that read the same low-res
+ * pixel of the nearest-upsampled input (exact in real arithmetic; sums formed in fp32, rounded once). */
+int aesr_pack_conv3x3_weight_up2fold(const float* w, void* packed, int Cout, int Cin, int dtype, void* stream);
+
+/* Decoder tail, first half: nn.Upsample(2) -> nn.Conv2d(32,32,3,padding=1) + LeakyReLU -> nn.Conv2d(32,1,3,padding=1)
+ * (networks/acai_vanilla.py:92,96-98) in one tensor-core kernel.  x NHWC 16-bit [N,H,W,Cin] is the LOW-res input of the
+ * upsample, w_folded the [9][128][Cin] bank of aesr_pack_conv3x3_weight_up2fold, head_w9c_host fp32 [9][32] the head
+ * filter in HOST memory (the one host pointer of this ABI: it is passed to the kernel by value so that the epilogue reads
+ * it from the constant bank; copied before the call returns).
+ * The 32-channel hi-res activation stays in registers; per low-res pixel the kernel writes the 4x4 patch (origin
+ * (2y-1, 2x-1)) of head-conv partial sums of its 2x2 hi-res block: partial fp32 [N,H,W,16]. */
+int aesr_conv3x3_up2_head_fwd(const void* x, const void* w_folded, const float* bias, const float* head_w9c_host,
+                              float* partial, int N, int H, int W, int Cin, int act, float slope, int dtype, int algo,
+                              void* stream);
+
+/* Decoder tail, second half: out(Y,X) = sigmoid(bias + the (up to) four overlapping patch entries), clamp(0,1)
+ * (networks/acai_vanilla.py:98, generate_hr_volumes.py:67).  partial fp32 [N,h,w,16]; image n ([2h,2w] fp32) is written at
+ * out + (out_index ? out_index[n] : n) * out_image_stride. */
+int aesr_head_gather(const float* partial, const float* bias, float* out, const int* out_index, int N, int h, int w,
+                     size_t out_image_stride, int apply_sigmoid, void* stream);
+
+/* Encoder stem: enc.0 nn.Conv2d(1,32,1,padding=1) and enc.1 nn.Conv2d(32,32,3,padding=1) + LeakyReLU
+ * (networks/acai_vanilla.py:51,55-56) composed into one 3x3 conv on the single input channel (both are linear).
+ * aesr_stem_fold: weff[tap][co] = sum_ci w1[co][ci][tap]*w0[ci], beff likewise with b0 (once per parameter version).
+ * aesr_stem_fwd: x fp32 [N,1,H,W] -> NHWC 16-bit [N,H+2,W+2,32]; border taps that fall off the (H+2)x(W+2) grid drop
+ * their bias term, ring pixels see x = 0, exactly as the two zero paddings of the reference do. */
+int aesr_stem_fold(const float* w0, const float* b0, const float* w1, float* weff, float* beff, int C, void* stream);
+int aesr_stem_fwd(const float* x, const float* weff, const float* beff, const float* b1, void* out, int N, int H, int W,
+                  int C, float slope, int dtype, void* stream);
 
 /* enc.0: nn.Conv2d(1, C, 1, padding=1) (networks/acai_vanilla.py:51).  x fp32 [N,1,H,W] -> NHWC 16-bit [N,H+2,W+2,C]. */
 int aesr_e0_fwd(const float* x, const float* w, const float* b, void* out, int N, int H, int W, int C, int dtype,
@@ -195,6 +229,16 @@ int aesr_pad_crop_gather(const float* in, float* out, const int* top, const int*
  * out fp32 [128][64] raw accumulators. */
 int aesr_probe_halo_conv(const void* x, const void* w_packed, float* out, int N, int H, int W, int x0, int y0, int n,
                          int pitch, int variant, void* stream);
+
+/* Diagnostic: cycles for `iters` back-to-back tcgen05.mma (M=128, N, K=16) with the A descriptor's start shifted by
+ * `shift_rows` rows, 8-row-group stride `pitch_rows`, advancing `a_advance_rows` rows between MMAs, rotating over `nacc`
+ * TMEM accumulators (tools/umma_rate.py). */
+int aesr_probe_umma_rate(long long* cycles, int N, int kc, int pitch_rows, int shift_rows, int iters,
+                         int a_advance_rows, int nacc, void* stream);
+
+/* Diagnostic: mbarrier round-trip latency between two warps (mode bit 0: signal with tcgen05.commit, bit 1: poll with
+ * test_wait instead of try_wait, bit 2: three waiting warps).  cycles[0] = total cycles for `iters` round trips. */
+int aesr_probe_sync(long long* cycles, int iters, int mode, void* stream);
 
 #ifdef __cplusplus
 }

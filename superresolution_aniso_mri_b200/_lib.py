@@ -23,12 +23,19 @@ _SIGNATURES = {
     "aesr_launch_count": (c_int64, []),
     "aesr_pack_conv3x3_weight": (I, [P, P, I, I, I, I, P]),
     "aesr_conv3x3_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, F, I, I, I, I, P]),
+    "aesr_pack_conv3x3_weight_up2fold": (I, [P, P, I, I, I, P]),
+    "aesr_conv3x3_up2_head_fwd": (I, [P, P, P, P, P, I, I, I, I, I, F, I, I, P]),
+    "aesr_head_gather": (I, [P, P, P, P, I, I, I, c_size_t, I, P]),
+    "aesr_stem_fold": (I, [P, P, P, P, P, I, P]),
+    "aesr_stem_fwd": (I, [P, P, P, P, P, I, I, I, I, F, I, P]),
     "aesr_e0_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
     "aesr_head_fwd": (I, [P, P, P, P, P, I, I, I, I, c_size_t, I, I, P]),
     "aesr_lerp_latents": (I, [P, P, P, P, P, P, P, I, I, I, I, P]),
     "aesr_place_slices": (I, [P, P, P, I, I, I, P]),
     "aesr_lerp_pairs": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "aesr_probe_halo_conv": (I, [P, P, P, I, I, I, I, I, I, I, I, P]),
+    "aesr_probe_umma_rate": (I, [P, I, I, I, I, I, I, I, P]),
+    "aesr_probe_sync": (I, [P, I, I, P]),
     # training step
     "aesr_bn_finalize": (I, [P, F, P, P, P, P, F, F, P, P, P, P, I, P]),
     "aesr_bn_apply": (I, [P, P, P, P, I, I, I, I, I, I, P]),

@@ -135,6 +135,30 @@ __global__ void pack_conv3x3_weight_kernel(const float* __restrict__ w, uint16_t
     }
 }
 
+// "nearest x2 upsample -> 3x3 conv" folded to the low resolution (conv3x3_tc.cuh OUT_SHUFFLE2): destination
+// [tap = (dy,dx) low-res offset][phase = 2a+b][co][ci] = sum of the original taps (ky,kx) that read low-res offset
+// (dy,dx) when producing hi-res pixel (2y+a, 2x+b):  a = 0: dy=0 <- {ky=0}, dy=1 <- {1,2};  a = 1: dy=1 <- {0,1}, dy=2 <- {2}.
+template <bool FP16>
+__global__ void pack_conv3x3_weight_up2fold_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cout,
+                                                   int Cin) {
+    const int total = 9 * 4 * Cout * Cin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ci = i % Cin;
+        const int co = (i / Cin) % Cout;
+        const int ph = (i / (Cin * Cout)) & 3;
+        const int tap = i / (Cin * Cout * 4);
+        const int a = ph >> 1, b = ph & 1, dy = tap / 3, dx = tap % 3;
+        const int my = a == 0 ? (dy == 0 ? 1 : dy == 1 ? 6 : 0) : (dy == 0 ? 0 : dy == 1 ? 3 : 4);   // bit ky set
+        const int mx = b == 0 ? (dx == 0 ? 1 : dx == 1 ? 6 : 0) : (dx == 0 ? 0 : dx == 1 ? 3 : 4);
+        const float* wk = w + (static_cast<size_t>(co) * Cin + ci) * 9;
+        float v = 0.f;
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx)
+                if (((my >> ky) & 1) && ((mx >> kx) & 1)) v += wk[ky * 3 + kx];
+        out[i] = cvt16_t<FP16>(v);
+    }
+}
+
 template <typename K>
 int set_max_smem(K kernel, int* configured) {
     if (!*configured) {
@@ -173,9 +197,33 @@ int halo_pick_bn(int Cin, int Cout) {
     using S = HaloSmem<KC>;
     for (int bn = Cout <= 256 ? Cout : 256; bn >= 32; bn -= 32) {
         if (Cout % bn != 0) continue;
-        if (S::total_bytes(bn, Cin, 2) <= g_max_smem_optin) return bn;
+        if (S::total_bytes(bn, Cin, 1, 2) <= g_max_smem_optin) return bn;
     }
     return 0;
+}
+
+// M-tiles per super-tile: the largest of {4, 2, 1} that (a) is not taller than the image needs, (b) leaves room for two
+// TMEM buffers of T accumulators, (c) still fits >= 3 activation stages next to the resident filter bank (2 for T = 1).
+template <int KC>
+void halo_pick_T(int BN, int Cin, int tiles_y, int* T_out, int* stages_out) {
+    using S = HaloSmem<KC>;
+    const int kchunks = Cin / KC;
+    const int forced = getenv("AESR_CONV_T") ? atoi(getenv("AESR_CONV_T")) : 0;     // profiling only
+    for (int T = 4; T >= 1; T >>= 1) {
+        if (forced && T != forced && T != 1) continue;
+        if (T > 1 && tiles_y <= T / 2) continue;
+        if (2 * T * BN > 512) continue;
+        int stages = CONV_MAX_STAGES;
+        while (stages > 1 && S::total_bytes(BN, Cin, T, stages) > g_max_smem_optin) --stages;
+        const int need = (T == 1) ? 2 : (kchunks > 1 ? 2 * kchunks : 3);
+        if (S::total_bytes(BN, Cin, T, stages) <= g_max_smem_optin && (stages >= need || T == 1)) {
+            *T_out = T;
+            *stages_out = stages;
+            return;
+        }
+    }
+    *T_out = 1;
+    *stages_out = 2;
 }
 
 template <int KC>
@@ -184,25 +232,38 @@ int launch_halo(const void* x, const void* w, ConvParams p, cudaStream_t stream)
     p.BN = halo_pick_bn<KC>(p.Cin, p.Cout);
     if (p.BN == 0) return fail(AESR_ERR_INVALID, "conv3x3_fwd: filter bank %dx%d does not fit the halo kernel", p.Cout, p.Cin);
     p.n_blocks = p.Cout / p.BN;
-    const int sp_tiles = p.N * p.tiles_x * p.tiles_y;
-    p.num_tiles = sp_tiles * p.n_blocks;
-    int stages = CONV_MAX_STAGES;
-    while (stages > 2 && S::total_bytes(p.BN, p.Cin, stages) > g_max_smem_optin) --stages;
+    int T = 1, stages = 2;
+    halo_pick_T<KC>(p.BN, p.Cin, p.tiles_y, &T, &stages);
+    p.T = T;
+    p.stiles_y = (p.tiles_y + T - 1) / T;
     p.num_stages = stages;
-    // two issuers are only safe when neither can run a full stage ring ahead of the producer's fills (parity aliasing)
-    p.num_issuers = (stages > p.Cin / KC) ? CONV_ISSUERS : 1;
+    const int st_total = p.N * p.tiles_x * p.stiles_y;
+    p.num_tiles = st_total * p.n_blocks;
     CUtensorMap tx, tw;
-    int rc = make_act_tmap(&tx, x, p.N, p.H, p.W, p.Cin, KC, HALO_W, HALO_H);
+    int rc = make_act_tmap(&tx, x, p.N, p.H, p.W, p.Cin, KC, HALO_W, CONV_TILE_H * T + 2);
     if (rc != AESR_OK) return rc;
     rc = make_wgt_tmap(&tw, w, 9 * p.Cout, p.Cin, KC, p.BN);
     if (rc != AESR_OK) return rc;
-    static int configured = 0;
-    rc = set_max_smem(conv3x3_halo_kernel<KC>, &configured);
-    if (rc != AESR_OK) return rc;
     int per_nb = g_sm_count / p.n_blocks;
     if (per_nb < 1) per_nb = 1;
-    if (per_nb > sp_tiles) per_nb = sp_tiles;
-    conv3x3_halo_kernel<KC><<<per_nb * p.n_blocks, CONV_THREADS, S::total_bytes(p.BN, p.Cin, stages), stream>>>(tx, tw, p);
+    if (per_nb > st_total) per_nb = st_total;
+    const int smem = S::total_bytes(p.BN, p.Cin, T, stages);
+    const int grid = per_nb * p.n_blocks;
+    // inference instantiations (output stage compiled in, no training extras) vs the fully dynamic one
+    const bool plain = p.mul_mode == MUL_NONE && p.stats == nullptr && p.out2 == nullptr;
+#define AESR_HALO(MODE)                                                                              \
+    {                                                                                                \
+        static int configured = 0;                                                                   \
+        rc = set_max_smem(conv3x3_halo_kernel<KC, MODE>, &configured);                               \
+        if (rc != AESR_OK) return rc;                                                                \
+        conv3x3_halo_kernel<KC, MODE><<<grid, CONV_THREADS, smem, stream>>>(tx, tw, p);              \
+    }
+    if (p.out_mode == OUT_SHUFFLE2_HEAD) AESR_HALO(OUT_SHUFFLE2_HEAD)
+    else if (plain && p.out_mode == OUT_SAME) AESR_HALO(OUT_SAME)
+    else if (plain && p.out_mode == OUT_AVGPOOL2) AESR_HALO(OUT_AVGPOOL2)
+    else if (plain && p.out_mode == OUT_SHUFFLE2) AESR_HALO(OUT_SHUFFLE2)
+    else AESR_HALO(-1)
+#undef AESR_HALO
     return check_launch("conv3x3_halo");
 }
 
@@ -234,9 +295,25 @@ int aesr_pack_conv3x3_weight(const float* w, void* packed, int Cout, int Cin, in
     return check_launch("pack_conv3x3_weight");
 }
 
-int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, const float* scale, const float* shift,
-                     void* out, void* out2, const void* mul_src, float* stats, int N, int H, int W, int Cin, int Cout,
-                     int act, float slope, int out_mode, int mul_mode, int dtype, int algo, void* stream) {
+int aesr_pack_conv3x3_weight_up2fold(const float* w, void* packed, int Cout, int Cin, int dtype, void* stream) {
+    if (!w || !packed || Cout <= 0 || Cin <= 0) return fail(AESR_ERR_INVALID, "pack_conv3x3_weight_up2fold: bad arguments");
+    const int total = 36 * Cout * Cin;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == AESR_DT_FP16)
+        pack_conv3x3_weight_up2fold_kernel<true><<<(total + 255) / 256, 256, 0, s>>>(w, static_cast<uint16_t*>(packed), Cout, Cin);
+    else
+        pack_conv3x3_weight_up2fold_kernel<false><<<(total + 255) / 256, 256, 0, s>>>(w, static_cast<uint16_t*>(packed), Cout, Cin);
+    return check_launch("pack_conv3x3_weight_up2fold");
+}
+
+}  // extern "C"
+
+namespace {
+// shared by the conv entry points: validate, fill ConvParams, pick the kernel
+int conv3x3_dispatch(const void* x, const void* w_packed, const float* bias, const float* scale, const float* shift,
+                     void* out, void* out2, const void* mul_src, float* stats, const float* head_w, int N, int H, int W,
+                     int Cin, int Cout, int act, float slope, int out_mode, int mul_mode, int dtype, int algo,
+                     void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!x || !w_packed || !out) return fail(AESR_ERR_INVALID, "conv3x3_fwd: null tensor");
@@ -245,8 +322,12 @@ int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, con
         return fail(AESR_ERR_INVALID, "conv3x3_fwd: Cin=%d unsupported (32, 64, 128, 256, 512)", Cin);
     if (Cout % 32 != 0 || Cout < 32 || Cout > 512) return fail(AESR_ERR_INVALID, "conv3x3_fwd: Cout=%d unsupported", Cout);
     if ((scale == nullptr) != (shift == nullptr)) return fail(AESR_ERR_INVALID, "conv3x3_fwd: scale/shift must come together");
-    if (out_mode < 0 || out_mode > 4) return fail(AESR_ERR_INVALID, "conv3x3_fwd: out_mode=%d", out_mode);
+    if (out_mode < 0 || out_mode > 6) return fail(AESR_ERR_INVALID, "conv3x3_fwd: out_mode=%d", out_mode);
     if (out_mode == AESR_OUT_SAME_MAXPOOL2 && !out2) return fail(AESR_ERR_INVALID, "conv3x3_fwd: maxpool needs out2");
+    if (out_mode == AESR_OUT_SHUFFLE2 && Cout % 128 != 0)
+        return fail(AESR_ERR_INVALID, "conv3x3_fwd: OUT_SHUFFLE2 needs Cout = 4*C with C a multiple of 32, got %d", Cout);
+    if (out_mode == OUT_SHUFFLE2_HEAD && (Cout != 128 || !head_w || scale || stats || mul_mode != AESR_MUL_NONE))
+        return fail(AESR_ERR_INVALID, "conv3x3_up2_head_fwd: needs Cout = 4*32, a head filter and a plain epilogue");
     if (mul_mode != AESR_MUL_NONE && !mul_src) return fail(AESR_ERR_INVALID, "conv3x3_fwd: mul_mode without mul_src");
     if (dtype != AESR_DT_BF16 && dtype != AESR_DT_FP16) return fail(AESR_ERR_INVALID, "conv3x3_fwd: dtype=%d", dtype);
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(out)) & 15)
@@ -264,6 +345,7 @@ int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, con
     p.bias = bias; p.scale = scale; p.shift = shift; p.slope = slope; p.act = act; p.out_mode = out_mode;
     p.out = out; p.out2 = out2; p.mul_src = static_cast<const uint16_t*>(mul_src); p.mul_mode = mul_mode;
     p.stats = stats;
+    if (head_w) memcpy(p.head_wc, head_w, sizeof(p.head_wc));      // HOST pointer: travels as a kernel parameter
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int KC = (Cin >= 64) ? 64 : 32;
@@ -273,9 +355,67 @@ int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, con
         halo = bn > 0;
         if (!halo && algo == AESR_ALGO_HALO)
             return fail(AESR_ERR_INVALID, "conv3x3_fwd: filter bank %dx%d too large for AESR_ALGO_HALO", Cout, Cin);
+        if (out_mode == OUT_SHUFFLE2_HEAD && bn != Cout) halo = false;     // all four phases must sit in one tile
     }
+    if (out_mode == OUT_SHUFFLE2_HEAD && !halo)
+        return fail(AESR_ERR_INVALID, "conv3x3_up2_head_fwd: Cin=%d: the 128-row folded bank must fit the resident-filter kernel", Cin);
     if (halo) return KC == 64 ? launch_halo<64>(x, w_packed, p, s) : launch_halo<32>(x, w_packed, p, s);
     return KC == 64 ? launch_stream<64>(x, w_packed, p, s) : launch_stream<32>(x, w_packed, p, s);
+}
+}  // namespace
+
+extern "C" {
+
+int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, const float* scale, const float* shift,
+                     void* out, void* out2, const void* mul_src, float* stats, int N, int H, int W, int Cin, int Cout,
+                     int act, float slope, int out_mode, int mul_mode, int dtype, int algo, void* stream) {
+    if (out_mode == OUT_SHUFFLE2_HEAD) return fail(AESR_ERR_INVALID, "conv3x3_fwd: use aesr_conv3x3_up2_head_fwd");
+    return conv3x3_dispatch(x, w_packed, bias, scale, shift, out, out2, mul_src, stats, nullptr, N, H, W, Cin, Cout, act,
+                            slope, out_mode, mul_mode, dtype, algo, stream);
+}
+
+int aesr_conv3x3_up2_head_fwd(const void* x, const void* w_folded, const float* bias, const float* head_w9c_host,
+                              float* partial, int N, int H, int W, int Cin, int act, float slope, int dtype, int algo,
+                              void* stream) {
+    return conv3x3_dispatch(x, w_folded, bias, nullptr, nullptr, partial, nullptr, nullptr, nullptr, head_w9c_host, N, H, W,
+                            Cin, 128, act, slope, OUT_SHUFFLE2_HEAD, AESR_MUL_NONE, dtype, algo, stream);
+}
+
+int aesr_head_gather(const float* partial, const float* bias, float* out, const int* out_index, int N, int h, int w,
+                     size_t out_image_stride, int apply_sigmoid, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!partial || !bias || !out || N <= 0 || h <= 0 || w <= 0) return fail(AESR_ERR_INVALID, "head_gather: bad arguments");
+    if ((out_image_stride & 1) || (reinterpret_cast<uintptr_t>(out) & 7))
+        return fail(AESR_ERR_INVALID, "head_gather: output images must be 8-byte aligned (even stride)");
+    if (static_cast<size_t>(h) * w > (1u << 28)) return fail(AESR_ERR_INVALID, "head_gather: image too large");
+    const dim3 grid((h * w + 255) / 256, N < 65535 ? N : 65535);
+    head_gather_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        partial, bias, out, out_index, N, h, w, out_image_stride, apply_sigmoid);
+    return check_launch("head_gather");
+}
+
+int aesr_stem_fold(const float* w0, const float* b0, const float* w1, float* weff, float* beff, int C, void* stream) {
+    if (!w0 || !b0 || !w1 || !weff || !beff || C != 32) return fail(AESR_ERR_INVALID, "stem_fold: bad arguments (C = 32)");
+    stem_fold_kernel<<<(9 * C + 95) / 96, 96, 0, static_cast<cudaStream_t>(stream)>>>(w0, b0, w1, weff, beff, C);
+    return check_launch("stem_fold");
+}
+
+int aesr_stem_fwd(const float* x, const float* weff, const float* beff, const float* b1, void* out, int N, int H, int W,
+                  int C, float slope, int dtype, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!x || !weff || !beff || !b1 || !out || N <= 0 || H <= 0 || W <= 0 || C != 32)
+        return fail(AESR_ERR_INVALID, "stem_fwd: bad arguments (C = 32)");
+    if (static_cast<size_t>(H + 2) * (W + 2) > (1u << 28)) return fail(AESR_ERR_INVALID, "stem_fwd: image too large");
+    const int per_img = (H + 2) * (W + 2) * 4;
+    const dim3 grid((per_img + 1023) / 1024, N < 65535 ? N : 65535);       // 4 items per thread
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == AESR_DT_FP16)
+        stem_conv_kernel<true><<<grid, 256, 0, s>>>(x, weff, beff, b1, static_cast<uint16_t*>(out), N, H, W, slope);
+    else
+        stem_conv_kernel<false><<<grid, 256, 0, s>>>(x, weff, beff, b1, static_cast<uint16_t*>(out), N, H, W, slope);
+    return check_launch("stem_conv");
 }
 
 int aesr_e0_fwd(const float* x, const float* w, const float* b, void* out, int N, int H, int W, int C, int dtype,
@@ -385,6 +525,35 @@ int aesr_probe_halo_conv(const void* x, const void* w_packed, float* out, int N,
     CUDA_TRY(cudaFuncSetAttribute(halo_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     halo_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(tx, tw, out, x0, y0, n, pitch, variant);
     return check_launch("halo_probe");
+}
+
+int aesr_probe_umma_rate(long long* cycles, int N, int kc, int pitch_rows, int shift_rows, int iters,
+                         int a_advance_rows, int nacc, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!cycles || N < 16 || N > 256 || N % 16 || (kc != 32 && kc != 64) || iters <= 0 || nacc < 1 || nacc * N > 512)
+        return fail(AESR_ERR_INVALID, "probe_umma_rate: bad arguments");
+    const int smem = 1024 + 160 * 1024;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+#define AESR_PROBE(NA)                                                                                             \
+    case NA:                                                                                                       \
+        CUDA_TRY(cudaFuncSetAttribute(umma_rate_probe_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        umma_rate_probe_kernel<NA><<<1, 128, smem, s>>>(cycles, N, kc, pitch_rows, shift_rows, iters, a_advance_rows); \
+        break;
+    switch (nacc) {
+        AESR_PROBE(1) AESR_PROBE(2) AESR_PROBE(4) AESR_PROBE(8)
+        default: return fail(AESR_ERR_INVALID, "probe_umma_rate: nacc must be 1, 2, 4 or 8");
+    }
+#undef AESR_PROBE
+    return check_launch("umma_rate_probe");
+}
+
+int aesr_probe_sync(long long* cycles, int iters, int mode, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!cycles || iters <= 0) return fail(AESR_ERR_INVALID, "probe_sync: bad arguments");
+    sync_probe_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(cycles, iters, mode);
+    return check_launch("sync_probe");
 }
 
 }  // extern "C"

@@ -37,6 +37,14 @@ enum ConvOut : int {
     OUT_UP2 = 2,           // out  = NHWC 16-bit [N,2H,2W,Cout]    (nearest)
     OUT_NCHW_F32 = 3,      // out  = NCHW fp32 [N,Cout,H,W]        (+ optional out2 = NHWC 16-bit copy)
     OUT_SAME_MAXPOOL2 = 4, // out  = NHWC 16-bit full res, out2 = NHWC 16-bit [N,H/2,W/2,Cout] 2x2 max
+    // "nearest x2 upsample followed by a 3x3 conv" folded into ONE 3x3 conv at the LOW resolution with 4*C output
+    // channels (row = phase * C + c, phase = 2a+b; filters pre-summed per phase, aesr_pack_conv3x3_weight_up2fold)
+    // followed by a depth-to-space store: channel block `phase` of low-res pixel (y,x) is pixel (2y+a, 2x+b).
+    OUT_SHUFFLE2 = 5,      // out  = NHWC 16-bit [N,2H,2W,Cout/4]
+    // same conv, but the C = 32 activations never leave the SM: the decoder head Conv2d(32,1,3,padding=1) is applied
+    // to the thread's 2x2 hi-res block and leaves a 4x4 patch of partial sums per LOW-res pixel (head_gather sums
+    // the four patches that overlap an output pixel, adds the bias and applies the sigmoid).
+    OUT_SHUFFLE2_HEAD = 6, // out  = fp32 [N,H,W,16]
 };
 enum ConvMul : int { MUL_NONE = 0, MUL_LEAKY_GRAD = 1, MUL_RELU_GRAD = 2 };
 
@@ -45,8 +53,7 @@ struct ConvParams {
     int BN;                 // output channels per tile (multiple of 32, <= 256, divides Cout)
     int tiles_x, tiles_y, n_blocks, num_tiles;   // num_tiles = spatial tiles (N * tiles_y * tiles_x) * n_blocks
     int num_stages;
-    int num_issuers;        // MMA-issuing threads in use (halo kernel): 2 when the stage ring is deeper than one tile's
-                            // K-chunks, else 1 (an issuer one full ring ahead would alias the mbarrier phase parity)
+    int T, stiles_y;        // halo kernel: M-tiles stacked vertically per super-tile, super-tile rows per image
     int fp16;               // 1: activations / weights are fp16, 0: bf16
     int debug;              // profiling only (AESR_CONV_DEBUG): bit0 = skip the MMAs, bit1 = skip the activation TMA loads
     // epilogue
@@ -63,13 +70,17 @@ struct ConvParams {
     int mul_mode;
     // optional per-channel statistics of the (post-activation, pre-affine) value: stats[c] += sum, stats[Cout+c] += sum^2
     float* stats;
+    // OUT_SHUFFLE2_HEAD: fp32 [9][32] filter of the 32 -> 1 head conv, BY VALUE: kernel parameters live in the constant
+    // bank, so the 1152 head MACs per thread read their weights as instruction operands (c[0][..]) instead of through
+    // 288 LDS.128 per thread and tile, which made the epilogue shared-memory-bandwidth-bound (191 -> see profiles/).
+    alignas(16) float head_wc[9 * 32];
 };
 
 constexpr int CONV_TILE_H = 16;
 constexpr int CONV_TILE_W = 8;
 constexpr int CONV_TILE_M = 128;
 constexpr int CONV_EPI_SETS = 4;                          // epilogue warp sets (4 warps = 128 TMEM lanes each)
-constexpr int CONV_ISSUERS = 2;                            // MMA-issuing threads (warps 1..CONV_ISSUERS)
+constexpr int CONV_ISSUERS = 1;                            // MMA-issuing warps (one elected thread each)
 constexpr int CONV_FIRST_EPI_WARP = 1 + CONV_ISSUERS;      // warp 0 TMA, warps 1-2 MMA issuers, then the epilogue sets
 constexpr int CONV_THREADS = 32 * CONV_FIRST_EPI_WARP + 128 * CONV_EPI_SETS;   // 608
 constexpr int CONV_MAX_STAGES = 8;
@@ -120,7 +131,8 @@ __device__ __forceinline__ uint32_t conv_tmem_cols(int BN) {
 }
 
 // Common prologue: barrier init, TMEM allocation (warp 1), epilogue constants.  Returns the TMEM base address.
-__device__ __forceinline__ uint32_t conv_prologue(const ConvParams& p, const ConvBarriers& bars, int num_stages) {
+__device__ __forceinline__ uint32_t conv_prologue(const ConvParams& p, const ConvBarriers& bars, int num_stages,
+                                                  uint32_t tmem_cols, uint32_t tmem_empty_count) {
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int s = 0; s < num_stages; ++s) {
@@ -129,16 +141,19 @@ __device__ __forceinline__ uint32_t conv_prologue(const ConvParams& p, const Con
         }
         for (int a = 0; a < CONV_EPI_SETS; ++a) {
             mbar_init(&bars.tmem_full[a], 1);
-            mbar_init(&bars.tmem_empty[a], 128);
+            mbar_init(&bars.tmem_empty[a], tmem_empty_count);   // one elected lane per epilogue warp
         }
         mbar_init(bars.b_full, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(bars.tmem_ptr, conv_tmem_cols(p.BN));
+    if (warp == 1) tmem_alloc(bars.tmem_ptr, tmem_cols);
+    // folded-upsample modes: the four phase blocks share the C = Cout/4 per-channel constants
+    const int cmod = (p.out_mode == OUT_SHUFFLE2 || p.out_mode == OUT_SHUFFLE2_HEAD) ? (p.Cout >> 2) : p.Cout;
     for (int c = threadIdx.x; c < p.Cout; c += CONV_THREADS) {
-        bars.s_bias[c] = p.bias ? p.bias[c] : 0.f;
-        bars.s_scale[c] = p.scale ? p.scale[c] : 1.f;
-        bars.s_shift[c] = p.shift ? p.shift[c] : 0.f;
+        const int cc = c % cmod;
+        bars.s_bias[c] = p.bias ? p.bias[cc] : 0.f;
+        bars.s_scale[c] = p.scale ? p.scale[cc] : 1.f;
+        bars.s_shift[c] = p.shift ? p.shift[cc] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -146,14 +161,14 @@ __device__ __forceinline__ uint32_t conv_prologue(const ConvParams& p, const Con
     return *bars.tmem_ptr;
 }
 
-__device__ __forceinline__ void conv_teardown(const ConvParams& p, uint32_t tmem_base) {
+__device__ __forceinline__ void conv_teardown(uint32_t tmem_base, uint32_t tmem_cols) {
     __syncwarp();
     tc_fence_before();
     __syncthreads();
     if ((threadIdx.x >> 5) == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, conv_tmem_cols(p.BN));
+        tmem_dealloc(tmem_base, tmem_cols);
     }
 }
 
@@ -175,6 +190,11 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int sp, int
 }
 
 // Epilogue of one tile, executed by the 4 epilogue warps (128 threads = 128 TMEM lanes = 128 pixels).
+// MODE >= 0: the output stage is a compile-time constant and the training extras (act' multiplier, BN statistics, second
+// output) are compiled out -- the inference instantiations; with every stage selected at run time the inlined body
+// exceeds the 96 registers a 576-thread CTA allows and the per-tile loop state spills to local memory (ncu: LDL stalls
+// on the loop counters in every tile).  MODE < 0: everything dynamic (training, VGG).
+template <int MODE>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
                                                    uint64_t* tmem_empty_bar, const TileCoord& t) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,6 +208,8 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
     const uint32_t t_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
     uint16_t* out16 = static_cast<uint16_t*>(p.out);
     uint16_t* out2_16 = static_cast<uint16_t*>(p.out2);
+    constexpr bool DYN = MODE < 0;
+    const int out_mode = DYN ? p.out_mode : MODE;
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
         uint32_t raw[32];
         if (p.debug & 8) {
@@ -198,8 +220,12 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
             tmem_ld_wait();
         }
         if (c0 + 32 >= p.BN) {                  // accumulator fully read: hand it back to the MMA warp
+            // one arrive per WARP (128 same-address shared-memory atomics per tile serialise in the LSU, next to
+            // the MMA's operand reads): every lane's tcgen05.ld has completed (wait::ld above), the warp converges,
+            // lane 0 signals for all 32 TMEM lanes of this warp's quadrant.
             tc_fence_before();
-            mbar_arrive(tmem_empty_bar);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar);
         }
         if (p.debug & 64) continue;
         float v[32];
@@ -218,7 +244,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                 v[j4 * 4 + 3] = fmaxf(a3, a3 * neg_slope);
             }
         }
-        if (p.mul_mode != MUL_NONE) {
+        if (DYN && p.mul_mode != MUL_NONE) {
             if (inb) {
                 const uint4* m4 = reinterpret_cast<const uint4*>(
                     p.mul_src + (static_cast<size_t>(n) * H * W + static_cast<size_t>(y) * W + x) * Cout + cg);
@@ -235,7 +261,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                 }
             }
         }
-        if (p.stats != nullptr) {
+        if (DYN && p.stats != nullptr) {
             // per-channel sum / sum of squares over the valid pixels of this warp, then one atomic per channel
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -264,7 +290,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                 v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], sc.w, sh.w);
             }
         }
-        if (p.out_mode == OUT_SAME || p.out_mode == OUT_SAME_MAXPOOL2) {
+        if (out_mode == OUT_SAME || out_mode == OUT_SAME_MAXPOOL2) {
             if (inb && !((p.debug & 4) && v[0] != 12345.f)) {
                 uint4* o4 = reinterpret_cast<uint4*>(
                     out16 + (static_cast<size_t>(n) * H * W + static_cast<size_t>(y) * W + x) * Cout + cg);
@@ -272,9 +298,9 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                 for (int j4 = 0; j4 < 4; ++j4) o4[j4] = pack8(v + j4 * 8, fp16);
             }
         }
-        if (p.out_mode == OUT_AVGPOOL2 || p.out_mode == OUT_SAME_MAXPOOL2) {
+        if (out_mode == OUT_AVGPOOL2 || out_mode == OUT_SAME_MAXPOOL2) {
             // 2x2 window = lanes {l, l^1, l^8} (x neighbour, y neighbour): tile origins are even.
-            const bool is_max = (p.out_mode == OUT_SAME_MAXPOOL2);
+            const bool is_max = (out_mode == OUT_SAME_MAXPOOL2);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 float a = v[j];
@@ -287,13 +313,13 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
             const int Ho = H >> 1, Wo = W >> 1;
             const int yo = y >> 1, xo = x >> 1;
             if (((px | py) & 1) == 0 && yo < Ho && xo < Wo) {
-                uint16_t* dst = (p.out_mode == OUT_AVGPOOL2) ? out16 : out2_16;
+                uint16_t* dst = (out_mode == OUT_AVGPOOL2) ? out16 : out2_16;
                 uint4* o4 = reinterpret_cast<uint4*>(
                     dst + (static_cast<size_t>(n) * Ho * Wo + static_cast<size_t>(yo) * Wo + xo) * Cout + cg);
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) o4[j4] = pack8(v + j4 * 8, fp16);
             }
-        } else if (p.out_mode == OUT_UP2) {
+        } else if (out_mode == OUT_UP2) {
             if (inb) {
                 const int Ho = 2 * H, Wo = 2 * W;
                 uint4 pk[4];
@@ -308,7 +334,17 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                     for (int j4 = 0; j4 < 4; ++j4) o4[j4] = pk[j4];
                 }
             }
-        } else if (p.out_mode == OUT_NCHW_F32) {
+        } else if (out_mode == OUT_SHUFFLE2) {
+            if (inb) {
+                const int C = Cout >> 2;
+                const int ph = cg / C, ch = cg - ph * C;
+                const int yo = 2 * y + (ph >> 1), xo = 2 * x + (ph & 1);
+                uint4* o4 = reinterpret_cast<uint4*>(
+                    out16 + ((static_cast<size_t>(n) * 2 * H + yo) * (2 * W) + xo) * C + ch);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) o4[j4] = pack8(v + j4 * 8, fp16);
+            }
+        } else if (out_mode == OUT_NCHW_F32) {
             if (inb) {
                 float* o = static_cast<float*>(p.out) + (static_cast<size_t>(n) * Cout + cg) * H * W +
                            static_cast<size_t>(y) * W + x;
@@ -325,25 +361,223 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
     }
 }
 
+
+// Lean epilogue of the inference output stages (OUT_SAME, OUT_AVGPOOL2, OUT_SHUFFLE2; no training extras): 16 accumulator
+// columns per TMEM load, so that 16 values + addresses + the role's loop state stay far below the 96 registers a
+// 576-thread CTA allows (the 32-column generic epilogue spills its loop state, ncu: LDL stalls in every tile).
+template <int MODE>
+__device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
+                                                   uint64_t* tmem_empty_bar, const TileCoord& t) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3;                     // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;              // pixel index inside the tile
+    const int py = row >> 3, px = row & 7;
+    const int H = p.H, W = p.W, fp16 = p.fp16;
+    const int y = t.y0 + py, x = t.x0 + px;
+    const bool inb = (y < H) && (x < W);
+    const float neg_slope = (p.act == ACT_LEAKY) ? p.slope : (p.act == ACT_RELU) ? 0.f : 1.f;
+    const uint32_t t_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+    const bool affine = p.scale != nullptr;
+    // element offset of this thread's pixel (channel 0) in the output tensor
+    size_t pix;
+    bool store;
+    int Cpix;                                   // channels per output pixel
+    if (MODE == OUT_SAME) {
+        Cpix = p.Cout;
+        pix = (static_cast<size_t>(t.n) * H + y) * W + x;
+        store = inb;
+    } else if (MODE == OUT_AVGPOOL2) {
+        Cpix = p.Cout;
+        const int Ho = H >> 1, Wo = W >> 1, yo = y >> 1, xo = x >> 1;
+        pix = (static_cast<size_t>(t.n) * Ho + yo) * Wo + xo;
+        store = ((px | py) & 1) == 0 && yo < Ho && xo < Wo;
+    } else {                                    // OUT_SHUFFLE2: phase offset added per chunk
+        Cpix = p.Cout >> 2;
+        pix = (static_cast<size_t>(t.n) * 2 * H + 2 * y) * (2 * W) + 2 * x;
+        store = inb;
+    }
+    if (p.debug & 4) store = false;
+    uint16_t* out16 = static_cast<uint16_t*>(p.out);
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        float v[16];
+        const int cg = t.n0 + c0;               // first global output channel of this chunk
+        {
+            uint32_t raw[16];
+            if (p.debug & 8) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) raw[j] = 0;
+            } else {
+                tmem_ld_32x32b_x16(t_addr + c0, raw);
+                tmem_ld_wait();
+            }
+            if (c0 + 16 >= p.BN) {              // accumulator fully read: one elected arrive per warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar);
+            }
+            if (p.debug & 64) continue;
+            // act(a) = max(a, a * neg_slope): neg_slope = 1 (identity), 0.01 (LeakyReLU), 0 (ReLU) -- branch-free
+            const float4* b4 = reinterpret_cast<const float4*>(bars.s_bias + cg);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b = b4[j4];
+                const float a0 = __uint_as_float(raw[j4 * 4 + 0]) + b.x, a1 = __uint_as_float(raw[j4 * 4 + 1]) + b.y;
+                const float a2 = __uint_as_float(raw[j4 * 4 + 2]) + b.z, a3 = __uint_as_float(raw[j4 * 4 + 3]) + b.w;
+                v[j4 * 4 + 0] = fmaxf(a0, a0 * neg_slope);
+                v[j4 * 4 + 1] = fmaxf(a1, a1 * neg_slope);
+                v[j4 * 4 + 2] = fmaxf(a2, a2 * neg_slope);
+                v[j4 * 4 + 3] = fmaxf(a3, a3 * neg_slope);
+            }
+        }
+        if (affine) {
+            const float4* sc4 = reinterpret_cast<const float4*>(bars.s_scale + cg);
+            const float4* sh4 = reinterpret_cast<const float4*>(bars.s_shift + cg);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 sc = sc4[j4], sh = sh4[j4];
+                v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], sc.x, sh.x);
+                v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], sc.y, sh.y);
+                v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], sc.z, sh.z);
+                v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], sc.w, sh.w);
+            }
+        }
+        size_t off;
+        if (MODE == OUT_AVGPOOL2) {
+            // 2x2 window = lanes {l, l^1, l^8} (x neighbour, y neighbour): tile origins are even.
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float a = v[j];
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                a += __shfl_xor_sync(0xffffffffu, a, 8);
+                v[j] = a * 0.25f;
+            }
+            off = pix * Cpix + cg;
+        } else if (MODE == OUT_SHUFFLE2) {
+            const int ph = cg / Cpix, ch = cg - ph * Cpix;
+            off = (pix + static_cast<size_t>(ph >> 1) * (2 * W) + (ph & 1)) * Cpix + ch;
+        } else {
+            off = pix * Cpix + cg;
+        }
+        if (store) {
+            uint4* o4 = reinterpret_cast<uint4*>(out16 + off);
+            o4[0] = pack8(v, fp16);
+            o4[1] = pack8(v + 8, fp16);
+        }
+    }
+}
+
+// Epilogue of one tile in OUT_SHUFFLE2_HEAD mode (BN = 128 = 4 phases x 32 channels, one accumulator = one low-res tile).
+// Thread = low-res pixel (y,x); accumulator columns [32*ph, 32*ph+32) = the 32 channels of hi-res pixel (2y+a, 2x+b),
+// ph = 2a+b.  act = LeakyReLU(acc + bias) stays in fp32 registers; the head filter tap (ky,kx) carries it to output
+// pixel (2y+a-ky+1, 2x+b-kx+1) = entry [(a-ky+2)*4 + (b-kx+2)] of this pixel's 4x4 patch (origin (2y-1, 2x-1)).
+// 4 x 288 MACs per thread, filter read from the constant bank as FFMA operands.
+__device__ __forceinline__ void conv_epilogue_head_tile(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
+                                                        uint64_t* tmem_empty_bar, const TileCoord& t) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int py = row >> 3, px = row & 7;
+    const int y = t.y0 + py, x = t.x0 + px;
+    const bool inb = (y < p.H) && (x < p.W);
+    const float neg_slope = (p.act == ACT_LEAKY) ? p.slope : (p.act == ACT_RELU) ? 0.f : 1.f;
+    const uint32_t t_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+    float hp[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) hp[i] = 0.f;
+    // One phase per iteration of a ROLLED loop (the body's constant-bank offsets stay static, the code stays small and
+    // the register allocator sees 16 values + 9 tap sums + 16 patch sums: no spills at 96 registers); 16 accumulator
+    // columns per TMEM load.
+#pragma unroll 1
+    for (int ph = 0; ph < 4; ++ph) {
+        float tsum[9];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) tsum[tap] = 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int c0 = half * 16;
+            uint32_t raw[16];
+            tmem_ld_32x32b_x16(t_addr + ph * 32 + c0, raw);
+            tmem_ld_wait();
+            if (half == 1 && ph == 3) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar);
+            }
+            float v[16];
+            const float4* b4 = reinterpret_cast<const float4*>(bars.s_bias + c0);   // phase blocks share the 32 biases
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b = b4[j4];
+                const float a0 = __uint_as_float(raw[j4 * 4 + 0]) + b.x, a1 = __uint_as_float(raw[j4 * 4 + 1]) + b.y;
+                const float a2 = __uint_as_float(raw[j4 * 4 + 2]) + b.z, a3 = __uint_as_float(raw[j4 * 4 + 3]) + b.w;
+                v[j4 * 4 + 0] = fmaxf(a0, a0 * neg_slope);
+                v[j4 * 4 + 1] = fmaxf(a1, a1 * neg_slope);
+                v[j4 * 4 + 2] = fmaxf(a2, a2 * neg_slope);
+                v[j4 * 4 + 3] = fmaxf(a3, a3 * neg_slope);
+            }
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                float s0 = 0.f, s1 = 0.f;        // even / odd channels: shorter dependent chains
+#pragma unroll
+                for (int j2 = 0; j2 < 8; ++j2) {
+                    s0 = fmaf(v[2 * j2], p.head_wc[tap * 32 + c0 + 2 * j2], s0);
+                    s1 = fmaf(v[2 * j2 + 1], p.head_wc[tap * 32 + c0 + 2 * j2 + 1], s1);
+                }
+                tsum[tap] += s0 + s1;
+            }
+        }
+        // scatter the 3x3 tap sums into the 4x4 patch at the phase's offset (static indices under a phase predicate)
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+            if (ph == q4) {
+                const int a = q4 >> 1, b = q4 & 1;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) hp[(a - tap / 3 + 2) * 4 + (b - tap % 3 + 2)] += tsum[tap];
+            }
+        }
+    }
+    if (inb) {
+        float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) +
+                                              ((static_cast<size_t>(t.n) * p.H + y) * p.W + x) * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = make_float4(hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // halo + resident-filter kernel
+//
+// Work quantum = a SUPER-TILE: T (4, 2 or 1) M-tiles of 16x8 pixels stacked vertically, fetched by ONE TMA box
+// {KC, 10, 16T+2, 1} per K-chunk and accumulated into T TMEM accumulators that are handed to the epilogue with ONE
+// commit.  Measured on B200 (tools/conv_debug_sweep.sh, tools/conv_n_sweep.sh): with one M-tile per pipeline step the
+// mbarrier hand-offs alone (producer -> MMA -> epilogue -> MMA, everything else stubbed out) cost ~510 cycles per tile
+// and do not overlap with the 720 cycles of a 32-channel tile's MMAs; a super-tile pays them once per T tiles.
+//   M-tile t of a stage starts 160 pixel rows (16 x pitch 10) further: same row-shifted descriptors as the taps.
+//   TMEM: 2 buffers x T accumulators x BN columns (<= 512); buffer b of super-tile i = i & 1.
+//   Epilogue sets (4 x 4 warps): T = 4: set e <-> M-tile e of every super-tile; T = 2: set e <-> M-tile e & 1 of the
+//   super-tiles with parity e >> 1; T = 1: sets 0 / 1 alternate super-tiles (sets 2, 3 idle: only the fat layers whose
+//   tiles carry >= 2304 MMA cycles run with T = 1).
 // ---------------------------------------------------------------------------------------------------------------
 template <int KC>
 struct HaloSmem {
     static constexpr int ROW_BYTES = KC * 2;
-    static constexpr int A_BYTES = HALO_H * HALO_W * ROW_BYTES;                  // 23040 (KC=64) / 11520 (KC=32)
-    static constexpr int A_STAGE = ((A_BYTES + 1023) / 1024) * 1024;
+    __host__ __device__ static constexpr int a_bytes(int T) { return (CONV_TILE_H * T + 2) * HALO_W * ROW_BYTES; }
+    __host__ __device__ static constexpr int a_stage(int T) { return ((a_bytes(T) + 1023) / 1024) * 1024; }
     __host__ __device__ static constexpr int b_block(int BN) { return BN * ROW_BYTES; }   // one (tap, chunk) block
     __host__ __device__ static constexpr int b_bytes(int BN, int Cin) { return 9 * (Cin / KC) * b_block(BN); }
-    __host__ __device__ static constexpr int total_bytes(int BN, int Cin, int stages) {
-        return 1024 + b_bytes(BN, Cin) + stages * A_STAGE + CONV_TAIL_BYTES;
+    __host__ __device__ static constexpr int total_bytes(int BN, int Cin, int T, int stages) {
+        return 1024 + b_bytes(BN, Cin) + stages * a_stage(T) + CONV_TAIL_BYTES;
     }
 };
+__host__ __device__ constexpr uint32_t halo_tmem_cols(int T, int BN) {
+    const int c = 2 * T * BN;
+    return (c <= 32) ? 32 : (c <= 64) ? 64 : (c <= 128) ? 128 : (c <= 256) ? 256 : 512;
+}
 
-template <int KC>
+template <int KC, int MODE>        // MODE: -1 = run-time epilogue, OUT_* = that output stage compiled in
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                    const ConvParams p) {
+                    const __grid_constant__ ConvParams p) {
     using S = HaloSmem<KC>;
     constexpr uint32_t LAYOUT = (KC == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
     constexpr uint32_t ROW_BYTES = S::ROW_BYTES;
@@ -351,136 +585,172 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int kchunks = p.Cin / KC;
+    const int T = p.T;
     const int b_block = S::b_block(p.BN);
+    const int a_stage = S::a_stage(T);
     uint8_t* b_smem = smem;                                         // [tap][chunk][BN rows][KC] swizzled
-    uint8_t* a_smem = smem + S::b_bytes(p.BN, p.Cin);               // [stage][18*10 rows][KC] swizzled (1024-aligned)
+    uint8_t* a_smem = smem + S::b_bytes(p.BN, p.Cin);               // [stage][(16T+2)*10 rows][KC] swizzled
     const int num_stages = p.num_stages;
-    ConvBarriers bars(a_smem + num_stages * S::A_STAGE);
+    ConvBarriers bars(a_smem + num_stages * a_stage);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_x);
         tma_prefetch_desc(&tmap_w);
     }
-    const uint32_t tmem_base = conv_prologue(p, bars, num_stages);
+    // epilogue warps attached to one TMEM buffer: T sets of 4 warps (T = 1: one set per buffer)
+    const uint32_t tmem_cols = halo_tmem_cols(T, p.BN);
+    const uint32_t tmem_base = conv_prologue(p, bars, num_stages, tmem_cols, 4 * T);
 
-    // CTA -> (n-block, first spatial tile, stride): the grid is split evenly between the n-blocks.
-    const int sp_tiles = p.num_tiles / p.n_blocks;
+    // CTA -> (n-block, first super-tile, stride): the grid is split evenly between the n-blocks.
+    const int st_per_img = p.tiles_x * p.stiles_y;
+    const int st_total = p.N * st_per_img;
     const int ctas_per_nb = gridDim.x / p.n_blocks;
     const int nb = blockIdx.x / ctas_per_nb;
     const int first = blockIdx.x - nb * ctas_per_nb;
     const bool active = nb < p.n_blocks;
 
     if (warp == 0) {
-        if (lane == 0 && active) {
-            // resident filter bank of this n-block: 9 * kchunks TMA boxes {KC, BN} on one barrier
-            mbar_arrive_expect_tx(bars.b_full, 9 * kchunks * b_block);
-            for (int tap = 0; tap < 9; ++tap)
-                for (int kc = 0; kc < kchunks; ++kc)
-                    tma_load_2d(b_smem + (tap * kchunks + kc) * b_block, &tmap_w, bars.b_full, kc * KC,
-                                tap * p.Cout + nb * p.BN);
+        // TMA producer: the whole warp runs the (uniform) loop, one elected lane issues
+        if (active) {
+            if (elect_one_sync()) {
+                // resident filter bank of this n-block: 9 * kchunks TMA boxes {KC, BN} on one barrier
+                mbar_arrive_expect_tx(bars.b_full, 9 * kchunks * b_block);
+                for (int tap = 0; tap < 9; ++tap)
+                    for (int kc = 0; kc < kchunks; ++kc)
+                        tma_load_2d(b_smem + (tap * kchunks + kc) * b_block, &tmap_w, bars.b_full, kc * KC,
+                                    tap * p.Cout + nb * p.BN);
+            }
             int stage = 0;
             uint32_t phase = 0;
-            // tile coordinates advance incrementally (one producer thread: no div/mod per tile)
-            const int tiles_per_img = p.tiles_x * p.tiles_y;
-            int n = first / tiles_per_img, ty = (first % tiles_per_img) / p.tiles_x, tx = first % p.tiles_x;
-            const int dn = ctas_per_nb / tiles_per_img, dty = (ctas_per_nb % tiles_per_img) / p.tiles_x,
+            const uint32_t a_bytes = S::a_bytes(T);
+            // super-tile coordinates advance incrementally (no div/mod per step)
+            int n = first / st_per_img, sy = (first % st_per_img) / p.tiles_x, tx = first % p.tiles_x;
+            const int dn = ctas_per_nb / st_per_img, dsy = (ctas_per_nb % st_per_img) / p.tiles_x,
                       dtx = ctas_per_nb % p.tiles_x;
-            for (int sp = first; sp < sp_tiles; sp += ctas_per_nb) {
+            for (int st = first; st < st_total; st += ctas_per_nb) {
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&bars.empty[stage], phase ^ 1);
-                    if (p.debug & 2) {
-                        mbar_arrive(&bars.full[stage]);
-                    } else {
-                        mbar_arrive_expect_tx(&bars.full[stage], S::A_BYTES);
-                        tma_load_4d(a_smem + stage * S::A_STAGE, &tmap_x, &bars.full[stage], kc * KC,
-                                    tx * CONV_TILE_W - 1, ty * CONV_TILE_H - 1, n);
+                    if (elect_one_sync()) {
+                        if (p.debug & 2) {
+                            mbar_arrive(&bars.full[stage]);
+                        } else {
+                            mbar_arrive_expect_tx(&bars.full[stage], a_bytes);
+                            tma_load_4d(a_smem + stage * a_stage, &tmap_x, &bars.full[stage], kc * KC,
+                                        tx * CONV_TILE_W - 1, sy * T * CONV_TILE_H - 1, n);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
                 tx += dtx;
-                if (tx >= p.tiles_x) { tx -= p.tiles_x; ++ty; }
-                ty += dty;
-                if (ty >= p.tiles_y) { ty -= p.tiles_y; ++n; }
+                if (tx >= p.tiles_x) { tx -= p.tiles_x; ++sy; }
+                sy += dsy;
+                if (sy >= p.stiles_y) { sy -= p.stiles_y; ++n; }
                 n += dn;
             }
         }
-    } else if (warp < CONV_FIRST_EPI_WARP) {
-        // CONV_ISSUERS MMA-issuing threads alternate tiles (issuer j takes this CTA's tiles j, j+2, ...).  A tile's
-        // barrier round trip (2 waits, 2 fences, 2 commits: ~760 cycles measured with everything else stubbed out) is
-        // serial in the issuing thread and the tensor-core queue is too shallow to cover it, so with ONE issuer a
-        // thin-layer tile costs overhead + MMA time (1900 cycles vs ~850 of MMA); with two, one thread feeds the tensor
-        // core while the other does its bookkeeping (1400 cycles; four issuers were slower again: register pressure at
-        // 672 threads).  Stages and accumulators are assigned by tile index: each thread steps them by two tiles.
-        const int issuer = warp - 1;
-        const int num_acc = conv_num_acc(p.BN);
-        const int n_iss = p.num_issuers;
-        if (lane == 0 && active && issuer < n_iss) {
+    } else if (warp == 1) {
+        // MMA issuer: warp-uniform loop, every tcgen05 instruction under elect.sync (see elect_one_sync)
+        if (active) {
             const uint32_t idesc = make_idesc_16(CONV_TILE_M, p.BN, p.fp16);
             int stage = 0;
             uint32_t phase = 0;
-            int acc = issuer % num_acc;
-            uint32_t acc_phase = 0;
-            for (int i = 0; i < issuer * kchunks; ++i)
-                if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            int buf = 0;
+            uint32_t buf_phase = 0;
             mbar_wait(bars.b_full, 0);
             // Descriptors: only the 14-bit start-address field (bits 0..13 of the low word, address >> 4) changes
             // between MMAs, so each MMA costs one 32-bit add per operand.
-            //   A rows: group g (output row g of the tile) starts at halo pixel (g + dy) * 10 + dx  =>  start address
-            //   advanced by (dy*10+dx) rows, 8-row group stride (SBO) = halo pitch.
+            //   A rows: group g (output row g of M-tile t) starts at halo pixel (16 t + g + dy) * 10 + dx  =>  start
+            //   address advanced by (160 t + dy*10 + dx) rows, 8-row group stride (SBO) = halo pitch.
             const uint64_t a_tmpl = make_smem_desc(smem_u32(a_smem), HALO_W * ROW_BYTES, LAYOUT);
             const uint64_t b_tmpl = make_smem_desc(smem_u32(b_smem), 8 * ROW_BYTES, LAYOUT);
             const uint32_t a_hi = static_cast<uint32_t>(a_tmpl >> 32), b_hi = static_cast<uint32_t>(b_tmpl >> 32);
             const uint32_t a_lo0 = static_cast<uint32_t>(a_tmpl), b_lo0 = static_cast<uint32_t>(b_tmpl);
             const uint32_t b_blk16 = static_cast<uint32_t>(b_block) >> 4;
             const uint32_t b_tap16 = b_blk16 * kchunks;
-            for (int sp = first + issuer * ctas_per_nb; sp < sp_tiles; sp += n_iss * ctas_per_nb) {
-                mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
+            constexpr uint32_t kRow16 = ROW_BYTES >> 4;
+            constexpr uint32_t kTile16 = CONV_TILE_H * HALO_W * kRow16;
+            int sy = (first % st_per_img) / p.tiles_x, tx = first % p.tiles_x;
+            const int dsy = (ctas_per_nb % st_per_img) / p.tiles_x, dtx = ctas_per_nb % p.tiles_x;
+            for (int st = first; st < st_total; st += ctas_per_nb) {
+                const int rows_left = p.tiles_y - sy * T;
+                const int nvalid = rows_left < T ? rows_left : T;          // M-tiles of this super-tile inside the image
+                mbar_wait(&bars.tmem_empty[buf], buf_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * p.BN;
+                const uint32_t d_tmem0 = tmem_base + buf * T * p.BN;
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&bars.full[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_lo = a_lo0 + stage * (S::A_STAGE >> 4);
-                    uint32_t b_lo = b_lo0 + kc * b_blk16;
+                    const uint32_t a_stage_lo = a_lo0 + stage * (static_cast<uint32_t>(a_stage) >> 4);
+                    const uint32_t b_kc = b_lo0 + kc * b_blk16;
+                    if (!(p.debug & 32)) {
+                        for (int t = 0; t < nvalid; ++t) {
+                            const uint32_t d_tmem = d_tmem0 + t * p.BN;
+                            const uint32_t a_lo = a_stage_lo + t * kTile16;
+                            if (elect_one_sync()) {
+                                uint32_t b_lo = b_kc;
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        if ((p.debug & 1) && tap > 0) break;
-                        if (p.debug & 32) break;
-                        constexpr uint32_t kRow16 = ROW_BYTES >> 4;
-                        const uint32_t a_tap = a_lo + ((tap / 3) * HALO_W + (tap % 3)) * kRow16;
+                                for (int tap = 0; tap < 9; ++tap) {
+                                    const uint32_t a_tap = a_lo + ((tap / 3) * HALO_W + (tap % 3)) * kRow16;
 #pragma unroll
-                        for (int k = 0; k < KC / 16; ++k)
-                            umma_f16_split(d_tmem, a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
-                                           (tap | k) != 0 ? 1u : static_cast<uint32_t>(kc != 0));
-                        b_lo += b_tap16;
+                                    for (int k = 0; k < KC / 16; ++k)
+                                        umma_f16_split(d_tmem, a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
+                                                       (tap | k) != 0 ? 1u : static_cast<uint32_t>(kc != 0));
+                                    b_lo += b_tap16;
+                                }
+                            }
+                            __syncwarp();
+                        }
                     }
-                    if (p.debug & 16) mbar_arrive(&bars.empty[stage]); else umma_commit(&bars.empty[stage]);
+                    if (elect_one_sync()) umma_commit(&bars.empty[stage]);
+                    __syncwarp();
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
-                if (p.debug & 32) mbar_arrive(&bars.tmem_full[acc]); else umma_commit(&bars.tmem_full[acc]);
-                acc += n_iss;                               // skip the other issuer's tile
-                if (acc >= num_acc) { acc -= num_acc; acc_phase ^= 1; }
-                for (int i = 0; i < (n_iss - 1) * kchunks; ++i)
-                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                if (elect_one_sync()) umma_commit(&bars.tmem_full[buf]);
+                __syncwarp();
+                buf ^= 1;
+                if (buf == 0) buf_phase ^= 1;
+                tx += dtx;
+                if (tx >= p.tiles_x) { tx -= p.tiles_x; ++sy; }
+                sy += dsy;
+                if (sy >= p.stiles_y) sy -= p.stiles_y;
             }
         }
     } else if (active) {
-        // epilogue set `eset` owns accumulator `eset`: it handles this CTA's tiles eset, eset + num_acc, ...
-        const int num_acc = conv_num_acc(p.BN);
         const int eset = (warp - CONV_FIRST_EPI_WARP) >> 2;
-        if (eset < num_acc) {
-            uint32_t acc_phase = 0;
-            for (int sp = first + eset * ctas_per_nb; sp < sp_tiles; sp += ctas_per_nb * num_acc) {
-                const TileCoord t = tile_coord(p, sp, nb);
-                mbar_wait(&bars.tmem_full[eset], acc_phase);
+        // (M-tile, buffer) this set serves; T = 4: every super-tile, else the super-tiles with local parity `my_buf`
+        const int t = (T == 4) ? eset : (T == 2) ? (eset & 1) : 0;
+        const int my_buf = (T == 4) ? -1 : (T == 2) ? (eset >> 1) : eset;
+        if (my_buf < 2) {
+            int i = 0;
+            for (int st = first; st < st_total; st += ctas_per_nb, ++i) {
+                const int buf = i & 1;
+                if (my_buf >= 0 && buf != my_buf) continue;
+                const int n = st / st_per_img;
+                const int r = st - n * st_per_img;
+                const int sy = r / p.tiles_x;
+                TileCoord tc;
+                tc.n = n;
+                tc.y0 = (sy * T + t) * CONV_TILE_H;
+                tc.x0 = (r - sy * p.tiles_x) * CONV_TILE_W;
+                tc.n0 = nb * p.BN;
+                mbar_wait(&bars.tmem_full[buf], (i >> 1) & 1);
                 tc_fence_after();
-                conv_epilogue_tile(p, bars, tmem_base + eset * p.BN, &bars.tmem_empty[eset], t);
-                acc_phase ^= 1;
+                if (sy * T + t < p.tiles_y) {
+                    const uint32_t acc = tmem_base + (buf * T + t) * p.BN;
+                    if (MODE == OUT_SHUFFLE2_HEAD) conv_epilogue_head_tile(p, bars, acc, &bars.tmem_empty[buf], tc);
+                    else if (MODE >= 0) conv_epilogue_lean<MODE>(p, bars, acc, &bars.tmem_empty[buf], tc);
+                    else conv_epilogue_tile<-1>(p, bars, acc, &bars.tmem_empty[buf], tc);
+                } else {                       // M-tile below the image: nothing to read, release the buffer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bars.tmem_empty[buf]);
+                }
             }
         }
     }
-    conv_teardown(p, tmem_base);
+    conv_teardown(tmem_base, tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -499,7 +769,7 @@ struct StreamSmem {
 template <int KC>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                      const ConvParams p) {
+                      const __grid_constant__ ConvParams p) {
     using S = StreamSmem<KC>;
     constexpr uint32_t LAYOUT = (KC == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
     constexpr uint32_t SBO = 8 * KC * 2;
@@ -515,7 +785,7 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         tma_prefetch_desc(&tmap_x);
         tma_prefetch_desc(&tmap_w);
     }
-    const uint32_t tmem_base = conv_prologue(p, bars, num_stages);
+    const uint32_t tmem_base = conv_prologue(p, bars, num_stages, conv_tmem_cols(p.BN), 4);
     const int kchunks = p.Cin / KC;
     const int KB = 9 * kchunks;
 
@@ -576,12 +846,12 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 const TileCoord t = tile_coord(p, tile / p.n_blocks, tile % p.n_blocks);
                 mbar_wait(&bars.tmem_full[eset], acc_phase);
                 tc_fence_after();
-                conv_epilogue_tile(p, bars, tmem_base + eset * p.BN, &bars.tmem_empty[eset], t);
+                conv_epilogue_tile<-1>(p, bars, tmem_base + eset * p.BN, &bars.tmem_empty[eset], t);
                 acc_phase ^= 1;
             }
         }
     }
-    conv_teardown(p, tmem_base);
+    conv_teardown(tmem_base, conv_tmem_cols(p.BN));
 }
 
 }  // namespace aesr

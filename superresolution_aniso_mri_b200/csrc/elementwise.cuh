@@ -169,6 +169,135 @@ head_conv3x3_tiled_kernel(const uint16_t* __restrict__ in, const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// encoder stem: enc.0 Conv2d(1,32,1,padding=1) and enc.1 Conv2d(32,32,3,padding=1) are both linear with nothing in
+// between (networks/acai_vanilla.py:51,55), so their composition is ONE 3x3 conv on the single input channel:
+//   a1[y,x,co] = b1[co] + sum_tap inside(tap) * ( Weff[tap][co] * xpad[tap] + Beff[tap][co] )
+//   Weff[tap][co] = sum_ci W1[co][ci][tap] * w0[ci],   Beff[tap][co] = sum_ci W1[co][ci][tap] * b0[ci]
+// on the (H+2)x(W+2) grid enc.0 produces; inside(tap) = the tap's pixel lies on that grid (enc.1's zero padding),
+// xpad = the image zero-padded by one pixel (enc.0's padding: ring pixels carry only the bias b0).
+// Replaces a 64 B/px activation round trip and a 32->32 tensor-core conv (smem-bandwidth-bound at N = 32) by
+// 4 B/px read + 64 B/px write.  stem_fold_kernel forms Weff/Beff once per parameter version.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void stem_fold_kernel(const float* __restrict__ w0, const float* __restrict__ b0,
+                                 const float* __restrict__ w1 /*[32][32][3][3]*/, float* __restrict__ weff /*[9][32]*/,
+                                 float* __restrict__ beff /*[9][32]*/, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 9 * C) return;
+    const int co = i % C, tap = i / C;
+    float sw = 0.f, sb = 0.f;
+    for (int ci = 0; ci < C; ++ci) {
+        const float w = w1[(static_cast<size_t>(co) * C + ci) * 9 + tap];
+        sw = fmaf(w, w0[ci], sw);
+        sb = fmaf(w, b0[ci], sb);
+    }
+    weff[i] = sw;
+    beff[i] = sb;
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ weff, const float* __restrict__ beff,
+                 const float* __restrict__ b1, uint16_t* __restrict__ out, int N, int H, int W, float slope) {
+    constexpr int C = 32;
+    __shared__ __align__(16) float sw[9 * C], sb[9 * C], sb1[C], sball[C];
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) { sw[i] = weff[i]; sb[i] = beff[i]; }
+    if (threadIdx.x < C) {
+        float t = b1[threadIdx.x];
+        sb1[threadIdx.x] = t;
+        for (int tap = 0; tap < 9; ++tap) t += beff[tap * C + threadIdx.x];
+        sball[threadIdx.x] = t;             // interior pixels: all nine taps on the grid
+    }
+    __syncthreads();
+    // grid = (blocks per image, images): 32-bit index math only (a 64-bit div/mod per item costs more than the 72 FMAs)
+    const int Ho = H + 2, Wo = W + 2;
+    const uint32_t per_img = static_cast<uint32_t>(Ho) * Wo * 4;
+    for (int n = blockIdx.y; n < N; n += gridDim.y)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per_img; i += gridDim.x * blockDim.x) {
+        const int g = static_cast<int>(i & 3);
+        const uint32_t pix = i >> 2;
+        const int yo = static_cast<int>(pix / static_cast<uint32_t>(Wo));
+        const int xo = static_cast<int>(pix - static_cast<uint32_t>(yo) * Wo);
+        const float* img = x + static_cast<size_t>(n) * H * W;
+        const bool interior = yo >= 1 && yo <= H && xo >= 1 && xo <= W;
+        float v[8];
+        if (interior) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = sball[g * 8 + j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = sb1[g * 8 + j];
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yy = yo + tap / 3 - 1, xx = xo + tap % 3 - 1;        // position on the (H+2)x(W+2) grid
+            if (yy < 0 || yy >= Ho || xx < 0 || xx >= Wo) continue;        // enc.1 zero padding
+            const int yi = yy - 1, xi = xx - 1;                            // position in the image
+            const float xv = (yi >= 0 && yi < H && xi >= 0 && xi < W) ? __ldg(img + static_cast<size_t>(yi) * W + xi) : 0.f;
+            const float4* w4 = reinterpret_cast<const float4*>(sw + tap * C + g * 8);
+            const float4 wa = w4[0], wb = w4[1];
+            v[0] = fmaf(wa.x, xv, v[0]); v[1] = fmaf(wa.y, xv, v[1]); v[2] = fmaf(wa.z, xv, v[2]); v[3] = fmaf(wa.w, xv, v[3]);
+            v[4] = fmaf(wb.x, xv, v[4]); v[5] = fmaf(wb.y, xv, v[5]); v[6] = fmaf(wb.z, xv, v[6]); v[7] = fmaf(wb.w, xv, v[7]);
+            if (!interior) {
+                const float4* q4 = reinterpret_cast<const float4*>(sb + tap * C + g * 8);
+                const float4 qa = q4[0], qb = q4[1];
+                v[0] += qa.x; v[1] += qa.y; v[2] += qa.z; v[3] += qa.w;
+                v[4] += qb.x; v[5] += qb.y; v[6] += qb.z; v[7] += qb.w;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], v[j] * slope);
+        reinterpret_cast<uint4*>(out)[static_cast<size_t>(n) * per_img + i] =
+            make_uint4(pack2_t<FP16>(v[0], v[1]), pack2_t<FP16>(v[2], v[3]), pack2_t<FP16>(v[4], v[5]),
+                       pack2_t<FP16>(v[6], v[7]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// head gather: second half of the decoder tail when dec.12 ran in OUT_SHUFFLE2_HEAD mode.  part fp32 [N,h,w,16] holds,
+// per LOW-res pixel (yl,xl), the 4x4 patch (origin (2yl-1, 2xl-1)) of head-conv partial sums of its own 2x2 hi-res
+// block.  Output pixel (Y,X) is covered by the patches of 2x2 low-res pixels; sum them, add the bias, sigmoid, clamp
+// (networks/acai_vanilla.py:98, generate_hr_volumes.py:67) and write image n at out + slot(n) * stride.
+// One thread = one low-res pixel = a 2x2 block of outputs.  16 B/hi-res px read + 4 B/px written.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_gather_kernel(const float* __restrict__ part, const float* __restrict__ bias_ptr, float* __restrict__ out,
+                   const int* __restrict__ out_index, int N, int h, int w, size_t out_image_stride, int apply_sigmoid) {
+    const float bias = __ldg(bias_ptr);
+    const int W = 2 * w;
+    const uint32_t per_img = static_cast<uint32_t>(h) * w;
+    for (int n = blockIdx.y; n < N; n += gridDim.y)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per_img; i += gridDim.x * blockDim.x) {
+        const int yl = static_cast<int>(i / static_cast<uint32_t>(w));
+        const int xl = static_cast<int>(i - static_cast<uint32_t>(yl) * w);
+        const float* pn = part + static_cast<size_t>(n) * h * w * 16;
+        float r[4];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                // rows: own patch row 1+a, plus the neighbour above (row 3) for a = 0 / below (row 0) for a = 1
+                const int yn = a ? yl + 1 : yl - 1, rn = a ? 0 : 3;
+                const int xn = b ? xl + 1 : xl - 1, cn = b ? 0 : 3;
+                const bool oky = yn >= 0 && yn < h, okx = xn >= 0 && xn < w;
+                float s = bias + __ldg(pn + (static_cast<size_t>(yl) * w + xl) * 16 + (1 + a) * 4 + (1 + b));
+                if (oky) s += __ldg(pn + (static_cast<size_t>(yn) * w + xl) * 16 + rn * 4 + (1 + b));
+                if (okx) s += __ldg(pn + (static_cast<size_t>(yl) * w + xn) * 16 + (1 + a) * 4 + cn);
+                if (oky && okx) s += __ldg(pn + (static_cast<size_t>(yn) * w + xn) * 16 + rn * 4 + cn);
+                if (apply_sigmoid) {
+                    s = 1.f / (1.f + __expf(-s));
+                    s = fminf(fmaxf(s, 0.f), 1.f);
+                }
+                r[a * 2 + b] = s;
+            }
+        }
+        const size_t slot = out_index ? static_cast<size_t>(__ldg(out_index + n)) : static_cast<size_t>(n);
+        float* o = out + slot * out_image_stride + static_cast<size_t>(2 * yl) * W + 2 * xl;
+        *reinterpret_cast<float2*>(o) = make_float2(r[0], r[1]);
+        *reinterpret_cast<float2*>(o + W) = make_float2(r[2], r[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // latent interpolation + layout change
 //   z    fp32 NCHW [*, C, HW]  (public latent layout)
 //   out  16-bit NHWC [M, HW, C]  (decoder input), optionally also fp32 NCHW [M, C, HW] (the public z_mix)

@@ -145,7 +145,7 @@ __global__ void normalize_apply_kernel(const float* __restrict__ x, float* __res
     const double lo = lo_hi[0], inv_den = lo_hi[1] - lo_hi[0];
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        double v = (static_cast<double>(x[i]) - lo) / inv_den;
+        double v = __ddiv_rn(__dsub_rn(static_cast<double>(x[i]), lo), inv_den);
         v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
         out[i] = static_cast<float>(v);
     }
@@ -159,8 +159,9 @@ __global__ void percentile_finish_kernel(const SelectState* st, double frac_lo, 
     const double a0 = st->result[0], a1 = st->result[1], b0 = st->result[2], b1 = st->result[3];
     const double da = static_cast<double>(__fsub_rn(st->result[1], st->result[0]));
     const double db = static_cast<double>(__fsub_rn(st->result[3], st->result[2]));
-    lo_hi[0] = frac_lo >= 0.5 ? a1 - da * (1.0 - frac_lo) : a0 + da * frac_lo;
-    lo_hi[1] = frac_hi >= 0.5 ? b1 - db * (1.0 - frac_hi) : b0 + db * frac_hi;
+    // separately rounded multiply and add (numpy has no fused multiply-add here; nvcc would contract a + b*c)
+    lo_hi[0] = frac_lo >= 0.5 ? __dsub_rn(a1, __dmul_rn(da, __dsub_rn(1.0, frac_lo))) : __dadd_rn(a0, __dmul_rn(da, frac_lo));
+    lo_hi[1] = frac_hi >= 0.5 ? __dsub_rn(b1, __dmul_rn(db, __dsub_rn(1.0, frac_hi))) : __dadd_rn(b0, __dmul_rn(db, frac_hi));
 }
 
 // ---------------------------------------------------------------------------------------------------------------

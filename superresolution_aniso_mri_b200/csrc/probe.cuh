@@ -66,4 +66,116 @@ halo_probe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
 }
 
+// Tensor-core issue-rate probe (diagnostic): `iters` back-to-back tcgen05.mma (M = 128, N, K = 16, fp16) on whatever is
+// in shared memory, A descriptor = {start row shift, 8-row-group stride `pitch_rows`}, row = KC*2 bytes (SW64 / SW128).
+// cycles[0] = clock64 from the first issue to the commit's mbarrier completion.  Answers: what does an SS-mode MMA cost
+// when its A operand rows are (a) dense and swizzle-atom aligned, (b) row-shifted / pitched like the halo tile?
+template <int NACC>
+__global__ void __launch_bounds__(128, 1)
+umma_rate_probe_kernel(long long* __restrict__ cycles, int N, int kc, int pitch_rows, int shift_rows, int iters,
+                       int a_advance_rows) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t done_bar;
+    __shared__ uint32_t tmem_ptr;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&done_bar, 1);
+        fence_barrier_init();
+    }
+    fence_proxy_async();
+    if (warp == 0) tmem_alloc(&tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_ptr;
+    if (warp == 1) {
+        const uint32_t row_bytes = kc * 2;
+        const uint32_t layout = (kc == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
+        const uint64_t a_desc0 = make_smem_desc(smem_u32(smem) + shift_rows * row_bytes, pitch_rows * row_bytes, layout);
+        const uint64_t b_desc = make_smem_desc(smem_u32(smem) + 128 * 1024, 8 * row_bytes, layout);
+        const uint32_t idesc = make_idesc_16(128, N, 1);
+        const uint32_t adv = (a_advance_rows * row_bytes) >> 4;
+        uint32_t d[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = tmem_base + (j % NACC) * N;
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; i += 8) {            // 8 MMAs per trip: loop overhead amortised
+            if (elect_one_sync()) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) umma_f16(d[j], a_desc0 + j * adv, b_desc, idesc, 1);
+            }
+            __syncwarp();
+        }
+        if (elect_one_sync()) umma_commit(&done_bar);
+        __syncwarp();
+        mbar_wait(&done_bar, 0);
+        const long long t1 = clock64();
+        if (elect_one_sync()) cycles[0] = t1 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// mbarrier hop-latency probe (diagnostic): warp 1 signals barrier A (plain arrive, or tcgen05.commit when mode & 1) and
+// waits on barrier B; warp 0 (or, mode & 4, all of warps 2-3 as well, 32 lanes each) waits on A and arrives on B.
+// mode & 2: poll with mbarrier.test_wait instead of the (possibly suspending) try_wait.  cycles[0] / iters = round trip.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__global__ void __launch_bounds__(128, 1) sync_probe_kernel(long long* __restrict__ cycles, int iters, int mode) {
+    __shared__ uint64_t bar_a, bar_b;
+    __shared__ uint32_t tmem_ptr;
+    const int warp = threadIdx.x >> 5;
+    const int waiters = (mode & 4) ? 3 : 1;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_a, 1);
+        mbar_init(&bar_b, waiters);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_ptr, 32);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const bool poll = mode & 2;
+    if (warp == 1) {
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            if (elect_one_sync()) {
+                if (mode & 1) umma_commit(&bar_a); else mbar_arrive(&bar_a);
+            }
+            __syncwarp();
+            if (poll) { while (!mbar_test_wait(&bar_b, i & 1)) {} } else mbar_wait(&bar_b, i & 1);
+        }
+        const long long t1 = clock64();
+        if (elect_one_sync()) cycles[0] = t1 - t0;
+    } else if (warp == 0 || ((mode & 4) && warp >= 2)) {
+        for (int i = 0; i < iters; ++i) {
+            if (poll) { while (!mbar_test_wait(&bar_a, i & 1)) {} } else mbar_wait(&bar_a, i & 1);
+            __syncwarp();
+            if (elect_one_sync()) mbar_arrive(&bar_b);
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_ptr, 32);
+    }
+}
+
 }  // namespace aesr

@@ -11,6 +11,7 @@ use_sigmoid as the ae_combined configs set them (networks/net_config.py:28-29).
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -146,6 +147,9 @@ class VanillaACAI(nn.Module):
         self.enc = build_encoder(scales, args["depth"], args["latent"], 1).to(args["device"])
         self.dec = build_decoder(scales, args["depth"], args["latent"], 1).to(args["device"])
         self._cache = _PackedCache()
+        # Inference pipelines use the algebraic folds (stem = enc.0 o enc.1, Upsample folded into the next conv, decoder
+        # head fused into dec.12's epilogue).  False = one kernel per reference layer (A/B measurements, tests).
+        self.fused_inference = os.environ.get("AESR_FUSED", "1") != "0"
 
     # ------------------------------------------------------------------ public API (reference signatures)
     def forward(self, img):
@@ -197,6 +201,19 @@ class VanillaACAI(nn.Module):
                 return scale.float().contiguous(), shift.float().contiguous()
         return self._cache.get(("bn", id(bn)), [bn.weight, bn.bias, bn.running_mean, bn.running_var], build)
 
+    def _packed_up2(self, conv: ConvHolder) -> torch.Tensor:
+        return self._cache.get(("wup", id(conv)), [conv.weight], lambda: ops.pack_conv3x3_weight_up2fold(conv.weight))
+
+    def _stem(self):
+        c0, c1 = self.enc[0], self.enc[1]
+        return self._cache.get(("stem",), [c0.weight, c0.bias, c1.weight],
+                               lambda: ops.stem_fold(c0.weight, c0.bias, c1.weight))
+
+    def _head_w_host(self, conv: ConvHolder):
+        """fp32 [9,32] head filter in host memory (one device->host copy per parameter version)."""
+        return self._cache.get(("head_host", id(conv)), [conv.weight],
+                               lambda: conv.weight.detach()[0].permute(1, 2, 0).reshape(9, -1).float().cpu().contiguous())
+
     def _head_w(self, conv: ConvHolder):
         def build():
             with torch.no_grad():
@@ -209,11 +226,17 @@ class VanillaACAI(nn.Module):
         """[N,1,H,W] fp32 -> z [N,latent,h,w] fp32 (eval-mode BN).  ``want_nhwc`` also returns the bf16 NHWC copy."""
         x = img.detach().float().contiguous()
         enc = self.enc
-        a = ops.e0(x, enc[0].weight.detach().reshape(-1).contiguous(), enc[0].bias.detach())
+        fused = self.fused_inference
+        if fused:
+            weff, beff = self._stem()
+            a = ops.stem(x, weff, beff, enc[1].bias.detach())
+        else:
+            a = ops.e0(x, enc[0].weight.detach().reshape(-1).contiguous(), enc[0].bias.detach())
         i = 1
-        for _ in range(self.scales):
+        for s in range(self.scales):
             c1, c2, bn = enc[i], enc[i + 2], enc[i + 4]
-            a = ops.conv3x3(a, self._packed(c1), c1.bias.detach(), act=ops.ACT_LEAKY)
+            if not (fused and s == 0):
+                a = ops.conv3x3(a, self._packed(c1), c1.bias.detach(), act=ops.ACT_LEAKY)
             sc, sh = self._bn_affine(bn)
             a = ops.conv3x3(a, self._packed(c2), c2.bias.detach(), act=ops.ACT_LEAKY, scale=sc, shift=sh,
                             out_mode=ops.OUT_AVGPOOL2)
@@ -229,6 +252,8 @@ class VanillaACAI(nn.Module):
                          out_index: Optional[torch.Tensor] = None) -> torch.Tensor:
         """decoder on an NHWC bf16 latent batch; images optionally written strided into ``out``."""
         dec = self.dec
+        if self.fused_inference:
+            return self._decode_nhwc_fused(a, out, out_image_stride, out_index)
         i = 0
         for _ in range(self.scales):
             c1, c2, bn = dec[i], dec[i + 2], dec[i + 4]
@@ -241,6 +266,26 @@ class VanillaACAI(nn.Module):
         a = ops.conv3x3(a, self._packed(c1), c1.bias.detach(), act=ops.ACT_LEAKY)
         w9c, b = self._head_w(c2)
         return ops.head(a, w9c, b, out=out, out_image_stride=out_image_stride, sigmoid=True, out_index=out_index)
+
+    def _decode_nhwc_fused(self, a, out, out_image_stride, out_index):
+        """Same decoder with every nn.Upsample folded into the conv that follows it (the producer stores the LOW-res
+        tensor, the consumer is a low-res conv with 4 phase blocks + depth-to-space) and dec.12 -> dec.14 -> sigmoid as
+        one tensor-core kernel + a 20 B/px gather."""
+        dec = self.dec
+        i = 0
+        for s in range(self.scales):
+            c1, c2, bn = dec[i], dec[i + 2], dec[i + 4]
+            if s == 0:
+                a = ops.conv3x3(a, self._packed(c1), c1.bias.detach(), act=ops.ACT_LEAKY)
+            else:       # input is the previous block's low-res output: Upsample folded into this conv
+                a = ops.conv3x3(a, self._packed_up2(c1), c1.bias.detach(), act=ops.ACT_LEAKY, out_mode=ops.OUT_SHUFFLE2)
+            sc, sh = self._bn_affine(bn)
+            a = ops.conv3x3(a, self._packed(c2), c2.bias.detach(), act=ops.ACT_LEAKY, scale=sc, shift=sh)
+            i += 6
+        c1, c2 = dec[i], dec[i + 2]
+        w9c, b = self._head_w(c2)
+        part = ops.conv3x3_up2_head(a, self._packed_up2(c1), c1.bias.detach(), self._head_w_host(c2), act=ops.ACT_LEAKY)
+        return ops.head_gather(part, b, out=out, out_image_stride=out_image_stride, sigmoid=True, out_index=out_index)
 
     @torch.no_grad()
     def decode_eval(self, z: torch.Tensor) -> torch.Tensor:

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
-OUT_SAME, OUT_AVGPOOL2, OUT_UP2, OUT_NCHW_F32, OUT_SAME_MAXPOOL2 = 0, 1, 2, 3, 4
+OUT_SAME, OUT_AVGPOOL2, OUT_UP2, OUT_NCHW_F32, OUT_SAME_MAXPOOL2, OUT_SHUFFLE2 = 0, 1, 2, 3, 4, 5
 MUL_NONE, MUL_LEAKY_GRAD, MUL_RELU_GRAD = 0, 1, 2
 ALGO_AUTO, ALGO_HALO, ALGO_STREAM = 0, 1, 2
 DT_BF16, DT_FP16 = 0, 1
@@ -30,8 +30,8 @@ TIMING = None
 
 
 class _timed:
-    def __init__(self, name: str, flops: float = 0.0):
-        self.name, self.flops = name, flops
+    def __init__(self, name: str, flops: float = 0.0, desc: str = ""):
+        self.name, self.flops, self.desc = name, flops, desc
 
     def __enter__(self):
         if TIMING is not None:
@@ -43,7 +43,7 @@ class _timed:
     def __exit__(self, *exc):
         if TIMING is not None:
             self.e1.record()
-            TIMING.append((self.name, self.e0, self.e1, self.flops))
+            TIMING.append((self.name, self.e0, self.e1, self.flops, self.desc))
         return False
 
 
@@ -84,7 +84,22 @@ def pack_conv3x3_weight(w: torch.Tensor, transpose_flip: bool = False, dtype: Op
     return out
 
 
+def pack_conv3x3_weight_up2fold(w: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """fp32 [Cout,Cin,3,3] of a conv that FOLLOWS nn.Upsample(2) -> 16-bit [9, 4*Cout, Cin]: the same conv expressed on
+    the low-resolution input, one block of Cout rows per output phase (2y+a, 2x+b) (conv3x3 out_mode OUT_SHUFFLE2)."""
+    lib = _dev(w)
+    dtype = dtype or DEFAULT_DTYPE
+    w = w.detach().contiguous().float()
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.empty((9, 4 * cout, cin), dtype=dtype, device=w.device)
+    _lib.check(lib.aesr_pack_conv3x3_weight_up2fold(w.data_ptr(), out.data_ptr(), cout, cin, dt_code(dtype), _stream(w)),
+               "pack_conv3x3_weight_up2fold")
+    return out
+
+
 def conv_out_shape(n, h, w, cout, out_mode) -> Tuple[int, ...]:
+    if out_mode == OUT_SHUFFLE2:
+        return (n, 2 * h, 2 * w, cout // 4)
     if out_mode == OUT_AVGPOOL2:
         return (n, h // 2, w // 2, cout)
     if out_mode == OUT_UP2:
@@ -111,12 +126,75 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     if out2 is None and (out_mode == OUT_SAME_MAXPOOL2 or (out_mode == OUT_NCHW_F32 and want_out2)):
         shp = (n, h // 2, w // 2, cout) if out_mode == OUT_SAME_MAXPOOL2 else (n, h, w, cout)
         out2 = torch.empty(shp, dtype=x.dtype, device=x.device)
-    with _timed("conv3x3", 2.0 * n * h * w * 9 * cin * cout):
+    with _timed("conv3x3", 2.0 * n * h * w * 9 * cin * cout, "%d->%d n%d %dx%d mode%d" % (cin, cout, n, h, w, out_mode)):
         _lib.check(lib.aesr_conv3x3_fwd(x.data_ptr(), w_packed.data_ptr(), _ptr(bias), _ptr(scale), _ptr(shift),
                                         out.data_ptr(), _ptr(out2), _ptr(mul_src), _ptr(stats), n, h, w, cin, cout,
                                         int(act), float(slope), int(out_mode), int(mul_mode), dt_code(x.dtype),
                                         int(algo), _stream(x)), "conv3x3_fwd")
     return (out, out2) if out2 is not None else out
+
+
+def conv3x3_up2_head(x: torch.Tensor, w_folded: torch.Tensor, bias: torch.Tensor, head_w9c: torch.Tensor,
+                     act: int = ACT_LEAKY, slope: float = LEAKY_SLOPE, out: Optional[torch.Tensor] = None,
+                     algo: int = ALGO_AUTO) -> torch.Tensor:
+    """Upsample(2) -> Conv2d(Cin,32,3,p=1)+act -> Conv2d(32,1,3,p=1) partial sums: x NHWC 16-bit [N,H,W,Cin] (low-res)
+    -> fp32 [N,H,W,16] patches for ``head_gather``.  ``head_w9c``: fp32 [9,32] on the HOST."""
+    lib = _dev(x)
+    assert x.is_contiguous() and x.dim() == 4 and x.dtype == w_folded.dtype
+    n, h, w, cin = x.shape
+    assert w_folded.shape == (9, 128, cin) and w_folded.is_contiguous() and head_w9c.shape == (9, 32)
+    # the head filter travels as a kernel parameter (constant bank): it must be HOST memory
+    assert not head_w9c.is_cuda and head_w9c.dtype == torch.float32 and head_w9c.is_contiguous()
+    if out is None:
+        out = torch.empty((n, h, w, 16), dtype=torch.float32, device=x.device)
+    with _timed("conv3x3", 2.0 * n * h * w * 9 * cin * 128 + 2.0 * n * 4 * h * w * 9 * 32,
+                "%d->128+head n%d %dx%d" % (cin, n, h, w)):
+        _lib.check(lib.aesr_conv3x3_up2_head_fwd(x.data_ptr(), w_folded.data_ptr(), bias.data_ptr(), head_w9c.data_ptr(),
+                                                 out.data_ptr(), n, h, w, cin, int(act), float(slope), dt_code(x.dtype),
+                                                 int(algo), _stream(x)), "conv3x3_up2_head_fwd")
+    return out
+
+
+def head_gather(partial: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None,
+                out_image_stride: Optional[int] = None, sigmoid: bool = True,
+                out_index: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """partial fp32 [N,h,w,16] -> fp32 images [N,1,2h,2w] (or image n -> out[out_index[n]])."""
+    lib = _dev(partial)
+    n, h, w, _ = partial.shape
+    if out is None:
+        out = torch.empty((n, 1, 2 * h, 2 * w), dtype=torch.float32, device=partial.device)
+        out_image_stride = 4 * h * w
+    with _timed("head"):
+        _lib.check(lib.aesr_head_gather(partial.data_ptr(), bias.data_ptr(), out.data_ptr(), _ptr(out_index), n, h, w,
+                                        int(out_image_stride), int(sigmoid), _stream(partial)), "head_gather")
+    return out
+
+
+def stem_fold(w0: torch.Tensor, b0: torch.Tensor, w1: torch.Tensor):
+    """enc.0 (1x1, 1->C) composed with enc.1 (3x3, C->C): effective single-channel 3x3 filter and bias taps [9,C]."""
+    lib = _dev(w1)
+    c = w1.shape[0]
+    weff = torch.empty((9, c), dtype=torch.float32, device=w1.device)
+    beff = torch.empty((9, c), dtype=torch.float32, device=w1.device)
+    _lib.check(lib.aesr_stem_fold(w0.detach().reshape(-1).contiguous().data_ptr(), b0.detach().contiguous().data_ptr(),
+                                  w1.detach().contiguous().data_ptr(), weff.data_ptr(), beff.data_ptr(), c, _stream(w1)),
+               "stem_fold")
+    return weff, beff
+
+
+def stem(x: torch.Tensor, weff: torch.Tensor, beff: torch.Tensor, b1: torch.Tensor, slope: float = LEAKY_SLOPE,
+         dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """enc.0 + enc.1 + LeakyReLU: x fp32 [N,1,H,W] -> NHWC 16-bit [N,H+2,W+2,32]."""
+    lib = _dev(x)
+    dtype = dtype or DEFAULT_DTYPE
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 1
+    n, _, h, wd = x.shape
+    c = weff.shape[1]
+    out = torch.empty((n, h + 2, wd + 2, c), dtype=dtype, device=x.device)
+    with _timed("stem", 2.0 * n * (h + 2) * (wd + 2) * c * (1 + 9 * c)):
+        _lib.check(lib.aesr_stem_fwd(x.data_ptr(), weff.data_ptr(), beff.data_ptr(), b1.data_ptr(), out.data_ptr(), n, h,
+                                     wd, c, float(slope), dt_code(dtype), _stream(x)), "stem_fwd")
+    return out
 
 
 def e0(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:

@@ -171,6 +171,100 @@ def test_invalid_arguments_raise(dev):
         ops.e0(torch.zeros(1, 1, 4, 4), torch.zeros(32), torch.zeros(32))      # CPU tensor
 
 
+# ------------------------------------------------------------------------------------------------ algebraic folds
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("case", [(32, 32, 2, 64, 64), (64, 32, 3, 32, 32), (32, 32, 1, 55, 55), (128, 64, 2, 16, 16),
+                                  (32, 32, 1, 1, 1), (64, 32, 1, 3, 5)])
+def test_upsample_folded_conv_vs_torch(dev, case, dtype):
+    """nn.Upsample(2) -> Conv2d(3x3, pad 1) (networks/acai_vanilla.py:92 then :87/:96) as one low-res conv with four phase
+    blocks + depth-to-space (OUT_SHUFFLE2): compared with torch fp32 on the same 16-bit input and fp32 filters (the
+    folded taps are sums of up to four filter taps rounded once to 16 bit: one more weight rounding than the unfolded
+    kernel, inside the tolerance below)."""
+    from superresolution_aniso_mri_b200 import ops
+    cin, cout, n, h, w = case
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = torch.randn(n, h, w, cin, generator=g).to(dtype).to(dev)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / np.sqrt(cin * 9)).to(dev)
+    b = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    sc = (torch.rand(cout, generator=g) + 0.5).to(dev)
+    sh = (torch.randn(cout, generator=g) * 0.1).to(dev)
+    got = ops.conv3x3(x, ops.pack_conv3x3_weight_up2fold(wt, dtype=dtype), b, act=1, scale=sc, shift=sh,
+                      out_mode=ops.OUT_SHUFFLE2)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2).cpu(), scale_factor=2, mode="nearest")
+    want = F.leaky_relu(F.conv2d(up, wt.cpu(), b.cpu(), padding=1), 0.01) * sc.cpu()[None, :, None, None] + \
+        sh.cpu()[None, :, None, None]
+    assert got.shape == (n, 2 * h, 2 * w, cout)
+    ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+    tol = 4 * ulp * max(1.0, want.abs().max().item()) + (2e-4 + ulp) * np.sqrt(cin * 9)
+    assert (got.float().permute(0, 3, 1, 2).cpu() - want).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("case", [(32, 2, 64, 64), (32, 3, 20, 12), (64, 1, 16, 16), (32, 1, 1, 1), (32, 1, 17, 9)])
+def test_decoder_tail_fused_head_vs_torch(dev, case):
+    """Upsample -> Conv2d(Cin,32)+LeakyReLU -> Conv2d(32,1) -> Sigmoid (networks/acai_vanilla.py:92,96-98) as one tensor
+    core kernel (head partial sums in the epilogue, fp32 activations never stored) + head_gather, scattered into a
+    larger volume."""
+    from superresolution_aniso_mri_b200 import ops
+    cin, n, h, w = case
+    dt = torch.float16
+    g = torch.Generator().manual_seed(cin + h + w)
+    x = torch.randn(n, h, w, cin, generator=g).to(dt).to(dev)
+    wt = (torch.randn(32, cin, 3, 3, generator=g) / np.sqrt(cin * 9)).to(dev)
+    b = (torch.randn(32, generator=g) * 0.1).to(dev)
+    wh = torch.randn(1, 32, 3, 3, generator=g) / 17
+    bh = torch.tensor([0.3])
+    part = ops.conv3x3_up2_head(x, ops.pack_conv3x3_weight_up2fold(wt, dtype=dt), b,
+                                wh[0].permute(1, 2, 0).reshape(9, 32).contiguous())       # host tensor (kernel parameter)
+    out = torch.full((n + 3, 2 * h, 2 * w), -1.0, device=dev)
+    idx = torch.arange(n, dtype=torch.int32, device=dev) + 2
+    ops.head_gather(part, bh.to(dev), out=out, out_image_stride=4 * h * w, out_index=idx)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2).cpu(), scale_factor=2, mode="nearest")
+    act = F.leaky_relu(F.conv2d(up, wt.cpu(), b.cpu(), padding=1), 0.01)
+    want = torch.sigmoid(F.conv2d(act, wh, bh, padding=1))[:, 0]
+    assert (out[2:2 + n].cpu() - want).abs().max().item() < 2e-3
+    assert torch.all(out[:2] == -1.0) and torch.all(out[2 + n:] == -1.0)
+    logits = ops.head_gather(part, bh.to(dev), sigmoid=False)
+    assert (logits[:, 0].cpu() - F.conv2d(act, wh, bh, padding=1)[:, 0]).abs().max().item() < 8e-3
+
+
+@pytest.mark.parametrize("shape", [(3, 20, 28), (1, 1, 1), (2, 128, 128), (1, 2, 3)])
+def test_encoder_stem_fold_vs_torch(dev, shape):
+    """enc.0 (1x1, padding 1) o enc.1 (3x3, padding 1) + LeakyReLU (networks/acai_vanilla.py:51,55-56) as one
+    single-channel 3x3 conv with border-aware bias."""
+    from superresolution_aniso_mri_b200 import ops
+    n, h, w = shape
+    g = torch.Generator().manual_seed(11 + h)
+    x = torch.rand(n, 1, h, w, generator=g)
+    w0, b0 = torch.randn(32, generator=g), torch.randn(32, generator=g)
+    w1, b1 = torch.randn(32, 32, 3, 3, generator=g) / 17, torch.randn(32, generator=g) * 0.1
+    weff, beff = ops.stem_fold(w0.to(dev), b0.to(dev), w1.to(dev))
+    got = ops.stem(x.to(dev), weff, beff, b1.to(dev))
+    want = F.leaky_relu(F.conv2d(F.conv2d(x.double(), w0.double().view(32, 1, 1, 1), b0.double(), padding=1),
+                                 w1.double(), b1.double(), padding=1), 0.01)
+    assert got.shape == (n, h + 2, w + 2, 32)
+    err = (got.double().permute(0, 3, 1, 2).cpu() - want).abs().max().item()
+    assert err <= 2.0 ** -10 * max(1.0, want.abs().max().item()) + 1e-5       # one fp16 rounding of the result
+
+
+def test_fused_and_layerwise_inference_agree(dev):
+    """The folded pipelines (default) and the one-kernel-per-reference-layer pipelines give the same slices within the
+    16-bit activation noise, and both meet the spec tolerance against the oracle."""
+    from superresolution_aniso_mri_b200 import synthesis
+    args = O.default_args(64, 16)
+    state = O.calibrated_state(args)
+    model = make_model(args, state, dev)
+    vol = 0.8 * O.smooth_phantom(5, 64, seed=2) + 0.2 * O.synthetic_volume(5, 64, seed=1)
+    ar = O.alpha_range_for(3)
+    want = O.create_super_volume(state, args, vol, ar, use_original=False)
+    outs = {}
+    for fused in (True, False):
+        model.fused_inference = fused
+        outs[fused] = synthesis.create_super_volume(model, vol, ar, use_original=False)["upsampled_image"]
+        d = (outs[fused] - want).abs()
+        assert d.max().item() < 6e-2 and d.mean().item() < 3e-3            # calibrated-checkpoint bounds (see above)
+    assert (outs[True] - outs[False]).abs().max().item() < 6e-2
+
+
 # ------------------------------------------------------------------------------------------------ network parity
 def test_random_init_checkpoint_meets_spec_tolerance(dev, golden):
     """BASELINE north_star: identical synthetic inputs + random-init weights, max-abs 2e-2 on [0,1]."""
