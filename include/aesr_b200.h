@@ -108,11 +108,12 @@ int aesr_head_gather(const float* partial, const float* bias, float* out, const 
 /* Encoder stem: enc.0 nn.Conv2d(1,32,1,padding=1) and enc.1 nn.Conv2d(32,32,3,padding=1) + LeakyReLU
  * (networks/acai_vanilla.py:51,55-56) composed into one 3x3 conv on the single input channel (both are linear).
  * aesr_stem_fold: weff[tap][co] = sum_ci w1[co][ci][tap]*w0[ci], beff likewise with b0 (once per parameter version).
- * aesr_stem_fwd: x fp32 [N,1,H,W] -> NHWC 16-bit [N,H+2,W+2,32]; border taps that fall off the (H+2)x(W+2) grid drop
+ * aesr_stem_fwd: weff_beff_b1_host = fp32 [9*32 weff | 9*32 beff | 32 b1] in HOST memory (kernel parameters: the filter is
+ * read from the constant bank); x fp32 [N,1,H,W] -> NHWC 16-bit [N,H+2,W+2,32]; border taps that fall off the (H+2)x(W+2) grid drop
  * their bias term, ring pixels see x = 0, exactly as the two zero paddings of the reference do. */
 int aesr_stem_fold(const float* w0, const float* b0, const float* w1, float* weff, float* beff, int C, void* stream);
-int aesr_stem_fwd(const float* x, const float* weff, const float* beff, const float* b1, void* out, int N, int H, int W,
-                  int C, float slope, int dtype, void* stream);
+int aesr_stem_fwd(const float* x, const float* weff_beff_b1_host, void* out, int N, int H, int W, int C, float slope,
+                  int dtype, void* stream);
 
 /* enc.0: nn.Conv2d(1, C, 1, padding=1) (networks/acai_vanilla.py:51).  x fp32 [N,1,H,W] -> NHWC 16-bit [N,H+2,W+2,C]. */
 int aesr_e0_fwd(const float* x, const float* w, const float* b, void* out, int N, int H, int W, int C, int dtype,

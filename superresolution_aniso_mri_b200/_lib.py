@@ -27,7 +27,7 @@ _SIGNATURES = {
     "aesr_conv3x3_up2_head_fwd": (I, [P, P, P, P, P, I, I, I, I, I, F, I, I, P]),
     "aesr_head_gather": (I, [P, P, P, P, I, I, I, c_size_t, I, P]),
     "aesr_stem_fold": (I, [P, P, P, P, P, I, P]),
-    "aesr_stem_fwd": (I, [P, P, P, P, P, I, I, I, I, F, I, P]),
+    "aesr_stem_fwd": (I, [P, P, P, I, I, I, I, F, I, P]),
     "aesr_e0_fwd": (I, [P, P, P, P, I, I, I, I, I, P]),
     "aesr_head_fwd": (I, [P, P, P, P, P, I, I, I, I, c_size_t, I, I, P]),
     "aesr_lerp_latents": (I, [P, P, P, P, P, P, P, I, I, I, I, P]),

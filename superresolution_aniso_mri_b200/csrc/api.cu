@@ -401,20 +401,29 @@ int aesr_stem_fold(const float* w0, const float* b0, const float* w1, float* wef
     return check_launch("stem_fold");
 }
 
-int aesr_stem_fwd(const float* x, const float* weff, const float* beff, const float* b1, void* out, int N, int H, int W,
-                  int C, float slope, int dtype, void* stream) {
+int aesr_stem_fwd(const float* x, const float* weff_beff_b1_host, void* out, int N, int H, int W, int C, float slope,
+                  int dtype, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
-    if (!x || !weff || !beff || !b1 || !out || N <= 0 || H <= 0 || W <= 0 || C != 32)
+    if (!x || !weff_beff_b1_host || !out || N <= 0 || H <= 0 || W <= 0 || C != 32)
         return fail(AESR_ERR_INVALID, "stem_fwd: bad arguments (C = 32)");
     if (static_cast<size_t>(H + 2) * (W + 2) > (1u << 28)) return fail(AESR_ERR_INVALID, "stem_fwd: image too large");
-    const int per_img = (H + 2) * (W + 2) * 4;
-    const dim3 grid((per_img + 1023) / 1024, N < 65535 ? N : 65535);       // 4 items per thread
+    StemParams sp;
+    memcpy(sp.weff, weff_beff_b1_host, sizeof(sp.weff));
+    memcpy(sp.beff, weff_beff_b1_host + 9 * 32, sizeof(sp.beff));
+    memcpy(sp.b1, weff_beff_b1_host + 18 * 32, sizeof(sp.b1));
+    for (int c = 0; c < 32; ++c) {
+        float t = sp.b1[c];
+        for (int tap = 0; tap < 9; ++tap) t += sp.beff[tap * 32 + c];
+        sp.ball[c] = t;
+    }
+    const int per_img = (H + 2) * (W + 2);
+    const dim3 grid((per_img + 255) / 256, N < 65535 ? N : 65535);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == AESR_DT_FP16)
-        stem_conv_kernel<true><<<grid, 256, 0, s>>>(x, weff, beff, b1, static_cast<uint16_t*>(out), N, H, W, slope);
+        stem_conv_kernel<true><<<grid, 256, 0, s>>>(x, sp, static_cast<uint16_t*>(out), N, H, W, slope);
     else
-        stem_conv_kernel<false><<<grid, 256, 0, s>>>(x, weff, beff, b1, static_cast<uint16_t*>(out), N, H, W, slope);
+        stem_conv_kernel<false><<<grid, 256, 0, s>>>(x, sp, static_cast<uint16_t*>(out), N, H, W, slope);
     return check_launch("stem_conv");
 }
 

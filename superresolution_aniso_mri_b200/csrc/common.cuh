@@ -185,6 +185,14 @@ __host__ __device__ constexpr uint32_t make_idesc_16(uint32_t M, uint32_t N, int
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
+// 16-byte shared-memory load through an explicit shared-state-space address.  The epilogue constants are reached through
+// pointers carved out of the dynamic shared-memory block; the compiler loses the address space and emits generic LD.E
+// (long-scoreboard, L1-path latency) -- ncu showed the bias loads as the top stall of the thin-layer epilogue.
+__device__ __forceinline__ float4 lds_f4(const float* p) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);

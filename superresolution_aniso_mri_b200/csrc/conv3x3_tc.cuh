@@ -232,10 +232,9 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
         const int cg = t.n0 + c0;               // first global output channel of this chunk
         {
             // act(a) = max(a, a * neg_slope): neg_slope = 1 (identity), 0.01 (LeakyReLU), 0 (ReLU) -- branch-free
-            const float4* b4 = reinterpret_cast<const float4*>(bars.s_bias + cg);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 b = b4[j4];
+                const float4 b = lds_f4(bars.s_bias + cg + 4 * j4);
                 const float a0 = __uint_as_float(raw[j4 * 4 + 0]) + b.x, a1 = __uint_as_float(raw[j4 * 4 + 1]) + b.y;
                 const float a2 = __uint_as_float(raw[j4 * 4 + 2]) + b.z, a3 = __uint_as_float(raw[j4 * 4 + 3]) + b.w;
                 v[j4 * 4 + 0] = fmaxf(a0, a0 * neg_slope);
@@ -279,11 +278,9 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
             }
         }
         if (p.scale != nullptr) {
-            const float4* sc4 = reinterpret_cast<const float4*>(bars.s_scale + cg);
-            const float4* sh4 = reinterpret_cast<const float4*>(bars.s_shift + cg);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 sc = sc4[j4], sh = sh4[j4];
+                const float4 sc = lds_f4(bars.s_scale + cg + 4 * j4), sh = lds_f4(bars.s_shift + cg + 4 * j4);
                 v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], sc.x, sh.x);
                 v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], sc.y, sh.y);
                 v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], sc.z, sh.z);
@@ -417,10 +414,9 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
             }
             if (p.debug & 64) continue;
             // act(a) = max(a, a * neg_slope): neg_slope = 1 (identity), 0.01 (LeakyReLU), 0 (ReLU) -- branch-free
-            const float4* b4 = reinterpret_cast<const float4*>(bars.s_bias + cg);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 b = b4[j4];
+                const float4 b = lds_f4(bars.s_bias + cg + 4 * j4);
                 const float a0 = __uint_as_float(raw[j4 * 4 + 0]) + b.x, a1 = __uint_as_float(raw[j4 * 4 + 1]) + b.y;
                 const float a2 = __uint_as_float(raw[j4 * 4 + 2]) + b.z, a3 = __uint_as_float(raw[j4 * 4 + 3]) + b.w;
                 v[j4 * 4 + 0] = fmaxf(a0, a0 * neg_slope);
@@ -430,11 +426,9 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
             }
         }
         if (affine) {
-            const float4* sc4 = reinterpret_cast<const float4*>(bars.s_scale + cg);
-            const float4* sh4 = reinterpret_cast<const float4*>(bars.s_shift + cg);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 sc = sc4[j4], sh = sh4[j4];
+                const float4 sc = lds_f4(bars.s_scale + cg + 4 * j4), sh = lds_f4(bars.s_shift + cg + 4 * j4);
                 v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], sc.x, sh.x);
                 v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], sc.y, sh.y);
                 v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], sc.z, sh.z);
@@ -503,27 +497,30 @@ __device__ __forceinline__ void conv_epilogue_head_tile(const ConvParams& p, con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty_bar);
             }
-            float v[16];
-            const float4* b4 = reinterpret_cast<const float4*>(bars.s_bias + c0);   // phase blocks share the 32 biases
+            // packed fp32x2 math (add.f32x2 / mul.f32x2 / fma.rn.f32x2): even/odd channel pairs, half the issue slots
+            // -- with scalar FFMAs this epilogue was instruction-issue-bound (ncu: issue active 83 %, 2400 warp
+            // instructions per tile against 1152 tensor-pipe cycles).
+            float2 v[8];
+            const float2 slope2 = make_float2(neg_slope, neg_slope);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 b = b4[j4];
-                const float a0 = __uint_as_float(raw[j4 * 4 + 0]) + b.x, a1 = __uint_as_float(raw[j4 * 4 + 1]) + b.y;
-                const float a2 = __uint_as_float(raw[j4 * 4 + 2]) + b.z, a3 = __uint_as_float(raw[j4 * 4 + 3]) + b.w;
-                v[j4 * 4 + 0] = fmaxf(a0, a0 * neg_slope);
-                v[j4 * 4 + 1] = fmaxf(a1, a1 * neg_slope);
-                v[j4 * 4 + 2] = fmaxf(a2, a2 * neg_slope);
-                v[j4 * 4 + 3] = fmaxf(a3, a3 * neg_slope);
+                const float4 b = lds_f4(bars.s_bias + c0 + 4 * j4);           // phase blocks share the 32 biases
+                const float2 a0 = __fadd2_rn(make_float2(__uint_as_float(raw[j4 * 4 + 0]), __uint_as_float(raw[j4 * 4 + 1])),
+                                             make_float2(b.x, b.y));
+                const float2 a1 = __fadd2_rn(make_float2(__uint_as_float(raw[j4 * 4 + 2]), __uint_as_float(raw[j4 * 4 + 3])),
+                                             make_float2(b.z, b.w));
+                const float2 s0 = __fmul2_rn(a0, slope2), s1 = __fmul2_rn(a1, slope2);
+                v[j4 * 2 + 0] = make_float2(fmaxf(a0.x, s0.x), fmaxf(a0.y, s0.y));
+                v[j4 * 2 + 1] = make_float2(fmaxf(a1.x, s1.x), fmaxf(a1.y, s1.y));
             }
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-                float s0 = 0.f, s1 = 0.f;        // even / odd channels: shorter dependent chains
+                float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j2 = 0; j2 < 8; ++j2) {
-                    s0 = fmaf(v[2 * j2], p.head_wc[tap * 32 + c0 + 2 * j2], s0);
-                    s1 = fmaf(v[2 * j2 + 1], p.head_wc[tap * 32 + c0 + 2 * j2 + 1], s1);
-                }
-                tsum[tap] += s0 + s1;
+                for (int j2 = 0; j2 < 8; ++j2)
+                    acc = __ffma2_rn(v[j2], make_float2(p.head_wc[tap * 32 + c0 + 2 * j2], p.head_wc[tap * 32 + c0 + 2 * j2 + 1]),
+                                     acc);
+                tsum[tap] += acc.x + acc.y;
             }
         }
         // scatter the 3x3 tap sums into the 4x4 patch at the phase's offset (static indices under a phase predicate)

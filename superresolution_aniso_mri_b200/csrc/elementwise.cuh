@@ -194,61 +194,67 @@ __global__ void stem_fold_kernel(const float* __restrict__ w0, const float* __re
     beff[i] = sb;
 }
 
+// Folded stem parameters BY VALUE (kernel parameters live in the constant bank: the 288 MACs per pixel read their
+// weights as instruction operands, no shared-memory traffic).  ball = b1 + sum of all nine beff taps (interior pixels).
+struct StemParams {
+    alignas(16) float weff[9 * 32];
+    alignas(16) float beff[9 * 32];
+    alignas(16) float b1[32];
+    alignas(16) float ball[32];
+};
+
+// one thread = one output pixel x 32 channels: 9 image loads, 144 packed fp32x2 FMAs, one 64-byte store
 template <bool FP16>
 __global__ void __launch_bounds__(256)
-stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ weff, const float* __restrict__ beff,
-                 const float* __restrict__ b1, uint16_t* __restrict__ out, int N, int H, int W, float slope) {
+stem_conv_kernel(const float* __restrict__ x, const __grid_constant__ StemParams sp, uint16_t* __restrict__ out, int N,
+                 int H, int W, float slope) {
     constexpr int C = 32;
-    __shared__ __align__(16) float sw[9 * C], sb[9 * C], sb1[C], sball[C];
-    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) { sw[i] = weff[i]; sb[i] = beff[i]; }
-    if (threadIdx.x < C) {
-        float t = b1[threadIdx.x];
-        sb1[threadIdx.x] = t;
-        for (int tap = 0; tap < 9; ++tap) t += beff[tap * C + threadIdx.x];
-        sball[threadIdx.x] = t;             // interior pixels: all nine taps on the grid
-    }
-    __syncthreads();
-    // grid = (blocks per image, images): 32-bit index math only (a 64-bit div/mod per item costs more than the 72 FMAs)
     const int Ho = H + 2, Wo = W + 2;
-    const uint32_t per_img = static_cast<uint32_t>(Ho) * Wo * 4;
-    for (int n = blockIdx.y; n < N; n += gridDim.y)
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per_img; i += gridDim.x * blockDim.x) {
-        const int g = static_cast<int>(i & 3);
-        const uint32_t pix = i >> 2;
-        const int yo = static_cast<int>(pix / static_cast<uint32_t>(Wo));
-        const int xo = static_cast<int>(pix - static_cast<uint32_t>(yo) * Wo);
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= Ho * Wo) return;
+    const int yo = pix / Wo, xo = pix - yo * Wo;
+    const bool interior = yo >= 1 && yo <= H && xo >= 1 && xo <= W;
+    for (int n = blockIdx.y; n < N; n += gridDim.y) {
         const float* img = x + static_cast<size_t>(n) * H * W;
-        const bool interior = yo >= 1 && yo <= H && xo >= 1 && xo <= W;
-        float v[8];
-        if (interior) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = sball[g * 8 + j];
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = sb1[g * 8 + j];
-        }
+        float xv[9];
+        bool on_grid[9];
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
             const int yy = yo + tap / 3 - 1, xx = xo + tap % 3 - 1;        // position on the (H+2)x(W+2) grid
-            if (yy < 0 || yy >= Ho || xx < 0 || xx >= Wo) continue;        // enc.1 zero padding
+            on_grid[tap] = yy >= 0 && yy < Ho && xx >= 0 && xx < Wo;      // else: enc.1 zero padding
             const int yi = yy - 1, xi = xx - 1;                            // position in the image
-            const float xv = (yi >= 0 && yi < H && xi >= 0 && xi < W) ? __ldg(img + static_cast<size_t>(yi) * W + xi) : 0.f;
-            const float4* w4 = reinterpret_cast<const float4*>(sw + tap * C + g * 8);
-            const float4 wa = w4[0], wb = w4[1];
-            v[0] = fmaf(wa.x, xv, v[0]); v[1] = fmaf(wa.y, xv, v[1]); v[2] = fmaf(wa.z, xv, v[2]); v[3] = fmaf(wa.w, xv, v[3]);
-            v[4] = fmaf(wb.x, xv, v[4]); v[5] = fmaf(wb.y, xv, v[5]); v[6] = fmaf(wb.z, xv, v[6]); v[7] = fmaf(wb.w, xv, v[7]);
-            if (!interior) {
-                const float4* q4 = reinterpret_cast<const float4*>(sb + tap * C + g * 8);
-                const float4 qa = q4[0], qb = q4[1];
-                v[0] += qa.x; v[1] += qa.y; v[2] += qa.z; v[3] += qa.w;
-                v[4] += qb.x; v[5] += qb.y; v[6] += qb.z; v[7] += qb.w;
+            xv[tap] = (yi >= 0 && yi < H && xi >= 0 && xi < W) ? __ldg(img + static_cast<size_t>(yi) * W + xi) : 0.f;
+        }
+        float2 acc[C / 2];
+        if (interior) {
+#pragma unroll
+            for (int j = 0; j < C / 2; ++j) acc[j] = make_float2(sp.ball[2 * j], sp.ball[2 * j + 1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < C / 2; ++j) acc[j] = make_float2(sp.b1[2 * j], sp.b1[2 * j + 1]);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                if (on_grid[tap]) {
+#pragma unroll
+                    for (int j = 0; j < C / 2; ++j)
+                        acc[j] = __fadd2_rn(acc[j], make_float2(sp.beff[tap * C + 2 * j], sp.beff[tap * C + 2 * j + 1]));
+                }
             }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], v[j] * slope);
-        reinterpret_cast<uint4*>(out)[static_cast<size_t>(n) * per_img + i] =
-            make_uint4(pack2_t<FP16>(v[0], v[1]), pack2_t<FP16>(v[2], v[3]), pack2_t<FP16>(v[4], v[5]),
-                       pack2_t<FP16>(v[6], v[7]));
+        for (int tap = 0; tap < 9; ++tap) {
+            const float2 x2 = make_float2(xv[tap], xv[tap]);
+#pragma unroll
+            for (int j = 0; j < C / 2; ++j)
+                acc[j] = __ffma2_rn(make_float2(sp.weff[tap * C + 2 * j], sp.weff[tap * C + 2 * j + 1]), x2, acc[j]);
+        }
+        uint32_t pk[C / 2];
+#pragma unroll
+        for (int j = 0; j < C / 2; ++j)
+            pk[j] = pack2_t<FP16>(fmaxf(acc[j].x, acc[j].x * slope), fmaxf(acc[j].y, acc[j].y * slope));
+        uint4* o4 = reinterpret_cast<uint4*>(out + (static_cast<size_t>(n) * Ho * Wo + pix) * C);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) o4[j4] = make_uint4(pk[4 * j4], pk[4 * j4 + 1], pk[4 * j4 + 2], pk[4 * j4 + 3]);
     }
 }
 

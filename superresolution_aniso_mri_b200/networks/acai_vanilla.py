@@ -206,8 +206,8 @@ class VanillaACAI(nn.Module):
 
     def _stem(self):
         c0, c1 = self.enc[0], self.enc[1]
-        return self._cache.get(("stem",), [c0.weight, c0.bias, c1.weight],
-                               lambda: ops.stem_fold(c0.weight, c0.bias, c1.weight))
+        return self._cache.get(("stem",), [c0.weight, c0.bias, c1.weight, c1.bias],
+                               lambda: ops.stem_host_params(*ops.stem_fold(c0.weight, c0.bias, c1.weight), c1.bias))
 
     def _head_w_host(self, conv: ConvHolder):
         """fp32 [9,32] head filter in host memory (one device->host copy per parameter version)."""
@@ -228,8 +228,7 @@ class VanillaACAI(nn.Module):
         enc = self.enc
         fused = self.fused_inference
         if fused:
-            weff, beff = self._stem()
-            a = ops.stem(x, weff, beff, enc[1].bias.detach())
+            a = ops.stem(x, self._stem())
         else:
             a = ops.e0(x, enc[0].weight.detach().reshape(-1).contiguous(), enc[0].bias.detach())
         i = 1

@@ -182,18 +182,24 @@ def stem_fold(w0: torch.Tensor, b0: torch.Tensor, w1: torch.Tensor):
     return weff, beff
 
 
-def stem(x: torch.Tensor, weff: torch.Tensor, beff: torch.Tensor, b1: torch.Tensor, slope: float = LEAKY_SLOPE,
+def stem_host_params(weff: torch.Tensor, beff: torch.Tensor, b1: torch.Tensor) -> torch.Tensor:
+    """[weff | beff | b1] as one fp32 HOST tensor (608 floats): travels to ``stem`` as kernel parameters."""
+    return torch.cat([t.detach().reshape(-1).float().cpu() for t in (weff, beff, b1)]).contiguous()
+
+
+def stem(x: torch.Tensor, params_host: torch.Tensor, slope: float = LEAKY_SLOPE,
          dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """enc.0 + enc.1 + LeakyReLU: x fp32 [N,1,H,W] -> NHWC 16-bit [N,H+2,W+2,32]."""
     lib = _dev(x)
     dtype = dtype or DEFAULT_DTYPE
     assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 1
+    assert not params_host.is_cuda and params_host.numel() == 608 and params_host.dtype == torch.float32
     n, _, h, wd = x.shape
-    c = weff.shape[1]
+    c = 32
     out = torch.empty((n, h + 2, wd + 2, c), dtype=dtype, device=x.device)
     with _timed("stem", 2.0 * n * (h + 2) * (wd + 2) * c * (1 + 9 * c)):
-        _lib.check(lib.aesr_stem_fwd(x.data_ptr(), weff.data_ptr(), beff.data_ptr(), b1.data_ptr(), out.data_ptr(), n, h,
-                                     wd, c, float(slope), dt_code(dtype), _stream(x)), "stem_fwd")
+        _lib.check(lib.aesr_stem_fwd(x.data_ptr(), params_host.data_ptr(), out.data_ptr(), n, h, wd, c, float(slope),
+                                     dt_code(dtype), _stream(x)), "stem_fwd")
     return out
 
 

@@ -238,7 +238,7 @@ def test_encoder_stem_fold_vs_torch(dev, shape):
     w0, b0 = torch.randn(32, generator=g), torch.randn(32, generator=g)
     w1, b1 = torch.randn(32, 32, 3, 3, generator=g) / 17, torch.randn(32, generator=g) * 0.1
     weff, beff = ops.stem_fold(w0.to(dev), b0.to(dev), w1.to(dev))
-    got = ops.stem(x.to(dev), weff, beff, b1.to(dev))
+    got = ops.stem(x.to(dev), ops.stem_host_params(weff, beff, b1))
     want = F.leaky_relu(F.conv2d(F.conv2d(x.double(), w0.double().view(32, 1, 1, 1), b0.double(), padding=1),
                                  w1.double(), b1.double(), padding=1), 0.01)
     assert got.shape == (n, h + 2, w + 2, 32)
