@@ -246,9 +246,16 @@ def run_ours(a):
             kernel_ms[name] = kernel_ms.get(name, 0.0) + e0.elapsed_time(e1)
         ops.TIMING = None
         ach = conv_fl / (conv_ms * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        tj = os.path.join(ROOT, "profiles", "r01b_conv_full.json")      # ncu --set full capture of the same conv launches
+        if os.path.exists(tj):
+            with open(tj) as f:
+                traffic = json.load(f)["mean_dram_bytes_per_launch"]
+            traffic_src = "profiles/r01b_conv_full.json (dram__bytes_read.sum + dram__bytes_write.sum, mean per conv launch)"
         roof = {"bound": "tensor", "kernel": "conv3x3_halo_kernel (tcgen05, all %d launches of a step)" % n_conv,
                 "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": None,
                 "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" % peaks["source"],
                 "conv_ms_per_step": conv_ms, "all_kernels_ms_per_step": all_ms,
                 "conv_share_of_kernel_time": conv_ms / all_ms if all_ms else None,
@@ -374,7 +381,8 @@ def bench_train(a, dev, rank, world, barrier):
                     "h2d_bytes_per_step": 36 * SIZE * SIZE * 4, "d2h_bytes_per_step": 16 + 48,
                     "ms_per_step": out["e2e"] / steps},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": None,
                          "note": "whole step (573 algorithmic GFLOP) over step time", "kernel_ms": agg},
             "cpu_baseline": {"value": cpu_rate, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": "2 steps of B=12 after 1 warm-up, %.2f s/step, oracle port of "

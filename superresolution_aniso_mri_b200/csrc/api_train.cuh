@@ -91,14 +91,13 @@ int aesr_head_bwd(const float* dout, const float* out, const void* a_in, const f
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t total = static_cast<size_t>(N) * H * W;
     const uint16_t* a16 = static_cast<const uint16_t*>(a_in);
-    if (dtype == AESR_DT_FP16) {
-        head_bwd_data_kernel<32, true><<<grid_for(total, 128, 32), 128, 0, s>>>(dout, out, a16, w9c, static_cast<uint16_t*>(g_in), N, H, W, slope);
-        head_bwd_weight_kernel<32, true><<<grid_for(total * 32 / 8, 256, 8), 256, 0, s>>>(dout, out, a16, dw9c, dbias, N, H, W);
-    } else {
-        head_bwd_data_kernel<32, false><<<grid_for(total, 128, 32), 128, 0, s>>>(dout, out, a16, w9c, static_cast<uint16_t*>(g_in), N, H, W, slope);
-        head_bwd_weight_kernel<32, false><<<grid_for(total * 32 / 8, 256, 8), 256, 0, s>>>(dout, out, a16, dw9c, dbias, N, H, W);
-    }
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    size_t blocks = (total * 4 + 255) / 256;
+    const size_t cap = static_cast<size_t>(g_sm_count);            // one resident block per SM (190 registers); 288 global atomics each at the end
+    if (blocks > cap) blocks = cap;
+    if (dtype == AESR_DT_FP16)
+        head_bwd_fused_kernel<true><<<static_cast<int>(blocks), 256, 0, s>>>(dout, out, a16, w9c, static_cast<uint16_t*>(g_in), dw9c, dbias, N, H, W, slope);
+    else
+        head_bwd_fused_kernel<false><<<static_cast<int>(blocks), 256, 0, s>>>(dout, out, a16, w9c, static_cast<uint16_t*>(g_in), dw9c, dbias, N, H, W, slope);
     return check_launch("head_bwd");
 }
 

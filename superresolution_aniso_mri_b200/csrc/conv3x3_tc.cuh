@@ -189,12 +189,37 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvParams& p, int sp, int
     return t;
 }
 
-// Epilogue of one tile, executed by the 4 epilogue warps (128 threads = 128 TMEM lanes = 128 pixels).
-// MODE >= 0: the output stage is a compile-time constant and the training extras (act' multiplier, BN statistics, second
-// output) are compiled out -- the inference instantiations; with every stage selected at run time the inlined body
-// exceeds the 96 registers a 576-thread CTA allows and the per-tile loop state spills to local memory (ncu: LDL stalls
-// on the loop counters in every tile).  MODE < 0: everything dynamic (training, VGG).
-template <int MODE>
+// Sum of 16 per-lane values over the 32 lanes of a warp, transposed: 16 shuffles instead of 16 x 5 butterflies.  Each
+// round a lane keeps half of its values and sends the other half to its partner (lane ^ 16, 8, 4, 2), adding what it
+// receives; a last xor-1 round folds the remaining pair.  On return lane l holds the total of value index
+// ((l >> 4) & 1) * 8 + ((l >> 3) & 1) * 4 + ((l >> 2) & 1) * 2 + ((l >> 1) & 1)  (both lanes of a pair hold it).
+__device__ __forceinline__ float warp_transpose_sum16(const float (&v)[16], int lane) {
+    float a8[8], a4[4], a2[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float keep = h16 ? v[8 + j] : v[j], send = h16 ? v[j] : v[8 + j];
+        a8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float keep = h8 ? a8[4 + j] : a8[j], send = h8 ? a8[j] : a8[4 + j];
+        a4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float keep = h4 ? a4[2 + j] : a4[j], send = h4 ? a4[j] : a4[2 + j];
+        a2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const float keep = h2 ? a2[1] : a2[0], send = h2 ? a2[0] : a2[1];
+    float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;
+}
+
+// General epilogue of one tile (training and VGG: act' multiplier, BN statistics, second outputs, every output stage
+// selected at run time), executed by the 4 warps of an epilogue set (128 threads = 128 TMEM lanes = 128 pixels);
+// 16 accumulator columns per TMEM load to stay inside the 96-register budget of a 576-thread CTA.
 __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
                                                    uint64_t* tmem_empty_bar, const TileCoord& t) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -208,32 +233,29 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
     const uint32_t t_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
     uint16_t* out16 = static_cast<uint16_t*>(p.out);
     uint16_t* out2_16 = static_cast<uint16_t*>(p.out2);
-    constexpr bool DYN = MODE < 0;
-    const int out_mode = DYN ? p.out_mode : MODE;
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        uint32_t raw[32];
-        if (p.debug & 8) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) raw[j] = 0;
-        } else {
-            tmem_ld_32x32b_x32(t_addr + c0, raw);
-            tmem_ld_wait();
-        }
-        if (c0 + 32 >= p.BN) {                  // accumulator fully read: hand it back to the MMA warp
-            // one arrive per WARP (128 same-address shared-memory atomics per tile serialise in the LSU, next to
-            // the MMA's operand reads): every lane's tcgen05.ld has completed (wait::ld above), the warp converges,
-            // lane 0 signals for all 32 TMEM lanes of this warp's quadrant.
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar);
-        }
-        if (p.debug & 64) continue;
-        float v[32];
+    const int out_mode = p.out_mode;
+    const size_t pix = (static_cast<size_t>(n) * H + y) * W + x;
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        float v[16];
         const int cg = t.n0 + c0;               // first global output channel of this chunk
         {
+            uint32_t raw[16];
+            if (p.debug & 8) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) raw[j] = 0;
+            } else {
+                tmem_ld_32x32b_x16(t_addr + c0, raw);
+                tmem_ld_wait();
+            }
+            if (c0 + 16 >= p.BN) {              // accumulator fully read: one elected arrive per warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar);
+            }
+            if (p.debug & 64) continue;
             // act(a) = max(a, a * neg_slope): neg_slope = 1 (identity), 0.01 (LeakyReLU), 0 (ReLU) -- branch-free
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
+            for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 b = lds_f4(bars.s_bias + cg + 4 * j4);
                 const float a0 = __uint_as_float(raw[j4 * 4 + 0]) + b.x, a1 = __uint_as_float(raw[j4 * 4 + 1]) + b.y;
                 const float a2 = __uint_as_float(raw[j4 * 4 + 2]) + b.z, a3 = __uint_as_float(raw[j4 * 4 + 3]) + b.w;
@@ -243,13 +265,12 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                 v[j4 * 4 + 3] = fmaxf(a3, a3 * neg_slope);
             }
         }
-        if (DYN && p.mul_mode != MUL_NONE) {
+        if (p.mul_mode != MUL_NONE) {
             if (inb) {
-                const uint4* m4 = reinterpret_cast<const uint4*>(
-                    p.mul_src + (static_cast<size_t>(n) * H * W + static_cast<size_t>(y) * W + x) * Cout + cg);
+                const uint4* m4 = reinterpret_cast<const uint4*>(p.mul_src + pix * Cout + cg);
                 const float neg = (p.mul_mode == MUL_LEAKY_GRAD) ? p.slope : 0.f;
 #pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) {
+                for (int j4 = 0; j4 < 2; ++j4) {
                     const uint4 m = __ldg(m4 + j4);
                     const uint32_t w[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
@@ -260,26 +281,25 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                 }
             }
         }
-        if (DYN && p.stats != nullptr) {
-            // per-channel sum / sum of squares over the valid pixels of this warp, then one atomic per channel
+        if (p.stats != nullptr) {
+            // per-channel sum / sum of squares over the valid pixels of this warp (transposed warp reduction), then one
+            // atomic per channel from the even lane of each pair
+            float s1[16], s2[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float s1 = inb ? v[j] : 0.f;
-                float s2 = s1 * s1;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                }
-                if (lane == j) {
-                    atomicAdd(p.stats + cg + j, s1);
-                    atomicAdd(p.stats + Cout + cg + j, s2);
-                }
+            for (int j = 0; j < 16; ++j) {
+                s1[j] = inb ? v[j] : 0.f;
+                s2[j] = s1[j] * s1[j];
+            }
+            const float t1 = warp_transpose_sum16(s1, lane), t2 = warp_transpose_sum16(s2, lane);
+            const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if ((lane & 1) == 0) {
+                atomicAdd(p.stats + cg + ch, t1);
+                atomicAdd(p.stats + Cout + cg + ch, t2);
             }
         }
         if (p.scale != nullptr) {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
+            for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 sc = lds_f4(bars.s_scale + cg + 4 * j4), sh = lds_f4(bars.s_shift + cg + 4 * j4);
                 v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], sc.x, sh.x);
                 v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], sc.y, sh.y);
@@ -288,18 +308,17 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
             }
         }
         if (out_mode == OUT_SAME || out_mode == OUT_SAME_MAXPOOL2) {
-            if (inb && !((p.debug & 4) && v[0] != 12345.f)) {
-                uint4* o4 = reinterpret_cast<uint4*>(
-                    out16 + (static_cast<size_t>(n) * H * W + static_cast<size_t>(y) * W + x) * Cout + cg);
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) o4[j4] = pack8(v + j4 * 8, fp16);
+            if (inb && !(p.debug & 4)) {
+                uint4* o4 = reinterpret_cast<uint4*>(out16 + pix * Cout + cg);
+                o4[0] = pack8(v, fp16);
+                o4[1] = pack8(v + 8, fp16);
             }
         }
         if (out_mode == OUT_AVGPOOL2 || out_mode == OUT_SAME_MAXPOOL2) {
             // 2x2 window = lanes {l, l^1, l^8} (x neighbour, y neighbour): tile origins are even.
             const bool is_max = (out_mode == OUT_SAME_MAXPOOL2);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 float a = v[j];
                 float b = __shfl_xor_sync(0xffffffffu, a, 1);
                 a = is_max ? fmaxf(a, b) : a + b;
@@ -313,22 +332,20 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                 uint16_t* dst = (out_mode == OUT_AVGPOOL2) ? out16 : out2_16;
                 uint4* o4 = reinterpret_cast<uint4*>(
                     dst + (static_cast<size_t>(n) * Ho * Wo + static_cast<size_t>(yo) * Wo + xo) * Cout + cg);
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) o4[j4] = pack8(v + j4 * 8, fp16);
+                o4[0] = pack8(v, fp16);
+                o4[1] = pack8(v + 8, fp16);
             }
         } else if (out_mode == OUT_UP2) {
             if (inb) {
-                const int Ho = 2 * H, Wo = 2 * W;
-                uint4 pk[4];
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) pk[j4] = pack8(v + j4 * 8, fp16);
+                const int Wo = 2 * W;
+                const uint4 pk0 = pack8(v, fp16), pk1 = pack8(v + 8, fp16);
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
                     const int yo = 2 * y + (d >> 1), xo = 2 * x + (d & 1);
                     uint4* o4 = reinterpret_cast<uint4*>(
-                        out16 + (static_cast<size_t>(n) * Ho * Wo + static_cast<size_t>(yo) * Wo + xo) * Cout + cg);
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) o4[j4] = pk[j4];
+                        out16 + ((static_cast<size_t>(n) * 2 * H + yo) * Wo + xo) * Cout + cg);
+                    o4[0] = pk0;
+                    o4[1] = pk1;
                 }
             }
         } else if (out_mode == OUT_SHUFFLE2) {
@@ -338,26 +355,24 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                 const int yo = 2 * y + (ph >> 1), xo = 2 * x + (ph & 1);
                 uint4* o4 = reinterpret_cast<uint4*>(
                     out16 + ((static_cast<size_t>(n) * 2 * H + yo) * (2 * W) + xo) * C + ch);
-#pragma unroll
-                for (int j4 = 0; j4 < 4; ++j4) o4[j4] = pack8(v + j4 * 8, fp16);
+                o4[0] = pack8(v, fp16);
+                o4[1] = pack8(v + 8, fp16);
             }
         } else if (out_mode == OUT_NCHW_F32) {
             if (inb) {
                 float* o = static_cast<float*>(p.out) + (static_cast<size_t>(n) * Cout + cg) * H * W +
                            static_cast<size_t>(y) * W + x;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) o[static_cast<size_t>(j) * H * W] = v[j];
+                for (int j = 0; j < 16; ++j) o[static_cast<size_t>(j) * H * W] = v[j];
                 if (p.out2 != nullptr) {
-                    uint4* o4 = reinterpret_cast<uint4*>(
-                        out2_16 + (static_cast<size_t>(n) * H * W + static_cast<size_t>(y) * W + x) * Cout + cg);
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) o4[j4] = pack8(v + j4 * 8, fp16);
+                    uint4* o4 = reinterpret_cast<uint4*>(out2_16 + pix * Cout + cg);
+                    o4[0] = pack8(v, fp16);
+                    o4[1] = pack8(v + 8, fp16);
                 }
             }
         }
     }
 }
-
 
 // Lean epilogue of the inference output stages (OUT_SAME, OUT_AVGPOOL2, OUT_SHUFFLE2; no training extras): 16 accumulator
 // columns per TMEM load, so that 16 values + addresses + the role's loop state stay far below the 96 registers a
@@ -738,7 +753,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     const uint32_t acc = tmem_base + (buf * T + t) * p.BN;
                     if (MODE == OUT_SHUFFLE2_HEAD) conv_epilogue_head_tile(p, bars, acc, &bars.tmem_empty[buf], tc);
                     else if (MODE >= 0) conv_epilogue_lean<MODE>(p, bars, acc, &bars.tmem_empty[buf], tc);
-                    else conv_epilogue_tile<-1>(p, bars, acc, &bars.tmem_empty[buf], tc);
+                    else conv_epilogue_tile(p, bars, acc, &bars.tmem_empty[buf], tc);
                 } else {                       // M-tile below the image: nothing to read, release the buffer
                     tc_fence_before();
                     __syncwarp();
@@ -843,7 +858,7 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 const TileCoord t = tile_coord(p, tile / p.n_blocks, tile % p.n_blocks);
                 mbar_wait(&bars.tmem_full[eset], acc_phase);
                 tc_fence_after();
-                conv_epilogue_tile<-1>(p, bars, tmem_base + eset * p.BN, &bars.tmem_empty[eset], t);
+                conv_epilogue_tile(p, bars, tmem_base + eset * p.BN, &bars.tmem_empty[eset], t);
                 acc_phase ^= 1;
             }
         }

@@ -245,6 +245,97 @@ __global__ void head_bwd_data_kernel(const float* __restrict__ dout, const float
     }
 }
 
+// Fused data + weight gradient of the head (one pass over a_in): both need the SAME nine neighbours dl[p - off(t)]:
+//   g_in[p][c]  = act'(a_in[p][c]) * sum_t w[t][c] * dl[p - off(t)]
+//   dW[t][c]   += a_in[p][c] * dl[p - off(t)]        (sum over q of dl[q] * a[q + off(t)] re-indexed by p = q + off(t))
+// thread = (pixel, 8-channel group): one 16-byte load of a_in, one 16-byte store of g_in (both coalesced), 72 + 72 FMAs,
+// 72 register accumulators reduced through shared-memory atomics once per block.  (The two-kernel version stored g_in
+// with 2-byte scattered stores and gathered a_in nine times: 1.44 ms of an 8 ms step.)
+template <bool AF>
+__global__ void __launch_bounds__(256)
+head_bwd_fused_kernel(const float* __restrict__ dout, const float* __restrict__ out, const uint16_t* __restrict__ a_in,
+                      const float* __restrict__ w /*[9][32]*/, uint16_t* __restrict__ g_in,
+                      float* __restrict__ dw /*[32][9]*/, float* __restrict__ dbias, int N, int H, int W, float slope) {
+    constexpr int C = 32;
+    __shared__ float sw[9 * C];
+    __shared__ float sdw[9 * C + 1];
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) { sw[i] = w[i]; sdw[i] = 0.f; }
+    if (threadIdx.x == 0) sdw[9 * C] = 0.f;
+    __syncthreads();
+    const int g = threadIdx.x & 3;                       // channel group: stays fixed along the grid-stride loop
+    float wreg[9][8], acc[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { wreg[t][j] = sw[t * C + g * 8 + j]; acc[t][j] = 0.f; }
+    float accb = 0.f;
+    const uint32_t per_img = static_cast<uint32_t>(H) * W;
+    const size_t total = static_cast<size_t>(N) * per_img * 4;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t pix = i >> 2;
+        const uint32_t n = static_cast<uint32_t>(pix / per_img);
+        const uint32_t r = static_cast<uint32_t>(pix - static_cast<size_t>(n) * per_img);
+        const int y = static_cast<int>(r / static_cast<uint32_t>(W)), x = static_cast<int>(r - static_cast<uint32_t>(y) * W);
+        const size_t nb = static_cast<size_t>(n) * per_img;
+        float dl[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
+            float v = 0.f;
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+                const size_t q = nb + static_cast<size_t>(yy) * W + xx;
+                const float o = __ldg(out + q);
+                v = __ldg(dout + q) * o * (1.f - o);
+            }
+            dl[t] = v;
+        }
+        if (g == 0) accb += dl[4];
+        const uint4 araw = __ldg(reinterpret_cast<const uint4*>(a_in) + i);
+        const uint32_t aw[4] = {araw.x, araw.y, araw.z, araw.w};
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            a[2 * k] = a16_to_f<AF>(static_cast<uint16_t>(aw[k] & 0xFFFFu));
+            a[2 * k + 1] = a16_to_f<AF>(static_cast<uint16_t>(aw[k] >> 16));
+        }
+        float gv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv[j] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                gv[j] = fmaf(wreg[t][j], dl[t], gv[j]);
+                acc[t][j] = fmaf(a[j], dl[t], acc[t][j]);
+            }
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            pk[k] = pack_bf16x2(gv[2 * k] * (a[2 * k] > 0.f ? 1.f : slope), gv[2 * k + 1] * (a[2 * k + 1] > 0.f ? 1.f : slope));
+        reinterpret_cast<uint4*>(g_in)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+    // lanes with the same channel group (lane & 3): butterfly over lane bits 2..4, then one shared atomic per value
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = acc[t][j];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if ((threadIdx.x & 31) < 4) atomicAdd(&sdw[t * C + g * 8 + j], v);
+        }
+    accb = warp_sum(accb);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sdw[9 * C], accb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+        const int t = i / C, c = i - t * C;
+        atomicAdd(dw + c * 9 + t, sdw[i]);               // nn.Conv2d layout [1][C][3][3]
+    }
+    if (threadIdx.x == 0) atomicAdd(dbias, sdw[9 * C]);
+}
+
 // one warp handles a strip of pixels; lane = channel (C = 32); 9 tap accumulators per lane.
 template <int C, bool AF>
 __global__ void head_bwd_weight_kernel(const float* __restrict__ dout, const float* __restrict__ out,

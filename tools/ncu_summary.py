@@ -67,6 +67,19 @@ def full(src, dst):
             for i in idx:
                 f.write("| %s | %s | %s |\n" % (hdr[i], r[i], units[i]))
             f.write("\n")
+    # machine-readable DRAM traffic per launch (bench.py's roofline.traffic)
+    def mb(r, name):
+        i = hdr.index(name)
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+        return float(r[i]) * scale
+    launches = [{"kernel": short(r[hdr.index("Kernel Name")]), "dram_bytes": mb(r, "dram__bytes_read.sum") + mb(r, "dram__bytes_write.sum"),
+                 "us": float(r[hdr.index("gpu__time_duration.sum")]),
+                 "tensor_pct": float(r[hdr.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")])}
+                for r in rows[2:]]
+    import json
+    with open(dst.replace(".md", ".json"), "w") as f:
+        json.dump({"source": src, "mean_dram_bytes_per_launch": sum(l["dram_bytes"] for l in launches) / len(launches),
+                   "launches": launches}, f, indent=1)
 
 
 if __name__ == "__main__":
