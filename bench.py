@@ -31,6 +31,7 @@ METRIC = "synthesized_hr_slices_per_sec"
 Z, SIZE, NI = 10, 128, 6
 # algorithmic conv FLOPs (2*MAC) of the reference's formulation, per image (ACDC scales=2 @128^2)
 ENC_GMAC, DEC_GMAC = 0.7722, 0.3822
+STEM_GMAC = (32 * 130 * 130 + 9 * 32 * 32 * 130 * 130) / 1e9      # enc.0 + enc.1 (folded into the CUDA-core stem kernel)
 
 
 def flops_per_step(V: int) -> float:
@@ -49,39 +50,78 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    """SM clock + clock-event (throttle) reasons while the timed region runs.  NVML in-process (one sample every few
+    ms, so that a 100 ms timed region is covered by tens of samples); nvidia-smi subprocess as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"),
+                    (0x4, "sw_power_cap"), (0x80, "hw_power_brake_slowdown"))
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_s: float = 0.004):
         super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.rows, self._halt, self.period = index, [], threading.Event(), period_s
+        self.nvml, self.handle, self.max_mhz, self.how = None, None, None, "nvidia-smi"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.nvml, self.handle, self.how = pynvml, h, "nvml"
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        mhz = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        try:
+            mw = float(n.nvmlDeviceGetPowerUsage(h))
+        except Exception:
+            mw = 0.0
+        self.rows.append((mhz, mask, mw))
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                         timeout=5).stdout
+                    parts = [x.strip() for x in out.strip().split(",")]
+                    if len(parts) >= 6:
+                        mask = 0
+                        for (bit, _n), v in zip(self.NVML_REASONS[:4], parts[2:6]):
+                            if v.lower().startswith("active"):
+                                mask |= bit
+                        self.max_mhz = float(parts[1])
+                        self.rows.append((float(parts[0]), mask, 0.0))
             except Exception:
                 pass
-            self._halt.wait(0.1)
+            self._halt.wait(self.period if self.nvml is not None else 0.1)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=6)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows)
-        reasons = set()
+        sm = sorted(r[0] for r in self.rows)
+        mask = 0
         for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+            mask |= r[1]
+        reasons = [name for bit, name in self.NVML_REASONS if mask & bit]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                "samples": len(self.rows), "power_w_max": max(r[2] for r in self.rows) / 1e3, "how": self.how}
 
 
 # ---------------------------------------------------------------------------------------------- reference arm (CPU)
@@ -245,7 +285,12 @@ def run_ours(a):
         for name, e0, e1, fl, _d in ops.TIMING:
             kernel_ms[name] = kernel_ms.get(name, 0.0) + e0.elapsed_time(e1)
         ops.TIMING = None
-        ach = conv_fl / (conv_ms * 1e-3) / 1e12
+        # ALGORITHMIC FLOPs (reference formulation, minimal-work count: each LR slice encoded once, each
+        # synthesized slice decoded once) of the layers the conv kernel family computes = everything but the stem
+        # (enc.0 + enc.1, a CUDA-core kernel).  The algebraic folds change the EXECUTED MMA work (dec.0 runs once per
+        # LR slice behind the interpolation; folded upsample convs execute the same MACs): reported separately.
+        alg_fl = 2e9 * (V * Z * (ENC_GMAC - STEM_GMAC) + V * (Z - 1) * NI * DEC_GMAC)
+        ach = alg_fl / (conv_ms * 1e-3) / 1e12
         traffic, traffic_src = None, None
         tj = os.path.join(ROOT, "profiles", "r01b_conv_full.json")      # ncu --set full capture of the same conv launches
         if os.path.exists(tj):
@@ -259,7 +304,8 @@ def run_ours(a):
                 "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" % peaks["source"],
                 "conv_ms_per_step": conv_ms, "all_kernels_ms_per_step": all_ms,
                 "conv_share_of_kernel_time": conv_ms / all_ms if all_ms else None,
-                "algorithmic_gflop_per_step": conv_fl / 1e9, "kernel_ms": kernel_ms}
+                "algorithmic_gflop_per_step": alg_fl / 1e9, "executed_gflop_per_step": conv_fl / 1e9,
+                "executed_tflops": conv_fl / (conv_ms * 1e-3) / 1e12, "kernel_ms": kernel_ms}
 
     train = bench_train(a, dev, rank, world, barrier) if a.train else None
 
@@ -381,8 +427,7 @@ def bench_train(a, dev, rank, world, barrier):
                     "h2d_bytes_per_step": 36 * SIZE * SIZE * 4, "d2h_bytes_per_step": 16 + 48,
                     "ms_per_step": out["e2e"] / steps},
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": None,
+                         "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
                          "note": "whole step (573 algorithmic GFLOP) over step time", "kernel_ms": agg},
             "cpu_baseline": {"value": cpu_rate, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": "2 steps of B=12 after 1 warm-up, %.2f s/step, oracle port of "
@@ -396,7 +441,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--volumes", type=int, default=64, help="volumes per GPU per step")
-    ap.add_argument("--chunk", type=int, default=256, help="slices per kernel launch")
+    ap.add_argument("--chunk", type=int, default=4096, help="max slices per kernel launch")
     ap.add_argument("--groups", type=int, default=4, help="e2e: volume groups pipelined over copy/compute streams")
     ap.add_argument("--cpu-sample", type=int, default=4, dest="cpu_sample")
     ap.add_argument("--no-train", action="store_false", dest="train", help="skip the training-step measurement")

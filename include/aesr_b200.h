@@ -50,6 +50,9 @@ extern "C" {
 #define AESR_OUT_SHUFFLE2 5      /* nn.Upsample(2) + the NEXT nn.Conv2d folded into one low-res conv with 4*C phase
                                     channels (weights from aesr_pack_conv3x3_weight_up2fold) + depth-to-space store:
                                     networks/acai_vanilla.py:92 followed by :87 / :96.  out NHWC 16-bit [N,2H,2W,Cout/4] */
+#define AESR_OUT_SAME_F32 7      /* NHWC fp32 [N,H,W,Cout], accumulators not rounded: the decoder's first conv
+                                    (networks/acai_vanilla.py:87) applied to the latents BEFORE the interpolation
+                                    (generate_hr_volumes.py:88; a conv is linear) -- see aesr_lerp_pairs_act */
 
 #define AESR_MUL_NONE 0
 #define AESR_MUL_LEAKY_GRAD 1 /* dgrad epilogue: multiply by LeakyReLU'(mul_src) */
@@ -137,6 +140,15 @@ int aesr_lerp_latents(const float* z, const int* ia, const int* ib, const float*
  * here the two fp32 latents of a pair are read once): out[p*K+k] = wa[k] * z[pa[p]] + wb[k] * z[pb[p]], NHWC 16-bit. */
 int aesr_lerp_pairs(const float* z, const int* pa, const int* pb, const float* wa, const float* wb, void* out_nhwc,
                     int P, int K, int C, int HW, int dtype, void* stream);
+
+/* Interpolation moved BEHIND the decoder's first conv (generate_hr_volumes.py:88 + networks/acai_vanilla.py:87-88):
+ *   dec.0(wa*z1 + wb*z2) = wa*conv(z1) + wb*conv(z2) + bias, so the conv runs once per low-resolution slice.
+ *   pre  fp32 NHWC [*,HW,C] = aesr_conv3x3_fwd(..., bias NULL, AESR_ACT_NONE, AESR_OUT_SAME_F32) of the encoder latents
+ *   out[p*K+k] = LeakyReLU_slope(wa[k] * pre[pa[p]] + wb[k] * pre[pb[p]] + bias[c])   NHWC 16-bit [P*K,HW,C]
+ * (slope = 1: no activation; bias may be NULL).  P <= 65535 per call, C % 8 == 0. */
+int aesr_lerp_pairs_act(const float* pre, const int* pa, const int* pb, const float* wa, const float* wb,
+                        const float* bias, void* out_nhwc, int P, int K, int C, int HW, float slope, int dtype,
+                        void* stream);
 
 /* Kept (non-synthesized) slices of the HR volume: dst[out_index[n]] = clamp(src[n], 0, 1)
  * (generate_hr_volumes.py:44,58-67: `recon_volume = images`, the torch.cat chain, the final torch.clamp).

@@ -33,6 +33,7 @@ _SIGNATURES = {
     "aesr_lerp_latents": (I, [P, P, P, P, P, P, P, I, I, I, I, P]),
     "aesr_place_slices": (I, [P, P, P, I, I, I, P]),
     "aesr_lerp_pairs": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
+    "aesr_lerp_pairs_act": (I, [P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
     "aesr_probe_halo_conv": (I, [P, P, P, I, I, I, I, I, I, I, I, P]),
     "aesr_probe_umma_rate": (I, [P, I, I, I, I, I, I, I, P]),
     "aesr_probe_sync": (I, [P, I, I, P]),

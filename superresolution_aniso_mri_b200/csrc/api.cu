@@ -262,6 +262,7 @@ int launch_halo(const void* x, const void* w, ConvParams p, cudaStream_t stream)
     else if (plain && p.out_mode == OUT_SAME) AESR_HALO(OUT_SAME)
     else if (plain && p.out_mode == OUT_AVGPOOL2) AESR_HALO(OUT_AVGPOOL2)
     else if (plain && p.out_mode == OUT_SHUFFLE2) AESR_HALO(OUT_SHUFFLE2)
+    else if (plain && p.out_mode == OUT_SAME_F32) AESR_HALO(OUT_SAME_F32)
     else AESR_HALO(-1)
 #undef AESR_HALO
     return check_launch("conv3x3_halo");
@@ -322,7 +323,7 @@ int conv3x3_dispatch(const void* x, const void* w_packed, const float* bias, con
         return fail(AESR_ERR_INVALID, "conv3x3_fwd: Cin=%d unsupported (32, 64, 128, 256, 512)", Cin);
     if (Cout % 32 != 0 || Cout < 32 || Cout > 512) return fail(AESR_ERR_INVALID, "conv3x3_fwd: Cout=%d unsupported", Cout);
     if ((scale == nullptr) != (shift == nullptr)) return fail(AESR_ERR_INVALID, "conv3x3_fwd: scale/shift must come together");
-    if (out_mode < 0 || out_mode > 6) return fail(AESR_ERR_INVALID, "conv3x3_fwd: out_mode=%d", out_mode);
+    if (out_mode < 0 || out_mode > 7) return fail(AESR_ERR_INVALID, "conv3x3_fwd: out_mode=%d", out_mode);
     if (out_mode == AESR_OUT_SAME_MAXPOOL2 && !out2) return fail(AESR_ERR_INVALID, "conv3x3_fwd: maxpool needs out2");
     if (out_mode == AESR_OUT_SHUFFLE2 && Cout % 128 != 0)
         return fail(AESR_ERR_INVALID, "conv3x3_fwd: OUT_SHUFFLE2 needs Cout = 4*C with C a multiple of 32, got %d", Cout);
@@ -335,8 +336,17 @@ int conv3x3_dispatch(const void* x, const void* w_packed, const float* bias, con
 
     ConvParams p{};
     p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
-    p.tiles_x = (W + CONV_TILE_W - 1) / CONV_TILE_W;
-    p.tiles_y = (H + CONV_TILE_H - 1) / CONV_TILE_H;
+    // AvgPool2d(2) floors: the last row / column of an odd-sized map never reaches the output (65x65 -> 32x32), so
+    // tiles only cover the even extent (the halo loads still read the real tensor bounds).  Not when per-channel
+    // statistics of the full map are wanted.
+    int He = H, We = W;
+    if (out_mode == AESR_OUT_AVGPOOL2 && stats == nullptr) {
+        He = (H / 2) * 2;
+        We = (W / 2) * 2;
+        if (He == 0 || We == 0) return AESR_OK;      // empty pooled output
+    }
+    p.tiles_x = (We + CONV_TILE_W - 1) / CONV_TILE_W;
+    p.tiles_y = (He + CONV_TILE_H - 1) / CONV_TILE_H;
     p.fp16 = (dtype == AESR_DT_FP16);
     {
         static const int dbg = getenv("AESR_CONV_DEBUG") ? atoi(getenv("AESR_CONV_DEBUG")) : 0;   // profiling only
@@ -504,6 +514,31 @@ int aesr_lerp_pairs(const float* z, const int* pa, const int* pb, const float* w
     else
         lerp_pairs_kernel<false><<<grid, block, 0, s>>>(z, pa, pb, wa, wb, static_cast<uint16_t*>(out_nhwc), K, C, HW);
     return check_launch("lerp_pairs");
+}
+
+int aesr_lerp_pairs_act(const float* pre, const int* pa, const int* pb, const float* wa, const float* wb,
+                        const float* bias, void* out_nhwc, int P, int K, int C, int HW, float slope, int dtype,
+                        void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!pre || !pa || !pb || !wa || !wb || !out_nhwc || C <= 0 || HW <= 0 || K <= 0)
+        return fail(AESR_ERR_INVALID, "lerp_pairs_act: bad arguments");
+    if (C % 8 != 0) return fail(AESR_ERR_INVALID, "lerp_pairs_act: C=%d must be a multiple of 8", C);
+    if (static_cast<size_t>(HW) * C > (1u << 30)) return fail(AESR_ERR_INVALID, "lerp_pairs_act: slice too large");
+    if ((reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(out_nhwc) | reinterpret_cast<uintptr_t>(bias)) & 15)
+        return fail(AESR_ERR_INVALID, "lerp_pairs_act: tensors must be 16-byte aligned");
+    if (P == 0) return AESR_OK;
+    if (P < 0 || P > 65535) return fail(AESR_ERR_INVALID, "lerp_pairs_act: P=%d out of range (1..65535 per call)", P);
+    const int HWC = HW * C;
+    int gx = ((HWC >> 3) + 255) / 256;
+    if (gx > 32) gx = 32;
+    dim3 grid(gx, P);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == AESR_DT_FP16)
+        lerp_pairs_act_kernel<true><<<grid, 256, 0, s>>>(pre, pa, pb, wa, wb, bias, static_cast<uint16_t*>(out_nhwc), K, C, HWC, slope);
+    else
+        lerp_pairs_act_kernel<false><<<grid, 256, 0, s>>>(pre, pa, pb, wa, wb, bias, static_cast<uint16_t*>(out_nhwc), K, C, HWC, slope);
+    return check_launch("lerp_pairs_act");
 }
 
 int aesr_place_slices(const float* src, float* dst, const int* out_index, int N, int HW, int do_clamp, void* stream) {

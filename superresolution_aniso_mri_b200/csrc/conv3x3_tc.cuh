@@ -45,6 +45,10 @@ enum ConvOut : int {
     // to the thread's 2x2 hi-res block and leaves a 4x4 patch of partial sums per LOW-res pixel (head_gather sums
     // the four patches that overlap an output pixel, adds the bias and applies the sigmoid).
     OUT_SHUFFLE2_HEAD = 6, // out  = fp32 [N,H,W,16]
+    // un-rounded accumulators (+ bias / activation / affine if given): the decoder's first conv applied to the encoder
+    // latents BEFORE the interpolation (conv is linear: conv(a*z1 + b*z2) = a*conv(z1) + b*conv(z2)), lerp_pairs_act
+    // then blends these pre-activations per alpha and applies bias + LeakyReLU.
+    OUT_SAME_F32 = 7,      // out  = NHWC fp32 [N,H,W,Cout]
 };
 enum ConvMul : int { MUL_NONE = 0, MUL_LEAKY_GRAD = 1, MUL_RELU_GRAD = 2 };
 
@@ -314,6 +318,13 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                 o4[1] = pack8(v + 8, fp16);
             }
         }
+        if (out_mode == OUT_SAME_F32) {
+            if (inb) {
+                float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + pix * Cout + cg);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) o4[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+            }
+        }
         if (out_mode == OUT_AVGPOOL2 || out_mode == OUT_SAME_MAXPOOL2) {
             // 2x2 window = lanes {l, l^1, l^8} (x neighbour, y neighbour): tile origins are even.
             const bool is_max = (out_mode == OUT_SAME_MAXPOOL2);
@@ -374,7 +385,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
     }
 }
 
-// Lean epilogue of the inference output stages (OUT_SAME, OUT_AVGPOOL2, OUT_SHUFFLE2; no training extras): 16 accumulator
+// Lean epilogue of the inference output stages (OUT_SAME, OUT_AVGPOOL2, OUT_SHUFFLE2, OUT_SAME_F32; no training extras): 16 accumulator
 // columns per TMEM load, so that 16 values + addresses + the role's loop state stay far below the 96 registers a
 // 576-thread CTA allows (the 32-column generic epilogue spills its loop state, ncu: LDL stalls in every tile).
 template <int MODE>
@@ -394,7 +405,7 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
     size_t pix;
     bool store;
     int Cpix;                                   // channels per output pixel
-    if (MODE == OUT_SAME) {
+    if (MODE == OUT_SAME || MODE == OUT_SAME_F32) {
         Cpix = p.Cout;
         pix = (static_cast<size_t>(t.n) * H + y) * W + x;
         store = inb;
@@ -467,7 +478,13 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
         } else {
             off = pix * Cpix + cg;
         }
-        if (store) {
+        if (MODE == OUT_SAME_F32) {
+            if (store) {
+                float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off);
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) o4[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+            }
+        } else if (store) {
             uint4* o4 = reinterpret_cast<uint4*>(out16 + off);
             o4[0] = pack8(v, fp16);
             o4[1] = pack8(v + 8, fp16);

@@ -378,6 +378,51 @@ __global__ void lerp_pairs_kernel(const float* __restrict__ z, const int* __rest
     }
 }
 
+// Interpolation AFTER the decoder's first conv (volume synthesis, fused pipeline).  dec.0 is linear, so
+//   dec.0(wa*z1 + wb*z2) = wa*dec.0_nobias(z1) + wb*dec.0_nobias(z2) + bias
+// and the conv runs once per low-resolution slice instead of once per synthesized slice (Z vs (Z-1)*A launches of the
+// same work).  pre = un-rounded fp32 NHWC accumulators [*, HW*C] of conv3x3(OUT_SAME_F32, no bias); this kernel forms
+//   out[p*K + k] = LeakyReLU(wa[k] * pre[pa[p]] + wb[k] * pre[pb[p]] + bias[c])   -> NHWC 16-bit
+// with the same three separately rounded lerp operations as lerp_pairs.  One thread = 8 consecutive channels of one
+// pixel: two 32-byte reads per operand, one 16-byte store per alpha.
+// Algorithmic bytes per pair: 2 * 4 * HW*C read + K * 2 * HW*C written.
+template <bool FP16>
+__global__ void __launch_bounds__(256)
+lerp_pairs_act_kernel(const float* __restrict__ pre, const int* __restrict__ pa, const int* __restrict__ pb,
+                      const float* __restrict__ wa, const float* __restrict__ wb, const float* __restrict__ bias,
+                      uint16_t* __restrict__ out, int K, int C, int HWC, float slope) {
+    const int p = blockIdx.y;
+    const float4* a4 = reinterpret_cast<const float4*>(pre + static_cast<size_t>(__ldg(pa + p)) * HWC);
+    const float4* b4 = reinterpret_cast<const float4*>(pre + static_cast<size_t>(__ldg(pb + p)) * HWC);
+    uint4* o4 = reinterpret_cast<uint4*>(out + static_cast<size_t>(p) * K * HWC);
+    const int groups = HWC >> 3;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+        const float4 a0 = __ldg(a4 + 2 * g), a1 = __ldg(a4 + 2 * g + 1);
+        const float4 b0 = __ldg(b4 + 2 * g), b1 = __ldg(b4 + 2 * g + 1);
+        const int c = (g << 3) % C;
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+        if (bias != nullptr) {
+            s0 = __ldg(reinterpret_cast<const float4*>(bias + c));
+            s1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+        }
+        const float va[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float vb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        const float sb[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        for (int k = 0; k < K; ++k) {
+            const float fa = __ldg(wa + k), fb = __ldg(wb + k);
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = __fadd_rn(__fadd_rn(__fmul_rn(fa, va[j]), __fmul_rn(fb, vb[j])), sb[j]);
+                v[j] = fmaxf(t, t * slope);
+            }
+            o4[static_cast<size_t>(k) * groups + g] =
+                make_uint4(pack2_t<FP16>(v[0], v[1]), pack2_t<FP16>(v[2], v[3]), pack2_t<FP16>(v[4], v[5]),
+                           pack2_t<FP16>(v[6], v[7]));
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // kept (original) slices of the HR volume: dst[out_index[n]] = clamp(src[n], 0, 1)   (generate_hr_volumes.py:44,58-67)
 // fp32 images of HW pixels, float4 vectorised when HW % 4 == 0.

@@ -150,6 +150,8 @@ class VanillaACAI(nn.Module):
         # Inference pipelines use the algebraic folds (stem = enc.0 o enc.1, Upsample folded into the next conv, decoder
         # head fused into dec.12's epilogue).  False = one kernel per reference layer (A/B measurements, tests).
         self.fused_inference = os.environ.get("AESR_FUSED", "1") != "0"
+        # Volume synthesis: interpolate BEHIND dec.0 (dec.0 is linear; it then runs once per low-res slice).
+        self.linear_fold = os.environ.get("AESR_LINFOLD", "1") != "0"
 
     # ------------------------------------------------------------------ public API (reference signatures)
     def forward(self, img):
@@ -222,8 +224,9 @@ class VanillaACAI(nn.Module):
         return self._cache.get(("head", id(conv)), [conv.weight, conv.bias], build)
 
     @torch.no_grad()
-    def encode_eval(self, img: torch.Tensor, want_nhwc: bool = False):
-        """[N,1,H,W] fp32 -> z [N,latent,h,w] fp32 (eval-mode BN).  ``want_nhwc`` also returns the bf16 NHWC copy."""
+    def encode_eval(self, img: torch.Tensor, want_nhwc: bool = False, nhwc_only: bool = False):
+        """[N,1,H,W] fp32 -> z [N,latent,h,w] fp32 (eval-mode BN).  ``want_nhwc`` also returns the 16-bit NHWC copy;
+        ``nhwc_only`` returns ONLY the 16-bit NHWC latent (volume synthesis: the fp32 NCHW tensor is never needed)."""
         x = img.detach().float().contiguous()
         enc = self.enc
         fused = self.fused_inference
@@ -242,17 +245,28 @@ class VanillaACAI(nn.Module):
             i += 6
         c1, c2 = enc[i], enc[i + 2]
         a = ops.conv3x3(a, self._packed(c1), c1.bias.detach(), act=ops.ACT_LEAKY)
+        if nhwc_only:
+            return ops.conv3x3(a, self._packed(c2), c2.bias.detach(), act=ops.ACT_NONE)
         return ops.conv3x3(a, self._packed(c2), c2.bias.detach(), act=ops.ACT_NONE, out_mode=ops.OUT_NCHW_F32,
                            want_out2=want_nhwc)
 
     @torch.no_grad()
+    def decode_pre_eval(self, z16: torch.Tensor) -> torch.Tensor:
+        """dec.0 WITHOUT bias / activation on 16-bit NHWC latents -> un-rounded fp32 NHWC pre-activations.  dec.0 is
+        linear, so interpolating these (``ops.lerp_pairs_act``: blend, + bias, LeakyReLU) equals dec.0 + LeakyReLU of
+        the interpolated latent (networks/acai_vanilla.py:87-88 after generate_hr_volumes.py:88) in real arithmetic."""
+        return ops.conv3x3(z16, self._packed(self.dec[0]), None, act=ops.ACT_NONE, out_mode=ops.OUT_SAME_F32)
+
+    @torch.no_grad()
     def decode_nhwc_eval(self, a: torch.Tensor, out: Optional[torch.Tensor] = None,
                          out_image_stride: Optional[int] = None,
-                         out_index: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """decoder on an NHWC bf16 latent batch; images optionally written strided into ``out``."""
+                         out_index: Optional[torch.Tensor] = None, after_first: bool = False) -> torch.Tensor:
+        """decoder on an NHWC 16-bit latent batch; images optionally written strided into ``out``.  ``after_first``:
+        ``a`` is already the output of dec.0 + LeakyReLU (``decode_pre_eval`` + ``ops.lerp_pairs_act``)."""
         dec = self.dec
         if self.fused_inference:
-            return self._decode_nhwc_fused(a, out, out_image_stride, out_index)
+            return self._decode_nhwc_fused(a, out, out_image_stride, out_index, after_first)
+        assert not after_first, "after_first needs the fused inference pipeline"
         i = 0
         for _ in range(self.scales):
             c1, c2, bn = dec[i], dec[i + 2], dec[i + 4]
@@ -266,7 +280,7 @@ class VanillaACAI(nn.Module):
         w9c, b = self._head_w(c2)
         return ops.head(a, w9c, b, out=out, out_image_stride=out_image_stride, sigmoid=True, out_index=out_index)
 
-    def _decode_nhwc_fused(self, a, out, out_image_stride, out_index):
+    def _decode_nhwc_fused(self, a, out, out_image_stride, out_index, after_first=False):
         """Same decoder with every nn.Upsample folded into the conv that follows it (the producer stores the LOW-res
         tensor, the consumer is a low-res conv with 4 phase blocks + depth-to-space) and dec.12 -> dec.14 -> sigmoid as
         one tensor-core kernel + a 20 B/px gather."""
@@ -275,7 +289,8 @@ class VanillaACAI(nn.Module):
         for s in range(self.scales):
             c1, c2, bn = dec[i], dec[i + 2], dec[i + 4]
             if s == 0:
-                a = ops.conv3x3(a, self._packed(c1), c1.bias.detach(), act=ops.ACT_LEAKY)
+                if not after_first:
+                    a = ops.conv3x3(a, self._packed(c1), c1.bias.detach(), act=ops.ACT_LEAKY)
             else:       # input is the previous block's low-res output: Upsample folded into this conv
                 a = ops.conv3x3(a, self._packed_up2(c1), c1.bias.detach(), act=ops.ACT_LEAKY, out_mode=ops.OUT_SHUFFLE2)
             sc, sh = self._bn_affine(bn)

@@ -13,6 +13,7 @@ from . import _lib
 
 ACT_NONE, ACT_LEAKY, ACT_RELU = 0, 1, 2
 OUT_SAME, OUT_AVGPOOL2, OUT_UP2, OUT_NCHW_F32, OUT_SAME_MAXPOOL2, OUT_SHUFFLE2 = 0, 1, 2, 3, 4, 5
+OUT_SAME_F32 = 7      # NHWC fp32, un-rounded accumulators (6 = the fused head, see conv3x3_up2_head)
 MUL_NONE, MUL_LEAKY_GRAD, MUL_RELU_GRAD = 0, 1, 2
 ALGO_AUTO, ALGO_HALO, ALGO_STREAM = 0, 1, 2
 DT_BF16, DT_FP16 = 0, 1
@@ -122,7 +123,8 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     assert w_packed.shape == (9, cout, cin) and w_packed.is_contiguous()
     if out is None:
         out = torch.empty(conv_out_shape(n, h, w, cout, out_mode),
-                          dtype=torch.float32 if out_mode == OUT_NCHW_F32 else x.dtype, device=x.device)
+                          dtype=torch.float32 if out_mode in (OUT_NCHW_F32, OUT_SAME_F32) else x.dtype,
+                          device=x.device)
     if out2 is None and (out_mode == OUT_SAME_MAXPOOL2 or (out_mode == OUT_NCHW_F32 and want_out2)):
         shp = (n, h // 2, w // 2, cout) if out_mode == OUT_SAME_MAXPOOL2 else (n, h, w, cout)
         out2 = torch.empty(shp, dtype=x.dtype, device=x.device)
@@ -271,6 +273,29 @@ def lerp_pairs(z: torch.Tensor, pa: torch.Tensor, pb: torch.Tensor, wa: torch.Te
             _lib.check(lib.aesr_lerp_pairs(z.data_ptr(), pa[done:].data_ptr(), pb[done:].data_ptr(), wa.data_ptr(),
                                            wb.data_ptr(), out[done * k:].data_ptr(), cnt, k, c, h * w, dt_code(dtype),
                                            _stream(z)), "lerp_pairs")
+            done += cnt
+    return out
+
+
+def lerp_pairs_act(pre: torch.Tensor, pa: torch.Tensor, pb: torch.Tensor, wa: torch.Tensor, wb: torch.Tensor,
+                   bias: Optional[torch.Tensor], slope: float = LEAKY_SLOPE, dtype: Optional[torch.dtype] = None
+                   ) -> torch.Tensor:
+    """out[p*K + k] = LeakyReLU(wa[k]*pre[pa[p]] + wb[k]*pre[pb[p]] + bias); pre fp32 NHWC [*,h,w,C] (the decoder's
+    first conv applied to the latents, OUT_SAME_F32) -> NHWC 16-bit [P*K,h,w,C]."""
+    lib = _dev(pre)
+    dtype = dtype or DEFAULT_DTYPE
+    assert pre.dtype == torch.float32 and pre.is_contiguous() and pre.dim() == 4
+    _, h, w, c = pre.shape
+    p, k = pa.numel(), wa.numel()
+    out = torch.empty((p * k, h, w, c), dtype=dtype, device=pre.device)
+    with _timed("lerp"):
+        done = 0
+        while done < p:
+            cnt = min(p - done, 65535)
+            _lib.check(lib.aesr_lerp_pairs_act(pre.data_ptr(), pa[done:].data_ptr(), pb[done:].data_ptr(),
+                                               wa.data_ptr(), wb.data_ptr(), _ptr(bias), out[done * k:].data_ptr(),
+                                               cnt, k, c, h * w, float(slope), dt_code(dtype), _stream(pre)),
+                       "lerp_pairs_act")
             done += cnt
     return out
 

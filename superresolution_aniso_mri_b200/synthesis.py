@@ -47,14 +47,19 @@ def pair_plan(num_slices: int, num_alphas: int, w_hi: np.ndarray, w_lo: np.ndarr
 
 @torch.no_grad()
 def synthesize_volumes(model, volumes: torch.Tensor, alpha_range: Sequence[float], use_original: bool = True,
-                       decode_chunk: int = 128, encode_chunk: int = 256, out: Optional[torch.Tensor] = None
+                       decode_chunk: int = 4096, encode_chunk: int = 2048, out: Optional[torch.Tensor] = None
                        ) -> torch.Tensor:
     """Batched synthesis of V independent volumes.  volumes: [V,Z,H,W] fp32 (device) -> [V,(Z-1)(A+1)+1,H,W] fp32.
 
-    ``decode_chunk`` / ``encode_chunk`` bound the slices per kernel launch so that inter-layer activations
-    (<= 1 MiB bf16 per 128x128 slice and layer) stay resident in the 126 MB L2 between producer and consumer."""
+    ``decode_chunk`` / ``encode_chunk`` bound the slices per kernel launch.  Large chunks win: measured on B200
+    (profiles/README.md, chunk sweep) a launch of the persistent conv kernel carries ~10 us of fixed cost (launch,
+    TMEM allocation, filter-bank load, tail wave), which at 256 slices per launch was 16 % of the step -- more than
+    keeping the inter-layer tensors L2-resident ever bought.  The chunks are additionally capped so that the largest
+    inter-layer tensor of a launch stays below ~4 GiB."""
     assert volumes.dim() == 4 and volumes.is_cuda
     V, Z, H, W = volumes.shape
+    cap = max(1, (4 << 30) // ((H + 2) * (W + 2) * 64))           # stem output: 32 channels x 2 bytes per pixel
+    decode_chunk, encode_chunk = max(1, min(decode_chunk, cap)), max(1, min(encode_chunk, cap))
     A = len(alpha_range)
     dev = volumes.device
     w_hi, w_lo = interp_weights(alpha_range)
@@ -63,29 +68,44 @@ def synthesize_volumes(model, volumes: torch.Tensor, alpha_range: Sequence[float
     if out is None:
         out = torch.empty((V, Zo, H, W), dtype=torch.float32, device=dev)
     flat_in = vol.view(V * Z, 1, H, W)
+    # Interpolation behind dec.0: dec.0 is linear, so it is applied ONCE per encoded slice (un-rounded fp32 output) and
+    # the blend + bias + LeakyReLU happen in lerp_pairs_act -- (Z-1)*A/Z times less dec.0 work, half the lerp bytes, and
+    # the fp32 NCHW latent is never materialised.
+    fold = bool(getattr(model, "fused_inference", False) and getattr(model, "linear_fold", False)
+                and getattr(model, "scales", 0) >= 1)
     # ---- encode every slice once
-    z_parts, rec_parts = [], []
+    z_parts = []
     for s in range(0, V * Z, encode_chunk):
-        z_parts.append(model.encode_eval(flat_in[s:s + encode_chunk]))
+        if fold:
+            z_parts.append(model.decode_pre_eval(model.encode_eval(flat_in[s:s + encode_chunk], nhwc_only=True)))
+        else:
+            z_parts.append(model.encode_eval(flat_in[s:s + encode_chunk]))
     z = z_parts[0] if len(z_parts) == 1 else torch.cat(z_parts, dim=0)
+    bias0 = model.dec[0].bias.detach() if fold else None
+
+    def blend_decode(pa_, pb_, wa_, wb_, oi_):
+        if fold:
+            a = ops.lerp_pairs_act(z, pa_, pb_, wa_, wb_, bias0)
+        else:
+            a = ops.lerp_pairs(z, pa_, pb_, wa_, wb_)
+        model.decode_nhwc_eval(a, out=out, out_image_stride=H * W, out_index=oi_, after_first=fold)
+
     # ---- kept slices: originals (clamped, generate_hr_volumes.py:44,67) or reconstructions
     idx = torch.arange(V * Z, dtype=torch.int32, device=dev)
+    oi = ((idx // Z) * Zo + (idx % Z) * (A + 1)).to(torch.int32)
     if use_original:
-        oi = ((idx // Z) * Zo + (idx % Z) * (A + 1)).to(torch.int32)
         ops.place_slices(flat_in, out, oi, clamp=True)
-    else:
-        neg = torch.full((V * Z,), -1, dtype=torch.int32, device=dev)
-        one = torch.ones(V * Z, dtype=torch.float32, device=dev)
-        oi = ((idx // Z) * Zo + (idx % Z) * (A + 1)).to(torch.int32)
+    else:       # decode(z_i) = the blend with weights (1, 0) of slice i with itself (1*z + 0*z = z exactly)
+        one = torch.ones(1, dtype=torch.float32, device=dev)
+        zero = torch.zeros(1, dtype=torch.float32, device=dev)
         for s in range(0, V * Z, decode_chunk):
             e = min(s + decode_chunk, V * Z)
-            a = ops.lerp_latents(z, idx[s:e], neg[s:e], one[s:e], one[s:e])
-            model.decode_nhwc_eval(a, out=out, out_image_stride=H * W, out_index=oi[s:e].contiguous())
+            blend_decode(idx[s:e], idx[s:e], one, zero, oi[s:e].contiguous())
     if A == 0 or Z < 2:
         return out
     # ---- all (volume, pair, alpha) lerp+decode problems
     #      pair q = v*(Z-1)+i blends z[v*Z+i+1] (weight w_hi[k]) and z[v*Z+i] (w_lo[k]); problem m = q*A + k lands at
-    #      out[v*Zo + i*(A+1) + 1 + k].  The two fp32 latents of a pair are read once for all A alphas.
+    #      out[v*Zo + i*(A+1) + 1 + k].  The two fp32 operands of a pair are read once for all A alphas.
     q = np.arange(V * (Z - 1), dtype=np.int64)
     v_of, i_of = q // (Z - 1), q % (Z - 1)
     pa = torch.from_numpy((v_of * Z + i_of + 1).astype(np.int32)).to(dev, non_blocking=True)
@@ -97,8 +117,7 @@ def synthesize_volumes(model, volumes: torch.Tensor, alpha_range: Sequence[float
     pairs_per_chunk = max(1, decode_chunk // A)
     for s in range(0, V * (Z - 1), pairs_per_chunk):
         e = min(s + pairs_per_chunk, V * (Z - 1))
-        a = ops.lerp_pairs(z, pa[s:e], pb[s:e], wa, wb)
-        model.decode_nhwc_eval(a, out=out, out_image_stride=H * W, out_index=oi[s * A:e * A])
+        blend_decode(pa[s:e], pb[s:e], wa, wb, oi[s * A:e * A])
     return out
 
 
@@ -107,7 +126,7 @@ class HostPipeline:
     [V,(Z-1)(A+1)+1,H,W] back in pinned host memory.  The V volumes are cut into groups; group g+1's host->device copy
     and group g-1's device->host copy run on their own streams while group g computes (double-buffered staging)."""
 
-    def __init__(self, model, V, Z, H, W, alpha_range, groups: int = 4, chunk: int = 256):
+    def __init__(self, model, V, Z, H, W, alpha_range, groups: int = 4, chunk: int = 4096):
         self.model, self.ar, self.chunk = model, list(alpha_range), chunk
         dev = next(model.parameters()).device
         self.dev = dev

@@ -38,6 +38,7 @@ CONV_CASES = [  # cin, cout, n, h, w, act, mode, affine
     (32, 32, 2, 64, 64, 1, 2, True), (32, 32, 2, 128, 128, 1, 0, False), (64, 64, 1, 55, 55, 1, 1, True),
     (128, 256, 1, 16, 16, 2, 0, False), (256, 256, 1, 16, 16, 2, 4, False), (512, 512, 1, 8, 8, 2, 0, False),
     (64, 64, 1, 1, 1, 1, 0, False), (32, 32, 1, 3, 5, 1, 1, False), (64, 64, 149, 32, 32, 1, 0, False),
+    (128, 64, 3, 32, 32, 0, 7, False), (32, 32, 2, 20, 12, 1, 7, True), (64, 64, 2, 65, 33, 1, 1, False),
 ]
 
 
@@ -77,8 +78,9 @@ def test_conv3x3_vs_torch_fp32(dev, case, algo, dtype):
     want = conv_reference(x, wt, b, act, sc, sh, mode if mode != 4 else 0, dtype)
     ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
     tol = 4 * ulp * max(1.0, want.abs().max().item()) + 2e-4 * np.sqrt(cin * 9)
-    if mode == 3:
-        got = res.cpu()
+    if mode == 3 or mode == 7:
+        got = res.cpu() if mode == 3 else res.permute(0, 3, 1, 2).cpu()
+        assert res.dtype == torch.float32
         tol = 2e-4 * np.sqrt(cin * 9)                 # fp32 output: only accumulation-order noise
     elif mode == 4:
         got = res[0].float().permute(0, 3, 1, 2).cpu()
@@ -159,6 +161,58 @@ def test_edge_kernels_e0_head_lerp_place(dev):
     dst = torch.zeros(5, 7, 9, device=dev)
     ops.place_slices(src.to(dev), dst, torch.tensor([4, 0, 2], dtype=torch.int32, device=dev))
     assert torch.equal(dst[[4, 0, 2]].cpu(), src.clamp(0, 1)) and torch.all(dst[[1, 3]] == 0)
+
+
+def test_lerp_pairs_act_vs_torch(dev):
+    """Blend of fp32 NHWC pre-activations + bias + LeakyReLU: the fp32 value is bit-exact with the same torch
+    expression (three-rounding lerp, then bias, then leaky), the output is its 16-bit rounding."""
+    from superresolution_aniso_mri_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    for (n, h, w, c, K, dtype) in ((5, 6, 6, 64, 6, torch.float16), (3, 5, 3, 8, 1, torch.bfloat16),
+                                   (4, 32, 32, 64, 3, torch.float16)):
+        pre = torch.randn(n, h, w, c, generator=g)
+        bias = torch.randn(c, generator=g)
+        ar = O.alpha_range_for(K)
+        hi, lo = O.interp_weights(ar)
+        pa = torch.arange(1, n, dtype=torch.int32)
+        pb = torch.arange(0, n - 1, dtype=torch.int32)
+        got = ops.lerp_pairs_act(pre.to(dev), pa.to(dev), pb.to(dev), torch.from_numpy(hi).to(dev),
+                                 torch.from_numpy(lo).to(dev), bias.to(dev), slope=0.01, dtype=dtype)
+        assert got.shape == ((n - 1) * K, h, w, c) and got.dtype == dtype
+        for p_ in range(n - 1):
+            for k in range(K):
+                t = (torch.tensor(hi[k]) * pre[pa[p_]] + torch.tensor(lo[k]) * pre[pb[p_]]) + bias
+                ref = torch.maximum(t, t * torch.tensor(0.01, dtype=torch.float32)).to(dtype)
+                assert torch.equal(got[p_ * K + k].cpu(), ref)
+    # no bias, slope 1 = plain blend
+    pre = torch.randn(2, 4, 4, 16, generator=g)
+    one = torch.ones(1, device=dev)
+    got = ops.lerp_pairs_act(pre.to(dev), torch.tensor([1], dtype=torch.int32, device=dev),
+                             torch.tensor([1], dtype=torch.int32, device=dev), one, 0 * one, None, slope=1.0)
+    assert torch.equal(got[0].cpu(), pre[1].to(torch.float16))
+
+
+def test_linear_fold_matches_unfolded_synthesis(dev):
+    """Interpolating behind dec.0 (conv is linear) vs interpolating the latents: same volume within the 16-bit
+    activation noise, both inside the calibrated-checkpoint bounds against the oracle; kept slices bit-exact."""
+    from superresolution_aniso_mri_b200 import synthesis
+    for (width, lw, Z, ni) in ((64, 16, 5, 3), (128, 16, 3, 2)):
+        args = O.default_args(width, lw)
+        state = O.calibrated_state(args)
+        model = make_model(args, state, dev)
+        vol = 0.8 * O.smooth_phantom(Z, width, seed=2) + 0.2 * O.synthetic_volume(Z, width, seed=1)
+        ar = O.alpha_range_for(ni)
+        for use_original in (True, False):
+            want = O.create_super_volume(state, args, vol, ar, use_original=use_original)
+            outs = {}
+            for fold in (True, False):
+                model.linear_fold = fold
+                outs[fold] = synthesis.create_super_volume(model, vol, ar, use_original=use_original)["upsampled_image"]
+                d = (outs[fold] - want).abs()
+                assert d.max().item() < 6e-2 and d.mean().item() < 3e-3
+            assert (outs[True] - outs[False]).abs().max().item() < 3e-2
+            if use_original:
+                assert torch.equal(outs[True][::ni + 1], outs[False][::ni + 1])
 
 
 def test_invalid_arguments_raise(dev):
