@@ -216,7 +216,10 @@ def run_ours(a):
     pipe = synthesis.HostPipeline(model, V, Z, SIZE, SIZE, ar, groups=a.groups, chunk=a.chunk)
 
     def step_host():
-        pipe.run(host_in, host_out)
+        # a stream of batches through the public host-buffer API: every step uploads its volumes from pinned host
+        # memory and downloads its HR volumes; the copies of step i overlap the compute of step i+1, and the timed
+        # region ends only after the LAST step's results are in host memory (pipe.wait() below)
+        pipe.run(host_in, host_out, wait=False)
 
     def barrier():
         torch.cuda.synchronize()
@@ -256,12 +259,14 @@ def run_ours(a):
     # ---- e2e: pinned host volumes -> HR volumes in pinned host memory, H2D/D2H inside the timed region
     for _ in range(max(a.warmup, 3)):
         step_host()
+    pipe.wait()
     barrier()
     t0 = time.perf_counter()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record()
     for _ in range(a.steps):
         step_host()
+    pipe.wait()
     e_end.record()
     barrier()
     e2e_ms = torch.tensor([e_start.elapsed_time(e_end)], device=dev, dtype=torch.float64)
@@ -290,17 +295,24 @@ def run_ours(a):
         # (enc.0 + enc.1, a CUDA-core kernel).  The algebraic folds change the EXECUTED MMA work (dec.0 runs once per
         # LR slice behind the interpolation; folded upsample convs execute the same MACs): reported separately.
         alg_fl = 2e9 * (V * Z * (ENC_GMAC - STEM_GMAC) + V * (Z - 1) * NI * DEC_GMAC)
+        # algorithmic bytes of the conv launches of a step (DESIGN.md section 3 table, 16-bit activations): per encoded
+        # slice enc.3 .. enc.15 + dec.0 on the latent, per synthesized slice dec.2 .. dec.12+head
+        KB = 1024.0
+        enc_bytes = (1056.25 + 264.06) + (264.06 + 528.13) + (528.13 + 128) + (128 + 256) + (256 + 256) + (256 + 256)
+        dec_bytes = (128 + 128) + (128 + 256) + (256 + 256) + (256 + 256)
+        alg_bytes = KB * (V * Z * enc_bytes + V * (Z - 1) * NI * dec_bytes)
         ach = alg_fl / (conv_ms * 1e-3) / 1e12
         traffic, traffic_src = None, None
-        tj = os.path.join(ROOT, "profiles", "r01b_conv_full.json")      # ncu --set full capture of the same conv launches
-        if os.path.exists(tj):
-            with open(tj) as f:
+        # ncu --set full capture of the same conv launches (tools/profile_round.sh): the newest committed summary
+        caps = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_conv_full.json"))
+        if caps:
+            with open(os.path.join(ROOT, "profiles", caps[-1])) as f:
                 traffic = json.load(f)["mean_dram_bytes_per_launch"]
-            traffic_src = "profiles/r01b_conv_full.json (dram__bytes_read.sum + dram__bytes_write.sum, mean per conv launch)"
+            traffic_src = "profiles/%s (dram__bytes_read.sum + dram__bytes_write.sum, mean per conv launch)" % caps[-1]
         roof = {"bound": "tensor", "kernel": "conv3x3_halo_kernel (tcgen05, all %d launches of a step)" % n_conv,
                 "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": None,
+                "algorithmic_bytes_per_launch": alg_bytes / max(n_conv, 1),
                 "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" % peaks["source"],
                 "conv_ms_per_step": conv_ms, "all_kernels_ms_per_step": all_ms,
                 "conv_share_of_kernel_time": conv_ms / all_ms if all_ms else None,
@@ -442,7 +454,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--volumes", type=int, default=64, help="volumes per GPU per step")
     ap.add_argument("--chunk", type=int, default=4096, help="max slices per kernel launch")
-    ap.add_argument("--groups", type=int, default=4, help="e2e: volume groups pipelined over copy/compute streams")
+    ap.add_argument("--groups", type=int, default=2, help="e2e: volume groups pipelined over copy/compute streams")
     ap.add_argument("--cpu-sample", type=int, default=4, dest="cpu_sample")
     ap.add_argument("--no-train", action="store_false", dest="train", help="skip the training-step measurement")
     ap.add_argument("--train-steps", type=int, default=30, dest="train_steps")

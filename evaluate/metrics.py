@@ -1,7 +1,8 @@
-"""``evaluate.metrics`` (reference: evaluate/metrics.py:29-45, 111-194): SSIM / PSNR over slice sets, on the device.
-VIF and the LPIPS-as-metric wrapper are "next" rows and not provided."""
+"""``evaluate.metrics`` (reference: evaluate/metrics.py:29-45, 65-108, 111-194, 210-242): SSIM / PSNR / VIF / LPIPS over
+slice sets, on the device."""
 from superresolution_aniso_mri_b200.evaluation import (  # noqa: F401
-    compute_psnr_for_batch, compute_ssim_for_batch, original_slice_ids)
+    compute_lpips_for_batch, compute_psnr_for_batch, compute_ssim_for_batch, compute_vif_for_batch, original_slice_ids,
+    vif_slices)
 
 
 def determine_original_sliceids(reference, downsample_steps, conv_interpol=False):

@@ -66,6 +66,10 @@ extern "C" {
 /* Select device, verify compute capability 10.x, resolve cuTensorMapEncodeTiled.  Idempotent. */
 int aesr_init(int device);
 const char* aesr_last_error(void);
+/* Profiling / tuning knobs of the conv kernel (no reference counterpart; initial values come from the environment):
+ * key 0 = stage-isolation mask AESR_CONV_DEBUG, 1 = forced M-tiles per super-tile, 2 = forced TMEM buffers,
+ * 3 = activation-ring stage cap.  value 0 = automatic. */
+int aesr_set_tuning(int key, int value);
 int aesr_sm_count(void);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 int64_t aesr_launch_count(void);
@@ -96,11 +100,14 @@ int aesr_pack_conv3x3_weight_up2fold(const float* w, void* packed, int Cout, int
  * upsample, w_folded the [9][128][Cin] bank of aesr_pack_conv3x3_weight_up2fold, head_w9c_host fp32 [9][32] the head
  * filter in HOST memory (the one host pointer of this ABI: it is passed to the kernel by value so that the epilogue reads
  * it from the constant bank; copied before the call returns).
- * The 32-channel hi-res activation stays in registers; per low-res pixel the kernel writes the 4x4 patch (origin
+ * head_w16 (device, may be NULL) = the same filter as 16-bit [16 taps (rows 9..15 zero)][32 channels]: when given, the
+ * head conv itself runs on the tensor cores (activations written back to tensor memory as a 16-bit A operand, one
+ * 128x16x32 GEMM per phase); when NULL it runs on the CUDA cores in fp32 from head_w9c_host.
+ * The 32-channel hi-res activation never leaves the SM; per low-res pixel the kernel writes the 4x4 patch (origin
  * (2y-1, 2x-1)) of head-conv partial sums of its 2x2 hi-res block: partial fp32 [N,H,W,16]. */
 int aesr_conv3x3_up2_head_fwd(const void* x, const void* w_folded, const float* bias, const float* head_w9c_host,
-                              float* partial, int N, int H, int W, int Cin, int act, float slope, int dtype, int algo,
-                              void* stream);
+                              const void* head_w16, float* partial, int N, int H, int W, int Cin, int act, float slope,
+                              int dtype, int algo, void* stream);
 
 /* Decoder tail, second half: out(Y,X) = sigmoid(bias + the (up to) four overlapping patch entries), clamp(0,1)
  * (networks/acai_vanilla.py:98, generate_hr_volumes.py:67).  partial fp32 [N,h,w,16]; image n ([2h,2w] fp32) is written at
@@ -225,6 +232,18 @@ int aesr_lpips_head(const void* o0, const void* o1, const float* lin, float* val
 int aesr_ssim_psnr(const float* a, const float* b, int Z, int H, int W, int win, double data_range, double* ssim_sum,
                    double* sqerr_sum, unsigned int* min_key, void* stream);
 
+/* Pixel-domain multi-scale VIF of Z slice pairs exactly as evaluate/vifvec.py:7-63 computes it when called with uint8
+ * slices (evaluate/metrics.py:65-108): four scales, scipy.ndimage.gaussian_filter semantics on uint8 planes (float64
+ * accumulation in scipy's order, truncation to uint8 after every 1-D pass, 'reflect' boundary), uint8 products and
+ * variance differences modulo 256.  ref_u8 / dist_u8: uint8 [Z,H,W] (aesr_vif_quantize_u8 = np.uint8(np.clip(x*255,0,255))
+ * of fp32 images); weights (device): the four gaussian kernels back to back, radii_host[4] their radii, both formed on
+ * the host like scipy's _gaussian_kernel1d; num_den (device) [Z][2] = (numerator, denominator), VIF = num/den (nan if 0). */
+size_t aesr_vif_workspace_bytes(int Z, int H, int W);
+int aesr_vif_quantize_u8(const float* x, void* out_u8, size_t n, void* stream);
+int aesr_vif_mscale(const void* ref_u8, const void* dist_u8, int Z, int H, int W, const double* weights,
+                    const int* radii_host, double sigma_nsq, void* workspace, size_t workspace_bytes, double* num_den,
+                    void* stream);
+
 /* np.percentile(x, (q_lo, q_hi)) ('linear', float64) by exact 3-pass radix select, then
  * out = clip((x - p_lo) / (p_hi - p_lo), 0, 1) in float64 rounded once to fp32 (generate_hr_volumes.py:130-133,
  * datasets/common.py:408-417).  out may be NULL (percentiles only -> lo_hi_out[2], device doubles, may be NULL). */
@@ -243,11 +262,12 @@ int aesr_pad_crop_gather(const float* in, float* out, const int* top, const int*
 int aesr_probe_halo_conv(const void* x, const void* w_packed, float* out, int N, int H, int W, int x0, int y0, int n,
                          int pitch, int variant, void* stream);
 
-/* Diagnostic: cycles for `iters` back-to-back tcgen05.mma (M=128, N, K=16) with the A descriptor's start shifted by
- * `shift_rows` rows, 8-row-group stride `pitch_rows`, advancing `a_advance_rows` rows between MMAs, rotating over `nacc`
- * TMEM accumulators (tools/umma_rate.py). */
+/* Diagnostic: `iters` back-to-back tcgen05.mma (M=128, N, K=16) per CTA on `grid` CTAs at once, A descriptor start shifted
+ * by `shift_rows` rows, 8-row-group stride `pitch_rows`, advancing `a_advance_rows` rows between MMAs, rotating over `nacc`
+ * TMEM accumulators; operands all-zero or (fill_random) pseudo-random fp16.  cycles[2*b] = SM cycles (clock64),
+ * cycles[2*b+1] = wall-clock ns (globaltimer) of CTA b (tools/umma_rate.py). */
 int aesr_probe_umma_rate(long long* cycles, int N, int kc, int pitch_rows, int shift_rows, int iters,
-                         int a_advance_rows, int nacc, void* stream);
+                         int a_advance_rows, int nacc, int grid, int fill_random, void* stream);
 
 /* Diagnostic: mbarrier round-trip latency between two warps (mode bit 0: signal with tcgen05.commit, bit 1: poll with
  * test_wait instead of try_wait, bit 2: three waiting warps).  cycles[0] = total cycles for `iters` round trips. */

@@ -539,6 +539,125 @@ def compute_psnr_for_batch(images: np.ndarray, recons: np.ndarray, downsample_st
 
 
 # ----------------------------------------------------------------------------------------------
+# VIF (pixel-domain, multi-scale) as the reference computes it: evaluate/vifvec.py:7-63 called with UINT8 images
+# (evaluate/metrics.py:72-73,99).  The arithmetic below the reference is scipy.ndimage.gaussian_filter (scipy is
+# present here, so the restatement is pinned bit for bit by oracle/make_golden.py::gold_vif against the reference's
+# own function).  Quirks that shape the numbers and are reproduced on purpose:
+#   * gaussian_filter on a uint8 array returns uint8, and so does every 1-D pass in between: each pass accumulates in
+#     float64 (centre tap first, then symmetric pairs from the farthest tap inwards, ni_filters.c NI_Correlate1D) and is
+#     truncated to uint8;
+#   * `ref * ref`, `mu1 * mu1` and the variance subtractions are uint8 arithmetic and wrap modulo 256.
+# ----------------------------------------------------------------------------------------------
+VIF_SIGMA_NSQ = 2.0
+VIF_EPS = 1e-10
+
+
+def gaussian_kernel1d(sd: float):
+    """scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius) with radius = int(4 * sd + 0.5) (truncate = 4)."""
+    lw = int(4.0 * float(sd) + 0.5)
+    x = np.arange(-lw, lw + 1)
+    phi = np.exp(-0.5 / (sd * sd) * x ** 2)
+    return phi / phi.sum(), lw
+
+
+def _reflect_index(i: np.ndarray, n: int) -> np.ndarray:
+    """scipy 'reflect' (half-sample symmetric: d c b a | a b c d | d c b a), any overhang."""
+    i = np.mod(i, 2 * n)
+    return np.where(i < n, i, 2 * n - 1 - i)
+
+
+def gaussian_filter1d_u8(a: np.ndarray, sd: float, axis: int) -> np.ndarray:
+    """One pass of scipy.ndimage.gaussian_filter on a uint8 array: float64 accumulation in scipy's order, C cast to uint8."""
+    w, lw = gaussian_kernel1d(sd)
+    a = np.moveaxis(a, axis, -1)
+    n = a.shape[-1]
+    idx = np.arange(n)
+    x = a.astype(np.float64)
+    tmp = x[..., idx] * w[lw]
+    for jj in range(-lw, 0):
+        left, right = x[..., _reflect_index(idx + jj, n)], x[..., _reflect_index(idx - jj, n)]
+        tmp = tmp + (left + right) * w[jj + lw]
+    return np.moveaxis(tmp.astype(np.uint8), -1, axis)       # values are in [0, 255]: the cast truncates
+
+
+def gaussian_filter_u8(a: np.ndarray, sd: float) -> np.ndarray:
+    """scipy.ndimage.gaussian_filter(a, sd) for a 2-D uint8 array: axis 0 then axis 1, uint8 in between."""
+    return gaussian_filter1d_u8(gaussian_filter1d_u8(a, sd, 0), sd, 1)
+
+
+def vifp_mscale_u8(ref: np.ndarray, dist: np.ndarray, sigma_nsq: float = VIF_SIGMA_NSQ) -> float:
+    """evaluate/vifvec.py:7-63 for 2-D uint8 inputs (do_rescale=False)."""
+    assert ref.dtype == np.uint8 and dist.dtype == np.uint8
+    eps = VIF_EPS
+    num, den = 0.0, 0.0
+    for scale in range(1, 5):
+        N = 2 ** (4 - scale + 1) + 1
+        sd = N / 5.0
+        if scale > 1:
+            ref = gaussian_filter_u8(ref, sd)[::2, ::2]
+            dist = gaussian_filter_u8(dist, sd)[::2, ::2]
+        mu1, mu2 = gaussian_filter_u8(ref, sd), gaussian_filter_u8(dist, sd)
+        mu1_sq, mu2_sq, mu1_mu2 = mu1 * mu1, mu2 * mu2, mu1 * mu2                      # uint8, modulo 256
+        sigma1_sq = gaussian_filter_u8(ref * ref, sd) - mu1_sq                        # uint8, modulo 256
+        sigma2_sq = gaussian_filter_u8(dist * dist, sd) - mu2_sq
+        sigma12 = gaussian_filter_u8(ref * dist, sd) - mu1_mu2
+        g = sigma12 / (sigma1_sq + eps)
+        sv_sq = sigma2_sq - g * sigma12
+        m1 = sigma1_sq < eps
+        g[m1] = 0
+        sv_sq[m1] = sigma2_sq[m1]
+        m2 = sigma2_sq < eps
+        g[m2] = 0
+        sv_sq[m2] = 0
+        sv_sq[g < 0] = sigma2_sq[g < 0]
+        g[g < 0] = 0
+        sv_sq[sv_sq <= eps] = eps
+        s1 = sigma1_sq.astype(np.float64)
+        num += np.sum(np.log10(1 + g * g * s1 / (sv_sq + sigma_nsq)))
+        den += np.sum(np.log10(1 + s1 / sigma_nsq))
+    return float(num / den) if den != 0 else float("nan")
+
+
+def quantize_u8(x: np.ndarray) -> np.ndarray:
+    """evaluate/metrics.py:72-73: np.uint8(np.clip(x * 255., 0, 255)) on float32 images (product in float32)."""
+    return np.uint8(np.clip(x.astype(np.float32) * 255., 0, 255))
+
+
+def compute_vif_for_batch(images: np.ndarray, recons: np.ndarray, downsample_steps: Optional[int] = None) -> float:
+    """evaluate/metrics.py:65-108 (eval_axis=0, normalize=False): mean VIF over non-original slices, nan/inf dropped."""
+    a, b = quantize_u8(images), quantize_u8(recons)
+    skip = set(determine_original_sliceids(a.shape[0], downsample_steps).tolist()) if downsample_steps else set()
+    res = []
+    for z in range(a.shape[0]):
+        if z in skip:
+            continue
+        with np.errstate(divide="ignore", invalid="ignore"):
+            v = vifp_mscale_u8(a[z], b[z])
+        if not np.isnan(v) and not np.isinf(v):
+            res.append(v)
+    return float(np.mean(np.array(res)))
+
+
+def determine_last_slice(orig_num_slices: int, downsample_steps: int) -> int:
+    """evaluate/common.py:36-39."""
+    return orig_num_slices - 1 - ((orig_num_slices - 1) % downsample_steps)
+
+
+def compute_metrics(images_ref: np.ndarray, new_images: np.ndarray, downsample_steps: int) -> Dict[str, float]:
+    """evaluate/create_HR_images.py:121-178 for one volume (eval_axis=0, normalize=False, no LPIPS): metrics over all
+    slices up to the last synthesised pair, over the synthesised slices only and over the reconstructed ones only."""
+    last = determine_last_slice(images_ref.shape[0], downsample_steps) + 1
+    r_mask, s_mask = synth_slice_mask(images_ref.shape[0], downsample_steps)
+    out = {}
+    for tag, sel in (("", slice(None)), ("_synth", s_mask), ("_recon", r_mask)):
+        a, b = images_ref[:last][sel], new_images[:last][sel]
+        out["ssim" + tag] = compute_ssim_for_batch(a, b)
+        out["psnr" + tag] = compute_psnr_for_batch(a, b)
+        out["vif" + tag] = compute_vif_for_batch(a, b)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # synthetic inputs shared by tests / bench / golden generation (SURVEY.md section 8(d), config 1)
 # ----------------------------------------------------------------------------------------------
 def synthetic_volume(num_slices: int, size: int, seed: int = 1) -> torch.Tensor:

@@ -276,12 +276,65 @@ def gold_transforms():
     _save("host_logic.npz", **out)
 
 
+def gold_vif():
+    """VIF: the oracle restatement must equal the reference's evaluate/vifvec.py::vifp_mscale (scipy.ndimage underneath)
+    on uint8 slices bit for bit in every uint8 plane, and to float64 rounding in the final ratio; also pins
+    evaluate/metrics.py::compute_vif_for_batch and evaluate/create_HR_images.py::compute_metrics' slice selection."""
+    import scipy.ndimage
+    from evaluate.vifvec import vifp_mscale
+    from evaluate import metrics as M
+    rs = np.random.RandomState(11)
+    out = {}
+    # (i) every intermediate uint8 plane of the gaussian filter, all four sigmas, odd sizes, flat regions included
+    for k, (h, w) in enumerate(((37, 53), (128, 128), (16, 9))):
+        a = rs.randint(0, 256, size=(h, w)).astype(np.uint8)
+        a[: h // 3, : w // 2] = 100                     # flat patch: sum(w) * 100 sits next to an integer boundary
+        for sd in (3.4, 1.8, 1.0, 0.6):
+            want = scipy.ndimage.gaussian_filter(a, sd)
+            got = O.gaussian_filter_u8(a, sd)
+            assert want.dtype == np.uint8 and np.array_equal(want, got), (h, w, sd)
+    # (ii) the metric itself on phantom-like slices and their degraded versions
+    vol = O.smooth_phantom(6, 128, seed=2)[:, 0].numpy()
+    noise = rs.normal(0, 0.05, vol.shape).astype(np.float32)
+    blurred = scipy.ndimage.gaussian_filter(vol, (0, 1.5, 1.5)).astype(np.float32)
+    cases = {"noisy": np.clip(vol + noise, 0, 1).astype(np.float32), "blurred": blurred, "same": vol.copy(),
+             "black": np.zeros_like(vol)}
+    for name, dist in cases.items():
+        ref_u8, dist_u8 = O.quantize_u8(vol), O.quantize_u8(dist)
+        vals = []
+        for z in range(vol.shape[0]):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                r = vifp_mscale(ref_u8[z], dist_u8[z])
+                m = O.vifp_mscale_u8(ref_u8[z], dist_u8[z])
+            assert (np.isnan(r) and np.isnan(m)) or abs(r - m) <= 1e-12 * max(1.0, abs(r)), (name, z, r, m)
+            vals.append(r)
+        out["vif_" + name] = np.array(vals, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for ds in (None, 2, 3):
+            r = M.compute_vif_for_batch(vol, cases["noisy"], downsample_steps=ds)
+            m = O.compute_vif_for_batch(vol, cases["noisy"], downsample_steps=ds)
+            assert abs(r - m) <= 1e-12, (ds, r, m)
+            out["vif_batch_ds%s" % ds] = np.array(r)
+    # 220 x 220 (OASIS eval size), odd size, rectangular
+    big = rs.rand(2, 220, 220).astype(np.float32)
+    big2 = np.clip(big + rs.normal(0, 0.1, big.shape), 0, 1).astype(np.float32)
+    out["vif_220"] = np.array([vifp_mscale(O.quantize_u8(big)[z], O.quantize_u8(big2)[z]) for z in range(2)])
+    rect = rs.rand(2, 45, 77).astype(np.float32)
+    rect2 = np.clip(rect * 0.8 + 0.1, 0, 1).astype(np.float32)
+    out["vif_rect"] = np.array([vifp_mscale(O.quantize_u8(rect)[z], O.quantize_u8(rect2)[z]) for z in range(2)])
+    for z in range(2):
+        assert abs(out["vif_220"][z] - O.vifp_mscale_u8(O.quantize_u8(big)[z], O.quantize_u8(big2)[z])) < 1e-12
+        assert abs(out["vif_rect"][z] - O.vifp_mscale_u8(O.quantize_u8(rect)[z], O.quantize_u8(rect2)[z])) < 1e-12
+    out["seed"] = np.array(11)
+    _save("vif_pins.npz", **out)
+
+
 def _sig(cls):
     return True
 
 
 ALL = {"init": gold_init, "lpips": gold_lpips_lin, "infer": gold_infer, "train_small": gold_train_small,
-       "transforms": gold_transforms, "train_acdc": gold_train_acdc}
+       "transforms": gold_transforms, "vif": gold_vif, "train_acdc": gold_train_acdc}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

@@ -20,11 +20,12 @@ _SIGNATURES = {
     "aesr_init": (I, [I]),
     "aesr_last_error": (c_char_p, []),
     "aesr_sm_count": (I, []),
+    "aesr_set_tuning": (I, [I, I]),
     "aesr_launch_count": (c_int64, []),
     "aesr_pack_conv3x3_weight": (I, [P, P, I, I, I, I, P]),
     "aesr_conv3x3_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, F, I, I, I, I, P]),
     "aesr_pack_conv3x3_weight_up2fold": (I, [P, P, I, I, I, P]),
-    "aesr_conv3x3_up2_head_fwd": (I, [P, P, P, P, P, I, I, I, I, I, F, I, I, P]),
+    "aesr_conv3x3_up2_head_fwd": (I, [P, P, P, P, P, P, I, I, I, I, I, F, I, I, P]),
     "aesr_head_gather": (I, [P, P, P, P, I, I, I, c_size_t, I, P]),
     "aesr_stem_fold": (I, [P, P, P, P, P, I, P]),
     "aesr_stem_fwd": (I, [P, P, P, I, I, I, I, F, I, P]),
@@ -35,7 +36,7 @@ _SIGNATURES = {
     "aesr_lerp_pairs": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "aesr_lerp_pairs_act": (I, [P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
     "aesr_probe_halo_conv": (I, [P, P, P, I, I, I, I, I, I, I, I, P]),
-    "aesr_probe_umma_rate": (I, [P, I, I, I, I, I, I, I, P]),
+    "aesr_probe_umma_rate": (I, [P, I, I, I, I, I, I, I, I, I, P]),
     "aesr_probe_sync": (I, [P, I, I, P]),
     # training step
     "aesr_bn_finalize": (I, [P, F, P, P, P, P, F, F, P, P, P, P, I, P]),
@@ -53,6 +54,9 @@ _SIGNATURES = {
     "aesr_lpips_head": (I, [P, P, P, P, P, P, I, I, I, I, P]),
     # evaluation / data path
     "aesr_ssim_psnr": (I, [P, P, I, I, I, I, ctypes.c_double, P, P, P, P]),
+    "aesr_vif_workspace_bytes": (c_size_t, [I, I, I]),
+    "aesr_vif_quantize_u8": (I, [P, P, c_size_t, P]),
+    "aesr_vif_mscale": (I, [P, P, I, I, I, P, P, ctypes.c_double, P, c_size_t, P, P]),
     "aesr_percentile_workspace_bytes": (c_size_t, []),
     "aesr_percentile_normalize": (I, [P, P, c_size_t, ctypes.c_double, ctypes.c_double, P, c_size_t, P, P]),
     "aesr_pad_crop_gather": (I, [P, P, P, P, I, I, I, I, I, I, P]),

@@ -13,6 +13,7 @@
 #include "lpips_kernels.cuh"
 #include "probe.cuh"
 #include "train_kernels.cuh"
+#include "vif_kernels.cuh"
 #include "wgrad_tc.cuh"
 
 using namespace aesr;
@@ -202,52 +203,81 @@ int halo_pick_bn(int Cin, int Cout) {
     return 0;
 }
 
-// M-tiles per super-tile: the largest of {4, 2, 1} that (a) is not taller than the image needs, (b) leaves room for two
-// TMEM buffers of T accumulators, (c) still fits >= 3 activation stages next to the resident filter bank (2 for T = 1).
+// Profiling / tuning knobs (aesr_set_tuning; initial values from the environment): 0 = AESR_CONV_DEBUG stage mask,
+// 1 = AESR_CONV_T forced M-tiles per super-tile, 2 = AESR_CONV_NBUF forced TMEM buffers, 3 = AESR_CONV_STAGES cap.
+int g_tune[4] = {-1, -1, -1, -1};
+int tune(int key) {
+    static const char* names[4] = {"AESR_CONV_DEBUG", "AESR_CONV_T", "AESR_CONV_NBUF", "AESR_CONV_STAGES"};
+    if (g_tune[key] < 0) g_tune[key] = getenv(names[key]) ? atoi(getenv(names[key])) : 0;
+    return g_tune[key];
+}
+
+// Super-tile shape: T M-tiles per pipeline step and nbuf TMEM buffers of T accumulators (nbuf * T * BN <= 512 columns).
+// Four buffers whenever the accumulators allow it (T * BN <= 128: the issuer then runs three super-tiles ahead of the
+// epilogue), T as large as that allows; the activation ring must still hold >= 3 stages next to the resident filter
+// bank (2 * kchunks for multi-chunk layers, 2 for T = 1).
 template <int KC>
-void halo_pick_T(int BN, int Cin, int tiles_y, int* T_out, int* stages_out) {
+void halo_pick_T(int BN, int Cin, int tiles_y, int extra, int* T_out, int* stages_out, int* nbuf_out) {
     using S = HaloSmem<KC>;
     const int kchunks = Cin / KC;
-    const int forced = getenv("AESR_CONV_T") ? atoi(getenv("AESR_CONV_T")) : 0;     // profiling only
-    for (int T = 4; T >= 1; T >>= 1) {
-        if (forced && T != forced && T != 1) continue;
-        if (T > 1 && tiles_y <= T / 2) continue;
-        if (2 * T * BN > 512) continue;
-        int stages = CONV_MAX_STAGES;
-        while (stages > 1 && S::total_bytes(BN, Cin, T, stages) > g_max_smem_optin) --stages;
-        const int need = (T == 1) ? 2 : (kchunks > 1 ? 2 * kchunks : 3);
-        if (S::total_bytes(BN, Cin, T, stages) <= g_max_smem_optin && (stages >= need || T == 1)) {
-            *T_out = T;
-            *stages_out = stages;
-            return;
+    const int forced = tune(1), forced_nbuf = tune(2), stage_cap = tune(3);
+    for (int pass = 0; pass < 2; ++pass) {          // pass 0: four buffers; pass 1: whatever fits
+        for (int T = 4; T >= 1; T >>= 1) {
+            if (forced && T != forced && T != 1) continue;
+            if (T > 1 && tiles_y <= T / 2) continue;
+            int nbuf = 512 / (T * BN);
+            if (nbuf > 4) nbuf = 4;
+            if (forced_nbuf >= 2 && forced_nbuf <= nbuf) nbuf = forced_nbuf;
+            if (nbuf == 3) nbuf = 2;                       // power of two: buffer <-> epilogue-set mapping
+            if (nbuf < 2) continue;
+            if (pass == 0 && nbuf < 4 && !forced && !forced_nbuf && T > 1) continue;
+            int stages = CONV_MAX_STAGES;
+            if (stage_cap >= 2 && stage_cap < stages) stages = stage_cap;
+            while (stages > 1 && S::total_bytes(BN, Cin, T, stages) + extra > g_max_smem_optin) --stages;
+            const int need = (T == 1) ? 2 : (kchunks > 1 ? 2 * kchunks : 3);
+            if (S::total_bytes(BN, Cin, T, stages) + extra <= g_max_smem_optin && (stages >= need || T == 1)) {
+                *T_out = T;
+                *stages_out = stages;
+                *nbuf_out = nbuf;
+                return;
+            }
         }
     }
     *T_out = 1;
     *stages_out = 2;
+    *nbuf_out = (512 / BN) >= 4 ? 4 : 2;
 }
 
 template <int KC>
-int launch_halo(const void* x, const void* w, ConvParams p, cudaStream_t stream) {
+int launch_halo(const void* x, const void* w, const void* head_w16, ConvParams p, cudaStream_t stream) {
     using S = HaloSmem<KC>;
     p.BN = halo_pick_bn<KC>(p.Cin, p.Cout);
     if (p.BN == 0) return fail(AESR_ERR_INVALID, "conv3x3_fwd: filter bank %dx%d does not fit the halo kernel", p.Cout, p.Cin);
     p.n_blocks = p.Cout / p.BN;
-    int T = 1, stages = 2;
-    halo_pick_T<KC>(p.BN, p.Cin, p.tiles_y, &T, &stages);
+    const bool head_tc = p.out_mode == OUT_SHUFFLE2_HEAD && head_w16 != nullptr;
+    p.head_smem = head_tc ? HEAD_SMEM_BYTES : 0;
+    int T = 1, stages = 2, nbuf = 2;
+    halo_pick_T<KC>(p.BN, p.Cin, p.tiles_y, p.head_smem, &T, &stages, &nbuf);
     p.T = T;
+    p.nbuf = nbuf;
     p.stiles_y = (p.tiles_y + T - 1) / T;
     p.num_stages = stages;
     const int st_total = p.N * p.tiles_x * p.stiles_y;
     p.num_tiles = st_total * p.n_blocks;
-    CUtensorMap tx, tw;
+    CUtensorMap tx, tw, th;
     int rc = make_act_tmap(&tx, x, p.N, p.H, p.W, p.Cin, KC, HALO_W, CONV_TILE_H * T + 2);
     if (rc != AESR_OK) return rc;
     rc = make_wgt_tmap(&tw, w, 9 * p.Cout, p.Cin, KC, p.BN);
     if (rc != AESR_OK) return rc;
+    th = tw;
+    if (head_tc) {      // [16 taps (9 used)][32 channels] 16-bit, one SW64 box
+        rc = make_wgt_tmap(&th, head_w16, 16, 32, 32, 16);
+        if (rc != AESR_OK) return rc;
+    }
     int per_nb = g_sm_count / p.n_blocks;
     if (per_nb < 1) per_nb = 1;
     if (per_nb > st_total) per_nb = st_total;
-    const int smem = S::total_bytes(p.BN, p.Cin, T, stages);
+    const int smem = S::total_bytes(p.BN, p.Cin, T, stages) + p.head_smem;
     const int grid = per_nb * p.n_blocks;
     // inference instantiations (output stage compiled in, no training extras) vs the fully dynamic one
     const bool plain = p.mul_mode == MUL_NONE && p.stats == nullptr && p.out2 == nullptr;
@@ -256,9 +286,10 @@ int launch_halo(const void* x, const void* w, ConvParams p, cudaStream_t stream)
         static int configured = 0;                                                                   \
         rc = set_max_smem(conv3x3_halo_kernel<KC, MODE>, &configured);                               \
         if (rc != AESR_OK) return rc;                                                                \
-        conv3x3_halo_kernel<KC, MODE><<<grid, CONV_THREADS, smem, stream>>>(tx, tw, p);              \
+        conv3x3_halo_kernel<KC, MODE><<<grid, CONV_THREADS, smem, stream>>>(tx, tw, th, p);          \
     }
-    if (p.out_mode == OUT_SHUFFLE2_HEAD) AESR_HALO(OUT_SHUFFLE2_HEAD)
+    if (head_tc) AESR_HALO(OUT_SHUFFLE2_HEAD_TC)
+    else if (p.out_mode == OUT_SHUFFLE2_HEAD) AESR_HALO(OUT_SHUFFLE2_HEAD)
     else if (plain && p.out_mode == OUT_SAME) AESR_HALO(OUT_SAME)
     else if (plain && p.out_mode == OUT_AVGPOOL2) AESR_HALO(OUT_AVGPOOL2)
     else if (plain && p.out_mode == OUT_SHUFFLE2) AESR_HALO(OUT_SHUFFLE2)
@@ -281,6 +312,12 @@ int aesr_init(int device) {
 }
 
 const char* aesr_last_error(void) { return g_err; }
+
+int aesr_set_tuning(int key, int value) {
+    if (key < 0 || key > 3 || value < 0) return fail(AESR_ERR_INVALID, "set_tuning: key %d value %d", key, value);
+    g_tune[key] = value;
+    return AESR_OK;
+}
 int aesr_sm_count(void) { return g_sm_count; }
 int64_t aesr_launch_count(void) { return g_launches.load(); }
 
@@ -312,7 +349,8 @@ int aesr_pack_conv3x3_weight_up2fold(const float* w, void* packed, int Cout, int
 namespace {
 // shared by the conv entry points: validate, fill ConvParams, pick the kernel
 int conv3x3_dispatch(const void* x, const void* w_packed, const float* bias, const float* scale, const float* shift,
-                     void* out, void* out2, const void* mul_src, float* stats, const float* head_w, int N, int H, int W,
+                     void* out, void* out2, const void* mul_src, float* stats, const float* head_w, const void* head_w16,
+                     int N, int H, int W,
                      int Cin, int Cout, int act, float slope, int out_mode, int mul_mode, int dtype, int algo,
                      void* stream) {
     int rc = ensure_init();
@@ -348,10 +386,7 @@ int conv3x3_dispatch(const void* x, const void* w_packed, const float* bias, con
     p.tiles_x = (We + CONV_TILE_W - 1) / CONV_TILE_W;
     p.tiles_y = (He + CONV_TILE_H - 1) / CONV_TILE_H;
     p.fp16 = (dtype == AESR_DT_FP16);
-    {
-        static const int dbg = getenv("AESR_CONV_DEBUG") ? atoi(getenv("AESR_CONV_DEBUG")) : 0;   // profiling only
-        p.debug = dbg;
-    }
+    p.debug = tune(0);                                          // profiling only
     p.bias = bias; p.scale = scale; p.shift = shift; p.slope = slope; p.act = act; p.out_mode = out_mode;
     p.out = out; p.out2 = out2; p.mul_src = static_cast<const uint16_t*>(mul_src); p.mul_mode = mul_mode;
     p.stats = stats;
@@ -369,7 +404,7 @@ int conv3x3_dispatch(const void* x, const void* w_packed, const float* bias, con
     }
     if (out_mode == OUT_SHUFFLE2_HEAD && !halo)
         return fail(AESR_ERR_INVALID, "conv3x3_up2_head_fwd: Cin=%d: the 128-row folded bank must fit the resident-filter kernel", Cin);
-    if (halo) return KC == 64 ? launch_halo<64>(x, w_packed, p, s) : launch_halo<32>(x, w_packed, p, s);
+    if (halo) return KC == 64 ? launch_halo<64>(x, w_packed, head_w16, p, s) : launch_halo<32>(x, w_packed, head_w16, p, s);
     return KC == 64 ? launch_stream<64>(x, w_packed, p, s) : launch_stream<32>(x, w_packed, p, s);
 }
 }  // namespace
@@ -380,15 +415,17 @@ int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, con
                      void* out, void* out2, const void* mul_src, float* stats, int N, int H, int W, int Cin, int Cout,
                      int act, float slope, int out_mode, int mul_mode, int dtype, int algo, void* stream) {
     if (out_mode == OUT_SHUFFLE2_HEAD) return fail(AESR_ERR_INVALID, "conv3x3_fwd: use aesr_conv3x3_up2_head_fwd");
-    return conv3x3_dispatch(x, w_packed, bias, scale, shift, out, out2, mul_src, stats, nullptr, N, H, W, Cin, Cout, act,
-                            slope, out_mode, mul_mode, dtype, algo, stream);
+    return conv3x3_dispatch(x, w_packed, bias, scale, shift, out, out2, mul_src, stats, nullptr, nullptr, N, H, W, Cin, Cout,
+                            act, slope, out_mode, mul_mode, dtype, algo, stream);
 }
 
 int aesr_conv3x3_up2_head_fwd(const void* x, const void* w_folded, const float* bias, const float* head_w9c_host,
-                              float* partial, int N, int H, int W, int Cin, int act, float slope, int dtype, int algo,
-                              void* stream) {
-    return conv3x3_dispatch(x, w_folded, bias, nullptr, nullptr, partial, nullptr, nullptr, nullptr, head_w9c_host, N, H, W,
-                            Cin, 128, act, slope, OUT_SHUFFLE2_HEAD, AESR_MUL_NONE, dtype, algo, stream);
+                              const void* head_w16, float* partial, int N, int H, int W, int Cin, int act, float slope,
+                              int dtype, int algo, void* stream) {
+    if (head_w16 && (reinterpret_cast<uintptr_t>(head_w16) & 15))
+        return fail(AESR_ERR_INVALID, "conv3x3_up2_head_fwd: head_w16 must be 16-byte aligned");
+    return conv3x3_dispatch(x, w_folded, bias, nullptr, nullptr, partial, nullptr, nullptr, nullptr, head_w9c_host, head_w16,
+                            N, H, W, Cin, 128, act, slope, OUT_SHUFFLE2_HEAD, AESR_MUL_NONE, dtype, algo, stream);
 }
 
 int aesr_head_gather(const float* partial, const float* bias, float* out, const int* out_index, int N, int h, int w,
@@ -399,7 +436,8 @@ int aesr_head_gather(const float* partial, const float* bias, float* out, const 
     if ((out_image_stride & 1) || (reinterpret_cast<uintptr_t>(out) & 7))
         return fail(AESR_ERR_INVALID, "head_gather: output images must be 8-byte aligned (even stride)");
     if (static_cast<size_t>(h) * w > (1u << 28)) return fail(AESR_ERR_INVALID, "head_gather: image too large");
-    const dim3 grid((h * w + 255) / 256, N < 65535 ? N : 65535);
+    const dim3 grid((w + HG_TW - 1) / HG_TW, (h + HG_TH - 1) / HG_TH, N < 65535 ? N : 65535);
+    if (grid.y > 65535) return fail(AESR_ERR_INVALID, "head_gather: image too tall");
     head_gather_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         partial, bias, out, out_index, N, h, w, out_image_stride, apply_sigmoid);
     return check_launch("head_gather");
@@ -428,12 +466,13 @@ int aesr_stem_fwd(const float* x, const float* weff_beff_b1_host, void* out, int
         sp.ball[c] = t;
     }
     const int per_img = (H + 2) * (W + 2);
-    const dim3 grid((per_img + 255) / 256, N < 65535 ? N : 65535);
+    const int groups = (N + STEM_P - 1) / STEM_P;
+    const dim3 grid((per_img + 127) / 128, groups < 65535 ? groups : 65535);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == AESR_DT_FP16)
-        stem_conv_kernel<true><<<grid, 256, 0, s>>>(x, sp, static_cast<uint16_t*>(out), N, H, W, slope);
+        stem_conv_kernel<true><<<grid, 128, 0, s>>>(x, sp, static_cast<uint16_t*>(out), N, H, W, slope);
     else
-        stem_conv_kernel<false><<<grid, 256, 0, s>>>(x, sp, static_cast<uint16_t*>(out), N, H, W, slope);
+        stem_conv_kernel<false><<<grid, 128, 0, s>>>(x, sp, static_cast<uint16_t*>(out), N, H, W, slope);
     return check_launch("stem_conv");
 }
 
@@ -572,17 +611,19 @@ int aesr_probe_halo_conv(const void* x, const void* w_packed, float* out, int N,
 }
 
 int aesr_probe_umma_rate(long long* cycles, int N, int kc, int pitch_rows, int shift_rows, int iters,
-                         int a_advance_rows, int nacc, void* stream) {
+                         int a_advance_rows, int nacc, int grid, int fill_random, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
-    if (!cycles || N < 16 || N > 256 || N % 16 || (kc != 32 && kc != 64) || iters <= 0 || nacc < 1 || nacc * N > 512)
+    if (!cycles || N < 16 || N > 256 || N % 16 || (kc != 32 && kc != 64) || iters <= 0 || nacc < 1 || nacc * N > 512 ||
+        grid < 1 || grid > 1024)
         return fail(AESR_ERR_INVALID, "probe_umma_rate: bad arguments");
     const int smem = 1024 + 160 * 1024;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
 #define AESR_PROBE(NA)                                                                                             \
     case NA:                                                                                                       \
         CUDA_TRY(cudaFuncSetAttribute(umma_rate_probe_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        umma_rate_probe_kernel<NA><<<1, 128, smem, s>>>(cycles, N, kc, pitch_rows, shift_rows, iters, a_advance_rows); \
+        umma_rate_probe_kernel<NA><<<grid, 128, smem, s>>>(cycles, N, kc, pitch_rows, shift_rows, iters, a_advance_rows, \
+                                                          fill_random);                                            \
         break;
     switch (nacc) {
         AESR_PROBE(1) AESR_PROBE(2) AESR_PROBE(4) AESR_PROBE(8)

@@ -270,6 +270,78 @@ int aesr_ssim_psnr(const float* a, const float* b, int Z, int H, int W, int win,
     return check_launch("ssim_psnr");
 }
 
+size_t aesr_vif_workspace_bytes(int Z, int H, int W) {
+    if (Z <= 0 || H <= 0 || W <= 0) return 0;
+    return 12 * static_cast<size_t>(Z) * H * W + 256;       // 12 uint8 planes (see aesr_vif_mscale)
+}
+
+int aesr_vif_quantize_u8(const float* x, void* out_u8, size_t n, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!x || !out_u8 || n == 0) return fail(AESR_ERR_INVALID, "vif_quantize_u8: bad arguments");
+    size_t grid = (n + 255) / 256;
+    if (grid > static_cast<size_t>(g_sm_count) * 16) grid = static_cast<size_t>(g_sm_count) * 16;
+    vif_quantize_kernel<<<static_cast<int>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, static_cast<uint8_t*>(out_u8), n);
+    return check_launch("vif_quantize");
+}
+
+int aesr_vif_mscale(const void* ref_u8, const void* dist_u8, int Z, int H, int W, const double* weights,
+                    const int* radii_host, double sigma_nsq, void* workspace, size_t workspace_bytes, double* num_den,
+                    void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!ref_u8 || !dist_u8 || !weights || !radii_host || !workspace || !num_den || Z <= 0 || Z > 65535 || H <= 0 || W <= 0)
+        return fail(AESR_ERR_INVALID, "vif_mscale: bad arguments (Z <= 65535)");
+    if (workspace_bytes < aesr_vif_workspace_bytes(Z, H, W)) return fail(AESR_ERR_WORKSPACE, "vif_mscale: workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t plane = static_cast<size_t>(Z) * H * W;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    uint8_t *cur_r = ws, *cur_d = ws + plane, *tmp = ws + 2 * plane, *full_r = ws + 3 * plane, *full_d = ws + 4 * plane,
+            *mu1 = ws + 5 * plane, *mu2 = ws + 6 * plane, *prr = ws + 7 * plane, *pdd = ws + 8 * plane,
+            *prd = ws + 9 * plane, *g3 = ws + 10 * plane;      // g3: the three filtered products reuse [10, 12) + tmp
+    CUDA_TRY(cudaMemsetAsync(num_den, 0, 2 * Z * sizeof(double), s));
+    CUDA_TRY(cudaMemcpyAsync(cur_r, ref_u8, plane, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(cur_d, dist_u8, plane, cudaMemcpyDeviceToDevice, s));
+    auto grid_for = [&](size_t n) {
+        size_t g = (n + 255) / 256;
+        const size_t cap = static_cast<size_t>(g_sm_count) * 16;
+        return static_cast<int>(g < cap ? (g ? g : 1) : cap);
+    };
+    // gaussian_filter of `planes` images of h x w: axis 0 then axis 1, uint8 in between (scipy.ndimage.gaussian_filter)
+    auto gauss = [&](const uint8_t* in, uint8_t* scratch, uint8_t* out, int planes, int h, int w, const double* wt, int lw) {
+        const size_t n = static_cast<size_t>(planes) * h * w;
+        vif_gauss1d_u8_kernel<<<grid_for(n), 256, 0, s>>>(in, scratch, planes, h, w, 0, wt, lw);
+        vif_gauss1d_u8_kernel<<<grid_for(n), 256, 0, s>>>(scratch, out, planes, h, w, 1, wt, lw);
+    };
+    int h = H, w = W;
+    const double* wt = weights;
+    for (int scale = 1; scale <= 4; ++scale) {
+        const int lw = radii_host[scale - 1];
+        if (lw < 0 || lw > 64) return fail(AESR_ERR_INVALID, "vif_mscale: filter radius %d", lw);
+        if (scale > 1) {
+            gauss(cur_r, tmp, full_r, Z, h, w, wt, lw);
+            gauss(cur_d, tmp, full_d, Z, h, w, wt, lw);
+            const int h2 = (h + 1) / 2, w2 = (w + 1) / 2;
+            const size_t n2 = static_cast<size_t>(Z) * h2 * w2;
+            vif_subsample_kernel<<<grid_for(n2), 256, 0, s>>>(full_r, cur_r, Z, h, w);
+            vif_subsample_kernel<<<grid_for(n2), 256, 0, s>>>(full_d, cur_d, Z, h, w);
+            h = h2;
+            w = w2;
+        }
+        const size_t n = static_cast<size_t>(Z) * h * w;
+        gauss(cur_r, tmp, mu1, Z, h, w, wt, lw);
+        gauss(cur_d, tmp, mu2, Z, h, w, wt, lw);
+        vif_products_kernel<<<grid_for(n), 256, 0, s>>>(cur_r, cur_d, prr, pdd, prd, n);
+        gauss(prr, tmp, full_r, Z, h, w, wt, lw);           // full_r / full_d / g3 are free here: filtered products
+        gauss(pdd, tmp, full_d, Z, h, w, wt, lw);
+        gauss(prd, tmp, g3, Z, h, w, wt, lw);
+        vif_accumulate_kernel<<<Z, 256, 0, s>>>(mu1, mu2, full_r, full_d, g3, h * w, sigma_nsq, num_den);
+        wt += 2 * lw + 1;
+    }
+    return check_launch("vif_mscale");
+}
+
 size_t aesr_percentile_workspace_bytes(void) { return 256 + 4 * 2048 * sizeof(unsigned int) + 64; }
 
 int aesr_percentile_normalize(const float* x, float* out, size_t n, double q_lo, double q_hi, void* workspace,

@@ -60,6 +60,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// Same wait with an explicit suspend-time hint (ns): the warp is parked by the hardware until the phase completes or the
+// hint elapses instead of re-polling the barrier word in shared memory -- for the many waiting warps of a role-specialised
+// CTA whose tcgen05.mma stream is shared-memory-bandwidth-bound.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+            : "memory");
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), tile mode, mbarrier completion
@@ -120,6 +135,32 @@ __device__ __forceinline__ void umma_f16_split(uint32_t tmem_d, uint32_t a_lo, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
         ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 lanes x K 16-bit values, two per 32-bit column) is read from
+// tensor memory, so only B costs shared-memory bandwidth.  Used for the decoder head conv in the fused tail epilogue.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// registers -> TMEM: thread t of the warp writes columns [col, col+16) of TMEM lane (lane_base + t)
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// named barrier among `count` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 // mbarrier arrive once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

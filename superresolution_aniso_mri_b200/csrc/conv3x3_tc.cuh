@@ -49,6 +49,10 @@ enum ConvOut : int {
     // latents BEFORE the interpolation (conv is linear: conv(a*z1 + b*z2) = a*conv(z1) + b*conv(z2)), lerp_pairs_act
     // then blends these pre-activations per alpha and applies bias + LeakyReLU.
     OUT_SAME_F32 = 7,      // out  = NHWC fp32 [N,H,W,Cout]
+    // OUT_SHUFFLE2_HEAD with the head conv itself on the tensor cores (kernel template value only; p.out_mode stays
+    // OUT_SHUFFLE2_HEAD): the epilogue writes LeakyReLU(acc + bias) back to TMEM as a 16-bit A operand and one elected
+    // thread issues D2[128 px x 16 taps] = A[128 x 32] * Whead[32 x 16] per phase (A from TMEM, B = 1 KB in smem).
+    OUT_SHUFFLE2_HEAD_TC = 8,
 };
 enum ConvMul : int { MUL_NONE = 0, MUL_LEAKY_GRAD = 1, MUL_RELU_GRAD = 2 };
 
@@ -58,6 +62,8 @@ struct ConvParams {
     int tiles_x, tiles_y, n_blocks, num_tiles;   // num_tiles = spatial tiles (N * tiles_y * tiles_x) * n_blocks
     int num_stages;
     int T, stiles_y;        // halo kernel: M-tiles stacked vertically per super-tile, super-tile rows per image
+    int head_smem;          // bytes reserved behind the filter bank for the 16 x 32 head filter block (0 or 1024)
+    int nbuf;               // halo kernel: TMEM buffers (super-tiles in flight between the MMA issuer and the epilogue), 2..4
     int fp16;               // 1: activations / weights are fp16, 0: bf16
     int debug;              // profiling only (AESR_CONV_DEBUG): bit0 = skip the MMAs, bit1 = skip the activation TMA loads
     // epilogue
@@ -114,6 +120,7 @@ struct ConvBarriers {
     uint64_t* tmem_full;   // [CONV_EPI_SETS]
     uint64_t* tmem_empty;  // [CONV_EPI_SETS]
     uint64_t* b_full;      // [1] resident filter bank landed
+    uint64_t* head_bar;    // [CONV_EPI_SETS] head MMAs of an epilogue set's tile completed (OUT_SHUFFLE2_HEAD_TC)
     uint32_t* tmem_ptr;
     float *s_bias, *s_scale, *s_shift;
     __device__ explicit ConvBarriers(uint8_t* tail) {
@@ -122,7 +129,8 @@ struct ConvBarriers {
         tmem_full = empty + CONV_MAX_STAGES;
         tmem_empty = tmem_full + CONV_EPI_SETS;
         b_full = tmem_empty + CONV_EPI_SETS;
-        tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
+        head_bar = b_full + 1;
+        tmem_ptr = reinterpret_cast<uint32_t*>(head_bar + CONV_EPI_SETS);
         s_bias = reinterpret_cast<float*>(tail + 256);
         s_scale = s_bias + 512;
         s_shift = s_scale + 512;
@@ -146,6 +154,7 @@ __device__ __forceinline__ uint32_t conv_prologue(const ConvParams& p, const Con
         for (int a = 0; a < CONV_EPI_SETS; ++a) {
             mbar_init(&bars.tmem_full[a], 1);
             mbar_init(&bars.tmem_empty[a], tmem_empty_count);   // one elected lane per epilogue warp
+            mbar_init(&bars.head_bar[a], 1);
         }
         mbar_init(bars.b_full, 1);
         fence_barrier_init();
@@ -573,6 +582,96 @@ __device__ __forceinline__ void conv_epilogue_head_tile(const ConvParams& p, con
     }
 }
 
+// OUT_SHUFFLE2_HEAD_TC: same result layout as conv_epilogue_head_tile, but the 32 -> 1 head conv (4 x 288 MACs per low-res
+// pixel) runs on the tensor cores.  The CUDA-core version needed ~1650 warp instructions per tile and scheduler --
+// more than the 1152 tensor-pipe cycles of the tile's main MMAs (ncu: 56 % issue utilisation, epilogue-bound).
+//   phase A  (per phase ph): acc columns [32ph, 32ph+32) -> + bias, LeakyReLU -> 16-bit pairs -> tcgen05.st into
+//            columns [32ph, 32ph+16) of the SAME accumulator (K-major A operand: lane = pixel, column j = channels 2j, 2j+1)
+//   MMA      one elected thread of the set: D2_ph[128 x 16] = A_ph[128 x 32] * Whead[32 x 16]  (2 K-steps, A from TMEM,
+//            B = the [16 taps (9 used)][32] head filter in shared memory) into columns [32ph+16, 32ph+32); commit -> head_bar
+//   phase B  D2_ph column tap = the head-conv contribution of hi-res pixel (2y+a, 2x+b) through tap (ky,kx): scatter
+//            into the 4x4 patch like the CUDA-core version.
+// The activations are rounded to 16 bit here (like every other layer); the head filter is 16-bit.
+__device__ __forceinline__ void conv_epilogue_head_tc_tile(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
+                                                           uint64_t* tmem_empty_bar, uint64_t* head_bar,
+                                                           uint32_t head_parity, uint32_t hdesc_lo, uint32_t hdesc_hi,
+                                                           int eset, const TileCoord& t) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int py = row >> 3, px = row & 7;
+    const int y = t.y0 + py, x = t.x0 + px;
+    const bool inb = (y < p.H) && (x < p.W);
+    const int fp16 = p.fp16;
+    const float neg_slope = (p.act == ACT_LEAKY) ? p.slope : (p.act == ACT_RELU) ? 0.f : 1.f;
+    const float2 slope2 = make_float2(neg_slope, neg_slope);
+    const uint32_t t_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int ph = 0; ph < 4; ++ph) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t raw[16];
+            tmem_ld_32x32b_x16(t_addr + ph * 32 + half * 16, raw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 b = lds_f4(bars.s_bias + half * 16 + 4 * j4);       // phase blocks share the 32 biases
+                const float2 a0 = __fadd2_rn(make_float2(__uint_as_float(raw[j4 * 4 + 0]), __uint_as_float(raw[j4 * 4 + 1])),
+                                             make_float2(b.x, b.y));
+                const float2 a1 = __fadd2_rn(make_float2(__uint_as_float(raw[j4 * 4 + 2]), __uint_as_float(raw[j4 * 4 + 3])),
+                                             make_float2(b.z, b.w));
+                const float2 s0 = __fmul2_rn(a0, slope2), s1 = __fmul2_rn(a1, slope2);
+                pk[half * 8 + j4 * 2 + 0] = pack2(fmaxf(a0.x, s0.x), fmaxf(a0.y, s0.y), fp16);
+                pk[half * 8 + j4 * 2 + 1] = pack2(fmaxf(a1.x, s1.x), fmaxf(a1.y, s1.y), fp16);
+            }
+        }
+        tmem_st_32x32b_x16(t_addr + ph * 32, pk);     // both halves of the phase are in registers: in-place is safe
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    named_bar_sync(1 + eset, 128);                    // all 128 pixels (lanes) of the tile have their A rows in TMEM
+    if (q == 0) {
+        tc_fence_after();
+        if (elect_one_sync()) {
+            const uint32_t idesc = make_idesc_16(CONV_TILE_M, 16, fp16);
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    umma_f16_ts(tmem_acc + ph * 32 + 16, tmem_acc + ph * 32 + 8 * k, hdesc_lo + 2 * k, hdesc_hi, idesc,
+                                static_cast<uint32_t>(k));
+            umma_commit(head_bar);
+        }
+        __syncwarp();
+    }
+    mbar_wait(head_bar, head_parity);
+    tc_fence_after();
+    float hp[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) hp[i] = 0.f;
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+        uint32_t raw[16];
+        tmem_ld_32x32b_x16(t_addr + ph * 32 + 16, raw);
+        tmem_ld_wait();
+        if (ph == 3) {                                 // accumulator fully consumed: one elected arrive per warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar);
+        }
+        const int a = ph >> 1, b = ph & 1;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) hp[(a - tap / 3 + 2) * 4 + (b - tap % 3 + 2)] += __uint_as_float(raw[tap]);
+    }
+    if (inb) {
+        float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) +
+                                              ((static_cast<size_t>(t.n) * p.H + y) * p.W + x) * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = make_float4(hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // halo + resident-filter kernel
 //
@@ -582,10 +681,8 @@ __device__ __forceinline__ void conv_epilogue_head_tile(const ConvParams& p, con
 // mbarrier hand-offs alone (producer -> MMA -> epilogue -> MMA, everything else stubbed out) cost ~510 cycles per tile
 // and do not overlap with the 720 cycles of a 32-channel tile's MMAs; a super-tile pays them once per T tiles.
 //   M-tile t of a stage starts 160 pixel rows (16 x pitch 10) further: same row-shifted descriptors as the taps.
-//   TMEM: 2 buffers x T accumulators x BN columns (<= 512); buffer b of super-tile i = i & 1.
-//   Epilogue sets (4 x 4 warps): T = 4: set e <-> M-tile e of every super-tile; T = 2: set e <-> M-tile e & 1 of the
-//   super-tiles with parity e >> 1; T = 1: sets 0 / 1 alternate super-tiles (sets 2, 3 idle: only the fat layers whose
-//   tiles carry >= 2304 MMA cycles run with T = 1).
+//   TMEM: nbuf (2..4) buffers x T accumulators x BN columns (<= 512); super-tile i uses buffer i % nbuf.
+//   Epilogue sets (4 x 4 warps): M-tile t of super-tile i belongs to set (i*T + t) & 3 (round-robin in issue order).
 // ---------------------------------------------------------------------------------------------------------------
 template <int KC>
 struct HaloSmem {
@@ -598,15 +695,16 @@ struct HaloSmem {
         return 1024 + b_bytes(BN, Cin) + stages * a_stage(T) + CONV_TAIL_BYTES;
     }
 };
-__host__ __device__ constexpr uint32_t halo_tmem_cols(int T, int BN) {
-    const int c = 2 * T * BN;
+constexpr int HEAD_SMEM_BYTES = 1024;          // 16 rows x 64 bytes, SW64
+__host__ __device__ constexpr uint32_t halo_tmem_cols(int T, int BN, int nbuf) {
+    const int c = nbuf * T * BN;
     return (c <= 32) ? 32 : (c <= 64) ? 64 : (c <= 128) ? 128 : (c <= 256) ? 256 : 512;
 }
 
 template <int KC, int MODE>        // MODE: -1 = run-time epilogue, OUT_* = that output stage compiled in
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                    const __grid_constant__ ConvParams p) {
+                    const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ ConvParams p) {
     using S = HaloSmem<KC>;
     constexpr uint32_t LAYOUT = (KC == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
     constexpr uint32_t ROW_BYTES = S::ROW_BYTES;
@@ -618,7 +716,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const int b_block = S::b_block(p.BN);
     const int a_stage = S::a_stage(T);
     uint8_t* b_smem = smem;                                         // [tap][chunk][BN rows][KC] swizzled
-    uint8_t* a_smem = smem + S::b_bytes(p.BN, p.Cin);               // [stage][(16T+2)*10 rows][KC] swizzled
+    uint8_t* h_smem = smem + S::b_bytes(p.BN, p.Cin);               // [16 taps][32] head filter, SW64 (head_smem bytes)
+    uint8_t* a_smem = h_smem + p.head_smem;                         // [stage][(16T+2)*10 rows][KC] swizzled
     const int num_stages = p.num_stages;
     ConvBarriers bars(a_smem + num_stages * a_stage);
 
@@ -628,7 +727,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         tma_prefetch_desc(&tmap_w);
     }
     // epilogue warps attached to one TMEM buffer: T sets of 4 warps (T = 1: one set per buffer)
-    const uint32_t tmem_cols = halo_tmem_cols(T, p.BN);
+    const int nbuf = p.nbuf;
+    const uint32_t tmem_cols = halo_tmem_cols(T, p.BN, nbuf);
     const uint32_t tmem_base = conv_prologue(p, bars, num_stages, tmem_cols, 4 * T);
 
     // CTA -> (n-block, first super-tile, stride): the grid is split evenly between the n-blocks.
@@ -644,7 +744,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         if (active) {
             if (elect_one_sync()) {
                 // resident filter bank of this n-block: 9 * kchunks TMA boxes {KC, BN} on one barrier
-                mbar_arrive_expect_tx(bars.b_full, 9 * kchunks * b_block);
+                mbar_arrive_expect_tx(bars.b_full, 9 * kchunks * b_block + p.head_smem);
+                if (MODE == OUT_SHUFFLE2_HEAD_TC) tma_load_2d(h_smem, &tmap_h, bars.b_full, 0, 0);
                 for (int tap = 0; tap < 9; ++tap)
                     for (int kc = 0; kc < kchunks; ++kc)
                         tma_load_2d(b_smem + (tap * kchunks + kc) * b_block, &tmap_w, bars.b_full, kc * KC,
@@ -659,7 +760,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                       dtx = ctas_per_nb % p.tiles_x;
             for (int st = first; st < st_total; st += ctas_per_nb) {
                 for (int kc = 0; kc < kchunks; ++kc) {
-                    mbar_wait(&bars.empty[stage], phase ^ 1);
+                    if (p.debug & 256) mbar_wait_parked(&bars.empty[stage], phase ^ 1, 20000);
+                    else mbar_wait(&bars.empty[stage], phase ^ 1);
                     if (elect_one_sync()) {
                         if (p.debug & 2) {
                             mbar_arrive(&bars.full[stage]);
@@ -738,8 +840,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 }
                 if (elect_one_sync()) umma_commit(&bars.tmem_full[buf]);
                 __syncwarp();
-                buf ^= 1;
-                if (buf == 0) buf_phase ^= 1;
+                if (++buf == nbuf) { buf = 0; buf_phase ^= 1; }
                 tx += dtx;
                 if (tx >= p.tiles_x) { tx -= p.tiles_x; ++sy; }
                 sy += dsy;
@@ -748,14 +849,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         }
     } else if (active) {
         const int eset = (warp - CONV_FIRST_EPI_WARP) >> 2;
-        // (M-tile, buffer) this set serves; T = 4: every super-tile, else the super-tiles with local parity `my_buf`
-        const int t = (T == 4) ? eset : (T == 2) ? (eset & 1) : 0;
-        const int my_buf = (T == 4) ? -1 : (T == 2) ? (eset >> 1) : eset;
-        if (my_buf < 2) {
-            int i = 0;
-            for (int st = first; st < st_total; st += ctas_per_nb, ++i) {
-                const int buf = i & 1;
-                if (my_buf >= 0 && buf != my_buf) continue;
+        // M-tiles are dealt to the four epilogue sets round-robin in issue order: M-tile t of super-tile i (running index
+        // i*T + t) belongs to set (i*T + t) % nsets.  T = 4: set e <-> M-tile e of every super-tile; T = 2: set e <-> M-tile
+        // e & 1 of the super-tiles with parity e >> 1; T = 1: set e <-> every 4th super-tile.  Super-tile i lives in TMEM
+        // buffer i % nbuf (its (i / nbuf)-th use), so with nbuf = 4 the issuer runs up to three super-tiles ahead of
+        // the slowest epilogue (measured: with two buffers the store-heavy epilogues of the 64/128-column layers stalled
+        // the MMAs, profiles/r01f_debug_sweep_large_n.txt).
+        // A set must see EVERY use of a buffer it touches (an mbarrier parity wait cannot skip a phase), hence only
+        // min(4, nbuf * T) sets take part: T = 1 with two buffers runs on sets 0 / 1.
+        const int nsets = (nbuf * T < CONV_EPI_SETS) ? nbuf * T : CONV_EPI_SETS;       // 2 or 4
+        int i = 0, buf = 0;
+        uint32_t buf_phase = 0, head_uses = 0;
+        const uint64_t h_tmpl = make_smem_desc(smem_u32(h_smem), 8 * 64, UMMA_LAYOUT_SW64);
+        const uint32_t hdesc_lo = static_cast<uint32_t>(h_tmpl), hdesc_hi = static_cast<uint32_t>(h_tmpl >> 32);
+        if (MODE == OUT_SHUFFLE2_HEAD_TC) mbar_wait(bars.b_full, 0);       // the head filter block landed with the bank
+        for (int st = first; st < st_total; st += ctas_per_nb, ++i) {
+            const int t = (eset - i * T) & (nsets - 1);
+            if (eset < nsets && t < T) {
                 const int n = st / st_per_img;
                 const int r = st - n * st_per_img;
                 const int sy = r / p.tiles_x;
@@ -764,11 +874,16 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 tc.y0 = (sy * T + t) * CONV_TILE_H;
                 tc.x0 = (r - sy * p.tiles_x) * CONV_TILE_W;
                 tc.n0 = nb * p.BN;
-                mbar_wait(&bars.tmem_full[buf], (i >> 1) & 1);
+                if (p.debug & 256) mbar_wait_parked(&bars.tmem_full[buf], buf_phase, 20000);
+                else mbar_wait(&bars.tmem_full[buf], buf_phase);
                 tc_fence_after();
                 if (sy * T + t < p.tiles_y) {
                     const uint32_t acc = tmem_base + (buf * T + t) * p.BN;
-                    if (MODE == OUT_SHUFFLE2_HEAD) conv_epilogue_head_tile(p, bars, acc, &bars.tmem_empty[buf], tc);
+                    if (MODE == OUT_SHUFFLE2_HEAD_TC) {
+                        conv_epilogue_head_tc_tile(p, bars, acc, &bars.tmem_empty[buf], &bars.head_bar[eset], head_uses & 1,
+                                                   hdesc_lo, hdesc_hi, eset, tc);
+                        ++head_uses;
+                    } else if (MODE == OUT_SHUFFLE2_HEAD) conv_epilogue_head_tile(p, bars, acc, &bars.tmem_empty[buf], tc);
                     else if (MODE >= 0) conv_epilogue_lean<MODE>(p, bars, acc, &bars.tmem_empty[buf], tc);
                     else conv_epilogue_tile(p, bars, acc, &bars.tmem_empty[buf], tc);
                 } else {                       // M-tile below the image: nothing to read, release the buffer
@@ -777,6 +892,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     if (lane == 0) mbar_arrive(&bars.tmem_empty[buf]);
                 }
             }
+            if (++buf == nbuf) { buf = 0; buf_phase ^= 1; }
         }
     }
     conv_teardown(tmem_base, tmem_cols);

@@ -203,58 +203,112 @@ struct StemParams {
     alignas(16) float ball[32];
 };
 
-// one thread = one output pixel x 32 channels: 9 image loads, 144 packed fp32x2 FMAs, one 64-byte store
+// One thread = one output pixel position in STEM_P = 4 images x 32 channels (two passes of 16 channels).
+//  * filter reuse: the folded filter reaches the FMAs through uniform registers (LDCU from the constant bank); with one
+//    pixel per thread the 72 LDCU.128 per pixel bounded the kernel (measured 1.5 TB/s, LDCU : FFMA2 = 1.3 : 1 in the
+//    SASS) -- four images at the same pixel position share every loaded filter value (and all border predicates).
+//  * coalesced stores: the 32 pixels of a warp are one contiguous 2 KB block of the NHWC output per image; each warp
+//    transposes its blocks through shared memory (XOR-swizzled, conflict-free both ways) and stores fully coalesced
+//    512-byte rows instead of 16 bytes per lane at a 64-byte stride.
+constexpr int STEM_P = 4;
 template <bool FP16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 stem_conv_kernel(const float* __restrict__ x, const __grid_constant__ StemParams sp, uint16_t* __restrict__ out, int N,
                  int H, int W, float slope) {
-    constexpr int C = 32;
+    constexpr int C = 32, P = STEM_P;
+    __shared__ uint4 stage[4][P][128];
     const int Ho = H + 2, Wo = W + 2;
+    const int total = Ho * Wo;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= Ho * Wo) return;
-    const int yo = pix / Wo, xo = pix - yo * Wo;
+    const int wpix0 = blockIdx.x * blockDim.x + warp * 32;          // first pixel of this warp
+    if (wpix0 >= total) return;                                      // whole warp out of range
+    const bool valid = pix < total;
+    const int yo = valid ? pix / Wo : 0, xo = valid ? pix - yo * Wo : 0;
     const bool interior = yo >= 1 && yo <= H && xo >= 1 && xo <= W;
-    for (int n = blockIdx.y; n < N; n += gridDim.y) {
-        const float* img = x + static_cast<size_t>(n) * H * W;
-        float xv[9];
-        bool on_grid[9];
+    const int n_chunks = min(32, total - wpix0) * 4;                 // 16-byte chunks this warp owns per image
+    const int sw = (lane >> 1) & 3;
+    bool on_grid[9];
+    int off[9];                                                      // image offset of the tap, -1 = outside the image
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const int yy = yo + tap / 3 - 1, xx = xo + tap % 3 - 1;        // position on the (H+2)x(W+2) grid
-            on_grid[tap] = yy >= 0 && yy < Ho && xx >= 0 && xx < Wo;      // else: enc.1 zero padding
-            const int yi = yy - 1, xi = xx - 1;                            // position in the image
-            xv[tap] = (yi >= 0 && yi < H && xi >= 0 && xi < W) ? __ldg(img + static_cast<size_t>(yi) * W + xi) : 0.f;
-        }
-        float2 acc[C / 2];
-        if (interior) {
+    for (int tap = 0; tap < 9; ++tap) {
+        const int yy = yo + tap / 3 - 1, xx = xo + tap % 3 - 1;            // position on the (H+2)x(W+2) grid
+        on_grid[tap] = yy >= 0 && yy < Ho && xx >= 0 && xx < Wo;          // else: enc.1 zero padding
+        const int yi = yy - 1, xi = xx - 1;                                // position in the image
+        off[tap] = (valid && yi >= 0 && yi < H && xi >= 0 && xi < W) ? yi * W + xi : -1;
+    }
+    for (int n0 = blockIdx.y * P; n0 < N; n0 += gridDim.y * P) {
+        const int np = min(P, N - n0);
+        float2 xv[P][9];
 #pragma unroll
-            for (int j = 0; j < C / 2; ++j) acc[j] = make_float2(sp.ball[2 * j], sp.ball[2 * j + 1]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < C / 2; ++j) acc[j] = make_float2(sp.b1[2 * j], sp.b1[2 * j + 1]);
+        for (int i = 0; i < P; ++i) {
+            const float* img = x + static_cast<size_t>(n0 + i) * H * W;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-                if (on_grid[tap]) {
-#pragma unroll
-                    for (int j = 0; j < C / 2; ++j)
-                        acc[j] = __fadd2_rn(acc[j], make_float2(sp.beff[tap * C + 2 * j], sp.beff[tap * C + 2 * j + 1]));
-                }
+                const float v = (i < np && off[tap] >= 0) ? __ldg(img + off[tap]) : 0.f;
+                xv[i][tap] = make_float2(v, v);
             }
         }
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const float2 x2 = make_float2(xv[tap], xv[tap]);
+        for (int half = 0; half < 2; ++half) {
+            constexpr int CH = C / 2;
+            const int c0 = half * CH;
+            float2 acc[P][CH / 2];
+            {
+                float2 a0[CH / 2];
+                if (interior) {
 #pragma unroll
-            for (int j = 0; j < C / 2; ++j)
-                acc[j] = __ffma2_rn(make_float2(sp.weff[tap * C + 2 * j], sp.weff[tap * C + 2 * j + 1]), x2, acc[j]);
+                    for (int j = 0; j < CH / 2; ++j) a0[j] = make_float2(sp.ball[c0 + 2 * j], sp.ball[c0 + 2 * j + 1]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CH / 2; ++j) a0[j] = make_float2(sp.b1[c0 + 2 * j], sp.b1[c0 + 2 * j + 1]);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (on_grid[tap]) {
+#pragma unroll
+                            for (int j = 0; j < CH / 2; ++j)
+                                a0[j] = __fadd2_rn(a0[j], make_float2(sp.beff[tap * C + c0 + 2 * j],
+                                                                      sp.beff[tap * C + c0 + 2 * j + 1]));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < P; ++i)
+#pragma unroll
+                    for (int j = 0; j < CH / 2; ++j) acc[i][j] = a0[j];
+            }
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                for (int j = 0; j < CH / 2; ++j) {
+                    const float2 wv = make_float2(sp.weff[tap * C + c0 + 2 * j], sp.weff[tap * C + c0 + 2 * j + 1]);
+#pragma unroll
+                    for (int i = 0; i < P; ++i) acc[i][j] = __ffma2_rn(wv, xv[i][tap], acc[i][j]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                uint32_t pk[CH / 2];
+#pragma unroll
+                for (int j = 0; j < CH / 2; ++j)
+                    pk[j] = pack2_t<FP16>(fmaxf(acc[i][j].x, acc[i][j].x * slope), fmaxf(acc[i][j].y, acc[i][j].y * slope));
+                uint4* st = stage[warp][i];
+                st[lane * 4 + ((2 * half) ^ sw)] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                st[lane * 4 + ((2 * half + 1) ^ sw)] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
         }
-        uint32_t pk[C / 2];
+        __syncwarp();
+        for (int i = 0; i < np; ++i) {
+            uint4* o4 = reinterpret_cast<uint4*>(out + (static_cast<size_t>(n0 + i) * total + wpix0) * C);
+            const uint4* st = stage[warp][i];
 #pragma unroll
-        for (int j = 0; j < C / 2; ++j)
-            pk[j] = pack2_t<FP16>(fmaxf(acc[j].x, acc[j].x * slope), fmaxf(acc[j].y, acc[j].y * slope));
-        uint4* o4 = reinterpret_cast<uint4*>(out + (static_cast<size_t>(n) * Ho * Wo + pix) * C);
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) o4[j4] = make_uint4(pk[4 * j4], pk[4 * j4 + 1], pk[4 * j4 + 2], pk[4 * j4 + 3]);
+            for (int k = 0; k < 4; ++k) {
+                const int c = k * 32 + lane;                               // linear 16-byte chunk of the warp's block
+                const int px = c >> 2, j = c & 3;
+                if (c < n_chunks) o4[c] = st[px * 4 + (j ^ ((px >> 1) & 3))];
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -265,41 +319,62 @@ stem_conv_kernel(const float* __restrict__ x, const __grid_constant__ StemParams
 // (networks/acai_vanilla.py:98, generate_hr_volumes.py:67) and write image n at out + slot(n) * stride.
 // One thread = one low-res pixel = a 2x2 block of outputs.  16 B/hi-res px read + 4 B/px written.
 // ---------------------------------------------------------------------------------------------------------------
+// Block = 8 x 32 low-res pixels of one image.  The (8+2) x (32+2) window of patches is staged once through shared
+// memory with fully coalesced 16-byte loads (a patch row of the window is one contiguous run of 64-byte patches) at a
+// 17-float pixel pitch, so that the 16 scattered patch entries a thread needs come from conflict-free LDS instead of
+// 16 global loads touching 32 sectors each (measured: the per-pixel version ran at 40 % of the HBM roofline).
+constexpr int HG_TW = 32, HG_TH = 8, HG_PITCH = 17;
 __global__ void __launch_bounds__(256)
 head_gather_kernel(const float* __restrict__ part, const float* __restrict__ bias_ptr, float* __restrict__ out,
                    const int* __restrict__ out_index, int N, int h, int w, size_t out_image_stride, int apply_sigmoid) {
+    __shared__ float tile[(HG_TH + 2) * (HG_TW + 2) * HG_PITCH];
     const float bias = __ldg(bias_ptr);
     const int W = 2 * w;
-    const uint32_t per_img = static_cast<uint32_t>(h) * w;
-    for (int n = blockIdx.y; n < N; n += gridDim.y)
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < per_img; i += gridDim.x * blockDim.x) {
-        const int yl = static_cast<int>(i / static_cast<uint32_t>(w));
-        const int xl = static_cast<int>(i - static_cast<uint32_t>(yl) * w);
-        const float* pn = part + static_cast<size_t>(n) * h * w * 16;
-        float r[4];
-#pragma unroll
-        for (int a = 0; a < 2; ++a) {
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                // rows: own patch row 1+a, plus the neighbour above (row 3) for a = 0 / below (row 0) for a = 1
-                const int yn = a ? yl + 1 : yl - 1, rn = a ? 0 : 3;
-                const int xn = b ? xl + 1 : xl - 1, cn = b ? 0 : 3;
-                const bool oky = yn >= 0 && yn < h, okx = xn >= 0 && xn < w;
-                float s = bias + __ldg(pn + (static_cast<size_t>(yl) * w + xl) * 16 + (1 + a) * 4 + (1 + b));
-                if (oky) s += __ldg(pn + (static_cast<size_t>(yn) * w + xl) * 16 + rn * 4 + (1 + b));
-                if (okx) s += __ldg(pn + (static_cast<size_t>(yl) * w + xn) * 16 + (1 + a) * 4 + cn);
-                if (oky && okx) s += __ldg(pn + (static_cast<size_t>(yn) * w + xn) * 16 + rn * 4 + cn);
-                if (apply_sigmoid) {
-                    s = 1.f / (1.f + __expf(-s));
-                    s = fminf(fmaxf(s, 0.f), 1.f);
-                }
-                r[a * 2 + b] = s;
-            }
+    const int x0 = blockIdx.x * HG_TW, y0 = blockIdx.y * HG_TH;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int xl = x0 + tx, yl = y0 + ty;
+    for (int n = blockIdx.z; n < N; n += gridDim.z) {
+        const float4* pn = reinterpret_cast<const float4*>(part + static_cast<size_t>(n) * h * w * 16);
+        // stage the window: (HG_TH+2) rows x (HG_TW+2) pixels x 4 float4
+        for (int i = threadIdx.x; i < (HG_TH + 2) * (HG_TW + 2) * 4; i += 256) {
+            const int q = i & 3, px = i >> 2;
+            const int hx = px % (HG_TW + 2), hy = px / (HG_TW + 2);
+            const int gx = x0 + hx - 1, gy = y0 + hy - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gx >= 0 && gx < w && gy >= 0 && gy < h) v = __ldg(pn + (static_cast<size_t>(gy) * w + gx) * 4 + q);
+            float* d = tile + px * HG_PITCH + q * 4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }
-        const size_t slot = out_index ? static_cast<size_t>(__ldg(out_index + n)) : static_cast<size_t>(n);
-        float* o = out + slot * out_image_stride + static_cast<size_t>(2 * yl) * W + 2 * xl;
-        *reinterpret_cast<float2*>(o) = make_float2(r[0], r[1]);
-        *reinterpret_cast<float2*>(o + W) = make_float2(r[2], r[3]);
+        __syncthreads();
+        if (xl < w && yl < h) {
+            // window pixel (hy, hx) = (ty + 1 + dy, tx + 1 + dx); out-of-image neighbours were staged as zeros
+            const float* c = tile + ((ty + 1) * (HG_TW + 2) + tx + 1) * HG_PITCH;
+            constexpr int ROW = (HG_TW + 2) * HG_PITCH;
+            float r[4];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    // rows: own patch row 1+a, plus the neighbour above (its row 3) for a = 0 / below (row 0) for a = 1
+                    const int dy = a ? 1 : -1, rn = a ? 0 : 3;
+                    const int dx = b ? 1 : -1, cn = b ? 0 : 3;
+                    float s = bias + c[(1 + a) * 4 + (1 + b)];
+                    s += c[dy * ROW + rn * 4 + (1 + b)];
+                    s += c[dx * HG_PITCH + (1 + a) * 4 + cn];
+                    s += c[dy * ROW + dx * HG_PITCH + rn * 4 + cn];
+                    if (apply_sigmoid) {
+                        s = 1.f / (1.f + __expf(-s));
+                        s = fminf(fmaxf(s, 0.f), 1.f);
+                    }
+                    r[a * 2 + b] = s;
+                }
+            }
+            const size_t slot = out_index ? static_cast<size_t>(__ldg(out_index + n)) : static_cast<size_t>(n);
+            float* o = out + slot * out_image_stride + static_cast<size_t>(2 * yl) * W + 2 * xl;
+            *reinterpret_cast<float2*>(o) = make_float2(r[0], r[1]);
+            *reinterpret_cast<float2*>(o + W) = make_float2(r[2], r[3]);
+        }
+        __syncthreads();
     }
 }
 

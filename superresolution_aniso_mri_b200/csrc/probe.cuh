@@ -73,13 +73,18 @@ halo_probe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 template <int NACC>
 __global__ void __launch_bounds__(128, 1)
 umma_rate_probe_kernel(long long* __restrict__ cycles, int N, int kc, int pitch_rows, int shift_rows, int iters,
-                       int a_advance_rows) {
+                       int a_advance_rows, int fill_random) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t done_bar;
     __shared__ uint32_t tmem_ptr;
     const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    // operands: zeros, or (fill_random) pseudo-random fp16 values in (-2, 2) -- data toggling changes the tensor-pipe power
+    for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) {
+        uint32_t h = (i + 1 + blockIdx.x * 7919u) * 2654435761u;
+        h ^= h >> 15;
+        reinterpret_cast<uint32_t*>(smem)[i] = fill_random ? ((h & 0x83FF83FFu) | 0x3C003C00u) : 0u;
+    }
     if (threadIdx.x == 0) {
         mbar_init(&done_bar, 1);
         fence_barrier_init();
@@ -100,6 +105,8 @@ umma_rate_probe_kernel(long long* __restrict__ cycles, int N, int kc, int pitch_
         uint32_t d[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) d[j] = tmem_base + (j % NACC) * N;
+        long long g0, g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
         const long long t0 = clock64();
         for (int i = 0; i < iters; i += 8) {            // 8 MMAs per trip: loop overhead amortised
             if (elect_one_sync()) {
@@ -112,7 +119,11 @@ umma_rate_probe_kernel(long long* __restrict__ cycles, int N, int kc, int pitch_
         __syncwarp();
         mbar_wait(&done_bar, 0);
         const long long t1 = clock64();
-        if (elect_one_sync()) cycles[0] = t1 - t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        if (elect_one_sync()) {                          // per CTA: SM cycles and wall-clock ns of the same interval
+            cycles[2 * blockIdx.x] = t1 - t0;
+            cycles[2 * blockIdx.x + 1] = g1 - g0;
+        }
     }
     tc_fence_before();
     __syncthreads();

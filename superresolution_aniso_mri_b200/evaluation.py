@@ -1,4 +1,5 @@
-"""Device-resident evaluation / data-path utilities: SSIM & PSNR per slice, percentile normalisation, pad / crop.
+"""Device-resident evaluation / data-path utilities: SSIM, PSNR, VIF and LPIPS per slice, the per-volume metric sets of
+the model-selection loop, percentile normalisation, pad / crop.
 
 Drop-ins for ``evaluate.metrics.compute_ssim_for_batch / compute_psnr_for_batch`` (evaluate/metrics.py:111-194),
 ``generate_hr_volumes.normalize_img`` (:130-133) / ``datasets.common.rescale_intensities`` (:408-417) and the crop / pad
@@ -97,6 +98,140 @@ def compute_psnr_for_batch(l_images, l_reconstructions, eval_axis=0, normalize=F
     vals = psnr[keep]
     vals = vals[np.isfinite(vals)]
     return float(np.mean(vals))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# VIF (evaluate/vifvec.py:7-63 through evaluate/metrics.py:65-108) and LPIPS as a metric (evaluate/metrics.py:210-242)
+# ------------------------------------------------------------------------------------------------------------------
+VIF_SIGMA_NSQ = 2.0
+_VIF_FILTERS = {}
+
+
+def _vif_filters(device):
+    """The four gaussian kernels of vifp_mscale (N = 17, 9, 5, 3 -> sd = N/5, radius int(4 sd + .5)), formed on the host
+    exactly like scipy.ndimage._filters._gaussian_kernel1d, concatenated on the device."""
+    key = str(device)
+    if key not in _VIF_FILTERS:
+        ws, radii = [], []
+        for scale in range(1, 5):
+            sd = (2 ** (4 - scale + 1) + 1) / 5.0
+            lw = int(4.0 * float(sd) + 0.5)
+            x = np.arange(-lw, lw + 1)
+            phi = np.exp(-0.5 / (sd * sd) * x ** 2)
+            ws.append(phi / phi.sum())
+            radii.append(lw)
+        _VIF_FILTERS[key] = (torch.from_numpy(np.concatenate(ws)).to(device), np.asarray(radii, dtype=np.int32))
+    return _VIF_FILTERS[key]
+
+
+def vif_slices(true_vol, test_vol, device="cuda:0") -> np.ndarray:
+    """Per-slice pixel-domain multi-scale VIF of two fp32 [Z,H,W] volumes in [0,1], exactly as the reference computes it
+    on np.uint8(np.clip(x * 255, 0, 255)) slices -> float64 [Z] (nan where the denominator is 0, e.g. black slices)."""
+    a = _as_dev_f32(true_vol, device).squeeze()
+    b = _as_dev_f32(test_vol, device).squeeze()
+    if a.dim() == 2:
+        a, b = a[None], b[None]
+    assert a.shape == b.shape and a.dim() == 3
+    lib = _dev(a)
+    z, h, w = a.shape
+    st = _stream(a)
+    a8 = torch.empty((z, h, w), dtype=torch.uint8, device=a.device)
+    b8 = torch.empty((z, h, w), dtype=torch.uint8, device=a.device)
+    _lib.check(lib.aesr_vif_quantize_u8(a.data_ptr(), a8.data_ptr(), a.numel(), st), "vif_quantize_u8")
+    _lib.check(lib.aesr_vif_quantize_u8(b.data_ptr(), b8.data_ptr(), b.numel(), st), "vif_quantize_u8")
+    wts, radii = _vif_filters(a.device)
+    ws = torch.empty(int(lib.aesr_vif_workspace_bytes(z, h, w)), dtype=torch.uint8, device=a.device)
+    nd = torch.empty((z, 2), dtype=torch.float64, device=a.device)
+    _lib.check(lib.aesr_vif_mscale(a8.data_ptr(), b8.data_ptr(), z, h, w, wts.data_ptr(), radii.ctypes.data,
+                                   float(VIF_SIGMA_NSQ), ws.data_ptr(), ws.numel(), nd.data_ptr(), st), "vif_mscale")
+    nd = nd.cpu().numpy()
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(nd[:, 1] != 0, nd[:, 0] / nd[:, 1], np.nan)
+
+
+def compute_vif_for_batch(l_images, l_reconstructions, eval_axis=0, normalize=False, downsample_steps=None,
+                          conv_interpol=False, device="cuda:0"):
+    """evaluate/metrics.py:65-108 (eval_axis=0): mean VIF over the non-original slices, nan / inf dropped."""
+    if eval_axis != 0 or normalize:
+        raise NotImplementedError("aesr_b200: eval_axis != 0 / normalize=True are outside the hot path")
+    vif = vif_slices(l_images, l_reconstructions, device=device)
+    skip = original_slice_ids(len(vif), downsample_steps, conv_interpol) if downsample_steps else []
+    vals = vif[np.setdiff1d(np.arange(len(vif)), skip)]
+    vals = vals[np.isfinite(vals)]
+    with np.errstate(invalid="ignore"):
+        return float(np.mean(vals)) if vals.size else float("nan")
+
+
+def compute_lpips_for_batch(l_images, l_reconstructions, eval_axis=0, normalize=False, downsample_steps=None,
+                            conv_interpol=False, criterion=None, device="cuda:0"):
+    """evaluate/metrics.py:210-242 (eval_axis=0): mean over the non-original slices of
+    ``criterion(image_slice, recon_slice, normalize=True)`` -- here ONE batched pass of the sm_100a LPIPS-VGG forward
+    (the reference loops over slices; the distance is per image, so batching cannot change a value)."""
+    if eval_axis != 0 or normalize:
+        raise NotImplementedError("aesr_b200: eval_axis != 0 / normalize=True are outside the hot path")
+    if criterion is None:
+        from .lpips_b200 import PerceptualLoss
+        criterion = PerceptualLoss(model="net-lin", net="vgg", device=device)
+    a = _as_dev_f32(l_images, device).squeeze()
+    b = _as_dev_f32(l_reconstructions, device).squeeze()
+    if a.dim() == 2:
+        a, b = a[None], b[None]
+    skip = original_slice_ids(a.shape[0], downsample_steps, conv_interpol) if downsample_steps else []
+    keep = torch.from_numpy(np.setdiff1d(np.arange(a.shape[0]), skip)).to(a.device)
+    vals = criterion(a[keep][:, None].contiguous(), b[keep][:, None].contiguous(), normalize=True)
+    return float(np.mean(vals.reshape(-1).cpu().numpy().astype(np.float64)))
+
+
+def compute_mean_metrics(ssim_results, psnr_results, vif_results, lpips_results, compute_percept_loss=False):
+    """evaluate/create_HR_images.py:110-118."""
+    out = []
+    for r in (ssim_results, psnr_results, vif_results):
+        out += [np.mean(np.array(r)), np.std(np.array(r))]
+    if compute_percept_loss:
+        out += [np.mean(np.array(lpips_results)), np.std(np.array(lpips_results))]
+    else:
+        out += [0, 0]
+    return tuple(out)
+
+
+def compute_metrics(images_ref, new_images, downsample_steps, ssim_results, psnr_results, vif_results, lpips_results,
+                    ssim_res_synth=None, psnr_res_synth=None, vif_res_synth=None, lpips_res_synth=None,
+                    ssim_res_recon=None, psnr_res_recon=None, vif_res_recon=None, lpips_res_recon=None,
+                    compute_percept_loss=False, percept_loss=None, normalize=False, eval_axis=0, device="cuda:0"):
+    """evaluate/create_HR_images.py:121-178, same signature and list side effects.  Per volume: SSIM / PSNR / VIF (and
+    LPIPS on request) over all slices up to the last synthesised pair, over the synthesised slices only and over the
+    reconstructed ones only (the masked LPIPS lists stay empty exactly like the reference, :172,177).  The per-slice
+    values of SSIM, PSNR and VIF are computed ONCE on the device for the whole volume; the three slice sets are masks
+    over them (each metric is per slice, so the subsets see the same numbers as three separate reference calls)."""
+    if eval_axis != 0 or normalize:
+        raise NotImplementedError("aesr_b200: eval_axis != 0 / normalize=True are outside the hot path")
+    a = _as_dev_f32(images_ref, device).squeeze()
+    b = _as_dev_f32(new_images, device).squeeze()
+    last = ((a.shape[0] - 1) // downsample_steps) * downsample_steps + 1
+    r_mask, s_mask = synth_slices_mask(a.shape[0], downsample_steps)
+    a, b = a[:last].contiguous(), b[:last].contiguous()
+    ssim, psnr = ssim_psnr_slices(a, b, device=device)
+    vif = vif_slices(a, b, device=device)
+
+    def finite_mean(v):
+        v = v[np.isfinite(v)]
+        with np.errstate(invalid="ignore"):
+            return float(np.mean(v)) if v.size else float("nan")
+
+    def push(mask, l_ssim, l_psnr, l_vif):
+        l_ssim.append(float(np.mean(ssim[mask])))
+        l_psnr.append(finite_mean(psnr[mask]))
+        l_vif.append(finite_mean(vif[mask]))
+
+    push(np.ones(last, dtype=bool), ssim_results, psnr_results, vif_results)
+    if compute_percept_loss:
+        lpips_results.append(compute_lpips_for_batch(a, b, criterion=percept_loss, device=device))
+    if ssim_res_synth is not None:
+        push(s_mask, ssim_res_synth, psnr_res_synth, vif_res_synth)
+    if ssim_res_recon is not None:
+        push(r_mask, ssim_res_recon, psnr_res_recon, vif_res_recon)
+    return (ssim_results, psnr_results, vif_results, lpips_results, ssim_res_synth, psnr_res_synth, vif_res_synth,
+            lpips_res_synth, ssim_res_recon, psnr_res_recon, vif_res_recon, lpips_res_recon)
 
 
 def normalize_img(img, perc=(1, 99), device="cuda:0", return_percentiles: bool = False):

@@ -216,6 +216,11 @@ class VanillaACAI(nn.Module):
         return self._cache.get(("head_host", id(conv)), [conv.weight],
                                lambda: conv.weight.detach()[0].permute(1, 2, 0).reshape(9, -1).float().cpu().contiguous())
 
+    def _head_w16(self, conv: ConvHolder):
+        """16-bit [16,32] head filter on the device (tensor-core head inside the fused decoder tail)."""
+        return self._cache.get(("head16", id(conv), ops.DEFAULT_DTYPE), [conv.weight],
+                               lambda: ops.pack_head_w16(conv.weight.detach()[0].permute(1, 2, 0).reshape(9, -1).float()))
+
     def _head_w(self, conv: ConvHolder):
         def build():
             with torch.no_grad():
@@ -298,7 +303,8 @@ class VanillaACAI(nn.Module):
             i += 6
         c1, c2 = dec[i], dec[i + 2]
         w9c, b = self._head_w(c2)
-        part = ops.conv3x3_up2_head(a, self._packed_up2(c1), c1.bias.detach(), self._head_w_host(c2), act=ops.ACT_LEAKY)
+        part = ops.conv3x3_up2_head(a, self._packed_up2(c1), c1.bias.detach(), self._head_w_host(c2), act=ops.ACT_LEAKY,
+                                    head_w16=self._head_w16(c2) if ops.HEAD_ON_TENSOR_CORES else None)
         return ops.head_gather(part, b, out=out, out_image_stride=out_image_stride, sigmoid=True, out_index=out_index)
 
     @torch.no_grad()

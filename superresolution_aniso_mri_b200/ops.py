@@ -136,24 +136,41 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
     return (out, out2) if out2 is not None else out
 
 
+# Decoder head conv inside the fused tail: False (default) = CUDA cores, fp32 activations and filter; True = tensor cores
+# (activations written back to tensor memory as a 16-bit A operand).  Measured equal within 1 % on B200 (the tile is
+# bound by reading its 64 KB accumulator out of TMEM either way, profiles/README.md), so the more exact one is the default.
+HEAD_ON_TENSOR_CORES = os.environ.get("AESR_HEAD_TC", "0") != "0"
+
+
+def pack_head_w16(head_w9c: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """fp32 [9,32] head filter (any device) -> 16-bit [16,32] on its device, rows 9..15 zero (GEMM N padded to 16)."""
+    dtype = dtype or DEFAULT_DTYPE
+    out = torch.zeros((16, 32), dtype=dtype, device=head_w9c.device)
+    out[:9] = head_w9c.to(dtype)
+    return out
+
+
 def conv3x3_up2_head(x: torch.Tensor, w_folded: torch.Tensor, bias: torch.Tensor, head_w9c: torch.Tensor,
                      act: int = ACT_LEAKY, slope: float = LEAKY_SLOPE, out: Optional[torch.Tensor] = None,
-                     algo: int = ALGO_AUTO) -> torch.Tensor:
+                     algo: int = ALGO_AUTO, head_w16: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Upsample(2) -> Conv2d(Cin,32,3,p=1)+act -> Conv2d(32,1,3,p=1) partial sums: x NHWC 16-bit [N,H,W,Cin] (low-res)
-    -> fp32 [N,H,W,16] patches for ``head_gather``.  ``head_w9c``: fp32 [9,32] on the HOST."""
+    -> fp32 [N,H,W,16] patches for ``head_gather``.  ``head_w9c``: fp32 [9,32] on the HOST; ``head_w16``: the same
+    filter as 16-bit [16,32] on the device (``pack_head_w16``) -> the head conv runs on the tensor cores."""
     lib = _dev(x)
     assert x.is_contiguous() and x.dim() == 4 and x.dtype == w_folded.dtype
     n, h, w, cin = x.shape
     assert w_folded.shape == (9, 128, cin) and w_folded.is_contiguous() and head_w9c.shape == (9, 32)
     # the head filter travels as a kernel parameter (constant bank): it must be HOST memory
     assert not head_w9c.is_cuda and head_w9c.dtype == torch.float32 and head_w9c.is_contiguous()
+    if head_w16 is not None:
+        assert head_w16.is_cuda and head_w16.shape == (16, 32) and head_w16.dtype == x.dtype and head_w16.is_contiguous()
     if out is None:
         out = torch.empty((n, h, w, 16), dtype=torch.float32, device=x.device)
     with _timed("conv3x3", 2.0 * n * h * w * 9 * cin * 128 + 2.0 * n * 4 * h * w * 9 * 32,
                 "%d->128+head n%d %dx%d" % (cin, n, h, w)):
         _lib.check(lib.aesr_conv3x3_up2_head_fwd(x.data_ptr(), w_folded.data_ptr(), bias.data_ptr(), head_w9c.data_ptr(),
-                                                 out.data_ptr(), n, h, w, cin, int(act), float(slope), dt_code(x.dtype),
-                                                 int(algo), _stream(x)), "conv3x3_up2_head_fwd")
+                                                 _ptr(head_w16), out.data_ptr(), n, h, w, cin, int(act), float(slope),
+                                                 dt_code(x.dtype), int(algo), _stream(x)), "conv3x3_up2_head_fwd")
     return out
 
 

@@ -124,9 +124,14 @@ def synthesize_volumes(model, volumes: torch.Tensor, alpha_range: Sequence[float
 class HostPipeline:
     """Host-buffer entry point for batched synthesis: pinned host volumes [V,Z,H,W] in, HR volumes
     [V,(Z-1)(A+1)+1,H,W] back in pinned host memory.  The V volumes are cut into groups; group g+1's host->device copy
-    and group g-1's device->host copy run on their own streams while group g computes (double-buffered staging)."""
+    and group g-1's device->host copy run on their own streams while group g computes (double-buffered staging).
 
-    def __init__(self, model, V, Z, H, W, alpha_range, groups: int = 4, chunk: int = 4096):
+    ``run(..., wait=True)`` (default) returns stream-ordered: the caller's stream has waited for the last device->host
+    copy.  A caller that feeds a sequence of batches passes ``wait=False`` and calls ``wait()`` (or ``synchronize()``)
+    once at the end: the staging buffers and their events persist across calls, so the copies of batch i overlap the
+    compute of batch i+1 and the only serial parts left are the first upload and the last download."""
+
+    def __init__(self, model, V, Z, H, W, alpha_range, groups: int = 2, chunk: int = 4096):
         self.model, self.ar, self.chunk = model, list(alpha_range), chunk
         dev = next(model.parameters()).device
         self.dev = dev
@@ -141,12 +146,13 @@ class HostPipeline:
         self.in_free = [torch.cuda.Event() for _ in range(2)]     # compute finished reading d_in[b]
         self.out_free = [torch.cuda.Event() for _ in range(2)]    # copy-out finished reading d_out[b]
         self.used = [False, False]
+        self.turn = 0                                             # staging buffer of the next group (persists over calls)
 
-    def run(self, host_in: torch.Tensor, host_out: torch.Tensor) -> None:
+    def run(self, host_in: torch.Tensor, host_out: torch.Tensor, wait: bool = True) -> None:
         main = torch.cuda.current_stream(self.dev)
-        last_copy = None
-        for g, (s, e) in enumerate(self.bounds):
-            b = g & 1
+        for (s, e) in self.bounds:
+            b = self.turn
+            self.turn ^= 1
             n = e - s
             with torch.cuda.stream(self.s_in):
                 if self.used[b]:
@@ -167,12 +173,21 @@ class HostPipeline:
                 host_out[s:e].copy_(self.d_out[b][:n], non_blocking=True)
                 self.out_free[b].record(self.s_out)
             self.used[b] = True
-            last_copy = self.out_free[b]
-        # the call returns stream-ordered on the caller's stream: results are in host_out once `main` passes this point
-        if last_copy is not None:
-            for b in range(2):
-                if self.used[b]:
-                    main.wait_event(self.out_free[b])
+        if wait:
+            self.wait()
+
+    def wait(self) -> None:
+        """Make the caller's current stream wait for every device->host copy issued so far (stream-ordered return)."""
+        main = torch.cuda.current_stream(self.dev)
+        for b in range(2):
+            if self.used[b]:
+                main.wait_event(self.out_free[b])
+
+    def synchronize(self) -> None:
+        """Block the host until every result issued so far is in host memory."""
+        for b in range(2):
+            if self.used[b]:
+                self.out_free[b].synchronize()
 
 
 @torch.no_grad()
@@ -194,8 +209,10 @@ def latent_space_interp(alpha, trainer, img1, img2, device="cuda", with_labels=F
 
 
 @torch.no_grad()
-def create_super_volume(trainer, images: torch.Tensor, alpha_range, use_original: bool = False, labels=None) -> dict:
-    """generate_hr_volumes.py:12-69: images [Z,1,H,W] or [Z,H,W] -> {'upsampled_image': [(Z-1)(A+1)+1,H,W] (CPU)}."""
+def create_super_volume(trainer, images: torch.Tensor, alpha_range, use_original: bool = False, labels=None,
+                        keep_on_device: bool = False) -> dict:
+    """generate_hr_volumes.py:12-69: images [Z,1,H,W] or [Z,H,W] -> {'upsampled_image': [(Z-1)(A+1)+1,H,W] (CPU; on the
+    model's device with ``keep_on_device``, for callers that score the volume with the device metrics)}."""
     if labels is not None:
         raise NotImplementedError("aesr_b200: label volumes belong to the multi-channel model family")
     model = _model_of(trainer)
@@ -205,14 +222,14 @@ def create_super_volume(trainer, images: torch.Tensor, alpha_range, use_original
     vol = images.float().to(dev).unsqueeze(0)
     # the final torch.clamp(0, 1) of the reference (:67) is applied inside the kernels that write `out`
     out = synthesize_volumes(model, vol, alpha_range, use_original=use_original)[0]
-    return {"upsampled_image": out.cpu(), "upsampled_labels": None}
+    return {"upsampled_image": out if keep_on_device else out.cpu(), "upsampled_labels": None}
 
 
 @torch.no_grad()
 def create_super_volume_eval(trainer, images: torch.Tensor, alpha_range=None, use_original: bool = False,
                              hierarchical: bool = False, downsample_steps: Optional[int] = None,
                              generate_inbetween_slices: bool = False, train_patch_size=None, feature_dict=None,
-                             labels=None) -> dict:
+                             labels=None, keep_on_device: bool = False) -> dict:
     """evaluate/common.py:134-235: optional slice dropping images[::d] after trimming (Z-1) % d tail slices, tail
     re-appended untouched."""
     if labels is not None or hierarchical:
@@ -227,11 +244,11 @@ def create_super_volume_eval(trainer, images: torch.Tensor, alpha_range=None, us
         images = images[::downsample_steps]
     if alpha_range is None:
         alpha_range = [0.25, 0.5, 0.75]
-    res = create_super_volume(trainer, images, alpha_range, use_original=use_original)
+    res = create_super_volume(trainer, images, alpha_range, use_original=use_original, keep_on_device=keep_on_device)
     new_volume = res["upsampled_image"]
     if generate_inbetween_slices and (orig_num - 1) % downsample_steps != 0:
         remain = (orig_num - 1) % downsample_steps
-        tail = orig_images[-remain:].float().cpu()
+        tail = orig_images[-remain:].float().to(new_volume.device)
         if tail.dim() == 4:
             tail = tail[:, 0]
         new_volume = torch.cat([new_volume, torch.clamp(tail, 0, 1.)])

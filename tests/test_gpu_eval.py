@@ -1,4 +1,6 @@
 """GPU tier: evaluation / data-path kernels (SSIM, PSNR, percentile normalisation, pad/crop) against the oracle."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -81,3 +83,141 @@ def test_pad_crop_transforms(cuda_lib):
     for b in range(4):
         top, left = O.random_crop_offsets(rs2, 160, 160, 128)
         np.testing.assert_array_equal(rc[b], sq[b, :, top:top + 128, left:left + 128])
+
+
+# ------------------------------------------------------------------------------------------------ VIF / metric sets
+def _vif_cases():
+    import scipy.ndimage                                               # inputs only (same construction as gold_vif)
+    rs = np.random.RandomState(11)
+    for (h, w) in ((37, 53), (128, 128), (16, 9)):                     # advance the stream like oracle/make_golden.py
+        rs.randint(0, 256, size=(h, w))
+    vol = O.smooth_phantom(6, 128, seed=2)[:, 0].numpy()
+    noise = rs.normal(0, 0.05, vol.shape).astype(np.float32)
+    blurred = scipy.ndimage.gaussian_filter(vol, (0, 1.5, 1.5)).astype(np.float32)
+    cases = {"noisy": np.clip(vol + noise, 0, 1).astype(np.float32), "blurred": blurred, "same": vol.copy(),
+             "black": np.zeros_like(vol)}
+    return rs, vol, cases
+
+
+def test_vif_matches_reference_golden_and_oracle(cuda_lib, golden):
+    """VIF on the device against the REFERENCE's own vifp_mscale outputs (tests/golden/vif_pins.npz) and the oracle:
+    the uint8 planes are integer work (bit-exact), the final ratio is float64 (summation order differs: 1e-9)."""
+    from superresolution_aniso_mri_b200 import evaluation as E
+    g = golden("vif_pins.npz")
+    rs, vol, cases = _vif_cases()
+    for name, dist in cases.items():
+        got = E.vif_slices(vol, dist)
+        want = g["vif_" + name]
+        assert got.shape == want.shape
+        assert np.array_equal(np.isnan(got), np.isnan(want)), name
+        ok = ~np.isnan(want)
+        assert np.all(np.abs(got[ok] - want[ok]) <= 1e-9 * np.maximum(1.0, np.abs(want[ok]))), (name, got, want)
+    from evaluate.metrics import compute_vif_for_batch
+    for ds in (None, 2, 3):
+        got = compute_vif_for_batch(vol, cases["noisy"], downsample_steps=ds)
+        assert abs(got - float(g["vif_batch_ds%s" % ds])) < 1e-9
+    big = rs.rand(2, 220, 220).astype(np.float32)
+    big2 = np.clip(big + rs.normal(0, 0.1, big.shape), 0, 1).astype(np.float32)
+    assert np.all(np.abs(E.vif_slices(big, big2) - g["vif_220"]) < 1e-9)
+    rect = rs.rand(2, 45, 77).astype(np.float32)
+    rect2 = np.clip(rect * 0.8 + 0.1, 0, 1).astype(np.float32)
+    assert np.all(np.abs(E.vif_slices(rect, rect2) - g["vif_rect"]) < 1e-9)
+    # tiny slices (filter radius > size: repeated reflection) and a flat non-zero image against the oracle
+    tiny = rs.rand(3, 9, 5).astype(np.float32)
+    tiny2 = np.clip(tiny + 0.1, 0, 1).astype(np.float32)
+    flat = np.full((1, 40, 40), 100 / 255.0 + 1e-4, dtype=np.float32)
+    for a, b in ((tiny, tiny2), (flat, np.clip(flat * 0.9, 0, 1).astype(np.float32))):
+        got = E.vif_slices(a, b)
+        for z in range(a.shape[0]):
+            with np.errstate(divide="ignore", invalid="ignore"):
+                want = O.vifp_mscale_u8(O.quantize_u8(a[z]), O.quantize_u8(b[z]))
+            assert (np.isnan(want) and np.isnan(got[z])) or abs(got[z] - want) < 1e-9
+
+
+def test_compute_metrics_sets_match_oracle(cuda_lib):
+    """evaluate/create_HR_images.py::compute_metrics: all / synthesised / reconstructed slice sets of one volume."""
+    from evaluate.create_HR_images import compute_mean_metrics, compute_metrics
+    rng = np.random.RandomState(4)
+    ref = O.smooth_phantom(11, 64, seed=5)[:, 0].numpy()
+    new = np.clip(ref + 0.04 * rng.randn(*ref.shape).astype(np.float32), 0, 1).astype(np.float32)
+    new[::3] = ref[::3] * 0.98                                          # "reconstructed" slices are closer
+    for ds in (2, 3):
+        lists = [[] for _ in range(12)]
+        out = compute_metrics(ref, new, ds, *lists)
+        want = O.compute_metrics(ref, new, ds)
+        names = ("ssim", "psnr", "vif", "lpips")
+        for k, tag in enumerate(("", "_synth", "_recon")):
+            for j, nm in enumerate(names[:3]):
+                got = out[4 * k + j]
+                assert len(got) == 1
+                tol = 1e-6 if nm == "ssim" else (1e-4 if nm == "psnr" else 1e-9)
+                assert abs(got[0] - want[nm + tag]) < tol, (ds, nm + tag, got[0], want[nm + tag])
+            assert out[4 * k + 3] == []                               # LPIPS lists stay empty without compute_percept_loss
+    m = compute_mean_metrics([0.5, 0.7], [20.0, 30.0], [0.2, 0.4], [])
+    assert m[:6] == (np.mean([0.5, 0.7]), np.std([0.5, 0.7]), 25.0, 5.0, np.mean([0.2, 0.4]), np.std([0.2, 0.4]))
+    assert m[6:] == (0, 0)
+
+
+def test_lpips_metric_batched_equals_per_slice(cuda_lib):
+    """evaluate/metrics.py::compute_lpips_for_batch: mean of per-slice distances; one batched pass == slice by slice."""
+    from superresolution_aniso_mri_b200.lpips_b200 import PerceptualLoss
+    from evaluate.metrics import compute_lpips_for_batch
+    from oracle.make_golden import acdc_batch  # noqa: F401  (import check only: fixtures share the generator)
+    dev = torch.device("cuda:0")
+    crit = PerceptualLoss(vgg_state=[t for pair in O.init_vgg(3) for t in pair], device=dev)
+    rng = np.random.RandomState(6)
+    ref = O.smooth_phantom(7, 64, seed=7)[:, 0].numpy()
+    rec = np.clip(ref + 0.05 * rng.randn(*ref.shape).astype(np.float32), 0, 1).astype(np.float32)
+    for ds in (None, 3):
+        got = compute_lpips_for_batch(ref, rec, downsample_steps=ds, criterion=crit)
+        skip = set(O.determine_original_sliceids(7, ds).tolist()) if ds else set()
+        per = [crit(torch.from_numpy(rec[z])[None, None].to(dev), torch.from_numpy(ref[z])[None, None].to(dev),
+                    normalize=True).item() for z in range(7) if z not in skip]
+        # the reference calls criterion(image_slice, recon_slice): LPIPS-VGG is symmetric up to rounding
+        assert abs(got - float(np.mean(per))) < 2e-3 * max(1.0, abs(got))
+
+
+def test_find_best_val_model_end_to_end(cuda_lib, tmp_path):
+    """evaluate/find_best_model.py::find_best_val_model over an experiment directory with two checkpoints
+    (settings.yaml + models/<epoch>.models resolved through get_trainer_dynamic): per-checkpoint mean SSIM / PSNR / VIF of
+    the device loop against the oracle (reference synthesis + reference metrics on the CPU), result files written."""
+    import yaml
+    from evaluate.find_best_model import find_best_val_model, load_model_scores
+    from kwatsch.get_trainer import get_trainer_dynamic
+    from networks.net_config import NetworkConfig
+    exper = str(tmp_path / "exper")
+    os.makedirs(os.path.join(exper, "models"))
+    args = dict(NetworkConfig("ae_combined", "ACDC").architecture)
+    args.update(dataset="ACDC", model="ae_combined", ae_class="VanillaACAI", width=64, latent_width=16, latent=128,
+                depth=32, lr=1e-5, weight_decay=0.0, epochs=10, device="cuda:0", gpu_ids=[0], ex_loss_weight1=0.05,
+                use_percept_loss=False, use_loss_annealing=False, get_masks=False, epoch_threshold=0,
+                log_tensorboard=False, batch_size=4, downsample_steps=2, output_dir=exper, dir_models=os.path.join(exper, "models"))
+    with open(os.path.join(exper, "settings.yaml"), "w") as fp:
+        yaml.dump(args, fp)
+    oargs = O.default_args(64, 16)
+    states = {1: O.calibrated_state(oargs, calib_seed=5), 2: O.calibrated_state(oargs, seed=1234, calib_seed=9)}
+    torch.manual_seed(0)
+    tr = get_trainer_dynamic(dict(args))
+    for ep, st in states.items():
+        tr.model.load_state_dict(st)
+        tr.save_models(os.path.join(exper, "models", "%d.models" % ep), ep)
+    vols = {i: {"image": (0.8 * O.smooth_phantom(7, 64, seed=20 + i) + 0.2 * O.synthetic_volume(7, 64, seed=30 + i))[:, 0].numpy(),
+                "patient_id": "p%d" % i, "spacing": np.array([5.0, 1.0, 1.0]), "frame_id": 4} for i in range(2)}
+    scores = find_best_val_model(vols, exper, epoch_range=[1, 2], ps_evaluate=64, downsample_steps=2)
+    assert list(scores) == ["1", "2"]
+    assert os.path.exists(os.path.join(exper, "model_perf_1_to_2_axis0.npz"))
+    assert os.path.exists(os.path.join(exper, "model_perf_synth_1_to_2_axis0.npz"))
+    loaded = load_model_scores(exper)
+    assert sorted(loaded[1].tolist()) == [1, 2]
+    for ep, st in states.items():
+        per = []
+        for v in vols.values():
+            img = torch.from_numpy(v["image"])
+            new = O.create_super_volume_eval(st, oargs, img[:, None], alpha_range=O.alpha_range_for(1), use_original=False,
+                                             downsample_steps=2, generate_inbetween_slices=True)
+            per.append(O.compute_metrics(v["image"], new.numpy(), 2))
+        want = np.array([np.mean([p[k] for p in per]) for k in ("ssim", "psnr", "vif")])
+        got = scores[str(ep)]
+        # synthesized slices carry the 16-bit activation noise of the stress checkpoint (<= 6e-2 max-abs, see the parity
+        # tests); spec deltas are 1e-3 SSIM / 0.05 dB PSNR on the random-init checkpoint
+        assert abs(got[0] - want[0]) < 3e-3 and abs(got[1] - want[1]) < 0.15 and abs(got[2] - want[2]) < 0.03, (ep, got, want)

@@ -253,8 +253,10 @@ def test_upsample_folded_conv_vs_torch(dev, case, dtype):
     assert (got.float().permute(0, 3, 1, 2).cpu() - want).abs().max().item() <= tol
 
 
-@pytest.mark.parametrize("case", [(32, 2, 64, 64), (32, 3, 20, 12), (64, 1, 16, 16), (32, 1, 1, 1), (32, 1, 17, 9)])
-def test_decoder_tail_fused_head_vs_torch(dev, case):
+@pytest.mark.parametrize("head_tc", [True, False])
+@pytest.mark.parametrize("case", [(32, 2, 64, 64), (32, 3, 20, 12), (64, 1, 16, 16), (32, 1, 1, 1), (32, 1, 17, 9),
+                                  (32, 40, 64, 64)])
+def test_decoder_tail_fused_head_vs_torch(dev, case, head_tc):
     """Upsample -> Conv2d(Cin,32)+LeakyReLU -> Conv2d(32,1) -> Sigmoid (networks/acai_vanilla.py:92,96-98) as one tensor
     core kernel (head partial sums in the epilogue, fp32 activations never stored) + head_gather, scattered into a
     larger volume."""
@@ -267,8 +269,11 @@ def test_decoder_tail_fused_head_vs_torch(dev, case):
     b = (torch.randn(32, generator=g) * 0.1).to(dev)
     wh = torch.randn(1, 32, 3, 3, generator=g) / 17
     bh = torch.tensor([0.3])
-    part = ops.conv3x3_up2_head(x, ops.pack_conv3x3_weight_up2fold(wt, dtype=dt), b,
-                                wh[0].permute(1, 2, 0).reshape(9, 32).contiguous())       # host tensor (kernel parameter)
+    w9c = wh[0].permute(1, 2, 0).reshape(9, 32).contiguous()                              # host tensor (kernel parameter)
+    # head_tc: the head conv runs on the tensor cores from 16-bit activations / a 16-bit filter (A operand in TMEM);
+    # otherwise on the CUDA cores in fp32.  Same bounds for both (the logits are O(1), fp16 has 11 bits).
+    part = ops.conv3x3_up2_head(x, ops.pack_conv3x3_weight_up2fold(wt, dtype=dt), b, w9c,
+                                head_w16=ops.pack_head_w16(w9c.to(dev), dtype=dt) if head_tc else None)
     out = torch.full((n + 3, 2 * h, 2 * w), -1.0, device=dev)
     idx = torch.arange(n, dtype=torch.int32, device=dev) + 2
     ops.head_gather(part, bh.to(dev), out=out, out_image_stride=4 * h * w, out_index=idx)
@@ -447,6 +452,14 @@ def test_host_pipeline_matches_device_path(dev):
     torch.cuda.synchronize()
     want = synthesis.synthesize_volumes(model, host_in.to(dev), ar).cpu()
     assert torch.equal(host_out, want)
+    # a sequence of batches without waiting in between: copies of batch i overlap the compute of batch i+1
+    host_in2 = torch.rand(5, 10, 128, 128, generator=torch.Generator().manual_seed(7)).pin_memory()
+    outs = [torch.empty(5, 64, 128, 128).pin_memory() for _ in range(3)]
+    for o, hi in zip(outs, (host_in, host_in2, host_in)):
+        pipe.run(hi, o, wait=False)
+    pipe.synchronize()
+    want2 = synthesis.synthesize_volumes(model, host_in2.to(dev), ar).cpu()
+    assert torch.equal(outs[0], want) and torch.equal(outs[1], want2) and torch.equal(outs[2], want)
 
 
 @pytest.mark.parametrize("cin,cout,hw,mode", [(256, 256, 32, 0), (256, 512, 16, 0), (128, 128, 64, 4), (32, 32, 130, 1),

@@ -171,3 +171,31 @@ def test_ssim_psnr_properties():
     f = O._uniform_filter_reflect(a.astype(np.float64), 7)
     p = np.pad(a.astype(np.float64), 3, mode="symmetric")
     assert abs(f[10, 20] - p[10:17, 20:27].mean()) < 1e-12 and abs(f[0, 0] - p[0:7, 0:7].mean()) < 1e-12
+
+
+def test_vif_oracle_against_reference_golden(golden):
+    """tests/golden/vif_pins.npz holds outputs of the REFERENCE's evaluate/vifvec.py::vifp_mscale and
+    evaluate/metrics.py::compute_vif_for_batch (oracle/make_golden.py::gold_vif, which also asserts every uint8 plane of
+    the restated gaussian filter equal to scipy.ndimage's): the oracle reproduces them."""
+    import scipy.ndimage
+    g = golden("vif_pins.npz")
+    rs = np.random.RandomState(11)
+    for (h, w) in ((37, 53), (128, 128), (16, 9)):
+        a = rs.randint(0, 256, size=(h, w)).astype(np.uint8)
+        a[: h // 3, : w // 2] = 100
+        for sd in (3.4, 1.8, 1.0, 0.6):
+            np.testing.assert_array_equal(O.gaussian_filter_u8(a, sd), scipy.ndimage.gaussian_filter(a, sd))
+    vol = O.smooth_phantom(6, 128, seed=2)[:, 0].numpy()
+    noise = rs.normal(0, 0.05, vol.shape).astype(np.float32)
+    noisy = np.clip(vol + noise, 0, 1).astype(np.float32)
+    for z in (0, 3, 5):
+        v = O.vifp_mscale_u8(O.quantize_u8(vol[z]), O.quantize_u8(noisy[z]))
+        assert abs(v - g["vif_noisy"][z]) < 1e-12
+    with np.errstate(divide="ignore", invalid="ignore"):
+        assert abs(O.vifp_mscale_u8(O.quantize_u8(vol[1]), O.quantize_u8(vol[1])) - g["vif_same"][1]) < 1e-12
+        assert np.isnan(O.vifp_mscale_u8(O.quantize_u8(vol[1]), O.quantize_u8(np.zeros_like(vol[1])))) == np.isnan(g["vif_black"][1])
+    for ds in (None, 2, 3):
+        assert abs(O.compute_vif_for_batch(vol, noisy, downsample_steps=ds) - float(g["vif_batch_ds%s" % ds])) < 1e-12
+    m = O.compute_metrics(vol, noisy, 2)
+    assert set(m) == {"ssim", "psnr", "vif", "ssim_synth", "psnr_synth", "vif_synth", "ssim_recon", "psnr_recon", "vif_recon"}
+    assert O.determine_last_slice(11, 3) == 9 and O.determine_last_slice(10, 3) == 9

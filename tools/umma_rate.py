@@ -1,4 +1,8 @@
-"""tcgen05.mma cost vs operand layout and accumulator rotation (diagnostic): cycles per MMA (M=128, K=16, fp16)."""
+"""tcgen05.mma cost vs operand layout, accumulator rotation, number of concurrently issuing SMs and operand data
+(diagnostic): SM cycles per MMA (M=128, K=16, fp16) and wall-clock ns per MMA (=> effective SM clock).
+
+  python tools/umma_rate.py [--full]
+"""
 import os
 import sys
 
@@ -8,16 +12,30 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from superresolution_aniso_mri_b200 import _lib  # noqa: E402
 
 lib = _lib.lib_for_device(0)
-out = torch.zeros(1, dtype=torch.int64, device="cuda:0")
-iters = 2000
-print("kc  N  nacc pitch shift adv : cycles/MMA")
+out = torch.zeros(2 * 148, dtype=torch.int64, device="cuda:0")
+iters = 20000
+full = "--full" in sys.argv
+
+
+def run(kc, N, nacc, pitch, shift, adv, grid, rnd):
+    out.zero_()
+    for _ in range(2):
+        _lib.check(lib.aesr_probe_umma_rate(out.data_ptr(), N, kc, pitch, shift, iters, adv, nacc, grid, rnd,
+                                            torch.cuda.current_stream().cuda_stream), "probe")
+    torch.cuda.synchronize()
+    r = out.view(-1, 2)[:grid].double()
+    cyc, ns = r[:, 0].max().item() / iters, r[:, 1].max().item() / iters
+    print("%2d %3d  %2d   %3d   %3d  %3d  %4d  %s : %6.1f cycles/MMA  %6.1f ns/MMA  (%4.0f MHz effective)"
+          % (kc, N, nacc, pitch, shift, adv, grid, "rand" if rnd else "zero", cyc, ns, 1e3 * cyc / ns))
+
+
+print("kc  N  nacc pitch shift adv  grid data")
 for kc in (32, 64):
     for N in (32, 64, 128, 256):
-        for nacc in (1, 2, 4, 8):
-            if nacc * N > 512:
-                continue
-            for pitch, shift, adv in ((8, 0, 0), (10, 1, 1)):
-                _lib.check(lib.aesr_probe_umma_rate(out.data_ptr(), N, kc, pitch, shift, iters, adv, nacc,
-                                                    torch.cuda.current_stream().cuda_stream), "probe")
-                torch.cuda.synchronize()
-                print("%2d %3d  %2d   %3d   %3d  %3d : %.1f" % (kc, N, nacc, pitch, shift, adv, out.item() / iters))
+        for grid in (1, 148):
+            for rnd in (0, 1):
+                run(kc, N, min(4, 512 // N), 10, 1, 1, grid, rnd)
+        if full:
+            for nacc in (1, 2, 4, 8):
+                if nacc * N <= 512:
+                    run(kc, N, nacc, 8, 0, 0, 1, 0)
