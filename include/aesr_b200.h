@@ -269,6 +269,13 @@ int aesr_probe_halo_conv(const void* x, const void* w_packed, float* out, int N,
 int aesr_probe_umma_rate(long long* cycles, int N, int kc, int pitch_rows, int shift_rows, int iters,
                          int a_advance_rows, int nacc, int grid, int fill_random, void* stream);
 
+/* Diagnostic: the MMA issue loop of the halo conv kernel in isolation (T M-tiles x 9 taps x kc/16 K-steps per super-tile,
+ * the kernel's descriptor arithmetic, no TMA, no epilogue).  variant bit 0: tcgen05.commit after every super-tile, bit 1:
+ * wait for the commit `lag` super-tiles back before issuing, bit 2: 17 more warps polling an mbarrier.
+ * cycles[2*b] = SM cycles, cycles[2*b+1] = ns for `iters` super-tiles on CTA b (tools/umma_rate.py --pattern). */
+int aesr_probe_umma_pattern(long long* cycles, int BN, int kc, int T, int iters, int variant, int lag, int grid,
+                            int fill_random, void* stream);
+
 /* Diagnostic: mbarrier round-trip latency between two warps (mode bit 0: signal with tcgen05.commit, bit 1: poll with
  * test_wait instead of try_wait, bit 2: three waiting warps).  cycles[0] = total cycles for `iters` round trips. */
 int aesr_probe_sync(long long* cycles, int iters, int mode, void* stream);

@@ -37,6 +37,7 @@ _SIGNATURES = {
     "aesr_lerp_pairs_act": (I, [P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
     "aesr_probe_halo_conv": (I, [P, P, P, I, I, I, I, I, I, I, I, P]),
     "aesr_probe_umma_rate": (I, [P, I, I, I, I, I, I, I, I, I, P]),
+    "aesr_probe_umma_pattern": (I, [P, I, I, I, I, I, I, I, I, P]),
     "aesr_probe_sync": (I, [P, I, I, P]),
     # training step
     "aesr_bn_finalize": (I, [P, F, P, P, P, P, F, F, P, P, P, P, I, P]),

@@ -633,6 +633,26 @@ int aesr_probe_umma_rate(long long* cycles, int N, int kc, int pitch_rows, int s
     return check_launch("umma_rate_probe");
 }
 
+int aesr_probe_umma_pattern(long long* cycles, int BN, int kc, int T, int iters, int variant, int lag, int grid,
+                            int fill_random, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!cycles || BN < 32 || BN > 256 || BN % 32 || (kc != 32 && kc != 64) || T < 1 || T > 4 || T * BN > 256 ||
+        iters <= 0 || lag < 1 || lag > 7 || grid < 1 || grid > 1024 || 9 * BN * kc * 2 > 148 * 1024 ||
+        (16 * T + 2) * 10 * kc * 2 > 48 * 1024)
+        return fail(AESR_ERR_INVALID, "probe_umma_pattern: bad arguments");
+    const int smem = 1024 + 196 * 1024;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (kc == 64) {
+        CUDA_TRY(cudaFuncSetAttribute(umma_pattern_probe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        umma_pattern_probe_kernel<64><<<grid, 576, smem, s>>>(cycles, BN, T, iters, variant, lag, fill_random);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(umma_pattern_probe_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        umma_pattern_probe_kernel<32><<<grid, 576, smem, s>>>(cycles, BN, T, iters, variant, lag, fill_random);
+    }
+    return check_launch("umma_pattern_probe");
+}
+
 int aesr_probe_sync(long long* cycles, int iters, int mode, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;

@@ -133,6 +133,109 @@ umma_rate_probe_kernel(long long* __restrict__ cycles, int N, int kc, int pitch_
     }
 }
 
+// Issue-pattern probe (diagnostic): the MMA issue loop of conv3x3_halo_kernel in isolation -- T M-tiles x 9 taps x KC/16
+// K-steps per "super-tile" with the kernel's descriptor arithmetic (row-shifted A per tap, one B block per tap, first MMA
+// of a tile overwrites), no TMA, no epilogue.  variant bit 0: tcgen05.commit to a barrier after every super-tile (like
+// empty[stage] + tmem_full); bit 1: additionally WAIT for the commit of the super-tile `lag` iterations back before
+// issuing (like the tmem_empty / empty[stage] round trips, without the other warps); bit 2: 17 extra warps spin on a
+// never-completing mbarrier (the parked producer / epilogue warps of the real kernel).
+// cycles[2b] = SM cycles, cycles[2b+1] = ns for `iters` super-tiles on CTA b.
+// variant bits 3..5 switch single features of the pattern OFF: bit 3: same B block for every tap, bit 4: no K-step
+// advance inside the swizzle row, bit 5: accumulate flag always 1.  KC compile-time and the tap / K loops unrolled like
+// the real kernel (a rolled loop with run-time div/mod makes the issuing thread itself the bound: ~57 cycles per MMA).
+template <int KC>
+__global__ void __launch_bounds__(576, 1)
+umma_pattern_probe_kernel(long long* __restrict__ cycles, int BN, int T, int iters, int variant, int lag,
+                          int fill_random) {
+    constexpr int kc = KC;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t bars[8];
+    __shared__ uint64_t never_bar;
+    __shared__ uint32_t tmem_ptr;
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 196 * 1024 / 4; i += blockDim.x) {
+        uint32_t h = (i + 1 + blockIdx.x * 7919u) * 2654435761u;
+        h ^= h >> 15;
+        reinterpret_cast<uint32_t*>(smem)[i] = fill_random ? ((h & 0x83FF83FFu) | 0x3C003C00u) : 0u;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
+        mbar_init(&never_bar, 1);
+        fence_barrier_init();
+    }
+    fence_proxy_async();
+    if (warp == 0) tmem_alloc(&tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_ptr;
+    __shared__ volatile int done_flag;
+    if (threadIdx.x == 0) done_flag = 0;
+    __syncthreads();
+    if (warp == 1) {
+        const uint32_t row_bytes = kc * 2;
+        const uint32_t layout = (kc == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
+        const uint64_t a_tmpl = make_smem_desc(smem_u32(smem), 10 * row_bytes, layout);
+        const uint64_t b_tmpl = make_smem_desc(smem_u32(smem) + 48 * 1024, 8 * row_bytes, layout);
+        const uint32_t a_hi = static_cast<uint32_t>(a_tmpl >> 32), b_hi = static_cast<uint32_t>(b_tmpl >> 32);
+        const uint32_t a_lo0 = static_cast<uint32_t>(a_tmpl), b_lo0 = static_cast<uint32_t>(b_tmpl);
+        const uint32_t idesc = make_idesc_16(128, BN, 1);
+        const uint32_t kRow16 = row_bytes >> 4, kTile16 = 16 * 10 * kRow16, b_tap16 = (BN * row_bytes) >> 4;
+        const int nbuf = (512 / (T * BN)) < 4 ? (512 / (T * BN)) : 4;
+        const uint32_t b_step = (variant & 8) ? 0u : b_tap16;
+        const uint32_t k_step = (variant & 16) ? 0u : 2u;
+        const uint32_t first_acc = (variant & 32) ? 1u : 0u;
+        long long g0, g1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+        const long long t0 = clock64();
+        for (int i = 0; i < iters; ++i) {
+            if ((variant & 2) && i >= lag) mbar_wait(&bars[(i - lag) & 7], ((i - lag) >> 3) & 1);
+            const uint32_t d0 = tmem_base + (i % nbuf) * T * BN;
+            for (int t = 0; t < T; ++t) {
+                if (elect_one_sync()) {
+                    uint32_t b_lo = b_lo0;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t a_tap = a_lo0 + t * kTile16 + ((tap / 3) * 10 + (tap % 3)) * kRow16;
+#pragma unroll
+                        for (int k = 0; k < KC / 16; ++k)
+                            umma_f16_split(d0 + t * BN, a_tap + k_step * k, a_hi, b_lo + k_step * k, b_hi, idesc,
+                                           (tap | k) != 0 ? 1u : first_acc);
+                        b_lo += b_step;
+                    }
+                }
+                __syncwarp();
+            }
+            if (variant & 1) {
+                if (elect_one_sync()) umma_commit(&bars[i & 7]);
+                __syncwarp();
+            }
+        }
+        if (elect_one_sync()) umma_commit(&never_bar);
+        __syncwarp();
+        mbar_wait(&never_bar, 0);
+        const long long t1 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+        if (elect_one_sync()) {
+            cycles[2 * blockIdx.x] = t1 - t0;
+            cycles[2 * blockIdx.x + 1] = g1 - g0;
+            done_flag = 1;
+        }
+    } else if (variant & 4) {
+        // parked warps: poll a barrier word in shared memory like the waiting roles of the real kernel
+        while (!done_flag) {
+            mbar_try_wait(&bars[7], 1);          // phase 1 of a barrier nobody completes twice: returns false quickly
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
 // mbarrier hop-latency probe (diagnostic): warp 1 signals barrier A (plain arrive, or tcgen05.commit when mode & 1) and
 // waits on barrier B; warp 0 (or, mode & 4, all of warps 2-3 as well, 32 lanes each) waits on A and arrives on B.
 // mode & 2: poll with mbarrier.test_wait instead of the (possibly suspending) try_wait.  cycles[0] / iters = round trip.

@@ -480,3 +480,51 @@ def test_conv_is_deterministic_across_launches(dev, cin, cout, hw, mode):
         if ref is None:
             ref = [o.clone() for o in outs]
         assert all(torch.equal(o, r) for o, r in zip(outs, ref))
+
+
+# ------------------------------------------------------------------------------------------------ other BASELINE configs
+def test_dhcp_config_256_encode_decode_and_synthesis(dev):
+    """BASELINE config 4 (dHCP: width 256, latent_width 64, latent 128): encode / decode / volume synthesis at 256^2
+    against the oracle, random-init checkpoint (spec tolerance 2e-2) and the stress checkpoint."""
+    from superresolution_aniso_mri_b200 import synthesis
+    args = O.default_args(256, 64)
+    vol = 0.8 * O.smooth_phantom(4, 256, seed=12) + 0.2 * O.synthetic_volume(4, 256, seed=13)
+    ar = O.alpha_range_for(3)
+    for kind, st in (("rnd", O.init_state(args, seed=892372)), ("cal", O.calibrated_state(args))):
+        model = make_model(args, st, dev)
+        assert model.scales == 2
+        z = model.encode(vol.to(dev)).cpu()
+        with torch.no_grad():
+            zr = O.encode(st, args, vol)
+        assert z.shape == zr.shape == (4, 128, 64, 64)
+        assert (z - zr).abs().max().item() < 0.03 * max(zr.abs().max().item(), 1e-12)
+        want = O.create_super_volume(st, args, vol, ar, use_original=True)
+        got = synthesis.create_super_volume(model, vol, ar, use_original=True)["upsampled_image"]
+        assert got.shape == want.shape == (13, 256, 256)
+        d = (got - want).abs()
+        if kind == "rnd":
+            assert d.max().item() < 2e-2
+        else:
+            assert d.max().item() < 8e-2 and d.mean().item() < 3e-3
+        assert torch.equal(got[::4], want[::4])                       # kept slices bit-exact
+
+
+@pytest.mark.parametrize("downsample_steps", [2, 3, 4, 5, 6])
+def test_sweep_downsample_steps_against_oracle(dev, downsample_steps):
+    """BASELINE config 5: downsample_steps 2..6 (num_interpolations = d - 1) through the evaluation twin (slice dropping,
+    tail re-appended) on a 14-slice volume, random-init checkpoint: spec tolerance, indexing bit-exact."""
+    from superresolution_aniso_mri_b200 import synthesis
+    args = O.default_args(128, 32)
+    st = O.init_state(args, seed=892372)
+    model = make_model(args, st, dev)
+    vol = O.smooth_phantom(14, 128, seed=30 + downsample_steps)
+    ar = O.alpha_range_for(downsample_steps - 1)
+    want = O.create_super_volume_eval(st, args, vol[:, 0], alpha_range=ar, use_original=True,
+                                      downsample_steps=downsample_steps, generate_inbetween_slices=True)
+    got = synthesis.create_super_volume_eval(model, vol[:, 0], ar, use_original=True, downsample_steps=downsample_steps,
+                                             generate_inbetween_slices=True)["upsampled_image"]
+    assert got.shape == want.shape == (14, 128, 128)
+    assert (got - want).abs().max().item() < 2e-2
+    last = ((14 - 1) // downsample_steps) * downsample_steps
+    kept = list(range(0, last + 1, downsample_steps)) + list(range(last + 1, 14))
+    assert torch.equal(got[kept], want[kept])                         # originals + untouched tail: bit-exact

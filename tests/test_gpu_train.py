@@ -188,3 +188,32 @@ def test_trainer_interface_checkpoint_roundtrip_and_validate(cuda_lib, tmp_path)
     val = tr.validate(batch)
     assert "loss_ae" in val and len(tr.losses_test["loss_ae_dist_extra"]) == 1
     assert tr.model.training
+
+
+@pytest.mark.parametrize("cfg", ["oasis", "dhcp"])
+def test_brain_config_train_steps_match_oracle(cuda_lib, cfg):
+    """BASELINE configs 3 / 4: OASIS (width 64, latent_width 16, B=16, alpha .5 / .5, weight 0.001) and dHCP (width 256,
+    latent_width 64, B=4 of the 8 here to bound the CPU oracle, per-sample alphas in {.25,.5,.75}): three optimisation
+    steps of AETrainerExtension1Brain against the oracle's autograd + Adam, logged losses within 1 %."""
+    width, lw, B = (64, 16, 16) if cfg == "oasis" else (256, 64, 4)
+    args = trainer_args(width=width, latent_width=lw, dataset="OASIS" if cfg == "oasis" else "dHCP", ex_loss_weight1=0.001,
+                        batch_size=B)
+    tr = make_trainer(args)
+    assert type(tr).__name__ == "AETrainerExtension1Brain"
+    oargs = O.default_args(width, lw)
+    st = O.init_state(oargs, seed=892372)
+    adam = O.AdamState(st, lr=1e-5)
+    vgg = O.init_vgg(3)
+    rs = np.random.RandomState(3)
+    for step in range(3):
+        img, mid = acdc_batch(step, B=B, size=width)
+        if cfg == "oasis":
+            af = torch.full((B, 1), 0.5)
+        else:
+            af = torch.from_numpy(rs.choice([0.25, 0.5, 0.75], size=(B, 1)).astype(np.float32))
+        at = 1 - af
+        lg = O.train_step(st, oargs, adam, img, mid, vgg, lins(), alpha_from=af, alpha_to=at, ex_loss_weight=0.001)
+        tr.train({"image": img, "slice_between": mid, "alpha_from": af, "alpha_to": at}, keep_predictions=False)
+        for k in ("loss_ae", "loss_ae_dist", "loss_ae_dist_extra"):
+            ours, ref = tr.losses[k][-1], lg[k]
+            assert abs(ours - ref) <= 0.01 * abs(ref) + 1e-9, (cfg, step, k, ours, ref)

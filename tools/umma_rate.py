@@ -29,6 +29,24 @@ def run(kc, N, nacc, pitch, shift, adv, grid, rnd):
           % (kc, N, nacc, pitch, shift, adv, grid, "rand" if rnd else "zero", cyc, ns, 1e3 * cyc / ns))
 
 
+if "--pattern" in sys.argv:
+    # the conv kernel's issue loop in isolation: cycles per MMA for the layer shapes of the ACDC pipeline
+    print("BN kc  T variant lag grid data : cycles/MMA (probe rate: N=32 40.1, 64 48.0, 128 64.0)")
+    its = 400
+    for BN, kc, T in ((32, 32, 4), (64, 32, 2), (64, 64, 2), (128, 32, 1), (128, 64, 1), (64, 64, 1)):
+        per = T * 9 * (kc // 16)
+        for variant, lag in ((0, 1), (1, 1), (3, 3), (7, 3), (8, 1), (16, 1), (32, 1), (56, 1)):
+            for grid, rnd in ((1, 0),):
+                out.zero_()
+                for _ in range(2):
+                    _lib.check(lib.aesr_probe_umma_pattern(out.data_ptr(), BN, kc, T, its, variant, lag, grid, rnd,
+                                                           torch.cuda.current_stream().cuda_stream), "pattern")
+                torch.cuda.synchronize()
+                r = out.view(-1, 2)[:grid].double()
+                cyc, ns = r[:, 0].max().item() / (its * per), r[:, 1].max().item() / (its * per)
+                print("%3d %2d  %d    %d     %d  %4d  %s : %6.1f cycles/MMA  %6.1f ns/MMA" %
+                      (BN, kc, T, variant, lag, grid, "rand" if rnd else "zero", cyc, ns))
+    sys.exit(0)
 print("kc  N  nacc pitch shift adv  grid data")
 for kc in (32, 64):
     for N in (32, 64, 128, 256):
