@@ -309,6 +309,19 @@ def run_ours(a):
             with open(os.path.join(ROOT, "profiles", caps[-1])) as f:
                 traffic = json.load(f)["mean_dram_bytes_per_launch"]
             traffic_src = "profiles/%s (dram__bytes_read.sum + dram__bytes_write.sum, mean per conv launch)" % caps[-1]
+        # memory-bound kernels of the step against the measured HBM copy bandwidth: algorithmic bytes
+        HW, HWs = SIZE * SIZE, (SIZE + 2) * (SIZE + 2)
+        n_enc, n_syn = V * Z, V * (Z - 1) * NI
+        mem_bytes = {"stem": n_enc * (4 * HW + 64 * HWs),
+                     "lerp": V * (Z - 1) * 2 * 4 * 64 * (HW // 16) + n_syn * 2 * 64 * (HW // 16),
+                     "head": n_syn * (16 * HW + 4 * HW)}
+        hbm = []
+        for name in ("stem", "lerp", "head"):
+            if name in kernel_ms and kernel_ms[name] > 0:
+                gbs = mem_bytes[name] / (kernel_ms[name] * 1e-3) / 1e9
+                hbm.append({"kernel": {"stem": "stem_conv", "lerp": "lerp_pairs_act", "head": "head_gather"}[name],
+                            "algorithmic_bytes": mem_bytes[name], "ms": kernel_ms[name], "achieved_gbs": gbs,
+                            "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]})
         roof = {"bound": "tensor", "kernel": "conv3x3_halo_kernel (tcgen05, all %d launches of a step)" % n_conv,
                 "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
@@ -317,7 +330,8 @@ def run_ours(a):
                 "conv_ms_per_step": conv_ms, "all_kernels_ms_per_step": all_ms,
                 "conv_share_of_kernel_time": conv_ms / all_ms if all_ms else None,
                 "algorithmic_gflop_per_step": alg_fl / 1e9, "executed_gflop_per_step": conv_fl / 1e9,
-                "executed_tflops": conv_fl / (conv_ms * 1e-3) / 1e12, "kernel_ms": kernel_ms}
+                "executed_tflops": conv_fl / (conv_ms * 1e-3) / 1e12, "kernel_ms": kernel_ms,
+                "memory_bound_kernels": hbm, "hbm_peak_gbs": peaks["hbm_gbs"]}
 
     train = bench_train(a, dev, rank, world, barrier) if a.train else None
 

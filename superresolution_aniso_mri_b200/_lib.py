@@ -10,7 +10,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libaesr_b200.so")
+# AESR_B200_LIB: another build of the same library (A/B timing of kernel variants on one box, tools/gpu_*.sh)
+LIB_PATH = os.environ.get("AESR_B200_LIB") or os.path.join(_HERE, "lib", "libaesr_b200.so")
 
 _lib = None
 _initialised_devices = set()

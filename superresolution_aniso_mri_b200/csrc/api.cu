@@ -204,10 +204,13 @@ int halo_pick_bn(int Cin, int Cout) {
 }
 
 // Profiling / tuning knobs (aesr_set_tuning; initial values from the environment): 0 = AESR_CONV_DEBUG stage mask,
-// 1 = AESR_CONV_T forced M-tiles per super-tile, 2 = AESR_CONV_NBUF forced TMEM buffers, 3 = AESR_CONV_STAGES cap.
-int g_tune[4] = {-1, -1, -1, -1};
+// 1 = AESR_CONV_T forced M-tiles per super-tile, 2 = AESR_CONV_NBUF forced TMEM buffers, 3 = AESR_CONV_STAGES cap,
+// 4 = AESR_HEAD_MMA decoder head behind dec.12 on warp-level mma.sync fragments (16-bit activations / filter).
+// 5 = AESR_STEM_CUDA_CORES encoder stem on the CUDA cores (fp32 FMAs) instead of warp-level tf32 mma.sync.
+int g_tune[6] = {-1, -1, -1, -1, -1, -1};
 int tune(int key) {
-    static const char* names[4] = {"AESR_CONV_DEBUG", "AESR_CONV_T", "AESR_CONV_NBUF", "AESR_CONV_STAGES"};
+    static const char* names[6] = {"AESR_CONV_DEBUG", "AESR_CONV_T", "AESR_CONV_NBUF", "AESR_CONV_STAGES", "AESR_HEAD_MMA",
+                                   "AESR_STEM_CUDA_CORES"};
     if (g_tune[key] < 0) g_tune[key] = getenv(names[key]) ? atoi(getenv(names[key])) : 0;
     return g_tune[key];
 }
@@ -255,7 +258,8 @@ int launch_halo(const void* x, const void* w, const void* head_w16, ConvParams p
     if (p.BN == 0) return fail(AESR_ERR_INVALID, "conv3x3_fwd: filter bank %dx%d does not fit the halo kernel", p.Cout, p.Cin);
     p.n_blocks = p.Cout / p.BN;
     const bool head_tc = p.out_mode == OUT_SHUFFLE2_HEAD && head_w16 != nullptr;
-    p.head_smem = head_tc ? HEAD_SMEM_BYTES : 0;
+    const bool head_mma = p.out_mode == OUT_SHUFFLE2_HEAD && !head_tc && tune(4) != 0;
+    p.head_smem = head_tc ? HEAD_SMEM_BYTES : head_mma ? HEAD_MMA_SMEM_BYTES : 0;
     int T = 1, stages = 2, nbuf = 2;
     halo_pick_T<KC>(p.BN, p.Cin, p.tiles_y, p.head_smem, &T, &stages, &nbuf);
     p.T = T;
@@ -289,6 +293,7 @@ int launch_halo(const void* x, const void* w, const void* head_w16, ConvParams p
         conv3x3_halo_kernel<KC, MODE><<<grid, CONV_THREADS, smem, stream>>>(tx, tw, th, p);          \
     }
     if (head_tc) AESR_HALO(OUT_SHUFFLE2_HEAD_TC)
+    else if (head_mma) AESR_HALO(OUT_SHUFFLE2_HEAD_MMA)
     else if (p.out_mode == OUT_SHUFFLE2_HEAD) AESR_HALO(OUT_SHUFFLE2_HEAD)
     else if (plain && p.out_mode == OUT_SAME) AESR_HALO(OUT_SAME)
     else if (plain && p.out_mode == OUT_AVGPOOL2) AESR_HALO(OUT_AVGPOOL2)
@@ -314,7 +319,7 @@ int aesr_init(int device) {
 const char* aesr_last_error(void) { return g_err; }
 
 int aesr_set_tuning(int key, int value) {
-    if (key < 0 || key > 3 || value < 0) return fail(AESR_ERR_INVALID, "set_tuning: key %d value %d", key, value);
+    if (key < 0 || key > 5 || value < 0) return fail(AESR_ERR_INVALID, "set_tuning: key %d value %d", key, value);
     g_tune[key] = value;
     return AESR_OK;
 }
@@ -456,10 +461,39 @@ int aesr_stem_fwd(const float* x, const float* weff_beff_b1_host, void* out, int
     if (!x || !weff_beff_b1_host || !out || N <= 0 || H <= 0 || W <= 0 || C != 32)
         return fail(AESR_ERR_INVALID, "stem_fwd: bad arguments (C = 32)");
     if (static_cast<size_t>(H + 2) * (W + 2) > (1u << 28)) return fail(AESR_ERR_INVALID, "stem_fwd: image too large");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const float *weff = weff_beff_b1_host, *beff = weff_beff_b1_host + 9 * 32, *b1 = weff_beff_b1_host + 18 * 32;
+    if (tune(5) == 0) {
+        // warp-level tensor-core stem: bias of the nine border classes (first / inner / last row x column) in fp32
+        StemMmaParams mp;
+        memcpy(mp.weff, weff, sizeof(mp.weff));
+        for (int cy = 0; cy < 3; ++cy)
+            for (int cx = 0; cx < 3; ++cx)
+                for (int c = 0; c < 32; ++c) {
+                    float t = b1[c];
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int dy = tap / 3, dx = tap % 3;
+                        const bool on_grid = !(cy == 0 && dy == 0) && !(cy == 2 && dy == 2) && !(cx == 0 && dx == 0) &&
+                                             !(cx == 2 && dx == 2);
+                        if (on_grid) t += beff[tap * 32 + c];
+                    }
+                    mp.bias_tab[(cy * 3 + cx) * 32 + c] = t;
+                }
+        const int blocks = ((H + 2) * (W + 2) + 15) / 16;
+        int gy = (8 * g_sm_count * 4 + blocks - 1) / blocks;          // ~8 resident CTAs of 4 warps per SM, the rest loops over images
+        if (gy > N) gy = N;
+        if (gy < 1) gy = 1;
+        const dim3 grid((blocks + 3) / 4, gy);
+        if (dtype == AESR_DT_FP16)
+            stem_mma_kernel<true><<<grid, 128, 0, s>>>(x, mp, static_cast<uint16_t*>(out), N, H, W, slope);
+        else
+            stem_mma_kernel<false><<<grid, 128, 0, s>>>(x, mp, static_cast<uint16_t*>(out), N, H, W, slope);
+        return check_launch("stem_mma");
+    }
     StemParams sp;
-    memcpy(sp.weff, weff_beff_b1_host, sizeof(sp.weff));
-    memcpy(sp.beff, weff_beff_b1_host + 9 * 32, sizeof(sp.beff));
-    memcpy(sp.b1, weff_beff_b1_host + 18 * 32, sizeof(sp.b1));
+    memcpy(sp.weff, weff, sizeof(sp.weff));
+    memcpy(sp.beff, beff, sizeof(sp.beff));
+    memcpy(sp.b1, b1, sizeof(sp.b1));
     for (int c = 0; c < 32; ++c) {
         float t = sp.b1[c];
         for (int tap = 0; tap < 9; ++tap) t += sp.beff[tap * 32 + c];
@@ -468,7 +502,6 @@ int aesr_stem_fwd(const float* x, const float* weff_beff_b1_host, void* out, int
     const int per_img = (H + 2) * (W + 2);
     const int groups = (N + STEM_P - 1) / STEM_P;
     const dim3 grid((per_img + 127) / 128, groups < 65535 ? groups : 65535);
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == AESR_DT_FP16)
         stem_conv_kernel<true><<<grid, 128, 0, s>>>(x, sp, static_cast<uint16_t*>(out), N, H, W, slope);
     else

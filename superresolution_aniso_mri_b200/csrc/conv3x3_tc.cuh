@@ -53,6 +53,11 @@ enum ConvOut : int {
     // OUT_SHUFFLE2_HEAD): the epilogue writes LeakyReLU(acc + bias) back to TMEM as a 16-bit A operand and one elected
     // thread issues D2[128 px x 16 taps] = A[128 x 32] * Whead[32 x 16] per phase (A from TMEM, B = 1 KB in smem).
     OUT_SHUFFLE2_HEAD_TC = 8,
+    // OUT_SHUFFLE2_HEAD with the head conv as warp-level mma.sync on register fragments (kernel template value only):
+    // the accumulator is read in the mma fragment distribution (tcgen05.ld.16x256b), bias + LeakyReLU + 16-bit rounding
+    // happen in registers and feed the A operand directly; the B operand maps (phase, channel) to the 16 patch entries,
+    // so the four phases accumulate into one D fragment and nothing is scattered or shuffled.
+    OUT_SHUFFLE2_HEAD_MMA = 9,
 };
 enum ConvMul : int { MUL_NONE = 0, MUL_LEAKY_GRAD = 1, MUL_RELU_GRAD = 2 };
 
@@ -506,7 +511,7 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
 // ph = 2a+b.  act = LeakyReLU(acc + bias) stays in fp32 registers; the head filter tap (ky,kx) carries it to output
 // pixel (2y+a-ky+1, 2x+b-kx+1) = entry [(a-ky+2)*4 + (b-kx+2)] of this pixel's 4x4 patch (origin (2y-1, 2x-1)).
 // 4 x 288 MACs per thread, filter read from the constant bank as FFMA operands.
-__device__ __forceinline__ void conv_epilogue_head_tile(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
+__device__ __forceinline__ void conv_epilogue_head_tile_v1(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
                                                         uint64_t* tmem_empty_bar, const TileCoord& t) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3;
@@ -579,6 +584,181 @@ __device__ __forceinline__ void conv_epilogue_head_tile(const ConvParams& p, con
                                               ((static_cast<size_t>(t.n) * p.H + y) * p.W + x) * 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[i] = make_float4(hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
+    }
+}
+
+// Channel-chunk-major variant: all four phases of an 8-channel chunk are in registers at once, so every filter value
+// fetched from the constant bank (LDCU.128 = two FFMA2 operands) feeds four FFMA2s instead of one, and the products
+// accumulate straight into the sixteen patch entries as fp32x2 (even / odd channel) partial sums -- no per-phase tap
+// sums, no scatter.  Per tile and thread: 576 FFMA2 + 72 LDCU.128 (was 576 + 288) and 16 final adds (was 144 + 36).
+// The phase-major version above executed ~1750 warp instructions per tile at 70 % issue utilisation against 1152-1460
+// tensor-pipe cycles of the tile's MMAs (profiles/r01k_conv_full.md): the layer was bound by this epilogue's issue slots.
+constexpr int HEAD_EPI_CW = 4;
+__device__ __forceinline__ void conv_epilogue_head_tile(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
+                                                        uint64_t* tmem_empty_bar, const TileCoord& t) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int py = row >> 3, px = row & 7;
+    const int y = t.y0 + py, x = t.x0 + px;
+    const bool inb = (y < p.H) && (x < p.W);
+    const float neg_slope = (p.act == ACT_LEAKY) ? p.slope : (p.act == ACT_RELU) ? 0.f : 1.f;
+    const float2 slope2 = make_float2(neg_slope, neg_slope);
+    const uint32_t t_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+    float2 hp2[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) hp2[i] = make_float2(0.f, 0.f);
+    constexpr int CW = HEAD_EPI_CW;              // channels per chunk (4: 16 + 32 live values, fits the 96-register budget)
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += CW) {
+        uint32_t raw[4][CW];
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+            if (p.debug & 8) {                   // profiling: no TMEM reads
+#pragma unroll
+                for (int j = 0; j < CW; ++j) raw[ph][j] = 0;
+            } else if (CW == 8) tmem_ld_32x32b_x8(t_addr + ph * 32 + c0, reinterpret_cast<uint32_t(&)[8]>(raw[ph]));
+            else tmem_ld_32x32b_x4(t_addr + ph * 32 + c0, reinterpret_cast<uint32_t(&)[4]>(raw[ph]));
+        }
+        if (!(p.debug & 8)) tmem_ld_wait();
+        if (c0 == 32 - CW) {                     // accumulator fully read: one elected arrive per warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar);
+        }
+        float2 bb[CW / 2];                       // phase blocks share the 32 biases
+#pragma unroll
+        for (int j4 = 0; j4 < CW / 4; ++j4) {
+            const float4 b = lds_f4(bars.s_bias + c0 + 4 * j4);
+            bb[2 * j4] = make_float2(b.x, b.y);
+            bb[2 * j4 + 1] = make_float2(b.z, b.w);
+        }
+        float2 v[4][CW / 2];
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+#pragma unroll
+            for (int j2 = 0; j2 < CW / 2; ++j2) {
+                const float2 a = __fadd2_rn(make_float2(__uint_as_float(raw[ph][2 * j2]), __uint_as_float(raw[ph][2 * j2 + 1])),
+                                            bb[j2]);
+                const float2 s = __fmul2_rn(a, slope2);
+                v[ph][j2] = make_float2(fmaxf(a.x, s.x), fmaxf(a.y, s.y));
+            }
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+            for (int j2 = 0; j2 < CW / 2; ++j2) {
+                const float2 w = make_float2(p.head_wc[tap * 32 + c0 + 2 * j2], p.head_wc[tap * 32 + c0 + 2 * j2 + 1]);
+#pragma unroll
+                for (int ph = 0; ph < 4; ++ph) {
+                    const int e = ((ph >> 1) - tap / 3 + 2) * 4 + ((ph & 1) - tap % 3 + 2);
+                    hp2[e] = __ffma2_rn(v[ph][j2], w, hp2[e]);
+                }
+            }
+        }
+    }
+    if (inb && !(p.debug & 4)) {
+        float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) +
+                                              ((static_cast<size_t>(t.n) * p.H + y) * p.W + x) * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            o[i] = make_float4(hp2[4 * i].x + hp2[4 * i].y, hp2[4 * i + 1].x + hp2[4 * i + 1].y,
+                               hp2[4 * i + 2].x + hp2[4 * i + 2].y, hp2[4 * i + 3].x + hp2[4 * i + 3].y);
+    }
+}
+
+// OUT_SHUFFLE2_HEAD_MMA: the head conv of a tile on the warp-level tensor-core path (mma.sync m16n8k16, fp32 accumulate).
+// The CUDA-core versions above need 1152 fp32 MACs per low-res pixel -- ~2300 FMA-pipe cycles per tile and scheduler,
+// more than the 1152-1460 tensor-pipe cycles of the tile's own MMAs, so dec.12 ran at the speed of its epilogue
+// (profiles/r01s).  Here the fp32 pipe only does bias + LeakyReLU + rounding (as every other layer's output is rounded).
+//   A  = act[16 px x 32 ch] of one phase, straight from the accumulator registers (C-fragment == A-fragment distribution)
+//   B  = Bp[ph][ch][e] = head filter tap (ky,kx) of channel ch if patch entry e = (a-ky+2)*4 + (b-kx+2) (ph = 2a+b), else 0
+//   D  = patch[16 px x 16 entries] summed over the four phases; thread (g,t) ends up with entries 8nt + 2t + {0,1} of
+//        pixels g and g+8 -> 8-byte stores, a quad writes one 32-byte sector.
+// s_bfrag: shared [4 ph][2 k-steps][2 n-tiles][32 lanes] uint2 = per-lane B fragments (head_mma_fill_bfrag).
+__device__ __forceinline__ void head_mma_fill_bfrag(const ConvParams& p, uint2* s_bfrag, int idx /* 0..511 */) {
+    const int lane = idx & 31, combo = idx >> 5;                 // combo = (ph * 2 + s) * 2 + nt
+    const int nt = combo & 1, ks = (combo >> 1) & 1, ph = combo >> 2;
+    const int g = lane >> 2, tq = lane & 3;
+    const int e = nt * 8 + g;
+    const int ky = (ph >> 1) + 2 - (e >> 2), kx = (ph & 1) + 2 - (e & 3);
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ky >= 0 && ky <= 2 && kx >= 0 && kx <= 2) {
+        const float* wt = p.head_wc + (ky * 3 + kx) * 32 + ks * 16 + 2 * tq;
+        w[0] = wt[0]; w[1] = wt[1]; w[2] = wt[8]; w[3] = wt[9];
+    }
+    s_bfrag[idx] = make_uint2(pack2(w[0], w[1], p.fp16), pack2(w[2], w[3], p.fp16));
+}
+
+__device__ __forceinline__ void conv_epilogue_head_mma_tile(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
+                                                            uint64_t* tmem_empty_bar, const TileCoord& t,
+                                                            const uint2* s_bfrag) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, g = lane >> 2, tq = lane & 3;
+    const int fp16 = p.fp16;
+    const float neg_slope = (p.act == ACT_LEAKY) ? p.slope : (p.act == ACT_RELU) ? 0.f : 1.f;
+    const float2 slope2 = make_float2(neg_slope, neg_slope);
+    float2 bb[4];                                                // biases of this thread's channel pairs 8j + 2t + {0,1}
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        bb[j].x = bars.s_bias[8 * j + 2 * tq];
+        bb[j].y = bars.s_bias[8 * j + 2 * tq + 1];
+    }
+    const uint32_t sb = smem_u32(s_bfrag) + lane * 8;
+    const int x = t.x0 + g;
+#pragma unroll
+    for (int hb = 0; hb < 2; ++hb) {                             // two blocks of 16 pixels (TMEM lanes) per warp
+        float d[2][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[0][i] = d[1][i] = 0.f;
+        const uint32_t t_addr = tmem_acc + (static_cast<uint32_t>(q * 32 + hb * 16) << 16);
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+            uint32_t raw[16];
+            if (p.debug & 8) {                                   // profiling: no TMEM reads
+#pragma unroll
+                for (int j = 0; j < 16; ++j) raw[j] = 0;
+            } else {
+                tmem_ld_16x256b_x4(t_addr + ph * 32, raw);
+                tmem_ld_wait();
+            }
+            if (hb == 1 && ph == 3) {                            // accumulator fully read: one elected arrive per warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar);
+            }
+            uint32_t lo[4], hi[4];                               // 16-bit pairs of pixel g / pixel g + 8
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 a = __fadd2_rn(make_float2(__uint_as_float(raw[4 * j]), __uint_as_float(raw[4 * j + 1])), bb[j]);
+                const float2 b = __fadd2_rn(make_float2(__uint_as_float(raw[4 * j + 2]), __uint_as_float(raw[4 * j + 3])), bb[j]);
+                const float2 sa = __fmul2_rn(a, slope2), sb2 = __fmul2_rn(b, slope2);
+                lo[j] = pack2(fmaxf(a.x, sa.x), fmaxf(a.y, sa.y), fp16);
+                hi[j] = pack2(fmaxf(b.x, sb2.x), fmaxf(b.y, sb2.y), fp16);
+            }
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    uint32_t b0, b1;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(sb + ((ph * 2 + ks) * 2 + nt) * 256));
+                    mma_m16n8k16(d[nt], lo[2 * ks], hi[2 * ks], lo[2 * ks + 1], hi[2 * ks + 1], b0, b1, fp16);
+                }
+            }
+        }
+        const int y = t.y0 + q * 4 + hb * 2;                     // tile row of pixel g (lane = 8 * row + column); g + 8 = next row
+        if (x < p.W && !(p.debug & 4)) {
+            float* o = static_cast<float*>(p.out) + ((static_cast<size_t>(t.n) * p.H + y) * p.W + x) * 16 + 2 * tq;
+            if (y < p.H) {
+                *reinterpret_cast<float2*>(o) = make_float2(d[0][0], d[0][1]);
+                *reinterpret_cast<float2*>(o + 8) = make_float2(d[1][0], d[1][1]);
+            }
+            if (y + 1 < p.H) {
+                o += static_cast<size_t>(p.W) * 16;
+                *reinterpret_cast<float2*>(o) = make_float2(d[0][2], d[0][3]);
+                *reinterpret_cast<float2*>(o + 8) = make_float2(d[1][2], d[1][3]);
+            }
+        }
     }
 }
 
@@ -696,6 +876,7 @@ struct HaloSmem {
     }
 };
 constexpr int HEAD_SMEM_BYTES = 1024;          // 16 rows x 64 bytes, SW64
+constexpr int HEAD_MMA_SMEM_BYTES = 4096;      // [4 ph][2 k-steps][2 n-tiles][32 lanes] uint2 B fragments
 __host__ __device__ constexpr uint32_t halo_tmem_cols(int T, int BN, int nbuf) {
     const int c = nbuf * T * BN;
     return (c <= 32) ? 32 : (c <= 64) ? 64 : (c <= 128) ? 128 : (c <= 256) ? 256 : 512;
@@ -729,6 +910,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // epilogue warps attached to one TMEM buffer: T sets of 4 warps (T = 1: one set per buffer)
     const int nbuf = p.nbuf;
     const uint32_t tmem_cols = halo_tmem_cols(T, p.BN, nbuf);
+    if (MODE == OUT_SHUFFLE2_HEAD_MMA && threadIdx.x >= 32 * CONV_FIRST_EPI_WARP)      // 512 epilogue threads, one entry each
+        head_mma_fill_bfrag(p, reinterpret_cast<uint2*>(h_smem), threadIdx.x - 32 * CONV_FIRST_EPI_WARP);
     const uint32_t tmem_base = conv_prologue(p, bars, num_stages, tmem_cols, 4 * T);
 
     // CTA -> (n-block, first super-tile, stride): the grid is split evenly between the n-blocks.
@@ -744,7 +927,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         if (active) {
             if (elect_one_sync()) {
                 // resident filter bank of this n-block: 9 * kchunks TMA boxes {KC, BN} on one barrier
-                mbar_arrive_expect_tx(bars.b_full, 9 * kchunks * b_block + p.head_smem);
+                mbar_arrive_expect_tx(bars.b_full, 9 * kchunks * b_block + (MODE == OUT_SHUFFLE2_HEAD_TC ? p.head_smem : 0));
                 if (MODE == OUT_SHUFFLE2_HEAD_TC) tma_load_2d(h_smem, &tmap_h, bars.b_full, 0, 0);
                 for (int tap = 0; tap < 9; ++tap)
                     for (int kc = 0; kc < kchunks; ++kc)
@@ -883,7 +1066,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         conv_epilogue_head_tc_tile(p, bars, acc, &bars.tmem_empty[buf], &bars.head_bar[eset], head_uses & 1,
                                                    hdesc_lo, hdesc_hi, eset, tc);
                         ++head_uses;
-                    } else if (MODE == OUT_SHUFFLE2_HEAD) conv_epilogue_head_tile(p, bars, acc, &bars.tmem_empty[buf], tc);
+                    } else if (MODE == OUT_SHUFFLE2_HEAD_MMA) {
+                        conv_epilogue_head_mma_tile(p, bars, acc, &bars.tmem_empty[buf], tc, reinterpret_cast<const uint2*>(h_smem));
+                    } else if (MODE == OUT_SHUFFLE2_HEAD) {
+                        conv_epilogue_head_tile(p, bars, acc, &bars.tmem_empty[buf], tc);
+                    }
                     else if (MODE >= 0) conv_epilogue_lean<MODE>(p, bars, acc, &bars.tmem_empty[buf], tc);
                     else conv_epilogue_tile(p, bars, acc, &bars.tmem_empty[buf], tc);
                 } else {                       // M-tile below the image: nothing to read, release the buffer

@@ -313,6 +313,132 @@ stem_conv_kernel(const float* __restrict__ x, const __grid_constant__ StemParams
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The same stem on warp-level tensor-core fragments (mma.sync m16n8k8, tf32 operands, fp32 accumulate).  The CUDA-core
+// kernel above executes 288 fp32 MACs per output pixel and was bound by instruction issue at 38 % of the HBM roofline
+// (profiles/r01q_memory_kernels_full.md); the work is a [pixels x 9] x [9 x 32] product, far too thin for a tcgen05 tile,
+// but four HMMA steps per 16 pixels make it disappear behind the 64 B/px store stream.
+//   D[16 px x 32 ch] = bias(px) + A[16 x 32] * B[32 x 32],  K = 32 slots = { xhi*Whi, xlo*Whi, xhi*Wlo } over the 9 taps
+//   (x = xhi + xlo, W = Whi + Wlo split into tf32 halves: the dropped xlo*Wlo term is ~2^-22 relative, i.e. fp32-exact
+//   for a result that is rounded to 16 bit anyway -- no range restriction on x, unlike an fp16 operand).
+//   K slots are dealt to the four threads of a quad so that thread t only needs taps 2t, 2t+1 (+ tap 8):
+//     k-step 0: xhi[2t], xhi[2t+1] * Whi     k-step 1: xlo[2t], xlo[2t+1] * Whi     k-step 2: xhi[2t], xhi[2t+1] * Wlo
+//     k-step 3: tap 8 -- t = 0: xhi*Whi, t = 1: xlo*Whi, t = 2: xhi*Wlo, t = 3: unused; upper half unused
+//   bias(px) = b1 + sum of beff over the taps on the (H+2)x(W+2) grid: nine border classes (first / inner / last row x
+//   column), formed in fp32 on the host and used as the accumulator's initial value -- exact.
+//   Channels are permuted across the four n-tiles (column c of n-tile nt = channel 8*(c/2) + 2*nt + c%2), so that thread
+//   (g, t) of the accumulator fragment owns channels 8t..8t+7 of pixels g and g+8: one 16-byte store per pixel, a quad
+//   writes a pixel's 64 bytes, a warp 2 x 512 contiguous bytes.
+// One warp = 16 consecutive output pixels (flat index on the (H+2)x(W+2) grid) of every STEM_MMA-strided image; all
+// pixel geometry (tap offsets, predicates, bias) is loop-invariant, the next image's taps are prefetched.
+// ---------------------------------------------------------------------------------------------------------------
+struct StemMmaParams {
+    alignas(16) float weff[9 * 32];
+    alignas(16) float bias_tab[9 * 32];      // [row class * 3 + column class][channel], class 0 first, 1 inner, 2 last
+};
+
+__device__ __forceinline__ void mma_m16n8k8_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                                 uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// tf32 split: hi = the 19 bits the tensor core reads, lo = the (exact) remainder, itself cut to tf32
+__device__ __forceinline__ void tf32_split(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xFFFFE000u;
+    lo = __float_as_uint(v - __uint_as_float(hi)) & 0xFFFFE000u;
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(128)
+stem_mma_kernel(const float* __restrict__ x, const __grid_constant__ StemMmaParams sp, uint16_t* __restrict__ out, int N,
+                int H, int W, float slope) {
+    const int Ho = H + 2, Wo = W + 2;
+    const int total = Ho * Wo;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const int blk = blockIdx.x * 4 + warp;                 // 16-pixel block of the output grid
+    if (blk * 16 >= total) return;
+    // B fragments (loop-invariant): b0 <-> k = t, b1 <-> k = t + 4 of each k-step; n = g of n-tile nt
+    uint32_t bhiA[4], bhiB[4], bloA[4], bloB[4], b8[4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const int ch = 8 * (g >> 1) + 2 * nt + (g & 1);
+        uint32_t h, l;
+        tf32_split(sp.weff[(2 * tq) * 32 + ch], h, l);
+        bhiA[nt] = h; bloA[nt] = l;
+        tf32_split(sp.weff[(2 * tq + 1) * 32 + ch], h, l);
+        bhiB[nt] = h; bloB[nt] = l;
+        tf32_split(sp.weff[8 * 32 + ch], h, l);
+        b8[nt] = (tq <= 1) ? h : (tq == 2) ? l : 0u;
+    }
+    // pixel geometry of this thread's two pixels (g and g + 8 of the block)
+    int off[2][3];                                          // image offsets of taps 2t, 2t+1, 8 (-1: reads zero)
+    bool valid[2];
+    float binit[2][8];                                      // accumulator start = bias of the pixel's border class, channels 8t..8t+7
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int pix = blk * 16 + g + 8 * r;
+        valid[r] = pix < total;
+        const int yo = valid[r] ? pix / Wo : 1, xo = valid[r] ? pix - yo * Wo : 1;
+        const int taps[3] = {2 * tq, 2 * tq + 1, 8};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int yi = yo + taps[i] / 3 - 2, xi = xo + taps[i] % 3 - 2;        // position in the image
+            off[r][i] = (valid[r] && yi >= 0 && yi < H && xi >= 0 && xi < W) ? yi * W + xi : -1;
+        }
+        const int cls = ((yo == 0) ? 0 : (yo == Ho - 1) ? 2 : 1) * 3 + ((xo == 0) ? 0 : (xo == Wo - 1) ? 2 : 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) binit[r][j] = sp.bias_tab[cls * 32 + 8 * tq + j];
+    }
+    const size_t img = static_cast<size_t>(H) * W;
+    float xv[2][3];
+    int n = blockIdx.y;
+    if (n < N) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) xv[r][i] = off[r][i] >= 0 ? __ldg(x + n * img + off[r][i]) : 0.f;
+    }
+    for (; n < N; n += gridDim.y) {
+        uint32_t hi[2][3], lo[2][3];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) tf32_split(xv[r][i], hi[r][i], lo[r][i]);
+        const int nn = n + gridDim.y;                       // prefetch the next image's taps
+        if (nn < N) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) xv[r][i] = off[r][i] >= 0 ? __ldg(x + nn * img + off[r][i]) : 0.f;
+        }
+        const uint32_t a8_0 = (tq == 1) ? lo[0][2] : (tq == 3) ? 0u : hi[0][2];
+        const uint32_t a8_1 = (tq == 1) ? lo[1][2] : (tq == 3) ? 0u : hi[1][2];
+        float d[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            d[nt][0] = binit[0][2 * nt]; d[nt][1] = binit[0][2 * nt + 1];
+            d[nt][2] = binit[1][2 * nt]; d[nt][3] = binit[1][2 * nt + 1];
+            mma_m16n8k8_tf32(d[nt], hi[0][0], hi[1][0], hi[0][1], hi[1][1], bhiA[nt], bhiB[nt]);
+            mma_m16n8k8_tf32(d[nt], lo[0][0], lo[1][0], lo[0][1], lo[1][1], bhiA[nt], bhiB[nt]);
+            mma_m16n8k8_tf32(d[nt], hi[0][0], hi[1][0], hi[0][1], hi[1][1], bloA[nt], bloB[nt]);
+            mma_m16n8k8_tf32(d[nt], a8_0, a8_1, 0u, 0u, b8[nt], 0u);
+        }
+        uint16_t* o = out + (static_cast<size_t>(n) * total + blk * 16 + g) * 32 + 8 * tq;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const float v0 = d[nt][2 * r], v1 = d[nt][2 * r + 1];
+                pk[nt] = pack2_t<FP16>(fmaxf(v0, v0 * slope), fmaxf(v1, v1 * slope));
+            }
+            if (valid[r]) *reinterpret_cast<uint4*>(o + r * 8 * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // head gather: second half of the decoder tail when dec.12 ran in OUT_SHUFFLE2_HEAD mode.  part fp32 [N,h,w,16] holds,
 // per LOW-res pixel (yl,xl), the 4x4 patch (origin (2yl-1, 2xl-1)) of head-conv partial sums of its own 2x2 hi-res
 // block.  Output pixel (Y,X) is covered by the patches of 2x2 low-res pixels; sum them, add the bias, sigmoid, clamp

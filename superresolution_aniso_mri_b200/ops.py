@@ -142,6 +142,14 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
 HEAD_ON_TENSOR_CORES = os.environ.get("AESR_HEAD_TC", "0") != "0"
 
 
+TUNE_CONV_DEBUG, TUNE_CONV_T, TUNE_CONV_NBUF, TUNE_CONV_STAGES, TUNE_HEAD_MMA = range(5)
+
+
+def set_tuning(key: int, value: int) -> None:
+    """``aesr_set_tuning``: kernel-variant / profiling knobs of the conv kernel (include/aesr_b200.h), 0 = automatic."""
+    _lib.check(_lib.load().aesr_set_tuning(int(key), int(value)), "set_tuning")
+
+
 def pack_head_w16(head_w9c: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """fp32 [9,32] head filter (any device) -> 16-bit [16,32] on its device, rows 9..15 zero (GEMM N padded to 16)."""
     dtype = dtype or DEFAULT_DTYPE
