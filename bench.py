@@ -347,8 +347,10 @@ def run_ours(a):
                                        % (V, V * 54),
                            "volumes_per_gpu": V, "chunk": a.chunk, "l2": "256 MB flush buffer written between steps",
                            "accumulate": "fp32 (TMEM)", "sharding": "volumes over ranks, no collective"},
-                "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": host_in.numel() * 4,
-                        "d2h_bytes_per_step": host_out.numel() * 4, "ms_per_step": float(e2e_ms.item()) / a.steps},
+                "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": pipe.h2d_bytes,
+                        "d2h_bytes_per_step": pipe.d2h_bytes, "d2h_note": "synthesized slices only; the kept slices = "
+                        "clamp(input) are written into the pinned output by a host thread inside the timed region"
+                        if pipe.host_kept else "whole HR volumes", "ms_per_step": float(e2e_ms.item()) / a.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
                 "cpu_baseline": {"value": cpu_rate, "unit": "slices/s", "cores": cores, "kind": "port",
                                  "sample": "%d volumes (%d synthesized slices), best of 3, %.2f s; oracle port of "

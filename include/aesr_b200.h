@@ -162,6 +162,14 @@ int aesr_lerp_pairs_act(const float* pre, const int* pa, const int* pb, const fl
  * src fp32 [N,HW], dst fp32 [*,HW], out_index int32 [N] or NULL (identity).  N <= 65535 per call. */
 int aesr_place_slices(const float* src, float* dst, const int* out_index, int N, int HW, int do_clamp, void* stream);
 
+/* Host pipeline utility: `outer` strided 2-D copies (cudaMemcpy2DAsync: `rows` rows of `width` bytes, row pitches dpitch /
+ * spitch, consecutive 2-D blocks dst_outer_stride / src_outer_stride bytes apart) between PINNED host memory and the device,
+ * stream-ordered.  to_host != 0: device -> host.  Used to download only the SYNTHESIZED slices of the HR volumes
+ * (generate_hr_volumes.py:58-66 interleaves them with the kept input slices, which the host already holds): one block per
+ * volume, one row per slice pair = A consecutive slices.  No reference counterpart (the reference copies whole tensors). */
+int aesr_copy_rows_async(void* dst, size_t dst_outer_stride, size_t dpitch, const void* src, size_t src_outer_stride,
+                         size_t spitch, size_t width, size_t rows, size_t outer, int to_host, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Training step (kwatsch/cardiac/trainer_ae.py:10-50, kwatsch/brain/trainer_ae.py:92-132).  Gradient tensors are
  * ALWAYS bf16 NHWC (fp32 range); activations are `dtype`; reductions, parameters and optimizer state are fp32.

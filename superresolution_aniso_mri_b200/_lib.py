@@ -34,6 +34,7 @@ _SIGNATURES = {
     "aesr_head_fwd": (I, [P, P, P, P, P, I, I, I, I, c_size_t, I, I, P]),
     "aesr_lerp_latents": (I, [P, P, P, P, P, P, P, I, I, I, I, P]),
     "aesr_place_slices": (I, [P, P, P, I, I, I, P]),
+    "aesr_copy_rows_async": (I, [P, c_size_t, c_size_t, P, c_size_t, c_size_t, c_size_t, c_size_t, c_size_t, I, P]),
     "aesr_lerp_pairs": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "aesr_lerp_pairs_act": (I, [P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
     "aesr_probe_halo_conv": (I, [P, P, P, I, I, I, I, I, I, I, I, P]),

@@ -463,7 +463,7 @@ int aesr_stem_fwd(const float* x, const float* weff_beff_b1_host, void* out, int
     if (static_cast<size_t>(H + 2) * (W + 2) > (1u << 28)) return fail(AESR_ERR_INVALID, "stem_fwd: image too large");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const float *weff = weff_beff_b1_host, *beff = weff_beff_b1_host + 9 * 32, *b1 = weff_beff_b1_host + 18 * 32;
-    if (tune(5) == 0) {
+    if (tune(5) != 1) {
         // warp-level tensor-core stem: bias of the nine border classes (first / inner / last row x column) in fp32
         StemMmaParams mp;
         memcpy(mp.weff, weff, sizeof(mp.weff));
@@ -480,14 +480,26 @@ int aesr_stem_fwd(const float* x, const float* weff_beff_b1_host, void* out, int
                     mp.bias_tab[(cy * 3 + cx) * 32 + c] = t;
                 }
         const int blocks = ((H + 2) * (W + 2) + 15) / 16;
-        int gy = (8 * g_sm_count * 4 + blocks - 1) / blocks;          // ~8 resident CTAs of 4 warps per SM, the rest loops over images
-        if (gy > N) gy = N;
-        if (gy < 1) gy = 1;
-        const dim3 grid((blocks + 3) / 4, gy);
-        if (dtype == AESR_DT_FP16)
-            stem_mma_kernel<true><<<grid, 128, 0, s>>>(x, mp, static_cast<uint16_t*>(out), N, H, W, slope);
+        const int gx = (blocks + 3) / 4;
+        // images are dealt to gridDim.y CTAs per pixel block; pick the split whose CTA count fills whole waves of the
+        // resident capacity (5 CTAs of 128 threads per SM at 91 registers) -- 265 x 5 CTAs left the second wave 79 % full
+        const long cap = 5L * g_sm_count;
+        int gy = 1;
+        double best = -1.0;
+        for (int c = 1; c <= 16 && c <= N; ++c) {
+            const long total = static_cast<long>(gx) * c;
+            const double fill = static_cast<double>(total) / (static_cast<double>((total + cap - 1) / cap) * cap);
+            if (fill > best + 0.02) { best = fill; gy = c; }
+        }
+        const dim3 grid(gx, gy);
+        const int variant = tune(5);
+        if (variant == 2) {
+            if (dtype == AESR_DT_FP16) stem_mma_kernel<true, 1><<<grid, 128, 0, s>>>(x, mp, static_cast<uint16_t*>(out), N, H, W, slope);
+            else stem_mma_kernel<false, 1><<<grid, 128, 0, s>>>(x, mp, static_cast<uint16_t*>(out), N, H, W, slope);
+        } else if (dtype == AESR_DT_FP16)
+            stem_mma_kernel<true, 3><<<grid, 128, 0, s>>>(x, mp, static_cast<uint16_t*>(out), N, H, W, slope);
         else
-            stem_mma_kernel<false><<<grid, 128, 0, s>>>(x, mp, static_cast<uint16_t*>(out), N, H, W, slope);
+            stem_mma_kernel<false, 3><<<grid, 128, 0, s>>>(x, mp, static_cast<uint16_t*>(out), N, H, W, slope);
         return check_launch("stem_mma");
     }
     StemParams sp;
@@ -625,6 +637,22 @@ int aesr_place_slices(const float* src, float* dst, const int* out_index, int N,
     if (gx > 64) gx = 64;
     place_slices_kernel<<<dim3(gx, N), block, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, out_index, N, HW, do_clamp);
     return check_launch("place_slices");
+}
+
+int aesr_copy_rows_async(void* dst, size_t dst_outer_stride, size_t dpitch, const void* src, size_t src_outer_stride,
+                         size_t spitch, size_t width, size_t rows, size_t outer, int to_host, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!dst || !src || width == 0 || width > dpitch || width > spitch)
+        return fail(AESR_ERR_INVALID, "copy_rows_async: bad arguments (width %zu, pitches %zu / %zu)", width, dpitch, spitch);
+    const cudaMemcpyKind kind = to_host ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice;
+    for (size_t o = 0; o < outer; ++o) {
+        const cudaError_t e = cudaMemcpy2DAsync(static_cast<char*>(dst) + o * dst_outer_stride, dpitch,
+                                                static_cast<const char*>(src) + o * src_outer_stride, spitch, width, rows,
+                                                kind, static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) return fail(AESR_ERR_CUDA, "copy_rows_async: %s", cudaGetErrorString(e));
+    }
+    return AESR_OK;
 }
 
 int aesr_probe_halo_conv(const void* x, const void* w_packed, float* out, int N, int H, int W, int x0, int y0, int n,

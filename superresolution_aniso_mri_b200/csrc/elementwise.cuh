@@ -348,7 +348,7 @@ __device__ __forceinline__ void tf32_split(float v, uint32_t& hi, uint32_t& lo) 
     lo = __float_as_uint(v - __uint_as_float(hi)) & 0xFFFFE000u;
 }
 
-template <bool FP16>
+template <bool FP16, int TERMS>      // TERMS = 3: xhi*Whi + xlo*Whi + xhi*Wlo (fp32-exact); 1: xhi*Whi only (profiling)
 __global__ void __launch_bounds__(128)
 stem_mma_kernel(const float* __restrict__ x, const __grid_constant__ StemMmaParams sp, uint16_t* __restrict__ out, int N,
                 int H, int W, float slope) {
@@ -420,8 +420,10 @@ stem_mma_kernel(const float* __restrict__ x, const __grid_constant__ StemMmaPara
             d[nt][0] = binit[0][2 * nt]; d[nt][1] = binit[0][2 * nt + 1];
             d[nt][2] = binit[1][2 * nt]; d[nt][3] = binit[1][2 * nt + 1];
             mma_m16n8k8_tf32(d[nt], hi[0][0], hi[1][0], hi[0][1], hi[1][1], bhiA[nt], bhiB[nt]);
-            mma_m16n8k8_tf32(d[nt], lo[0][0], lo[1][0], lo[0][1], lo[1][1], bhiA[nt], bhiB[nt]);
-            mma_m16n8k8_tf32(d[nt], hi[0][0], hi[1][0], hi[0][1], hi[1][1], bloA[nt], bloB[nt]);
+            if (TERMS == 3) {
+                mma_m16n8k8_tf32(d[nt], lo[0][0], lo[1][0], lo[0][1], lo[1][1], bhiA[nt], bhiB[nt]);
+                mma_m16n8k8_tf32(d[nt], hi[0][0], hi[1][0], hi[0][1], hi[1][1], bloA[nt], bloB[nt]);
+            }
             mma_m16n8k8_tf32(d[nt], a8_0, a8_1, 0u, 0u, b8[nt], 0u);
         }
         uint16_t* o = out + (static_cast<size_t>(n) * total + blk * 16 + g) * 32 + 8 * tq;

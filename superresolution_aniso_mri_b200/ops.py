@@ -325,6 +325,20 @@ def lerp_pairs_act(pre: torch.Tensor, pa: torch.Tensor, pb: torch.Tensor, wa: to
     return out
 
 
+def copy_rows_async(dst: torch.Tensor, src: torch.Tensor, dst_offset: int, src_offset: int, outer: int,
+                    dst_outer_stride: int, src_outer_stride: int, rows: int, dpitch: int, spitch: int, width: int,
+                    stream: torch.cuda.Stream) -> None:
+    """``outer`` strided 2-D copies between a PINNED host tensor and a device tensor (either direction, taken from
+    which of the two is on the device); offsets / strides / pitches / width in BYTES.  Stream-ordered on ``stream``."""
+    to_host = src.is_cuda
+    lib = _dev(src if to_host else dst)
+    host = dst if to_host else src
+    assert host.is_pinned() and dst.is_contiguous() and src.is_contiguous()
+    _lib.check(lib.aesr_copy_rows_async(dst.data_ptr() + dst_offset, dst_outer_stride, dpitch, src.data_ptr() + src_offset,
+                                        src_outer_stride, spitch, width, rows, outer, int(to_host), stream.cuda_stream),
+               "copy_rows_async")
+
+
 def place_slices(src: torch.Tensor, dst: torch.Tensor, out_index: Optional[torch.Tensor], clamp: bool = True) -> None:
     """dst[out_index[n]] = clamp(src[n], 0, 1) for fp32 images; src [N,HW...] contiguous, dst [*,HW...] contiguous."""
     lib = _dev(src)

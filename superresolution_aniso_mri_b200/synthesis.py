@@ -10,6 +10,8 @@ from the reference cannot change a value.
 """
 from __future__ import annotations
 
+import collections
+import concurrent.futures
 from typing import Optional, Sequence
 
 import numpy as np
@@ -45,17 +47,54 @@ def pair_plan(num_slices: int, num_alphas: int, w_hi: np.ndarray, w_lo: np.ndarr
     return ia, ib, w_hi[k].astype(np.float32), w_lo[k].astype(np.float32), out_idx
 
 
+_PLAN_CACHE: "collections.OrderedDict" = collections.OrderedDict()
+_PLAN_CACHE_MAX = 16
+
+
+def _synthesis_plan(V: int, Z: int, alpha_range: Sequence[float], dev: torch.device) -> dict:
+    """Device-resident index / weight tables of a (V volumes, Z slices, alphas) synthesis problem, cached per shape: a
+    steady stream of equally shaped batches then issues no host->device copies and no index arithmetic kernels (the
+    pageable-memory copies of these tables used to block the host behind the previous batch's kernels, which kept the
+    copy / compute pipeline of HostPipeline from running ahead, profiles/README.md r01x)."""
+    a64 = np.asarray(alpha_range, dtype=np.float64)
+    key = (V, Z, a64.tobytes(), dev.type, dev.index)
+    plan = _PLAN_CACHE.get(key)
+    if plan is not None:
+        _PLAN_CACHE.move_to_end(key)
+        return plan
+    A = len(a64)
+    Zo = (Z - 1) * (A + 1) + 1
+    w_hi, w_lo = interp_weights(alpha_range)
+    n = np.arange(V * Z, dtype=np.int64)
+    q = np.arange(V * max(Z - 1, 0), dtype=np.int64)
+    v_of, i_of = (q // (Z - 1), q % (Z - 1)) if Z > 1 else (q, q)
+    oi_np = (v_of * Zo + i_of * (A + 1) + 1)[:, None] + np.arange(A, dtype=np.int64)[None, :]
+
+    def dev_i32(x):
+        return torch.from_numpy(np.ascontiguousarray(x, dtype=np.int32)).to(dev)
+
+    plan = {"idx": dev_i32(n), "oi_kept": dev_i32((n // Z) * Zo + (n % Z) * (A + 1)),
+            "pa": dev_i32(v_of * Z + i_of + 1), "pb": dev_i32(v_of * Z + i_of), "oi": dev_i32(oi_np.reshape(-1)),
+            "wa": torch.from_numpy(w_hi.astype(np.float32)).to(dev), "wb": torch.from_numpy(w_lo.astype(np.float32)).to(dev),
+            "one": torch.ones(1, dtype=torch.float32, device=dev), "zero": torch.zeros(1, dtype=torch.float32, device=dev)}
+    _PLAN_CACHE[key] = plan
+    while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
 @torch.no_grad()
 def synthesize_volumes(model, volumes: torch.Tensor, alpha_range: Sequence[float], use_original: bool = True,
-                       decode_chunk: int = 4096, encode_chunk: int = 2048, out: Optional[torch.Tensor] = None
-                       ) -> torch.Tensor:
+                       decode_chunk: int = 4096, encode_chunk: int = 2048, out: Optional[torch.Tensor] = None,
+                       place_kept: bool = True) -> torch.Tensor:
     """Batched synthesis of V independent volumes.  volumes: [V,Z,H,W] fp32 (device) -> [V,(Z-1)(A+1)+1,H,W] fp32.
 
     ``decode_chunk`` / ``encode_chunk`` bound the slices per kernel launch.  Large chunks win: measured on B200
     (profiles/README.md, chunk sweep) a launch of the persistent conv kernel carries ~10 us of fixed cost (launch,
     TMEM allocation, filter-bank load, tail wave), which at 256 slices per launch was 16 % of the step -- more than
     keeping the inter-layer tensors L2-resident ever bought.  The chunks are additionally capped so that the largest
-    inter-layer tensor of a launch stays below ~4 GiB."""
+    inter-layer tensor of a launch stays below ~4 GiB.  ``place_kept=False`` (with ``use_original``) leaves the kept
+    slices of ``out`` unwritten: the caller already holds them (HostPipeline forms clamp(input) on the host)."""
     assert volumes.dim() == 4 and volumes.is_cuda
     V, Z, H, W = volumes.shape
     cap = max(1, (4 << 30) // ((H + 2) * (W + 2) * 64))           # stem output: 32 channels x 2 bytes per pixel
@@ -90,14 +129,14 @@ def synthesize_volumes(model, volumes: torch.Tensor, alpha_range: Sequence[float
             a = ops.lerp_pairs(z, pa_, pb_, wa_, wb_)
         model.decode_nhwc_eval(a, out=out, out_image_stride=H * W, out_index=oi_, after_first=fold)
 
+    plan = _synthesis_plan(V, Z, alpha_range, dev)
     # ---- kept slices: originals (clamped, generate_hr_volumes.py:44,67) or reconstructions
-    idx = torch.arange(V * Z, dtype=torch.int32, device=dev)
-    oi = ((idx // Z) * Zo + (idx % Z) * (A + 1)).to(torch.int32)
+    idx, oi = plan["idx"], plan["oi_kept"]
     if use_original:
-        ops.place_slices(flat_in, out, oi, clamp=True)
+        if place_kept:
+            ops.place_slices(flat_in, out, oi, clamp=True)
     else:       # decode(z_i) = the blend with weights (1, 0) of slice i with itself (1*z + 0*z = z exactly)
-        one = torch.ones(1, dtype=torch.float32, device=dev)
-        zero = torch.zeros(1, dtype=torch.float32, device=dev)
+        one, zero = plan["one"], plan["zero"]
         for s in range(0, V * Z, decode_chunk):
             e = min(s + decode_chunk, V * Z)
             blend_decode(idx[s:e], idx[s:e], one, zero, oi[s:e].contiguous())
@@ -106,14 +145,7 @@ def synthesize_volumes(model, volumes: torch.Tensor, alpha_range: Sequence[float
     # ---- all (volume, pair, alpha) lerp+decode problems
     #      pair q = v*(Z-1)+i blends z[v*Z+i+1] (weight w_hi[k]) and z[v*Z+i] (w_lo[k]); problem m = q*A + k lands at
     #      out[v*Zo + i*(A+1) + 1 + k].  The two fp32 operands of a pair are read once for all A alphas.
-    q = np.arange(V * (Z - 1), dtype=np.int64)
-    v_of, i_of = q // (Z - 1), q % (Z - 1)
-    pa = torch.from_numpy((v_of * Z + i_of + 1).astype(np.int32)).to(dev, non_blocking=True)
-    pb = torch.from_numpy((v_of * Z + i_of).astype(np.int32)).to(dev, non_blocking=True)
-    oi_np = (v_of * Zo + i_of * (A + 1) + 1)[:, None] + np.arange(A, dtype=np.int64)[None, :]
-    oi = torch.from_numpy(oi_np.reshape(-1).astype(np.int32)).to(dev, non_blocking=True)
-    wa = torch.from_numpy(w_hi.astype(np.float32)).to(dev, non_blocking=True)
-    wb = torch.from_numpy(w_lo.astype(np.float32)).to(dev, non_blocking=True)
+    pa, pb, oi, wa, wb = plan["pa"], plan["pb"], plan["oi"], plan["wa"], plan["wb"]
     pairs_per_chunk = max(1, decode_chunk // A)
     for s in range(0, V * (Z - 1), pairs_per_chunk):
         e = min(s + pairs_per_chunk, V * (Z - 1))
@@ -126,13 +158,22 @@ class HostPipeline:
     [V,(Z-1)(A+1)+1,H,W] back in pinned host memory.  The V volumes are cut into groups; group g+1's host->device copy
     and group g-1's device->host copy run on their own streams while group g computes (double-buffered staging).
 
+    Only the SYNTHESIZED slices cross PCIe on the way back (``host_kept``, default): the kept slices of the HR volume are
+    clamp(input, 0, 1) of slices the host already holds (generate_hr_volumes.py:44,58-67), so a host worker thread writes
+    them into ``host_out`` while the GPU computes, and the download is one strided 2-D copy per volume (rows = slice
+    pairs, A slices each).  The device->host copy bounds this path (268 MB per 64-volume step at ~55 GB/s = 4.9 ms against
+    4.2 ms of compute, profiles/README.md); leaving out the Z of (Z-1)(A+1)+1 kept slices cuts it by 16 % for A = 6.
+
     ``run(..., wait=True)`` (default) returns stream-ordered: the caller's stream has waited for the last device->host
-    copy.  A caller that feeds a sequence of batches passes ``wait=False`` and calls ``wait()`` (or ``synchronize()``)
+    copy and the host worker has finished.  A caller that feeds a sequence of batches passes ``wait=False`` and calls ``wait()`` (or ``synchronize()``)
     once at the end: the staging buffers and their events persist across calls, so the copies of batch i overlap the
     compute of batch i+1 and the only serial parts left are the first upload and the last download."""
 
-    def __init__(self, model, V, Z, H, W, alpha_range, groups: int = 2, chunk: int = 4096):
+    def __init__(self, model, V, Z, H, W, alpha_range, groups: int = 2, chunk: int = 4096, host_kept: bool = True):
         self.model, self.ar, self.chunk = model, list(alpha_range), chunk
+        self.host_kept = bool(host_kept) and len(self.ar) >= 1 and Z >= 2
+        self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=1) if self.host_kept else None
+        self.jobs = []
         dev = next(model.parameters()).device
         self.dev = dev
         groups = max(1, min(groups, V))
@@ -145,6 +186,9 @@ class HostPipeline:
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         self.in_free = [torch.cuda.Event() for _ in range(2)]     # compute finished reading d_in[b]
         self.out_free = [torch.cuda.Event() for _ in range(2)]    # copy-out finished reading d_out[b]
+        # bytes crossing PCIe per run() (what bench.py reports): all inputs up, synthesized (or all) slices down
+        self.h2d_bytes = V * Z * H * W * 4
+        self.d2h_bytes = V * ((Z - 1) * A if self.host_kept else Zo) * H * W * 4
         self.used = [False, False]
         self.turn = 0                                             # staging buffer of the next group (persists over calls)
 
@@ -164,14 +208,26 @@ class HostPipeline:
             if self.used[b]:
                 main.wait_event(self.out_free[b])
             synthesize_volumes(self.model, self.d_in[b][:n], self.ar, use_original=True, out=self.d_out[b][:n],
-                               decode_chunk=self.chunk, encode_chunk=self.chunk)
+                               decode_chunk=self.chunk, encode_chunk=self.chunk, place_kept=not self.host_kept)
             self.in_free[b].record(main)
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(done)
-                host_out[s:e].copy_(self.d_out[b][:n], non_blocking=True)
+                if self.host_kept:
+                    # volume v: rows i = 0..Z-2 of A consecutive slices starting at slice i*(A+1)+1, pitch (A+1) slices
+                    Z, A = host_in.shape[1], len(self.ar)
+                    sl = host_out.shape[2] * host_out.shape[3] * 4          # bytes per slice
+                    vol = host_out.shape[1] * sl
+                    ops.copy_rows_async(host_out, self.d_out[b], s * vol + sl, sl, outer=n, dst_outer_stride=vol,
+                                        src_outer_stride=vol, rows=Z - 1, dpitch=(A + 1) * sl, spitch=(A + 1) * sl,
+                                        width=A * sl, stream=self.s_out)
+                else:
+                    host_out[s:e].copy_(self.d_out[b][:n], non_blocking=True)
                 self.out_free[b].record(self.s_out)
+            if self.host_kept:
+                self.jobs.append(self.pool.submit(torch.clamp, host_in[s:e], 0.0, 1.0,
+                                                  out=host_out[s:e, ::len(self.ar) + 1]))
             self.used[b] = True
         if wait:
             self.wait()
@@ -182,9 +238,16 @@ class HostPipeline:
         for b in range(2):
             if self.used[b]:
                 main.wait_event(self.out_free[b])
+        self._join_host()
+
+    def _join_host(self) -> None:
+        jobs, self.jobs = self.jobs, []
+        for j in jobs:
+            j.result()
 
     def synchronize(self) -> None:
         """Block the host until every result issued so far is in host memory."""
+        self._join_host()
         for b in range(2):
             if self.used[b]:
                 self.out_free[b].synchronize()

@@ -448,14 +448,18 @@ def test_odd_sizes_and_batch_invariance_at_full_size(dev):
     assert (got - want).abs().max().item() < 8e-2 and (got - want).abs().mean().item() < 3e-3
 
 
-def test_host_pipeline_matches_device_path(dev):
+@pytest.mark.parametrize("host_kept", [True, False])
+def test_host_pipeline_matches_device_path(dev, host_kept):
+    """host_kept: only the synthesized slices are downloaded (strided 2-D copies), the kept slices = clamp(input) are
+    written by the host worker; otherwise whole volumes come back.  Inputs exceed [0,1] so the clamp is exercised."""
     from superresolution_aniso_mri_b200 import synthesis
     args = O.default_args(128, 32)
     model = make_model(args, O.calibrated_state(args), dev)
     ar = O.alpha_range_for(6)
-    host_in = torch.rand(5, 10, 128, 128, generator=torch.Generator().manual_seed(6)).pin_memory()
-    host_out = torch.empty(5, 64, 128, 128).pin_memory()
-    pipe = synthesis.HostPipeline(model, 5, 10, 128, 128, ar, groups=3)
+    host_in = (torch.rand(5, 10, 128, 128, generator=torch.Generator().manual_seed(6)) * 1.2 - 0.1).pin_memory()
+    host_out = torch.full((5, 64, 128, 128), -7.0).pin_memory()
+    pipe = synthesis.HostPipeline(model, 5, 10, 128, 128, ar, groups=3, host_kept=host_kept)
+    assert pipe.d2h_bytes == 5 * (54 if host_kept else 64) * 128 * 128 * 4
     pipe.run(host_in, host_out)
     pipe.run(host_in, host_out)                                   # buffer reuse across calls
     torch.cuda.synchronize()

@@ -16,6 +16,7 @@ from superresolution_aniso_mri_b200 import ops  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--stem-only", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 dt = torch.float16
@@ -41,7 +42,7 @@ wp = ops.pack_conv3x3_weight_up2fold(torch.randn(32, cin, 3, 3, device=dev) * 0.
 hw9 = torch.randn(9, 32) * 0.1
 out = torch.empty(n, hw, hw, 16, device=dev)
 fn = lambda: ops.conv3x3_up2_head(x, wp, b, hw9, out=out)      # noqa: E731
-for variant in (0, 1):
+for variant in (() if a.stem_only else (0, 1)):
     ops.set_tuning(ops.TUNE_HEAD_MMA, variant)
     print("== dec.12+head, head on %s" % ("warp MMA" if variant else "CUDA cores"))
     for dbg in (0, 4, 8, 12, 32, 2, 34, 40, 44, 46):
@@ -64,11 +65,12 @@ args["device"] = "cuda:0"
 m = VanillaACAI(args).eval()
 sp = m._stem()
 xs = torch.rand(640, 1, 128, 128, device=dev)
-for cuda_cores in (1, 0, 1, 0):
-    ops.set_tuning(5, cuda_cores)
+for variant in (1, 0, 2, 1, 0, 2):
+    ops.set_tuning(5, variant)
     ms = timed(lambda: ops.stem(xs, sp))
     print("stem n=640 (%s): %.3f ms  %.0f GB/s (algorithmic 4 B/px in + 64 B/px out)" % (
-        "CUDA cores" if cuda_cores else "warp MMA", ms, 640 * (128 * 128 * 4 + 130 * 130 * 64) / ms / 1e6))
+        ("warp MMA, 3 tf32 terms", "CUDA cores", "warp MMA, 1 tf32 term")[variant], ms,
+        640 * (128 * 128 * 4 + 130 * 130 * 64) / ms / 1e6))
 ops.set_tuning(5, 1)
 r0 = ops.stem(xs[:8], sp).float()
 ops.set_tuning(5, 0)
