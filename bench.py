@@ -319,7 +319,7 @@ def run_ours(a):
         for name in ("stem", "lerp", "head"):
             if name in kernel_ms and kernel_ms[name] > 0:
                 gbs = mem_bytes[name] / (kernel_ms[name] * 1e-3) / 1e9
-                hbm.append({"kernel": {"stem": "stem_conv", "lerp": "lerp_pairs_act", "head": "head_gather"}[name],
+                hbm.append({"kernel": {"stem": "stem_mma", "lerp": "lerp_pairs_act", "head": "head_gather"}[name],
                             "algorithmic_bytes": mem_bytes[name], "ms": kernel_ms[name], "achieved_gbs": gbs,
                             "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]})
         roof = {"bound": "tensor", "kernel": "conv3x3_halo_kernel (tcgen05, all %d launches of a step)" % n_conv,

@@ -498,6 +498,31 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) o4[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
             }
+        } else if ((MODE == OUT_SAME || MODE == OUT_SHUFFLE2) && p.BN >= 64) {
+            // Lane pairs (x, x+1) trade halves so that every store instruction writes whole 32-byte sectors: lane 2i
+            // holds pixel P's channels [c0, c0+16) = 16-byte halves A0 A1, lane 2i+1 pixel P+1's B0 B1.  Stored directly
+            // (A0 | B0, then A1 | B1) each STG.128 touches 32 half-written sectors; after one exchange the pair writes
+            // A0 A1 (one sector of P), then B0 B1 (one sector of P+1): 16 full sectors per instruction.  At launch sizes
+            // whose outputs stream to HBM the LSU's sector rate made the stores additive to the MMA time (dec.6:
+            // 0.54 ms with, 0.37 ms without stores, profiles/r01i_conv_sweep_tc_head_parked.txt).  Measured (r02a, A/B on one
+            // box): 64- and 128-column layers 5-10 % faster, the 32-column dec.8 7 % slower (its short epilogue sits on
+            // the MMA -> epilogue -> MMA latency chain and the exchange lengthens it) -- hence BN >= 64 only.
+            const uint4 p0 = pack8(v, fp16), p1 = pack8(v + 8, fp16);
+            const bool odd = lane & 1;
+            const uint4 send = odd ? p0 : p1;
+            uint4 recv;
+            recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+            recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+            recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+            recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+            const int xp = odd ? x - 1 : x + 1;                                  // partner pixel (same row of the tile)
+            const bool pstore = (y < H) && (xp < W) && !(p.debug & 4);
+            const long long pstep = (MODE == OUT_SHUFFLE2 ? 2 : 1) * static_cast<long long>(Cpix);
+            const size_t poff = odd ? off - pstep : off + pstep;
+            // instruction 1: the even lane's pixel (A0 from the even lane, A1 from the odd lane)
+            if (odd ? pstore : store) *reinterpret_cast<uint4*>(out16 + (odd ? poff + 8 : off)) = odd ? recv : p0;
+            // instruction 2: the odd lane's pixel (B0 from the even lane, B1 from the odd lane)
+            if (odd ? store : pstore) *reinterpret_cast<uint4*>(out16 + (odd ? off + 8 : poff)) = odd ? p1 : recv;
         } else if (store) {
             uint4* o4 = reinterpret_cast<uint4*>(out16 + off);
             o4[0] = pack8(v, fp16);

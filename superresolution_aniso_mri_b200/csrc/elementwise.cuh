@@ -405,12 +405,19 @@ stem_mma_kernel(const float* __restrict__ x, const __grid_constant__ StemMmaPara
         for (int r = 0; r < 2; ++r)
 #pragma unroll
             for (int i = 0; i < 3; ++i) tf32_split(xv[r][i], hi[r][i], lo[r][i]);
-        const int nn = n + gridDim.y;                       // prefetch the next image's taps
+        const int nn = n + gridDim.y;                       // next image's taps into registers ...
         if (nn < N) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
                 for (int i = 0; i < 3; ++i) xv[r][i] = off[r][i] >= 0 ? __ldg(x + nn * img + off[r][i]) : 0.f;
+        }
+        // ... and the image four iterations ahead into L2: one iteration of work (~600 cycles) does not cover a DRAM
+        // miss, ncu showed 45 % of the warp samples waiting on the first use of xv (profiles/r02a_stem_mma_full.md)
+        const int np = n + 4 * gridDim.y;
+        if (np < N) {
+            if (off[0][0] >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + np * img + off[0][0]));
+            if (off[1][2] >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(x + np * img + off[1][2]));
         }
         const uint32_t a8_0 = (tq == 1) ? lo[0][2] : (tq == 3) ? 0u : hi[0][2];
         const uint32_t a8_1 = (tq == 1) ? lo[1][2] : (tq == 3) ? 0u : hi[1][2];

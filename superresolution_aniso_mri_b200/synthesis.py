@@ -189,6 +189,7 @@ class HostPipeline:
         # bytes crossing PCIe per run() (what bench.py reports): all inputs up, synthesized (or all) slices down
         self.h2d_bytes = V * Z * H * W * 4
         self.d2h_bytes = V * ((Z - 1) * A if self.host_kept else Zo) * H * W * 4
+        self.trace = None          # set to a list to collect (tag, group, timing event) for tools/e2e_probe.py
         self.used = [False, False]
         self.turn = 0                                             # staging buffer of the next group (persists over calls)
 
@@ -207,13 +208,16 @@ class HostPipeline:
             main.wait_event(ready)
             if self.used[b]:
                 main.wait_event(self.out_free[b])
+            self._mark("compute_start", s, main)
             synthesize_volumes(self.model, self.d_in[b][:n], self.ar, use_original=True, out=self.d_out[b][:n],
                                decode_chunk=self.chunk, encode_chunk=self.chunk, place_kept=not self.host_kept)
             self.in_free[b].record(main)
             done = torch.cuda.Event()
             done.record(main)
+            self._mark("compute_end", s, main)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(done)
+                self._mark("d2h_start", s, self.s_out)
                 if self.host_kept:
                     # volume v: rows i = 0..Z-2 of A consecutive slices starting at slice i*(A+1)+1, pitch (A+1) slices
                     Z, A = host_in.shape[1], len(self.ar)
@@ -225,12 +229,19 @@ class HostPipeline:
                 else:
                     host_out[s:e].copy_(self.d_out[b][:n], non_blocking=True)
                 self.out_free[b].record(self.s_out)
+                self._mark("d2h_end", s, self.s_out)
             if self.host_kept:
                 self.jobs.append(self.pool.submit(torch.clamp, host_in[s:e], 0.0, 1.0,
                                                   out=host_out[s:e, ::len(self.ar) + 1]))
             self.used[b] = True
         if wait:
             self.wait()
+
+    def _mark(self, tag, group, stream) -> None:
+        if self.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            self.trace.append((tag, group, ev))
 
     def wait(self) -> None:
         """Make the caller's current stream wait for every device->host copy issued so far (stream-ordered return)."""

@@ -105,3 +105,40 @@ for groups in (1, 2, 4):
         torch.cuda.synchronize()
         t = (time.perf_counter() - t0) / 10 * 1e3
         print("HostPipeline groups=%d host_kept=%s: %.3f ms per step (host enqueue %.3f ms)" % (groups, kept, t, t_enq))
+
+# ---- independent streams: does compute slow down the copies (or the reverse) when nothing orders them?
+sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+torch.cuda.synchronize()
+reps = 10
+with torch.cuda.stream(sa):
+    evs[0].record()
+    for _ in range(reps):
+        synthesis.synthesize_volumes(model, d_in, ar, out=d_out)
+    evs[1].record()
+with torch.cuda.stream(sb):
+    evs[2].record()
+    for _ in range(reps):
+        ops.copy_rows_async(host_out, d_out, sl, sl, outer=V, dst_outer_stride=vol, src_outer_stride=vol, rows=Z - 1,
+                            dpitch=(NI + 1) * sl, spitch=(NI + 1) * sl, width=NI * sl, stream=sb)
+        d_in.copy_(host_in, non_blocking=True)
+    evs[3].record()
+torch.cuda.synchronize()
+print("unordered, concurrent: compute %.3f ms per step, D2H rows + H2D %.3f ms per step" % (
+    evs[0].elapsed_time(evs[1]) / reps, evs[2].elapsed_time(evs[3]) / reps))
+
+# ---- timeline of the pipeline in steady state (events on the compute and the download streams)
+pipe = synthesis.HostPipeline(model, V, Z, S, S, ar, groups=2)
+for _ in range(3):
+    pipe.run(host_in, host_out, wait=False)
+pipe.synchronize()
+torch.cuda.synchronize()
+pipe.trace = []
+t_ref = torch.cuda.Event(enable_timing=True)
+t_ref.record()
+for _ in range(4):
+    pipe.run(host_in, host_out, wait=False)
+pipe.synchronize()
+torch.cuda.synchronize()
+for tag, grp, ev in pipe.trace:
+    print("  %-14s group@%-3d %8.3f ms" % (tag, grp, t_ref.elapsed_time(ev)))
