@@ -618,6 +618,9 @@ __device__ __forceinline__ void conv_epilogue_head_tile_v1(const ConvParams& p, 
 // sums, no scatter.  Per tile and thread: 576 FFMA2 + 72 LDCU.128 (was 576 + 288) and 16 final adds (was 144 + 36).
 // The phase-major version above executed ~1750 warp instructions per tile at 70 % issue utilisation against 1152-1460
 // tensor-pipe cycles of the tile's MMAs (profiles/r01k_conv_full.md): the layer was bound by this epilogue's issue slots.
+// The same loop with 1152 scalar FFMAs (uniform-register filter operand) instead of 576 FFMA2 is SLOWER (1.28 vs 1.07 ms,
+// profiles/r02f_head_scalar_vs_packed.txt): a 3-operand FFMA occupies the fp32 pipe for two cycles per warp just like an
+// FFMA2, so the packed form is the pipe's full rate and 576 x 2 cycles per tile and scheduler is this epilogue's floor.
 constexpr int HEAD_EPI_CW = 4;
 __device__ __forceinline__ void conv_epilogue_head_tile(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
                                                         uint64_t* tmem_empty_bar, const TileCoord& t) {
