@@ -264,6 +264,14 @@ int aesr_percentile_normalize(const float* x, float* out, size_t n, double q_lo,
 int aesr_pad_crop_gather(const float* in, float* out, const int* top, const int* left, int B, int C, int Hin, int Win,
                          int Hout, int Wout, void* stream);
 
+/* Fused training augmentation of a batch of fp32 samples [B,C,Hin,Win] -> [B,C,P,P]: composite pad/crop window
+ * (AdjustToPatchSize / CenterCrop / RandomCrop, datasets/shared_transforms.py:389-447, 297-363, 48-120; top/left may be
+ * negative = zero padding), np.rot90 by rot_k[b] quarter turns (RandomRotation :224-254; NULL = none) and the sigmoid
+ * contrast 1/(1+exp(gain[b]*(cutoff[b]-x))) of RandomIntensity (:366-386; gain/cutoff NULL = none) on the channels whose
+ * bit is set in chan_mask (`slice_mask`).  The draws come from the caller (numpy RandomState stream preserved on the host). */
+int aesr_augment_gather(const float* in, float* out, const int* top, const int* left, const int* rot_k, const float* gain,
+                        const float* cutoff, unsigned chan_mask, int B, int C, int Hin, int Win, int P, void* stream);
+
 /* DIAGNOSTIC (not on the product path): one 16x8 tile of a 64->64 bf16 conv computed from a single TMA halo load with
  * row-shifted UMMA descriptors; used by tools/gpu_diag.py to establish what the hardware's swizzle addressing does.
  * out fp32 [128][64] raw accumulators. */

@@ -299,6 +299,46 @@ def random_intensity(img: np.ndarray, gain: float, cutoff: float) -> np.ndarray:
     return 1.0 / (1.0 + np.exp(gain * (cutoff - img)))
 
 
+def random_rotation(img: np.ndarray, k: int) -> np.ndarray:
+    """datasets/shared_transforms.py:224-254 (RandomRotation): np.rot90 by k quarter turns in the last two axes."""
+    return np.rot90(img, k, (img.ndim - 2, img.ndim - 1)).copy()
+
+
+def augment_sample(img: np.ndarray, rs: np.random.RandomState, width: int, aug_patch: Optional[int] = None,
+                   center: bool = False, intensity_first: bool = True, slice_mask=None) -> Tuple[np.ndarray, dict]:
+    """The training transform chain of one sample [C,H,W] with the reference's RandomState draw order:
+    ACDC (train_cardiac_aesr.py:90-96): AdjustToPatchSize(aug) -> CenterCrop(aug) -> RandomCrop(width) ->
+    RandomIntensity -> RandomRotation (``intensity_first``); brains (datasets/common_brains.py:55-57,77-80):
+    [AdjustToPatchSize(aug)] -> RandomCrop(width) -> RandomRotation -> RandomIntensity.
+    Returns the augmented sample and the draws {top, left, gain, cutoff, k}."""
+    x = img
+    if aug_patch is not None:
+        x = adjust_to_patch_size(x, aug_patch)
+        if center:
+            x = center_crop(x, aug_patch)
+    top, left = random_crop_offsets(rs, x.shape[-2], x.shape[-1], width)
+    x = x[..., top:top + width, left:left + width] if x.shape[-1] != width or x.shape[-2] != width else x
+
+    def intensity(v):
+        gain = rs.uniform(2.5, 7.5)
+        cutoff = rs.uniform(0.25, 0.75)
+        if slice_mask is None:
+            return random_intensity(v, gain, cutoff), gain, cutoff
+        v = v.copy()
+        v[slice_mask] = random_intensity(v[slice_mask], gain, cutoff)
+        return v, gain, cutoff
+
+    if intensity_first:
+        x, gain, cutoff = intensity(x)
+        k = rs.randint(0, 4)
+        x = random_rotation(x, k)
+    else:
+        k = rs.randint(0, 4)
+        x = random_rotation(x, k)
+        x, gain, cutoff = intensity(x)
+    return x, {"top": top, "left": left, "gain": gain, "cutoff": cutoff, "k": k}
+
+
 def prepare_batch_pairs(batch_images: torch.Tensor) -> Dict[str, torch.Tensor]:
     """datasets/common_brains.py:285-321 / datasets/ACDC/data4d_simple.py:327-387 ('repeat'):
     [B,3,H,W] -> image [2B,1,H,W] (all 'from' then all 'to'), slice_between [B,1,H,W]."""

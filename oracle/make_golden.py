@@ -329,12 +329,53 @@ def gold_vif():
     _save("vif_pins.npz", **out)
 
 
+def gold_augment():
+    """Training transform chains (datasets/shared_transforms.py) with a shared RandomState: the ACDC order
+    (train_cardiac_aesr.py:90-96) and the brain order (datasets/common_brains.py:77-80).  Pins the oracle's
+    augment_sample (values AND the RandomState draw order) against the reference classes."""
+    rb.bootstrap()
+    import datasets.shared_transforms as stf
+    out = {}
+    g = np.random.RandomState(21)
+    cases = (("acdc", dict(width=128, aug_patch=160, center=True, intensity_first=True), (3, 150, 171)),
+             ("acdc_small", dict(width=64, aug_patch=96, center=True, intensity_first=True), (3, 70, 101)),
+             ("oasis", dict(width=64, aug_patch=220, center=False, intensity_first=False), (3, 176, 208)),
+             ("dhcp_crop", dict(width=128, aug_patch=None, center=False, intensity_first=False), (3, 256, 256)))
+    for name, kw, shape in cases:
+        rs_ref, rs_mine = np.random.RandomState(4321), np.random.RandomState(4321)
+        chain = []
+        if kw["aug_patch"] is not None:
+            chain.append(stf.AdjustToPatchSize((kw["aug_patch"], kw["aug_patch"])))
+            if kw["center"]:
+                chain.append(stf.CenterCrop((kw["aug_patch"], kw["aug_patch"])))
+        chain.append(stf.RandomCrop(kw["width"], rs=rs_ref))
+        if kw["intensity_first"]:
+            chain += [stf.RandomIntensity(rs=rs_ref, slice_mask=None), stf.RandomRotation(rs_ref)]
+        else:
+            chain += [stf.RandomRotation(rs=rs_ref), stf.RandomIntensity(rs=rs_ref)]
+        draws = []
+        for i in range(4):
+            img = g.rand(*shape).astype(np.float32)
+            sample = {"image": img.copy()}
+            for t in chain:
+                sample = t(sample)
+            want = np.asarray(sample["image"])
+            got, d = O.augment_sample(img, rs_mine, **kw)
+            assert want.dtype == got.dtype == np.float32 and np.array_equal(want, got), (name, i)
+            draws.append([d["top"], d["left"], d["gain"], d["cutoff"], d["k"]])
+            out["%s_out%d" % (name, i)] = want[:, ::7, ::5]
+        out["%s_draws" % name] = np.array(draws, dtype=np.float64)
+        out["%s_shape" % name] = np.array(shape)
+    out["input_seed"], out["rs_seed"] = np.array(21), np.array(4321)
+    _save("augment_pins.npz", **out)
+
+
 def _sig(cls):
     return True
 
 
 ALL = {"init": gold_init, "lpips": gold_lpips_lin, "infer": gold_infer, "train_small": gold_train_small,
-       "transforms": gold_transforms, "vif": gold_vif, "train_acdc": gold_train_acdc}
+       "transforms": gold_transforms, "augment": gold_augment, "vif": gold_vif, "train_acdc": gold_train_acdc}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

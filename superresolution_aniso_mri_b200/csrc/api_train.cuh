@@ -393,4 +393,18 @@ int aesr_pad_crop_gather(const float* in, float* out, const int* top, const int*
     return check_launch("pad_crop_gather");
 }
 
+int aesr_augment_gather(const float* in, float* out, const int* top, const int* left, const int* rot_k, const float* gain,
+                        const float* cutoff, unsigned chan_mask, int B, int C, int Hin, int Win, int P, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!in || !out || !top || !left || B <= 0 || B > 65535 || C <= 0 || C > 65535 || P <= 0 || Hin <= 0 || Win <= 0)
+        return fail(AESR_ERR_INVALID, "augment_gather: bad arguments");
+    if ((gain == nullptr) != (cutoff == nullptr)) return fail(AESR_ERR_INVALID, "augment_gather: gain and cutoff go together");
+    int gx = (P * P + 255) / 256;
+    if (gx > 64) gx = 64;
+    augment_gather_kernel<<<dim3(gx, C, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, top, left, rot_k, gain, cutoff,
+                                                                                       chan_mask, C, Hin, Win, P);
+    return check_launch("augment_gather");
+}
+
 }  // extern "C"

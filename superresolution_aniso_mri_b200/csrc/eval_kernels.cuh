@@ -182,4 +182,40 @@ __global__ void pad_crop_gather_kernel(const float* __restrict__ in, float* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused training augmentation (datasets/shared_transforms.py: AdjustToPatchSize :389-447 / CenterCrop :297-363 /
+// RandomCrop :48-120 as one composite window, RandomRotation :224-254, RandomIntensity :366-386):
+//   A[y][x]   = in[b, c, y + top[b], x + left[b]] inside the source image, else 0          (P x P window)
+//   R         = np.rot90(A, k[b]):  k=1: R[i][j] = A[j][P-1-i],  k=2: A[P-1-i][P-1-j],  k=3: A[P-1-j][i]
+//   out[b,c]  = 1 / (1 + exp(gain[b] * (cutoff[b] - R)))  for the channels of chan_mask (every fp32 operation rounded
+//               separately like numpy: sub, mul, exp, add, div; exp correctly rounded through double), else R.
+// The random draws are made on the host from the caller's numpy RandomState in the reference's order.  Writes are
+// coalesced along x; the rotated reads of k = 1, 3 walk a column of the 4 B/px source (L1/L2 resident: one sample's
+// window is P*P*4 bytes).  8 B per output pixel.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void augment_gather_kernel(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ top,
+                                      const int* __restrict__ left, const int* __restrict__ rot_k,
+                                      const float* __restrict__ gain, const float* __restrict__ cutoff, unsigned chan_mask,
+                                      int C, int Hin, int Win, int P) {
+    const int b = blockIdx.z, c = blockIdx.y;
+    const int t = top[b], l = left[b], k = rot_k ? (rot_k[b] & 3) : 0;
+    const bool contrast = gain != nullptr && ((chan_mask >> (c & 31)) & 1u);
+    const float g = contrast ? gain[b] : 0.f, co = contrast ? cutoff[b] : 0.f;
+    const float* src = in + (static_cast<size_t>(b) * C + c) * Hin * Win;
+    float* dst = out + (static_cast<size_t>(b) * C + c) * P * P;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < P * P; idx += gridDim.x * blockDim.x) {
+        const int i = idx / P, j = idx - i * P;
+        const int ay = (k == 0) ? i : (k == 1) ? j : (k == 2) ? P - 1 - i : P - 1 - j;
+        const int ax = (k == 0) ? j : (k == 1) ? P - 1 - i : (k == 2) ? P - 1 - j : i;
+        const int sy = ay + t, sx = ax + l;
+        float v = (sy >= 0 && sy < Hin && sx >= 0 && sx < Win) ? __ldg(src + static_cast<size_t>(sy) * Win + sx) : 0.f;
+        if (contrast) {
+            const float u = __fmul_rn(g, __fsub_rn(co, v));
+            const float e = static_cast<float>(exp(static_cast<double>(u)));
+            v = __fdiv_rn(1.f, __fadd_rn(1.f, e));
+        }
+        dst[idx] = v;
+    }
+}
+
 }  // namespace aesr

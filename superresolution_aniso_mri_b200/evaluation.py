@@ -290,3 +290,85 @@ def random_crop(images, patch: int, rs: np.random.RandomState, device="cuda:0") 
         tops.append(rs.randint(0, h - patch))
         lefts.append(rs.randint(0, w - patch))
     return pad_crop(images, np.array(tops), np.array(lefts), patch, patch, device=device)
+
+
+def augment_batch(images, rs: np.random.RandomState, width: int, aug_patch: Optional[int] = None, center: bool = False,
+                  intensity_first: bool = True, slice_mask=None, device="cuda:0", return_draws: bool = False):
+    """The training transform chain of the reference on a batch [B,C,H,W] of equally sized samples, one kernel:
+    ACDC (train_cardiac_aesr.py:90-96): AdjustToPatchSize(aug) -> CenterCrop(aug) -> RandomCrop(width) -> RandomIntensity
+    -> RandomRotation (``intensity_first=True, center=True``); brains (datasets/common_brains.py:55-57,77-80):
+    [AdjustToPatchSize(aug)] -> RandomCrop(width) -> RandomRotation -> RandomIntensity.  The draws are taken from ``rs``
+    on the host, sample by sample, in exactly the order the reference's transform objects take them
+    (randint(0,h-P), randint(0,w-P) unless the sample already has the crop size; uniform(2.5,7.5), uniform(.25,.75);
+    randint(0,4)), so a seeded RandomState yields the reference's augmentation stream.  ``slice_mask``: boolean per
+    channel (ACDCLBL).  Returns fp32 [B,C,width,width] on ``device`` (and the draws with ``return_draws``)."""
+    x = _as_dev_f32(images, device)
+    lib = _dev(x)
+    b, c, h, w = x.shape
+    # composite window: zero-pad to >= aug_patch (left = floor(d/2)), optional centre crop to aug_patch, random crop
+    off_y = off_x = 0
+    hh, ww = h, w
+    if aug_patch is not None:
+        dh, dw = max(aug_patch - h, 0), max(aug_patch - w, 0)
+        off_y, off_x, hh, ww = -(dh // 2), -(dw // 2), h + dh, w + dw
+        if center:
+            half = int(aug_patch / 2)
+            off_y, off_x = off_y + int(hh / 2) - half, off_x + int(ww / 2) - half
+            hh = ww = 2 * half
+    tops, lefts, ks, gains, cuts = [], [], [], [], []
+    for _ in range(b):
+        if hh == width and ww == width:
+            t = l_ = 0
+        else:
+            t = rs.randint(0, hh - width)
+            l_ = rs.randint(0, ww - width)
+        if intensity_first:
+            g, cu = rs.uniform(2.5, 7.5), rs.uniform(0.25, 0.75)
+            k = rs.randint(0, 4)
+        else:
+            k = rs.randint(0, 4)
+            g, cu = rs.uniform(2.5, 7.5), rs.uniform(0.25, 0.75)
+        tops.append(t + off_y), lefts.append(l_ + off_x), ks.append(k), gains.append(g), cuts.append(cu)
+    mask = 0xFFFFFFFF
+    if slice_mask is not None:
+        sm = np.asarray(slice_mask, dtype=bool)
+        assert sm.shape == (c,) and c <= 32
+        mask = int(sum(1 << i for i in range(c) if sm[i]))
+    ti = torch.as_tensor(np.asarray([tops, lefts, ks], dtype=np.int32), device=x.device)
+    # python floats are "weak" scalars against float32 arrays in numpy: gain and cutoff act as float32
+    tf = torch.as_tensor(np.asarray([gains, cuts], dtype=np.float64).astype(np.float32), device=x.device)
+    out = torch.empty((b, c, width, width), dtype=torch.float32, device=x.device)
+    _lib.check(lib.aesr_augment_gather(x.data_ptr(), out.data_ptr(), ti[0].data_ptr(), ti[1].data_ptr(), ti[2].data_ptr(),
+                                       tf[0].data_ptr(), tf[1].data_ptr(), mask, b, c, h, w, width, _stream(x)),
+               "augment_gather")
+    if return_draws:
+        return out, {"top": np.asarray(tops) - off_y, "left": np.asarray(lefts) - off_x, "gain": np.asarray(gains),
+                     "cutoff": np.asarray(cuts), "k": np.asarray(ks)}
+    return out
+
+
+def prepare_batch_pairs(batch_dict: dict, expand_type: str = "repeat") -> dict:
+    """datasets/common_brains.py:285-321 / datasets/ACDC/data4d_simple.py:327-387, same signature and in-place dict
+    semantics: batch_dict['image'] [B,2|3,H,W] -> 'image' [2B,1,H,W] (all "from" slices, then all "to" slices) and
+    'slice_between' [B,1,H,W]; 'split' keeps 'image' and adds 'image_from' / 'image_to'.  Works on device tensors (the
+    output of ``augment_batch``): no host round trip between augmentation and the training step."""
+    batch_images = batch_dict["image"]
+    assert batch_images.size(0) % 2 == 0
+    if expand_type not in ("repeat", "split"):
+        raise ValueError("Error - prepare_batch_pairs - valid values for expand_type parameter are repeat, "
+                         "reshape, split.")
+    a = torch.unsqueeze(batch_images[:, 0], dim=1)
+    b = torch.unsqueeze(batch_images[:, 1], dim=1)
+    if batch_images.shape[1] == 3:
+        batch_dict["slice_between"] = torch.unsqueeze(batch_images[:, 2], dim=1)
+    if expand_type == "split":
+        batch_dict["image_from"], batch_dict["image_to"] = a, b
+    else:
+        batch_dict["image"] = torch.cat([a, b], dim=0)
+    return batch_dict
+
+
+def determine_interpol_coefficients(sliceid_from, sliceid_to, sliceid_between):
+    """datasets/common_brains.py:117-119 (float64; the brain trainers cast to float32, :259-260)."""
+    gap = sliceid_to - sliceid_from
+    return 1 - ((sliceid_between - sliceid_from) * 1 / gap), 1 - ((sliceid_to - sliceid_between) * 1 / gap)

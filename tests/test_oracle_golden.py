@@ -158,6 +158,30 @@ def test_host_logic(golden):
     assert np.any((np.float32(1) - hi) != lo)
 
 
+AUGMENT_CASES = (("acdc", dict(width=128, aug_patch=160, center=True, intensity_first=True)),
+                 ("acdc_small", dict(width=64, aug_patch=96, center=True, intensity_first=True)),
+                 ("oasis", dict(width=64, aug_patch=220, center=False, intensity_first=False)),
+                 ("dhcp_crop", dict(width=128, aug_patch=None, center=False, intensity_first=False)))
+
+
+def test_augment_chain_against_reference_golden(golden):
+    """The training transform chains (AdjustToPatchSize / CenterCrop / RandomCrop / RandomIntensity / RandomRotation,
+    datasets/shared_transforms.py) in the ACDC and the brain order: values and RandomState draw order pinned against
+    the reference's own classes (oracle/make_golden.py::gold_augment)."""
+    g = golden("augment_pins.npz")
+    rng = np.random.RandomState(int(g["input_seed"]))
+    for name, kw in AUGMENT_CASES:
+        rs = np.random.RandomState(int(g["rs_seed"]))
+        shape = tuple(int(v) for v in g["%s_shape" % name])
+        for i in range(4):
+            img = rng.rand(*shape).astype(np.float32)
+            got, d = O.augment_sample(img, rs, **kw)
+            assert got.shape == (shape[0], kw["width"], kw["width"]) and got.dtype == np.float32
+            np.testing.assert_array_equal(got[:, ::7, ::5], g["%s_out%d" % (name, i)])
+            np.testing.assert_array_equal(np.array([d["top"], d["left"], d["gain"], d["cutoff"], d["k"]], dtype=np.float64),
+                                          g["%s_draws" % name][i])
+
+
 def test_ssim_psnr_properties():
     """scikit-image is absent and unpinned (parity unpinned): check the restatement on analytic properties."""
     rng = np.random.RandomState(0)
