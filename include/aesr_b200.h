@@ -272,6 +272,12 @@ int aesr_pad_crop_gather(const float* in, float* out, const int* top, const int*
 int aesr_augment_gather(const float* in, float* out, const int* top, const int* left, const int* rot_k, const float* gain,
                         const float* cutoff, unsigned chan_mask, int B, int C, int Hin, int Win, int P, void* stream);
 
+/* LR-dataset synthesis, datasets/common_brains.py:37-44 (simulate_thick_slices): scipy.ndimage.gaussian_filter1d along
+ * axis 0 of a fp32 volume [Z,HW] ('reflect' borders, float64 accumulation in scipy's order, rounded once to fp32).
+ * taps = device float64 [2*lw+1], the normalised gaussian (sigma = slice_thickness / 2.355, lw = int(4*sigma + 0.5)).
+ * Out of place. */
+int aesr_gauss1d_axis0(const float* in, float* out, const double* taps, int lw, int Z, size_t HW, void* stream);
+
 /* DIAGNOSTIC (not on the product path): one 16x8 tile of a 64->64 bf16 conv computed from a single TMA halo load with
  * row-shifted UMMA descriptors; used by tools/gpu_diag.py to establish what the hardware's swizzle addressing does.
  * out fp32 [128][64] raw accumulators. */

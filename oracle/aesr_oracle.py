@@ -339,6 +339,48 @@ def augment_sample(img: np.ndarray, rs: np.random.RandomState, width: int, aug_p
     return x, {"top": top, "left": left, "gain": gain, "cutoff": cutoff, "k": k}
 
 
+def get_random_adjacent_slice(slice_id: int, num_slices: int, rs: np.random.RandomState, step: int = 1):
+    """datasets/common.py:34-43: the partner slice `step` away; a draw (rs.choice of two) only when both sides exist."""
+    last = num_slices - 1
+    if slice_id + step > last:
+        return slice_id - step
+    if slice_id == 0:
+        return step
+    if slice_id - step < 0:
+        return slice_id + step
+    return rs.choice([slice_id - step, slice_id + step])
+
+
+def sample_triplet(slice_id_1: int, num_slices: int, rs: np.random.RandomState, kind: str = "acdc",
+                   slice_selection: str = "adjacent_plus", downsample_steps: int = 2) -> dict:
+    """One training triplet (from, to, between) with the reference's RandomState draw order:
+    ACDC  datasets/ACDC/data4d_simple.py:191-205,245-263 (step 1 / 2 / choice([1,2]); midpoint or slice 1 itself, alphas 0.5)
+    brain datasets/common_brains.py:241-260,272-282 (step 1 / downsample_steps / choice; in-between drawn from the open
+    interval; alphas from determine_interpol_coefficients, cast to float32)."""
+    if slice_selection == "adjacent":
+        step = 1
+    elif slice_selection == "adjacent_plus":
+        step = 2 if kind == "acdc" else downsample_steps
+    else:
+        step = rs.choice([1, 2 if kind == "acdc" else downsample_steps])
+    s2 = get_random_adjacent_slice(slice_id_1, num_slices, rs, step)
+    if kind == "acdc":
+        if (slice_id_1 + s2) % 2 == 0:
+            between, is_between = (slice_id_1 + s2) // 2, 1
+        else:
+            between, is_between = slice_id_1, 0
+    else:
+        between, is_between = rs.choice(np.arange(min(slice_id_1, s2) + 1, max(slice_id_1, s2))), 1
+    s_from, s_to = (slice_id_1, s2) if rs.choice([0, 1]) == 0 else (s2, slice_id_1)
+    if kind == "acdc":
+        a_from = a_to = np.float32(0.5)
+    else:
+        af, at = determine_interpol_coefficients(s_from, s_to, between)
+        a_from, a_to = np.float32(af), np.float32(at)
+    return {"slice_idx_from": int(s_from), "slice_idx_to": int(s_to), "inbetween_slice_id": int(between),
+            "is_inbetween": is_between, "alpha_from": a_from, "alpha_to": a_to}
+
+
 def prepare_batch_pairs(batch_images: torch.Tensor) -> Dict[str, torch.Tensor]:
     """datasets/common_brains.py:285-321 / datasets/ACDC/data4d_simple.py:327-387 ('repeat'):
     [B,3,H,W] -> image [2B,1,H,W] (all 'from' then all 'to'), slice_between [B,1,H,W]."""
@@ -618,6 +660,21 @@ def gaussian_filter1d_u8(a: np.ndarray, sd: float, axis: int) -> np.ndarray:
         left, right = x[..., _reflect_index(idx + jj, n)], x[..., _reflect_index(idx - jj, n)]
         tmp = tmp + (left + right) * w[jj + lw]
     return np.moveaxis(tmp.astype(np.uint8), -1, axis)       # values are in [0, 255]: the cast truncates
+
+
+def simulate_thick_slices(img3d: np.ndarray, slice_thickness: float) -> np.ndarray:
+    """datasets/common_brains.py:37-44: per (y, x) column scipy.ndimage.gaussian_filter1d along z with
+    sigma = slice_thickness / 2.355 (FWHM of the slice profile), 'reflect' borders, truncate 4: float64 accumulation in
+    scipy's order (centre tap, then symmetric pairs from the farthest tap inwards), result cast to the input dtype."""
+    sd = slice_thickness / 2.355
+    w, lw = gaussian_kernel1d(sd)
+    n = img3d.shape[0]
+    idx = np.arange(n)
+    x = img3d.astype(np.float64)
+    tmp = x * w[lw]
+    for jj in range(-lw, 0):
+        tmp = tmp + (x[_reflect_index(idx + jj, n)] + x[_reflect_index(idx - jj, n)]) * w[jj + lw]
+    return tmp.astype(img3d.dtype)
 
 
 def gaussian_filter_u8(a: np.ndarray, sd: float) -> np.ndarray:

@@ -370,12 +370,84 @@ def gold_augment():
     _save("augment_pins.npz", **out)
 
 
+def gold_thick_slices():
+    """LR-dataset synthesis: datasets/common_brains.py::simulate_thick_slices (scipy gaussian_filter1d per column)."""
+    rb.bootstrap()
+    from datasets.common_brains import simulate_thick_slices
+    rs = np.random.RandomState(31)
+    out = {}
+    for k, (shape, thick) in enumerate((((24, 9, 11), 2.0), ((24, 9, 11), 3.0), ((7, 5, 6), 5.0), ((40, 6, 7), 6.0),
+                                        ((3, 4, 5), 4.0))):
+        vol = rs.rand(*shape).astype(np.float32)
+        want = simulate_thick_slices(vol, thick)
+        got = O.simulate_thick_slices(vol, thick)
+        assert want.dtype == got.dtype == np.float32 and np.array_equal(want, got), (shape, thick)
+        out["thick%d" % k] = want
+        out["cfg%d" % k] = np.array(list(shape) + [thick], dtype=np.float64)
+    out["seed"] = np.array(31)
+    _save("thick_slices_pins.npz", **out)
+
+
+def gold_sampling():
+    """Pair / triplet sampling of the datasets' __getitem__ (RandomState draw order), run through the reference classes'
+    own methods on a mock dataset object (no image files needed)."""
+    rb.bootstrap()
+    import types
+    from datasets.common_brains import BrainDataset
+    from datasets.ACDC.data4d_simple import ACDCDataset4DPairs
+    out = {}
+    for kind, sel, ds, Z in (("brain", "adjacent_plus", 4, 44), ("brain", "mix", 2, 30), ("brain", "adjacent_plus", 2, 9),
+                             ("acdc", "adjacent_plus", 2, 10), ("acdc", "mix", 2, 8), ("acdc", "adjacent", 2, 6)):
+        rs_ref, rs_mine = np.random.RandomState(2024), np.random.RandomState(2024)
+        rows = []
+        vol = np.broadcast_to(np.arange(Z, dtype=np.float32)[:, None, None], (Z, 2, 2)).copy()   # slice z holds the value z
+        if kind == "brain":
+            first = 1 if sel == "adjacent" else 0
+            mock = types.SimpleNamespace(rs=rs_ref, slice_selection=sel, downsample_steps=ds, transform=None,
+                                         images={0: {"image": vol}}, _idcs=[(0, z, Z) for z in range(Z)])
+            mock._get_slice_step = lambda m=mock: BrainDataset._get_slice_step(m)
+            mock._get_inbetween_sliceid = lambda a, b, m=mock: BrainDataset._get_inbetween_sliceid(m, a, b)
+            cls = BrainDataset
+        else:
+            mock = types.SimpleNamespace(rs=rs_ref, slice_selection=sel, transform=None, _get_masks=False,
+                                         images4d={0: {"image": vol[None], "orig_num_frames": 1, "num_slices": Z,
+                                                       "spacing": None, "original_spacing": None, "patient_id": 0}},
+                                         _idcs=np.array([(0, 0, z, Z) for z in range(Z)]))
+            mock._get_slice_step = lambda m=mock: ACDCDataset4DPairs._get_slice_step(m)
+            mock._get_inbetween_sliceid = ACDCDataset4DPairs._get_inbetween_sliceid
+            cls = ACDCDataset4DPairs
+        for rep in range(3):
+            for z in range(Z):
+                if kind == "brain" and (min(z + ds, Z - 1) - z < 2 and z - max(z - ds, 0) < 2) and sel != "mix":
+                    continue
+                try:
+                    smp = cls.__getitem__(mock, z)
+                except ValueError:                       # empty open interval (adjacent pair in a brain set): no triplet
+                    rs_mine.set_state(rs_ref.get_state())
+                    continue
+                mine = O.sample_triplet(z, Z, rs_mine, kind=kind, slice_selection=sel, downsample_steps=ds)
+                f = smp["slice_idx_from"] if kind == "brain" else int(smp["slice_id_from"][0])
+                t = smp["slice_idx_to"] if kind == "brain" else int(smp["slice_id_to"][0])
+                b = smp["inbetween_slice_id"] if kind == "brain" else None
+                if kind == "acdc":       # the ACDC sample does not carry the in-between id: read it off the stacked slices
+                    b = int(smp["image"][2, 0, 0])
+                assert [int(v) for v in smp["image"][:, 0, 0]] == [int(f), int(t), int(b)]
+                assert (int(f), int(t), int(b)) == (mine["slice_idx_from"], mine["slice_idx_to"], mine["inbetween_slice_id"]), (kind, sel, z)
+                assert float(smp["is_inbetween"]) == float(mine["is_inbetween"])
+                assert np.float32(smp["alpha_from"][0]) == mine["alpha_from"] and np.float32(smp["alpha_to"][0]) == mine["alpha_to"]
+                rows.append([z, int(f), int(t), int(b), float(mine["is_inbetween"]), float(mine["alpha_from"]), float(mine["alpha_to"])])
+        assert rs_ref.randint(0, 1 << 30) == rs_mine.randint(0, 1 << 30), (kind, sel)
+        out["%s_%s_%d_%d" % (kind, sel, ds, Z)] = np.array(rows, dtype=np.float64)
+    out["seed"] = np.array(2024)
+    _save("sampling_pins.npz", **out)
+
+
 def _sig(cls):
     return True
 
 
 ALL = {"init": gold_init, "lpips": gold_lpips_lin, "infer": gold_infer, "train_small": gold_train_small,
-       "transforms": gold_transforms, "augment": gold_augment, "vif": gold_vif, "train_acdc": gold_train_acdc}
+       "transforms": gold_transforms, "augment": gold_augment, "thick": gold_thick_slices, "sampling": gold_sampling, "vif": gold_vif, "train_acdc": gold_train_acdc}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

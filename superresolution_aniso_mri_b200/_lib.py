@@ -64,6 +64,7 @@ _SIGNATURES = {
     "aesr_percentile_normalize": (I, [P, P, c_size_t, ctypes.c_double, ctypes.c_double, P, c_size_t, P, P]),
     "aesr_pad_crop_gather": (I, [P, P, P, P, I, I, I, I, I, I, P]),
     "aesr_augment_gather": (I, [P, P, P, P, P, P, P, ctypes.c_uint, I, I, I, I, I, P]),
+    "aesr_gauss1d_axis0": (I, [P, P, P, I, I, c_size_t, P]),
 }
 
 

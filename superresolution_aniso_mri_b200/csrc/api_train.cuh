@@ -407,4 +407,15 @@ int aesr_augment_gather(const float* in, float* out, const int* top, const int* 
     return check_launch("augment_gather");
 }
 
+int aesr_gauss1d_axis0(const float* in, float* out, const double* taps, int lw, int Z, size_t HW, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!in || !out || !taps || lw < 0 || Z <= 0 || Z > 65535 || HW == 0 || in == out)
+        return fail(AESR_ERR_INVALID, "gauss1d_axis0: bad arguments (out of place, Z <= 65535)");
+    size_t gx = (HW + 255) / 256;
+    if (gx > 4096) gx = 4096;
+    gauss1d_axis0_kernel<<<dim3(static_cast<unsigned>(gx), Z), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, out, taps, lw, Z, HW);
+    return check_launch("gauss1d_axis0");
+}
+
 }  // extern "C"

@@ -218,4 +218,32 @@ __global__ void augment_gather_kernel(const float* __restrict__ in, float* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// LR-dataset synthesis (datasets/common_brains.py:37-44, simulate_thick_slices): scipy.ndimage.gaussian_filter1d along z
+// for every (y, x) column -- 'reflect' borders (half-sample symmetric, any overhang), float64 accumulation in scipy's
+// order (centre tap, then symmetric pairs from the farthest tap inwards, separately rounded multiply and add), result
+// rounded once to fp32.  w = the 2*lw+1 normalised taps formed on the host with scipy's formula.  One thread per output
+// voxel, coalesced along the in-plane index; the 2*lw+1 planes a block reads stay in L1/L2.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    const int m = 2 * n;
+    i %= m;
+    if (i < 0) i += m;
+    return i < n ? i : m - 1 - i;
+}
+__global__ void gauss1d_axis0_kernel(const float* __restrict__ in, float* __restrict__ out, const double* __restrict__ w,
+                                     int lw, int Z, size_t HW) {
+    const int z = blockIdx.y;
+    for (size_t p = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; p < HW;
+         p += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        double acc = __dmul_rn(static_cast<double>(__ldg(in + static_cast<size_t>(z) * HW + p)), w[lw]);
+        for (int jj = -lw; jj < 0; ++jj) {
+            const double a = static_cast<double>(__ldg(in + static_cast<size_t>(reflect_index(z + jj, Z)) * HW + p));
+            const double b = static_cast<double>(__ldg(in + static_cast<size_t>(reflect_index(z - jj, Z)) * HW + p));
+            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(a, b), w[jj + lw]));
+        }
+        out[static_cast<size_t>(z) * HW + p] = static_cast<float>(acc);
+    }
+}
+
 }  // namespace aesr

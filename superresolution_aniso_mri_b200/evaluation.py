@@ -372,3 +372,22 @@ def determine_interpol_coefficients(sliceid_from, sliceid_to, sliceid_between):
     """datasets/common_brains.py:117-119 (float64; the brain trainers cast to float32, :259-260)."""
     gap = sliceid_to - sliceid_from
     return 1 - ((sliceid_between - sliceid_from) * 1 / gap), 1 - ((sliceid_to - sliceid_between) * 1 / gap)
+
+
+def simulate_thick_slices(img3d, slice_thickness: float, device="cuda:0") -> torch.Tensor:
+    """datasets/common_brains.py:37-44: thick-slice simulation of a volume [Z,H,W] -- a gaussian slice profile of
+    FWHM = ``slice_thickness`` along z for every (y, x) column (scipy.ndimage.gaussian_filter1d semantics, bit-exact:
+    'reflect' borders, float64 accumulation in scipy's order).  Returns fp32 [Z,H,W] on ``device``."""
+    x = _as_dev_f32(img3d, device)
+    lib = _dev(x)
+    assert x.dim() == 3
+    sd = slice_thickness / 2.355
+    lw = int(4.0 * float(sd) + 0.5)
+    k = np.arange(-lw, lw + 1)
+    phi = np.exp(-0.5 / (sd * sd) * k ** 2)             # scipy.ndimage._filters._gaussian_kernel1d(sigma, 0, radius)
+    taps = torch.as_tensor(phi / phi.sum(), dtype=torch.float64, device=x.device)
+    out = torch.empty_like(x)
+    z, h, w = x.shape
+    _lib.check(lib.aesr_gauss1d_axis0(x.data_ptr(), out.data_ptr(), taps.data_ptr(), lw, z, h * w, _stream(x)),
+               "gauss1d_axis0")
+    return out

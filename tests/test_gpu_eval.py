@@ -135,6 +135,43 @@ def test_prepare_batch_pairs_and_alphas_on_device(cuda_lib):
     np.testing.assert_array_equal(a2, o2)
 
 
+@pytest.mark.parametrize("shape,thick", [((24, 9, 11), 2.0), ((44, 220, 220), 4.0), ((3, 4, 5), 4.0), ((34, 64, 80), 6.0),
+                                         ((1, 7, 3), 3.0)])
+def test_simulate_thick_slices_bit_exact(cuda_lib, shape, thick):
+    """Device thick-slice simulation against the oracle (itself pinned bit-exact against the reference function and
+    scipy): bit-exact, incl. radius > Z and a single slice."""
+    from superresolution_aniso_mri_b200 import evaluation as E
+    vol = np.random.RandomState(int(thick * 10) + shape[0]).rand(*shape).astype(np.float32)
+    got = E.simulate_thick_slices(vol, thick).cpu().numpy()
+    np.testing.assert_array_equal(got, O.simulate_thick_slices(vol, thick))
+
+
+def test_triplet_gather_feeds_augmentation_and_pairs(cuda_lib):
+    """sampling.sample_triplet (host draws) -> gather_triplets (device index_select) -> augment_batch -> prepare_batch_pairs:
+    the dataset / transform / collate chain of the reference without a host copy of image data, against the oracle."""
+    from superresolution_aniso_mri_b200 import evaluation as E, sampling
+    vol = np.random.RandomState(8).rand(12, 150, 141).astype(np.float32)
+    rs1, rs2 = np.random.RandomState(17), np.random.RandomState(17)
+    trip = [sampling.sample_triplet(z, 12, rs1, kind="acdc") for z in (0, 3, 5, 11)]
+    want_t = [O.sample_triplet(z, 12, rs2, kind="acdc") for z in (0, 3, 5, 11)]
+    assert [(t["slice_idx_from"], t["slice_idx_to"], t["inbetween_slice_id"]) for t in trip] == \
+           [(t["slice_idx_from"], t["slice_idx_to"], t["inbetween_slice_id"]) for t in want_t]
+    batch = sampling.gather_triplets(torch.from_numpy(vol).to("cuda:0"), trip)
+    assert batch["image"].shape == (4, 3, 150, 141) and batch["alpha_from"].shape == (4, 1)
+    for b, t in enumerate(want_t):
+        want = vol[[t["slice_idx_from"], t["slice_idx_to"], t["inbetween_slice_id"]]]
+        np.testing.assert_array_equal(batch["image"][b].cpu().numpy(), want)
+    aug = E.augment_batch(batch["image"], rs1, width=128, aug_patch=160, center=True)
+    pairs = E.prepare_batch_pairs({"image": aug})
+    assert pairs["image"].shape == (8, 1, 128, 128) and pairs["slice_between"].shape == (4, 1, 128, 128)
+    for b in range(4):
+        want, _ = O.augment_sample(batch["image"][b].cpu().numpy(), rs2, width=128, aug_patch=160, center=True)
+        ulp = np.spacing(np.abs(want))
+        assert np.all(np.abs(pairs["image"][b, 0].cpu().numpy() - want[0]) <= 4 * ulp[0])
+        assert np.all(np.abs(pairs["image"][4 + b, 0].cpu().numpy() - want[1]) <= 4 * ulp[1])
+        assert np.all(np.abs(pairs["slice_between"][b, 0].cpu().numpy() - want[2]) <= 4 * ulp[2])
+
+
 # ------------------------------------------------------------------------------------------------ VIF / metric sets
 def _vif_cases():
     import scipy.ndimage                                               # inputs only (same construction as gold_vif)

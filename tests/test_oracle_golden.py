@@ -182,6 +182,49 @@ def test_augment_chain_against_reference_golden(golden):
                                           g["%s_draws" % name][i])
 
 
+def test_thick_slices_against_reference_golden(golden):
+    """datasets/common_brains.py::simulate_thick_slices (scipy gaussian_filter1d per column), incl. a filter radius
+    larger than the volume."""
+    g = golden("thick_slices_pins.npz")
+    rs = np.random.RandomState(int(g["seed"]))
+    for k in range(5):
+        cfg = g["cfg%d" % k]
+        vol = rs.rand(*[int(v) for v in cfg[:3]]).astype(np.float32)
+        np.testing.assert_array_equal(O.simulate_thick_slices(vol, float(cfg[3])), g["thick%d" % k])
+
+
+def test_triplet_sampling_against_reference_golden(golden):
+    """Dataset __getitem__ index sampling (datasets/common.py:34-43, data4d_simple.py:191-205, common_brains.py:241-260):
+    oracle and the product's host function against the sequences the reference's own methods produced."""
+    from superresolution_aniso_mri_b200 import sampling
+    g = golden("sampling_pins.npz")
+    for key in g.files:
+        if key == "seed":
+            continue
+        kind, sel = key.split("_")[0], "_".join(key.split("_")[1:-2])
+        ds, Z = int(key.split("_")[-2]), int(key.split("_")[-1])
+        for fn in (O.sample_triplet, sampling.sample_triplet):
+            rs = np.random.RandomState(int(g["seed"]))
+            rows = g[key]
+            r = 0
+            for rep in range(3):
+                for z in range(Z):
+                    if r >= len(rows) or int(rows[r][0]) != z:
+                        # the reference raised (empty open interval) or the generator skipped this slice: replay the draws
+                        if kind == "brain" and sel == "mix":
+                            try:
+                                fn(z, Z, rs, kind=kind, slice_selection=sel, downsample_steps=ds)
+                            except ValueError:
+                                pass
+                        continue
+                    t = fn(z, Z, rs, kind=kind, slice_selection=sel, downsample_steps=ds)
+                    got = [z, t["slice_idx_from"], t["slice_idx_to"], t["inbetween_slice_id"], float(t["is_inbetween"]),
+                           float(t["alpha_from"]), float(t["alpha_to"])]
+                    assert got == list(rows[r]), (key, fn.__module__, rep, z)
+                    r += 1
+            assert r == len(rows)
+
+
 def test_ssim_psnr_properties():
     """scikit-image is absent and unpinned (parity unpinned): check the restatement on analytic properties."""
     rng = np.random.RandomState(0)
