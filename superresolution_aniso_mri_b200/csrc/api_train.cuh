@@ -52,22 +52,25 @@ int aesr_bn_bwd(const void* dnext, const void* a, const float* mean, const float
     const size_t npix = static_cast<size_t>(N) * H * W;
     const bool do_reduce = phase != 2, do_apply = phase != 1;
     if (do_reduce) CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), s));
-    int gx = static_cast<int>((npix + 63) / 64);
-    const int capx = g_sm_count * 8 / (C / 32);
-    if (gx > capx) gx = capx;
+    if (C > 512) return fail(AESR_ERR_INVALID, "bn_bwd: C=%d > 512", C);
+    const int groups = C / 8;
+    const int rows = 256 / groups;                                   // pixel rows per block (C = 32: 64 ... C = 512: 4)
+    int gx = static_cast<int>((npix + static_cast<size_t>(rows) * 4 - 1) / (static_cast<size_t>(rows) * 4));
+    if (gx > g_sm_count * 8) gx = g_sm_count * 8;
     if (gx < 1) gx = 1;
-    dim3 grid(gx, C / 32), block(32, 8);
-    const size_t total = npix * C;
+    const int block = rows * groups;
+    const size_t red_smem = static_cast<size_t>(rows) * 2 * C * sizeof(float);      // <= 32 KB
+    const size_t total = npix * groups;
     if (count <= 0.f) count = static_cast<float>(npix);       // global-batch count in SyncBN mode
     // phase 0: the apply kernel banks dgamma / dbeta from the (local) sums; phase 1 banks them right after the local
     // reduce; phase 2 (sums all-reduced by the caller) must not bank them again.
     float* dg_apply = phase == 0 ? dgamma : nullptr;
     float* db_apply = phase == 0 ? dbeta : nullptr;
     if (dtype == AESR_DT_FP16) {
-        if (do_reduce) bn_bwd_reduce_kernel<true><<<grid, block, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode);
+        if (do_reduce) bn_bwd_reduce_kernel<true><<<gx, block, red_smem, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode);
         if (do_apply) bn_bwd_apply_kernel<true><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, slope, static_cast<uint16_t*>(g_out), dg_apply, db_apply, N, H, W, C, mode);
     } else {
-        if (do_reduce) bn_bwd_reduce_kernel<false><<<grid, block, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode);
+        if (do_reduce) bn_bwd_reduce_kernel<false><<<gx, block, red_smem, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode);
         if (do_apply) bn_bwd_apply_kernel<false><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, slope, static_cast<uint16_t*>(g_out), dg_apply, db_apply, N, H, W, C, mode);
     }
     if (phase == 1) bn_bwd_accum_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, dgamma, dbeta, C);
@@ -215,8 +218,8 @@ int aesr_maxpool_bwd(const void* a, const void* d_pooled, const void* g_tap, voi
                      int dtype, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
-    if (!a || !g_out || (!d_pooled && !g_tap)) return fail(AESR_ERR_INVALID, "maxpool_bwd: bad arguments");
-    const size_t total = static_cast<size_t>(N) * H * W * C;
+    if (!a || !g_out || (!d_pooled && !g_tap) || C % 8 != 0) return fail(AESR_ERR_INVALID, "maxpool_bwd: bad arguments (C % 8 == 0)");
+    const size_t total = static_cast<size_t>(N) * H * W * (C / 8);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == AESR_DT_FP16)
         maxpool_bwd_kernel<true><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(a), static_cast<const uint16_t*>(d_pooled), static_cast<const uint16_t*>(g_tap), static_cast<uint16_t*>(g_out), N, H, W, C);
@@ -230,11 +233,14 @@ int aesr_lpips_head(const void* o0, const void* o1, const float* lin, float* val
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!o0 || !o1 || !lin || (!val && !g1) || (g1 && !upstream)) return fail(AESR_ERR_INVALID, "lpips_head: bad arguments");
+    if (C % 8 != 0 || C > 512 || ((C / 8) & (C / 8 - 1)) != 0)
+        return fail(AESR_ERR_INVALID, "lpips_head: C=%d must be 8 * 2^k <= 512 (the VGG16 taps: 64, 128, 256, 512)", C);
     const size_t total = static_cast<size_t>(N) * HW;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const uint16_t* a = static_cast<const uint16_t*>(o0);
     const uint16_t* b = static_cast<const uint16_t*>(o1);
-    const int grid = grid_for(total * 32, 256, 8);
+    const int lanes_per_px = (C / 8) < 32 ? (C / 8) : 32;
+    const int grid = grid_for(total * lanes_per_px, 256, 8);
     if (val) {
         if (dtype == AESR_DT_FP16) lpips_head_fwd_kernel<true><<<grid, 256, 0, s>>>(a, b, lin, val, N, HW, C);
         else lpips_head_fwd_kernel<false><<<grid, 256, 0, s>>>(a, b, lin, val, N, HW, C);

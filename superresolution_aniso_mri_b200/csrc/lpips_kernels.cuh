@@ -98,108 +98,210 @@ __global__ void vgg_conv1_bwd_kernel(const uint16_t* __restrict__ g, const float
 //   g_out[y,x,c] = relu'(a) * ( first_argmax(a over its 2x2 window) ? d_pooled[y/2,x/2,c] : 0  +  g_tap[y,x,c] )
 // a: post-ReLU activation 16-bit [N,H,W,C]; d_pooled bf16 [N,H/2,W/2,C]; g_tap bf16 [N,H,W,C] or null.
 // ---------------------------------------------------------------------------------------------------------------
+// One thread = 8 channels (16 bytes) of one pixel: the element-per-thread version spent its time on 2-byte accesses and
+// three integer divisions per element (0.23 ms of a 5 ms training step, bench.py kernel_ms).
+template <bool AF>
+__device__ __forceinline__ void load8(const uint16_t* p, float (&v)[8]) {
+    const uint4 m = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t u[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack2_t<AF>(u[k]);
+        v[2 * k] = f.x;
+        v[2 * k + 1] = f.y;
+    }
+}
 template <bool AF>
 __global__ void maxpool_bwd_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ d_pooled,
                                    const uint16_t* __restrict__ g_tap, uint16_t* __restrict__ g_out, int N, int H,
                                    int W, int C) {
-    const int Ho = H / 2, Wo = W / 2;
-    const size_t total = static_cast<size_t>(N) * H * W * C;
+    const int Ho = H / 2, Wo = W / 2, groups = C >> 3;
+    const size_t total = static_cast<size_t>(N) * H * W * groups;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(i % C);
-        const size_t p = i / C;
+        const int g = static_cast<int>(i % groups);
+        const size_t p = i / groups;
         const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
         const int n = static_cast<int>(p / (static_cast<size_t>(W) * H));
-        const float av = a16_to_f<AF>(a[i]);
-        float gsum = g_tap ? bf16_to_f(g_tap[i]) : 0.f;
+        float av[8], gs[8];
+        load8<AF>(a + i * 8, av);
+        if (g_tap) load8<false>(g_tap + i * 8, gs);
+        else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gs[k] = 0.f;
+        }
         const int yo = y >> 1, xo = x >> 1;
         if (d_pooled != nullptr && yo < Ho && xo < Wo) {
             // torch picks the first maximum in window scan order (0,0),(0,1),(1,0),(1,1)
-            const uint16_t* base = a + ((static_cast<size_t>(n) * H + 2 * yo) * W + 2 * xo) * C + c;
-            const float w0 = a16_to_f<AF>(base[0]), w1 = a16_to_f<AF>(base[C]);
-            const float w2 = a16_to_f<AF>(base[static_cast<size_t>(W) * C]), w3 = a16_to_f<AF>(base[static_cast<size_t>(W) * C + C]);
-            int arg = 0;
-            float best = w0;
-            if (w1 > best) { best = w1; arg = 1; }
-            if (w2 > best) { best = w2; arg = 2; }
-            if (w3 > best) { best = w3; arg = 3; }
-            if (arg == ((y & 1) * 2 + (x & 1)))
-                gsum += bf16_to_f(d_pooled[((static_cast<size_t>(n) * Ho + yo) * Wo + xo) * C + c]);
+            const uint16_t* base = a + ((static_cast<size_t>(n) * H + 2 * yo) * W + 2 * xo) * C + g * 8;
+            float w0[8], w1[8], w2[8], w3[8], dp[8];
+            load8<AF>(base, w0);
+            load8<AF>(base + C, w1);
+            load8<AF>(base + static_cast<size_t>(W) * C, w2);
+            load8<AF>(base + static_cast<size_t>(W) * C + C, w3);
+            load8<false>(d_pooled + ((static_cast<size_t>(n) * Ho + yo) * Wo + xo) * C + g * 8, dp);
+            const int me = (y & 1) * 2 + (x & 1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int arg = 0;
+                float best = w0[k];
+                if (w1[k] > best) { best = w1[k]; arg = 1; }
+                if (w2[k] > best) { best = w2[k]; arg = 2; }
+                if (w3[k] > best) { best = w3[k]; arg = 3; }
+                if (arg == me) gs[k] += dp[k];
+            }
         }
-        g_out[i] = __bfloat16_as_ushort(__float2bfloat16_rn(av > 0.f ? gsum : 0.f));
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            o[k] = pack_bf16x2(av[2 * k] > 0.f ? gs[2 * k] : 0.f, av[2 * k + 1] > 0.f ? gs[2 * k + 1] : 0.f);
+        reinterpret_cast<uint4*>(g_out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // LPIPS distance head of one tap (networks_basic.py:70-77 + lpips/common.py:12-14):
 //   f = o / (||o||_2 + 1e-10) over channels ; val[n] += (1/HW) * sum_px sum_c lin_c (f0_c - f1_c)^2
-// f0 = features of image set 0 (reference), f1 = set 1 (synthesized); both 16-bit NHWC [N,HW,C].  One warp per pixel.
+// f0 = features of image set 0 (reference), f1 = set 1 (synthesized); both 16-bit NHWC [N,HW,C], C % 8 == 0, C <= 512.
 // ---------------------------------------------------------------------------------------------------------------
+// G = min(C/8, 32) lanes share a pixel, each lane owns 16-byte chunks of 8 channels (chunk index lane, lane+G, ...: at most
+// two for C <= 512, kept in registers for both passes); 32/G pixels per warp.  The per-image sums are collected in shared
+// memory and leave the block as one atomic per image (the one-warp-per-pixel version issued 2-byte loads and one global
+// atomic per PIXEL onto N addresses: 0.53 ms of a 5 ms training step for ten launches, bench.py kernel_ms).
+constexpr int LPIPS_MAX_IMG_SMEM = 256;
+__device__ __forceinline__ float group_sum(float v, int G) {
+    for (int off = G >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
 template <bool AF>
 __global__ void lpips_head_fwd_kernel(const uint16_t* __restrict__ o0, const uint16_t* __restrict__ o1,
                                       const float* __restrict__ lin, float* __restrict__ val, int N, int HW, int C) {
-    const int lane = threadIdx.x & 31;
+    __shared__ float s_val[LPIPS_MAX_IMG_SMEM];
+    const bool use_smem = N <= LPIPS_MAX_IMG_SMEM;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < N; i += blockDim.x) s_val[i] = 0.f;
+        __syncthreads();
+    }
+    const int chunks = C >> 3;
+    const int G = chunks < 32 ? chunks : 32;
+    const int lane = threadIdx.x & 31, sub = lane % G, ppw = 32 / G;
     const size_t warp_id = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
     const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
     const size_t total = static_cast<size_t>(N) * HW;
-    for (size_t p = warp_id; p < total; p += nwarps) {
-        const uint16_t* a = o0 + p * C;
-        const uint16_t* b = o1 + p * C;
+    const float inv_hw = 1.f / static_cast<float>(HW);
+    for (size_t base = warp_id * ppw; base < total; base += nwarps * ppw) {          // warp-uniform trip count
+        const size_t p = base + lane / G;
+        const bool live = p < total;
+        float x0[2][8], x1[2][8];
         float n0 = 0.f, n1 = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float x0 = a16_to_f<AF>(a[c]), x1 = a16_to_f<AF>(b[c]);
-            n0 = fmaf(x0, x0, n0);
-            n1 = fmaf(x1, x1, n1);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int ch = sub + r * G;
+            if (live && ch < chunks) {
+                load8<AF>(o0 + p * C + ch * 8, x0[r]);
+                load8<AF>(o1 + p * C + ch * 8, x1[r]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x0[r][k] = x1[r][k] = 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                n0 = fmaf(x0[r][k], x0[r][k], n0);
+                n1 = fmaf(x1[r][k], x1[r][k], n1);
+            }
         }
-        n0 = warp_sum(n0);
-        n1 = warp_sum(n1);
+        n0 = group_sum(n0, G);
+        n1 = group_sum(n1, G);
         const float i0 = 1.f / (sqrtf(n0) + 1e-10f), i1 = 1.f / (sqrtf(n1) + 1e-10f);
         float acc = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float d = a16_to_f<AF>(a[c]) * i0 - a16_to_f<AF>(b[c]) * i1;
-            acc = fmaf(lin[c] * d, d, acc);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int ch = sub + r * G;
+            if (ch < chunks) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float d = x0[r][k] * i0 - x1[r][k] * i1;
+                    acc = fmaf(__ldg(lin + ch * 8 + k) * d, d, acc);
+                }
+            }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) atomicAdd(val + p / HW, acc / HW);
+        acc = group_sum(acc, G);
+        if (live && sub == 0) {
+            const int n = static_cast<int>(p / HW);
+            if (use_smem) atomicAdd(&s_val[n], acc * inv_hw);
+            else atomicAdd(val + n, acc * inv_hw);
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += blockDim.x)
+            if (s_val[i] != 0.f) atomicAdd(val + i, s_val[i]);
     }
 }
-
 // backward w.r.t. o1:  with e_c = 2 lin_c (f1_c - f0_c), s = sum_c e_c o1_c, r = ||o1||, q = r + eps
 //   d val / d o1_j = e_j / q - o1_j * s / (r q^2)       ; times upstream[n] / HW.   Output bf16 NHWC.
 template <bool AF>
 __global__ void lpips_head_bwd_kernel(const uint16_t* __restrict__ o0, const uint16_t* __restrict__ o1,
                                       const float* __restrict__ lin, const float* __restrict__ upstream /*[N]*/,
                                       uint16_t* __restrict__ g1, int N, int HW, int C) {
-    const int lane = threadIdx.x & 31;
+    const int chunks = C >> 3;
+    const int G = chunks < 32 ? chunks : 32;
+    const int lane = threadIdx.x & 31, sub = lane % G, ppw = 32 / G;
     const size_t warp_id = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
     const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
     const size_t total = static_cast<size_t>(N) * HW;
-    for (size_t p = warp_id; p < total; p += nwarps) {
-        const uint16_t* a = o0 + p * C;
-        const uint16_t* b = o1 + p * C;
+    for (size_t base = warp_id * ppw; base < total; base += nwarps * ppw) {
+        const size_t p = base + lane / G;
+        const bool live = p < total;
+        float x0[2][8], x1[2][8];
         float n0 = 0.f, n1 = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float x0 = a16_to_f<AF>(a[c]), x1 = a16_to_f<AF>(b[c]);
-            n0 = fmaf(x0, x0, n0);
-            n1 = fmaf(x1, x1, n1);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int ch = sub + r * G;
+            if (live && ch < chunks) {
+                load8<AF>(o0 + p * C + ch * 8, x0[r]);
+                load8<AF>(o1 + p * C + ch * 8, x1[r]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x0[r][k] = x1[r][k] = 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                n0 = fmaf(x0[r][k], x0[r][k], n0);
+                n1 = fmaf(x1[r][k], x1[r][k], n1);
+            }
         }
-        n0 = warp_sum(n0);
-        n1 = warp_sum(n1);
-        const float r = sqrtf(n1);
-        const float i0 = 1.f / (sqrtf(n0) + 1e-10f), q = r + 1e-10f, i1 = 1.f / q;
-        float s = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float x1 = a16_to_f<AF>(b[c]);
-            const float e = 2.f * lin[c] * (x1 * i1 - a16_to_f<AF>(a[c]) * i0);
-            s = fmaf(e, x1, s);
+        n0 = group_sum(n0, G);
+        n1 = group_sum(n1, G);
+        const float r_ = sqrtf(n1);
+        const float i0 = 1.f / (sqrtf(n0) + 1e-10f), q = r_ + 1e-10f, i1 = 1.f / q;
+        float e[2][8];
+        float sdot = 0.f;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int ch = sub + r * G;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float l = ch < chunks ? __ldg(lin + ch * 8 + k) : 0.f;
+                e[r][k] = 2.f * l * (x1[r][k] * i1 - x0[r][k] * i0);
+                sdot = fmaf(e[r][k], x1[r][k], sdot);
+            }
         }
-        s = warp_sum(s);
+        sdot = group_sum(sdot, G);
+        if (!live) continue;                       // no shuffles below this point
         const float up = upstream[p / HW] / HW;
-        const float k = (r > 0.f) ? s / (r * q * q) : 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const float x1 = a16_to_f<AF>(b[c]);
-            const float e = 2.f * lin[c] * (x1 * i1 - a16_to_f<AF>(a[c]) * i0);
-            g1[p * C + c] = __bfloat16_as_ushort(__float2bfloat16_rn(up * (e * i1 - x1 * k)));
+        const float kq = (r_ > 0.f) ? sdot / (r_ * q * q) : 0.f;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int ch = sub + r * G;
+            if (ch < chunks) {
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    o[k] = pack_bf16x2(up * (e[r][2 * k] * i1 - x1[r][2 * k] * kq),
+                                       up * (e[r][2 * k + 1] * i1 - x1[r][2 * k + 1] * kq));
+                *reinterpret_cast<uint4*>(g1 + p * C + ch * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
         }
     }
 }
