@@ -146,11 +146,12 @@ int aesr_wgrad3x3(const void* g, const void* x, float* dW, float* dbias, int N, 
         rc = check_launch("wgrad3x3_tc");
         if (rc != AESR_OK) return rc;
         if (dbias) {
-            int gx = static_cast<int>((npix + 255) / 256);
-            const int cap = g_sm_count * 8 / (Cout / 32);
-            if (gx > cap) gx = cap;
+            const int groups = Cout / 8, rows = 256 / groups;
+            int gx = static_cast<int>((npix + static_cast<size_t>(rows) * 4 - 1) / (static_cast<size_t>(rows) * 4));
+            if (gx > g_sm_count * 8) gx = g_sm_count * 8;
             if (gx < 1) gx = 1;
-            colsum_bf16_kernel<<<dim3(gx, Cout / 32), dim3(32, 8), 0, s>>>(static_cast<const uint16_t*>(g), dbias, npix, Cout);
+            colsum_bf16_kernel<<<gx, rows * groups, static_cast<size_t>(rows) * Cout * sizeof(float), s>>>(
+                static_cast<const uint16_t*>(g), dbias, npix, Cout);
             return check_launch("colsum_bf16");
         }
         return AESR_OK;
@@ -241,18 +242,14 @@ int aesr_lpips_head(const void* o0, const void* o1, const float* lin, float* val
     const uint16_t* b = static_cast<const uint16_t*>(o1);
     const int lanes_per_px = (C / 8) < 32 ? (C / 8) : 32;
     const int grid = grid_for(total * lanes_per_px, 256, 8);
-    if (val) {
-        if (dtype == AESR_DT_FP16) lpips_head_fwd_kernel<true><<<grid, 256, 0, s>>>(a, b, lin, val, N, HW, C);
-        else lpips_head_fwd_kernel<false><<<grid, 256, 0, s>>>(a, b, lin, val, N, HW, C);
-        int r2 = check_launch("lpips_head_fwd");
-        if (r2 != AESR_OK) return r2;
-    }
-    if (g1) {
-        if (dtype == AESR_DT_FP16) lpips_head_bwd_kernel<true><<<grid, 256, 0, s>>>(a, b, lin, upstream, static_cast<uint16_t*>(g1), N, HW, C);
-        else lpips_head_bwd_kernel<false><<<grid, 256, 0, s>>>(a, b, lin, upstream, static_cast<uint16_t*>(g1), N, HW, C);
+    if (g1) {       // backward (+ the forward value in the same pass when asked for)
+        if (dtype == AESR_DT_FP16) lpips_head_bwd_kernel<true><<<grid, 256, 0, s>>>(a, b, lin, upstream, static_cast<uint16_t*>(g1), val, N, HW, C);
+        else lpips_head_bwd_kernel<false><<<grid, 256, 0, s>>>(a, b, lin, upstream, static_cast<uint16_t*>(g1), val, N, HW, C);
         return check_launch("lpips_head_bwd");
     }
-    return AESR_OK;
+    if (dtype == AESR_DT_FP16) lpips_head_fwd_kernel<true><<<grid, 256, 0, s>>>(a, b, lin, val, N, HW, C);
+    else lpips_head_fwd_kernel<false><<<grid, 256, 0, s>>>(a, b, lin, val, N, HW, C);
+    return check_launch("lpips_head_fwd");
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -240,10 +240,19 @@ __global__ void lpips_head_fwd_kernel(const uint16_t* __restrict__ o0, const uin
 }
 // backward w.r.t. o1:  with e_c = 2 lin_c (f1_c - f0_c), s = sum_c e_c o1_c, r = ||o1||, q = r + eps
 //   d val / d o1_j = e_j / q - o1_j * s / (r q^2)       ; times upstream[n] / HW.   Output bf16 NHWC.
+// val != NULL: the forward value is accumulated in the same pass (lin_c d_c^2 = e_c^2 / (4 lin_c) needs nothing new:
+// d_c = x0_c i0 - x1_c i1 is formed anyway) -- training calls forward and backward together, one read of the features.
 template <bool AF>
 __global__ void lpips_head_bwd_kernel(const uint16_t* __restrict__ o0, const uint16_t* __restrict__ o1,
                                       const float* __restrict__ lin, const float* __restrict__ upstream /*[N]*/,
-                                      uint16_t* __restrict__ g1, int N, int HW, int C) {
+                                      uint16_t* __restrict__ g1, float* __restrict__ val, int N, int HW, int C) {
+    __shared__ float s_val[LPIPS_MAX_IMG_SMEM];
+    const bool use_smem = val != nullptr && N <= LPIPS_MAX_IMG_SMEM;
+    if (use_smem) {
+        for (int i = threadIdx.x; i < N; i += blockDim.x) s_val[i] = 0.f;
+        __syncthreads();
+    }
+    const float inv_hw = 1.f / static_cast<float>(HW);
     const int chunks = C >> 3;
     const int G = chunks < 32 ? chunks : 32;
     const int lane = threadIdx.x & 31, sub = lane % G, ppw = 32 / G;
@@ -276,18 +285,28 @@ __global__ void lpips_head_bwd_kernel(const uint16_t* __restrict__ o0, const uin
         const float r_ = sqrtf(n1);
         const float i0 = 1.f / (sqrtf(n0) + 1e-10f), q = r_ + 1e-10f, i1 = 1.f / q;
         float e[2][8];
-        float sdot = 0.f;
+        float sdot = 0.f, acc = 0.f;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const int ch = sub + r * G;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const float l = ch < chunks ? __ldg(lin + ch * 8 + k) : 0.f;
+                const float d = x0[r][k] * i0 - x1[r][k] * i1;                 // same expression as the forward kernel
+                acc = fmaf(l * d, d, acc);
                 e[r][k] = 2.f * l * (x1[r][k] * i1 - x0[r][k] * i0);
                 sdot = fmaf(e[r][k], x1[r][k], sdot);
             }
         }
         sdot = group_sum(sdot, G);
+        if (val != nullptr) {
+            acc = group_sum(acc, G);
+            if (live && sub == 0) {
+                const int n = static_cast<int>(p / HW);
+                if (use_smem) atomicAdd(&s_val[n], acc * inv_hw);
+                else atomicAdd(val + n, acc * inv_hw);
+            }
+        }
         if (!live) continue;                       // no shuffles below this point
         const float up = upstream[p / HW] / HW;
         const float kq = (r_ > 0.f) ? sdot / (r_ * q * q) : 0.f;
@@ -303,6 +322,11 @@ __global__ void lpips_head_bwd_kernel(const uint16_t* __restrict__ o0, const uin
                 *reinterpret_cast<uint4*>(g1 + p * C + ch * 8) = make_uint4(o[0], o[1], o[2], o[3]);
             }
         }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += blockDim.x)
+            if (s_val[i] != 0.f) atomicAdd(val + i, s_val[i]);
     }
 }
 
