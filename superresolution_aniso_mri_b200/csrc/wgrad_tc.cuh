@@ -91,57 +91,69 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_cons
     const int ntaps = (9 - tap0) < p.taps_per_group ? (9 - tap0) : p.taps_per_group;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
 
+    // Producer and issuer run WARP-UNIFORM loops and issue under elect.sync (see elect_one_sync in common.cuh): issued
+    // from `if (lane == 0)` code every TMA / tcgen05 instruction is wrapped in an ELECT + broadcast + branch loop, and with
+    // the 64-bit descriptors rebuilt per MMA the single issuing thread needed ~150 cycles per MMA -- 10.6 k cycles per
+    // 128-pixel tile against 72 MMAs x 40-48 tensor-pipe cycles (tools/train_layer_times.py: 138 us for 32->32 @130^2).
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = first; t < p.num_tiles; t += p.ctas_per_group) {
-                const int n = t / tiles_per_img, r = t - n * tiles_per_img;
-                const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = first; t < p.num_tiles; t += p.ctas_per_group) {
+            const int n = t / tiles_per_img, r = t - n * tiles_per_img;
+            const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one_sync()) {
                 uint8_t* base = smem + stage * stage_bytes;
                 mbar_arrive_expect_tx(&full_bar[stage], 128 * p.Cg * 2 + 180 * p.Cx * 2);
                 for (int c = 0; c < g_chunks; ++c)
                     tma_load_4d(base + c * g_chunk_bytes, &tmap_g, &full_bar[stage], c * 64, x0, y0, n);
                 for (int c = 0; c < x_chunks; ++c)
                     tma_load_4d(base + g_bytes + c * x_chunk_bytes, &tmap_x, &full_bar[stage], c * 64, x0 - 1, y0 - 1, n);
-                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
+            if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // idesc: D f32, A = bf16 (g), B = x format, both MN-major, M = 128, N = Cx
-            const uint32_t bfmt = p.x_fp16 ? 0u : 1u;
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (bfmt << 10) | (1u << 15) | (1u << 16) |
-                                   ((static_cast<uint32_t>(NN) >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t a_layout = gKC == 64 ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
-            const uint32_t b_layout = xKC == 64 ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
-            const uint32_t a_row = gKC * 2, b_row = xKC * 2;
-            const uint32_t a_lbo = g_chunks > 1 ? g_chunk_bytes : 0;     // Cout < 128: duplicate the block (rows unused)
-            const uint32_t b_lbo = x_chunks > 1 ? x_chunk_bytes : 0;
-            int stage = 0;
-            uint32_t phase = 0;
-            bool first_tile = true;
-            for (int t = first; t < p.num_tiles; t += p.ctas_per_group) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
-                const uint32_t b_base = a_base + g_bytes;
+        // idesc: D f32, A = bf16 (g), B = x format, both MN-major, M = 128, N = Cx
+        const uint32_t bfmt = p.x_fp16 ? 0u : 1u;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (bfmt << 10) | (1u << 15) | (1u << 16) |
+                               ((static_cast<uint32_t>(NN) >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t a_layout = gKC == 64 ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
+        const uint32_t b_layout = xKC == 64 ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
+        const uint32_t a_row = gKC * 2, b_row = xKC * 2;
+        const uint32_t a_lbo = g_chunks > 1 ? g_chunk_bytes : 0;     // Cout < 128: duplicate the block (rows unused)
+        const uint32_t b_lbo = x_chunks > 1 ? x_chunk_bytes : 0;
+        // only the 14-bit start-address field (address >> 4, low word) changes between MMAs
+        const uint64_t a_tmpl = make_smem_desc_mn(smem_u32(smem), a_lbo, 8 * a_row, a_layout);
+        const uint64_t b_tmpl = make_smem_desc_mn(smem_u32(smem) + g_bytes, b_lbo, 10 * b_row, b_layout);
+        const uint32_t a_hi = static_cast<uint32_t>(a_tmpl >> 32), b_hi = static_cast<uint32_t>(b_tmpl >> 32);
+        const uint32_t a_lo0 = static_cast<uint32_t>(a_tmpl), b_lo0 = static_cast<uint32_t>(b_tmpl);
+        const uint32_t a_ks16 = (16 * a_row) >> 4, b_row16 = b_row >> 4, stage16 = static_cast<uint32_t>(stage_bytes) >> 4;
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t acc0 = 0;                                           // 0 for the very first K-step of every accumulator
+        for (int t = first; t < p.num_tiles; t += p.ctas_per_group) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_st = a_lo0 + stage * stage16, b_st = b_lo0 + stage * stage16;
+            if (elect_one_sync()) {
                 for (int tl = 0; tl < ntaps; ++tl) {
                     const int tap = tap0 + tl, dy = tap / 3, dx = tap - dy * 3;
-                    for (int ks = 0; ks < 8; ++ks) {                     // K = 128 pixels = 8 x 16
-                        const uint64_t a_desc = make_smem_desc_mn(a_base + ks * 16 * a_row, a_lbo, 8 * a_row, a_layout);
-                        const uint64_t b_desc = make_smem_desc_mn(
-                            b_base + ((2 * ks + dy) * 10 + dx) * b_row, b_lbo, 10 * b_row, b_layout);
-                        umma_f16(tmem_base + tl * NN, a_desc, b_desc, idesc, (first_tile && ks == 0) ? 0u : 1u);
-                    }
+                    const uint32_t b_tap = b_st + (dy * 10 + dx) * b_row16;
+                    const uint32_t d_tmem = tmem_base + tl * NN;
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)                       // K = 128 pixels = 8 x 16
+                        umma_f16_split(d_tmem, a_st + ks * a_ks16, a_hi, b_tap + ks * 20 * b_row16, b_hi, idesc,
+                                       ks == 0 ? acc0 : 1u);
                 }
                 umma_commit(&empty_bar[stage]);
-                first_tile = false;
-                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(done_bar);
+            __syncwarp();
+            acc0 = 1u;
+            if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
+        if (elect_one_sync()) umma_commit(done_bar);
+        __syncwarp();
     } else {
         // final epilogue: TMEM lane = output channel co, columns = [tap][ci]
         mbar_wait(done_bar, 0);
