@@ -210,6 +210,10 @@ int aesr_mix_bwd(const void* g_dec, const void* g_mix, const float* wa, const fl
 /* torch.optim.Adam step over flat fp32 buffers (kwatsch/trainer_ae.py:29-30); `step` is the 1-based step count. */
 int aesr_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int step, void* stream);
+/* Same step with the 1-based step count read from device memory (the bias corrections are formed in the kernel): the launch
+ * carries no per-step host value, so a training step captured in a CUDA graph can be replayed. */
+int aesr_adam_step_dev(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, const int* step_dev, void* stream);
 
 /* LPIPS-VGG v0.1 (lpips/perceptual.py:19-33, lpips/networks_basic.py:63-110, lpips/pretrained_networks.py:97-135). */
 /* conv1_1 with the input pipeline folded in: (2*img-1 if normalize), ScalingLayer 1->3 channels, conv 3->64, ReLU.

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "aesr_wgrad3x3": (I, [P, P, P, P, I, I, I, I, I, I, I, P]),
     "aesr_mix_bwd": (I, [P, P, P, P, P, I, c_size_t, P]),
     "aesr_adam_step": (I, [P, P, P, P, c_size_t, F, F, F, F, F, I, P]),
+    "aesr_adam_step_dev": (I, [P, P, P, P, c_size_t, F, F, F, F, F, P, P]),
     "aesr_vgg_conv1_fwd": (I, [P, P, P, P, I, I, I, P, P, I, I, P]),
     "aesr_vgg_conv1_bwd": (I, [P, P, P, I, I, I, P, I, F, P]),
     "aesr_maxpool_bwd": (I, [P, P, P, P, I, I, I, I, I, P]),

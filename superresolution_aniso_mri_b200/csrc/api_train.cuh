@@ -186,8 +186,17 @@ int aesr_adam_step(float* p, const float* g, float* m, float* v, size_t n, float
     if (!p || !g || !m || !v || n == 0 || step < 1) return fail(AESR_ERR_INVALID, "adam_step: bad arguments");
     const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
     const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
-    adam_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2));
+    adam_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), nullptr);
     return check_launch("adam_step");
+}
+
+int aesr_adam_step_dev(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, const int* step_dev, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!p || !g || !m || !v || n == 0 || !step_dev) return fail(AESR_ERR_INVALID, "adam_step_dev: bad arguments");
+    adam_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, step_dev);
+    return check_launch("adam_step_dev");
 }
 
 int aesr_vgg_conv1_fwd(const float* img, const float* w, const float* b, void* out, int N, int H, int W,

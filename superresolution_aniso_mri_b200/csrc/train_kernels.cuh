@@ -542,7 +542,12 @@ __global__ void mix_bwd_kernel(const uint16_t* __restrict__ g_dec, const uint16_
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                            float bc1, float bc2_sqrt) {
+                            float bc1, float bc2_sqrt, const int* __restrict__ step_dev) {
+    if (step_dev != nullptr) {      // step count in device memory (a captured CUDA graph replays with a new count)
+        const float t = static_cast<float>(*step_dev);
+        bc1 = 1.f - powf(b1, t);
+        bc2_sqrt = sqrtf(1.f - powf(b2, t));
+    }
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         float gi = g[i];

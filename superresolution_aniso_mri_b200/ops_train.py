@@ -120,6 +120,15 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
                "adam_step")
 
 
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev: torch.Tensor):
+    """Adam step whose step count lives in device memory (int32 [1]): replayable inside a CUDA graph."""
+    lib = _dev(p)
+    assert step_dev.dtype == torch.int32 and step_dev.is_cuda
+    _lib.check(lib.aesr_adam_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr),
+                                      float(beta1), float(beta2), float(eps), float(weight_decay), step_dev.data_ptr(),
+                                      _stream(p)), "adam_step_dev")
+
+
 def vgg_conv1_fwd(img, w, b, shift3, scale3, normalize, dtype):
     lib = _dev(img)
     n, _, h, wd = img.shape

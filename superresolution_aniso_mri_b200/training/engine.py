@@ -17,6 +17,7 @@ ONE (two, overlapped) NCCL all-reduce(s) of the flat gradient buffer.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -65,6 +66,12 @@ class TrainEngine(TrainForward):
         self.opt = optimizer
         self.params = [p for p in model.parameters()]
         self.step_count = 0
+        # CUDA-graph replay of the whole step (168 launches; the host needs 3.2 ms to enqueue what the device runs in
+        # 3.9 ms, and the launch gaps between ~60 short conv kernels cost another 11 %, tools/train_graph_probe.py).
+        # Single-process only (the NCCL all-reduces of the data-parallel step stay eager); AESR_TRAIN_GRAPH=0 disables.
+        self.use_graph = os.environ.get("AESR_TRAIN_GRAPH", "1") != "0"
+        self._graphs = {}
+        self._graph_seen = {}
         self._flatten()
 
     # ------------------------------------------------------------------ flat parameter / gradient / moment buffers
@@ -217,6 +224,59 @@ class TrainEngine(TrainForward):
              lpips=None, ex_loss_weight: float = 0.0, combined: bool = True, do_update: bool = True,
              lr: Optional[float] = None, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
              keep: bool = False) -> dict:
+        """One optimisation step.  With ``use_graph`` (default, single process) the second and later calls of a given
+        (shapes, loss weight, lr, ...) configuration replay a CUDA graph of the step: the inputs are copied into the
+        graph's static buffers, the Adam step count travels through device memory, and the returned tensors are the
+        graph's static outputs (valid until the next step -- the trainers read them right away)."""
+        if lr is None and do_update:
+            lr = self.opt.param_groups[0]["lr"]
+        if (self.use_graph and self.world == 1 and do_update and not keep and ops.TIMING is None
+                and not torch.cuda.is_current_stream_capturing()):
+            return self._step_graphed(image, slice_between, wa, wb, lpips, ex_loss_weight, combined, lr, betas, eps,
+                                      weight_decay)
+        return self._step_impl(image, slice_between, wa, wb, lpips, ex_loss_weight, combined, do_update, lr, betas, eps,
+                               weight_decay, keep)
+
+    def _step_graphed(self, image, slice_between, wa, wb, lpips, ex_loss_weight, combined, lr, betas, eps, weight_decay):
+        key = (tuple(image.shape), tuple(slice_between.shape), tuple(wa.shape), bool(combined), float(ex_loss_weight),
+               float(lr), tuple(float(b) for b in betas), float(eps), float(weight_decay), id(lpips))
+        ent = self._graphs.get(key)
+        if ent is None:
+            if self._graph_seen.get(key, 0) < 1:
+                # first step of this configuration runs eagerly (one-time host work: shared-memory attributes, caches)
+                self._graph_seen[key] = 1
+                return self._step_impl(image, slice_between, wa, wb, lpips, ex_loss_weight, combined, True, lr, betas,
+                                       eps, weight_decay, False)
+            ent = {"x": image.detach().float().contiguous().clone(), "sb": slice_between.detach().float().contiguous().clone(),
+                   "wa": wa.detach().clone(), "wb": wb.detach().clone(),
+                   "step": torch.zeros(1, dtype=torch.int32, device=self.dev)}
+            torch.cuda.synchronize(self.dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                ent["res"] = self._step_impl(ent["x"], ent["sb"], ent["wa"], ent["wb"], lpips, ex_loss_weight, combined,
+                                             True, lr, betas, eps, weight_decay, False, step_dev=ent["step"])
+            ent["graph"] = graph
+            self._graphs[key] = ent
+        ent["x"].copy_(image, non_blocking=True)
+        ent["sb"].copy_(slice_between, non_blocking=True)
+        ent["wa"].copy_(wa, non_blocking=True)
+        ent["wb"].copy_(wb, non_blocking=True)
+        self.step_count += 1
+        ent["step"].fill_(self.step_count)
+        ent["graph"].replay()
+        self._after_update()
+        return ent["res"]
+
+    def _after_update(self):
+        if self.opt is not None:
+            for p in self.params:                # one tensor per parameter, like torch.optim.Adam keeps them
+                self.opt.state[p]["step"] = torch.tensor(float(self.step_count))
+        self.model.invalidate_cache()            # weights / BN buffers changed under the eval-path caches
+
+    def _step_impl(self, image: torch.Tensor, slice_between: torch.Tensor, wa: torch.Tensor, wb: torch.Tensor,
+                   lpips=None, ex_loss_weight: float = 0.0, combined: bool = True, do_update: bool = True,
+                   lr: Optional[float] = None, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                   keep: bool = False, step_dev: Optional[torch.Tensor] = None) -> dict:
         m = self.model
         B = image.shape[0] // 2
         x = image.detach().float().contiguous()
@@ -256,17 +316,18 @@ class TrainEngine(TrainForward):
             dist.all_reduce(self.flat_g[:self.enc_numel], op=dist.ReduceOp.AVG)
             handle_dec.wait()
 
-        if do_update:
+        if do_update and step_dev is not None:       # graph capture: the count is read from device memory at replay time
+            T.adam_step_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr, betas[0], betas[1], eps, weight_decay,
+                            step_dev)
+        elif do_update:
             self.step_count += 1
             if lr is None:
                 lr = self.opt.param_groups[0]["lr"]
             T.adam_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr, betas[0], betas[1], eps, weight_decay,
                         self.step_count)
-            if self.opt is not None:
-                for p in self.params:
-                    self.opt.state[p]["step"] = torch.tensor(float(self.step_count))
-
-        m.invalidate_cache()            # weights / BN buffers changed under the eval-path caches
+            self._after_update()
+        if not do_update:
+            m.invalidate_cache()        # BN running statistics changed under the eval-path caches
         res = {"scalars": scal, "lpips_per_image": val, "B": B, "ex_loss_weight": ex_loss_weight}
         if keep:
             res.update(reconstruction=out, s_between_mix=s_mix, z=z, z_mix=z_mix)
