@@ -168,7 +168,7 @@ def run_reference(a):
                                        "generate_hr_volumes.create_super_volume" % (sample, sample * 54, a.steps)},
             "e2e": {"value": value, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------- this repo's arm (GPU)
@@ -358,7 +358,7 @@ def run_ours(a):
                                            "reference)" % (a.cpu_sample, a.cpu_sample * 54, cpu_t)}}
         if train is not None:
             line["train"] = train
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -462,7 +462,21 @@ def bench_train(a, dev, rank, world, barrier):
                                        "AETrainerEndToEnd.train (autograd + Adam)" % cpu_dt}}
 
 
+JSON_OUT = sys.stdout
+
+
+def _json_only_stdout():
+    """The contract is ONE JSON line on stdout: keep a private handle to the real stdout for it and point file
+    descriptor 1 at stderr, so that banners written by libraries (e.g. NCCL's version line under NCCL_DEBUG=VERSION) end
+    up on stderr instead of in front of the JSON."""
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
+    _json_only_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
