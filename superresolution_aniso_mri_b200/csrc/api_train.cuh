@@ -219,7 +219,7 @@ int aesr_vgg_conv1_bwd(const void* g, const float* w, float* dimg, int N, int H,
     if (rc != AESR_OK) return rc;
     if (!g || !w || !dimg || !scale3) return fail(AESR_ERR_INVALID, "vgg_conv1_bwd: bad arguments");
     const size_t total = static_cast<size_t>(N) * H * W;
-    vgg_conv1_bwd_kernel<<<grid_for(total * 32, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    vgg_conv1_bwd_kernel<<<grid_for(total * 8, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint16_t*>(g), w, dimg, N, H, W, scale3[0], scale3[1], scale3[2], normalize, out_scale);
     return check_launch("vgg_conv1_bwd");
 }

@@ -536,88 +536,13 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
 // ph = 2a+b.  act = LeakyReLU(acc + bias) stays in fp32 registers; the head filter tap (ky,kx) carries it to output
 // pixel (2y+a-ky+1, 2x+b-kx+1) = entry [(a-ky+2)*4 + (b-kx+2)] of this pixel's 4x4 patch (origin (2y-1, 2x-1)).
 // 4 x 288 MACs per thread, filter read from the constant bank as FFMA operands.
-__device__ __forceinline__ void conv_epilogue_head_tile_v1(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
-                                                        uint64_t* tmem_empty_bar, const TileCoord& t) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int py = row >> 3, px = row & 7;
-    const int y = t.y0 + py, x = t.x0 + px;
-    const bool inb = (y < p.H) && (x < p.W);
-    const float neg_slope = (p.act == ACT_LEAKY) ? p.slope : (p.act == ACT_RELU) ? 0.f : 1.f;
-    const uint32_t t_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-    float hp[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) hp[i] = 0.f;
-    // One phase per iteration of a ROLLED loop (the body's constant-bank offsets stay static, the code stays small and
-    // the register allocator sees 16 values + 9 tap sums + 16 patch sums: no spills at 96 registers); 16 accumulator
-    // columns per TMEM load.
-#pragma unroll 1
-    for (int ph = 0; ph < 4; ++ph) {
-        float tsum[9];
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) tsum[tap] = 0.f;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int c0 = half * 16;
-            uint32_t raw[16];
-            tmem_ld_32x32b_x16(t_addr + ph * 32 + c0, raw);
-            tmem_ld_wait();
-            if (half == 1 && ph == 3) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tmem_empty_bar);
-            }
-            // packed fp32x2 math (add.f32x2 / mul.f32x2 / fma.rn.f32x2): even/odd channel pairs, half the issue slots
-            // -- with scalar FFMAs this epilogue was instruction-issue-bound (ncu: issue active 83 %, 2400 warp
-            // instructions per tile against 1152 tensor-pipe cycles).
-            float2 v[8];
-            const float2 slope2 = make_float2(neg_slope, neg_slope);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 b = lds_f4(bars.s_bias + c0 + 4 * j4);           // phase blocks share the 32 biases
-                const float2 a0 = __fadd2_rn(make_float2(__uint_as_float(raw[j4 * 4 + 0]), __uint_as_float(raw[j4 * 4 + 1])),
-                                             make_float2(b.x, b.y));
-                const float2 a1 = __fadd2_rn(make_float2(__uint_as_float(raw[j4 * 4 + 2]), __uint_as_float(raw[j4 * 4 + 3])),
-                                             make_float2(b.z, b.w));
-                const float2 s0 = __fmul2_rn(a0, slope2), s1 = __fmul2_rn(a1, slope2);
-                v[j4 * 2 + 0] = make_float2(fmaxf(a0.x, s0.x), fmaxf(a0.y, s0.y));
-                v[j4 * 2 + 1] = make_float2(fmaxf(a1.x, s1.x), fmaxf(a1.y, s1.y));
-            }
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int j2 = 0; j2 < 8; ++j2)
-                    acc = __ffma2_rn(v[j2], make_float2(p.head_wc[tap * 32 + c0 + 2 * j2], p.head_wc[tap * 32 + c0 + 2 * j2 + 1]),
-                                     acc);
-                tsum[tap] += acc.x + acc.y;
-            }
-        }
-        // scatter the 3x3 tap sums into the 4x4 patch at the phase's offset (static indices under a phase predicate)
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-            if (ph == q4) {
-                const int a = q4 >> 1, b = q4 & 1;
-#pragma unroll
-                for (int tap = 0; tap < 9; ++tap) hp[(a - tap / 3 + 2) * 4 + (b - tap % 3 + 2)] += tsum[tap];
-            }
-        }
-    }
-    if (inb) {
-        float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) +
-                                              ((static_cast<size_t>(t.n) * p.H + y) * p.W + x) * 16);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = make_float4(hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
-    }
-}
-
-// Channel-chunk-major variant: all four phases of an 8-channel chunk are in registers at once, so every filter value
+// Channel-chunk-major: all four phases of a 4-channel chunk are in registers at once, so every filter value
 // fetched from the constant bank (LDCU.128 = two FFMA2 operands) feeds four FFMA2s instead of one, and the products
 // accumulate straight into the sixteen patch entries as fp32x2 (even / odd channel) partial sums -- no per-phase tap
 // sums, no scatter.  Per tile and thread: 576 FFMA2 + 72 LDCU.128 (was 576 + 288) and 16 final adds (was 144 + 36).
-// The phase-major version above executed ~1750 warp instructions per tile at 70 % issue utilisation against 1152-1460
-// tensor-pipe cycles of the tile's MMAs (profiles/r01k_conv_full.md): the layer was bound by this epilogue's issue slots.
+// The earlier phase-major version (one phase per iteration, 9 tap sums scattered into the patch) executed ~1750 warp
+// instructions per tile at 70 % issue utilisation against 1152-1460 tensor-pipe cycles of the tile's MMAs
+// (profiles/r01k_conv_full.md): the layer was bound by this epilogue's issue slots.
 // The same loop with 1152 scalar FFMAs (uniform-register filter operand) instead of 576 FFMA2 is SLOWER (1.28 vs 1.07 ms,
 // profiles/r02f_head_scalar_vs_packed.txt): a 3-operand FFMA occupies the fp32 pipe for two cycles per warp just like an
 // FFMA2, so the packed form is the pipe's full rate and 576 x 2 cycles per tile and scheduler is this epilogue's floor.

@@ -10,96 +10,7 @@
 
 namespace aesr {
 
-// ---------------------------------------------------------------------------------------------------------------
-// conv1_1 with the LPIPS input pipeline folded in:
-//   u = 2*img - 1 (perceptual.py:30-31, normalize=True) ; v_c = (u - shift_c) / scale_c for c in 0..2
-//   (ScalingLayer, networks_basic.py:99-100: a 1-channel image broadcasts against the [1,3,1,1] buffers) ;
-//   y = ReLU(conv3x3(v, W[64,3,3,3]) + b), zero padding applies to v (after the scaling).
-// img fp32 [N,1,H,W] -> out 16-bit NHWC [N,H,W,64].  One thread = one pixel x 8 output channels.
-// ---------------------------------------------------------------------------------------------------------------
-template <bool AF>
-__global__ void vgg_conv1_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][3][3][3]*/,
-                                     const float* __restrict__ b, uint16_t* __restrict__ out, int N, int H, int W,
-                                     float sh0, float sh1, float sh2, float sc0, float sc1, float sc2, int normalize) {
-    __shared__ float sw[64 * 27];
-    __shared__ float sb[64];
-    for (int i = threadIdx.x; i < 64 * 27; i += blockDim.x) sw[i] = w[i];
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) sb[i] = b[i];
-    __syncthreads();
-    const float shf[3] = {sh0, sh1, sh2}, scv[3] = {sc0, sc1, sc2};
-    const size_t total = static_cast<size_t>(N) * H * W * 8;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const int grp = static_cast<int>(i & 7);
-        const size_t p = i >> 3;
-        const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
-        const size_t nb = (p / (static_cast<size_t>(W) * H)) * H * W;
-        float v[3][9];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
-            const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
-            float u = in ? img[nb + static_cast<size_t>(yy) * W + xx] : 0.f;
-            if (normalize) u = 2.f * u - 1.f;
-#pragma unroll
-            for (int c = 0; c < 3; ++c) v[c][t] = in ? (u - shf[c]) / scv[c] : 0.f;
-        }
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int co = grp * 8 + j;
-            float acc = sb[co];
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int t = 0; t < 9; ++t) acc = fmaf(sw[co * 27 + c * 9 + t], v[c][t], acc);
-            o[j] = fmaxf(acc, 0.f);
-        }
-        reinterpret_cast<uint4*>(out)[i] = make_uint4(pack2_t<AF>(o[0], o[1]), pack2_t<AF>(o[2], o[3]),
-                                                      pack2_t<AF>(o[4], o[5]), pack2_t<AF>(o[6], o[7]));
-    }
-}
-
-// backward of the above w.r.t. the image: g bf16 [N,H,W,64] is dL/d(pre-ReLU conv1_1 output) (ReLU' already applied)
-//   dimg[p] = (normalize ? 2 : 1) * sum_c (1/scale_c) * sum_{tap,co} W[co][c][tap] * g[p - off(tap)][co]
-// One warp per pixel: lanes split the 64 output channels (2 each), shuffle-reduce.
-__global__ void vgg_conv1_bwd_kernel(const uint16_t* __restrict__ g, const float* __restrict__ w,
-                                     float* __restrict__ dimg, int N, int H, int W, float sc0, float sc1, float sc2,
-                                     int normalize, float out_scale) {
-    __shared__ float swe[9 * 64];          // effective 1-channel filter: sum_c W[co][c][tap] / scale_c
-    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) {
-        const int t = i / 64, co = i % 64;
-        swe[i] = w[co * 27 + 0 * 9 + t] / sc0 + w[co * 27 + 1 * 9 + t] / sc1 + w[co * 27 + 2 * 9 + t] / sc2;
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const size_t warp_id = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
-    const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
-    const size_t total = static_cast<size_t>(N) * H * W;
-    for (size_t p = warp_id; p < total; p += nwarps) {
-        const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
-        const size_t nb = (p / (static_cast<size_t>(W) * H)) * H * W;
-        float acc = 0.f;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
-            if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-            const uint32_t u = *reinterpret_cast<const uint32_t*>(g + (nb + static_cast<size_t>(yy) * W + xx) * 64 + lane * 2);
-            acc = fmaf(swe[t * 64 + lane * 2], bf16_lo(u), acc);
-            acc = fmaf(swe[t * 64 + lane * 2 + 1], bf16_hi(u), acc);
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) dimg[p] = acc * (normalize ? 2.f : 1.f) * out_scale;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// MaxPool2d(2) backward fused with the tap gradient and the ReLU' of the producing conv:
-//   g_out[y,x,c] = relu'(a) * ( first_argmax(a over its 2x2 window) ? d_pooled[y/2,x/2,c] : 0  +  g_tap[y,x,c] )
-// a: post-ReLU activation 16-bit [N,H,W,C]; d_pooled bf16 [N,H/2,W/2,C]; g_tap bf16 [N,H,W,C] or null.
-// ---------------------------------------------------------------------------------------------------------------
-// One thread = 8 channels (16 bytes) of one pixel: the element-per-thread version spent its time on 2-byte accesses and
-// three integer divisions per element (0.23 ms of a 5 ms training step, bench.py kernel_ms).
+// 8 consecutive 16-bit channels (one 16-byte load) as floats
 template <bool AF>
 __device__ __forceinline__ void load8(const uint16_t* p, float (&v)[8]) {
     const uint4 m = __ldg(reinterpret_cast<const uint4*>(p));
@@ -111,6 +22,142 @@ __device__ __forceinline__ void load8(const uint16_t* p, float (&v)[8]) {
         v[2 * k + 1] = f.y;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// conv1_1 with the LPIPS input pipeline folded in:
+//   u = 2*img - 1 (perceptual.py:30-31, normalize=True) ; v_c = (u - shift_c) / scale_c for c in 0..2
+//   (ScalingLayer, networks_basic.py:99-100: a 1-channel image broadcasts against the [1,3,1,1] buffers) ;
+//   y = ReLU(conv3x3(v, W[64,3,3,3]) + b), zero padding applies to v (after the scaling).
+// img fp32 [N,1,H,W] -> out 16-bit NHWC [N,H,W,64].  One thread = one pixel x 8 output channels.
+// ---------------------------------------------------------------------------------------------------------------
+// The three input channels are affine images of ONE image (v_c = (u - shift_c) / scale_c), so the 3 -> 64 conv collapses to
+// a 1 -> 64 conv on img with a border-dependent bias (zero padding applies to v, i.e. an off-image tap contributes
+// nothing, not even its shift term):
+//   y[co] = bcls[class(y,x)][co] + sum_{t on image} W2[t][co] * img_t ,   W2 = s * sum_c W[co][c][t] / scale_c   (s = 2 if normalize)
+//   bcls[class][co] = b[co] - sum_{t valid for the class} ( sum_c W[co][c][t] * shift_c / scale_c  [+ sum_c W/scale_c if normalize] )
+// with nine classes (first / inner / last row x column) like the encoder stem.  72 instead of 216 MACs per thread and the
+// filter read as 16-byte shared-memory words (the 3-channel version did one LDS per MAC: 231 us for 24 images).
+template <bool AF>
+__global__ void vgg_conv1_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][3][3][3]*/,
+                                     const float* __restrict__ b, uint16_t* __restrict__ out, int N, int H, int W,
+                                     float sh0, float sh1, float sh2, float sc0, float sc1, float sc2, int normalize) {
+    __shared__ __align__(16) float sW[9][64];       // W2[t][co]
+    __shared__ float sK[9][64];                      // per-tap constant that an on-image tap subtracts
+    __shared__ __align__(16) float sB[9][64];       // bias per border class
+    const float shf[3] = {sh0, sh1, sh2}, scv[3] = {sc0, sc1, sc2};
+    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) {
+        const int t = i / 64, co = i % 64;
+        float we = 0.f, ws = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float wv = w[co * 27 + c * 9 + t];
+            we += wv / scv[c];
+            ws += wv * shf[c] / scv[c];
+        }
+        sW[t][co] = normalize ? 2.f * we : we;
+        sK[t][co] = normalize ? ws + we : ws;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) {
+        const int cls = i / 64, co = i % 64, cy = cls / 3, cx = cls % 3;
+        float acc = b[co];
+        for (int t = 0; t < 9; ++t) {
+            const int dy = t / 3, dx = t % 3;
+            // H == 1 / W == 1: a pixel is first and last at once; class 0 then also drops the far tap (handled below)
+            const bool ok = !(cy == 0 && dy == 0) && !(cy == 2 && dy == 2) && !(cx == 0 && dx == 0) && !(cx == 2 && dx == 2);
+            if (ok) acc -= sK[t][co];
+        }
+        sB[cls][co] = acc;
+    }
+    __syncthreads();
+    const size_t total = static_cast<size_t>(N) * H * W * 8;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int grp = static_cast<int>(i & 7);
+        const size_t p = i >> 3;
+        const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+        const size_t nb = (p / (static_cast<size_t>(W) * H)) * H * W;
+        float o[8];
+        const bool degenerate = H < 2 || W < 2;          // single-row / single-column images: generic per-tap bias
+        if (!degenerate) {
+            const int cls = ((y == 0) ? 0 : (y == H - 1) ? 2 : 1) * 3 + ((x == 0) ? 0 : (x == W - 1) ? 2 : 1);
+            const float4 b0 = *reinterpret_cast<const float4*>(&sB[cls][grp * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sB[cls][grp * 8 + 4]);
+            o[0] = b0.x; o[1] = b0.y; o[2] = b0.z; o[3] = b0.w; o[4] = b1.x; o[5] = b1.y; o[6] = b1.z; o[7] = b1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = b[grp * 8 + j];
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+            const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            if (!in) continue;
+            const float u = img[nb + static_cast<size_t>(yy) * W + xx];
+            const float4 w0 = *reinterpret_cast<const float4*>(&sW[t][grp * 8]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&sW[t][grp * 8 + 4]);
+            o[0] = fmaf(w0.x, u, o[0]); o[1] = fmaf(w0.y, u, o[1]); o[2] = fmaf(w0.z, u, o[2]); o[3] = fmaf(w0.w, u, o[3]);
+            o[4] = fmaf(w1.x, u, o[4]); o[5] = fmaf(w1.y, u, o[5]); o[6] = fmaf(w1.z, u, o[6]); o[7] = fmaf(w1.w, u, o[7]);
+            if (degenerate) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] -= sK[t][grp * 8 + j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(pack2_t<AF>(o[0], o[1]), pack2_t<AF>(o[2], o[3]),
+                                                      pack2_t<AF>(o[4], o[5]), pack2_t<AF>(o[6], o[7]));
+    }
+}
+// backward of the above w.r.t. the image: g bf16 [N,H,W,64] is dL/d(pre-ReLU conv1_1 output) (ReLU' already applied)
+//   dimg[p] = (normalize ? 2 : 1) * sum_c (1/scale_c) * sum_{tap,co} W[co][c][tap] * g[p - off(tap)][co]
+// Eight lanes per pixel, 8 channels (one 16-byte load) per lane and tap, three shuffles to fold the eight partial sums.
+__global__ void vgg_conv1_bwd_kernel(const uint16_t* __restrict__ g, const float* __restrict__ w,
+                                     float* __restrict__ dimg, int N, int H, int W, float sc0, float sc1, float sc2,
+                                     int normalize, float out_scale) {
+    __shared__ __align__(16) float swe[9 * 64];          // effective 1-channel filter: sum_c W[co][c][tap] / scale_c
+    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) {
+        const int t = i / 64, co = i % 64;
+        swe[i] = w[co * 27 + 0 * 9 + t] / sc0 + w[co * 27 + 1 * 9 + t] / sc1 + w[co * 27 + 2 * 9 + t] / sc2;
+    }
+    __syncthreads();
+    const int sub = threadIdx.x & 7;
+    const size_t grp_id = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 3;
+    const size_t ngrp = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 3;
+    const size_t total = static_cast<size_t>(N) * H * W;
+    const size_t rounds = (total + ngrp - 1) / ngrp;                          // warp-uniform trip count (shuffles inside)
+    for (size_t it = 0; it < rounds; ++it) {
+        const size_t p = it * ngrp + grp_id;
+        const bool live = p < total;
+        float acc = 0.f;
+        if (live) {
+            const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
+            const size_t nb = (p / (static_cast<size_t>(W) * H)) * H * W;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                float gv[8];
+                load8<false>(g + (nb + static_cast<size_t>(yy) * W + xx) * 64 + sub * 8, gv);
+                const float4 w0 = *reinterpret_cast<const float4*>(&swe[t * 64 + sub * 8]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&swe[t * 64 + sub * 8 + 4]);
+                acc = fmaf(w0.x, gv[0], acc); acc = fmaf(w0.y, gv[1], acc); acc = fmaf(w0.z, gv[2], acc); acc = fmaf(w0.w, gv[3], acc);
+                acc = fmaf(w1.x, gv[4], acc); acc = fmaf(w1.y, gv[5], acc); acc = fmaf(w1.z, gv[6], acc); acc = fmaf(w1.w, gv[7], acc);
+            }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (live && sub == 0) dimg[p] = acc * (normalize ? 2.f : 1.f) * out_scale;
+    }
+}
+// ---------------------------------------------------------------------------------------------------------------
+// MaxPool2d(2) backward fused with the tap gradient and the ReLU' of the producing conv:
+//   g_out[y,x,c] = relu'(a) * ( first_argmax(a over its 2x2 window) ? d_pooled[y/2,x/2,c] : 0  +  g_tap[y,x,c] )
+// a: post-ReLU activation 16-bit [N,H,W,C]; d_pooled bf16 [N,H/2,W/2,C]; g_tap bf16 [N,H,W,C] or null.
+// ---------------------------------------------------------------------------------------------------------------
+// One thread = 8 channels (16 bytes) of one pixel: the element-per-thread version spent its time on 2-byte accesses and
+// three integer divisions per element (0.23 ms of a 5 ms training step, bench.py kernel_ms).
 template <bool AF>
 __global__ void maxpool_bwd_kernel(const uint16_t* __restrict__ a, const uint16_t* __restrict__ d_pooled,
                                    const uint16_t* __restrict__ g_tap, uint16_t* __restrict__ g_out, int N, int H,

@@ -329,7 +329,10 @@ def copy_rows_async(dst: torch.Tensor, src: torch.Tensor, dst_offset: int, src_o
                     dst_outer_stride: int, src_outer_stride: int, rows: int, dpitch: int, spitch: int, width: int,
                     stream: torch.cuda.Stream) -> None:
     """``outer`` strided 2-D copies between a PINNED host tensor and a device tensor (either direction, taken from
-    which of the two is on the device); offsets / strides / pitches / width in BYTES.  Stream-ordered on ``stream``."""
+    which of the two is on the device); offsets / strides / pitches / width in BYTES.  Stream-ordered on ``stream``.
+    (A download done by a few thread blocks storing straight into the pinned buffer reaches the same 52 GB/s alone but
+    starves behind the persistent conv CTAs inside the pipeline: 7.0 vs 5.1 ms per step,
+    profiles/r02n_e2e_sm_download_probe.txt -- the copy engine stays.)"""
     to_host = src.is_cuda
     lib = _dev(src if to_host else dst)
     host = dst if to_host else src

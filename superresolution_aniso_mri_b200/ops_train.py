@@ -144,8 +144,9 @@ def vgg_conv1_bwd(g, w, scale3, normalize, out_scale=1.0):
     lib = _dev(g)
     n, h, wd, _ = g.shape
     dimg = torch.empty((n, 1, h, wd), dtype=torch.float32, device=g.device)
-    _lib.check(lib.aesr_vgg_conv1_bwd(g.data_ptr(), w.data_ptr(), dimg.data_ptr(), n, h, wd, _F3(*scale3),
-                                      int(normalize), float(out_scale), _stream(g)), "vgg_conv1_bwd")
+    with _timed("vgg_conv1"):
+        _lib.check(lib.aesr_vgg_conv1_bwd(g.data_ptr(), w.data_ptr(), dimg.data_ptr(), n, h, wd, _F3(*scale3),
+                                          int(normalize), float(out_scale), _stream(g)), "vgg_conv1_bwd")
     return dimg
 
 
