@@ -207,10 +207,12 @@ int halo_pick_bn(int Cin, int Cout) {
 // 1 = AESR_CONV_T forced M-tiles per super-tile, 2 = AESR_CONV_NBUF forced TMEM buffers, 3 = AESR_CONV_STAGES cap,
 // 4 = AESR_HEAD_MMA decoder head behind dec.12 on warp-level mma.sync fragments (16-bit activations / filter).
 // 5 = AESR_STEM_CUDA_CORES encoder stem on the CUDA cores (fp32 FMAs) instead of warp-level tf32 mma.sync.
-int g_tune[6] = {-1, -1, -1, -1, -1, -1};
+// 6 = AESR_WGRAD_NO_FOLD weight gradient of Cin = 32 layers with one MMA per tap instead of one per filter row.
+// 7 = AESR_WGRAD_CTAS cap on the CTAs of a weight-gradient launch (each CTA ends with Cout x Cin x taps atomics).
+int g_tune[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
 int tune(int key) {
-    static const char* names[6] = {"AESR_CONV_DEBUG", "AESR_CONV_T", "AESR_CONV_NBUF", "AESR_CONV_STAGES", "AESR_HEAD_MMA",
-                                   "AESR_STEM_CUDA_CORES"};
+    static const char* names[8] = {"AESR_CONV_DEBUG", "AESR_CONV_T", "AESR_CONV_NBUF", "AESR_CONV_STAGES", "AESR_HEAD_MMA",
+                                   "AESR_STEM_CUDA_CORES", "AESR_WGRAD_NO_FOLD", "AESR_WGRAD_CTAS"};
     if (g_tune[key] < 0) g_tune[key] = getenv(names[key]) ? atoi(getenv(names[key])) : 0;
     return g_tune[key];
 }
@@ -319,7 +321,7 @@ int aesr_init(int device) {
 const char* aesr_last_error(void) { return g_err; }
 
 int aesr_set_tuning(int key, int value) {
-    if (key < 0 || key > 5 || value < 0) return fail(AESR_ERR_INVALID, "set_tuning: key %d value %d", key, value);
+    if (key < 0 || key > 7 || value < 0) return fail(AESR_ERR_INVALID, "set_tuning: key %d value %d", key, value);
     g_tune[key] = value;
     return AESR_OK;
 }

@@ -129,10 +129,26 @@ int aesr_wgrad3x3(const void* g, const void* x, float* dW, float* dbias, int N, 
         p.taps_per_group = Cin <= 32 ? 9 : Cin <= 64 ? 5 : 3;
         p.num_groups = (9 + p.taps_per_group - 1) / p.taps_per_group;
         int per = g_sm_count / p.num_groups;
+        if (tune(7) > 0) {
+            if (per > tune(7) / p.num_groups) per = tune(7) / p.num_groups;
+        } else {
+            // Every CTA ends with Cout x Cin x taps fp32 atomics on dW, so the launch costs about
+            //   tiles / C * t_tile + C * t_atomics   per tap group;
+            // measured (profiles/r02q_wgrad_cta_sweep.txt): ~24.5 ns per 1000 atomics chip-wide, a tile's MMAs at the
+            // tensor-pipe rate of its N (0.7 us for a folded Cin = 32 tile).  C = sqrt(tiles * t_tile / t_atomics).
+            const double cyc = Cin <= 32 ? 56.0 * 3 * 8 : (Cin <= 64 ? 48.0 : 64.0) * p.taps_per_group * 8;
+            const double t_tile = cyc / 1900.0;                                                    // us
+            const double t_atom = 24.5e-6 * static_cast<double>(Cout) * Cin * p.taps_per_group;   // us per CTA
+            const int best = static_cast<int>(sqrt(static_cast<double>(p.num_tiles) * t_tile / t_atom) + 0.5);
+            if (per > best) per = best;
+        }
         if (per > p.num_tiles) per = p.num_tiles;
         if (per < 1) per = 1;
         p.ctas_per_group = per;
         p.x_fp16 = (dtype == AESR_DT_FP16);
+        p.fold_dx = tune(6) == 0;
+        p.stages = WG_MAX_STAGES;
+        while (p.stages > 2 && wg_smem_bytes(Cout, Cin, p.stages) > g_max_smem_optin) --p.stages;
         p.dW = dW;
         CUtensorMap tg, tx;
         rc = make_act_tmap(&tg, g, N, H, W, Cout, Cout < 64 ? 32 : 64, 8, 16);
@@ -142,7 +158,7 @@ int aesr_wgrad3x3(const void* g, const void* x, float* dW, float* dbias, int N, 
         static int configured = 0;
         rc = set_max_smem(wgrad3x3_tc_kernel, &configured);
         if (rc != AESR_OK) return rc;
-        wgrad3x3_tc_kernel<<<per * p.num_groups, WG_THREADS, wg_smem_bytes(Cout, Cin), s>>>(tg, tx, p);
+        wgrad3x3_tc_kernel<<<per * p.num_groups, WG_THREADS, wg_smem_bytes(Cout, Cin, p.stages), s>>>(tg, tx, p);
         rc = check_launch("wgrad3x3_tc");
         if (rc != AESR_OK) return rc;
         if (dbias) {

@@ -21,11 +21,14 @@ struct WgradParams {
     int taps_per_group, num_groups;
     int ctas_per_group;
     int x_fp16;                   // x operand format: 1 fp16, 0 bf16 (g is always bf16)
+    int stages;                   // pipeline depth (2..WG_MAX_STAGES, as many as fit in shared memory)
+    int fold_dx;                  // Cin = 32: one N = 96 MMA per filter row (tuning knob, default on)
     float* dW;                    // [Cg][Cx][9] fp32, accumulated
 };
 
 constexpr int WG_THREADS = 192;
-constexpr int WG_STAGES = 2;
+constexpr int WG_MAX_STAGES = 6;       // (g tile, x halo) pairs in flight: as many as fit (one tile's MMAs are ~1.3-5 k cycles, an
+                                       // L2 -> SMEM round trip under load about as much: two stages left the producer exposed)
 
 __host__ __device__ constexpr int wg_g_chunk_bytes(int Cg) { return 128 * (Cg < 64 ? Cg : 64) * 2; }
 __host__ __device__ constexpr int wg_x_chunk_bytes(int Cx) {
@@ -34,7 +37,7 @@ __host__ __device__ constexpr int wg_x_chunk_bytes(int Cx) {
 __host__ __device__ constexpr int wg_stage_bytes(int Cg, int Cx) {
     return wg_g_chunk_bytes(Cg) * ((Cg + 63) / 64) + wg_x_chunk_bytes(Cx) * ((Cx + 63) / 64);
 }
-__host__ __device__ constexpr int wg_smem_bytes(int Cg, int Cx) { return 1024 + WG_STAGES * wg_stage_bytes(Cg, Cx) + 256; }
+__host__ __device__ constexpr int wg_smem_bytes(int Cg, int Cx, int stages) { return 1024 + stages * wg_stage_bytes(Cg, Cx) + 256; }
 
 // MN-major shared-memory descriptor: LBO = stride between 64-element (swizzle-row) blocks along M/N,
 // SBO = stride between groups of 8 K-rows.
@@ -59,10 +62,11 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_cons
     const int g_chunk_bytes = wg_g_chunk_bytes(p.Cg), x_chunk_bytes = wg_x_chunk_bytes(p.Cx);
     const int g_bytes = g_chunk_bytes * g_chunks;
     const int stage_bytes = wg_stage_bytes(p.Cg, p.Cx);
-    uint8_t* tail = smem + WG_STAGES * stage_bytes;
+    const int num_stages = p.stages;
+    uint8_t* tail = smem + num_stages * stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-    uint64_t* empty_bar = full_bar + WG_STAGES;
-    uint64_t* done_bar = empty_bar + WG_STAGES;
+    uint64_t* empty_bar = full_bar + WG_MAX_STAGES;
+    uint64_t* done_bar = empty_bar + WG_MAX_STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -72,7 +76,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_cons
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_g);
         tma_prefetch_desc(&tmap_x);
-        for (int s = 0; s < WG_STAGES; ++s) {
+        for (int s = 0; s < num_stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
@@ -111,7 +115,7 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_cons
                     tma_load_4d(base + g_bytes + c * x_chunk_bytes, &tmap_x, &full_bar[stage], c * 64, x0 - 1, y0 - 1, n);
             }
             __syncwarp();
-            if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1) {
         // idesc: D f32, A = bf16 (g), B = x format, both MN-major, M = 128, N = Cx
@@ -129,6 +133,10 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_cons
         const uint32_t a_hi = static_cast<uint32_t>(a_tmpl >> 32), b_hi = static_cast<uint32_t>(b_tmpl >> 32);
         const uint32_t a_lo0 = static_cast<uint32_t>(a_tmpl), b_lo0 = static_cast<uint32_t>(b_tmpl);
         const uint32_t a_ks16 = (16 * a_row) >> 4, b_row16 = b_row >> 4, stage16 = static_cast<uint32_t>(stage_bytes) >> 4;
+        // dx-folded variant (Cin = 32, all nine taps in this CTA): same descriptor with LBO = one pixel, N = 96
+        const bool fold_dx = p.Cx == 32 && ntaps == 9 && p.fold_dx;
+        const uint32_t b_lo96 = static_cast<uint32_t>(make_smem_desc_mn(smem_u32(smem) + g_bytes, b_row, 10 * b_row, b_layout));
+        const uint32_t idesc96 = (idesc & ~(0x3Fu << 17)) | ((96u >> 3) << 17);
         int stage = 0;
         uint32_t phase = 0;
         uint32_t acc0 = 0;                                           // 0 for the very first K-step of every accumulator
@@ -136,21 +144,38 @@ wgrad3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_g, const __grid_cons
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint32_t a_st = a_lo0 + stage * stage16, b_st = b_lo0 + stage * stage16;
+            const uint32_t b_st96 = b_lo96 + stage * stage16;
             if (elect_one_sync()) {
-                for (int tl = 0; tl < ntaps; ++tl) {
-                    const int tap = tap0 + tl, dy = tap / 3, dx = tap - dy * 3;
-                    const uint32_t b_tap = b_st + (dy * 10 + dx) * b_row16;
-                    const uint32_t d_tmem = tmem_base + tl * NN;
+                if (fold_dx) {
+                    // Cin = 32: the three dx taps of a filter row are ONE MMA with N = 96 -- the B operand's 32-channel
+                    // N-blocks are strided by LBO = one halo pixel (64 bytes), so block j reads the window shifted by
+                    // j pixels, and its 32 accumulator columns are exactly tap (dy, j)'s.  24 MMAs of N = 96 per tile
+                    // instead of 72 of N = 32 (each A read of 4 KB now feeds three taps).
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)                       // K = 128 pixels = 8 x 16
-                        umma_f16_split(d_tmem, a_st + ks * a_ks16, a_hi, b_tap + ks * 20 * b_row16, b_hi, idesc,
-                                       ks == 0 ? acc0 : 1u);
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const uint32_t b_tap = b_st96 + dy * 10 * b_row16;
+                        const uint32_t d_tmem = tmem_base + dy * 3 * NN;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            umma_f16_split(d_tmem, a_st + ks * a_ks16, a_hi, b_tap + ks * 20 * b_row16, b_hi, idesc96,
+                                           ks == 0 ? acc0 : 1u);
+                    }
+                } else {
+                    for (int tl = 0; tl < ntaps; ++tl) {
+                        const int tap = tap0 + tl, dy = tap / 3, dx = tap - dy * 3;
+                        const uint32_t b_tap = b_st + (dy * 10 + dx) * b_row16;
+                        const uint32_t d_tmem = tmem_base + tl * NN;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)                       // K = 128 pixels = 8 x 16
+                            umma_f16_split(d_tmem, a_st + ks * a_ks16, a_hi, b_tap + ks * 20 * b_row16, b_hi, idesc,
+                                           ks == 0 ? acc0 : 1u);
+                    }
                 }
                 umma_commit(&empty_bar[stage]);
             }
             __syncwarp();
             acc0 = 1u;
-            if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
         if (elect_one_sync()) umma_commit(done_bar);
         __syncwarp();
