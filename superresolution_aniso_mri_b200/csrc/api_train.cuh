@@ -109,7 +109,10 @@ int aesr_e0_bwd(const void* g, const float* x, float* dw, float* db, int N, int 
     if (rc != AESR_OK) return rc;
     if (!g || !x || !dw || !db || C != 32) return fail(AESR_ERR_INVALID, "e0_bwd: bad arguments (C must be 32)");
     const size_t total = static_cast<size_t>(N) * (H + 2) * (W + 2);
-    e0_bwd_kernel<<<grid_for(total * 32 / 16, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint16_t*>(g), x, dw, db, N, H, W, C);
+    int gx = static_cast<int>((total + 64 * 8 - 1) / (64 * 8));            // >= 8 pixels per thread
+    if (gx > g_sm_count * 8) gx = g_sm_count * 8;
+    if (gx < 1) gx = 1;
+    e0_bwd_kernel<<<gx, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint16_t*>(g), x, dw, db, N, H, W, C);
     return check_launch("e0_bwd");
 }
 

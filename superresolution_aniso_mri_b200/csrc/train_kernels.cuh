@@ -442,27 +442,47 @@ __global__ void head_bwd_weight_kernel(const float* __restrict__ dout, const flo
 
 // ---------------------------------------------------------------------------------------------------------------
 // enc.0 backward: a0[p][c] = w0[c] * xpad[p] + b0[c]  =>  dw0[c] += sum_p g[p][c] * xpad[p], db0[c] += sum_p g[p][c]
-// g bf16 [N,H+2,W+2,C] (C = 32: lane = channel), x fp32 [N,1,H,W].
+// g bf16 [N,H+2,W+2,C] (C = 32), x fp32 [N,1,H,W].  Four threads per pixel, 8 channels (one 16-byte load) each; the 64
+// pixel rows of a block are folded through shared memory and the block issues 64 atomics.  (One warp per pixel with
+// 2-byte loads and 64 atomics per WARP onto the same 64 addresses: 89 us, profiles/r02u_train_launches.md.)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void e0_bwd_kernel(const uint16_t* __restrict__ g, const float* __restrict__ x, float* __restrict__ dw,
-                              float* __restrict__ db, int N, int H, int W, int C) {
-    const int lane = threadIdx.x & 31;
-    const size_t warp_id = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5;
-    const size_t nwarps = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5;
+__global__ void __launch_bounds__(256)
+e0_bwd_kernel(const uint16_t* __restrict__ g, const float* __restrict__ x, float* __restrict__ dw,
+              float* __restrict__ db, int N, int H, int W, int C) {
+    __shared__ float s_w[64][33], s_b[64][33];
+    const int cg = threadIdx.x & 3, row = threadIdx.x >> 2;          // 4 channel groups x 64 pixel rows
     const int Ho = H + 2, Wo = W + 2;
     const size_t total = static_cast<size_t>(N) * Ho * Wo;
-    float aw = 0.f, ab = 0.f;
-    for (size_t p = warp_id; p < total; p += nwarps) {
+    float aw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, ab[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (size_t p = blockIdx.x * static_cast<size_t>(64) + row; p < total; p += static_cast<size_t>(gridDim.x) * 64) {
         const int xo = static_cast<int>(p % Wo), yo = static_cast<int>((p / Wo) % Ho);
         const int n = static_cast<int>(p / (static_cast<size_t>(Wo) * Ho));
         const int yi = yo - 1, xi = xo - 1;
-        const float xv = (yi >= 0 && yi < H && xi >= 0 && xi < W) ? x[(static_cast<size_t>(n) * H + yi) * W + xi] : 0.f;
-        const float gv = bf16_to_f(g[p * C + lane]);
-        aw = fmaf(gv, xv, aw);
-        ab += gv;
+        const float xv = (yi >= 0 && yi < H && xi >= 0 && xi < W) ? __ldg(x + (static_cast<size_t>(n) * H + yi) * W + xi) : 0.f;
+        const uint4 m = __ldg(reinterpret_cast<const uint4*>(g + p * C) + cg);
+        const uint32_t u[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float lo = bf16_lo(u[k]), hi = bf16_hi(u[k]);
+            aw[2 * k] = fmaf(lo, xv, aw[2 * k]);
+            aw[2 * k + 1] = fmaf(hi, xv, aw[2 * k + 1]);
+            ab[2 * k] += lo;
+            ab[2 * k + 1] += hi;
+        }
     }
-    atomicAdd(dw + lane, aw);
-    atomicAdd(db + lane, ab);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        s_w[row][cg * 8 + k] = aw[k];
+        s_b[row][cg * 8 + k] = ab[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x & 31;
+        const bool bias = threadIdx.x >= 32;
+        float t = 0.f;
+        for (int r = 0; r < 64; ++r) t += bias ? s_b[r][c] : s_w[r][c];
+        atomicAdd((bias ? db : dw) + c, t);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
