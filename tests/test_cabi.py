@@ -78,3 +78,30 @@ def test_top_level_dropin_import_paths():
     assert hasattr(mod, "VanillaACAI")
     ghv = importlib.import_module("generate_hr_volumes")
     assert hasattr(ghv, "create_super_volume") and hasattr(ghv, "latent_space_interp")
+
+
+def test_synthesis_plan_tables_match_per_volume_pair_plan():
+    """The cached device-resident index / weight tables of a batched synthesis problem (synthesis._synthesis_plan) equal
+    the per-volume plan (pair_plan: out[i*(A+1)+1+k] = dec(w_hi[k] z[i+1] + w_lo[k] z[i]), generate_hr_volumes.py:46-66),
+    including the degenerate shapes (one slice, no alphas)."""
+    import numpy as np
+    import torch
+    from superresolution_aniso_mri_b200 import synthesis as S
+    for V, Z, ar in ((2, 1, [0.5]), (1, 2, []), (3, 4, [0.25, 0.5, 0.75]), (1, 2, [0.5]), (5, 10, list(np.linspace(0, 1, 8)[1:-1]))):
+        p = S._synthesis_plan(V, Z, ar, torch.device("cpu"))
+        A = len(ar)
+        Zo = (Z - 1) * (A + 1) + 1
+        assert p["idx"].tolist() == list(range(V * Z))
+        assert p["oi_kept"].tolist() == [v * Zo + i * (A + 1) for v in range(V) for i in range(Z)]
+        assert p["pa"].numel() == V * (Z - 1) and p["oi"].numel() == V * (Z - 1) * A
+        if Z > 1 and A > 0:
+            w_hi, w_lo = S.interp_weights(ar)
+            assert np.array_equal(p["wa"].numpy(), w_hi) and np.array_equal(p["wb"].numpy(), w_lo)
+            for v in range(V):
+                ia, ib, _, _, oi = S.pair_plan(Z, A, w_hi, w_lo, "cpu", slice_offset=v * Z, out_offset=v * Zo)
+                q0 = v * (Z - 1)
+                assert np.array_equal(p["pa"][q0:q0 + Z - 1].numpy(), ia[::A])
+                assert np.array_equal(p["pb"][q0:q0 + Z - 1].numpy(), ib[::A])
+                assert np.array_equal(p["oi"][q0 * A:(q0 + Z - 1) * A].numpy(), oi)
+    assert S._synthesis_plan(3, 4, [0.25, 0.5, 0.75], torch.device("cpu")) is S._synthesis_plan(3, 4, [0.25, 0.5, 0.75],
+                                                                                                 torch.device("cpu"))
