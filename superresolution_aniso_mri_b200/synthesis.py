@@ -169,7 +169,8 @@ class HostPipeline:
     once at the end: the staging buffers and their events persist across calls, so the copies of batch i overlap the
     compute of batch i+1 and the only serial parts left are the first upload and the last download."""
 
-    def __init__(self, model, V, Z, H, W, alpha_range, groups: int = 2, chunk: int = 4096, host_kept: bool = True):
+    def __init__(self, model, V, Z, H, W, alpha_range, groups: int = 2, chunk: int = 4096, host_kept: bool = True,
+                 d2h_streams: int = 2):
         self.model, self.ar, self.chunk = model, list(alpha_range), chunk
         self.host_kept = bool(host_kept) and len(self.ar) >= 1 and Z >= 2
         self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=1) if self.host_kept else None
@@ -184,6 +185,9 @@ class HostPipeline:
         self.d_in = [torch.empty(gmax, Z, H, W, device=dev) for _ in range(2)]
         self.d_out = [torch.empty(gmax, Zo, H, W, device=dev) for _ in range(2)]
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        # download streams: each group's volumes are split between them (two copy engines in flight: 5.03 vs 5.13-5.30 ms
+        # per step, profiles/r02x_d2h_streams.txt; a third changes nothing)
+        self.s_out_extra = [torch.cuda.Stream(dev) for _ in range(max(0, int(d2h_streams) - 1))] if host_kept else []
         self.in_free = [torch.cuda.Event() for _ in range(2)]     # compute finished reading d_in[b]
         self.out_free = [torch.cuda.Event() for _ in range(2)]    # copy-out finished reading d_out[b]
         # bytes crossing PCIe per run() (what bench.py reports): all inputs up, synthesized (or all) slices down
@@ -223,9 +227,20 @@ class HostPipeline:
                     Z, A = host_in.shape[1], len(self.ar)
                     sl = host_out.shape[2] * host_out.shape[3] * 4          # bytes per slice
                     vol = host_out.shape[1] * sl
-                    ops.copy_rows_async(host_out, self.d_out[b], s * vol + sl, sl, outer=n, dst_outer_stride=vol,
-                                        src_outer_stride=vol, rows=Z - 1, dpitch=(A + 1) * sl, spitch=(A + 1) * sl,
-                                        width=A * sl, stream=self.s_out)
+                    streams = [self.s_out] + self.s_out_extra
+                    parts = [(k * n // len(streams), (k + 1) * n // len(streams)) for k in range(len(streams))]
+                    for st, (v0, v1) in zip(streams, parts):
+                        if v1 <= v0:
+                            continue
+                        if st is not self.s_out:
+                            st.wait_event(done)
+                        ops.copy_rows_async(host_out, self.d_out[b], (s + v0) * vol + sl, v0 * vol + sl, outer=v1 - v0,
+                                            dst_outer_stride=vol, src_outer_stride=vol, rows=Z - 1, dpitch=(A + 1) * sl,
+                                            spitch=(A + 1) * sl, width=A * sl, stream=st)
+                        if st is not self.s_out:
+                            ev = torch.cuda.Event()
+                            ev.record(st)
+                            self.s_out.wait_event(ev)
                 else:
                     host_out[s:e].copy_(self.d_out[b][:n], non_blocking=True)
                 self.out_free[b].record(self.s_out)
