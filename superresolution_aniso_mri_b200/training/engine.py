@@ -70,6 +70,11 @@ class TrainEngine(TrainForward):
         # 3.9 ms, and the launch gaps between ~60 short conv kernels cost another 11 %, tools/train_graph_probe.py).
         # Single-process only (the NCCL all-reduces of the data-parallel step stay eager); AESR_TRAIN_GRAPH=0 disables.
         self.use_graph = os.environ.get("AESR_TRAIN_GRAPH", "1") != "0"
+        # data-parallel: capture the NCCL all-reduces inside the step graph as well.  OPT-IN (AESR_TRAIN_GRAPH_DP=1): measured
+        # on 2 x B200 (profiles/r03c_dp_graph_check.txt) the replayed step matches the eager one (DP CHECK OK) and runs at
+        # 3.16 instead of 3.47 ms, but dist.destroy_process_group() blocked while the captured graphs were alive -- call
+        # release_graphs() before tearing the process group down (that teardown order has not been re-run on a GPU yet).
+        self.use_graph_dp = os.environ.get("AESR_TRAIN_GRAPH_DP", "0") != "0"
         self._graphs = {}
         self._graph_seen = {}
         self._flatten()
@@ -230,7 +235,7 @@ class TrainEngine(TrainForward):
         graph's static outputs (valid until the next step -- the trainers read them right away)."""
         if lr is None and do_update:
             lr = self.opt.param_groups[0]["lr"]
-        if (self.use_graph and self.world == 1 and do_update and not keep and ops.TIMING is None
+        if (self.use_graph and (self.world == 1 or self.use_graph_dp) and do_update and not keep and ops.TIMING is None
                 and not torch.cuda.is_current_stream_capturing()):
             return self._step_graphed(image, slice_between, wa, wb, lpips, ex_loss_weight, combined, lr, betas, eps,
                                       weight_decay)
@@ -252,7 +257,8 @@ class TrainEngine(TrainForward):
                    "step": torch.zeros(1, dtype=torch.int32, device=self.dev)}
             torch.cuda.synchronize(self.dev)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # thread-local capture mode: the NCCL watchdog thread polls events while the step is being captured
+            with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.world > 1 else "global"):
                 ent["res"] = self._step_impl(ent["x"], ent["sb"], ent["wa"], ent["wb"], lpips, ex_loss_weight, combined,
                                              True, lr, betas, eps, weight_decay, False, step_dev=ent["step"])
             ent["graph"] = graph
@@ -266,6 +272,12 @@ class TrainEngine(TrainForward):
         ent["graph"].replay()
         self._after_update()
         return ent["res"]
+
+    def release_graphs(self) -> None:
+        """Drop every captured step graph (and its private memory pool)."""
+        torch.cuda.synchronize(self.dev)
+        self._graphs.clear()
+        self._graph_seen.clear()
 
     def _after_update(self):
         if self.opt is not None:

@@ -97,4 +97,33 @@ if rank == 0:
     # parameters: Adam's first steps are sign-like (|update| ~ lr whatever the gradient size), so fp32-atomic ordering
     # noise on near-zero gradients can flip an update: allow 2 * steps * lr.
     print("DP CHECK", "OK" if worst < 1e-3 and pdiff < 2.05 * steps * 1e-5 and rdiff < 1e-3 else "FAILED", flush=True)
+# ---------------------------------------------------------------- (c) timing of the data-parallel step, eager vs graph
+import time  # noqa: E402
+for label, dp_graph in (("eager", False), ("graph", True)):
+    m4 = model_from(st0, train=True)
+    e4 = TrainEngine(m4, None)
+    e4.use_graph_dp = dp_graph
+    if not dp_graph:
+        e4.use_graph = False
+    img, mid = acdc_batch(0)
+    x4, s4 = img.to(dev), mid.to(dev)
+    w = torch.full((12,), 0.5, device=dev)
+    for _ in range(4):
+        e4.step(x4, s4, w, w, lpips=lp, ex_loss_weight=0.05, lr=1e-5)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(30):
+        e4.step(x4, s4, w, w, lpips=lp, ex_loss_weight=0.05, lr=1e-5)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        ms = (time.perf_counter() - t0) / 30 * 1e3
+        print("DP x%d step (B = 12 per rank), %s: %.3f ms -> %.0f samples/s" % (world, label, ms, world * 12 / ms * 1e3), flush=True)
+    e4.release_graphs()
+    del e4, m4
+# graphs that contain NCCL kernels must be gone before the communicator is torn down (r03c: destroy_process_group blocked)
+e2.release_graphs()
+torch.cuda.synchronize()
+dist.barrier()
 dist.destroy_process_group()
