@@ -2,8 +2,9 @@
 
 Same flags (--exper_dir --model_nbr --num_interpolations --data_input_dir --output_dir --save), same functions
 (create_super_volume, latent_space_interp, normalize_img, sitk_to_torch); the arithmetic runs in the sm_100a kernels of
-superresolution_aniso_mri_b200.  Volume IO uses SimpleITK when it is installed (as the reference does); ``.npy`` volumes
-[z,y,x] are accepted as well so the path is usable where SimpleITK is absent.
+superresolution_aniso_mri_b200.  Volume IO uses SimpleITK when it is installed (as the reference does); where it is absent
+``.nii`` / ``.nii.gz`` / ``.mha`` / ``.mhd`` files go through the small reader / writer of
+``superresolution_aniso_mri_b200.volume_io`` (same spacing bookkeeping, :177-182), and ``.npy`` volumes [z,y,x] are accepted.
 """
 import argparse
 import os
@@ -12,6 +13,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
+from superresolution_aniso_mri_b200 import volume_io
 from superresolution_aniso_mri_b200.synthesis import create_super_volume, latent_space_interp  # noqa: F401
 
 try:                                    # IO only -- no arithmetic on the path
@@ -61,9 +63,9 @@ def load_images(input_dir: Path, suffix='.nii*'):
     for fname in file_list:
         if fname.suffix == ".npy":
             images.append((fname, np.load(str(fname))))
+        elif sitk is None:
+            images.append((fname, volume_io.read_volume(fname)))
         else:
-            if sitk is None:
-                raise ImportError("SimpleITK is required to read {}".format(fname))
             images.append((fname, sitk.ReadImage(str(fname))))
     return images
 
@@ -71,11 +73,20 @@ def load_images(input_dir: Path, suffix='.nii*'):
 def synthesize_image(trainer, image, num_interpolations):
     """Per-file body of the reference main() (generate_hr_volumes.py:159-183)."""
     alpha_range = np.linspace(0, 1, num_interpolations + 2, endpoint=True)[1:-1]
-    if isinstance(image, np.ndarray):
-        frames = [image] if image.ndim == 3 else [image[f] for f in range(image.shape[0])]
+    if isinstance(image, (np.ndarray, volume_io.Volume)):
+        arr = image if isinstance(image, np.ndarray) else image.array
+        frames = [arr] if arr.ndim == 3 else [arr[f] for f in range(arr.shape[0])]
         vols = [create_super_volume(trainer, array_to_torch(f), alpha_range, use_original=True)["upsampled_image"]
                 .numpy().squeeze() for f in frames]
-        return vols[0] if image.ndim == 3 else np.stack(vols)
+        np_img_hr = vols[0] if arr.ndim == 3 else np.stack(vols)
+        if isinstance(image, np.ndarray):
+            return np_img_hr
+        # generate_hr_volumes.py:177-180: z spacing / (ni + 1); a 4-D series keeps 1 as its last spacing
+        sp = image.GetSpacing()[:3]
+        new_spacing_z = (sp[-1] / (num_interpolations + 1),) if arr.ndim == 3 else (sp[-1] / (num_interpolations + 1), 1,)
+        new_spacing = np.asarray(sp[:2] + new_spacing_z).astype(np.float64)
+        return volume_io.Volume(array=np_img_hr, spacing=tuple(float(v) for v in new_spacing), origin=image.origin,
+                                direction=image.direction, fmt=image.fmt, header=image.header, byteorder=image.byteorder)
     num_frames = 1 if len(image.GetSize()) == 3 else image.GetSize()[-1]
     vols = []
     for f_id in range(num_frames):
@@ -89,6 +100,15 @@ def synthesize_image(trainer, image, num_interpolations):
     return numpy_to_sitk(np_img_hr, image, new_spacing=new_spacing)
 
 
+def _source_spacing(vol):
+    """Spacing recorded in the NIfTI header a Volume still carries (the file it was read from); its own otherwise."""
+    if vol.fmt == "nifti" and vol.header is not None:
+        nd = vol.array.ndim
+        pix = np.frombuffer(vol.header, np.dtype("f4").newbyteorder(vol.byteorder), 8, 76)
+        return tuple(float(abs(v)) for v in pix[1:nd + 1])
+    return vol.spacing
+
+
 def main(args, trainer, input_images, output_dir):
     images_hr = []
     for (fname, img) in input_images:
@@ -100,6 +120,11 @@ def save_images(images_hr):
     for (fname, img) in images_hr:
         if isinstance(img, np.ndarray):
             np.save(str(fname), img)
+        elif isinstance(img, volume_io.Volume):
+            # `img` carries the source header with the NEW spacing already in .spacing: rescale from the source's spacing
+            src = volume_io.Volume(array=img.array, spacing=_source_spacing(img), origin=img.origin, direction=img.direction,
+                                   fmt=img.fmt, header=img.header, byteorder=img.byteorder)
+            volume_io.write_volume(fname, img.array, like=src, spacing=img.spacing)
         else:
             sitk.WriteImage(img, str(fname))
         print("Save image HR {}".format(str(fname)))
