@@ -169,9 +169,15 @@ class HostPipeline:
     once at the end: the staging buffers and their events persist across calls, so the copies of batch i overlap the
     compute of batch i+1 and the only serial parts left are the first upload and the last download."""
 
-    def __init__(self, model, V, Z, H, W, alpha_range, groups: int = 2, chunk: int = 4096, host_kept: bool = True,
-                 d2h_streams: int = 2):
+    def __init__(self, model, V, Z, H, W, alpha_range, groups: int = 2, chunk: int = 4096,
+                 host_kept: Optional[bool] = None, d2h_streams: int = 2):
         self.model, self.ar, self.chunk = model, list(alpha_range), chunk
+        if host_kept is None:
+            # The host worker's clamp of the kept slices must stay well below the download time: 0.5 ms per 64-volume step
+            # with 16 intra-op threads, but 10 ms with one (torchrun exports OMP_NUM_THREADS=1 to every rank; the 2- and
+            # 4-GPU runs of profiles/r02l / r02z were bound by it).  With few threads the device writes the kept slices
+            # and whole volumes are downloaded, as before.
+            host_kept = torch.get_num_threads() >= 8
         self.host_kept = bool(host_kept) and len(self.ar) >= 1 and Z >= 2
         self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=1) if self.host_kept else None
         self.jobs = []
@@ -187,7 +193,7 @@ class HostPipeline:
         self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         # download streams: each group's volumes are split between them (two copy engines in flight: 5.03 vs 5.13-5.30 ms
         # per step, profiles/r02x_d2h_streams.txt; a third changes nothing)
-        self.s_out_extra = [torch.cuda.Stream(dev) for _ in range(max(0, int(d2h_streams) - 1))] if host_kept else []
+        self.s_out_extra = [torch.cuda.Stream(dev) for _ in range(max(0, int(d2h_streams) - 1))] if self.host_kept else []
         self.in_free = [torch.cuda.Event() for _ in range(2)]     # compute finished reading d_in[b]
         self.out_free = [torch.cuda.Event() for _ in range(2)]    # copy-out finished reading d_out[b]
         # bytes crossing PCIe per run() (what bench.py reports): all inputs up, synthesized (or all) slices down
