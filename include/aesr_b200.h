@@ -87,10 +87,12 @@ int aesr_pack_conv3x3_weight(const float* w, void* packed, int Cout, int Cin, in
  *   x        NHWC 16-bit [N,H,W,Cin],  Cin  in {32,64,128,256,512}
  *   w_packed 16-bit [9][Cout][Cin],    Cout multiple of 32
  *   y = act(conv(x) + bias) [* act'(mul_src)] ; stats += {sum y, sum y^2} per channel ; y = y*scale + shift ; out stage
- *   bias/scale/shift/out2/mul_src/stats may be NULL. */
+ *   bias/scale/shift/out2/mul_src/stats may be NULL.  stats: fp32 [2*Cout], or [2][2*Cout] with 0 < stats_split < N:
+ *   images >= stats_split (the second pass of a merged batch, see "Merged batches" below) accumulate into the second
+ *   block. */
 int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, const float* scale, const float* shift,
                      void* out, void* out2, const void* mul_src, float* stats, int N, int H, int W, int Cin, int Cout,
-                     int act, float slope, int out_mode, int mul_mode, int dtype, int algo, void* stream);
+                     int act, float slope, int out_mode, int mul_mode, int dtype, int algo, int stats_split, void* stream);
 
 /* Folded filter bank for AESR_OUT_SHUFFLE2: fp32 [Cout,Cin,3,3] -> 16-bit [9 low-res taps][4 phases][Cout][Cin],
  * phase 2a+b = hi-res pixel (2y+a, 2x+b); each entry is the sum of the original taps that read the same low-res
@@ -177,23 +179,33 @@ int aesr_copy_rows_async(void* dst, size_t dst_outer_stride, size_t dpitch, cons
  * ALWAYS bf16 NHWC (fp32 range); activations are `dtype`; reductions, parameters and optimizer state are fp32.
  * ------------------------------------------------------------------------------------------------------------------ */
 
-/* nn.BatchNorm2d in train mode (networks/acai_vanilla.py:58,90).  stats[c] = sum a, stats[C+c] = sum a^2 over `count`
- * positions (accumulated by aesr_conv3x3_fwd's epilogue).  Writes this pass' scale/shift (gamma/sqrt(var+eps), ...),
- * mean, invstd, and updates running_mean/var (momentum, unbiased variance); running_* may be NULL. */
-int aesr_bn_finalize(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
-                     float* running_var, float momentum, float eps, float* scale, float* shift, float* mean_out,
-                     float* invstd_out, int C, void* stream);
-/* out = mode(a * scale + shift), mode 0 same / 1 AvgPool2d(2) / 2 Upsample(2) nearest; a, out NHWC `dtype`. */
+/* Merged batches.  One training step runs the SAME modules on two batches with separate BatchNorm statistics: enc(x) and
+ * enc(slice_between), dec(z) and dec(z_mix) (kwatsch/cardiac/trainer_ae.py:18-26,165-182).  Convolutions do not care, so the
+ * two batches are concatenated (images [0, split) = first pass, [split, N) = second pass) and every conv launches once;
+ * the BatchNorm entry points below take `split` and keep per-pass statistics ([2][...] arrays), i.e. the results are those
+ * of two module calls in that order.  split <= 0 or >= N: a single pass. */
+
+/* nn.BatchNorm2d in train mode (networks/acai_vanilla.py:58,90).  Per pass p: stats[p][c] = sum a, stats[p][C+c] = sum a^2
+ * over count / count1 positions (accumulated by aesr_conv3x3_fwd's epilogue, `stats_split`).  Writes every pass'
+ * scale/shift (gamma/sqrt(var+eps), ...), mean, invstd ([passes][C] each), and updates running_mean/var (momentum,
+ * unbiased variance) once per pass in order; running_* may be NULL. */
+int aesr_bn_finalize(const float* stats, float count, float count1, int passes, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                     float* mean_out, float* invstd_out, int C, void* stream);
+/* out = mode(a * scale + shift), mode 0 same / 1 AvgPool2d(2) / 2 Upsample(2) nearest; a, out NHWC `dtype`; images >= split
+ * use scale[C..2C) / shift[C..2C). */
 int aesr_bn_apply(const void* a, const float* scale, const float* shift, void* out, int N, int H, int W, int C, int mode,
-                  int dtype, void* stream);
+                  int dtype, int split, void* stream);
 /* Backward of [LeakyReLU ->] BatchNorm(train) -> pool/upsample: dnext bf16 (gradient of the pooled / upsampled tensor),
  * a = saved post-activation input of the BN; g_out bf16 [N,H,W,C] = gradient w.r.t. the producing conv's
- * pre-activation output; dgamma / dbeta accumulated; sums = 2*C floats of scratch.
- * phase 0 = reduce + apply; 1 = reduce only (sums[c] = sum dy, sums[C+c] = sum dy*xhat); 2 = apply only -- a data-parallel
- * caller all-reduces `sums` between 1 and 2 and passes the GLOBAL element count (`count` <= 0: local N*H*W). */
+ * pre-activation output; dgamma / dbeta accumulated (over both passes); sums = passes*2*C floats of scratch;
+ * mean / invstd [passes][C].
+ * phase 0 = reduce + apply; 1 = reduce only (sums[p][c] = sum dy, sums[p][C+c] = sum dy*xhat); 2 = apply only -- a
+ * data-parallel caller all-reduces `sums` between 1 and 2 and passes the GLOBAL element counts (`count` / `count1` <= 0:
+ * the local ones). */
 int aesr_bn_bwd(const void* dnext, const void* a, const float* mean, const float* invstd, const float* gamma,
                 float* sums, float slope, void* g_out, float* dgamma, float* dbeta, int N, int H, int W, int C, int mode,
-                int dtype, int phase, float count, void* stream);
+                int dtype, int phase, float count, float count1, int split, void* stream);
 /* F.mse_loss(a, b) (kwatsch/base_trainer.py:177): *loss_acc += mean((a-b)^2); d (optional) = grad_scale * 2 (a-b)/n. */
 int aesr_mse(const float* a, const float* b, size_t n, float* loss_acc, float* d, float grad_scale, void* stream);
 /* Backward of dec.14 + Sigmoid: g_in bf16 (includes LeakyReLU'(a_in)), dw9c[9*C] and dbias accumulated. */
@@ -212,10 +224,12 @@ int aesr_mix_bwd(const void* g_dec, const void* g_mix, const float* wa, const fl
 /* torch.optim.Adam step over flat fp32 buffers (kwatsch/trainer_ae.py:29-30); `step` is the 1-based step count. */
 int aesr_adam_step(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int step, void* stream);
-/* Same step with the 1-based step count read from device memory (the bias corrections are formed in the kernel): the launch
- * carries no per-step host value, so a training step captured in a CUDA graph can be replayed. */
+/* Same step with the 1-based step count read from device memory (the bias corrections are formed in the kernel) and,
+ * when `lr_dev` is not NULL, the learning rate read from device memory too (`lr` is then ignored): the launch carries no
+ * per-step host value, so a training step captured in a CUDA graph can be replayed under a per-iteration scheduler
+ * (CosineAnnealingLR, kwatsch/base_trainer.py:18-22). */
 int aesr_adam_step_dev(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
-                       float weight_decay, const int* step_dev, void* stream);
+                       float weight_decay, const int* step_dev, const float* lr_dev, void* stream);
 
 /* LPIPS-VGG v0.1 (lpips/perceptual.py:19-33, lpips/networks_basic.py:63-110, lpips/pretrained_networks.py:97-135). */
 /* conv1_1 with the input pipeline folded in: (2*img-1 if normalize), ScalingLayer 1->3 channels, conv 3->64, ReLU.

@@ -132,6 +132,21 @@ def _run(spec, prefix, state, x, train: bool, bn_updates: Optional[dict], moment
     return x
 
 
+def run_trace(spec, prefix, state, x: torch.Tensor) -> List[Tuple[str, torch.Tensor, torch.Tensor]]:
+    """Eval-mode pass that records, for every conv of ``spec``, (state key prefix, conv INPUT, conv OUTPUT after its
+    activation and the BatchNorm / pool / upsample entries that follow it up to the next conv) -- the per-layer error
+    ledger of tests/test_gpu_parity.py feeds each of our fused layers the oracle's input and compares the outputs."""
+    out, cur_in, cur_key = [], None, None
+    for ent in spec:
+        if ent[0] == "conv":
+            if cur_key is not None:
+                out.append((cur_key, cur_in, x))
+            cur_key, cur_in = "%s.%d" % (prefix, ent[1]), x
+        x = _run([ent], prefix, state, x, False, None)
+    out.append((cur_key, cur_in, x))
+    return out
+
+
 def encode(state, args, x: torch.Tensor, train: bool = False) -> torch.Tensor:
     """VanillaACAI.encode, networks/acai_vanilla.py:134-135.  ``train=True`` mutates BN running stats in ``state``."""
     scales = num_scales(args["width"], args["latent_width"])
@@ -778,6 +793,17 @@ def smooth_phantom(num_slices: int, size: int, seed: int = 2, sigma: float = 6.0
         slices.append(prev)
     v = torch.cat(slices, dim=0)
     return (v - v.min()) / (v.max() - v.min())
+
+
+def mri_phantom(num_slices: int, size: int, seed: int = 2, sigma: float = 5.0, noise: float = 0.02) -> torch.Tensor:
+    """MRI-like phantom [Z,1,size,size]: soft-thresholded smooth noise (bright blobs with edges on a black background,
+    adjacent slices correlated) + a little pixel noise -- the training / test images of the reference-trained checkpoint
+    (oracle/make_golden.py::gold_trained)."""
+    v = smooth_phantom(num_slices, size, seed=seed, sigma=sigma)
+    g = torch.Generator().manual_seed(seed + 7919)
+    fine = smooth_phantom(num_slices, size, seed=seed + 1, sigma=1.5)
+    img = ((v - 0.38) * 2.6).clamp(0, 1) * (0.75 + 0.25 * fine)
+    return (img + noise * torch.rand(img.shape, generator=g)).clamp(0, 1)
 
 
 def default_args(width=128, latent_width=32, latent=128, depth=32) -> dict:

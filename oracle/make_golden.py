@@ -213,6 +213,62 @@ def gold_train_acdc(steps=200):
     _save("train_acdc_%d.npz" % steps, **out)
 
 
+def trained_batch(i: int, B: int = 8, size: int = 64):
+    """Seeded MRI-like triplets for the reference-trained checkpoint: sample b = slices (3b, 3b+1, 3b+2) of a phantom."""
+    v = O.mri_phantom(3 * B, size, seed=5000 + i)
+    return torch.cat([v[0::3], v[2::3]], dim=0), v[1::3].clone()
+
+
+def gold_trained(steps=400):
+    """A checkpoint TRAINED BY THE REFERENCE (AETrainerEndToEnd.train, lr 1e-3, MSE + 0.05 LPIPS on MRI-like phantoms) so that
+    BatchNorm running statistics, gamma / beta and the filters are those of a model that reconstructs images -- and the
+    reference's own synthesis outputs for it at BASELINE configs 1 (ACDC 128^2, ni 6), 3 (OASIS 220^2, ds 4) and
+    4 / published (dHCP 256^2, ds 4 and 6).  All three share the scales=2 architecture (fully convolutional)."""
+    torch.set_num_threads(os.cpu_count())
+    args = rb.reference_args(width=64, latent_width=16, batch_size=8, ex_loss_weight1=0.05, lr=1e-3)
+    tr = rb.make_reference_trainer(dict(args), trainer="cardiac")
+    t0 = time.time()
+    for s in range(steps):
+        img, mid = trained_batch(s)
+        tr.train({"image": img, "slice_between": mid}, keep_predictions=False)
+        if s % 20 == 0:
+            print(s, tr.losses["loss_ae"][-1], tr.losses["loss_ae_dist"][-1], "%.1fs" % (time.time() - t0), flush=True)
+    sd = {k: v.detach().clone() for k, v in tr.model.state_dict().items()}
+    out = {"state__" + k: v.numpy() for k, v in sd.items()}
+    out["train_loss_ae"] = np.array(tr.losses["loss_ae"])
+    out["train_loss_ae_dist"] = np.array(tr.losses["loss_ae_dist"])
+    ghv = rb.reference_generate_module()
+    ec = rb.reference_eval_common_module()
+    oargs = O.default_args(64, 16)
+    m = _ref_model(oargs, sd)
+    # config 1: ACDC-shaped volume through generate_hr_volumes.create_super_volume
+    vol = O.mri_phantom(10, 128, seed=41)
+    for ni in (6, 2):
+        ar = O.alpha_range_for(ni)
+        hr = ghv.create_super_volume(rb.CpuEvalTrainer(m), vol, ar, use_original=True)["upsampled_image"]
+        assert torch.equal(hr, O.create_super_volume(sd, oargs, vol, ar, use_original=True))
+        out["acdc128_ni%d_sub" % ni] = hr[:, ::4, ::4].numpy()
+        out["acdc128_ni%d_slice_sum" % ni] = hr.double().sum(dim=(1, 2)).numpy()
+    with torch.no_grad():
+        rec = m(vol)
+    out["acdc128_recon_mse"] = np.array(torch.mean((rec - vol) ** 2).item())
+    print("reconstruction MSE of the trained model on a held-out phantom: %.5f" % out["acdc128_recon_mse"])
+    # configs 3 / 4 / published: the evaluation twin (slice dropping) at 220^2 and 256^2
+    for tag, size, Z, ds in (("oasis220_ds4", 220, 9, 4), ("dhcp256_ds4", 256, 9, 4), ("dhcp256_ds6", 256, 13, 6)):
+        v3 = O.mri_phantom(Z, size, seed=43 + ds)[:, 0]
+        with rb.cuda_to_cpu():
+            hr = ec.create_super_volume(rb.CpuEvalTrainer(m), v3, alpha_range=O.alpha_range_for(ds - 1), use_original=False,
+                                        downsample_steps=ds, generate_inbetween_slices=True)["upsampled_image"]
+        mine = O.create_super_volume_eval(sd, oargs, v3, O.alpha_range_for(ds - 1), use_original=False, downsample_steps=ds,
+                                          generate_inbetween_slices=True)
+        assert hr.shape == mine.shape and torch.equal(hr, mine), (tag, hr.shape, mine.shape)
+        out[tag + "_sub"] = hr[:, ::5, ::5].numpy()
+        out[tag + "_slice_sum"] = hr.double().sum(dim=(1, 2)).numpy()
+        print(tag, tuple(hr.shape), "synth-vs-truth mean abs %.4f" % (hr - v3[: hr.shape[0]]).abs().mean().item())
+    out["steps"], out["sec_per_step"] = np.array(steps), np.array((time.time() - t0) / steps)
+    _save("trained_ckpt.npz", **out)
+
+
 def gold_transforms():
     rb.bootstrap()
     import datasets.shared_transforms as stf
@@ -447,7 +503,7 @@ def _sig(cls):
 
 
 ALL = {"init": gold_init, "lpips": gold_lpips_lin, "infer": gold_infer, "train_small": gold_train_small,
-       "transforms": gold_transforms, "augment": gold_augment, "thick": gold_thick_slices, "sampling": gold_sampling, "vif": gold_vif, "train_acdc": gold_train_acdc}
+       "transforms": gold_transforms, "augment": gold_augment, "thick": gold_thick_slices, "sampling": gold_sampling, "vif": gold_vif, "train_acdc": gold_train_acdc, "trained": gold_trained}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -460,7 +516,7 @@ if __name__ == "__main__":
     for name, fn in ALL.items():
         if a.only is not None and name not in a.only:
             continue
-        if name == "train_acdc" and (a.only is None or "train_acdc" not in a.only):
-            continue                    # 200 CPU steps ~ 7 min: only on request
+        if name in ("train_acdc", "trained") and (a.only is None or name not in a.only):
+            continue                    # hundreds of CPU train steps (minutes): only on request
         print("== %s" % name, flush=True)
         fn(a.steps) if name == "train_acdc" else fn()

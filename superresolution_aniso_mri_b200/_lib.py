@@ -24,7 +24,7 @@ _SIGNATURES = {
     "aesr_set_tuning": (I, [I, I]),
     "aesr_launch_count": (c_int64, []),
     "aesr_pack_conv3x3_weight": (I, [P, P, I, I, I, I, P]),
-    "aesr_conv3x3_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, F, I, I, I, I, P]),
+    "aesr_conv3x3_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, F, I, I, I, I, I, P]),
     "aesr_pack_conv3x3_weight_up2fold": (I, [P, P, I, I, I, P]),
     "aesr_conv3x3_up2_head_fwd": (I, [P, P, P, P, P, P, I, I, I, I, I, F, I, I, P]),
     "aesr_head_gather": (I, [P, P, P, P, I, I, I, c_size_t, I, P]),
@@ -42,16 +42,16 @@ _SIGNATURES = {
     "aesr_probe_umma_pattern": (I, [P, I, I, I, I, I, I, I, I, P]),
     "aesr_probe_sync": (I, [P, I, I, P]),
     # training step
-    "aesr_bn_finalize": (I, [P, F, P, P, P, P, F, F, P, P, P, P, I, P]),
-    "aesr_bn_apply": (I, [P, P, P, P, I, I, I, I, I, I, P]),
-    "aesr_bn_bwd": (I, [P, P, P, P, P, P, F, P, P, P, I, I, I, I, I, I, I, F, P]),
+    "aesr_bn_finalize": (I, [P, F, F, I, P, P, P, P, F, F, P, P, P, P, I, P]),
+    "aesr_bn_apply": (I, [P, P, P, P, I, I, I, I, I, I, I, P]),
+    "aesr_bn_bwd": (I, [P, P, P, P, P, P, F, P, P, P, I, I, I, I, I, I, I, F, F, I, P]),
     "aesr_mse": (I, [P, P, c_size_t, P, P, F, P]),
     "aesr_head_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
     "aesr_e0_bwd": (I, [P, P, P, P, I, I, I, I, P]),
     "aesr_wgrad3x3": (I, [P, P, P, P, I, I, I, I, I, I, I, P]),
     "aesr_mix_bwd": (I, [P, P, P, P, P, I, c_size_t, P]),
     "aesr_adam_step": (I, [P, P, P, P, c_size_t, F, F, F, F, F, I, P]),
-    "aesr_adam_step_dev": (I, [P, P, P, P, c_size_t, F, F, F, F, F, P, P]),
+    "aesr_adam_step_dev": (I, [P, P, P, P, c_size_t, F, F, F, F, F, P, P, P]),
     "aesr_vgg_conv1_fwd": (I, [P, P, P, P, I, I, I, P, P, I, I, P]),
     "aesr_vgg_conv1_bwd": (I, [P, P, P, I, I, I, P, I, F, P]),
     "aesr_maxpool_bwd": (I, [P, P, P, P, I, I, I, I, I, P]),

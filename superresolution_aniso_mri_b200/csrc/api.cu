@@ -359,7 +359,7 @@ int conv3x3_dispatch(const void* x, const void* w_packed, const float* bias, con
                      void* out, void* out2, const void* mul_src, float* stats, const float* head_w, const void* head_w16,
                      int N, int H, int W,
                      int Cin, int Cout, int act, float slope, int out_mode, int mul_mode, int dtype, int algo,
-                     void* stream) {
+                     void* stream, int stats_split = 0) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!x || !w_packed || !out) return fail(AESR_ERR_INVALID, "conv3x3_fwd: null tensor");
@@ -397,6 +397,8 @@ int conv3x3_dispatch(const void* x, const void* w_packed, const float* bias, con
     p.bias = bias; p.scale = scale; p.shift = shift; p.slope = slope; p.act = act; p.out_mode = out_mode;
     p.out = out; p.out2 = out2; p.mul_src = static_cast<const uint16_t*>(mul_src); p.mul_mode = mul_mode;
     p.stats = stats;
+    p.stats_split = (stats_split > 0 && stats_split < N) ? stats_split : N;
+    if (stats && Cout > 256) return fail(AESR_ERR_INVALID, "conv3x3_fwd: statistics need Cout <= 256, got %d", Cout);
     if (head_w) memcpy(p.head_wc, head_w, sizeof(p.head_wc));      // HOST pointer: travels as a kernel parameter
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -420,10 +422,10 @@ extern "C" {
 
 int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, const float* scale, const float* shift,
                      void* out, void* out2, const void* mul_src, float* stats, int N, int H, int W, int Cin, int Cout,
-                     int act, float slope, int out_mode, int mul_mode, int dtype, int algo, void* stream) {
+                     int act, float slope, int out_mode, int mul_mode, int dtype, int algo, int stats_split, void* stream) {
     if (out_mode == OUT_SHUFFLE2_HEAD) return fail(AESR_ERR_INVALID, "conv3x3_fwd: use aesr_conv3x3_up2_head_fwd");
     return conv3x3_dispatch(x, w_packed, bias, scale, shift, out, out2, mul_src, stats, nullptr, nullptr, N, H, W, Cin, Cout,
-                            act, slope, out_mode, mul_mode, dtype, algo, stream);
+                            act, slope, out_mode, mul_mode, dtype, algo, stream, stats_split);
 }
 
 int aesr_conv3x3_up2_head_fwd(const void* x, const void* w_folded, const float* bias, const float* head_w9c_host,

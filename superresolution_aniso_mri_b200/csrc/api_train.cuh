@@ -13,67 +13,76 @@ inline int grid_for(size_t total, int block, int per_sm = 8) {
 
 extern "C" {
 
-int aesr_bn_finalize(const float* stats, float count, const float* gamma, const float* beta, float* running_mean,
-                     float* running_var, float momentum, float eps, float* scale, float* shift, float* mean_out,
-                     float* invstd_out, int C, void* stream) {
+int aesr_bn_finalize(const float* stats, float count, float count1, int passes, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                     float* mean_out, float* invstd_out, int C, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
-    if (!stats || !gamma || !beta || !scale || !shift || !mean_out || !invstd_out || C <= 0 || count <= 0)
+    if (!stats || !gamma || !beta || !scale || !shift || !mean_out || !invstd_out || C <= 0 || count <= 0 || passes < 1 ||
+        passes > 2 || (passes == 2 && count1 <= 0))
         return fail(AESR_ERR_INVALID, "bn_finalize: bad arguments");
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        stats, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, mean_out, invstd_out, C);
+        stats, count, count1, passes, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, mean_out,
+        invstd_out, C);
     return check_launch("bn_finalize");
 }
 
 int aesr_bn_apply(const void* a, const float* scale, const float* shift, void* out, int N, int H, int W, int C, int mode,
-                  int dtype, void* stream) {
+                  int dtype, int split, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!a || !scale || !shift || !out || C % 8 != 0 || mode < 0 || mode > 2) return fail(AESR_ERR_INVALID, "bn_apply: bad arguments");
+    if (split <= 0 || split > N) split = N;
     const int Ho = mode == BN_POOL ? H / 2 : mode == BN_UP ? 2 * H : H, Wo = mode == BN_POOL ? W / 2 : mode == BN_UP ? 2 * W : W;
     const size_t total = static_cast<size_t>(N) * Ho * Wo * (C / 8);
     if (total == 0) return AESR_OK;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (dtype == AESR_DT_FP16)
-        bn_apply_kernel<true><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(a), scale, shift, static_cast<uint16_t*>(out), N, H, W, C, mode);
+        bn_apply_kernel<true><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(a), scale, shift, static_cast<uint16_t*>(out), N, H, W, C, mode, split);
     else
-        bn_apply_kernel<false><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(a), scale, shift, static_cast<uint16_t*>(out), N, H, W, C, mode);
+        bn_apply_kernel<false><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(a), scale, shift, static_cast<uint16_t*>(out), N, H, W, C, mode, split);
     return check_launch("bn_apply");
 }
 
 int aesr_bn_bwd(const void* dnext, const void* a, const float* mean, const float* invstd, const float* gamma,
                 float* sums, float slope, void* g_out, float* dgamma, float* dbeta, int N, int H, int W, int C, int mode,
-                int dtype, int phase, float count, void* stream) {
+                int dtype, int phase, float count, float count1, int split, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!dnext || !a || !mean || !invstd || !gamma || !sums || !g_out || !dgamma || !dbeta || C % 32 != 0 || mode < 0 || mode > 2)
         return fail(AESR_ERR_INVALID, "bn_bwd: bad arguments");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (split <= 0 || split > N) split = N;
+    const int passes = split < N ? 2 : 1;                            // merged batch: images [0, split) and [split, N)
     const size_t npix = static_cast<size_t>(N) * H * W;
     const bool do_reduce = phase != 2, do_apply = phase != 1;
-    if (do_reduce) CUDA_TRY(cudaMemsetAsync(sums, 0, 2 * C * sizeof(float), s));
+    if (do_reduce) CUDA_TRY(cudaMemsetAsync(sums, 0, static_cast<size_t>(passes) * 2 * C * sizeof(float), s));
     if (C > 512) return fail(AESR_ERR_INVALID, "bn_bwd: C=%d > 512", C);
     const int groups = C / 8;
     const int rows = 256 / groups;                                   // pixel rows per block (C = 32: 64 ... C = 512: 4)
-    int gx = static_cast<int>((npix + static_cast<size_t>(rows) * 4 - 1) / (static_cast<size_t>(rows) * 4));
-    if (gx > g_sm_count * 8) gx = g_sm_count * 8;
+    const size_t npix_pass = passes == 2 ? static_cast<size_t>(split > N - split ? split : N - split) * H * W : npix;
+    int gx = static_cast<int>((npix_pass + static_cast<size_t>(rows) * 4 - 1) / (static_cast<size_t>(rows) * 4));
+    const int gx_cap = g_sm_count * 8 / passes;
+    if (gx > gx_cap) gx = gx_cap;
     if (gx < 1) gx = 1;
+    const dim3 rgrid(gx, passes);
     const int block = rows * groups;
     const size_t red_smem = static_cast<size_t>(rows) * 2 * C * sizeof(float);      // <= 32 KB
     const size_t total = npix * groups;
-    if (count <= 0.f) count = static_cast<float>(npix);       // global-batch count in SyncBN mode
+    if (count <= 0.f) count = static_cast<float>(static_cast<size_t>(split) * H * W);       // global-batch counts in SyncBN mode
+    if (count1 <= 0.f) count1 = static_cast<float>(static_cast<size_t>(N - split) * H * W);
     // phase 0: the apply kernel banks dgamma / dbeta from the (local) sums; phase 1 banks them right after the local
     // reduce; phase 2 (sums all-reduced by the caller) must not bank them again.
     float* dg_apply = phase == 0 ? dgamma : nullptr;
     float* db_apply = phase == 0 ? dbeta : nullptr;
     if (dtype == AESR_DT_FP16) {
-        if (do_reduce) bn_bwd_reduce_kernel<true><<<gx, block, red_smem, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode);
-        if (do_apply) bn_bwd_apply_kernel<true><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, slope, static_cast<uint16_t*>(g_out), dg_apply, db_apply, N, H, W, C, mode);
+        if (do_reduce) bn_bwd_reduce_kernel<true><<<rgrid, block, red_smem, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode, split);
+        if (do_apply) bn_bwd_apply_kernel<true><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, count1, split, slope, static_cast<uint16_t*>(g_out), dg_apply, db_apply, N, H, W, C, mode);
     } else {
-        if (do_reduce) bn_bwd_reduce_kernel<false><<<gx, block, red_smem, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode);
-        if (do_apply) bn_bwd_apply_kernel<false><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, slope, static_cast<uint16_t*>(g_out), dg_apply, db_apply, N, H, W, C, mode);
+        if (do_reduce) bn_bwd_reduce_kernel<false><<<rgrid, block, red_smem, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode, split);
+        if (do_apply) bn_bwd_apply_kernel<false><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, count1, split, slope, static_cast<uint16_t*>(g_out), dg_apply, db_apply, N, H, W, C, mode);
     }
-    if (phase == 1) bn_bwd_accum_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, dgamma, dbeta, C);
+    if (phase == 1) bn_bwd_accum_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, dgamma, dbeta, C, passes);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return check_launch("bn_bwd");
 }
@@ -205,16 +214,16 @@ int aesr_adam_step(float* p, const float* g, float* m, float* v, size_t n, float
     if (!p || !g || !m || !v || n == 0 || step < 1) return fail(AESR_ERR_INVALID, "adam_step: bad arguments");
     const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
     const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
-    adam_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), nullptr);
+    adam_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), nullptr, nullptr);
     return check_launch("adam_step");
 }
 
 int aesr_adam_step_dev(float* p, const float* g, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
-                       float weight_decay, const int* step_dev, void* stream) {
+                       float weight_decay, const int* step_dev, const float* lr_dev, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!p || !g || !m || !v || n == 0 || !step_dev) return fail(AESR_ERR_INVALID, "adam_step_dev: bad arguments");
-    adam_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, step_dev);
+    adam_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, step_dev, lr_dev);
     return check_launch("adam_step_dev");
 }
 

@@ -83,8 +83,10 @@ struct ConvParams {
     // optional elementwise multiplier (dgrad): out *= act'(mul_src) with mul_src NHWC 16-bit [N,H,W,Cout]
     const uint16_t* mul_src;
     int mul_mode;
-    // optional per-channel statistics of the (post-activation, pre-affine) value: stats[c] += sum, stats[Cout+c] += sum^2
+    // optional per-channel statistics of the (post-activation, pre-affine) value: stats[c] += sum, stats[Cout+c] += sum^2;
+    // images >= stats_split (second pass of a merged batch, own BatchNorm statistics) accumulate into stats + 2*Cout
     float* stats;
+    int stats_split;
     // OUT_SHUFFLE2_HEAD: fp32 [9][32] filter of the 32 -> 1 head conv, BY VALUE: kernel parameters live in the constant
     // bank, so the 1152 head MACs per thread read their weights as instruction operands (c[0][..]) instead of through
     // 288 LDS.128 per thread and tile, which made the epilogue shared-memory-bandwidth-bound (191 -> see profiles/).
@@ -104,6 +106,7 @@ __host__ __device__ constexpr int conv_num_acc(int BN) { return (CONV_EPI_SETS *
 constexpr int HALO_H = CONV_TILE_H + 2;     // 18
 constexpr int HALO_W = CONV_TILE_W + 2;     // 10
 constexpr int CONV_TAIL_BYTES = 256 + 5 * 512 * 4;   // barriers + tmem ptr + per-channel epilogue constants + BN statistics
+                                                     // (s_stats: [2 passes][2][Cout], Cout <= 256 when statistics are taken)
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi, int fp16) {
     if (fp16) {
@@ -176,7 +179,7 @@ __device__ __forceinline__ uint32_t conv_prologue(const ConvParams& p, const Con
         bars.s_shift[c] = p.shift ? p.shift[cc] : 0.f;
     }
     if (p.stats != nullptr)
-        for (int c = threadIdx.x; c < 2 * p.Cout; c += CONV_THREADS) bars.s_stats[c] = 0.f;
+        for (int c = threadIdx.x; c < 4 * p.Cout; c += CONV_THREADS) bars.s_stats[c] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -190,7 +193,7 @@ __device__ __forceinline__ void conv_teardown(const ConvParams& p, const ConvBar
     tc_fence_before();
     __syncthreads();
     if (WITH_STATS && p.stats != nullptr)        // every epilogue of this CTA has added its sums: flush them
-        for (int c = threadIdx.x; c < 2 * p.Cout; c += CONV_THREADS) {
+        for (int c = threadIdx.x; c < (p.stats_split < p.N ? 4 : 2) * p.Cout; c += CONV_THREADS) {
             const float v = bars.s_stats[c];
             if (v != 0.f) atomicAdd(p.stats + c, v);
         }
@@ -325,8 +328,9 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                 // shared-memory accumulators: one global atomic per channel and CTA at the end of the kernel instead of one
                 // per warp and 16-channel chunk (940 k atomics onto 64 addresses made enc.3's forward 95 us against 36 us
                 // without statistics, tools/train_layer_times.py)
-                atomicAdd(bars.s_stats + cg + ch, t1);
-                atomicAdd(bars.s_stats + Cout + cg + ch, t2);
+                float* sst = bars.s_stats + (n >= p.stats_split ? 2 * Cout : 0);      // pass of a merged batch (tile-uniform)
+                atomicAdd(sst + cg + ch, t1);
+                atomicAdd(sst + Cout + cg + ch, t2);
             }
         }
         if (p.scale != nullptr) {

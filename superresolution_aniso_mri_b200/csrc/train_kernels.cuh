@@ -31,26 +31,34 @@ __device__ __forceinline__ float a16_to_f(uint16_t u) {
 //   scale = gamma / sqrt(var_biased + eps), shift = beta - mean * scale          (normalisation of this pass)
 //   running_mean = (1-m) rm + m mean ; running_var = (1-m) rv + m var * count/(count-1)   (torch semantics)
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ stats, float count, const float* __restrict__ gamma,
+// `groups` (1 or 2) consecutive passes of the SAME BatchNorm module computed by one conv launch (images [0, split) and
+// [split, N) of a merged batch, e.g. enc(x) and enc(slice_between) of one training step): stats / outputs are
+// [groups][...]; the running statistics are updated once per group IN ORDER, exactly like two module calls.
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, float count0, float count1, int groups,
+                                   const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float momentum, float eps,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const double mean = static_cast<double>(stats[c]) / count;
-    double var = static_cast<double>(stats[C + c]) / count - mean * mean;
-    if (var < 0) var = 0;
-    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-    const float sc = gamma[c] * invstd;
-    scale[c] = sc;
-    shift[c] = beta[c] - static_cast<float>(mean) * sc;
-    mean_out[c] = static_cast<float>(mean);
-    invstd_out[c] = invstd;
-    if (running_mean != nullptr) {
-        const double unbiased = count > 1.f ? var * count / (count - 1.0) : var;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    for (int g = 0; g < groups; ++g) {
+        const float count = g == 0 ? count0 : count1;
+        const float* st = stats + static_cast<size_t>(g) * 2 * C;
+        const double mean = static_cast<double>(st[c]) / count;
+        double var = static_cast<double>(st[C + c]) / count - mean * mean;
+        if (var < 0) var = 0;
+        const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        const float sc = gamma[c] * invstd;
+        scale[g * C + c] = sc;
+        shift[g * C + c] = beta[c] - static_cast<float>(mean) * sc;
+        mean_out[g * C + c] = static_cast<float>(mean);
+        invstd_out[g * C + c] = invstd;
+        if (running_mean != nullptr) {
+            const double unbiased = count > 1.f ? var * count / (count - 1.0) : var;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+        }
     }
 }
 
@@ -58,7 +66,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, float count,
 template <bool AF>
 __global__ void bn_apply_kernel(const uint16_t* __restrict__ a, const float* __restrict__ scale,
                                 const float* __restrict__ shift, uint16_t* __restrict__ out, int N, int H, int W, int C,
-                                int mode) {
+                                int mode, int split) {
+    // images >= split belong to the second pass of a merged batch: scale / shift are [2][C]
     const int Ho = mode == BN_POOL ? H / 2 : mode == BN_UP ? 2 * H : H;
     const int Wo = mode == BN_POOL ? W / 2 : mode == BN_UP ? 2 * W : W;
     const int groups = C >> 3;
@@ -84,8 +93,9 @@ __global__ void bn_apply_kernel(const uint16_t* __restrict__ a, const float* __r
             }
         }
         const float inv = mode == BN_POOL ? 0.25f : 1.f;
+        const int go = (n >= split ? C : 0) + g * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j] * inv, __ldg(scale + g * 8 + j), __ldg(shift + g * 8 + j));
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j] * inv, __ldg(scale + go + j), __ldg(shift + go + j));
         reinterpret_cast<uint4*>(out)[i] = make_uint4(pack2_t<AF>(v[0], v[1]), pack2_t<AF>(v[2], v[3]),
                                                       pack2_t<AF>(v[4], v[5]), pack2_t<AF>(v[6], v[7]));
     }
@@ -151,11 +161,17 @@ __device__ __forceinline__ void bn_dy8_at(const uint16_t* __restrict__ dnext, in
 template <bool AF>
 __global__ void bn_bwd_reduce_kernel(const uint16_t* __restrict__ dnext, const uint16_t* __restrict__ a,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
-                                     float* __restrict__ sums, int N, int H, int W, int C, int mode) {
+                                     float* __restrict__ sums, int N, int H, int W, int C, int mode, int split) {
+    // blockIdx.y = pass of a merged batch: images [0, split) or [split, N); mean / invstd are [2][C], sums [2][2][C]
     extern __shared__ float s_red[];                 // [rows][2][C]
     const int groups = C >> 3, rows = blockDim.x / groups;
     const int g = threadIdx.x % groups, row = threadIdx.x / groups;
-    const size_t npix = static_cast<size_t>(N) * H * W;
+    const int pass = blockIdx.y;
+    const size_t p_begin = pass == 0 ? 0 : static_cast<size_t>(split) * H * W;
+    const size_t npix = pass == 0 && gridDim.y > 1 ? static_cast<size_t>(split) * H * W : static_cast<size_t>(N) * H * W;
+    mean += pass * C;
+    invstd += pass * C;
+    sums += pass * 2 * C;
     float mu[8], is[8], a1[8], a2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -164,7 +180,7 @@ __global__ void bn_bwd_reduce_kernel(const uint16_t* __restrict__ dnext, const u
         a1[k] = a2[k] = 0.f;
     }
     if (row < rows) {
-        for (size_t p = blockIdx.x * static_cast<size_t>(rows) + row; p < npix; p += static_cast<size_t>(gridDim.x) * rows) {
+        for (size_t p = p_begin + blockIdx.x * static_cast<size_t>(rows) + row; p < npix; p += static_cast<size_t>(gridDim.x) * rows) {
             const int x = static_cast<int>(p % W), y = static_cast<int>((p / W) % H);
             const int n = static_cast<int>(p / (static_cast<size_t>(W) * H));
             float dy[8], av[8];
@@ -203,14 +219,15 @@ template <bool AF>
 __global__ void bn_bwd_apply_kernel(const uint16_t* __restrict__ dnext, const uint16_t* __restrict__ a,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ sums, float count,
+                                    float count1, int split,
                                     float slope, uint16_t* __restrict__ g_out, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, int N, int H, int W, int C, int mode) {
     const int groups = C >> 3;
     const size_t total = static_cast<size_t>(N) * H * W * groups;
     if (blockIdx.x == 0 && dgamma != nullptr)
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            atomicAdd(dgamma + c, sums[C + c]);
-            atomicAdd(dbeta + c, sums[c]);
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {      // both passes of a merged batch share gamma / beta
+            atomicAdd(dgamma + c, sums[C + c] + (split < N ? sums[3 * C + c] : 0.f));
+            atomicAdd(dbeta + c, sums[c] + (split < N ? sums[2 * C + c] : 0.f));
         }
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -228,12 +245,17 @@ __global__ void bn_bwd_apply_kernel(const uint16_t* __restrict__ dnext, const ui
             av[2 * k] = f.x;
             av[2 * k + 1] = f.y;
         }
+        const int pass = n >= split ? 1 : 0;
+        const float cnt = pass ? count1 : count;
+        const float* mean_p = mean + pass * C;
+        const float* invstd_p = invstd + pass * C;
+        const float* sums_p = sums + pass * 2 * C;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int c = g * 8 + k;
-            const float is = __ldg(invstd + c);
-            const float xh = (av[k] - __ldg(mean + c)) * is;
-            float gr = __ldg(gamma + c) * is * (dy[k] - __ldg(sums + c) / count - xh * __ldg(sums + C + c) / count);
+            const float is = __ldg(invstd_p + c);
+            const float xh = (av[k] - __ldg(mean_p + c)) * is;
+            float gr = __ldg(gamma + c) * is * (dy[k] - __ldg(sums_p + c) / cnt - xh * __ldg(sums_p + C + c) / cnt);
             o[k] = gr * (av[k] > 0.f ? 1.f : slope);
         }
         reinterpret_cast<uint4*>(g_out)[i] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
@@ -244,11 +266,11 @@ __global__ void bn_bwd_apply_kernel(const uint16_t* __restrict__ dnext, const ui
 // SyncBN: dgamma / dbeta come from the LOCAL sums (the gradient all-reduce averages them over ranks), while the apply
 // pass uses the all-reduced sums.  This tiny kernel banks the local sums between the two.
 __global__ void bn_bwd_accum_kernel(const float* __restrict__ sums, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, int C) {
+                                    float* __restrict__ dbeta, int C, int passes) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) {
-        dgamma[c] += sums[C + c];
-        dbeta[c] += sums[c];
+        dgamma[c] += sums[C + c] + (passes > 1 ? sums[3 * C + c] : 0.f);
+        dbeta[c] += sums[c] + (passes > 1 ? sums[2 * C + c] : 0.f);
     }
 }
 
@@ -562,7 +584,9 @@ __global__ void mix_bwd_kernel(const uint16_t* __restrict__ g_dec, const uint16_
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps, float wd,
-                            float bc1, float bc2_sqrt, const int* __restrict__ step_dev) {
+                            float bc1, float bc2_sqrt, const int* __restrict__ step_dev,
+                            const float* __restrict__ lr_dev) {
+    if (lr_dev != nullptr) lr = *lr_dev;      // learning rate in device memory (per-iteration schedulers under graph replay)
     if (step_dev != nullptr) {      // step count in device memory (a captured CUDA graph replays with a new count)
         const float t = static_cast<float>(*step_dev);
         bc1 = 1.f - powf(b1, t);

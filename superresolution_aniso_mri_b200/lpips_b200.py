@@ -29,8 +29,9 @@ _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "lpips_
 
 
 def vgg16_random_init(seed: Optional[int] = None) -> List[torch.Tensor]:
-    """The 13 conv weight/bias pairs as ``torchvision.models.vgg16(weights=None)`` initialises them (the reference
-    needs the ImageNet download, unavailable offline: SURVEY.md 8(c) shim 3).  Same RNG stream as torchvision."""
+    """The 13 conv weight/bias pairs as ``torchvision.models.vgg16(weights=None)`` initialises them -- TEST / BENCH ONLY
+    (explicit opt-in through ``random_init_seed``): a randomly initialised trunk is not LPIPS.  Same RNG stream as
+    torchvision, so a seed reproduces the oracle's ``init_vgg``."""
     if seed is not None:
         torch.manual_seed(seed)
     convs = [nn.Conv2d(cin, cout, 3, padding=1) for cin, cout in VGG_CFG]
@@ -44,17 +45,70 @@ def vgg16_random_init(seed: Optional[int] = None) -> List[torch.Tensor]:
     return out
 
 
+VGG16_HUB_FILES = ("vgg16-397923af.pth",)        # torchvision IMAGENET1K_V1 = what vgg16(pretrained=True) downloads
+
+
+def load_vgg16_features(path: str) -> List[torch.Tensor]:
+    """The 13 conv weight/bias pairs of a torchvision VGG16 checkpoint (``features.N.weight`` keys, or the bare
+    ``features`` Sequential, or the reference's ``slice{k}.N`` naming, lpips/pretrained_networks.py:104-116)."""
+    sd = torch.load(os.path.expanduser(path), map_location="cpu")
+    if isinstance(sd, dict) and "state_dict" in sd:
+        sd = sd["state_dict"]
+    ws = [(k, v) for k, v in sd.items() if k.endswith(".weight") and torch.is_tensor(v) and v.dim() == 4]
+    if len(ws) < 13:
+        raise RuntimeError("aesr_b200 LPIPS: %s holds %d conv filters, a VGG16 trunk has 13" % (path, len(ws)))
+    out = []
+    for (k, w), (cin, cout) in zip(ws[:13], VGG_CFG):
+        if tuple(w.shape) != (cout, cin, 3, 3):
+            raise RuntimeError("aesr_b200 LPIPS: %s in %s has shape %s, expected %s" % (k, path, tuple(w.shape),
+                                                                                        (cout, cin, 3, 3)))
+        out += [w.float(), sd[k[:-len("weight")] + "bias"].float()]
+    return out
+
+
+def resolve_vgg16_state(vgg_state=None, vgg_weights: Optional[str] = None, random_init_seed: Optional[int] = None
+                        ) -> List[torch.Tensor]:
+    """Where the LPIPS trunk's filters come from, in this order: explicit tensors; a checkpoint path (argument, then
+    ``AESR_VGG16_WEIGHTS``); torchvision's ImageNet file in the torch hub cache (what the reference's
+    ``vgg16(pretrained=True)`` leaves there, lpips/pretrained_networks.py:100); a SEEDED random trunk only on explicit
+    request (``random_init_seed`` / ``AESR_LPIPS_RANDOM_INIT_SEED`` -- identical on every rank).  Otherwise raise: a loss
+    computed on an unseeded random trunk differs per run and per data-parallel rank and is not LPIPS."""
+    if vgg_state is not None:
+        return list(vgg_state)
+    path = vgg_weights or os.environ.get("AESR_VGG16_WEIGHTS")
+    if path:
+        return load_vgg16_features(path)
+    hub = os.path.join(torch.hub.get_dir(), "checkpoints")
+    for name in VGG16_HUB_FILES:
+        if os.path.isfile(os.path.join(hub, name)):
+            return load_vgg16_features(os.path.join(hub, name))
+    if random_init_seed is None and os.environ.get("AESR_LPIPS_RANDOM_INIT_SEED"):
+        random_init_seed = int(os.environ["AESR_LPIPS_RANDOM_INIT_SEED"])
+    if random_init_seed is not None:
+        state = torch.random.get_rng_state()
+        try:
+            return vgg16_random_init(int(random_init_seed))
+        finally:
+            torch.random.set_rng_state(state)
+    raise RuntimeError(
+        "aesr_b200 LPIPS: no VGG16 weights.  The reference uses torchvision's ImageNet-pretrained vgg16 "
+        "(lpips/pretrained_networks.py:100); give its checkpoint as args['vgg_weights'] / PerceptualLoss(vgg_weights=...) / "
+        "AESR_VGG16_WEIGHTS, or place %s under %s.  For tests and benchmarks only, a seeded random trunk can be requested "
+        "with args['lpips_random_init_seed'] / AESR_LPIPS_RANDOM_INIT_SEED." % (VGG16_HUB_FILES[0], hub))
+
+
 class PerceptualLoss(nn.Module):
     """Same constructor / forward signature as the reference class; ``model='net-lin', net='vgg'`` only."""
 
     def __init__(self, model="net-lin", net="vgg", colorspace="rgb", spatial=False, use_gpu=True, gpu_ids=[0],
-                 vgg_state: Optional[List[torch.Tensor]] = None, device=None, act_dtype=None):
+                 vgg_state: Optional[List[torch.Tensor]] = None, device=None, act_dtype=None,
+                 vgg_weights: Optional[str] = None, random_init_seed: Optional[int] = None):
         super().__init__()
         if model != "net-lin" or net not in ("vgg", "vgg16") or spatial:
             raise NotImplementedError("aesr_b200 LPIPS: only model='net-lin', net='vgg', spatial=False are on the hot "
                                       "path (kwatsch/base_trainer.py:41-43)")
         dev = torch.device(device if device is not None else "cuda:%d" % int(gpu_ids[0]))
-        state = vgg_state if vgg_state is not None else vgg16_random_init()
+        state = resolve_vgg16_state(vgg_state, vgg_weights, random_init_seed)
         self.weights = nn.ParameterList([nn.Parameter(t.detach().clone().float().to(dev), requires_grad=False)
                                          for t in state])
         lins = np.load(_DATA)
@@ -101,7 +155,7 @@ class PerceptualLoss(nn.Module):
 
     @torch.no_grad()
     def value_and_grad(self, reference: torch.Tensor, synthesized: torch.Tensor, upstream: torch.Tensor,
-                       normalize: bool = True):
+                       normalize: bool = True, grad_out: Optional[torch.Tensor] = None):
         """Per-image distances [N] and d(sum_n upstream[n] * val[n]) / d synthesized  (fp32 [N,1,H,W])."""
         n = reference.shape[0]
         imgs = torch.cat([reference.detach().float(), synthesized.detach().float()], dim=0).contiguous()
@@ -120,5 +174,5 @@ class PerceptualLoss(nn.Module):
                 g = T.maxpool_bwd(syn[i - 1], d_pooled, g_tap.get(i - 1))
             else:
                 g = ops.conv3x3(g, bwd[i], None, mul_src=syn[i - 1], mul_mode=ops.MUL_RELU_GRAD)
-        dimg = T.vgg_conv1_bwd(g, self.weights[0], SCALE, normalize)
+        dimg = T.vgg_conv1_bwd(g, self.weights[0], SCALE, normalize, out=grad_out)
         return val, dimg

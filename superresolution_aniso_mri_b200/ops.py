@@ -114,8 +114,9 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
             slope: float = LEAKY_SLOPE, scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None,
             out_mode: int = OUT_SAME, out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
             want_out2: bool = False, mul_src: Optional[torch.Tensor] = None, mul_mode: int = MUL_NONE,
-            stats: Optional[torch.Tensor] = None, algo: int = ALGO_AUTO):
-    """x NHWC 16-bit [N,H,W,Cin]; w_packed same dtype [9,Cout,Cin].  Returns out (and out2 when the mode has one)."""
+            stats: Optional[torch.Tensor] = None, algo: int = ALGO_AUTO, stats_split: int = 0):
+    """x NHWC 16-bit [N,H,W,Cin]; w_packed same dtype [9,Cout,Cin].  Returns out (and out2 when the mode has one).
+    ``stats_split``: images >= it accumulate their BatchNorm sums into the second [2*Cout] block of ``stats``."""
     lib = _dev(x)
     assert x.is_contiguous() and x.dim() == 4 and x.dtype == w_packed.dtype
     n, h, w, cin = x.shape
@@ -132,7 +133,7 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
         _lib.check(lib.aesr_conv3x3_fwd(x.data_ptr(), w_packed.data_ptr(), _ptr(bias), _ptr(scale), _ptr(shift),
                                         out.data_ptr(), _ptr(out2), _ptr(mul_src), _ptr(stats), n, h, w, cin, cout,
                                         int(act), float(slope), int(out_mode), int(mul_mode), dt_code(x.dtype),
-                                        int(algo), _stream(x)), "conv3x3_fwd")
+                                        int(algo), int(stats_split), _stream(x)), "conv3x3_fwd")
     return (out, out2) if out2 is not None else out
 
 
@@ -261,14 +262,16 @@ def head(a: torch.Tensor, w9c: torch.Tensor, bias: torch.Tensor, out: Optional[t
 
 
 def lerp_latents(z: torch.Tensor, ia: torch.Tensor, ib: torch.Tensor, wa: torch.Tensor, wb: torch.Tensor,
-                 want_nchw: bool = False, dtype: Optional[torch.dtype] = None):
+                 want_nchw: bool = False, dtype: Optional[torch.dtype] = None, out: Optional[torch.Tensor] = None):
     """out[m] = wa[m]*z[ia[m]] + wb[m]*z[ib[m]]; z fp32 NCHW -> NHWC 16-bit [M,h,w,C] (+ fp32 NCHW z_mix)."""
     lib = _dev(z)
-    dtype = dtype or DEFAULT_DTYPE
+    dtype = dtype or (out.dtype if out is not None else DEFAULT_DTYPE)
     assert z.dtype == torch.float32 and z.is_contiguous() and z.dim() == 4
     _, c, h, w = z.shape
     m = ia.numel()
-    out = torch.empty((m, h, w, c), dtype=dtype, device=z.device)
+    if out is None:
+        out = torch.empty((m, h, w, c), dtype=dtype, device=z.device)
+    assert out.shape == (m, h, w, c) and out.dtype == dtype and out.is_contiguous()
     out_nchw = torch.empty((m, c, h, w), dtype=torch.float32, device=z.device) if want_nchw else None
     done = 0
     tm = _timed("lerp").__enter__()
@@ -351,7 +354,7 @@ def place_slices(src: torch.Tensor, dst: torch.Tensor, out_index: Optional[torch
     done = 0
     while done < n:
         cnt = min(n - done, 65535)
-        _lib.check(lib.aesr_place_slices(src[done:].data_ptr(), dst.data_ptr(),
+        _lib.check(lib.aesr_place_slices(src[done:].data_ptr(), dst.data_ptr() if out_index is not None else dst[done:].data_ptr(),
                                          None if out_index is None else out_index[done:].data_ptr(), cnt, hw,
                                          int(clamp), _stream(src)), "place_slices")
         done += cnt

@@ -14,58 +14,69 @@ GRAD_DTYPE = torch.bfloat16
 _F3 = ctypes.c_float * 3
 
 
-def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps):
-    """-> (scale, shift, mean, invstd); running stats updated in place (torch BatchNorm2d.train() semantics)."""
+def bn_finalize(stats, count, gamma, beta, running_mean, running_var, momentum, eps, count1: float = 0.0):
+    """-> (scale, shift, mean, invstd); running stats updated in place (torch BatchNorm2d.train() semantics).
+    ``count1`` > 0: ``stats`` is [2][2C] (two passes of a merged batch), the outputs are [2, C] and the running statistics
+    are updated once per pass in order."""
     lib = _dev(stats)
     c = gamma.numel()
-    out = torch.empty(4, c, dtype=torch.float32, device=stats.device)
-    _lib.check(lib.aesr_bn_finalize(stats.data_ptr(), float(count), gamma.data_ptr(), beta.data_ptr(),
+    passes = 2 if count1 > 0 else 1
+    assert stats.numel() == passes * 2 * c
+    out = torch.empty(4, passes * c, dtype=torch.float32, device=stats.device)
+    _lib.check(lib.aesr_bn_finalize(stats.data_ptr(), float(count), float(count1), passes, gamma.data_ptr(), beta.data_ptr(),
                                     _ptr(running_mean), _ptr(running_var), float(momentum), float(eps),
                                     out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), c,
                                     _stream(stats)), "bn_finalize")
     return out[0], out[1], out[2], out[3]
 
 
-def bn_apply(a, scale, shift, mode):
+def bn_apply(a, scale, shift, mode, split: int = 0):
     lib = _dev(a)
     n, h, w, c = a.shape
     ho, wo = (h // 2, w // 2) if mode == BN_POOL else (2 * h, 2 * w) if mode == BN_UP else (h, w)
     out = torch.empty((n, ho, wo, c), dtype=a.dtype, device=a.device)
     with _timed("bn_apply"):
         _lib.check(lib.aesr_bn_apply(a.data_ptr(), scale.data_ptr(), shift.data_ptr(), out.data_ptr(), n, h, w, c, mode,
-                                     dt_code(a.dtype), _stream(a)), "bn_apply")
+                                     dt_code(a.dtype), int(split), _stream(a)), "bn_apply")
     return out
 
 
-def bn_bwd(dnext, a, mean, invstd, gamma, dgamma, dbeta, mode, slope=0.01, sync_world: int = 1):
+def bn_bwd(dnext, a, mean, invstd, gamma, dgamma, dbeta, mode, slope=0.01, sync_world: int = 1, split: int = 0):
     """dnext bf16 (grad of pooled / upsampled BN output), a saved activation -> g bf16 [N,H,W,C].
+    ``split``: images >= split are the second pass of a merged batch (mean / invstd [2, C]).
     sync_world > 1 (SyncBN parity mode): the per-channel sums are all-reduced between the reduce and apply kernels."""
     lib = _dev(a)
     n, h, w, c = a.shape
     assert dnext.dtype == GRAD_DTYPE and dnext.is_contiguous()
+    passes = 2 if 0 < split < n else 1
+    assert mean.numel() >= passes * c
     g = torch.empty((n, h, w, c), dtype=GRAD_DTYPE, device=a.device)
-    sums = torch.empty(2 * c, dtype=torch.float32, device=a.device)
+    sums = torch.empty(passes * 2 * c, dtype=torch.float32, device=a.device)
+    n0 = split if passes == 2 else n
 
-    def call(phase, count):
+    def call(phase, count, count1):
         _lib.check(lib.aesr_bn_bwd(dnext.data_ptr(), a.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
                                    sums.data_ptr(), float(slope), g.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), n,
-                                   h, w, c, mode, dt_code(a.dtype), phase, float(count), _stream(a)), "bn_bwd")
+                                   h, w, c, mode, dt_code(a.dtype), phase, float(count), float(count1), int(split),
+                                   _stream(a)), "bn_bwd")
     with _timed("bn_bwd"):
         if sync_world > 1:
             import torch.distributed as dist
-            call(1, 0)
+            call(1, 0, 0)
             dist.all_reduce(sums)
-            call(2, n * h * w * sync_world)
+            call(2, n0 * h * w * sync_world, (n - n0) * h * w * sync_world)
             # dgamma / dbeta were accumulated from the GLOBAL sums on every rank; the gradient all-reduce averages them
         else:
-            call(0, 0)
+            call(0, 0, 0)
     return g
 
 
-def mse(a, b, loss_acc, want_grad=False, grad_scale=1.0):
+def mse(a, b, loss_acc, want_grad=False, grad_scale=1.0, grad_out: Optional[torch.Tensor] = None):
     lib = _dev(a)
     assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous()
-    d = torch.empty_like(a) if want_grad else None
+    assert a.numel() == b.numel()
+    d = grad_out if grad_out is not None else (torch.empty_like(a) if want_grad else None)
+    assert d is None or (d.dtype == torch.float32 and d.is_contiguous() and d.numel() == a.numel())
     _lib.check(lib.aesr_mse(a.data_ptr(), b.data_ptr(), a.numel(), loss_acc.data_ptr(), _ptr(d), float(grad_scale),
                             _stream(a)), "mse")
     return d
@@ -120,13 +131,16 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step):
                "adam_step")
 
 
-def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev: torch.Tensor):
-    """Adam step whose step count lives in device memory (int32 [1]): replayable inside a CUDA graph."""
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev: torch.Tensor,
+                  lr_dev: Optional[torch.Tensor] = None):
+    """Adam step whose step count (int32 [1]) and, optionally, learning rate (fp32 [1]) live in device memory:
+    replayable inside a CUDA graph."""
     lib = _dev(p)
     assert step_dev.dtype == torch.int32 and step_dev.is_cuda
+    assert lr_dev is None or (lr_dev.dtype == torch.float32 and lr_dev.is_cuda)
     _lib.check(lib.aesr_adam_step_dev(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), float(lr),
                                       float(beta1), float(beta2), float(eps), float(weight_decay), step_dev.data_ptr(),
-                                      _stream(p)), "adam_step_dev")
+                                      _ptr(lr_dev), _stream(p)), "adam_step_dev")
 
 
 def vgg_conv1_fwd(img, w, b, shift3, scale3, normalize, dtype):
@@ -140,10 +154,11 @@ def vgg_conv1_fwd(img, w, b, shift3, scale3, normalize, dtype):
     return out
 
 
-def vgg_conv1_bwd(g, w, scale3, normalize, out_scale=1.0):
+def vgg_conv1_bwd(g, w, scale3, normalize, out_scale=1.0, out: Optional[torch.Tensor] = None):
     lib = _dev(g)
     n, h, wd, _ = g.shape
-    dimg = torch.empty((n, 1, h, wd), dtype=torch.float32, device=g.device)
+    dimg = out if out is not None else torch.empty((n, 1, h, wd), dtype=torch.float32, device=g.device)
+    assert dimg.dtype == torch.float32 and dimg.is_contiguous() and dimg.numel() == n * h * wd
     with _timed("vgg_conv1"):
         _lib.check(lib.aesr_vgg_conv1_bwd(g.data_ptr(), w.data_ptr(), dimg.data_ptr(), n, h, wd, _F3(*scale3),
                                           int(normalize), float(out_scale), _stream(g)), "vgg_conv1_bwd")

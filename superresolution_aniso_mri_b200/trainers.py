@@ -38,7 +38,9 @@ class BaseTrainer(object):
         if need:
             dev = self.args['device'] if str(self.args['device']).startswith('cuda') else 'cuda:0'
             self.percept_criterion = PerceptualLoss(model='net-lin', net='vgg', use_gpu=True, device=dev,
-                                                    vgg_state=self.args.get('_vgg_state'))
+                                                    vgg_state=self.args.get('_vgg_state'),
+                                                    vgg_weights=self.args.get('vgg_weights'),
+                                                    random_init_seed=self.args.get('lpips_random_init_seed'))
         else:
             self.percept_criterion = None
 

@@ -11,6 +11,13 @@ One call = what ``AETrainerEndToEnd.train`` / ``AETrainerExtension1Brain.train``
     loss   = MSE(out, x) + w * mean_b LPIPS(slice_between, s_mix)
     backward (dgrad + wgrad for the AE, dgrad only through VGG), Adam.
 
+Merged passes: convolutions do not care which BatchNorm pass an image belongs to, so enc(x) and enc(slice_between) run as
+ONE 3B-image launch per layer, and so do dec(z) and dec(z_mix); only the BatchNorm statistics are kept per pass
+(``split`` = 2B: images [0, 2B) and [2B, 3B) have their own batch statistics and update the running statistics in the
+reference's order, include/aesr_b200.h "Merged batches").  The decoder backward runs on the merged batch as well (weight
+gradients of both passes land in the same buffers, as autograd would sum them); the encoder backward runs on the 2B-image
+prefix -- enc(slice_between) only feeds a logged scalar.
+
 No autograd: forward saves exactly the tensors the hand-written backward needs.  Parameters, gradients and Adam
 moments live in flat fp32 buffers (parameters are views), so the optimizer is ONE kernel and data-parallel training is
 ONE (two, overlapped) NCCL all-reduce(s) of the flat gradient buffer.
@@ -37,10 +44,10 @@ class _ConvRec:
 
 
 class _BnRec:
-    __slots__ = ("bn", "a", "mean", "invstd", "mode")
+    __slots__ = ("bn", "a", "mean", "invstd", "mode", "split")
 
-    def __init__(self, bn, a, mean, invstd, mode):
-        self.bn, self.a, self.mean, self.invstd, self.mode = bn, a, mean, invstd, mode
+    def __init__(self, bn, a, mean, invstd, mode, split=0):
+        self.bn, self.a, self.mean, self.invstd, self.mode, self.split = bn, a, mean, invstd, mode, split
 
 
 class TrainForward:
@@ -129,20 +136,25 @@ class TrainEngine(TrainForward):
                     self.w_fwd[id(m)] = ops.pack_conv3x3_weight(m.weight, dtype=self.dtype)
                     self.w_bwd[id(m)] = ops.pack_conv3x3_weight(m.weight, transpose_flip=True, dtype=T.GRAD_DTYPE)
 
-    def _bn_train(self, bn: BatchNormHolder, stats: torch.Tensor, count: int, update_running: bool = True):
+    def _bn_train(self, bn: BatchNormHolder, stats: torch.Tensor, count: int, update_running: bool = True,
+                  count1: int = 0):
+        """``count1`` > 0: two passes of a merged batch ([2][2C] sums) -> [2, C] outputs, two running-stat updates."""
         if self.sync_bn and self.world > 1:
             dist.all_reduce(stats)
             count *= self.world
+            count1 *= self.world
         out = T.bn_finalize(stats, count, bn.weight, bn.bias, bn.running_mean if update_running else None,
-                            bn.running_var if update_running else None, bn.momentum, bn.eps)
+                            bn.running_var if update_running else None, bn.momentum, bn.eps, count1=count1)
         if update_running:
-            bn.num_batches_tracked += 1
+            bn.num_batches_tracked += 2 if count1 > 0 else 1
         return out
 
     # ------------------------------------------------------------------ forward passes (train mode)
-    def encode_train(self, x: torch.Tensor, save: bool = True):
+    def encode_train(self, x: torch.Tensor, save: bool = True, split: int = 0):
+        """``split``: images >= split are a second module call (own BatchNorm batch statistics), 0 = one call."""
         enc, sc = self.model.enc, self.model.scales
         n = x.shape[0]
+        n0 = split if 0 < split < n else n
         recs: List[_ConvRec] = []
         a = ops.e0(x, enc[0].weight.reshape(-1), enc[0].bias, dtype=self.dtype)
         prev = "e0"
@@ -151,11 +163,12 @@ class TrainEngine(TrainForward):
             c1, c2, bn = enc[i], enc[i + 2], enc[i + 4]
             recs.append(_ConvRec(c1, a, prev))
             a1 = ops.conv3x3(a, self.w_fwd[id(c1)], c1.bias, act=ops.ACT_LEAKY)
-            stats = torch.zeros(2 * c2.out_channels, dtype=torch.float32, device=self.dev)
-            a2 = ops.conv3x3(a1, self.w_fwd[id(c2)], c2.bias, act=ops.ACT_LEAKY, stats=stats)
-            scale, shift, mean, invstd = self._bn_train(bn, stats, n * a2.shape[1] * a2.shape[2])
-            a = T.bn_apply(a2, scale, shift, T.BN_POOL)
-            recs.append(_ConvRec(c2, a1, "leaky", _BnRec(bn, a2, mean, invstd, T.BN_POOL)))
+            stats = torch.zeros((2 if n0 < n else 1) * 2 * c2.out_channels, dtype=torch.float32, device=self.dev)
+            a2 = ops.conv3x3(a1, self.w_fwd[id(c2)], c2.bias, act=ops.ACT_LEAKY, stats=stats, stats_split=n0)
+            hw = a2.shape[1] * a2.shape[2]
+            scale, shift, mean, invstd = self._bn_train(bn, stats, n0 * hw, count1=(n - n0) * hw)
+            a = T.bn_apply(a2, scale, shift, T.BN_POOL, split=n0)
+            recs.append(_ConvRec(c2, a1, "leaky", _BnRec(bn, a2, mean, invstd, T.BN_POOL, n0)))
             prev = "bn"
             i += 6
         c1, c2 = enc[i], enc[i + 2]
@@ -166,9 +179,10 @@ class TrainEngine(TrainForward):
                              want_out2=True)
         return z, z16, (recs if save else None)
 
-    def decode_train(self, z16: torch.Tensor, save: bool = True):
+    def decode_train(self, z16: torch.Tensor, save: bool = True, split: int = 0):
         dec, sc = self.model.dec, self.model.scales
         n = z16.shape[0]
+        n0 = split if 0 < split < n else n
         recs: List[_ConvRec] = []
         a, prev = z16, "latent"
         i = 0
@@ -176,39 +190,50 @@ class TrainEngine(TrainForward):
             c1, c2, bn = dec[i], dec[i + 2], dec[i + 4]
             recs.append(_ConvRec(c1, a, prev))
             a1 = ops.conv3x3(a, self.w_fwd[id(c1)], c1.bias, act=ops.ACT_LEAKY)
-            stats = torch.zeros(2 * c2.out_channels, dtype=torch.float32, device=self.dev)
-            a2 = ops.conv3x3(a1, self.w_fwd[id(c2)], c2.bias, act=ops.ACT_LEAKY, stats=stats)
-            scale, shift, mean, invstd = self._bn_train(bn, stats, n * a2.shape[1] * a2.shape[2])
-            a = T.bn_apply(a2, scale, shift, T.BN_UP)
-            recs.append(_ConvRec(c2, a1, "leaky", _BnRec(bn, a2, mean, invstd, T.BN_UP)))
+            stats = torch.zeros((2 if n0 < n else 1) * 2 * c2.out_channels, dtype=torch.float32, device=self.dev)
+            a2 = ops.conv3x3(a1, self.w_fwd[id(c2)], c2.bias, act=ops.ACT_LEAKY, stats=stats, stats_split=n0)
+            hw = a2.shape[1] * a2.shape[2]
+            scale, shift, mean, invstd = self._bn_train(bn, stats, n0 * hw, count1=(n - n0) * hw)
+            a = T.bn_apply(a2, scale, shift, T.BN_UP, split=n0)
+            recs.append(_ConvRec(c2, a1, "leaky", _BnRec(bn, a2, mean, invstd, T.BN_UP, n0)))
             prev = "bn"
             i += 6
         c1, head = dec[i], dec[i + 2]
         recs.append(_ConvRec(c1, a, prev))
         a1 = ops.conv3x3(a, self.w_fwd[id(c1)], c1.bias, act=ops.ACT_LEAKY)
-        w9c, hb = self.model._head_w(head)
+        w9c, hb = self._head_params(head)
         out = ops.head(a1, w9c, hb, sigmoid=True)
         return out, ((recs, a1, out, head, w9c) if save else None)
+
+    def _head_params(self, head):
+        """[9,32] fp32 filter + bias of dec.14, formed HERE (not through the model's version-keyed eval cache): inside a
+        captured step graph the tensors must be recomputed on replay and owned by the graph's pool."""
+        with torch.no_grad():
+            return (head.weight.detach()[0].permute(1, 2, 0).reshape(9, -1).contiguous().float(),
+                    head.bias.detach().float().contiguous())
 
     # ------------------------------------------------------------------ backward passes
     def _backward_convs(self, recs: List[_ConvRec], g: torch.Tensor, x_img: Optional[torch.Tensor] = None):
         """g: bf16 gradient w.r.t. the LAST conv's pre-activation output.  Returns the gradient w.r.t. the stage input
-        (latent for the decoder, nothing for the encoder whose first op is enc.0)."""
+        (latent for the decoder, nothing for the encoder whose first op is enc.0).  ``g`` may cover only the first
+        images of the saved activations (encoder: enc(slice_between) has no gradient): saved tensors are sliced to it."""
+        n = g.shape[0]
         for k in range(len(recs) - 1, -1, -1):
             r = recs[k]
-            T.wgrad3x3(g, r.x_in, self.grad[id(r.conv.weight)], self.grad[id(r.conv.bias)])
+            x_in = r.x_in[:n]
+            T.wgrad3x3(g, x_in, self.grad[id(r.conv.weight)], self.grad[id(r.conv.bias)])
             wt = self.w_bwd[id(r.conv)]
             if r.prev == "leaky":
                 prev_rec = recs[k - 1]
                 if prev_rec.bn is not None:
                     raise AssertionError("a conv fed by a BN'd tensor is tagged 'bn'")
-                g = ops.conv3x3(g, wt, None, mul_src=r.x_in, mul_mode=ops.MUL_LEAKY_GRAD, slope=SLOPE)
+                g = ops.conv3x3(g, wt, None, mul_src=x_in, mul_mode=ops.MUL_LEAKY_GRAD, slope=SLOPE)
             elif r.prev == "bn":
                 bnrec = recs[k - 1].bn
                 dnext = ops.conv3x3(g, wt, None)
-                g = T.bn_bwd(dnext, bnrec.a, bnrec.mean, bnrec.invstd, bnrec.bn.weight,
+                g = T.bn_bwd(dnext, bnrec.a[:n], bnrec.mean, bnrec.invstd, bnrec.bn.weight,
                              self.grad[id(bnrec.bn.weight)], self.grad[id(bnrec.bn.bias)], bnrec.mode, SLOPE,
-                             sync_world=self.world if self.sync_bn else 1)
+                             sync_world=self.world if self.sync_bn else 1, split=bnrec.split if bnrec.split < n else 0)
             elif r.prev == "e0":
                 d_a0 = ops.conv3x3(g, wt, None)
                 e0 = self.model.enc[0]
@@ -242,35 +267,53 @@ class TrainEngine(TrainForward):
         return self._step_impl(image, slice_between, wa, wb, lpips, ex_loss_weight, combined, do_update, lr, betas, eps,
                                weight_decay, keep)
 
+    MAX_GRAPHS = 2      # captured configurations kept (each owns a private pool with one step's activations)
+
     def _step_graphed(self, image, slice_between, wa, wb, lpips, ex_loss_weight, combined, lr, betas, eps, weight_decay):
-        key = (tuple(image.shape), tuple(slice_between.shape), tuple(wa.shape), bool(combined), float(ex_loss_weight),
-               float(lr), tuple(float(b) for b in betas), float(eps), float(weight_decay), id(lpips))
+        # lr and the LPIPS weight travel through device memory (like the Adam step count): one graph serves a per-iteration
+        # lr scheduler (kwatsch/base_trainer.py:18-22) and the per-epoch loss-weight annealing (:456-459).
+        key = (tuple(image.shape), tuple(slice_between.shape), tuple(wa.shape), bool(combined),
+               tuple(float(b) for b in betas), float(eps), float(weight_decay), id(lpips))
         ent = self._graphs.get(key)
+        B = image.shape[0] // 2
         if ent is None:
             if self._graph_seen.get(key, 0) < 1:
                 # first step of this configuration runs eagerly (one-time host work: shared-memory attributes, caches)
+                if len(self._graph_seen) > 64:
+                    self._graph_seen.clear()
                 self._graph_seen[key] = 1
                 return self._step_impl(image, slice_between, wa, wb, lpips, ex_loss_weight, combined, True, lr, betas,
                                        eps, weight_decay, False)
+            while len(self._graphs) >= self.MAX_GRAPHS:           # least recently used configuration goes (with its pool)
+                torch.cuda.synchronize(self.dev)
+                self._graphs.pop(next(iter(self._graphs)))
             ent = {"x": image.detach().float().contiguous().clone(), "sb": slice_between.detach().float().contiguous().clone(),
                    "wa": wa.detach().clone(), "wb": wb.detach().clone(),
-                   "step": torch.zeros(1, dtype=torch.int32, device=self.dev)}
+                   "step": torch.zeros(1, dtype=torch.int32, device=self.dev),
+                   "lr": torch.full((1,), float(lr), dtype=torch.float32, device=self.dev),
+                   "upstream": torch.full((B,), ex_loss_weight / B, dtype=torch.float32, device=self.dev)}
             torch.cuda.synchronize(self.dev)
             graph = torch.cuda.CUDAGraph()
             # thread-local capture mode: the NCCL watchdog thread polls events while the step is being captured
             with torch.cuda.graph(graph, capture_error_mode="thread_local" if self.world > 1 else "global"):
                 ent["res"] = self._step_impl(ent["x"], ent["sb"], ent["wa"], ent["wb"], lpips, ex_loss_weight, combined,
-                                             True, lr, betas, eps, weight_decay, False, step_dev=ent["step"])
+                                             True, lr, betas, eps, weight_decay, False, step_dev=ent["step"],
+                                             lr_dev=ent["lr"], upstream_dev=ent["upstream"])
             ent["graph"] = graph
             self._graphs[key] = ent
+        else:
+            self._graphs[key] = self._graphs.pop(key)            # mark as most recently used
         ent["x"].copy_(image, non_blocking=True)
         ent["sb"].copy_(slice_between, non_blocking=True)
         ent["wa"].copy_(wa, non_blocking=True)
         ent["wb"].copy_(wb, non_blocking=True)
         self.step_count += 1
         ent["step"].fill_(self.step_count)
+        ent["lr"].fill_(float(lr))
+        ent["upstream"].fill_(ex_loss_weight / B)
         ent["graph"].replay()
         self._after_update()
+        ent["res"]["ex_loss_weight"] = ex_loss_weight
         return ent["res"]
 
     def release_graphs(self) -> None:
@@ -288,38 +331,51 @@ class TrainEngine(TrainForward):
     def _step_impl(self, image: torch.Tensor, slice_between: torch.Tensor, wa: torch.Tensor, wb: torch.Tensor,
                    lpips=None, ex_loss_weight: float = 0.0, combined: bool = True, do_update: bool = True,
                    lr: Optional[float] = None, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                   keep: bool = False, step_dev: Optional[torch.Tensor] = None) -> dict:
+                   keep: bool = False, step_dev: Optional[torch.Tensor] = None, lr_dev: Optional[torch.Tensor] = None,
+                   upstream_dev: Optional[torch.Tensor] = None) -> dict:
         m = self.model
+        m.invalidate_cache()            # nothing derived by an earlier eval-mode call may leak into this step (or its graph)
         B = image.shape[0] // 2
         x = image.detach().float().contiguous()
         sb = slice_between.detach().float().contiguous()
         self._pack_all()
         self.flat_g.zero_()
         scal = torch.zeros(4, dtype=torch.float32, device=self.dev)      # [mse_recon, latent_mse, spare, spare]
-
-        z, z16, enc_ctx = self.encode_train(x)
-        out, dec_ctx = self.decode_train(z16)
-        dout = T.mse(out, x, scal[0:1], want_grad=True)
-
         idx = torch.arange(B, dtype=torch.int32, device=self.dev)
-        z16_mix, z_mix = ops.lerp_latents(z, idx, idx + B, wa, wb, want_nchw=True, dtype=self.dtype)
         val = None
         if combined:
-            s_mix, mix_ctx = self.decode_train(z16_mix)
-            z_ref, _, _ = self.encode_train(sb, save=False)               # logged only; updates BN running stats
+            # enc(x) and enc(slice_between) as one 3B-image pass, dec(z) and dec(z_mix) as another (see module docstring)
+            z3, z16, enc_ctx = self.encode_train(torch.cat([x, sb], dim=0), split=2 * B)
+            z, z_ref = z3[:2 * B], z3[2 * B:]                 # z_ref: logged only; its pass updated the BN running stats
+            _, z_mix = ops.lerp_latents(z3, idx, idx + B, wa, wb, want_nchw=True, out=z16[2 * B:])
+            out3, dec_ctx = self.decode_train(z16, split=2 * B)
+            out, s_mix = out3[:2 * B], out3[2 * B:]
+            dout3 = torch.empty_like(out3)
+            T.mse(out, x, scal[0:1], grad_out=dout3[:2 * B])
             T.mse(z_mix, z_ref, scal[1:2])
-            upstream = torch.full((B,), ex_loss_weight / B, dtype=torch.float32, device=self.dev)
-            val, d_smix = lpips.value_and_grad(sb, s_mix, upstream, normalize=True)
+            upstream = upstream_dev if upstream_dev is not None else \
+                torch.full((B,), ex_loss_weight / B, dtype=torch.float32, device=self.dev)
+            val, _ = lpips.value_and_grad(sb, s_mix, upstream, normalize=True, grad_out=dout3[2 * B:])
+            # ---- backward
+            g3 = self.decode_backward(dec_ctx, dout3)                     # [3B,h,w,latent] bf16
+            g_z = T.mix_bwd(g3[:2 * B], g3[2 * B:], wa, wb)
         else:
+            z, z16, enc_ctx = self.encode_train(x)
+            out, dec_ctx = self.decode_train(z16)
+            dout = T.mse(out, x, scal[0:1], want_grad=True)
+            _, z_mix = ops.lerp_latents(z, idx, idx + B, wa, wb, want_nchw=True, dtype=self.dtype)
             s_mix = None
-            z_ref = m.encode_eval(sb)                                     # AEBaseTrainer: eval-mode encode (no_grad)
+            # AEBaseTrainer: eval-mode encode (no_grad).  Layer-per-kernel pipeline: its derived tensors (packed filters,
+            # folded BN affine) are formed on the device, so the pass can be captured in the step graph (the folded stem
+            # carries its filter as kernel parameters = a host round trip); dropped again so they cannot outlive the step.
+            fused, m.fused_inference = m.fused_inference, False
+            try:
+                z_ref = m.encode_eval(sb)
+            finally:
+                m.fused_inference = fused
+            m.invalidate_cache()
             T.mse(z_mix, z_ref, scal[1:2])
-
-        # ---- backward
-        g_z = self.decode_backward(dec_ctx, dout)                         # [2B,h,w,latent] bf16
-        if combined:
-            g_mix = self.decode_backward(mix_ctx, d_smix)                 # [B,...]
-            g_z = T.mix_bwd(g_z, g_mix, wa, wb)
+            g_z = self.decode_backward(dec_ctx, dout)                     # [2B,h,w,latent] bf16
         handle_dec = None
         if self.world > 1:                                                # decoder grads are final: reduce them now
             handle_dec = dist.all_reduce(self.flat_g[self.enc_numel:], op=dist.ReduceOp.AVG, async_op=True)
@@ -328,9 +384,9 @@ class TrainEngine(TrainForward):
             dist.all_reduce(self.flat_g[:self.enc_numel], op=dist.ReduceOp.AVG)
             handle_dec.wait()
 
-        if do_update and step_dev is not None:       # graph capture: the count is read from device memory at replay time
+        if do_update and step_dev is not None:       # graph capture: step count / lr are read from device memory at replay time
             T.adam_step_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr, betas[0], betas[1], eps, weight_decay,
-                            step_dev)
+                            step_dev, lr_dev)
         elif do_update:
             self.step_count += 1
             if lr is None:
@@ -361,5 +417,5 @@ class TrainEngine(TrainForward):
 
 
 # The forward-only helper shares the pass implementations with the engine (they only touch TrainForward state).
-for _name in ("_pack_all", "_bn_train", "encode_train", "decode_train"):
+for _name in ("_pack_all", "_bn_train", "encode_train", "decode_train", "_head_params"):
     setattr(TrainForward, _name, getattr(TrainEngine, _name))

@@ -278,7 +278,8 @@ def test_find_best_val_model_end_to_end(cuda_lib, tmp_path):
     args.update(dataset="ACDC", model="ae_combined", ae_class="VanillaACAI", width=64, latent_width=16, latent=128,
                 depth=32, lr=1e-5, weight_decay=0.0, epochs=10, device="cuda:0", gpu_ids=[0], ex_loss_weight1=0.05,
                 use_percept_loss=False, use_loss_annealing=False, get_masks=False, epoch_threshold=0,
-                log_tensorboard=False, batch_size=4, downsample_steps=2, output_dir=exper, dir_models=os.path.join(exper, "models"))
+                log_tensorboard=False, batch_size=4, downsample_steps=2, output_dir=exper, dir_models=os.path.join(exper, "models"),
+                lpips_random_init_seed=3)           # no ImageNet checkpoint offline: explicit opt-in to a seeded random trunk
     with open(os.path.join(exper, "settings.yaml"), "w") as fp:
         yaml.dump(args, fp)
     oargs = O.default_args(64, 16)

@@ -242,3 +242,141 @@ def test_graphed_step_matches_eager_step(cuda_lib):
     # two runs can drift apart by up to 2 * 6 * lr; almost everywhere they agree to ~1e-6 (measured: max 7.6e-4, typical 1e-6)
     diff = (runs[True][1] - runs[False][1]).abs()
     assert diff.max().item() < 1.3e-3 and diff.mean().item() < 2e-5
+
+
+def test_plain_ae_trainer_steps_match_oracle(cuda_lib, golden):
+    """``--model ae`` (kwatsch/trainer_ae.py:71-109): MSE-only step, logged latent loss from an EVAL-mode encode of
+    slice_between (base_trainer.py:203-205) which leaves the module in eval mode when train() returns (:251-252; train()
+    switches back at its start).  Four steps against the oracle (autograd + Adam) and the reference's own logged losses
+    (tests/golden/train_small.npz 'plain': 32x32, B=4, seeded uniform batches)."""
+    from networks.net_config import NetworkConfig
+    g = golden("train_small.npz")
+    args = trainer_args(width=32, latent_width=8, batch_size=4)
+    args.update(NetworkConfig("ae", "ACDC").architecture)
+    args.update(width=32, latent_width=8, latent=128, depth=32, model="ae")
+    tr = make_trainer(args)
+    assert type(tr).__name__ == "AEBaseTrainer" and tr.percept_criterion is None and not tr.combined
+    oargs = O.default_args(32, 8)
+    st = O.init_state(oargs, seed=892372)
+    adam = O.AdamState(st, lr=args["lr"])
+    gen = torch.Generator().manual_seed(11)
+    for step in range(4):
+        img = torch.rand(8, 1, 32, 32, generator=gen)
+        sb = torch.rand(4, 1, 32, 32, generator=gen)
+        lg = O.train_step(st, oargs, adam, img, sb, combined=False)
+        tr.train({"image": img, "slice_between": sb}, keep_predictions=(step == 3))
+        assert not tr.model.training                      # the quirk: eval mode after train()
+        for k in ("loss_ae", "loss_latent_1"):
+            ours, ref = tr.losses[k][-1], lg[k]
+            assert abs(ours - ref) <= 0.01 * abs(ref) + 1e-9, (step, k, ours, ref)
+            assert abs(ours - float(g["plain_" + k][step])) <= 0.01 * abs(float(g["plain_" + k][step])) + 1e-9
+    assert "loss_ae_extra" not in tr.losses
+    assert tr.train_predictions["slice_inbetween_mix"].shape == (4, 1, 32, 32)
+    assert int(tr.model.enc[5].num_batches_tracked) == 4   # one train-mode encoder pass per step (the eval encode adds none)
+    sd = tr.model.state_dict()
+    for k, v in sd.items():
+        if "running" in k:
+            assert torch.allclose(v.cpu(), st[k], rtol=5e-3, atol=5e-4), k
+
+
+def test_loss_annealing_weight_and_scheduler_share_one_graph(cuda_lib):
+    """use_loss_annealing=True (kwatsch/cardiac/trainer_ae.py:80, table base_trainer.py:456-459): the LPIPS weight of epoch e
+    is loss_weights[e]; with use_lr_scheduler the learning rate changes EVERY iteration (CosineAnnealingLR).  Both travel
+    through device memory, so one captured graph serves all values -- checked against the oracle with the same weights / lrs."""
+    import math
+    args = trainer_args(width=64, latent_width=16, batch_size=4, use_loss_annealing=True, epochs=4, lr=1e-4,
+                        use_lr_scheduler=True, lr_iter_max=8)
+    tr = make_trainer(args)
+    x = np.linspace(-5, 5, 4)
+    want_w = (1.0 / (1.0 + np.exp(-x)) * 0.05)[::-1]
+    np.testing.assert_allclose(tr.loss_weights, want_w, rtol=1e-12)
+    oargs = O.default_args(64, 16)
+    st = O.init_state(oargs, seed=892372)
+    adam = O.AdamState(st, lr=1e-4)
+    vgg = O.init_vgg(3)
+    it = 0
+    for epoch in range(3):
+        for s in range(2):
+            img, mid = acdc_batch(2 * epoch + s, B=4, size=64)
+            adam.lr = 1e-4 * (1 + math.cos(math.pi * it / 8)) / 2          # CosineAnnealingLR(T_max=8, eta_min=0) closed form
+            assert abs(tr.opt_ae.param_groups[0]["lr"] - adam.lr) < 1e-12
+            lg = O.train_step(st, oargs, adam, img, mid, vgg, lins(), ex_loss_weight=float(want_w[epoch]))
+            tr.train({"image": img, "slice_between": mid}, keep_predictions=False)
+            for k in ("loss_ae", "loss_ae_dist", "loss_ae_dist_extra"):
+                ours, ref = tr.losses[k][-1], lg[k]
+                assert abs(ours - ref) <= 0.01 * abs(ref) + 1e-9, (epoch, s, k, ours, ref)
+            it += 1
+        tr.epoch += 1
+    assert len(tr.engine._graphs) == 1 and tr.engine.step_count == 6
+    # Adam moves every weight by ~lr per step, so the mean distance travelled measures the sum of the learning rates that
+    # were actually applied: schedule 1, .96, .85, .69, .5, .31 (x 1e-4) = 4.3e-4 against 6e-4 for an lr stuck in a graph
+    p0 = O.init_state(oargs, seed=892372)["dec.0.weight"]
+    ours = (tr.model.dec[0].weight.detach().cpu() - p0).abs().mean().item()
+    ref = (st["dec.0.weight"] - p0).abs().mean().item()
+    assert ref > 1e-4 and abs(ours - ref) < 0.12 * ref, (ours, ref)
+
+
+def test_dhcp_batch8_train_step(cuda_lib):
+    """BASELINE config 4 at its real batch size (width 256, latent_width 64, B=8): two steps run, losses finite and equal
+    to the oracle's within 1 % on the first step (one oracle step at this size takes a few seconds of CPU)."""
+    args = trainer_args(width=256, latent_width=64, dataset="dHCP", ex_loss_weight1=0.001, batch_size=8)
+    tr = make_trainer(args)
+    B = 8
+    rs = np.random.RandomState(5)
+    oargs = O.default_args(256, 64)
+    st = O.init_state(oargs, seed=892372)
+    adam = O.AdamState(st, lr=1e-5)
+    for step in range(2):
+        img, mid = acdc_batch(step, B=B, size=256)
+        af = torch.from_numpy(rs.choice([0.25, 0.5, 0.75], size=(B, 1)).astype(np.float32))
+        tr.train({"image": img, "slice_between": mid, "alpha_from": af, "alpha_to": 1 - af}, keep_predictions=False)
+        if step == 0:
+            lg = O.train_step(st, oargs, adam, img, mid, O.init_vgg(3), lins(), alpha_from=af, alpha_to=1 - af,
+                              ex_loss_weight=0.001)
+            for k in ("loss_ae", "loss_ae_dist", "loss_ae_dist_extra"):
+                assert abs(tr.losses[k][-1] - lg[k]) <= 0.01 * abs(lg[k]) + 1e-9, (k, tr.losses[k][-1], lg[k])
+    assert all(np.isfinite(v).all() for v in tr.losses.values())
+
+
+def test_merged_batch_batchnorm_equals_two_passes(cuda_lib):
+    """The merged-batch BatchNorm entry points (conv statistics with ``stats_split``, bn_finalize with two passes, bn_apply /
+    bn_bwd with ``split``) against the same kernels run once per pass."""
+    from superresolution_aniso_mri_b200 import ops, ops_train as T
+    dev = torch.device("cuda:0")
+    dt = torch.bfloat16
+    g = torch.Generator().manual_seed(8)
+    n, n0, h, w, c = 5, 3, 18, 22, 64
+    x = torch.randn(n, h, w, c, generator=g).to(dt).to(dev)
+    wt = ops.pack_conv3x3_weight((torch.randn(c, c, 3, 3, generator=g) / 24).to(dev), dtype=dt)
+    b = (torch.randn(c, generator=g) * 0.1).to(dev)
+    gamma, beta = (torch.rand(c, generator=g) + 0.5).to(dev), (torch.randn(c, generator=g) * 0.1).to(dev)
+    stats = torch.zeros(4 * c, device=dev)
+    a = ops.conv3x3(x, wt, b, act=ops.ACT_LEAKY, stats=stats, stats_split=n0)
+    parts, st_parts = [], []
+    for sl in (slice(0, n0), slice(n0, n)):
+        sp = torch.zeros(2 * c, device=dev)
+        parts.append(ops.conv3x3(x[sl].contiguous(), wt, b, act=ops.ACT_LEAKY, stats=sp))
+        st_parts.append(sp)
+    assert torch.equal(a, torch.cat(parts))
+    assert torch.allclose(stats, torch.cat(st_parts), rtol=1e-5, atol=1e-3)
+    rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+    rm2, rv2 = rm.clone(), rv.clone()
+    sc, sh, mean, inv = T.bn_finalize(stats, n0 * h * w, gamma, beta, rm, rv, 0.1, 1e-5, count1=(n - n0) * h * w)
+    outs = [T.bn_finalize(st_parts[k], cnt * h * w, gamma, beta, rm2, rv2, 0.1, 1e-5) for k, cnt in ((0, n0), (1, n - n0))]
+    for k in range(2):
+        for got, want in zip((sc, sh, mean, inv), outs[k]):
+            assert torch.allclose(got[k * c:(k + 1) * c], want, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(rm, rm2, rtol=1e-5, atol=1e-7) and torch.allclose(rv, rv2, rtol=1e-5, atol=1e-7)
+    for mode in (T.BN_POOL, T.BN_UP):
+        y = T.bn_apply(a, sc, sh, mode, split=n0)
+        want = torch.cat([T.bn_apply(parts[k], outs[k][0], outs[k][1], mode) for k in range(2)])
+        # scale / shift of the merged finalize agree with the per-pass ones to fp32 rounding: at most one bf16 ulp apart
+        assert ((y.float() - want.float()).abs() <= 2.0 ** -7 * want.float().abs() + 1e-6).all()
+        dn = (torch.randn(y.shape, generator=g) * 1e-3).to(torch.bfloat16).to(dev)
+        dg, db = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+        dg2, db2 = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+        gg = T.bn_bwd(dn, a, mean, inv, gamma, dg, db, mode, split=n0)
+        want_g = torch.cat([T.bn_bwd(dn[sl].contiguous(), parts[k], outs[k][2], outs[k][3], gamma, dg2, db2, mode)
+                            for k, sl in enumerate((slice(0, n0), slice(n0, n)))])
+        assert (gg.float() - want_g.float()).abs().max().item() <= 2e-2 * want_g.float().abs().max().item()
+        assert torch.allclose(dg, dg2, rtol=1e-3, atol=1e-6) and torch.allclose(db, db2, rtol=1e-3, atol=1e-6)

@@ -266,3 +266,28 @@ def test_vif_oracle_against_reference_golden(golden):
     m = O.compute_metrics(vol, noisy, 2)
     assert set(m) == {"ssim", "psnr", "vif", "ssim_synth", "psnr_synth", "vif_synth", "ssim_recon", "psnr_recon", "vif_recon"}
     assert O.determine_last_slice(11, 3) == 9 and O.determine_last_slice(10, 3) == 9
+
+
+def test_reference_trained_checkpoint_pins(golden):
+    """tests/golden/trained_ckpt.npz: a checkpoint trained by the reference itself (make_golden.gold_trained) and the
+    reference's synthesis outputs for it; the oracle reproduces them bit for bit, and the checkpoint is a real model
+    (it reconstructs held-out phantoms, BN statistics are trained, latents are O(1))."""
+    from collections import OrderedDict
+    g = golden("trained_ckpt.npz")
+    st = OrderedDict((k[len("state__"):], torch.from_numpy(g[k].copy())) for k in g.files if k.startswith("state__"))
+    args = O.default_args(64, 16)
+    assert list(st.keys()) == list(O.init_state(args, seed=1).keys())
+    assert int(st["enc.5.num_batches_tracked"]) == 2 * int(g["steps"])          # enc(x) and enc(slice_between) per step
+    vol = O.mri_phantom(10, 128, seed=41)
+    hr = O.create_super_volume(st, args, vol, O.alpha_range_for(2), use_original=True)
+    np.testing.assert_array_equal(hr[:, ::4, ::4].numpy(), g["acdc128_ni2_sub"])
+    np.testing.assert_array_equal(hr.double().sum(dim=(1, 2)).numpy(), g["acdc128_ni2_slice_sum"])
+    v3 = O.mri_phantom(9, 220, seed=47)[:, 0]
+    out = O.create_super_volume_eval(st, args, v3, O.alpha_range_for(3), use_original=False, downsample_steps=4,
+                                     generate_inbetween_slices=True)
+    np.testing.assert_array_equal(out[:, ::5, ::5].numpy(), g["oasis220_ds4_sub"])
+    with torch.no_grad():
+        z = O.encode(st, args, vol)
+        rec = O.decode(st, args, z)
+    assert float(torch.mean((rec - vol) ** 2)) < 3e-3 and float(z.std()) > 0.05
+    assert abs(float(torch.mean((rec - vol) ** 2)) - float(g["acdc128_recon_mse"])) < 1e-9
