@@ -81,6 +81,12 @@ int64_t aesr_launch_count(void);
 int aesr_pack_conv3x3_weight(const float* w, void* packed, int Cout, int Cin, int transpose_flip, int dtype,
                              void* stream);
 
+/* aesr_pack_conv3x3_weight for many filters in one launch: job j = 6 int64 in DEVICE memory {offset of the fp32 filter in
+ * src_base (floats), offset of the packed filter in dst_base (16-bit elements), Cout, Cin, transpose_flip, 0};
+ * max_elems = the largest 9*Cout*Cin.  The training step re-packs all filters after every optimizer update. */
+int aesr_pack_conv3x3_weight_batch(const float* src_base, void* dst_base, const long long* jobs_dev, int n_jobs,
+                                   int max_elems, int dtype, void* stream);
+
 /* 3x3 / pad 1 / stride 1 convolution, implicit GEMM on tcgen05 tensor cores with TMA operand loads.
  * Replaces nn.Conv2d(k,k,3,padding=1) + activation (+ eval BatchNorm2d affine) (+ AvgPool2d / Upsample) of
  * networks/acai_vanilla.py:55-59,68-70,87-92,96 and the VGG16 convs of lpips/pretrained_networks.py:107-116.
@@ -89,7 +95,8 @@ int aesr_pack_conv3x3_weight(const float* w, void* packed, int Cout, int Cin, in
  *   y = act(conv(x) + bias) [* act'(mul_src)] ; stats += {sum y, sum y^2} per channel ; y = y*scale + shift ; out stage
  *   bias/scale/shift/out2/mul_src/stats may be NULL.  stats: fp32 [2*Cout], or [2][2*Cout] with 0 < stats_split < N:
  *   images >= stats_split (the second pass of a merged batch, see "Merged batches" below) accumulate into the second
- *   block. */
+ *   block.  stats_split < 0: stats is [Cout] and only the sums are accumulated -- a data-gradient launch whose output is the
+ *   gradient of the previous layer's pre-activation delivers that layer's bias gradient on the way. */
 int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, const float* scale, const float* shift,
                      void* out, void* out2, const void* mul_src, float* stats, int N, int H, int W, int Cin, int Cout,
                      int act, float slope, int out_mode, int mul_mode, int dtype, int algo, int stats_split, void* stream);
@@ -199,18 +206,20 @@ int aesr_bn_apply(const void* a, const float* scale, const float* shift, void* o
 /* Backward of [LeakyReLU ->] BatchNorm(train) -> pool/upsample: dnext bf16 (gradient of the pooled / upsampled tensor),
  * a = saved post-activation input of the BN; g_out bf16 [N,H,W,C] = gradient w.r.t. the producing conv's
  * pre-activation output; dgamma / dbeta accumulated (over both passes); sums = passes*2*C floats of scratch;
- * mean / invstd [passes][C].
+ * mean / invstd [passes][C]; dbias_conv (C floats or NULL) += per-channel sums of g_out = the bias gradient of the
+ * producing conv (summed by the apply pass, no extra pass over g_out).
  * phase 0 = reduce + apply; 1 = reduce only (sums[p][c] = sum dy, sums[p][C+c] = sum dy*xhat); 2 = apply only -- a
  * data-parallel caller all-reduces `sums` between 1 and 2 and passes the GLOBAL element counts (`count` / `count1` <= 0:
  * the local ones). */
 int aesr_bn_bwd(const void* dnext, const void* a, const float* mean, const float* invstd, const float* gamma,
-                float* sums, float slope, void* g_out, float* dgamma, float* dbeta, int N, int H, int W, int C, int mode,
-                int dtype, int phase, float count, float count1, int split, void* stream);
+                float* sums, float slope, void* g_out, float* dgamma, float* dbeta, float* dbias_conv, int N, int H, int W,
+                int C, int mode, int dtype, int phase, float count, float count1, int split, void* stream);
 /* F.mse_loss(a, b) (kwatsch/base_trainer.py:177): *loss_acc += mean((a-b)^2); d (optional) = grad_scale * 2 (a-b)/n. */
 int aesr_mse(const float* a, const float* b, size_t n, float* loss_acc, float* d, float grad_scale, void* stream);
-/* Backward of dec.14 + Sigmoid: g_in bf16 (includes LeakyReLU'(a_in)), dw9c[9*C] and dbias accumulated. */
+/* Backward of dec.14 + Sigmoid: g_in bf16 (includes LeakyReLU'(a_in)), dw9c[9*C] and dbias accumulated; dbias_in (C floats
+ * or NULL) += per-channel sums of g_in = the bias gradient of the conv that produced a_in (dec.12). */
 int aesr_head_bwd(const float* dout, const float* out, const void* a_in, const float* w9c, void* g_in, float* dw9c,
-                  float* dbias, int N, int H, int W, int C, float slope, int dtype, void* stream);
+                  float* dbias, float* dbias_in, int N, int H, int W, int C, float slope, int dtype, void* stream);
 /* Backward of enc.0 (1x1 conv, padding 1): dw[C], db[C] accumulated from g bf16 [N,H+2,W+2,C] and x fp32 [N,1,H,W]. */
 int aesr_e0_bwd(const void* g, const float* x, float* dw, float* db, int N, int H, int W, int C, void* stream);
 /* Weight gradient of a 3x3 conv: dW fp32 [Cout,Cin,3,3] += g^T * shifted(x), dbias[Cout] += sum g (dbias may be NULL).

@@ -24,6 +24,7 @@ _SIGNATURES = {
     "aesr_set_tuning": (I, [I, I]),
     "aesr_launch_count": (c_int64, []),
     "aesr_pack_conv3x3_weight": (I, [P, P, I, I, I, I, P]),
+    "aesr_pack_conv3x3_weight_batch": (I, [P, P, P, I, I, I, P]),
     "aesr_conv3x3_fwd": (I, [P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, F, I, I, I, I, I, P]),
     "aesr_pack_conv3x3_weight_up2fold": (I, [P, P, I, I, I, P]),
     "aesr_conv3x3_up2_head_fwd": (I, [P, P, P, P, P, P, I, I, I, I, I, F, I, I, P]),
@@ -44,9 +45,9 @@ _SIGNATURES = {
     # training step
     "aesr_bn_finalize": (I, [P, F, F, I, P, P, P, P, F, F, P, P, P, P, I, P]),
     "aesr_bn_apply": (I, [P, P, P, P, I, I, I, I, I, I, I, P]),
-    "aesr_bn_bwd": (I, [P, P, P, P, P, P, F, P, P, P, I, I, I, I, I, I, I, F, F, I, P]),
+    "aesr_bn_bwd": (I, [P, P, P, P, P, P, F, P, P, P, P, I, I, I, I, I, I, I, F, F, I, P]),
     "aesr_mse": (I, [P, P, c_size_t, P, P, F, P]),
-    "aesr_head_bwd": (I, [P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
+    "aesr_head_bwd": (I, [P, P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
     "aesr_e0_bwd": (I, [P, P, P, P, I, I, I, I, P]),
     "aesr_wgrad3x3": (I, [P, P, P, P, I, I, I, I, I, I, I, P]),
     "aesr_mix_bwd": (I, [P, P, P, P, P, I, c_size_t, P]),

@@ -55,7 +55,7 @@ int check_launch(const char* what) {
 
 void do_init(int device) {
     cudaDeviceProp prop;
-    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
         g_init_status = fail(AESR_ERR_CUDA, "no usable CUDA device %d: %s", device,
                              cudaGetErrorString(cudaGetLastError()));
         return;
@@ -136,6 +136,30 @@ __global__ void pack_conv3x3_weight_kernel(const float* __restrict__ w, uint16_t
     }
 }
 
+// All 3x3 filters of a model in ONE launch (training re-packs every filter after every optimizer step: 24 launches of
+// ~2 us each otherwise).  jobs[j] = {src offset (floats), dst offset (16-bit elements), Cout, Cin, transpose_flip, 0}.
+template <bool FP16>
+__global__ void pack_conv3x3_weight_batch_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst,
+                                                 const long long* __restrict__ jobs) {
+    const long long* jb = jobs + 6 * blockIdx.y;
+    const float* w = src + jb[0];
+    uint16_t* out = dst + jb[1];
+    const int Cout = static_cast<int>(jb[2]), Cin = static_cast<int>(jb[3]), transpose_flip = static_cast<int>(jb[4]);
+    const int total = 9 * Cout * Cin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int tap, row, col;
+        float v;
+        if (!transpose_flip) {
+            col = i % Cin; row = (i / Cin) % Cout; tap = i / (Cin * Cout);
+            v = w[(static_cast<size_t>(row) * Cin + col) * 9 + tap];
+        } else {
+            col = i % Cout; row = (i / Cout) % Cin; tap = i / (Cin * Cout);
+            v = w[(static_cast<size_t>(col) * Cin + row) * 9 + (8 - tap)];
+        }
+        out[i] = cvt16_t<FP16>(v);
+    }
+}
+
 // "nearest x2 upsample -> 3x3 conv" folded to the low resolution (conv3x3_tc.cuh OUT_SHUFFLE2): destination
 // [tap = (dy,dx) low-res offset][phase = 2a+b][co][ci] = sum of the original taps (ky,kx) that read low-res offset
 // (dy,dx) when producing hi-res pixel (2y+a, 2x+b):  a = 0: dy=0 <- {ky=0}, dy=1 <- {1,2};  a = 1: dy=1 <- {0,1}, dy=2 <- {2}.
@@ -160,11 +184,16 @@ __global__ void pack_conv3x3_weight_up2fold_kernel(const float* __restrict__ w, 
     }
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: `configured` is a bit mask over device ordinals
+// (a process that drives a second GPU, like the reference's cuda:1 loss offload, configures each kernel once per device).
 template <typename K>
 int set_max_smem(K kernel, int* configured) {
-    if (!*configured) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    const int bit = 1 << (dev & 31);
+    if (!(*configured & bit)) {
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem_optin));
-        *configured = 1;
+        *configured |= bit;
     }
     return AESR_OK;
 }
@@ -310,11 +339,18 @@ int launch_halo(const void* x, const void* w, const void* head_w16, ConvParams p
 
 extern "C" {
 
+// The calling thread's current device is NOT changed: every entry point launches on the device that is current when it
+// is called (PyTorch's device guard / the caller's cudaSetDevice).  SM count and shared-memory limits are taken from the
+// first device initialised; every device of a node must be the same B200 part (checked below).
 int aesr_init(int device) {
     std::call_once(g_init_once, do_init, device);
     if (g_init_status != AESR_OK) return g_init_status;
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) return fail(AESR_ERR_CUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return fail(AESR_ERR_CUDA, "no usable CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+    if (prop.major != 10 || prop.multiProcessorCount != g_sm_count)
+        return fail(AESR_ERR_ARCH, "aesr_b200: device %d (%s, cc %d.%d, %d SMs) differs from the initialised B200 (%d SMs)",
+                    device, prop.name, prop.major, prop.minor, prop.multiProcessorCount, g_sm_count);
     return AESR_OK;
 }
 
@@ -398,6 +434,7 @@ int conv3x3_dispatch(const void* x, const void* w_packed, const float* bias, con
     p.out = out; p.out2 = out2; p.mul_src = static_cast<const uint16_t*>(mul_src); p.mul_mode = mul_mode;
     p.stats = stats;
     p.stats_split = (stats_split > 0 && stats_split < N) ? stats_split : N;
+    p.stats_sum_only = stats_split < 0;
     if (stats && Cout > 256) return fail(AESR_ERR_INVALID, "conv3x3_fwd: statistics need Cout <= 256, got %d", Cout);
     if (head_w) memcpy(p.head_wc, head_w, sizeof(p.head_wc));      // HOST pointer: travels as a kernel parameter
 
@@ -419,6 +456,21 @@ int conv3x3_dispatch(const void* x, const void* w_packed, const float* bias, con
 }  // namespace
 
 extern "C" {
+
+int aesr_pack_conv3x3_weight_batch(const float* src_base, void* dst_base, const long long* jobs_dev, int n_jobs,
+                                   int max_elems, int dtype, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!src_base || !dst_base || !jobs_dev || n_jobs <= 0 || n_jobs > 65535 || max_elems <= 0)
+        return fail(AESR_ERR_INVALID, "pack_conv3x3_weight_batch: bad arguments");
+    int gx = (max_elems + 255) / 256;
+    if (gx > 64) gx = 64;
+    const dim3 grid(gx, n_jobs);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == AESR_DT_FP16) pack_conv3x3_weight_batch_kernel<true><<<grid, 256, 0, s>>>(src_base, static_cast<uint16_t*>(dst_base), jobs_dev);
+    else pack_conv3x3_weight_batch_kernel<false><<<grid, 256, 0, s>>>(src_base, static_cast<uint16_t*>(dst_base), jobs_dev);
+    return check_launch("pack_conv3x3_weight_batch");
+}
 
 int aesr_conv3x3_fwd(const void* x, const void* w_packed, const float* bias, const float* scale, const float* shift,
                      void* out, void* out2, const void* mul_src, float* stats, int N, int H, int W, int Cin, int Cout,

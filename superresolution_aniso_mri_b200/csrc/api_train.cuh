@@ -45,8 +45,8 @@ int aesr_bn_apply(const void* a, const float* scale, const float* shift, void* o
 }
 
 int aesr_bn_bwd(const void* dnext, const void* a, const float* mean, const float* invstd, const float* gamma,
-                float* sums, float slope, void* g_out, float* dgamma, float* dbeta, int N, int H, int W, int C, int mode,
-                int dtype, int phase, float count, float count1, int split, void* stream) {
+                float* sums, float slope, void* g_out, float* dgamma, float* dbeta, float* dbias_conv, int N, int H, int W,
+                int C, int mode, int dtype, int phase, float count, float count1, int split, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!dnext || !a || !mean || !invstd || !gamma || !sums || !g_out || !dgamma || !dbeta || C % 32 != 0 || mode < 0 || mode > 2)
@@ -56,7 +56,7 @@ int aesr_bn_bwd(const void* dnext, const void* a, const float* mean, const float
     const int passes = split < N ? 2 : 1;                            // merged batch: images [0, split) and [split, N)
     const size_t npix = static_cast<size_t>(N) * H * W;
     const bool do_reduce = phase != 2, do_apply = phase != 1;
-    if (do_reduce) CUDA_TRY(cudaMemsetAsync(sums, 0, static_cast<size_t>(passes) * 2 * C * sizeof(float), s));
+    if (do_reduce) CUDA_TRY(cudaMemsetAsync(sums, 0, static_cast<size_t>(passes) * BN_SUMS * C * sizeof(float), s));
     if (C > 512) return fail(AESR_ERR_INVALID, "bn_bwd: C=%d > 512", C);
     const int groups = C / 8;
     const int rows = 256 / groups;                                   // pixel rows per block (C = 32: 64 ... C = 512: 4)
@@ -67,20 +67,21 @@ int aesr_bn_bwd(const void* dnext, const void* a, const float* mean, const float
     if (gx < 1) gx = 1;
     const dim3 rgrid(gx, passes);
     const int block = rows * groups;
-    const size_t red_smem = static_cast<size_t>(rows) * 2 * C * sizeof(float);      // <= 32 KB
+    const size_t red_smem = static_cast<size_t>(rows) * BN_SUMS * C * sizeof(float);      // <= 32 KB
     const size_t total = npix * groups;
     if (count <= 0.f) count = static_cast<float>(static_cast<size_t>(split) * H * W);       // global-batch counts in SyncBN mode
     if (count1 <= 0.f) count1 = static_cast<float>(static_cast<size_t>(N - split) * H * W);
     // phase 0: the apply kernel banks dgamma / dbeta from the (local) sums; phase 1 banks them right after the local
     // reduce; phase 2 (sums all-reduced by the caller) must not bank them again.
+    const int apply_grid = grid_for(total, 256, dbias_conv ? 4 : 16);      // dbias_conv: C global atomics per block at the end
     float* dg_apply = phase == 0 ? dgamma : nullptr;
     float* db_apply = phase == 0 ? dbeta : nullptr;
     if (dtype == AESR_DT_FP16) {
-        if (do_reduce) bn_bwd_reduce_kernel<true><<<rgrid, block, red_smem, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode, split);
-        if (do_apply) bn_bwd_apply_kernel<true><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, count1, split, slope, static_cast<uint16_t*>(g_out), dg_apply, db_apply, N, H, W, C, mode);
+        if (do_reduce) bn_bwd_reduce_kernel<true><<<rgrid, block, red_smem, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode, split, slope);
+        if (do_apply) bn_bwd_apply_kernel<true><<<apply_grid, 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, count1, split, slope, static_cast<uint16_t*>(g_out), dg_apply, db_apply, dbias_conv, N, H, W, C, mode);
     } else {
-        if (do_reduce) bn_bwd_reduce_kernel<false><<<rgrid, block, red_smem, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode, split);
-        if (do_apply) bn_bwd_apply_kernel<false><<<grid_for(total, 256, 16), 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, count1, split, slope, static_cast<uint16_t*>(g_out), dg_apply, db_apply, N, H, W, C, mode);
+        if (do_reduce) bn_bwd_reduce_kernel<false><<<rgrid, block, red_smem, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, sums, N, H, W, C, mode, split, slope);
+        if (do_apply) bn_bwd_apply_kernel<false><<<apply_grid, 256, 0, s>>>(static_cast<const uint16_t*>(dnext), static_cast<const uint16_t*>(a), mean, invstd, gamma, sums, count, count1, split, slope, static_cast<uint16_t*>(g_out), dg_apply, db_apply, dbias_conv, N, H, W, C, mode);
     }
     if (phase == 1) bn_bwd_accum_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, dgamma, dbeta, C, passes);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -96,20 +97,20 @@ int aesr_mse(const float* a, const float* b, size_t n, float* loss_acc, float* d
 }
 
 int aesr_head_bwd(const float* dout, const float* out, const void* a_in, const float* w9c, void* g_in, float* dw9c,
-                  float* dbias, int N, int H, int W, int C, float slope, int dtype, void* stream) {
+                  float* dbias, float* dbias_in, int N, int H, int W, int C, float slope, int dtype, void* stream) {
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!dout || !out || !a_in || !w9c || !g_in || !dw9c || !dbias || C != 32) return fail(AESR_ERR_INVALID, "head_bwd: bad arguments");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t total = static_cast<size_t>(N) * H * W;
     const uint16_t* a16 = static_cast<const uint16_t*>(a_in);
-    size_t blocks = (total * 4 + 255) / 256;
-    const size_t cap = static_cast<size_t>(g_sm_count);            // one resident block per SM (190 registers); 288 global atomics each at the end
+    const long long tiles = static_cast<long long>(N) * ((H + HB_ROWS - 1) / HB_ROWS) * ((W + HB_PIX - 1) / HB_PIX);
+    long long blocks = tiles;
+    const long long cap = 3LL * g_sm_count;                        // three resident blocks per SM; 321 global atomics each at the end
     if (blocks > cap) blocks = cap;
     if (dtype == AESR_DT_FP16)
-        head_bwd_fused_kernel<true><<<static_cast<int>(blocks), 256, 0, s>>>(dout, out, a16, w9c, static_cast<uint16_t*>(g_in), dw9c, dbias, N, H, W, slope);
+        head_bwd_fused_kernel<true><<<static_cast<int>(blocks), 256, 0, s>>>(dout, out, a16, w9c, static_cast<uint16_t*>(g_in), dw9c, dbias, dbias_in, N, H, W, slope);
     else
-        head_bwd_fused_kernel<false><<<static_cast<int>(blocks), 256, 0, s>>>(dout, out, a16, w9c, static_cast<uint16_t*>(g_in), dw9c, dbias, N, H, W, slope);
+        head_bwd_fused_kernel<false><<<static_cast<int>(blocks), 256, 0, s>>>(dout, out, a16, w9c, static_cast<uint16_t*>(g_in), dw9c, dbias, dbias_in, N, H, W, slope);
     return check_launch("head_bwd");
 }
 
@@ -232,8 +233,16 @@ int aesr_vgg_conv1_fwd(const float* img, const float* w, const float* b, void* o
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!img || !w || !b || !out || !shift3 || !scale3) return fail(AESR_ERR_INVALID, "vgg_conv1_fwd: bad arguments");
-    const size_t total = static_cast<size_t>(N) * H * W * 8;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (H >= 2 && W >= 2) {          // four pixels per thread
+        const size_t totq = static_cast<size_t>(N) * H * ((W + 3) / 4) * 8;
+        if (dtype == AESR_DT_FP16)
+            vgg_conv1_fwd_quad_kernel<true><<<grid_for(totq, 256, 3), 256, 0, s>>>(img, w, b, static_cast<uint16_t*>(out), N, H, W, shift3[0], shift3[1], shift3[2], scale3[0], scale3[1], scale3[2], normalize);
+        else
+            vgg_conv1_fwd_quad_kernel<false><<<grid_for(totq, 256, 3), 256, 0, s>>>(img, w, b, static_cast<uint16_t*>(out), N, H, W, shift3[0], shift3[1], shift3[2], scale3[0], scale3[1], scale3[2], normalize);
+        return check_launch("vgg_conv1_fwd_quad");
+    }
+    const size_t total = static_cast<size_t>(N) * H * W * 8;
     if (dtype == AESR_DT_FP16)
         vgg_conv1_fwd_kernel<true><<<grid_for(total, 256, 8), 256, 0, s>>>(img, w, b, static_cast<uint16_t*>(out), N, H, W, shift3[0], shift3[1], shift3[2], scale3[0], scale3[1], scale3[2], normalize);
     else
@@ -246,8 +255,8 @@ int aesr_vgg_conv1_bwd(const void* g, const float* w, float* dimg, int N, int H,
     int rc = ensure_init();
     if (rc != AESR_OK) return rc;
     if (!g || !w || !dimg || !scale3) return fail(AESR_ERR_INVALID, "vgg_conv1_bwd: bad arguments");
-    const size_t total = static_cast<size_t>(N) * H * W;
-    vgg_conv1_bwd_kernel<<<grid_for(total * 8, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    const size_t totq = static_cast<size_t>(N) * H * ((W + 3) / 4);
+    vgg_conv1_bwd_quad_kernel<<<grid_for(totq * 8, 256, 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint16_t*>(g), w, dimg, N, H, W, scale3[0], scale3[1], scale3[2], normalize, out_scale);
     return check_launch("vgg_conv1_bwd");
 }
@@ -280,8 +289,13 @@ int aesr_lpips_head(const void* o0, const void* o1, const float* lin, float* val
     const int lanes_per_px = (C / 8) < 32 ? (C / 8) : 32;
     const int grid = grid_for(total * lanes_per_px, 256, 8);
     if (g1) {       // backward (+ the forward value in the same pass when asked for)
-        if (dtype == AESR_DT_FP16) lpips_head_bwd_kernel<true><<<grid, 256, 0, s>>>(a, b, lin, upstream, static_cast<uint16_t*>(g1), val, N, HW, C);
-        else lpips_head_bwd_kernel<false><<<grid, 256, 0, s>>>(a, b, lin, upstream, static_cast<uint16_t*>(g1), val, N, HW, C);
+        if (C <= 256) {
+            if (dtype == AESR_DT_FP16) lpips_head_bwd_kernel<true, 1><<<grid, 256, 0, s>>>(a, b, lin, upstream, static_cast<uint16_t*>(g1), val, N, HW, C);
+            else lpips_head_bwd_kernel<false, 1><<<grid, 256, 0, s>>>(a, b, lin, upstream, static_cast<uint16_t*>(g1), val, N, HW, C);
+        } else {
+            if (dtype == AESR_DT_FP16) lpips_head_bwd_kernel<true, 2><<<grid, 256, 0, s>>>(a, b, lin, upstream, static_cast<uint16_t*>(g1), val, N, HW, C);
+            else lpips_head_bwd_kernel<false, 2><<<grid, 256, 0, s>>>(a, b, lin, upstream, static_cast<uint16_t*>(g1), val, N, HW, C);
+        }
         return check_launch("lpips_head_bwd");
     }
     if (dtype == AESR_DT_FP16) lpips_head_fwd_kernel<true><<<grid, 256, 0, s>>>(a, b, lin, val, N, HW, C);

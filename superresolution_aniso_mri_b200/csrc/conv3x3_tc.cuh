@@ -87,6 +87,8 @@ struct ConvParams {
     // images >= stats_split (second pass of a merged batch, own BatchNorm statistics) accumulate into stats + 2*Cout
     float* stats;
     int stats_split;
+    int stats_sum_only;     // 1: stats is [Cout], only the sums are taken (bias gradient of the layer whose output gradient this
+                            // data-gradient launch produces: dbias[c] = sum over pixels of the epilogue's output)
     // OUT_SHUFFLE2_HEAD: fp32 [9][32] filter of the 32 -> 1 head conv, BY VALUE: kernel parameters live in the constant
     // bank, so the 1152 head MACs per thread read their weights as instruction operands (c[0][..]) instead of through
     // 288 LDS.128 per thread and tile, which made the epilogue shared-memory-bandwidth-bound (191 -> see profiles/).
@@ -193,7 +195,7 @@ __device__ __forceinline__ void conv_teardown(const ConvParams& p, const ConvBar
     tc_fence_before();
     __syncthreads();
     if (WITH_STATS && p.stats != nullptr)        // every epilogue of this CTA has added its sums: flush them
-        for (int c = threadIdx.x; c < (p.stats_split < p.N ? 4 : 2) * p.Cout; c += CONV_THREADS) {
+        for (int c = threadIdx.x; c < (p.stats_sum_only ? 1 : p.stats_split < p.N ? 4 : 2) * p.Cout; c += CONV_THREADS) {
             const float v = bars.s_stats[c];
             if (v != 0.f) atomicAdd(p.stats + c, v);
         }
@@ -322,8 +324,12 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                 s1[j] = inb ? v[j] : 0.f;
                 s2[j] = s1[j] * s1[j];
             }
-            const float t1 = warp_transpose_sum16(s1, lane), t2 = warp_transpose_sum16(s2, lane);
+            const float t1 = warp_transpose_sum16(s1, lane);
             const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if (p.stats_sum_only) {
+                if ((lane & 1) == 0) atomicAdd(bars.s_stats + cg + ch, t1);
+            } else {
+            const float t2 = warp_transpose_sum16(s2, lane);
             if ((lane & 1) == 0) {
                 // shared-memory accumulators: one global atomic per channel and CTA at the end of the kernel instead of one
                 // per warp and 16-channel chunk (940 k atomics onto 64 addresses made enc.3's forward 95 us against 36 us
@@ -331,6 +337,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                 float* sst = bars.s_stats + (n >= p.stats_split ? 2 * Cout : 0);      // pass of a merged batch (tile-uniform)
                 atomicAdd(sst + cg + ch, t1);
                 atomicAdd(sst + Cout + cg + ch, t2);
+            }
             }
         }
         if (p.scale != nullptr) {

@@ -109,6 +109,97 @@ __global__ void vgg_conv1_fwd_kernel(const float* __restrict__ img, const float*
                                                       pack2_t<AF>(o[4], o[5]), pack2_t<AF>(o[6], o[7]));
     }
 }
+// Same conv, one thread = 8 output channels of FOUR consecutive pixels of a row: the 3 x 6 image window is loaded once
+// (18 instead of 36 loads) and every 16-byte filter word read from shared memory feeds four pixels (18 instead of 72 LDS.128
+// per quad) -- the one-pixel version was bound by its shared-memory reads (77 us for 24 images at 128^2, 0.4 % of the DRAM
+// bandwidth, ncu profiles/r04b_train_elementwise_ncu.md).  H, W >= 2 (the host falls back to the kernel above otherwise).
+template <bool AF>
+__global__ void __launch_bounds__(256)
+vgg_conv1_fwd_quad_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][3][3][3]*/,
+                          const float* __restrict__ b, uint16_t* __restrict__ out, int N, int H, int W,
+                          float sh0, float sh1, float sh2, float sc0, float sc1, float sc2, int normalize) {
+    __shared__ __align__(16) float sW[9][64];       // W2[t][co]
+    __shared__ float sK[9][64];                      // per-tap constant that an on-image tap subtracts
+    __shared__ __align__(16) float sB[9][64];       // bias per border class
+    const float shf[3] = {sh0, sh1, sh2}, scv[3] = {sc0, sc1, sc2};
+    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) {
+        const int t = i / 64, co = i % 64;
+        float we = 0.f, ws = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float wv = w[co * 27 + c * 9 + t];
+            we += wv / scv[c];
+            ws += wv * shf[c] / scv[c];
+        }
+        sW[t][co] = normalize ? 2.f * we : we;
+        sK[t][co] = normalize ? ws + we : ws;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) {
+        const int cls = i / 64, co = i % 64, cy = cls / 3, cx = cls % 3;
+        float acc = b[co];
+        for (int t = 0; t < 9; ++t) {
+            const int dy = t / 3, dx = t % 3;
+            const bool ok = !(cy == 0 && dy == 0) && !(cy == 2 && dy == 2) && !(cx == 0 && dx == 0) && !(cx == 2 && dx == 2);
+            if (ok) acc -= sK[t][co];
+        }
+        sB[cls][co] = acc;
+    }
+    __syncthreads();
+    const int qx = (W + 3) >> 2;
+    const size_t total = static_cast<size_t>(N) * H * qx * 8;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int grp = static_cast<int>(i & 7);
+        const size_t q = i >> 3;
+        const int x0 = static_cast<int>(q % qx) * 4, y = static_cast<int>((q / qx) % H);
+        const size_t nb = (q / (static_cast<size_t>(qx) * H)) * H * W;
+        float u[3][6];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int yy = y + r - 1;
+            const bool row_in = yy >= 0 && yy < H;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const int xx = x0 + c - 1;
+                u[r][c] = (row_in && xx >= 0 && xx < W) ? __ldg(img + nb + static_cast<size_t>(yy) * W + xx) : 0.f;
+            }
+        }
+        float o[4][8];
+        const int cy = (y == 0) ? 0 : (y == H - 1) ? 2 : 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = x0 + j;
+            const int cls = cy * 3 + ((x == 0) ? 0 : (x >= W - 1) ? 2 : 1);
+            const float4 b0 = *reinterpret_cast<const float4*>(&sB[cls][grp * 8]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sB[cls][grp * 8 + 4]);
+            o[j][0] = b0.x; o[j][1] = b0.y; o[j][2] = b0.z; o[j][3] = b0.w;
+            o[j][4] = b1.x; o[j][5] = b1.y; o[j][6] = b1.z; o[j][7] = b1.w;
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float4 w0 = *reinterpret_cast<const float4*>(&sW[t][grp * 8]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&sW[t][grp * 8 + 4]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float uv = u[t / 3][j + t % 3];          // off-image taps hold 0: they contribute nothing
+                o[j][0] = fmaf(w0.x, uv, o[j][0]); o[j][1] = fmaf(w0.y, uv, o[j][1]);
+                o[j][2] = fmaf(w0.z, uv, o[j][2]); o[j][3] = fmaf(w0.w, uv, o[j][3]);
+                o[j][4] = fmaf(w1.x, uv, o[j][4]); o[j][5] = fmaf(w1.y, uv, o[j][5]);
+                o[j][6] = fmaf(w1.z, uv, o[j][6]); o[j][7] = fmaf(w1.w, uv, o[j][7]);
+            }
+        }
+        uint16_t* orow = out + (nb + static_cast<size_t>(y) * W + x0) * 64 + grp * 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (x0 + j >= W) break;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[j][k] = fmaxf(o[j][k], 0.f);
+            *reinterpret_cast<uint4*>(orow + j * 64) = make_uint4(pack2_t<AF>(o[j][0], o[j][1]), pack2_t<AF>(o[j][2], o[j][3]),
+                                                                  pack2_t<AF>(o[j][4], o[j][5]), pack2_t<AF>(o[j][6], o[j][7]));
+        }
+    }
+}
 // backward of the above w.r.t. the image: g bf16 [N,H,W,64] is dL/d(pre-ReLU conv1_1 output) (ReLU' already applied)
 //   dimg[p] = (normalize ? 2 : 1) * sum_c (1/scale_c) * sum_{tap,co} W[co][c][tap] * g[p - off(tap)][co]
 // Eight lanes per pixel, 8 channels (one 16-byte load) per lane and tap, three shuffles to fold the eight partial sums.
@@ -149,6 +240,74 @@ __global__ void vgg_conv1_bwd_kernel(const uint16_t* __restrict__ g, const float
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         if (live && sub == 0) dimg[p] = acc * (normalize ? 2.f : 1.f) * out_scale;
+    }
+}
+// Quad version of the backward: one thread = 8 channels (lane & 7) of FOUR consecutive output pixels; the effective filter
+// of the lane's 8 channels lives in 72 registers, the 3 x 6 window of g is loaded once (18 x 16 bytes for 4 outputs instead
+// of 36), no shared-memory reads in the loop.
+__global__ void __launch_bounds__(256, 2)
+vgg_conv1_bwd_quad_kernel(const uint16_t* __restrict__ g, const float* __restrict__ w, float* __restrict__ dimg, int N,
+                          int H, int W, float sc0, float sc1, float sc2, int normalize, float out_scale) {
+    const int sub = threadIdx.x & 7;
+    __shared__ float swe[9 * 64];                        // effective 1-channel filter, formed once per block
+    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) {
+        const int t = i / 64, co = i % 64;
+        swe[i] = w[co * 27 + 0 * 9 + t] / sc0 + w[co * 27 + 1 * 9 + t] / sc1 + w[co * 27 + 2 * 9 + t] / sc2;
+    }
+    __syncthreads();
+    float we[9][8];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) we[t][k] = swe[t * 64 + sub * 8 + k];
+    const int qx = (W + 3) >> 2;
+    const size_t grp_id = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 3;
+    const size_t ngrp = (static_cast<size_t>(gridDim.x) * blockDim.x) >> 3;
+    const size_t total = static_cast<size_t>(N) * H * qx;
+    const size_t rounds = (total + ngrp - 1) / ngrp;                          // warp-uniform trip count (shuffles inside)
+    const float osc = (normalize ? 2.f : 1.f) * out_scale;
+    for (size_t it = 0; it < rounds; ++it) {
+        const size_t q = it * ngrp + grp_id;
+        const bool live = q < total;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        int x0 = 0, y = 0;
+        size_t nb = 0;
+        if (live) {
+            x0 = static_cast<int>(q % qx) * 4;
+            y = static_cast<int>((q / qx) % H);
+            nb = (q / (static_cast<size_t>(qx) * H)) * H * W;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int yy = y + r - 1;
+                if (yy < 0 || yy >= H) continue;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    const int xx = x0 + c - 1;
+                    if (xx < 0 || xx >= W) continue;
+                    float gv[8];
+                    load8<false>(g + (nb + static_cast<size_t>(yy) * W + xx) * 64 + sub * 8, gv);
+                    // g pixel (yy, xx) reaches output (y, x0 + j) through tap (2 - r, j - c + 2)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int tx = j - c + 2;
+                        if (tx < 0 || tx > 2) continue;
+                        const int t = (2 - r) * 3 + tx;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[j] = fmaf(we[t][k], gv[k], acc[j]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+        }
+        if (live && sub < 4 && x0 + sub < W) {
+            const float v = sub == 0 ? acc[0] : sub == 1 ? acc[1] : sub == 2 ? acc[2] : acc[3];
+            dimg[nb + static_cast<size_t>(y) * W + x0 + sub] = v * osc;
+        }
     }
 }
 // ---------------------------------------------------------------------------------------------------------------
@@ -289,7 +448,9 @@ __global__ void lpips_head_fwd_kernel(const uint16_t* __restrict__ o0, const uin
 //   d val / d o1_j = e_j / q - o1_j * s / (r q^2)       ; times upstream[n] / HW.   Output bf16 NHWC.
 // val != NULL: the forward value is accumulated in the same pass (lin_c d_c^2 = e_c^2 / (4 lin_c) needs nothing new:
 // d_c = x0_c i0 - x1_c i1 is formed anyway) -- training calls forward and backward together, one read of the features.
-template <bool AF>
+// R = 16-byte chunks per lane: 1 for C <= 256 (the three large taps; halves the live registers: 72 -> fewer, more warps in
+// flight for a kernel that waits on its loads), 2 for C = 512.
+template <bool AF, int R>
 __global__ void lpips_head_bwd_kernel(const uint16_t* __restrict__ o0, const uint16_t* __restrict__ o1,
                                       const float* __restrict__ lin, const float* __restrict__ upstream /*[N]*/,
                                       uint16_t* __restrict__ g1, float* __restrict__ val, int N, int HW, int C) {
@@ -309,10 +470,10 @@ __global__ void lpips_head_bwd_kernel(const uint16_t* __restrict__ o0, const uin
     for (size_t base = warp_id * ppw; base < total; base += nwarps * ppw) {
         const size_t p = base + lane / G;
         const bool live = p < total;
-        float x0[2][8], x1[2][8];
+        float x0[R][8], x1[R][8];
         float n0 = 0.f, n1 = 0.f;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < R; ++r) {
             const int ch = sub + r * G;
             if (live && ch < chunks) {
                 load8<AF>(o0 + p * C + ch * 8, x0[r]);
@@ -331,10 +492,10 @@ __global__ void lpips_head_bwd_kernel(const uint16_t* __restrict__ o0, const uin
         n1 = group_sum(n1, G);
         const float r_ = sqrtf(n1);
         const float i0 = 1.f / (sqrtf(n0) + 1e-10f), q = r_ + 1e-10f, i1 = 1.f / q;
-        float e[2][8];
+        float e[R][8];
         float sdot = 0.f, acc = 0.f;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < R; ++r) {
             const int ch = sub + r * G;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -358,7 +519,7 @@ __global__ void lpips_head_bwd_kernel(const uint16_t* __restrict__ o0, const uin
         const float up = upstream[p / HW] / HW;
         const float kq = (r_ > 0.f) ? sdot / (r_ * q * q) : 0.f;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < R; ++r) {
             const int ch = sub + r * G;
             if (ch < chunks) {
                 uint32_t o[4];

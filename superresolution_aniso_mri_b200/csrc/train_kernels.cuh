@@ -157,11 +157,14 @@ __device__ __forceinline__ void bn_dy8_at(const uint16_t* __restrict__ dnext, in
 // pass 1: sums[c] += sum dy, sums[C+c] += sum dy * xhat   (xhat = (a - mean) * invstd)
 // block = 256 threads = (C/8 channel groups) x (256 / (C/8) pixel rows); a thread owns 8 channels (16-byte loads) of a
 // strip of pixels, the rows are folded through shared memory and the block issues one atomic per channel and sum.
-// (The lane-per-channel version moved 2 bytes per lane and load: 0.48 ms of a 5 ms training step together with pass 2.)
+// (The lane-per-channel version moved 2 bytes per lane and load: 0.48 ms of a 5 ms training step together with pass 2.
+//  Three more mask-weighted sums here would give the producing conv's bias gradient in closed form, but 24 more
+//  accumulators took the kernel from 64 to 110 registers and every launch got 15-30 % slower -- measured, reverted.)
+constexpr int BN_SUMS = 2;
 template <bool AF>
 __global__ void bn_bwd_reduce_kernel(const uint16_t* __restrict__ dnext, const uint16_t* __restrict__ a,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
-                                     float* __restrict__ sums, int N, int H, int W, int C, int mode, int split) {
+                                     float* __restrict__ sums, int N, int H, int W, int C, int mode, int split, float slope) {
     // blockIdx.y = pass of a merged batch: images [0, split) or [split, N); mean / invstd are [2][C], sums [2][2][C]
     extern __shared__ float s_red[];                 // [rows][2][C]
     const int groups = C >> 3, rows = blockDim.x / groups;
@@ -171,7 +174,7 @@ __global__ void bn_bwd_reduce_kernel(const uint16_t* __restrict__ dnext, const u
     const size_t npix = pass == 0 && gridDim.y > 1 ? static_cast<size_t>(split) * H * W : static_cast<size_t>(N) * H * W;
     mean += pass * C;
     invstd += pass * C;
-    sums += pass * 2 * C;
+    sums += pass * BN_SUMS * C;
     float mu[8], is[8], a1[8], a2[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -221,14 +224,21 @@ __global__ void bn_bwd_apply_kernel(const uint16_t* __restrict__ dnext, const ui
                                     const float* __restrict__ gamma, const float* __restrict__ sums, float count,
                                     float count1, int split,
                                     float slope, uint16_t* __restrict__ g_out, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, int N, int H, int W, int C, int mode) {
+                                    float* __restrict__ dbeta, float* __restrict__ dbias_conv, int N, int H, int W, int C,
+                                    int mode) {
     const int groups = C >> 3;
     const size_t total = static_cast<size_t>(N) * H * W * groups;
-    if (blockIdx.x == 0 && dgamma != nullptr)
+    if (blockIdx.x == 0)
         for (int c = threadIdx.x; c < C; c += blockDim.x) {      // both passes of a merged batch share gamma / beta
-            atomicAdd(dgamma + c, sums[C + c] + (split < N ? sums[3 * C + c] : 0.f));
-            atomicAdd(dbeta + c, sums[c] + (split < N ? sums[2 * C + c] : 0.f));
+            const float* s2 = sums + BN_SUMS * C;
+            if (dgamma != nullptr) {
+                atomicAdd(dgamma + c, sums[C + c] + (split < N ? s2[C + c] : 0.f));
+                atomicAdd(dbeta + c, sums[c] + (split < N ? s2[c] : 0.f));
+            }
         }
+    // dbias_conv: this thread's channel group is the same in every iteration (the grid stride is a multiple of C/8), so the
+    // sums of the stored (bf16-rounded) gradients stay in 8 registers; blocks fold them through shared memory at the end.
+    float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         const int g = static_cast<int>(i % groups);
@@ -249,7 +259,7 @@ __global__ void bn_bwd_apply_kernel(const uint16_t* __restrict__ dnext, const ui
         const float cnt = pass ? count1 : count;
         const float* mean_p = mean + pass * C;
         const float* invstd_p = invstd + pass * C;
-        const float* sums_p = sums + pass * 2 * C;
+        const float* sums_p = sums + pass * BN_SUMS * C;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const int c = g * 8 + k;
@@ -258,8 +268,30 @@ __global__ void bn_bwd_apply_kernel(const uint16_t* __restrict__ dnext, const ui
             float gr = __ldg(gamma + c) * is * (dy[k] - __ldg(sums_p + c) / cnt - xh * __ldg(sums_p + C + c) / cnt);
             o[k] = gr * (av[k] > 0.f ? 1.f : slope);
         }
-        reinterpret_cast<uint4*>(g_out)[i] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                        pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        const uint4 pk = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                    pack_bf16x2(o[6], o[7]));
+        reinterpret_cast<uint4*>(g_out)[i] = pk;
+        if (dbias_conv != nullptr) {
+            const uint32_t pw[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { bsum[2 * k] += bf16_lo(pw[k]); bsum[2 * k + 1] += bf16_hi(pw[k]); }
+        }
+    }
+    if (dbias_conv != nullptr) {                     // block-uniform
+        __shared__ float s_b[512];
+        for (int c = threadIdx.x; c < C; c += blockDim.x) s_b[c] = 0.f;
+        __syncthreads();
+        const int g = static_cast<int>((blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) % groups);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = bsum[k];
+            // lanes that share a channel group: lane % groups (groups = 4 .. 64 -> fold the lane bits above log2(groups))
+            for (int off = 16; off >= groups && off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (groups >= 32 || (threadIdx.x & 31) < groups) atomicAdd(&s_b[g * 8 + k], v);
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x)
+            if (s_b[c] != 0.f) atomicAdd(dbias_conv + c, s_b[c]);
     }
 }
 
@@ -269,8 +301,8 @@ __global__ void bn_bwd_accum_kernel(const float* __restrict__ sums, float* __res
                                     float* __restrict__ dbeta, int C, int passes) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) {
-        dgamma[c] += sums[C + c] + (passes > 1 ? sums[3 * C + c] : 0.f);
-        dbeta[c] += sums[c] + (passes > 1 ? sums[2 * C + c] : 0.f);
+        dgamma[c] += sums[C + c] + (passes > 1 ? sums[BN_SUMS * C + C + c] : 0.f);
+        dbeta[c] += sums[c] + (passes > 1 ? sums[BN_SUMS * C + c] : 0.f);
     }
 }
 
@@ -347,81 +379,117 @@ __global__ void head_bwd_data_kernel(const float* __restrict__ dout, const float
 // thread = (pixel, 8-channel group): one 16-byte load of a_in, one 16-byte store of g_in (both coalesced), 72 + 72 FMAs,
 // 72 register accumulators reduced through shared-memory atomics once per block.  (The two-kernel version stored g_in
 // with 2-byte scattered stores and gathered a_in nine times: 1.44 ms of an 8 ms step.)
+// Version 2 (this one): thread = (pixel, 4-channel group), 8 threads per pixel, a tile of 8 rows x 32 pixels per block
+// iteration.  The 10 x 34 window of dlogit = dout * out * (1 - out) that the tile needs is formed ONCE per iteration in shared
+// memory (the first version recomputed the nine neighbours in each of a pixel's four threads from two global loads
+// each), the filter is read from shared memory (16-byte broadcasts) instead of 72 registers, and 36 instead of 72 dW
+// accumulators per thread let three blocks of 256 threads share an SM: the first version ran one block of 190-register
+// threads per SM, 2 warps per scheduler, and took 109 us for 36 images at 12.7 % occupancy (ncu, profiles/r04b_*).
+// Also accumulates dbias_in[c] += sum_p g_in[p][c]: the bias gradient of the conv that produced a_in (dec.12), so that no
+// separate column-sum pass over g_in is needed.
+constexpr int HB_PIX = 32;                       // tile width (pixels of a row; W % 32 == 0 not required)
+constexpr int HB_ROWS = 8;                       // tile height: one barrier pair and eight independent a_in loads per thread
 template <bool AF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 head_bwd_fused_kernel(const float* __restrict__ dout, const float* __restrict__ out, const uint16_t* __restrict__ a_in,
                       const float* __restrict__ w /*[9][32]*/, uint16_t* __restrict__ g_in,
-                      float* __restrict__ dw /*[32][9]*/, float* __restrict__ dbias, int N, int H, int W, float slope) {
+                      float* __restrict__ dw /*[32][9]*/, float* __restrict__ dbias, float* __restrict__ dbias_in /*[32] or null*/,
+                      int N, int H, int W, float slope) {
     constexpr int C = 32;
-    __shared__ float sw[9 * C];
-    __shared__ float sdw[9 * C + 1];
-    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) { sw[i] = w[i]; sdw[i] = 0.f; }
-    if (threadIdx.x == 0) sdw[9 * C] = 0.f;
-    __syncthreads();
-    const int g = threadIdx.x & 3;                       // channel group: stays fixed along the grid-stride loop
-    float wreg[9][8], acc[9][8];
+    __shared__ __align__(16) float sw[9 * C];
+    __shared__ float sdw[9 * C + 1 + C];
+    __shared__ float sdl[HB_ROWS + 2][HB_PIX + 2];
+    for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < 9 * C + 1 + C; i += blockDim.x) sdw[i] = 0.f;
+    const int g = threadIdx.x & 7;                       // 4-channel group
+    const int pl = threadIdx.x >> 3;                     // pixel column inside the tile
+    float acc[9][4];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { wreg[t][j] = sw[t * C + g * 8 + j]; acc[t][j] = 0.f; }
-    float accb = 0.f;
-    const uint32_t per_img = static_cast<uint32_t>(H) * W;
-    const size_t total = static_cast<size_t>(N) * per_img * 4;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const size_t pix = i >> 2;
-        const uint32_t n = static_cast<uint32_t>(pix / per_img);
-        const uint32_t r = static_cast<uint32_t>(pix - static_cast<size_t>(n) * per_img);
-        const int y = static_cast<int>(r / static_cast<uint32_t>(W)), x = static_cast<int>(r - static_cast<uint32_t>(y) * W);
-        const size_t nb = static_cast<size_t>(n) * per_img;
-        float dl[9];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
+        for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+    float accb = 0.f, accg[4] = {0.f, 0.f, 0.f, 0.f};
+    const int tiles_x = (W + HB_PIX - 1) / HB_PIX, tiles_y = (H + HB_ROWS - 1) / HB_ROWS;
+    const long long tiles = static_cast<long long>(N) * tiles_y * tiles_x;
+    for (long long tidx = blockIdx.x; tidx < tiles; tidx += gridDim.x) {
+        const int tx = static_cast<int>(tidx % tiles_x);
+        const long long nty = tidx / tiles_x;
+        const int y0 = static_cast<int>(nty % tiles_y) * HB_ROWS;
+        const size_t nb = static_cast<size_t>(nty / tiles_y) * H * W;
+        const int x0 = tx * HB_PIX;
+        __syncthreads();                                  // previous iteration's readers are done (also covers the init above)
+        // (HB_ROWS + 2) x (HB_PIX + 2) window of dlogit = dout * out * (1 - out), formed once per tile
+        for (int e = threadIdx.x; e < (HB_ROWS + 2) * (HB_PIX + 2); e += blockDim.x) {
+            const int r = e / (HB_PIX + 2), cidx = e - r * (HB_PIX + 2);
+            const int yy = y0 + r - 1, xx = x0 + cidx - 1;
             float v = 0.f;
             if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
                 const size_t q = nb + static_cast<size_t>(yy) * W + xx;
                 const float o = __ldg(out + q);
                 v = __ldg(dout + q) * o * (1.f - o);
             }
-            dl[t] = v;
+            sdl[r][cidx] = v;
         }
-        if (g == 0) accb += dl[4];
-        const uint4 araw = __ldg(reinterpret_cast<const uint4*>(a_in) + i);
-        const uint32_t aw[4] = {araw.x, araw.y, araw.z, araw.w};
-        float a[8];
+        const int x = x0 + pl;
+        uint2 araw[HB_ROWS];                              // the tile's activations: all loads in flight before the barrier
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            a[2 * k] = a16_to_f<AF>(static_cast<uint16_t>(aw[k] & 0xFFFFu));
-            a[2 * k + 1] = a16_to_f<AF>(static_cast<uint16_t>(aw[k] >> 16));
+        for (int r = 0; r < HB_ROWS; ++r) {
+            const bool in = (x < W) && (y0 + r < H);
+            araw[r] = in ? __ldg(reinterpret_cast<const uint2*>(a_in + (nb + static_cast<size_t>(y0 + r) * W + x) * C) + g)
+                         : make_uint2(0u, 0u);
         }
-        float gv[8];
+        __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) gv[j] = 0.f;
+        for (int r = 0; r < HB_ROWS; ++r) {
+            if (x >= W || y0 + r >= H) continue;
+            // forward tap t reads a[q + (t/3-1, t%3-1)]; pixel p receives from q = p - off(t): window entry (r + 2 - dy, pl + 2 - dx)
+            float dl[9];
 #pragma unroll
-        for (int t = 0; t < 9; ++t)
+            for (int t = 0; t < 9; ++t) dl[t] = sdl[r + 2 - t / 3][pl + 2 - t % 3];
+            if (g == 0) accb += dl[4];
+            float a[4];
+            a[0] = a16_to_f<AF>(static_cast<uint16_t>(araw[r].x & 0xFFFFu));
+            a[1] = a16_to_f<AF>(static_cast<uint16_t>(araw[r].x >> 16));
+            a[2] = a16_to_f<AF>(static_cast<uint16_t>(araw[r].y & 0xFFFFu));
+            a[3] = a16_to_f<AF>(static_cast<uint16_t>(araw[r].y >> 16));
+            float gv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                gv[j] = fmaf(wreg[t][j], dl[t], gv[j]);
-                acc[t][j] = fmaf(a[j], dl[t], acc[t][j]);
+            for (int t = 0; t < 9; ++t) {
+                const float4 wv = *reinterpret_cast<const float4*>(&sw[t * C + g * 4]);
+                gv[0] = fmaf(wv.x, dl[t], gv[0]); gv[1] = fmaf(wv.y, dl[t], gv[1]);
+                gv[2] = fmaf(wv.z, dl[t], gv[2]); gv[3] = fmaf(wv.w, dl[t], gv[3]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[t][j] = fmaf(a[j], dl[t], acc[t][j]);
             }
-        uint32_t pk[4];
+            // the stored (bf16-rounded) value is what the weight-gradient GEMM of dec.12 multiplies: sum the rounded values
+            uint32_t pk[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            pk[k] = pack_bf16x2(gv[2 * k] * (a[2 * k] > 0.f ? 1.f : slope), gv[2 * k + 1] * (a[2 * k + 1] > 0.f ? 1.f : slope));
-        reinterpret_cast<uint4*>(g_in)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            for (int k = 0; k < 2; ++k) {
+                const float v0 = gv[2 * k] * (a[2 * k] > 0.f ? 1.f : slope), v1 = gv[2 * k + 1] * (a[2 * k + 1] > 0.f ? 1.f : slope);
+                pk[k] = pack_bf16x2(v0, v1);
+                accg[2 * k] += bf16_lo(pk[k]);
+                accg[2 * k + 1] += bf16_hi(pk[k]);
+            }
+            reinterpret_cast<uint2*>(g_in + (nb + static_cast<size_t>(y0 + r) * W + x) * C)[g] = make_uint2(pk[0], pk[1]);
+        }
     }
-    // lanes with the same channel group (lane & 3): butterfly over lane bits 2..4, then one shared atomic per value
+    // lanes with the same channel group (lane & 7): butterfly over lane bits 3..4, then one shared atomic per value
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
             float v = acc[t][j];
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
             v += __shfl_xor_sync(0xffffffffu, v, 8);
             v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if ((threadIdx.x & 31) < 4) atomicAdd(&sdw[t * C + g * 8 + j], v);
+            if ((threadIdx.x & 31) < 8) atomicAdd(&sdw[t * C + g * 4 + j], v);
         }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float v = accg[j];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if ((threadIdx.x & 31) < 8) atomicAdd(&sdw[9 * C + 1 + g * 4 + j], v);
+    }
     accb = warp_sum(accb);
     if ((threadIdx.x & 31) == 0) atomicAdd(&sdw[9 * C], accb);
     __syncthreads();
@@ -430,6 +498,7 @@ head_bwd_fused_kernel(const float* __restrict__ dout, const float* __restrict__ 
         atomicAdd(dw + c * 9 + t, sdw[i]);               // nn.Conv2d layout [1][C][3][3]
     }
     if (threadIdx.x == 0) atomicAdd(dbias, sdw[9 * C]);
+    if (dbias_in != nullptr && threadIdx.x < C) atomicAdd(dbias_in + threadIdx.x, sdw[9 * C + 1 + threadIdx.x]);
 }
 
 // one warp handles a strip of pixels; lane = channel (C = 32); 9 tap accumulators per lane.

@@ -154,18 +154,32 @@ class PerceptualLoss(nn.Module):
         return val.view(n, 1, 1, 1)
 
     @torch.no_grad()
+    def reference_features(self, reference: torch.Tensor, normalize: bool = True):
+        """Trunk activations of the reference images alone: they depend on the batch only, not on the autoencoder, so the
+        training engine computes them on a second stream while the autoencoder's forward pass runs."""
+        return self._trunk(reference.detach().float().contiguous(), normalize)
+
+    @torch.no_grad()
     def value_and_grad(self, reference: torch.Tensor, synthesized: torch.Tensor, upstream: torch.Tensor,
-                       normalize: bool = True, grad_out: Optional[torch.Tensor] = None):
-        """Per-image distances [N] and d(sum_n upstream[n] * val[n]) / d synthesized  (fp32 [N,1,H,W])."""
+                       normalize: bool = True, grad_out: Optional[torch.Tensor] = None, ref_acts=None):
+        """Per-image distances [N] and d(sum_n upstream[n] * val[n]) / d synthesized  (fp32 [N,1,H,W]).
+        ``ref_acts``: ``reference_features(reference)`` computed earlier (then only the synthesized half runs here)."""
         n = reference.shape[0]
-        imgs = torch.cat([reference.detach().float(), synthesized.detach().float()], dim=0).contiguous()
-        acts = self._trunk(imgs, normalize)
         _, bwd = self._packs()
-        val = torch.zeros(n, dtype=torch.float32, device=imgs.device)
+        if ref_acts is None:
+            imgs = torch.cat([reference.detach().float(), synthesized.detach().float()], dim=0).contiguous()
+            acts = self._trunk(imgs, normalize)
+            ref = [a[:n] for a in acts]
+            syn = [a[n:] for a in acts]
+            dev = imgs.device
+        else:
+            ref = ref_acts
+            syn = self._trunk(synthesized.detach().float().contiguous(), normalize)
+            dev = synthesized.device
+        val = torch.zeros(n, dtype=torch.float32, device=dev)
         g_tap = {}
         for k, ci in enumerate(TAPS):
-            g_tap[ci] = T.lpips_head(acts[ci][:n], acts[ci][n:], self.lins[k], val, upstream, want_grad=True)
-        syn = [a[n:] for a in acts]
+            g_tap[ci] = T.lpips_head(ref[ci], syn[ci], self.lins[k], val, upstream, want_grad=True)
         # walk the trunk backwards on the synthesized half
         g = T.maxpool_bwd(syn[12], None, g_tap[12])                       # relu'(c5_3) * tap gradient
         for i in range(12, 0, -1):

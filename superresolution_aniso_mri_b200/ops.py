@@ -60,7 +60,12 @@ def _dev(t: torch.Tensor):
     if not t.is_cuda:
         raise RuntimeError("aesr_b200 operators run on a CUDA (sm_100a) device only; got a %s tensor -- there is no "
                            "CPU fallback" % t.device)
-    return _lib.lib_for_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx != torch.cuda.current_device():
+        raise RuntimeError("aesr_b200: tensor on cuda:%d but the current device is cuda:%d -- kernels launch on the current "
+                           "device; wrap the call in `with torch.cuda.device(%d):` (one process per GPU is the supported "
+                           "layout)" % (idx, torch.cuda.current_device(), idx))
+    return _lib.lib_for_device(idx)
 
 
 def _stream(t: torch.Tensor) -> int:
@@ -83,6 +88,16 @@ def pack_conv3x3_weight(w: torch.Tensor, transpose_flip: bool = False, dtype: Op
     _lib.check(lib.aesr_pack_conv3x3_weight(w.data_ptr(), out.data_ptr(), cout, cin, int(transpose_flip),
                                             dt_code(dtype), _stream(w)), "pack_conv3x3_weight")
     return out
+
+
+def pack_conv3x3_weight_batch(src_base: torch.Tensor, dst_base: torch.Tensor, jobs_dev: torch.Tensor, max_elems: int) -> None:
+    """All filters of a model in one launch: ``jobs_dev`` int64 [n,6] on the device = (offset in src_base, offset in
+    dst_base, Cout, Cin, transpose_flip, 0) per filter; ``src_base`` fp32 flat parameters, ``dst_base`` 16-bit flat."""
+    lib = _dev(src_base)
+    assert src_base.dtype == torch.float32 and jobs_dev.dtype == torch.int64 and jobs_dev.is_cuda and jobs_dev.is_contiguous()
+    _lib.check(lib.aesr_pack_conv3x3_weight_batch(src_base.data_ptr(), dst_base.data_ptr(), jobs_dev.data_ptr(),
+                                                  jobs_dev.shape[0], int(max_elems), dt_code(dst_base.dtype),
+                                                  _stream(src_base)), "pack_conv3x3_weight_batch")
 
 
 def pack_conv3x3_weight_up2fold(w: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:

@@ -41,9 +41,11 @@ def bn_apply(a, scale, shift, mode, split: int = 0):
     return out
 
 
-def bn_bwd(dnext, a, mean, invstd, gamma, dgamma, dbeta, mode, slope=0.01, sync_world: int = 1, split: int = 0):
+def bn_bwd(dnext, a, mean, invstd, gamma, dgamma, dbeta, mode, slope=0.01, sync_world: int = 1, split: int = 0,
+           dbias_conv: Optional[torch.Tensor] = None):
     """dnext bf16 (grad of pooled / upsampled BN output), a saved activation -> g bf16 [N,H,W,C].
     ``split``: images >= split are the second pass of a merged batch (mean / invstd [2, C]).
+    ``dbias_conv`` [C] += sum over pixels of g (bias gradient of the producing conv; not in SyncBN mode).
     sync_world > 1 (SyncBN parity mode): the per-channel sums are all-reduced between the reduce and apply kernels."""
     lib = _dev(a)
     n, h, w, c = a.shape
@@ -53,12 +55,13 @@ def bn_bwd(dnext, a, mean, invstd, gamma, dgamma, dbeta, mode, slope=0.01, sync_
     g = torch.empty((n, h, w, c), dtype=GRAD_DTYPE, device=a.device)
     sums = torch.empty(passes * 2 * c, dtype=torch.float32, device=a.device)
     n0 = split if passes == 2 else n
+    assert dbias_conv is None or sync_world <= 1
 
     def call(phase, count, count1):
         _lib.check(lib.aesr_bn_bwd(dnext.data_ptr(), a.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gamma.data_ptr(),
-                                   sums.data_ptr(), float(slope), g.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), n,
-                                   h, w, c, mode, dt_code(a.dtype), phase, float(count), float(count1), int(split),
-                                   _stream(a)), "bn_bwd")
+                                   sums.data_ptr(), float(slope), g.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                   _ptr(dbias_conv), n, h, w, c, mode, dt_code(a.dtype), phase, float(count),
+                                   float(count1), int(split), _stream(a)), "bn_bwd")
     with _timed("bn_bwd"):
         if sync_world > 1:
             import torch.distributed as dist
@@ -82,14 +85,15 @@ def mse(a, b, loss_acc, want_grad=False, grad_scale=1.0, grad_out: Optional[torc
     return d
 
 
-def head_bwd(dout, out, a_in, w9c, dw9c, dbias, slope=0.01):
+def head_bwd(dout, out, a_in, w9c, dw9c, dbias, slope=0.01, dbias_in: Optional[torch.Tensor] = None):
+    """``dbias_in`` [C] += per-channel sums of the returned gradient (bias gradient of the conv that produced a_in)."""
     lib = _dev(a_in)
     n, h, w, c = a_in.shape
     g = torch.empty((n, h, w, c), dtype=GRAD_DTYPE, device=a_in.device)
     with _timed("head_bwd"):
         _lib.check(lib.aesr_head_bwd(dout.data_ptr(), out.data_ptr(), a_in.data_ptr(), w9c.data_ptr(), g.data_ptr(),
-                                     dw9c.data_ptr(), dbias.data_ptr(), n, h, w, c, float(slope), dt_code(a_in.dtype),
-                                     _stream(a_in)), "head_bwd")
+                                     dw9c.data_ptr(), dbias.data_ptr(), _ptr(dbias_in), n, h, w, c, float(slope),
+                                     dt_code(a_in.dtype), _stream(a_in)), "head_bwd")
     return g
 
 

@@ -64,6 +64,7 @@ class TrainForward:
         self.dtype = act_dtype or T.GRAD_DTYPE
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.w_fwd, self.w_bwd = {}, {}
+        self.flat_p, self._pack_plan = None, None
 
 
 class TrainEngine(TrainForward):
@@ -84,6 +85,13 @@ class TrainEngine(TrainForward):
         self.use_graph_dp = os.environ.get("AESR_TRAIN_GRAPH_DP", "0") != "0"
         self._graphs = {}
         self._graph_seen = {}
+        # Weight-gradient GEMMs on a second stream: wgrad(layer k) and the data-gradient chain (dgrad k -> BN backward ->
+        # dgrad k-1 ...) both start from the same output gradient and do not depend on each other; the wgrad launches use
+        # 28-136 CTAs (atomics / MMA cost model), so they fill SMs the short dgrad launches leave idle.  Joined before the
+        # gradient all-reduce / Adam.  AESR_TRAIN_WGRAD_STREAM=0 keeps everything on one stream.
+        self.overlap_wgrad = os.environ.get("AESR_TRAIN_WGRAD_STREAM", "1") != "0"
+        self._side = None
+        self._side_keep = []
         self._flatten()
 
     # ------------------------------------------------------------------ flat parameter / gradient / moment buffers
@@ -129,12 +137,40 @@ class TrainEngine(TrainForward):
 
     # ------------------------------------------------------------------ per-step derived tensors
     def _pack_all(self):
-        self.w_fwd, self.w_bwd = {}, {}
-        for seq in (self.model.enc, self.model.dec):
-            for m in seq:
-                if isinstance(m, ConvHolder) and m.kernel_size == 3 and m.out_channels > 1:
-                    self.w_fwd[id(m)] = ops.pack_conv3x3_weight(m.weight, dtype=self.dtype)
-                    self.w_bwd[id(m)] = ops.pack_conv3x3_weight(m.weight, transpose_flip=True, dtype=T.GRAD_DTYPE)
+        """16-bit [9][Cout][Cin] forward filters and [9][Cin][Cout] mirrored data-gradient filters of every 3x3 conv, re-formed
+        from the current fp32 parameters.  TrainEngine (flat parameter buffer): ONE launch per dtype over a static job
+        table; the forward-only helper packs layer by layer."""
+        if getattr(self, "flat_p", None) is None:
+            self.w_fwd, self.w_bwd = {}, {}
+            for seq in (self.model.enc, self.model.dec):
+                for m in seq:
+                    if isinstance(m, ConvHolder) and m.kernel_size == 3 and m.out_channels > 1:
+                        self.w_fwd[id(m)] = ops.pack_conv3x3_weight(m.weight, dtype=self.dtype)
+                        self.w_bwd[id(m)] = ops.pack_conv3x3_weight(m.weight, transpose_flip=True, dtype=T.GRAD_DTYPE)
+            return
+        if getattr(self, "_pack_plan", None) is None:
+            off_of = {id(p): off for p, (off, _k) in zip(self.params, self.offsets)}
+            convs = [m for seq in (self.model.enc, self.model.dec) for m in seq
+                     if isinstance(m, ConvHolder) and m.kernel_size == 3 and m.out_channels > 1]
+            plan = {}
+            for dtype, kinds in ({self.dtype: (0, 1)} if self.dtype == T.GRAD_DTYPE else
+                                 {self.dtype: (0,), T.GRAD_DTYPE: (1,)}).items():
+                jobs, views, pos = [], [], 0
+                for m in convs:
+                    k = 9 * m.out_channels * m.in_channels
+                    for flip in kinds:
+                        jobs.append([off_of[id(m.weight)], pos, m.out_channels, m.in_channels, flip, 0])
+                        views.append((m, flip, pos, k))
+                        pos += k
+                buf = torch.empty(pos, dtype=dtype, device=self.dev)
+                for m, flip, p0, k in views:
+                    shape = (9, m.in_channels, m.out_channels) if flip else (9, m.out_channels, m.in_channels)
+                    (self.w_bwd if flip else self.w_fwd)[id(m)] = buf[p0:p0 + k].view(shape)
+                plan[dtype] = (buf, torch.tensor(jobs, dtype=torch.int64, device=self.dev),
+                               max(9 * m.out_channels * m.in_channels for m in convs))
+            self._pack_plan = plan
+        for buf, jobs, max_elems in self._pack_plan.values():
+            ops.pack_conv3x3_weight_batch(self.flat_p, buf, jobs, max_elems)
 
     def _bn_train(self, bn: BatchNormHolder, stats: torch.Tensor, count: int, update_running: bool = True,
                   count1: int = 0):
@@ -213,27 +249,62 @@ class TrainEngine(TrainForward):
                     head.bias.detach().float().contiguous())
 
     # ------------------------------------------------------------------ backward passes
-    def _backward_convs(self, recs: List[_ConvRec], g: torch.Tensor, x_img: Optional[torch.Tensor] = None):
+    def _on_side(self, fn, keep=()):
+        """Run ``fn`` on the second stream once everything enqueued so far on the current stream is done."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            out = fn()
+        self._side_keep.append((keep, out))     # keep operands / results alive (allocator reuse) until the join
+        return out
+
+    def _wgrad(self, g, x_in, dW, dbias):
+        if not self.overlap_wgrad or ops.TIMING is not None:
+            T.wgrad3x3(g, x_in, dW, dbias)
+            return
+        self._on_side(lambda: T.wgrad3x3(g, x_in, dW, dbias), keep=(g, x_in))
+
+    def _join_side(self):
+        if self._side is not None and self._side_keep:
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            torch.cuda.current_stream(self.dev).wait_event(ev)
+            self._side_keep.clear()
+
+    def _backward_convs(self, recs: List[_ConvRec], g: torch.Tensor, x_img: Optional[torch.Tensor] = None,
+                        bias_done: bool = False):
         """g: bf16 gradient w.r.t. the LAST conv's pre-activation output.  Returns the gradient w.r.t. the stage input
         (latent for the decoder, nothing for the encoder whose first op is enc.0).  ``g`` may cover only the first
-        images of the saved activations (encoder: enc(slice_between) has no gradient): saved tensors are sliced to it."""
+        images of the saved activations (encoder: enc(slice_between) has no gradient): saved tensors are sliced to it.
+        Bias gradients: the kernel that PRODUCES a layer's output gradient also sums it over the pixels (conv epilogue
+        ``stats_split=-1``, BN backward ``dbias_conv``, head backward ``dbias_in``), so the weight-gradient launch only
+        falls back to its own column-sum pass when nobody did (``bias_done`` tells about the incoming ``g``)."""
         n = g.shape[0]
+        fuse_bn_bias = not (self.sync_bn and self.world > 1)
         for k in range(len(recs) - 1, -1, -1):
             r = recs[k]
             x_in = r.x_in[:n]
-            T.wgrad3x3(g, x_in, self.grad[id(r.conv.weight)], self.grad[id(r.conv.bias)])
+            self._wgrad(g, x_in, self.grad[id(r.conv.weight)], None if bias_done else self.grad[id(r.conv.bias)])
             wt = self.w_bwd[id(r.conv)]
+            db_prev = self.grad[id(recs[k - 1].conv.bias)] if k > 0 else None
             if r.prev == "leaky":
                 prev_rec = recs[k - 1]
                 if prev_rec.bn is not None:
                     raise AssertionError("a conv fed by a BN'd tensor is tagged 'bn'")
-                g = ops.conv3x3(g, wt, None, mul_src=x_in, mul_mode=ops.MUL_LEAKY_GRAD, slope=SLOPE)
+                g = ops.conv3x3(g, wt, None, mul_src=x_in, mul_mode=ops.MUL_LEAKY_GRAD, slope=SLOPE, stats=db_prev,
+                                stats_split=-1)
+                bias_done = True
             elif r.prev == "bn":
                 bnrec = recs[k - 1].bn
                 dnext = ops.conv3x3(g, wt, None)
                 g = T.bn_bwd(dnext, bnrec.a[:n], bnrec.mean, bnrec.invstd, bnrec.bn.weight,
                              self.grad[id(bnrec.bn.weight)], self.grad[id(bnrec.bn.bias)], bnrec.mode, SLOPE,
-                             sync_world=self.world if self.sync_bn else 1, split=bnrec.split if bnrec.split < n else 0)
+                             sync_world=self.world if self.sync_bn else 1, split=bnrec.split if bnrec.split < n else 0,
+                             dbias_conv=db_prev if fuse_bn_bias else None)
+                bias_done = fuse_bn_bias
             elif r.prev == "e0":
                 d_a0 = ops.conv3x3(g, wt, None)
                 e0 = self.model.enc[0]
@@ -245,8 +316,9 @@ class TrainEngine(TrainForward):
 
     def decode_backward(self, ctx, dout: torch.Tensor):
         recs, a1, out, head, w9c = ctx
-        g = T.head_bwd(dout, out, a1, w9c, self.grad[id(head.weight)].view(-1), self.grad[id(head.bias)], SLOPE)
-        return self._backward_convs(recs, g)
+        g = T.head_bwd(dout, out, a1, w9c, self.grad[id(head.weight)].view(-1), self.grad[id(head.bias)], SLOPE,
+                       dbias_in=self.grad[id(recs[-1].conv.bias)])
+        return self._backward_convs(recs, g, bias_done=True)
 
     # ------------------------------------------------------------------ the step
     @torch.no_grad()
@@ -344,6 +416,9 @@ class TrainEngine(TrainForward):
         idx = torch.arange(B, dtype=torch.int32, device=self.dev)
         val = None
         if combined:
+            # (The LPIPS trunk of the reference images depends on the batch only; running it on the second stream under the
+            # autoencoder's forward was measured SLOWER -- 2.44 vs 2.39 ms per step: two 12-image trunk passes cost more than
+            # one 24-image pass because the 8x8 / 16x16 layers are launch-bound -- so both halves stay one batch.)
             # enc(x) and enc(slice_between) as one 3B-image pass, dec(z) and dec(z_mix) as another (see module docstring)
             z3, z16, enc_ctx = self.encode_train(torch.cat([x, sb], dim=0), split=2 * B)
             z, z_ref = z3[:2 * B], z3[2 * B:]                 # z_ref: logged only; its pass updated the BN running stats
@@ -378,8 +453,10 @@ class TrainEngine(TrainForward):
             g_z = self.decode_backward(dec_ctx, dout)                     # [2B,h,w,latent] bf16
         handle_dec = None
         if self.world > 1:                                                # decoder grads are final: reduce them now
+            self._join_side()
             handle_dec = dist.all_reduce(self.flat_g[self.enc_numel:], op=dist.ReduceOp.AVG, async_op=True)
         self._backward_convs(enc_ctx, g_z, x_img=x)
+        self._join_side()
         if self.world > 1:
             dist.all_reduce(self.flat_g[:self.enc_numel], op=dist.ReduceOp.AVG)
             handle_dec.wait()
