@@ -1,24 +1,32 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: batched HR-volume synthesis (encode -> interpolate latents -> decode).
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one process per GPU)
-  python bench.py --impl reference --steps K --warmup W    # the reference's CPU algorithm (oracle port) on host cores
+  python bench.py --gpus N --steps K --warmup W [--workload acdc|oasis220|dhcp|dhcp202]   # this repo's sm_100a path
+  python bench.py --impl reference --steps K --warmup W                                    # the reference's CPU algorithm
 
-One "step" = one pass of the hot path over one batch of synthetic volumes: V ACDC-shaped volumes [10,128,128] per GPU,
-num_interpolations = 6 (the generate_hr_volumes.py default) -> V*54 synthesized slices per GPU per step.  The metric
-is BASELINE.json's "synthesized HR slices/sec"; `value` has the inputs resident in HBM, `e2e` goes through the public
-host-buffer API (pinned host volumes in, HR volumes back to pinned host memory, copies inside the timed region).
-Prints ONE JSON line on rank 0.
+One "step" = one pass of the hot path over one batch of synthetic volumes.  Workloads (BASELINE.json configs):
+  acdc     (default; configs 1 / 5)  V=64 ACDC-shaped volumes [10,128,128] per GPU, num_interpolations 6
+  oasis220 (config 3)                V=16 OASIS evaluation volumes, 45 kept slices of 220x220, downsample_steps 4
+  dhcp     (config 4)                V=8 dHCP volumes, 34 kept slices of 256x256, downsample_steps 4
+  dhcp202  (the reference's only published timing, notebooks/evaluate_brain.ipynb:229,240)  ONE call of
+           evaluate.common.create_super_volume on [202,256,256], downsample_steps 6, use_original=False
+The metric is BASELINE.json's "synthesized HR slices/sec"; `value` has the inputs resident in HBM, `e2e` goes through the
+public host-buffer API (pinned host volumes in, HR volumes back to pinned host memory, copies inside the timed region).
+Prints ONE JSON line on rank 0.  The oracle (oracle/) is used here for seeded inputs, as the parity CHECKER of the
+benchmarked build (`parity`), and as the timed thing only in the baseline legs (`cpu_baseline`, `gpu_eager_baseline`,
+`--impl reference`) -- never on the product path.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
 import sys
 import threading
 import time
+from collections import OrderedDict
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -28,15 +36,46 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "synthesized_hr_slices_per_sec"
-Z, SIZE, NI = 10, 128, 6
-# algorithmic conv FLOPs (2*MAC) of the reference's formulation, per image (ACDC scales=2 @128^2)
-ENC_GMAC, DEC_GMAC = 0.7722, 0.3822
-STEM_GMAC = (32 * 130 * 130 + 9 * 32 * 32 * 130 * 130) / 1e9      # enc.0 + enc.1 (folded into the CUDA-core stem kernel)
+# kept (low-resolution) slices per volume, in-plane size, interpolations per pair, volumes per GPU per step
+WORKLOADS = {
+    "acdc": dict(Z=10, size=128, ni=6, V=64, use_original=True,
+                 what="batched HR volume generation: %(V)d ACDC-shaped volumes [10,128,128] per GPU per step, "
+                      "num_interpolations=6 (generate_hr_volumes.py default)"),
+    "oasis220": dict(Z=45, size=220, ni=3, V=16, use_original=True,
+                     what="OASIS HR volume generation: %(V)d volumes per GPU per step, 45 kept slices of 220x220 "
+                          "(177 slices at downsample_steps=4), 3 synthesized slices per pair"),
+    "dhcp": dict(Z=34, size=256, ni=3, V=8, use_original=True,
+                 what="dHCP HR volume generation: %(V)d volumes per GPU per step, 34 kept slices of 256x256 "
+                      "(downsample_steps=4), 3 synthesized slices per pair"),
+    "dhcp202": dict(Z=202, size=256, ni=5, V=1, use_original=False, ds=6,
+                    what="the reference's published call: evaluate.common.create_super_volume on ONE dHCP volume "
+                         "[202,256,256], downsample_steps=6, use_original=False, generate_inbetween_slices=True "
+                         "(notebooks/evaluate_brain.ipynb:229,240: 638 ms per call on the authors' GPU)"),
+}
+PUBLISHED_DHCP202_MS = 638.0
 
 
-def flops_per_step(V: int) -> float:
-    """Minimal-work count: every slice encoded once, every synthesized slice decoded once."""
-    return 2e9 * (V * Z * ENC_GMAC + V * (Z - 1) * NI * DEC_GMAC)
+def layer_macs(size: int):
+    """Per-image MACs of the scales=2 ae_combined network at in-plane size `size`, by layer."""
+    p0 = (size + 2) ** 2
+    s1 = (size + 2) // 2
+    s2 = s1 // 2
+    enc = {"enc.0": 32 * p0, "enc.1": 9 * 32 * 32 * p0, "enc.3": 9 * 32 * 32 * p0, "enc.7": 9 * 32 * 64 * s1 * s1,
+           "enc.9": 9 * 64 * 64 * s1 * s1, "enc.13": 9 * 64 * 128 * s2 * s2, "enc.15": 9 * 128 * 128 * s2 * s2}
+    dec = {"dec.0": 9 * 128 * 64 * s2 * s2, "dec.2": 9 * 64 * 64 * s2 * s2, "dec.6": 9 * 64 * 32 * 4 * s2 * s2,
+           "dec.8": 9 * 32 * 32 * 4 * s2 * s2, "dec.12": 9 * 32 * 32 * 16 * s2 * s2, "dec.14": 9 * 32 * 16 * s2 * s2}
+    return enc, dec, (p0, s1, s2)
+
+
+def conv_launch_bytes(size: int):
+    """Algorithmic bytes (DESIGN.md section 3, 16-bit activations) of the conv launches: per encoded slice (enc.3 .. enc.15 +
+    dec.0 on the latent, fp32 out) and per synthesized slice (dec.2 .. dec.12+head, fp32 partial sums out)."""
+    _, _, (p0, s1, s2) = layer_macs(size)
+    l2, l1 = s2 * s2, 4 * s2 * s2
+    enc = (p0 * 64 + s1 * s1 * 64) + (s1 * s1 * 64 + s1 * s1 * 128) + (s1 * s1 * 128 + l2 * 128) + (l2 * 128 + l2 * 256) + \
+          (l2 * 256 + l2 * 256) + (l2 * 256 + l2 * 256)
+    dec = (l2 * 128 + l2 * 128) + (l2 * 128 + l1 * 64) + (l1 * 64 + l1 * 64) + (l1 * 64 + l1 * 64)
+    return enc, dec
 
 
 def load_peaks():
@@ -47,6 +86,16 @@ def load_peaks():
         return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
                 "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def csrc_hash() -> str:
+    """Hash of the kernel sources the loaded .so was built from (stamps ncu-derived numbers to a build)."""
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "superresolution_aniso_mri_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:12]
 
 
 class ClockSampler(threading.Thread):
@@ -124,58 +173,174 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "power_w_max": max(r[2] for r in self.rows) / 1e3, "how": self.how}
 
 
+# ---------------------------------------------------------------------------------------------- checkpoints / inputs
+def trained_state():
+    """The checkpoint trained by the reference itself (tests/golden/trained_ckpt.npz, oracle/make_golden.py::gold_trained):
+    scales=2 architecture, fully convolutional -> every workload uses it."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "trained_ckpt.npz"), allow_pickle=False)
+    st = OrderedDict()
+    for k in g.files:
+        if k.startswith("state__"):
+            st[k[len("state__"):]] = torch.from_numpy(g[k].copy())
+    return st
+
+
+def workload_volumes(wl, V, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(V, wl["Z"], wl["size"], wl["size"], generator=g)
+
+
 # ---------------------------------------------------------------------------------------------- reference arm (CPU)
-def cpu_synthesis_rate(sample_volumes: int, repeats: int):
+CPU_SAMPLE_VOLUMES = 2
+
+
+def cpu_sample(wl):
+    """Bounded CPU sample of a workload: CPU_SAMPLE_VOLUMES volumes of at most 10 kept slices (the reference's loop is linear
+    in slice pairs, so the rate per synthesized slice does not depend on the depth)."""
+    Zc = min(wl["Z"], 10) if "ds" not in wl else 13
+    return Zc
+
+
+def cpu_synthesis_rate(wl, repeats: int):
     """The reference's algorithm for the path (generate_hr_volumes.create_super_volume as written: both neighbours
-    re-encoded for every alpha) restated in oracle/aesr_oracle.py, on all host threads torch will use."""
+    re-encoded for every alpha; evaluate.common's twin for dhcp202) restated in oracle/aesr_oracle.py, on all host threads
+    torch will use.  ONE method for both the `cpu_baseline` key and `--impl reference`: CPU_SAMPLE_VOLUMES volumes per
+    repeat, one untimed warm-up, MEAN rate over the repeats."""
     from oracle import aesr_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    args = O.default_args(SIZE, 32)
-    state = O.init_state(args, seed=892372)
-    ar = O.alpha_range_for(NI)
-    vols = [O.synthetic_volume(Z, SIZE, seed=1 + i) for i in range(sample_volumes)]
-    O.create_super_volume(state, args, vols[0], ar, use_original=True)        # warm-up
-    best = float("inf")
+    args = O.default_args(64, 16)
+    state = trained_state()
+    ar = O.alpha_range_for(wl["ni"])
+    Zc, size = cpu_sample(wl), wl["size"]
+    vols = [O.synthetic_volume(Zc, size, seed=1 + i) for i in range(CPU_SAMPLE_VOLUMES)]
+
+    def one(v):
+        if "ds" in wl:
+            out = O.create_super_volume_eval(state, args, v[:, 0], ar, use_original=False, downsample_steps=wl["ds"],
+                                             generate_inbetween_slices=True)
+            return out.shape[0] - (Zc - 1) % wl["ds"]            # synthesized + reconstructed slices (the tail is a copy)
+        O.create_super_volume(state, args, v, ar, use_original=True)
+        return (Zc - 1) * wl["ni"]
+    n_slices = one(vols[0])                                       # warm-up
+    rates, secs = [], []
     for _ in range(repeats):
         t0 = time.perf_counter()
         for v in vols:
-            O.create_super_volume(state, args, v, ar, use_original=True)
-        best = min(best, time.perf_counter() - t0)
-    return sample_volumes * (Z - 1) * NI / best, torch.get_num_threads(), best
+            one(v)
+        dt = time.perf_counter() - t0
+        secs.append(dt)
+        rates.append(CPU_SAMPLE_VOLUMES * n_slices / dt)
+    desc = "%d volumes of %d slices %dx%d (%d slices out) per repeat, mean of %d repeats after 1 warm-up, %.2f s per repeat; " \
+           "oracle port of %s" % (CPU_SAMPLE_VOLUMES, Zc, size, size, CPU_SAMPLE_VOLUMES * n_slices, repeats, float(np.mean(secs)),
+                                  "evaluate.common.create_super_volume" if "ds" in wl else
+                                  "generate_hr_volumes.create_super_volume (re-encodes per alpha like the reference)")
+    return float(np.mean(rates)), torch.get_num_threads(), desc
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 2
+    wl = WORKLOADS[a.workload]
     t0 = time.perf_counter()
-    for _ in range(a.warmup):
-        cpu_synthesis_rate(1, 1)
-    rates = []
-    for _ in range(a.steps):
-        r, cores, _ = cpu_synthesis_rate(sample, 1)
-        rates.append(r)
+    value, cores, desc = cpu_synthesis_rate(wl, max(1, a.steps))
     wall = time.perf_counter() - t0
-    value = float(np.mean(rates))
+    per_step = CPU_SAMPLE_VOLUMES * ((cpu_sample(wl) - 1) * wl["ni"])
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * sample * (Z - 1) * NI / value,
+            "steps": a.steps, "warmup": 1, "ms_per_step": 1e3 * per_step / value,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ACDC-shaped volumes [10,128,128], num_interpolations=6, ae_combined scales=2 "
-                                   "(width 128, latent_width 32, latent 128)", "sample": "%d volumes per step" % sample},
-            "cpu_baseline": {"value": value, "unit": "slices/s", "cores": cores, "kind": "port",
-                             "sample": "%d volumes (%d synthesized slices) per step, %d steps, oracle port of "
-                                       "generate_hr_volumes.create_super_volume" % (sample, sample * 54, a.steps)},
+            "config": {"workload": a.workload + ": " + wl["what"] % {"V": CPU_SAMPLE_VOLUMES}, "sample": desc},
+            "cpu_baseline": {"value": value, "unit": "slices/s", "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": value, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": wall}
     print(json.dumps(line), file=JSON_OUT, flush=True)
 
 
+# ---------------------------------------------------------------------------------------------- same-box GPU bar (library eager)
+def gpu_eager_baseline(dev, wl, train: bool):
+    """SURVEY 2.2 / BASELINE.md 4.5: the reference's algorithm as eager PyTorch (ATen / cuDNN) on the SAME B200 -- the oracle's
+    torch ops with the tensors on the GPU.  Three arithmetic settings: fp32 with TF32 off, fp32 with PyTorch's default
+    (cuDNN TF32 allowed: what the unmodified reference would run), and bf16 autocast with channels_last (the fair library
+    comparison for a 16-bit kernel).  Inference: the reference loop as written AND a minimal-work batched formulation
+    (every slice encoded once, all alphas decoded in one batch).  Training: the reference step (autograd + Adam)."""
+    from oracle import aesr_oracle as O
+    from oracle.make_golden import acdc_batch
+    args = O.default_args(64, 16)
+    st = OrderedDict((k, v.to(dev)) for k, v in trained_state().items())
+    ar = O.alpha_range_for(wl["ni"])
+    Zc = cpu_sample(wl)
+    nv = 4
+    vols = [O.synthetic_volume(Zc, wl["size"], seed=1 + i).to(dev) for i in range(nv)]
+    hi, lo = O.interp_weights(ar)
+    res = {"what": "oracle torch ops (ATen/cuDNN eager) on this GPU; %d volumes of %d slices %dx%d" % (nv, Zc, wl["size"], wl["size"])}
+
+    def as_written():
+        for v in vols:
+            O.create_super_volume(st, args, v, ar, use_original=True)
+
+    def batched():
+        x = torch.cat(vols, dim=0)
+        z = O.encode(st, args, x).view(nv, Zc, 128, *([(wl["size"] + 2) // 4] * 2))
+        zs = torch.stack([float(h) * z[:, 1:] + float(l) * z[:, :-1] for h, l in zip(hi, lo)], dim=2)
+        O.decode(st, args, zs.reshape(-1, *z.shape[2:]))
+
+    def timeit(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps
+
+    n_syn = nv * (Zc - 1) * wl["ni"]
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        with torch.no_grad():
+            for tag, tf32, amp in (("fp32_tf32_off", False, None), ("fp32_tf32_default", True, None),
+                                   ("bf16_autocast_channels_last", True, torch.bfloat16)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                if amp is not None:
+                    vols_cl = [v.contiguous(memory_format=torch.channels_last) for v in vols]
+                    keep, vols[:] = list(vols), vols_cl
+                    with torch.autocast("cuda", dtype=amp):
+                        r = {"as_written_slices_per_s": n_syn / timeit(as_written), "batched_slices_per_s": n_syn / timeit(batched)}
+                    vols[:] = keep
+                else:
+                    r = {"as_written_slices_per_s": n_syn / timeit(as_written), "batched_slices_per_s": n_syn / timeit(batched)}
+                res[tag] = r
+        if train:
+            d = np.load(os.path.join(ROOT, "superresolution_aniso_mri_b200", "data", "lpips_vgg_lin_v0_1.npz"))
+            lins = [torch.from_numpy(d["lin%d" % i]).to(dev) for i in range(5)]
+            vgg = [(w.to(dev), b.to(dev)) for w, b in O.init_vgg(3)]
+            img, mid = (t.to(dev) for t in acdc_batch(0))
+            for tag, tf32, amp in (("fp32_tf32_off", False, None), ("fp32_tf32_default", True, None),
+                                   ("bf16_autocast_channels_last", True, torch.bfloat16)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                stt = OrderedDict((k, v.clone()) for k, v in st.items())
+                adam = O.AdamState(stt, lr=1e-5)
+                x, m = (img, mid) if amp is None else (img.contiguous(memory_format=torch.channels_last),
+                                                       mid.contiguous(memory_format=torch.channels_last))
+
+                def step():
+                    if amp is None:
+                        O.train_step(stt, args, adam, x, m, vgg, lins, ex_loss_weight=0.05)
+                    else:
+                        with torch.autocast("cuda", dtype=amp):
+                            O.train_step(stt, args, adam, x, m, vgg, lins, ex_loss_weight=0.05)
+                res[tag]["train_samples_per_s"] = 12.0 / timeit(step, reps=5)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    return res
+
+
 # ---------------------------------------------------------------------------------------------- this repo's arm (GPU)
 def run_ours(a):
     import torch.distributed as dist
-    from oracle import aesr_oracle as O          # synthetic inputs / seeded weights only (never computes on this arm)
-    from superresolution_aniso_mri_b200 import _lib, ops, synthesis
+    from oracle import aesr_oracle as O          # seeded inputs + the parity checker (never the product path)
+    from superresolution_aniso_mri_b200 import _lib, ops, parallel, synthesis
     from superresolution_aniso_mri_b200.networks.acai_vanilla import VanillaACAI
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,6 +350,7 @@ def run_ours(a):
         raise RuntimeError("bench.py needs a B200 GPU; there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = parallel.bind_to_gpu_numa(local) if world > 1 else None     # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from superresolution_aniso_mri_b200 import build
@@ -192,34 +358,19 @@ def run_ours(a):
         build.build_library()
     if world > 1:
         dist.barrier()
-    V = a.volumes
-    args = O.default_args(SIZE, 32)
+    wl = dict(WORKLOADS[a.workload])
+    V = a.volumes if a.volumes else wl["V"]
+    Z, SIZE, NI = wl["Z"], wl["size"], wl["ni"]
+    args = O.default_args(64, 16)
     margs = dict(args)
     margs["device"] = str(dev)
     torch.manual_seed(892372)
     model = VanillaACAI(margs)
-    model.load_state_dict(O.calibrated_state(args))      # seeded synthetic checkpoint with O(1) activations
+    state = trained_state()
+    model.load_state_dict(state)
     model.eval()
     ar = O.alpha_range_for(NI)
-    g = torch.Generator().manual_seed(100 + rank)
-    host_in = torch.rand(V, Z, SIZE, SIZE, generator=g).pin_memory()
-    dev_in = host_in.to(dev)
-    Zo = (Z - 1) * (NI + 1) + 1
-    dev_out = torch.empty(V, Zo, SIZE, SIZE, device=dev)
-    host_out = torch.empty(V, Zo, SIZE, SIZE).pin_memory()
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)          # 256 MB > 126 MB L2
-
-    def step_device():
-        synthesis.synthesize_volumes(model, dev_in, ar, use_original=True, out=dev_out,
-                                     decode_chunk=a.chunk, encode_chunk=a.chunk)
-
-    pipe = synthesis.HostPipeline(model, V, Z, SIZE, SIZE, ar, groups=a.groups, chunk=a.chunk)
-
-    def step_host():
-        # a stream of batches through the public host-buffer API: every step uploads its volumes from pinned host
-        # memory and downloads its HR volumes; the copies of step i overlap the compute of step i+1, and the timed
-        # region ends only after the LAST step's results are in host memory (pipe.wait() below)
-        pipe.run(host_in, host_out, wait=False)
 
     def barrier():
         torch.cuda.synchronize()
@@ -244,6 +395,49 @@ def run_ours(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    extra = {}
+    if a.workload == "dhcp202":
+        # ---- one call of the evaluation twin per step, the reference's own call signature
+        ds = wl["ds"]
+        host_vol = workload_volumes(wl, 1, 100 + rank)[0].pin_memory()
+        dev_vol = host_vol.to(dev)
+        kept = (Z - 1) // ds + 1
+        slices_out = (kept - 1) * NI + kept                      # synthesized + reconstructed (use_original=False)
+        slices_per_step = world * slices_out
+
+        def step_device():
+            synthesis.create_super_volume_eval(model, dev_vol, ar, use_original=False, downsample_steps=ds,
+                                               generate_inbetween_slices=True, keep_on_device=True)
+
+        def step_host():
+            out = synthesis.create_super_volume_eval(model, host_vol, ar, use_original=False, downsample_steps=ds,
+                                                     generate_inbetween_slices=True)["upsampled_image"]
+            assert not out.is_cuda and out.shape[0] == Z
+        h2d_bytes, d2h_bytes = kept * SIZE * SIZE * 4, slices_out * SIZE * SIZE * 4
+        n_enc, n_dec = kept, slices_out
+        pipe = None
+    else:
+        host_in = workload_volumes(wl, V, 100 + rank).pin_memory()
+        dev_in = host_in.to(dev)
+        Zo = (Z - 1) * (NI + 1) + 1
+        dev_out = torch.empty(V, Zo, SIZE, SIZE, device=dev)
+        host_out = torch.empty(V, Zo, SIZE, SIZE).pin_memory()
+        slices_per_step = world * V * (Z - 1) * NI
+
+        def step_device():
+            synthesis.synthesize_volumes(model, dev_in, ar, use_original=True, out=dev_out,
+                                         decode_chunk=a.chunk, encode_chunk=a.chunk)
+
+        pipe = synthesis.HostPipeline(model, V, Z, SIZE, SIZE, ar, groups=a.groups, chunk=a.chunk)
+
+        def step_host():
+            # a stream of batches through the public host-buffer API: every step uploads its volumes from pinned host
+            # memory and downloads its HR volumes; the copies of step i overlap the compute of step i+1, and the timed
+            # region ends only after the LAST step's results are in host memory (pipe.wait() below)
+            pipe.run(host_in, host_out, wait=False)
+        h2d_bytes, d2h_bytes = pipe.h2d_bytes, pipe.d2h_bytes
+        n_enc, n_dec = V * Z, V * (Z - 1) * NI
+
     for _ in range(max(a.warmup, 3)):
         step_device()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -253,30 +447,34 @@ def run_ours(a):
     ms_total = timed(step_device, a.steps, True)
     launches = (_lib.launch_count() - l0)
     clocks = sampler.stop() if sampler else None
-    slices_per_step = world * V * (Z - 1) * NI
     value = slices_per_step * a.steps / (ms_total * 1e-3)
 
-    # ---- e2e: pinned host volumes -> HR volumes in pinned host memory, H2D/D2H inside the timed region
+    # ---- e2e: host volumes -> HR volumes in host memory, H2D/D2H inside the timed region
     for _ in range(max(a.warmup, 3)):
         step_host()
-    pipe.wait()
+    if pipe is not None:
+        pipe.wait()
     barrier()
-    t0 = time.perf_counter()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
     e_start.record()
     for _ in range(a.steps):
         step_host()
-    pipe.wait()
+    if pipe is not None:
+        pipe.wait()
     e_end.record()
     barrier()
-    e2e_ms = torch.tensor([e_start.elapsed_time(e_end)], device=dev, dtype=torch.float64)
+    e2e_ms_dev = e_start.elapsed_time(e_end)
+    e2e_ms_wall = (time.perf_counter() - t0) * 1e3
+    # dhcp202 returns a pageable CPU tensor per call (like the reference): the host-side part is in the wall clock only
+    e2e_ms = torch.tensor([max(e2e_ms_dev, e2e_ms_wall) if pipe is None else e2e_ms_dev], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = slices_per_step * a.steps / (float(e2e_ms.item()) * 1e-3)
-    _ = time.perf_counter() - t0
 
     # ---- roofline of the dominant kernel family (tcgen05 conv3x3), timed per launch with CUDA events, untimed pass
     roof = None
+    parity = None
     if rank == 0:
         peaks = load_peaks()
         ops.TIMING = []
@@ -291,30 +489,34 @@ def run_ours(a):
             kernel_ms[name] = kernel_ms.get(name, 0.0) + e0.elapsed_time(e1)
         ops.TIMING = None
         # ALGORITHMIC FLOPs (reference formulation, minimal-work count: each LR slice encoded once, each
-        # synthesized slice decoded once) of the layers the conv kernel family computes = everything but the stem
-        # (enc.0 + enc.1, a CUDA-core kernel).  The algebraic folds change the EXECUTED MMA work (dec.0 runs once per
-        # LR slice behind the interpolation; folded upsample convs execute the same MACs): reported separately.
-        alg_fl = 2e9 * (V * Z * (ENC_GMAC - STEM_GMAC) + V * (Z - 1) * NI * DEC_GMAC)
-        # algorithmic bytes of the conv launches of a step (DESIGN.md section 3 table, 16-bit activations): per encoded
-        # slice enc.3 .. enc.15 + dec.0 on the latent, per synthesized slice dec.2 .. dec.12+head
-        KB = 1024.0
-        enc_bytes = (1056.25 + 264.06) + (264.06 + 528.13) + (528.13 + 128) + (128 + 256) + (256 + 256) + (256 + 256)
-        dec_bytes = (128 + 128) + (128 + 256) + (256 + 256) + (256 + 256)
-        alg_bytes = KB * (V * Z * enc_bytes + V * (Z - 1) * NI * dec_bytes)
+        # output slice decoded once) of the layers the conv kernel family computes = everything but the stem
+        # (enc.0 + enc.1: warp-level tf32 mma.sync kernel, HBM-bound, listed under memory_bound_kernels; its FLOPs are stated,
+        # not counted).  The algebraic folds change the EXECUTED MMA work (dec.0 runs once per LR slice behind the
+        # interpolation; folded upsample convs execute the same MACs): reported separately.
+        emac, dmac, (p0, s1, s2) = layer_macs(SIZE)
+        stem_mac = emac["enc.0"] + emac["enc.1"]
+        alg_fl = 2.0 * (n_enc * (sum(emac.values()) - stem_mac) + n_dec * sum(dmac.values()))
+        enc_b, dec_b = conv_launch_bytes(SIZE)
+        alg_bytes = float(n_enc * enc_b + n_dec * dec_b)
         ach = alg_fl / (conv_ms * 1e-3) / 1e12
-        traffic, traffic_src = None, None
-        # ncu --set full capture of the same conv launches (tools/profile_round.sh): the newest committed summary
+        # operand-bandwidth bound of the tcgen05 SS-mode MMA for this network (measured curve
+        # (4096 + 32 N) / 128 cycles per M=128,K=16 MMA): cycles the EXECUTED MMAs need at that rate / elapsed cycles
+        build_hash = csrc_hash()
+        traffic, traffic_src = None, "no ncu capture of this build (sources %s)" % build_hash
         caps = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_conv_full.json"))
-        if caps:
-            with open(os.path.join(ROOT, "profiles", caps[-1])) as f:
-                traffic = json.load(f)["mean_dram_bytes_per_launch"]
-            traffic_src = "profiles/%s (dram__bytes_read.sum + dram__bytes_write.sum, mean per conv launch)" % caps[-1]
-        # memory-bound kernels of the step against the measured HBM copy bandwidth: algorithmic bytes
-        HW, HWs = SIZE * SIZE, (SIZE + 2) * (SIZE + 2)
-        n_enc, n_syn = V * Z, V * (Z - 1) * NI
-        mem_bytes = {"stem": n_enc * (4 * HW + 64 * HWs),
-                     "lerp": V * (Z - 1) * 2 * 4 * 64 * (HW // 16) + n_syn * 2 * 64 * (HW // 16),
-                     "head": n_syn * (16 * HW + 4 * HW)}
+        for cap in reversed(caps):
+            with open(os.path.join(ROOT, "profiles", cap)) as f:
+                cj = json.load(f)
+            if cj.get("csrc_hash") == build_hash and cj.get("workload", "acdc") == a.workload:
+                traffic = cj["mean_dram_bytes_per_launch"]
+                traffic_src = "profiles/%s (ncu --set full of THIS build, sources %s: dram__bytes_read.sum + " \
+                              "dram__bytes_write.sum, mean per conv launch)" % (cap, build_hash)
+                break
+        HW = SIZE * SIZE
+        n_pairs = n_dec // max(NI, 1)
+        mem_bytes = {"stem": n_enc * (4 * HW + 64 * p0),
+                     "lerp": n_pairs * 2 * 4 * 64 * s2 * s2 + n_dec * 2 * 64 * s2 * s2,
+                     "head": n_dec * (16 * HW + 4 * HW)}
         hbm = []
         for name in ("stem", "lerp", "head"):
             if name in kernel_ms and kernel_ms[name] > 0:
@@ -323,47 +525,103 @@ def run_ours(a):
                             "algorithmic_bytes": mem_bytes[name], "ms": kernel_ms[name], "achieved_gbs": gbs,
                             "frac_of_hbm_peak": gbs / peaks["hbm_gbs"]})
         roof = {"bound": "tensor", "kernel": "conv3x3_halo_kernel (tcgen05, all %d launches of a step)" % n_conv,
-                "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
+                "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+                "peak_source": "%s MEASURED_PEAKS.json bf16_tflops = BURST cuBLAS bf16 figure (the timed region is ~0.1 s at full "
+                               "clocks, not a power-capped seconds-long step)" % peaks["source"],
+                "frac_of_sustained_peak": ach / peaks["bf16_tflops_sustained"],
+                "traffic": traffic, "traffic_source": traffic_src, "csrc_hash": build_hash,
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_conv, 1),
-                "peak_source": "%s MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" % peaks["source"],
                 "conv_ms_per_step": conv_ms, "all_kernels_ms_per_step": all_ms,
                 "conv_share_of_kernel_time": conv_ms / all_ms if all_ms else None,
                 "algorithmic_gflop_per_step": alg_fl / 1e9, "executed_gflop_per_step": conv_fl / 1e9,
+                "stem_gflop_per_step_not_counted": 2.0 * n_enc * stem_mac / 1e9,
                 "executed_tflops": conv_fl / (conv_ms * 1e-3) / 1e12, "kernel_ms": kernel_ms,
                 "memory_bound_kernels": hbm, "hbm_peak_gbs": peaks["hbm_gbs"]}
+        # ---- parity of the benchmarked build / dtype against the oracle (checker use), reference-trained checkpoint
+        pv = O.mri_phantom(4, SIZE, seed=41)
+        par = O.alpha_range_for(2)
+        want = O.create_super_volume(state, args, pv, par, use_original=False)
+        got = synthesis.create_super_volume(model, pv, par, use_original=False)["upsampled_image"]
+        dd = (got - want).abs()
+        parity = {"max_abs_vs_oracle": float(dd.max()), "mean_abs_vs_oracle": float(dd.mean()), "tolerance": 2e-2,
+                  "what": "create_super_volume(use_original=False) of a 4-slice %dx%d phantom, checkpoint trained by the "
+                          "reference (tests/golden/trained_ckpt.npz), fp16 activations / fp32 accumulate vs fp32 oracle" % (SIZE, SIZE)}
 
     train = bench_train(a, dev, rank, world, barrier) if a.train else None
 
     if rank == 0:
-        cpu_rate, cores, cpu_t = cpu_synthesis_rate(a.cpu_sample, 3)
+        if a.extras and a.workload == "acdc":
+            extra["sweep"] = sweep_acdc(a, model, dev, flush)
+        if a.extras:
+            extra["gpu_eager_baseline"] = gpu_eager_baseline(dev, wl, train=a.train and a.workload == "acdc")
+        cpu_rate, cores, cpu_desc = cpu_synthesis_rate(wl, 3)
         line = {"metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": a.steps,
                 "warmup": max(a.warmup, 3), "ms_per_step": ms_total / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16" if ops.DEFAULT_DTYPE == torch.float16 else "bf16",
                 "data": "synthetic",
-                "config": {"workload": "batched HR volume generation: %d ACDC-shaped volumes [10,128,128] per GPU per "
-                                       "step, num_interpolations=6 -> %d synthesized slices/GPU/step; ae_combined "
-                                       "scales=2 (width 128, latent_width 32, latent 128), seeded synthetic checkpoint"
-                                       % (V, V * 54),
+                "config": {"workload": a.workload + ": " + wl["what"] % {"V": V} +
+                                       " -> %d output slices/GPU/step; ae_combined scales=2 (latent 128), checkpoint trained by "
+                                       "the reference on phantoms" % (slices_per_step // world),
                            "volumes_per_gpu": V, "chunk": a.chunk, "l2": "256 MB flush buffer written between steps",
-                           "accumulate": "fp32 (TMEM)", "sharding": "volumes over ranks, no collective"},
-                "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": pipe.h2d_bytes,
-                        "d2h_bytes_per_step": pipe.d2h_bytes, "d2h_note": "synthesized slices only; the kept slices = "
-                        "clamp(input) are written into the pinned output by a host thread inside the timed region"
-                        if pipe.host_kept else "whole HR volumes", "ms_per_step": float(e2e_ms.item()) / a.steps},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-                "cpu_baseline": {"value": cpu_rate, "unit": "slices/s", "cores": cores, "kind": "port",
-                                 "sample": "%d volumes (%d synthesized slices), best of 3, %.2f s; oracle port of "
-                                           "generate_hr_volumes.create_super_volume (re-encodes per alpha like the "
-                                           "reference)" % (a.cpu_sample, a.cpu_sample * 54, cpu_t)}}
+                           "accumulate": "fp32 (TMEM)", "sharding": "volumes over ranks, no collective",
+                           "numa_bound_cores": len(numa_cores) if numa_cores else None},
+                "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": float(e2e_ms.item()) / a.steps,
+                        "d2h_note": ("synthesized slices only; the kept slices = clamp(input) are written into the pinned "
+                                     "output by %d host worker threads inside the timed region" % pipe.host_workers
+                                     if pipe is not None and pipe.host_kept else
+                                     "whole HR volumes" if pipe is not None else
+                                     "one call per step, pageable host tensor in, CPU tensor out (the reference's return type)")},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "parity": parity,
+                "cpu_baseline": {"value": cpu_rate, "unit": "slices/s", "cores": cores, "kind": "port", "sample": cpu_desc}}
+        if a.workload == "dhcp202":
+            line["ms_per_call"] = {"device_resident": ms_total / a.steps, "host_in_host_out": float(e2e_ms.item()) / a.steps,
+                                   "published_reference_ms": PUBLISHED_DHCP202_MS,
+                                   "published_source": "notebooks/evaluate_brain.ipynb:229,240 (the authors' GPU, model unnamed)"}
+        line.update(extra)
         if train is not None:
             line["train"] = train
         print(json.dumps(line), file=JSON_OUT, flush=True)
+        JSON_OUT.flush()
     if world > 1:
+        # graphs that contain NCCL kernels must be gone before the communicator is torn down; a watchdog ends the process if
+        # the teardown still blocks (the JSON line is out already)
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
+
+
+def sweep_acdc(a, model, dev, flush):
+    """BASELINE config 5: 64-512 volumes, downsample_steps 2-6 (num_interpolations = d - 1), device-resident, 5 steps each."""
+    from oracle import aesr_oracle as O
+    from superresolution_aniso_mri_b200 import synthesis
+    out = []
+    for V, ds in ((64, 2), (64, 3), (64, 4), (64, 5), (64, 6), (512, 2), (512, 6)):
+        ni = ds - 1
+        ar = O.alpha_range_for(ni)
+        vols = torch.rand(V, 10, 128, 128, device=dev)
+        res = torch.empty(V, 9 * (ni + 1) + 1, 128, 128, device=dev)
+        for _ in range(2):
+            synthesis.synthesize_volumes(model, vols, ar, use_original=True, out=res, decode_chunk=a.chunk, encode_chunk=a.chunk)
+        ms = 0.0
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            synthesis.synthesize_volumes(model, vols, ar, use_original=True, out=res, decode_chunk=a.chunk, encode_chunk=a.chunk)
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        out.append({"volumes": V, "downsample_steps": ds, "num_interpolations": ni, "ms_per_step": ms / 5,
+                    "slices_per_s": V * 9 * ni * 5 / (ms * 1e-3)})
+        del vols, res
+    return out
 
 
 TRAIN_GFLOP_PER_STEP = 573.0      # BASELINE.md section 3: ACDC B=12 step, reference formulation (2*MAC, convs only)
+SIZE = 128
 
 
 def cpu_train_rate(steps: int = 2):
@@ -384,6 +642,68 @@ def cpu_train_rate(steps: int = 2):
         O.train_step(st, args, adam, img, mid, vgg, lins, ex_loss_weight=0.05)
     dt = (time.perf_counter() - t0) / steps
     return 12.0 / dt, torch.get_num_threads(), dt
+
+
+def dp_check(dev, rank, world):
+    """Data-parallel parity inside the driver's own run: 3 steps of a global batch of 2*world triplets (64x64) sharded over the
+    ranks with SyncBN sums + gradient all-reduce (AVG), against the single-GPU step on the global batch (rank 0, no
+    collectives) -- losses and parameters."""
+    import torch.distributed as dist
+    from oracle import aesr_oracle as O
+    from oracle.make_golden import acdc_batch
+    from superresolution_aniso_mri_b200 import parallel as P
+    from superresolution_aniso_mri_b200.lpips_b200 import PerceptualLoss
+    from superresolution_aniso_mri_b200.networks.acai_vanilla import VanillaACAI
+    from superresolution_aniso_mri_b200.training.engine import TrainEngine
+    args = O.default_args(64, 16)
+    st0 = O.init_state(args, seed=892372)
+    lp = PerceptualLoss(vgg_state=[t for pair in O.init_vgg(3) for t in pair], device=dev)
+    steps, Bg, lr = 3, 2 * world, 1e-5
+
+    def model_from():
+        margs = dict(args)
+        margs["device"] = str(dev)
+        m = VanillaACAI(margs)
+        m.load_state_dict(st0)
+        return m.train()
+    ref_losses, ref_state = [], None
+    if rank == 0:
+        m1 = model_from()
+        e1 = TrainEngine(m1, None)
+        e1.world = 1
+        for s in range(steps):
+            img, mid = acdc_batch(s, B=Bg, size=64)
+            w = torch.full((Bg,), 0.5, device=dev)
+            res = e1.step(img.to(dev), mid.to(dev), w, w, lpips=lp, ex_loss_weight=0.05, lr=lr)
+            ref_losses.append(e1.logged_losses(res)["loss_ae"])
+        ref_state = {k: v.clone() for k, v in m1.state_dict().items()}
+        e1.release_graphs()
+    dist.barrier()
+    m2 = model_from()
+    e2 = TrainEngine(m2, None, sync_bn=True)
+    dp_losses = []
+    for s in range(steps):
+        img, mid = acdc_batch(s, B=Bg, size=64)
+        lb = P.shard_batch_pairs({"image": img, "slice_between": mid}, rank, world)
+        b = lb["slice_between"].shape[0]
+        w = torch.full((b,), 0.5, device=dev)
+        res = e2.step(lb["image"].to(dev), lb["slice_between"].to(dev), w, w, lpips=lp, ex_loss_weight=0.05, lr=lr)
+        t = torch.tensor([e2.logged_losses(res)["loss_ae"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)                    # equal shard sizes: mean of per-rank means = global mean
+        dp_losses.append(float(t.item()) / world)
+    e2.release_graphs()
+    if rank != 0:
+        return None
+    worst = max(abs(x - y) / abs(x) for x, y in zip(ref_losses, dp_losses))
+    sd = m2.state_dict()
+    pdiff = max((sd[k].float() - ref_state[k].float()).abs().max().item() for k in sd
+                if sd[k].dtype.is_floating_point and "running" not in k)
+    rdiff = max((sd[k].float() - ref_state[k].float()).abs().max().item() for k in sd if "running" in k)
+    ok = worst < 2e-3 and pdiff < 2.05 * steps * lr and rdiff < 2e-3
+    return {"ok": bool(ok), "mode": "SyncBN sums + gradient all-reduce (AVG), %d triplets over %d ranks vs one GPU" % (Bg, world),
+            "losses_single": ref_losses, "losses_dp": dp_losses, "max_rel_loss_dev": worst, "max_abs_param_diff": pdiff,
+            "param_diff_bound": 2.05 * steps * lr, "max_abs_running_stat_diff": rdiff,
+            "graph_replay": bool(e2.use_graph and e2.use_graph_dp)}
 
 
 def bench_train(a, dev, rank, world, barrier):
@@ -433,6 +753,9 @@ def bench_train(a, dev, rank, world, barrier):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         out[name] = float(ms.item())
+    graph_replay = bool(eng._graphs)
+    eng.release_graphs()
+    check = dp_check(dev, rank, world) if world > 1 else None
     if rank != 0:
         return None
     ops.TIMING = []
@@ -447,19 +770,25 @@ def bench_train(a, dev, rank, world, barrier):
     ms_step = out["device"] / steps
     ach = TRAIN_GFLOP_PER_STEP / ms_step          # GFLOP / ms = TFLOP/s
     peaks = load_peaks()
-    return {"metric": "train_samples_per_sec", "value": world * 12 * steps / (out["device"] * 1e-3), "unit": "samples/s",
-            "steps": steps, "ms_per_step": ms_step, "scaling": "weak", "dtype": "bf16",
-            "config": {"workload": "ACDC training step: B=12/GPU, 128x128, latent 128, MSE + 0.05*LPIPS-VGG, Adam 1e-5; "
-                                   "gradient all-reduce (NCCL, AVG) over ranks"},
-            "e2e": {"value": world * 12 * steps / (out["e2e"] * 1e-3), "unit": "samples/s",
-                    "h2d_bytes_per_step": 36 * SIZE * SIZE * 4, "d2h_bytes_per_step": 16 + 48,
-                    "ms_per_step": out["e2e"] / steps},
-            "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None,
-                         "note": "whole step (573 algorithmic GFLOP) over step time", "kernel_ms": agg},
-            "cpu_baseline": {"value": cpu_rate, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": "2 steps of B=12 after 1 warm-up, %.2f s/step, oracle port of "
-                                       "AETrainerEndToEnd.train (autograd + Adam)" % cpu_dt}}
+    res = {"metric": "train_samples_per_sec", "value": world * 12 * steps / (out["device"] * 1e-3), "unit": "samples/s",
+           "steps": steps, "ms_per_step": ms_step, "scaling": "weak", "dtype": "bf16", "graph_replay": graph_replay,
+           "config": {"workload": "ACDC training step: B=12/GPU, 128x128, latent 128, MSE + 0.05*LPIPS-VGG, Adam 1e-5; "
+                                  "gradient all-reduce (NCCL, AVG, 3 buckets overlapped with the backward pass) over ranks"},
+           "e2e": {"value": world * 12 * steps / (out["e2e"] * 1e-3), "unit": "samples/s",
+                   "h2d_bytes_per_step": 36 * SIZE * SIZE * 4, "d2h_bytes_per_step": 16 + 48,
+                   "ms_per_step": out["e2e"] / steps},
+           "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["bf16_tflops"], "frac_of_sustained_peak": ach / peaks["bf16_tflops_sustained"],
+                        "traffic": None,
+                        "note": "whole step (573 algorithmic GFLOP) over step time, against the BURST cuBLAS bf16 peak; "
+                                "kernel_ms = per-family CUDA-event sums of one eager step on one stream",
+                        "kernel_ms": agg},
+           "cpu_baseline": {"value": cpu_rate, "unit": "samples/s", "cores": cores, "kind": "port",
+                            "sample": "2 steps of B=12 after 1 warm-up, %.2f s/step, oracle port of "
+                                      "AETrainerEndToEnd.train (autograd + Adam)" % cpu_dt}}
+    if check is not None:
+        res["dp_check"] = check
+    return res
 
 
 JSON_OUT = sys.stdout
@@ -482,13 +811,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--volumes", type=int, default=64, help="volumes per GPU per step")
+    ap.add_argument("--workload", default="acdc", choices=sorted(WORKLOADS))
+    ap.add_argument("--volumes", type=int, default=0, help="volumes per GPU per step (0 = the workload's default)")
     ap.add_argument("--chunk", type=int, default=4096, help="max slices per kernel launch")
     ap.add_argument("--groups", type=int, default=2, help="e2e: volume groups pipelined over copy/compute streams")
-    ap.add_argument("--cpu-sample", type=int, default=4, dest="cpu_sample")
     ap.add_argument("--no-train", action="store_false", dest="train", help="skip the training-step measurement")
+    ap.add_argument("--no-extras", action="store_false", dest="extras",
+                    help="skip the V / downsample_steps sweep and the same-box eager-PyTorch GPU baselines")
     ap.add_argument("--train-steps", type=int, default=30, dest="train_steps")
     a = ap.parse_args()
+    if a.workload != "acdc":
+        a.train = False                      # the training measurement belongs to the default (ACDC) line
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -467,8 +467,8 @@ def lpips_forward(vgg, lins: Sequence[torch.Tensor], pred: torch.Tensor, target:
         target = 2 * target - 1
         pred = 2 * pred - 1
     in0, in1 = target, pred                      # self.model.forward(target, pred)
-    shift = torch.tensor(LPIPS_SHIFT)[None, :, None, None]
-    scale = torch.tensor(LPIPS_SCALE)[None, :, None, None]
+    shift = torch.tensor(LPIPS_SHIFT, device=pred.device)[None, :, None, None]
+    scale = torch.tensor(LPIPS_SCALE, device=pred.device)[None, :, None, None]
     o0 = vgg_taps(vgg, (in0 - shift) / scale)   # 1 -> 3 channel broadcast, lpips/networks_basic.py:99-100
     o1 = vgg_taps(vgg, (in1 - shift) / scale)
     val = None
@@ -536,7 +536,7 @@ def train_step(state, args, adam: Optional[AdamState], image: torch.Tensor, slic
     logs = {"loss_ae_dist": float(loss_dist.detach())}
     if combined:
         if alpha_from is None:
-            a05 = torch.tensor([0.5])[:, None, None, None]
+            a05 = torch.tensor([0.5], device=z.device)[:, None, None, None]
             z_mix = a05 * z[:B] + (1 - a05) * z[B:]
         else:
             z_mix = alpha_from[:, :, None, None] * z[:B] + alpha_to[:, :, None, None] * z[B:]

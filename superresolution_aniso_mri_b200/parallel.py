@@ -8,10 +8,39 @@ mode, the per-channel BatchNorm sums).
 """
 from __future__ import annotations
 
-from typing import Dict, List, Tuple
+import os
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+def bind_to_gpu_numa(device_index: int) -> Optional[List[int]]:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU ``device_index`` (its NUMA node), BEFORE
+    pinned host buffers are allocated: cudaHostAlloc places pages on the allocating thread's node, and a host-buffer
+    pipeline whose staging memory sits behind the other socket's interconnect pays for it on every device->host copy
+    when eight ranks copy at once.  Returns the core list (None when NVML / affinity control is unavailable; nothing
+    is changed then).  Safe to call once per rank at start-up (bench.py, generate_hr_volumes.py under torchrun)."""
+    if not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
 
 
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import collections
 import concurrent.futures
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -170,16 +171,24 @@ class HostPipeline:
     compute of batch i+1 and the only serial parts left are the first upload and the last download."""
 
     def __init__(self, model, V, Z, H, W, alpha_range, groups: int = 2, chunk: int = 4096,
-                 host_kept: Optional[bool] = None, d2h_streams: int = 2):
+                 host_kept: Optional[bool] = None, d2h_streams: int = 2, host_workers: Optional[int] = None):
         self.model, self.ar, self.chunk = model, list(alpha_range), chunk
         if host_kept is None:
-            # The host worker's clamp of the kept slices must stay well below the download time: 0.5 ms per 64-volume step
-            # with 16 intra-op threads, but 10 ms with one (torchrun exports OMP_NUM_THREADS=1 to every rank; the 2- and
-            # 4-GPU runs of profiles/r02l / r02z were bound by it).  With few threads the device writes the kept slices
-            # and whole volumes are downloaded, as before.
-            host_kept = torch.get_num_threads() >= 8
+            host_kept = True
         self.host_kept = bool(host_kept) and len(self.ar) >= 1 and Z >= 2
-        self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=1) if self.host_kept else None
+        # The host workers' clamp of the kept slices must stay well below the download time (0.5 ms per 64-volume step on
+        # 16 threads, 10 ms on one).  torchrun exports OMP_NUM_THREADS=1 to every rank, so torch's intra-op pool cannot be
+        # relied on (the 2- and 4-GPU runs of profiles/r02l / r02z were bound by a single-threaded clamp): the group's
+        # volumes are cut into slabs for an OWN pool of workers -- torch releases the GIL inside clamp, the slabs run in
+        # parallel whatever the intra-op setting.  Workers = the cores this process may use (its share of the box under
+        # one-process-per-GPU affinity), at most 8.
+        try:
+            avail = len(os.sched_getaffinity(0))
+        except AttributeError:
+            avail = os.cpu_count() or 1
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+        self.host_workers = host_workers or max(1, min(8, avail if avail < (os.cpu_count() or 1) else avail // local_world))
+        self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=self.host_workers) if self.host_kept else None
         self.jobs = []
         dev = next(model.parameters()).device
         self.dev = dev
@@ -252,8 +261,11 @@ class HostPipeline:
                 self.out_free[b].record(self.s_out)
                 self._mark("d2h_end", s, self.s_out)
             if self.host_kept:
-                self.jobs.append(self.pool.submit(torch.clamp, host_in[s:e], 0.0, 1.0,
-                                                  out=host_out[s:e, ::len(self.ar) + 1]))
+                step = len(self.ar) + 1
+                k = min(self.host_workers, n)
+                for j in range(k):
+                    a0, a1 = s + j * n // k, s + (j + 1) * n // k
+                    self.jobs.append(self.pool.submit(torch.clamp, host_in[a0:a1], 0.0, 1.0, out=host_out[a0:a1, ::step]))
             self.used[b] = True
         if wait:
             self.wait()
@@ -303,6 +315,15 @@ def latent_space_interp(alpha, trainer, img1, img2, device="cuda", with_labels=F
     return {"inter_image": img.detach().cpu(), "inter_label": None}
 
 
+def _to_host(t: torch.Tensor) -> torch.Tensor:
+    """Device -> host through a PINNED buffer from torch's caching host allocator (one cudaMemcpyAsync at PCIe speed; a
+    pageable ``.cpu()`` of a 50 MB volume takes ~20 ms).  The returned CPU tensor owns its buffer."""
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host
+
+
 @torch.no_grad()
 def create_super_volume(trainer, images: torch.Tensor, alpha_range, use_original: bool = False, labels=None,
                         keep_on_device: bool = False) -> dict:
@@ -317,7 +338,7 @@ def create_super_volume(trainer, images: torch.Tensor, alpha_range, use_original
     vol = images.float().to(dev).unsqueeze(0)
     # the final torch.clamp(0, 1) of the reference (:67) is applied inside the kernels that write `out`
     out = synthesize_volumes(model, vol, alpha_range, use_original=use_original)[0]
-    return {"upsampled_image": out if keep_on_device else out.cpu(), "upsampled_labels": None}
+    return {"upsampled_image": out if keep_on_device else _to_host(out), "upsampled_labels": None}
 
 
 @torch.no_grad()
@@ -326,28 +347,31 @@ def create_super_volume_eval(trainer, images: torch.Tensor, alpha_range=None, us
                              generate_inbetween_slices: bool = False, train_patch_size=None, feature_dict=None,
                              labels=None, keep_on_device: bool = False) -> dict:
     """evaluate/common.py:134-235: optional slice dropping images[::d] after trimming (Z-1) % d tail slices, tail
-    re-appended untouched."""
+    re-appended untouched.  Only the kept slices and the tail cross PCIe on the way in; the volume is assembled on the
+    device and comes back in one pinned copy."""
     if labels is not None or hierarchical:
         raise NotImplementedError("aesr_b200: labels / hierarchical latents are out of scope")
     if generate_inbetween_slices and downsample_steps is None:
         downsample_steps = int(len(alpha_range) + 1)
-    orig_images, orig_num = None, images.shape[0]
+    tail, orig_num = None, images.shape[0]
     if downsample_steps is not None or generate_inbetween_slices:
-        orig_images = images.clone()
-        if (orig_num - 1) % downsample_steps != 0:
-            images = images[:-((orig_num - 1) % downsample_steps)]
+        remain = (orig_num - 1) % downsample_steps
+        if remain != 0:
+            if generate_inbetween_slices:
+                tail = images[-remain:]
+            images = images[:-remain]
         images = images[::downsample_steps]
     if alpha_range is None:
         alpha_range = [0.25, 0.5, 0.75]
-    res = create_super_volume(trainer, images, alpha_range, use_original=use_original, keep_on_device=keep_on_device)
+    res = create_super_volume(trainer, images, alpha_range, use_original=use_original, keep_on_device=True)
     new_volume = res["upsampled_image"]
-    if generate_inbetween_slices and (orig_num - 1) % downsample_steps != 0:
-        remain = (orig_num - 1) % downsample_steps
-        tail = orig_images[-remain:].float().to(new_volume.device)
+    if tail is not None:
+        tail = tail.float().to(new_volume.device)
         if tail.dim() == 4:
             tail = tail[:, 0]
         new_volume = torch.cat([new_volume, torch.clamp(tail, 0, 1.)])
     n_alpha = len(alpha_range)
     pred_alphas = torch.cat([torch.FloatTensor([a]).expand(images.shape[0] - 1) for a in alpha_range]) \
         if n_alpha else None
-    return {"upsampled_image": new_volume, "upsampled_labels": None, "pred_alphas": pred_alphas}
+    return {"upsampled_image": new_volume if keep_on_device else _to_host(new_volume), "upsampled_labels": None,
+            "pred_alphas": pred_alphas}

@@ -82,7 +82,7 @@ class TrainEngine(TrainForward):
         # on 2 x B200 (profiles/r03c_dp_graph_check.txt) the replayed step matches the eager one (DP CHECK OK) and runs at
         # 3.16 instead of 3.47 ms, but dist.destroy_process_group() blocked while the captured graphs were alive -- call
         # release_graphs() before tearing the process group down (that teardown order has not been re-run on a GPU yet).
-        self.use_graph_dp = os.environ.get("AESR_TRAIN_GRAPH_DP", "0") != "0"
+        self.use_graph_dp = os.environ.get("AESR_TRAIN_GRAPH_DP", "1") != "0"
         self._graphs = {}
         self._graph_seen = {}
         # Weight-gradient GEMMs on a second stream: wgrad(layer k) and the data-gradient chain (dgrad k -> BN backward ->
@@ -115,6 +115,15 @@ class TrainEngine(TrainForward):
         enc_params = sum(p.numel() for p in self.model.enc.parameters())
         self.enc_numel = enc_params              # encoder parameters come first (module order)
         self._bind_optimizer_state(adopt=True)
+
+    def _enc_deep_offset(self) -> int:
+        """Offset (in the flat buffers) of the first parameter of the encoder's last two convs (module order = flat order)."""
+        convs = [m for m in self.model.enc if isinstance(m, ConvHolder)]
+        first = convs[-2].weight
+        for p, (off, _k) in zip(self.params, self.offsets):
+            if p is first:
+                return off
+        raise AssertionError("encoder parameter not found in the flat buffer")
 
     def _bind_optimizer_state(self, adopt: bool):
         """Make opt.state[p]['exp_avg' / 'exp_avg_sq'] views of the flat moment buffers so that
@@ -275,13 +284,14 @@ class TrainEngine(TrainForward):
             self._side_keep.clear()
 
     def _backward_convs(self, recs: List[_ConvRec], g: torch.Tensor, x_img: Optional[torch.Tensor] = None,
-                        bias_done: bool = False):
+                        bias_done: bool = False, after_launch=None):
         """g: bf16 gradient w.r.t. the LAST conv's pre-activation output.  Returns the gradient w.r.t. the stage input
         (latent for the decoder, nothing for the encoder whose first op is enc.0).  ``g`` may cover only the first
         images of the saved activations (encoder: enc(slice_between) has no gradient): saved tensors are sliced to it.
         Bias gradients: the kernel that PRODUCES a layer's output gradient also sums it over the pixels (conv epilogue
         ``stats_split=-1``, BN backward ``dbias_conv``, head backward ``dbias_in``), so the weight-gradient launch only
-        falls back to its own column-sum pass when nobody did (``bias_done`` tells about the incoming ``g``)."""
+        falls back to its own column-sum pass when nobody did (``bias_done`` tells about the incoming ``g``).
+        ``after_launch(k)`` is called once everything that writes the gradients of layers >= k has been enqueued."""
         n = g.shape[0]
         fuse_bn_bias = not (self.sync_bn and self.world > 1)
         for k in range(len(recs) - 1, -1, -1):
@@ -305,12 +315,14 @@ class TrainEngine(TrainForward):
                              sync_world=self.world if self.sync_bn else 1, split=bnrec.split if bnrec.split < n else 0,
                              dbias_conv=db_prev if fuse_bn_bias else None)
                 bias_done = fuse_bn_bias
-            elif r.prev == "e0":
+            if after_launch is not None:
+                after_launch(k)
+            if r.prev == "e0":
                 d_a0 = ops.conv3x3(g, wt, None)
                 e0 = self.model.enc[0]
                 T.e0_bwd(d_a0, x_img, self.grad[id(e0.weight)].view(-1), self.grad[id(e0.bias)])
                 return None
-            elif r.prev == "latent":
+            if r.prev == "latent":
                 return ops.conv3x3(g, wt, None)
         return None
 
@@ -451,15 +463,35 @@ class TrainEngine(TrainForward):
             m.invalidate_cache()
             T.mse(z_mix, z_ref, scal[1:2])
             g_z = self.decode_backward(dec_ctx, dout)                     # [2B,h,w,latent] bf16
-        handle_dec = None
-        if self.world > 1:                                                # decoder grads are final: reduce them now
-            self._join_side()
-            handle_dec = dist.all_reduce(self.flat_g[self.enc_numel:], op=dist.ReduceOp.AVG, async_op=True)
-        self._backward_convs(enc_ctx, g_z, x_img=x)
-        self._join_side()
+        # Data parallel: three gradient buckets, each all-reduced (NCCL, AVG) as soon as the launches that write it are
+        # enqueued -- decoder after the decoder backward, the two deepest encoder convs (75 % of the encoder's parameters)
+        # after their weight gradients, the shallow rest at the end (the only exposed one: ~0.3 MB).  The collectives are
+        # enqueued from the second stream (behind the weight-gradient GEMMs, which run there), so the data-gradient chain on
+        # the main stream never waits for them.
+        handles = []
+
+        def reduce_bucket(lo, hi):
+            def run():
+                return dist.all_reduce(self.flat_g[lo:hi], op=dist.ReduceOp.AVG, async_op=True)
+            if self.overlap_wgrad and ops.TIMING is None:
+                handles.append(self._on_side(run))
+            else:
+                handles.append(run())
+
+        deep_lo = self._enc_deep_offset()
         if self.world > 1:
-            dist.all_reduce(self.flat_g[:self.enc_numel], op=dist.ReduceOp.AVG)
-            handle_dec.wait()
+            reduce_bucket(self.enc_numel, self.flat_g.numel())
+
+        def enc_hook(k):
+            if self.world > 1 and k == len(enc_ctx) - 2:                  # enc.13 and enc.15: gradients enqueued
+                reduce_bucket(deep_lo, self.enc_numel)
+
+        self._backward_convs(enc_ctx, g_z, x_img=x, after_launch=enc_hook)
+        if self.world > 1:
+            reduce_bucket(0, deep_lo)
+        self._join_side()
+        for h in handles:
+            h.wait()
 
         if do_update and step_dev is not None:       # graph capture: step count / lr are read from device memory at replay time
             T.adam_step_dev(self.flat_p, self.flat_g, self.flat_m, self.flat_v, lr, betas[0], betas[1], eps, weight_decay,
