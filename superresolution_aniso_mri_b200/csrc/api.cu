@@ -198,6 +198,36 @@ int set_max_smem(K kernel, int* configured) {
     return AESR_OK;
 }
 
+// Split-K workspace: one buffer per device, grown on demand OUTSIDE stream capture (cudaMalloc is not capturable; the
+// training engine's first, eager step of a configuration sizes it before the step is captured).  Kernels of one stream use it
+// one after the other; the weight-gradient side stream never runs split-K convs.
+float* g_splitk_ws[32] = {nullptr};
+size_t g_splitk_bytes[32] = {0};
+int tune(int key);
+int splitk_workspace(size_t need, cudaStream_t stream, float** out) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    dev &= 31;
+    if (g_splitk_bytes[dev] < need) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        CUDA_TRY(cudaStreamIsCapturing(stream, &st));
+        if (st != cudaStreamCaptureStatusNone)
+            return fail(AESR_ERR_INVALID, "conv3x3_fwd: the split-K workspace must grow (%zu bytes) inside a stream capture; "
+                                          "run the same shapes once outside the capture first", need);
+        if (g_splitk_ws[dev]) {
+            CUDA_TRY(cudaDeviceSynchronize());
+            CUDA_TRY(cudaFree(g_splitk_ws[dev]));
+            g_splitk_ws[dev] = nullptr;
+            g_splitk_bytes[dev] = 0;
+        }
+        size_t bytes = need < (size_t(64) << 20) ? (size_t(64) << 20) : need;
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&g_splitk_ws[dev]), bytes));
+        g_splitk_bytes[dev] = bytes;
+    }
+    *out = g_splitk_ws[dev];
+    return AESR_OK;
+}
+
 template <int KC>
 int launch_stream(const void* x, const void* w, ConvParams p, cudaStream_t stream) {
     using S = StreamSmem<KC>;
@@ -216,9 +246,39 @@ int launch_stream(const void* x, const void* w, ConvParams p, cudaStream_t strea
     static int configured = 0;
     rc = set_max_smem(conv3x3_stream_kernel<KC>, &configured);
     if (rc != AESR_OK) return rc;
-    const int grid = p.num_tiles < g_sm_count ? p.num_tiles : g_sm_count;
+    // Split-K: layers with fewer tiles than half the SMs (the 16x16 / 8x8 VGG layers of a 12-24 image batch: 12-96 tiles,
+    // each streaming its whole 9 x Cin filter slab through one SM's L2 port) are cut along K so that ~all SMs take part;
+    // the splits leave raw fp32 accumulators in a workspace and a small kernel adds them and runs the epilogue.
+    p.ksplit = 1;
+    const int KB = 9 * (p.Cin / KC);
+    const bool simple = p.out_mode == OUT_SAME && p.stats == nullptr && p.scale == nullptr && p.out2 == nullptr;
+    if (simple && tune(8) != 1 && p.num_tiles * 2 <= g_sm_count) {
+        int sk = g_sm_count / p.num_tiles;
+        if (sk > KB / 4) sk = KB / 4;                      // at least four K-blocks per split
+        if (sk > 16) sk = 16;
+        if (sk >= 2) p.ksplit = sk;
+    }
+    if (p.ksplit > 1) {
+        const size_t npix = static_cast<size_t>(p.N) * p.H * p.W;
+        const size_t need = static_cast<size_t>(p.ksplit) * npix * p.Cout * sizeof(float);
+        rc = splitk_workspace(need, stream, &p.ws);
+        if (rc != AESR_OK) return rc;
+    }
+    const int items = p.num_tiles * p.ksplit;
+    const int grid = items < g_sm_count ? items : g_sm_count;
+    void* out_final = p.out;
     conv3x3_stream_kernel<KC><<<grid, CONV_THREADS, S::total_bytes(p.BN, stages), stream>>>(tx, tw, p);
-    return check_launch("conv3x3_stream");
+    rc = check_launch("conv3x3_stream");
+    if (rc != AESR_OK || p.ksplit == 1) return rc;
+    const size_t npix = static_cast<size_t>(p.N) * p.H * p.W;
+    const size_t total = npix * (p.Cout / 8);
+    size_t fg = (total + 255) / 256;
+    if (fg > static_cast<size_t>(g_sm_count) * 8) fg = static_cast<size_t>(g_sm_count) * 8;
+    if (p.fp16)
+        splitk_finish_kernel<true><<<static_cast<int>(fg), 256, 0, stream>>>(p.ws, p.ksplit, npix, p.Cout, p.bias, p.act, p.slope, p.mul_src, p.mul_mode, static_cast<uint16_t*>(out_final));
+    else
+        splitk_finish_kernel<false><<<static_cast<int>(fg), 256, 0, stream>>>(p.ws, p.ksplit, npix, p.Cout, p.bias, p.act, p.slope, p.mul_src, p.mul_mode, static_cast<uint16_t*>(out_final));
+    return check_launch("splitk_finish");
 }
 
 // largest N tile (multiple of 32 dividing Cout, <= 256) whose resident filter bank + >= 2 halo stages fit; 0 = none
@@ -238,10 +298,11 @@ int halo_pick_bn(int Cin, int Cout) {
 // 5 = AESR_STEM_CUDA_CORES encoder stem on the CUDA cores (fp32 FMAs) instead of warp-level tf32 mma.sync.
 // 6 = AESR_WGRAD_NO_FOLD weight gradient of Cin = 32 layers with one MMA per tap instead of one per filter row.
 // 7 = AESR_WGRAD_CTAS cap on the CTAs of a weight-gradient launch (each CTA ends with Cout x Cin x taps atomics).
-int g_tune[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+// 8 = AESR_NO_SPLITK streamed conv kernel without split-K (A/B measurements).
+int g_tune[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
 int tune(int key) {
-    static const char* names[8] = {"AESR_CONV_DEBUG", "AESR_CONV_T", "AESR_CONV_NBUF", "AESR_CONV_STAGES", "AESR_HEAD_MMA",
-                                   "AESR_STEM_CUDA_CORES", "AESR_WGRAD_NO_FOLD", "AESR_WGRAD_CTAS"};
+    static const char* names[9] = {"AESR_CONV_DEBUG", "AESR_CONV_T", "AESR_CONV_NBUF", "AESR_CONV_STAGES", "AESR_HEAD_MMA",
+                                   "AESR_STEM_CUDA_CORES", "AESR_WGRAD_NO_FOLD", "AESR_WGRAD_CTAS", "AESR_NO_SPLITK"};
     if (g_tune[key] < 0) g_tune[key] = getenv(names[key]) ? atoi(getenv(names[key])) : 0;
     return g_tune[key];
 }
@@ -357,7 +418,7 @@ int aesr_init(int device) {
 const char* aesr_last_error(void) { return g_err; }
 
 int aesr_set_tuning(int key, int value) {
-    if (key < 0 || key > 7 || value < 0) return fail(AESR_ERR_INVALID, "set_tuning: key %d value %d", key, value);
+    if (key < 0 || key > 8 || value < 0) return fail(AESR_ERR_INVALID, "set_tuning: key %d value %d", key, value);
     g_tune[key] = value;
     return AESR_OK;
 }

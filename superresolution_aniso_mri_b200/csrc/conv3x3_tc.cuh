@@ -87,6 +87,10 @@ struct ConvParams {
     // images >= stats_split (second pass of a merged batch, own BatchNorm statistics) accumulate into stats + 2*Cout
     float* stats;
     int stats_split;
+    // streamed kernel, split-K: work item = (tile, split s), split s accumulates K-blocks [s*KB/ksplit, (s+1)*KB/ksplit) and
+    // stores its raw fp32 accumulators to ws[s][pixel][Cout]; splitk_finish_kernel adds the splits and runs the epilogue.
+    int ksplit;
+    float* ws;
     int stats_sum_only;     // 1: stats is [Cout], only the sums are taken (bias gradient of the layer whose output gradient this
                             // data-gradient launch produces: dbias[c] = sum over pixels of the epilogue's output)
     // OUT_SHUFFLE2_HEAD: fp32 [9][32] filter of the 32 -> 1 head conv, BY VALUE: kernel parameters live in the constant
@@ -421,6 +425,73 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvParams& p, const Co
                 }
             }
         }
+    }
+}
+
+// Split-K epilogue of the streamed kernel: raw fp32 accumulators -> ws[split][pixel][Cout] (no bias / activation).
+__device__ __forceinline__ void conv_epilogue_splitk(const ConvParams& p, uint32_t tmem_acc, uint64_t* tmem_empty_bar,
+                                                     const TileCoord& t, int split) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int py = row >> 3, px = row & 7;
+    const int y = t.y0 + py, x = t.x0 + px;
+    const bool inb = (y < p.H) && (x < p.W);
+    const uint32_t t_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+    const size_t npix = static_cast<size_t>(p.N) * p.H * p.W;
+    const size_t pix = (static_cast<size_t>(t.n) * p.H + y) * p.W + x;
+    float* dst = p.ws + (static_cast<size_t>(split) * npix + pix) * p.Cout + t.n0;
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t raw[16];
+        tmem_ld_32x32b_x16(t_addr + c0, raw);
+        tmem_ld_wait();
+        if (c0 + 16 >= p.BN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar);
+        }
+        if (inb) {
+            float4* o4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4)
+                o4[j4] = make_float4(__uint_as_float(raw[4 * j4]), __uint_as_float(raw[4 * j4 + 1]),
+                                     __uint_as_float(raw[4 * j4 + 2]), __uint_as_float(raw[4 * j4 + 3]));
+        }
+    }
+}
+
+// out[pix][c] = act(sum_s ws[s][pix][c] + bias[c]) * act'(mul_src[pix][c]) -> 16-bit NHWC; one thread = 8 channels of a pixel.
+template <bool AF>
+__global__ void splitk_finish_kernel(const float* __restrict__ ws, int ksplit, size_t npix, int Cout,
+                                     const float* __restrict__ bias, int act, float slope,
+                                     const uint16_t* __restrict__ mul_src, int mul_mode, uint16_t* __restrict__ out) {
+    const int groups = Cout >> 3;
+    const size_t total = npix * groups;
+    const float neg_slope = (act == ACT_LEAKY) ? slope : (act == ACT_RELU) ? 0.f : 1.f;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(i % groups);
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = bias ? __ldg(bias + g * 8 + k) : 0.f;
+        for (int sidx = 0; sidx < ksplit; ++sidx) {
+            const float4* w4 = reinterpret_cast<const float4*>(ws + (static_cast<size_t>(sidx) * npix * Cout) + i * 8);
+            const float4 a = __ldg(w4), b = __ldg(w4 + 1);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], v[k] * neg_slope);
+        if (mul_mode != MUL_NONE) {
+            const uint4 m = __ldg(reinterpret_cast<const uint4*>(mul_src) + i);
+            const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+            const float neg = (mul_mode == MUL_LEAKY_GRAD) ? slope : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[2 * u] *= pos16(w[u] & 0xFFFFu) ? 1.f : neg;
+                v[2 * u + 1] *= pos16(w[u] >> 16) ? 1.f : neg;
+            }
+        }
+        reinterpret_cast<uint4*>(out)[i] = pack8(v, AF ? 1 : 0);
     }
 }
 
@@ -1099,22 +1170,26 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     const int kchunks = p.Cin / KC;
     const int KB = 9 * kchunks;
 
+    // work item = (tile, K split): item / ksplit = tile, item % ksplit = split; ksplit = 1: the whole K range per tile
+    const int ksplit = p.ksplit;
+    const int num_items = p.num_tiles * ksplit;
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int tile = item / ksplit, sp = item - tile * ksplit;
                 const TileCoord t = tile_coord(p, tile / p.n_blocks, tile % p.n_blocks);
-                for (int tap = 0; tap < 9; ++tap) {
+                const int kb0 = sp * KB / ksplit, kb1 = (sp + 1) * KB / ksplit;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const int tap = kb / kchunks, kc = kb - tap * kchunks;
                     const int dy = tap / 3, dx = tap - dy * 3;
-                    for (int kc = 0; kc < kchunks; ++kc) {
-                        mbar_wait(&bars.empty[stage], phase ^ 1);
-                        uint8_t* a_dst = smem + stage * stage_bytes;
-                        mbar_arrive_expect_tx(&bars.full[stage], S::A_BYTES + p.BN * KC * 2);
-                        tma_load_4d(a_dst, &tmap_x, &bars.full[stage], kc * KC, t.x0 + dx - 1, t.y0 + dy - 1, t.n);
-                        tma_load_2d(a_dst + S::A_BYTES, &tmap_w, &bars.full[stage], kc * KC, tap * p.Cout + t.n0);
-                        if (++stage == num_stages) { stage = 0; phase ^= 1; }
-                    }
+                    mbar_wait(&bars.empty[stage], phase ^ 1);
+                    uint8_t* a_dst = smem + stage * stage_bytes;
+                    mbar_arrive_expect_tx(&bars.full[stage], S::A_BYTES + p.BN * KC * 2);
+                    tma_load_4d(a_dst, &tmap_x, &bars.full[stage], kc * KC, t.x0 + dx - 1, t.y0 + dy - 1, t.n);
+                    tma_load_2d(a_dst + S::A_BYTES, &tmap_w, &bars.full[stage], kc * KC, tap * p.Cout + t.n0);
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -1128,18 +1203,20 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             uint32_t acc_phase = 0;
             const uint64_t s_tmpl = make_smem_desc(smem_u32(smem), SBO, LAYOUT);
             const uint32_t s_hi = static_cast<uint32_t>(s_tmpl >> 32), s_lo0 = static_cast<uint32_t>(s_tmpl);
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const int sp = item % ksplit;
+                const int kb0 = sp * KB / ksplit, kb1 = (sp + 1) * KB / ksplit;
                 mbar_wait(&bars.tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * p.BN;
-                for (int kb = 0; kb < KB; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&bars.full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_lo = s_lo0 + stage * (static_cast<uint32_t>(stage_bytes) >> 4);
 #pragma unroll
                     for (int k = 0; k < KC / 16; ++k)   // +32 bytes along K inside the swizzle row
                         umma_f16_split(d_tmem, a_lo + 2 * k, s_hi, a_lo + (S::A_BYTES >> 4) + 2 * k, s_hi, idesc,
-                                       k != 0 ? 1u : static_cast<uint32_t>(kb != 0));
+                                       k != 0 ? 1u : static_cast<uint32_t>(kb != kb0));
                     umma_commit(&bars.empty[stage]);
                     if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
@@ -1152,11 +1229,13 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         const int eset = (warp - CONV_FIRST_EPI_WARP) >> 2;
         if (eset < num_acc) {
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x + eset * gridDim.x; tile < p.num_tiles; tile += gridDim.x * num_acc) {
+            for (int item = blockIdx.x + eset * gridDim.x; item < num_items; item += gridDim.x * num_acc) {
+                const int tile = item / ksplit, sp = item - tile * ksplit;
                 const TileCoord t = tile_coord(p, tile / p.n_blocks, tile % p.n_blocks);
                 mbar_wait(&bars.tmem_full[eset], acc_phase);
                 tc_fence_after();
-                conv_epilogue_tile(p, bars, tmem_base + eset * p.BN, &bars.tmem_empty[eset], t);
+                if (ksplit > 1) conv_epilogue_splitk(p, tmem_base + eset * p.BN, &bars.tmem_empty[eset], t, sp);
+                else conv_epilogue_tile(p, bars, tmem_base + eset * p.BN, &bars.tmem_empty[eset], t);
                 acc_phase ^= 1;
             }
         }
