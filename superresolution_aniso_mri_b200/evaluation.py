@@ -292,20 +292,9 @@ def random_crop(images, patch: int, rs: np.random.RandomState, device="cuda:0") 
     return pad_crop(images, np.array(tops), np.array(lefts), patch, patch, device=device)
 
 
-def augment_batch(images, rs: np.random.RandomState, width: int, aug_patch: Optional[int] = None, center: bool = False,
-                  intensity_first: bool = True, slice_mask=None, device="cuda:0", return_draws: bool = False):
-    """The training transform chain of the reference on a batch [B,C,H,W] of equally sized samples, one kernel:
-    ACDC (train_cardiac_aesr.py:90-96): AdjustToPatchSize(aug) -> CenterCrop(aug) -> RandomCrop(width) -> RandomIntensity
-    -> RandomRotation (``intensity_first=True, center=True``); brains (datasets/common_brains.py:55-57,77-80):
-    [AdjustToPatchSize(aug)] -> RandomCrop(width) -> RandomRotation -> RandomIntensity.  The draws are taken from ``rs``
-    on the host, sample by sample, in exactly the order the reference's transform objects take them
-    (randint(0,h-P), randint(0,w-P) unless the sample already has the crop size; uniform(2.5,7.5), uniform(.25,.75);
-    randint(0,4)), so a seeded RandomState yields the reference's augmentation stream.  ``slice_mask``: boolean per
-    channel (ACDCLBL).  Returns fp32 [B,C,width,width] on ``device`` (and the draws with ``return_draws``)."""
-    x = _as_dev_f32(images, device)
-    lib = _dev(x)
-    b, c, h, w = x.shape
-    # composite window: zero-pad to >= aug_patch (left = floor(d/2)), optional centre crop to aug_patch, random crop
+def augment_window(h: int, w: int, aug_patch: Optional[int], center: bool):
+    """Composite window of AdjustToPatchSize(aug) [-> CenterCrop(aug)]: (offset_y, offset_x, height, width) of the region the
+    random crop is drawn from, in the coordinates of the unpadded h x w sample (zero padding: left = floor(d/2))."""
     off_y = off_x = 0
     hh, ww = h, w
     if aug_patch is not None:
@@ -315,20 +304,50 @@ def augment_batch(images, rs: np.random.RandomState, width: int, aug_patch: Opti
             half = int(aug_patch / 2)
             off_y, off_x = off_y + int(hh / 2) - half, off_x + int(ww / 2) - half
             hh = ww = 2 * half
-    tops, lefts, ks, gains, cuts = [], [], [], [], []
-    for _ in range(b):
-        if hh == width and ww == width:
-            t = l_ = 0
-        else:
-            t = rs.randint(0, hh - width)
-            l_ = rs.randint(0, ww - width)
-        if intensity_first:
-            g, cu = rs.uniform(2.5, 7.5), rs.uniform(0.25, 0.75)
-            k = rs.randint(0, 4)
-        else:
-            k = rs.randint(0, 4)
-            g, cu = rs.uniform(2.5, 7.5), rs.uniform(0.25, 0.75)
-        tops.append(t + off_y), lefts.append(l_ + off_x), ks.append(k), gains.append(g), cuts.append(cu)
+    return off_y, off_x, hh, ww
+
+
+def augment_draw(rs: np.random.RandomState, hh: int, ww: int, width: int, intensity_first: bool):
+    """One sample's draws in the order the reference's transform objects take them: RandomCrop randint(0,h-P),
+    randint(0,w-P) (none when the sample already has the crop size); RandomIntensity uniform(2.5,7.5), uniform(.25,.75);
+    RandomRotation randint(0,4) -- intensity before rotation for ACDC, after it for the brain sets.
+    Returns (top, left, k, gain, cutoff) relative to the window of ``augment_window``."""
+    if hh == width and ww == width:
+        t = l_ = 0
+    else:
+        t = rs.randint(0, hh - width)
+        l_ = rs.randint(0, ww - width)
+    if intensity_first:
+        g, cu = rs.uniform(2.5, 7.5), rs.uniform(0.25, 0.75)
+        k = rs.randint(0, 4)
+    else:
+        k = rs.randint(0, 4)
+        g, cu = rs.uniform(2.5, 7.5), rs.uniform(0.25, 0.75)
+    return t, l_, k, g, cu
+
+
+def augment_batch(images, rs: Optional[np.random.RandomState], width: int, aug_patch: Optional[int] = None,
+                  center: bool = False, intensity_first: bool = True, slice_mask=None, device="cuda:0",
+                  return_draws: bool = False, draws=None):
+    """The training transform chain of the reference on a batch [B,C,H,W] of equally sized samples, one kernel:
+    ACDC (train_cardiac_aesr.py:90-96): AdjustToPatchSize(aug) -> CenterCrop(aug) -> RandomCrop(width) -> RandomIntensity
+    -> RandomRotation (``intensity_first=True, center=True``); brains (datasets/common_brains.py:55-57,77-80):
+    [AdjustToPatchSize(aug)] -> RandomCrop(width) -> RandomRotation -> RandomIntensity.  The draws are taken from ``rs``
+    on the host, sample by sample, in exactly the order the reference's transform objects take them (``augment_draw``),
+    so a seeded RandomState yields the reference's augmentation stream; a caller that interleaves them with other draws
+    (``data_loader.DeviceTripletLoader``: triplet indices, then transforms, per sample like ``__getitem__``) passes them as
+    ``draws`` = B tuples of ``augment_draw``.  ``slice_mask``: boolean per channel (ACDCLBL).  Returns fp32
+    [B,C,width,width] on ``device`` (and the draws with ``return_draws``)."""
+    x = _as_dev_f32(images, device)
+    lib = _dev(x)
+    b, c, h, w = x.shape
+    off_y, off_x, hh, ww = augment_window(h, w, aug_patch, center)
+    if draws is None:
+        draws = [augment_draw(rs, hh, ww, width, intensity_first) for _ in range(b)]
+    assert len(draws) == b
+    tops = [d[0] + off_y for d in draws]
+    lefts = [d[1] + off_x for d in draws]
+    ks, gains, cuts = [d[2] for d in draws], [d[3] for d in draws], [d[4] for d in draws]
     mask = 0xFFFFFFFF
     if slice_mask is not None:
         sm = np.asarray(slice_mask, dtype=bool)

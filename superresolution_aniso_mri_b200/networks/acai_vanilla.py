@@ -170,16 +170,35 @@ class VanillaACAI(nn.Module):
         """Parameters / BN buffers were updated in place by our kernels (no torch version bump): drop derived tensors."""
         self._cache.clear()
 
-    @torch.no_grad()
+    @staticmethod
+    def _no_autograd(t, what):
+        """The reference module is differentiable through autograd (networks/acai_vanilla.py:130-138); this one runs
+        hand-written kernels and builds no graph.  Gradients exist through ``training.engine.TrainEngine.step`` (the
+        trainers' ``train()``).  A caller that expects autograd gradients must hear about it instead of silently
+        getting a detached tensor."""
+        if torch.is_grad_enabled() and torch.is_tensor(t) and t.requires_grad:
+            raise RuntimeError("aesr_b200: VanillaACAI.%s received a tensor that requires grad with autograd enabled; this "
+                               "module builds no autograd graph (its backward pass is TrainEngine.step / trainer.train()). "
+                               "Call it under torch.no_grad() or detach the input." % what)
+
     def encode(self, img):
+        self._no_autograd(img, "encode")
+        with torch.no_grad():
+            return self._encode(img)
+
+    def decode(self, z):
+        self._no_autograd(z, "decode")
+        with torch.no_grad():
+            return self._decode(z)
+
+    def _encode(self, img):
         if self.training:
             z, _, _ = self._train_forward().encode_train(img.detach().float().contiguous(), save=False)
             self.invalidate_cache()
             return z
         return self.encode_eval(img)
 
-    @torch.no_grad()
-    def decode(self, z):
+    def _decode(self, z):
         if self.training:
             z = z.detach().float().contiguous()
             m = z.shape[0]

@@ -410,3 +410,65 @@ def test_merged_batch_batchnorm_equals_two_passes(cuda_lib):
                             for k, sl in enumerate((slice(0, n0), slice(n0, n)))])
         assert (gg.float() - want_g.float()).abs().max().item() <= 2e-2 * want_g.float().abs().max().item()
         assert torch.allclose(dg, dg2, rtol=1e-3, atol=1e-6) and torch.allclose(db, db2, rtol=1e-3, atol=1e-6)
+
+
+def test_device_triplet_loader_feeds_trainer_and_follows_reference_draw_order(cuda_lib):
+    """sample_triplet -> gather_triplets -> augment_batch -> prepare_batch_pairs as ONE batch source that
+    ``trainer.train()`` consumes.  The batches equal a host replay of the reference's per-sample ``__getitem__`` order
+    (triplet draws, then the transform draws) through the oracle's pinned ``sample_triplet`` / ``augment_sample``."""
+    from superresolution_aniso_mri_b200.data_loader import DeviceTripletLoader
+    dev = torch.device("cuda:0")
+    vols = [O.mri_phantom(12, 150, seed=70 + i)[:, 0, :, :141].numpy() for i in range(3)]
+    for kind, kw in (("acdc", dict(width=128, aug_patch=160, center=True)), ("brain", dict(width=64, downsample_steps=4))):
+        rs = np.random.RandomState(99)
+        loader = DeviceTripletLoader(vols, batch_size=4, kind=kind, rs=rs, device=dev, **kw)
+        batches = [b for _, b in zip(range(3), loader)]
+        rs2 = np.random.RandomState(99)
+        perm = rs2.permutation(len(loader.items))
+        for bi, b in enumerate(batches):
+            want_img, want_af = [], []
+            for i in perm[bi * 4:(bi + 1) * 4]:
+                vi, z, Z = loader.items[i]
+                t = O.sample_triplet(z, Z, rs2, kind=kind, slice_selection="adjacent_plus", downsample_steps=kw.get("downsample_steps", 2))
+                img3 = np.stack([vols[vi][t["slice_idx_from"]], vols[vi][t["slice_idx_to"]], vols[vi][t["inbetween_slice_id"]]])
+                out, _ = O.augment_sample(img3, rs2, width=kw["width"], aug_patch=kw.get("aug_patch"), center=kw.get("center", False),
+                                          intensity_first=(kind == "acdc"))
+                want_img.append(out)
+                want_af.append(float(t["alpha_from"]))
+            want = torch.from_numpy(np.stack(want_img))
+            got = torch.cat([b["image"][:4], b["image"][4:], b["slice_between"]], dim=1).cpu()      # back to [B,3,H,W]
+            assert got.shape == want.shape == (4, 3, kw["width"], kw["width"])
+            assert (got - want).abs().max().item() <= 4 * 2.0 ** -23 * max(1.0, want.abs().max().item())
+            assert torch.allclose(b["alpha_from"].cpu().reshape(-1), torch.tensor(want_af))
+            assert b["image"].is_cuda and b["image"].shape == (8, 1, kw["width"], kw["width"])
+    # end to end: the loader drives the ACDC trainer for a few iterations
+    tr = make_trainer(trainer_args(width=64, latent_width=16, batch_size=4))
+    loader = DeviceTripletLoader(vols, batch_size=4, kind="acdc", width=64, aug_patch=96, center=True,
+                                 rs=np.random.RandomState(5), device=dev)
+    n = 0
+    for batch_item in loader:
+        tr.train(batch_item, keep_predictions=False)
+        n += 1
+        if n == 4:
+            break
+    assert n == 4 and len(tr.losses["loss_ae"]) == 4 and all(np.isfinite(tr.losses["loss_ae"]))
+
+
+def test_encode_decode_refuse_autograd_inputs(cuda_lib):
+    """networks/acai_vanilla.py:130-138 is differentiable through autograd; this module is not -- it must say so."""
+    from superresolution_aniso_mri_b200.networks.acai_vanilla import VanillaACAI
+    args = dict(O.default_args(64, 16))
+    args["device"] = "cuda:0"
+    m = VanillaACAI(args).eval()
+    x = torch.rand(2, 1, 64, 64, device="cuda:0", requires_grad=True)
+    with pytest.raises(RuntimeError, match="builds no autograd graph"):
+        m.encode(x)
+    with torch.no_grad():
+        z = m.encode(x)
+    assert not z.requires_grad
+    with pytest.raises(RuntimeError, match="builds no autograd graph"):
+        m(x)
+    z2 = z.clone().requires_grad_(True)
+    with pytest.raises(RuntimeError, match="builds no autograd graph"):
+        m.decode(z2)
+    assert m.decode(z).shape == (2, 1, 64, 64)              # plain tensors with grad mode on: fine
