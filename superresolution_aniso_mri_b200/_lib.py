@@ -38,10 +38,6 @@ _SIGNATURES = {
     "aesr_copy_rows_async": (I, [P, c_size_t, c_size_t, P, c_size_t, c_size_t, c_size_t, c_size_t, c_size_t, I, P]),
     "aesr_lerp_pairs": (I, [P, P, P, P, P, P, I, I, I, I, I, P]),
     "aesr_lerp_pairs_act": (I, [P, P, P, P, P, P, P, I, I, I, I, F, I, P]),
-    "aesr_probe_halo_conv": (I, [P, P, P, I, I, I, I, I, I, I, I, P]),
-    "aesr_probe_umma_rate": (I, [P, I, I, I, I, I, I, I, I, I, P]),
-    "aesr_probe_umma_pattern": (I, [P, I, I, I, I, I, I, I, I, P]),
-    "aesr_probe_sync": (I, [P, I, I, P]),
     # training step
     "aesr_bn_finalize": (I, [P, F, F, I, P, P, P, P, F, F, P, P, P, P, I, P]),
     "aesr_bn_apply": (I, [P, P, P, P, I, I, I, I, I, I, I, P]),
@@ -68,6 +64,30 @@ _SIGNATURES = {
     "aesr_augment_gather": (I, [P, P, P, P, P, P, P, ctypes.c_uint, I, I, I, I, I, P]),
     "aesr_gauss1d_axis0": (I, [P, P, P, I, I, c_size_t, P]),
 }
+
+
+# diagnostic entry points of lib/libaesr_b200_probe.so (include/aesr_b200_probe.h; not in the product library)
+_PROBE_SIGNATURES = {
+    "aesr_probe_halo_conv": (I, [P, P, P, I, I, I, I, I, I, I, I, P]),
+    "aesr_probe_umma_rate": (I, [P, I, I, I, I, I, I, I, I, I, P]),
+    "aesr_probe_umma_pattern": (I, [P, I, I, I, I, I, I, I, I, P]),
+    "aesr_probe_sync": (I, [P, I, I, P]),
+}
+_probe_lib = None
+
+
+def load_probe():
+    """The diagnostic build (product entry points + aesr_probe_*), built on demand: tools only."""
+    global _probe_lib
+    if _probe_lib is None:
+        from . import build
+        lib = ctypes.CDLL(build.build_library(probes=True))
+        for name, (res, args) in {**_SIGNATURES, **_PROBE_SIGNATURES}.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _probe_lib = lib
+    return _probe_lib
 
 
 def exported_symbols():

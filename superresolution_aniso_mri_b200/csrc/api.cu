@@ -11,7 +11,10 @@
 #include "elementwise.cuh"
 #include "eval_kernels.cuh"
 #include "lpips_kernels.cuh"
+#ifdef AESR_WITH_PROBES
+#include "../../include/aesr_b200_probe.h"
 #include "probe.cuh"
+#endif
 #include "train_kernels.cuh"
 #include "vif_kernels.cuh"
 #include "wgrad_tc.cuh"
@@ -772,6 +775,7 @@ int aesr_copy_rows_async(void* dst, size_t dst_outer_stride, size_t dpitch, cons
     return AESR_OK;
 }
 
+#ifdef AESR_WITH_PROBES
 int aesr_probe_halo_conv(const void* x, const void* w_packed, float* out, int N, int H, int W, int x0, int y0, int n,
                          int pitch, int variant, void* stream) {
     int rc = ensure_init();
@@ -838,6 +842,8 @@ int aesr_probe_sync(long long* cycles, int iters, int mode, void* stream) {
     sync_probe_kernel<<<1, 128, 0, static_cast<cudaStream_t>(stream)>>>(cycles, iters, mode);
     return check_launch("sync_probe");
 }
+
+#endif  // AESR_WITH_PROBES
 
 }  // extern "C"
 

@@ -104,8 +104,8 @@ constexpr int CONV_TILE_W = 8;
 constexpr int CONV_TILE_M = 128;
 constexpr int CONV_EPI_SETS = 4;                          // epilogue warp sets (4 warps = 128 TMEM lanes each)
 constexpr int CONV_ISSUERS = 1;                            // MMA-issuing warps (one elected thread each)
-constexpr int CONV_FIRST_EPI_WARP = 1 + CONV_ISSUERS;      // warp 0 TMA, warps 1-2 MMA issuers, then the epilogue sets
-constexpr int CONV_THREADS = 32 * CONV_FIRST_EPI_WARP + 128 * CONV_EPI_SETS;   // 608
+constexpr int CONV_FIRST_EPI_WARP = 1 + CONV_ISSUERS;      // warp 0 TMA, warp 1 MMA issuer, then the epilogue sets
+constexpr int CONV_THREADS = 32 * CONV_FIRST_EPI_WARP + 128 * CONV_EPI_SETS;   // 576
 constexpr int CONV_MAX_STAGES = 8;
 // TMEM accumulators in flight: one per epilogue set while they fit in the 512 columns
 __host__ __device__ constexpr int conv_num_acc(int BN) { return (CONV_EPI_SETS * BN <= 512) ? CONV_EPI_SETS : 512 / BN; }

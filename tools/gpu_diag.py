@@ -105,7 +105,7 @@ try:
         for pitch in (10,):
             for variant in (0,):
                 out = torch.zeros(128, 64, device=dev)
-                _lib.check(lib.aesr_probe_halo_conv(x.data_ptr(), wp.data_ptr(), out.data_ptr(), 1, 40, 40, x0, y0, 0,
+                _lib.check(_lib.load_probe().aesr_probe_halo_conv(x.data_ptr(), wp.data_ptr(), out.data_ptr(), 1, 40, 40, x0, y0, 0,
                                                     pitch, variant, torch.cuda.current_stream().cuda_stream), "probe")
                 torch.cuda.synchronize()
                 valid = torch.tensor([(y0 + r // 8 < 40) and (x0 + r % 8 < 40) for r in range(128)])

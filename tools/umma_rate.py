@@ -11,7 +11,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from superresolution_aniso_mri_b200 import _lib  # noqa: E402
 
-lib = _lib.lib_for_device(0)
+lib = _lib.load_probe()          # diagnostic build (include/aesr_b200_probe.h)
+_lib.check(lib.aesr_init(0), "init")
 out = torch.zeros(2 * 148, dtype=torch.int64, device="cuda:0")
 iters = 20000
 full = "--full" in sys.argv
