@@ -499,8 +499,24 @@ def run_ours(a):
         enc_b, dec_b = conv_launch_bytes(SIZE)
         alg_bytes = float(n_enc * enc_b + n_dec * dec_b)
         ach = alg_fl / (conv_ms * 1e-3) / 1e12
-        # operand-bandwidth bound of the tcgen05 SS-mode MMA for this network (measured curve
-        # (4096 + 32 N) / 128 cycles per M=128,K=16 MMA): cycles the EXECUTED MMAs need at that rate / elapsed cycles
+        # Operand-bandwidth ceiling of the tcgen05 SS-mode MMA for THIS network: measured on B200
+        # (profiles/r01_umma_rate.txt) an M=128, K=16 MMA takes (4096 + 32 N) / 128 cycles = 40 / 48 / 64 at N = 32 / 64 / 128
+        # against N / 2 at the math rate, i.e. a layer with N output columns per tile cannot exceed (N/2) / ((4096+32N)/128)
+        # of the tensor peak: 0.40 / 0.67 / 1.0.  Time of the EXECUTED MMA work of a step at that per-layer ceiling:
+        def ceil_frac(n_cols):
+            return min(1.0, (n_cols / 2.0) / ((4096.0 + 32.0 * n_cols) / 128.0))
+        n_cols = {"enc.3": 32, "enc.7": 64, "enc.9": 64, "enc.13": 128, "enc.15": 128, "dec.0": 64, "dec.2": 64,
+                  "dec.6": 128, "dec.8": 32, "dec.12": 128}          # dec.6 / dec.12: upsample folded -> 4 x 32 phase columns
+        n_run = {"dec.0": n_enc}          # interpolation behind dec.0: it runs once per encoded slice
+        bound_s = 0.0
+        exec_fl = 0.0
+        for name, ncol in n_cols.items():
+            macs = emac[name] if name.startswith("enc") else dmac[name]
+            cnt = n_enc if name.startswith("enc") else n_run.get(name, n_dec)
+            fl = 2.0 * macs * cnt
+            exec_fl += fl
+            bound_s += fl / (peaks["bf16_tflops"] * 1e12 * ceil_frac(ncol))
+        operand_bound_tflops = exec_fl / bound_s / 1e12
         build_hash = csrc_hash()
         traffic, traffic_src = None, "no ncu capture of this build (sources %s)" % build_hash
         caps = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_conv_full.json"))
@@ -529,6 +545,11 @@ def run_ours(a):
                 "peak_source": "%s MEASURED_PEAKS.json bf16_tflops = BURST cuBLAS bf16 figure (the timed region is ~0.1 s at full "
                                "clocks, not a power-capped seconds-long step)" % peaks["source"],
                 "frac_of_sustained_peak": ach / peaks["bf16_tflops_sustained"],
+                "mma_operand_bound": {"tflops": operand_bound_tflops, "frac_of_it": (conv_fl / (conv_ms * 1e-3) / 1e12) / operand_bound_tflops,
+                                      "note": "ceiling of the executed MMA work when every layer runs at the measured SS-mode "
+                                              "tcgen05 rate of its N (0.40 / 0.67 / 1.0 of peak at N = 32 / 64 / 128 columns per "
+                                              "tile: the MMA reads 4 KB of A per 128 x N x 16 MACs at 128 B/clk); frac_of_it = "
+                                              "executed TFLOP/s over that ceiling"},
                 "traffic": traffic, "traffic_source": traffic_src, "csrc_hash": build_hash,
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_conv, 1),
                 "conv_ms_per_step": conv_ms, "all_kernels_ms_per_step": all_ms,

@@ -33,6 +33,10 @@ int aesr_probe_umma_pattern(long long* cycles, int BN, int kc, int T, int iters,
  * test_wait instead of try_wait, bit 2: three waiting warps).  cycles[0] = total cycles for `iters` round trips. */
 int aesr_probe_sync(long long* cycles, int iters, int mode, void* stream);
 
+/* Diagnostic: device time per kernel of a CUDA graph holding a chain of `n_kernels` dependent launches (`ctas` CTAs of 128
+ * threads, each spinning `spin_cycles`), with (`pdl` = 1) or without programmatic dependent launch; HOST pointer result. */
+int aesr_probe_launch_gap(float* us_per_kernel, int n_kernels, int ctas, int spin_cycles, int pdl, int replays);
+
 #ifdef __cplusplus
 }
 #endif

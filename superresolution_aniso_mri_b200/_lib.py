@@ -68,6 +68,7 @@ _SIGNATURES = {
 
 # diagnostic entry points of lib/libaesr_b200_probe.so (include/aesr_b200_probe.h; not in the product library)
 _PROBE_SIGNATURES = {
+    "aesr_probe_launch_gap": (I, [P, I, I, I, I, I]),
     "aesr_probe_halo_conv": (I, [P, P, P, I, I, I, I, I, I, I, I, P]),
     "aesr_probe_umma_rate": (I, [P, I, I, I, I, I, I, I, I, I, P]),
     "aesr_probe_umma_pattern": (I, [P, I, I, I, I, I, I, I, I, P]),

@@ -843,6 +843,52 @@ int aesr_probe_sync(long long* cycles, int iters, int mode, void* stream) {
     return check_launch("sync_probe");
 }
 
+int aesr_probe_launch_gap(float* us_per_kernel, int n_kernels, int ctas, int spin_cycles, int pdl, int replays) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!us_per_kernel || n_kernels <= 0 || ctas <= 0 || replays <= 0) return fail(AESR_ERR_INVALID, "probe_launch_gap: bad arguments");
+    cudaStream_t s;
+    CUDA_TRY(cudaStreamCreate(&s));
+    int* sink = nullptr;
+    CUDA_TRY(cudaMalloc(&sink, sizeof(int)));
+    CUDA_TRY(cudaMemset(sink, 0, sizeof(int)));
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < n_kernels; ++i) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(ctas);
+        cfg.blockDim = dim3(128);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, launch_gap_probe_kernel, sink, spin_cycles));
+    }
+    CUDA_TRY(cudaStreamEndCapture(s, &graph));
+    CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaGraphLaunch(exec, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(cudaEventRecord(e0, s));
+    for (int r = 0; r < replays; ++r) CUDA_TRY(cudaGraphLaunch(exec, s));
+    CUDA_TRY(cudaEventRecord(e1, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    *us_per_kernel = ms * 1e3f / (static_cast<float>(replays) * n_kernels);
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaStreamDestroy(s);
+    return AESR_OK;
+}
 #endif  // AESR_WITH_PROBES
 
 }  // extern "C"

@@ -292,4 +292,14 @@ __global__ void __launch_bounds__(128, 1) sync_probe_kernel(long long* __restric
     }
 }
 
+// Launch-gap probe: a chain of dependent kernels of `ctas` CTAs x 128 threads, each spinning `spin` clock cycles after the
+// programmatic-dependency wait (griddepcontrol.wait is a no-op for a launch without the attribute).
+__global__ void launch_gap_probe_kernel(int* sink, int spin) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const long long t0 = clock64();
+    while (clock64() - t0 < spin) {}
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(sink, 1);
+}
+
 }  // namespace aesr

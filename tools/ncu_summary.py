@@ -77,8 +77,12 @@ def full(src, dst):
                  "tensor_pct": float(r[hdr.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")])}
                 for r in rows[2:]]
     import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench            # csrc_hash(): stamps the capture to the kernel sources it was taken from
     with open(dst.replace(".md", ".json"), "w") as f:
-        json.dump({"source": src, "mean_dram_bytes_per_launch": sum(l["dram_bytes"] for l in launches) / len(launches),
+        json.dump({"source": src, "csrc_hash": bench.csrc_hash(), "workload": os.environ.get("AESR_PROFILE_WORKLOAD", "acdc"),
+                   "mean_dram_bytes_per_launch": sum(l["dram_bytes"] for l in launches) / len(launches),
                    "launches": launches}, f, indent=1)
 
 
