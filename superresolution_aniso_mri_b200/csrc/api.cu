@@ -394,6 +394,11 @@ int launch_halo(const void* x, const void* w, const void* head_w16, ConvParams p
     else if (plain && p.out_mode == OUT_AVGPOOL2) AESR_HALO(OUT_AVGPOOL2)
     else if (plain && p.out_mode == OUT_SHUFFLE2) AESR_HALO(OUT_SHUFFLE2)
     else if (plain && p.out_mode == OUT_SAME_F32) AESR_HALO(OUT_SAME_F32)
+    // training instantiations (conv3x3_tc.cuh ConvLean): no eval-BatchNorm affine, no second output except the max-pool
+    else if (!p.scale && p.out_mode == OUT_SAME_MAXPOOL2 && p.mul_mode == MUL_NONE && !p.stats) AESR_HALO(OUT_SAME_MAXPOOL2)
+    else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode != MUL_NONE && !p.stats) AESR_HALO(LEAN_SAME_MUL)
+    else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode != MUL_NONE && p.stats && p.stats_sum_only) AESR_HALO(LEAN_SAME_MUL_SUM)
+    else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode == MUL_NONE && p.stats && !p.stats_sum_only) AESR_HALO(LEAN_SAME_STATS)
     else AESR_HALO(-1)
 #undef AESR_HALO
     return check_launch("conv3x3_halo");
@@ -511,6 +516,10 @@ int conv3x3_dispatch(const void* x, const void* w_packed, const float* bias, con
         if (!halo && algo == AESR_ALGO_HALO)
             return fail(AESR_ERR_INVALID, "conv3x3_fwd: filter bank %dx%d too large for AESR_ALGO_HALO", Cout, Cin);
         if (out_mode == OUT_SHUFFLE2_HEAD && bn != Cout) halo = false;     // all four phases must sit in one tile
+        // Cin = 256: the resident bank only fits with 32-column tiles (40 % MMA ceiling, the activation re-read by Cout / 32
+        // n-blocks); the streamed kernel with 256-column tiles is 1.4-1.5x faster on the VGG conv3/conv4 shapes
+        // (profiles/r06d_vgg_halo_vs_stream_sweep.txt: 256->256 @32^2 n24 60 vs 40 us, 256->512 @16^2 37 vs 26 us)
+        if (halo && algo == AESR_ALGO_AUTO && bn < 64 && Cout >= 128 && out_mode != AESR_OUT_SHUFFLE2) halo = false;
     }
     if (out_mode == OUT_SHUFFLE2_HEAD && !halo)
         return fail(AESR_ERR_INVALID, "conv3x3_up2_head_fwd: Cin=%d: the 128-row folded bank must fit the resident-filter kernel", Cin);

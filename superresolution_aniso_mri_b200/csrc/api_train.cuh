@@ -73,7 +73,9 @@ int aesr_bn_bwd(const void* dnext, const void* a, const float* mean, const float
     if (count1 <= 0.f) count1 = static_cast<float>(static_cast<size_t>(N - split) * H * W);
     // phase 0: the apply kernel banks dgamma / dbeta from the (local) sums; phase 1 banks them right after the local
     // reduce; phase 2 (sums all-reduced by the caller) must not bank them again.
-    const int apply_grid = grid_for(total, 256, dbias_conv ? 4 : 16);      // dbias_conv: C global atomics per block at the end
+    // dbias_conv: C global atomics per block at the end (same-address REDs: ~2k per address, a few us, fire-and-forget); a grid
+    // capped at 4 blocks per SM to save them made the kernel 50 % slower (34 vs 23 us per launch, profiles/r06_train_launches.md)
+    const int apply_grid = grid_for(total, 256, tune(7) == 9999 ? 4 : 16);
     float* dg_apply = phase == 0 ? dgamma : nullptr;
     float* db_apply = phase == 0 ? dbeta : nullptr;
     if (dtype == AESR_DT_FP16) {

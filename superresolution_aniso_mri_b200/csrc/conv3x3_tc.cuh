@@ -498,9 +498,24 @@ __global__ void splitk_finish_kernel(const float* __restrict__ ws, int ksplit, s
 // Lean epilogue of the inference output stages (OUT_SAME, OUT_AVGPOOL2, OUT_SHUFFLE2, OUT_SAME_F32; no training extras): 16 accumulator
 // columns per TMEM load, so that 16 values + addresses + the role's loop state stay far below the 96 registers a
 // 576-thread CTA allows (the 32-column generic epilogue spills its loop state, ncu: LDL stalls in every tile).
-template <int MODE>
+// Training variants of the lean epilogue (kernel template values only; p.out_mode stays OUT_SAME / OUT_SAME_MAXPOOL2): the
+// fully dynamic epilogue spills (148 bytes of spill stores at 96 registers) and ncu shows its warps waiting on local-memory
+// loads (long_scoreboard 5-30 per issue, profiles/r06c_train_conv_ncu.md): VGG conv1_2 took 70 us through it against 45 us
+// through the plain OUT_SAME instantiation.  One instantiation per combination the training step uses:
+enum ConvLean : int {
+    LEAN_SAME_MUL = 16,        // OUT_SAME * act'(mul_src)                      (VGG data gradients)
+    LEAN_SAME_STATS = 17,      // OUT_SAME + per-channel sum / sum^2 (2 passes)  (conv in front of a train-mode BatchNorm)
+    LEAN_SAME_MUL_SUM = 18,    // OUT_SAME * act'(mul_src) + per-channel sum     (autoencoder data gradients + bias gradient)
+};
+__host__ __device__ constexpr int lean_out(int mode) { return mode >= 16 ? OUT_SAME : mode; }
+__host__ __device__ constexpr bool lean_mul(int mode) { return mode == LEAN_SAME_MUL || mode == LEAN_SAME_MUL_SUM; }
+__host__ __device__ constexpr bool lean_stats(int mode) { return mode == LEAN_SAME_STATS || mode == LEAN_SAME_MUL_SUM; }
+
+template <int KMODE>
 __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
                                                    uint64_t* tmem_empty_bar, const TileCoord& t) {
+    constexpr int MODE = lean_out(KMODE);
+    constexpr bool WITH_MUL = lean_mul(KMODE), WITH_STATS = lean_stats(KMODE);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3;                     // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;              // pixel index inside the tile
@@ -515,7 +530,7 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
     size_t pix;
     bool store;
     int Cpix;                                   // channels per output pixel
-    if (MODE == OUT_SAME || MODE == OUT_SAME_F32) {
+    if (MODE == OUT_SAME || MODE == OUT_SAME_F32 || MODE == OUT_SAME_MAXPOOL2) {
         Cpix = p.Cout;
         pix = (static_cast<size_t>(t.n) * H + y) * W + x;
         store = inb;
@@ -561,6 +576,41 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
                 v[j4 * 4 + 3] = fmaxf(a3, a3 * neg_slope);
             }
         }
+        if (WITH_MUL) {
+            if (inb) {
+                const uint4* m4 = reinterpret_cast<const uint4*>(p.mul_src + pix * Cpix + cg);
+                const float neg = (p.mul_mode == MUL_LEAKY_GRAD) ? p.slope : 0.f;
+#pragma unroll
+                for (int j4 = 0; j4 < 2; ++j4) {
+                    const uint4 m = __ldg(m4 + j4);
+                    const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        v[j4 * 8 + u * 2] *= pos16(w[u] & 0xFFFFu) ? 1.f : neg;
+                        v[j4 * 8 + u * 2 + 1] *= pos16(w[u] >> 16) ? 1.f : neg;
+                    }
+                }
+            }
+        }
+        if (WITH_STATS) {
+            float s1[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) s1[j] = inb ? v[j] : 0.f;
+            const float t1 = warp_transpose_sum16(s1, lane);
+            const int ch = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if (KMODE == LEAN_SAME_MUL_SUM) {                 // bias gradient: sums only, one block
+                if ((lane & 1) == 0) atomicAdd(bars.s_stats + cg + ch, t1);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) s1[j] *= s1[j];
+                const float t2 = warp_transpose_sum16(s1, lane);
+                if ((lane & 1) == 0) {
+                    float* sst = bars.s_stats + (t.n >= p.stats_split ? 2 * p.Cout : 0);
+                    atomicAdd(sst + cg + ch, t1);
+                    atomicAdd(sst + p.Cout + cg + ch, t2);
+                }
+            }
+        }
         if (affine) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
@@ -594,7 +644,7 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) o4[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
             }
-        } else if ((MODE == OUT_SAME || MODE == OUT_SHUFFLE2) && p.BN >= 64) {
+        } else if ((MODE == OUT_SAME || MODE == OUT_SHUFFLE2 || MODE == OUT_SAME_MAXPOOL2) && p.BN >= 64) {
             // Lane pairs (x, x+1) trade halves so that every store instruction writes whole 32-byte sectors: lane 2i
             // holds pixel P's channels [c0, c0+16) = 16-byte halves A0 A1, lane 2i+1 pixel P+1's B0 B1.  Stored directly
             // (A0 | B0, then A1 | B1) each STG.128 touches 32 half-written sectors; after one exchange the pair writes
@@ -623,6 +673,23 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
             uint4* o4 = reinterpret_cast<uint4*>(out16 + off);
             o4[0] = pack8(v, fp16);
             o4[1] = pack8(v + 8, fp16);
+        }
+        if (MODE == OUT_SAME_MAXPOOL2) {
+            // 2x2 window = lanes {l, l^1, l^8} (x neighbour, y neighbour): tile origins are even.
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float a = v[j];
+                a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
+                a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 8));
+                v[j] = a;
+            }
+            const int Ho = H >> 1, Wo = W >> 1, yo = y >> 1, xo = x >> 1;
+            if (((px | py) & 1) == 0 && yo < Ho && xo < Wo && !(p.debug & 4)) {
+                uint4* o4 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out2) +
+                                                     ((static_cast<size_t>(t.n) * Ho + yo) * Wo + xo) * Cpix + cg);
+                o4[0] = pack8(v, fp16);
+                o4[1] = pack8(v + 8, fp16);
+            }
         }
     }
 }
@@ -1131,7 +1198,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             if (++buf == nbuf) { buf = 0; buf_phase ^= 1; }
         }
     }
-    conv_teardown<(MODE < 0)>(p, bars, tmem_base, tmem_cols);
+    conv_teardown<(MODE < 0) || lean_stats(MODE)>(p, bars, tmem_base, tmem_cols);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
