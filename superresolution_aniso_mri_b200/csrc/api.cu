@@ -246,9 +246,6 @@ int launch_stream(const void* x, const void* w, ConvParams p, cudaStream_t strea
     if (rc != AESR_OK) return rc;
     rc = make_wgt_tmap(&tw, w, 9 * p.Cout, p.Cin, KC, p.BN);
     if (rc != AESR_OK) return rc;
-    static int configured = 0;
-    rc = set_max_smem(conv3x3_stream_kernel<KC>, &configured);
-    if (rc != AESR_OK) return rc;
     // Split-K: layers with fewer tiles than half the SMs (the 16x16 / 8x8 VGG layers of a 12-24 image batch: 12-96 tiles,
     // each streaming its whole 9 x Cin filter slab through one SM's L2 port) are cut along K so that ~all SMs take part;
     // the splits leave raw fp32 accumulators in a workspace and a small kernel adds them and runs the epilogue.
@@ -270,7 +267,21 @@ int launch_stream(const void* x, const void* w, ConvParams p, cudaStream_t strea
     const int items = p.num_tiles * p.ksplit;
     const int grid = items < g_sm_count ? items : g_sm_count;
     void* out_final = p.out;
-    conv3x3_stream_kernel<KC><<<grid, CONV_THREADS, S::total_bytes(p.BN, stages), stream>>>(tx, tw, p);
+    const int smem = S::total_bytes(p.BN, stages);
+#define AESR_STREAM(MODE)                                                                            \
+    {                                                                                                \
+        static int configured = 0;                                                                   \
+        rc = set_max_smem(conv3x3_stream_kernel<KC, MODE>, &configured);                             \
+        if (rc != AESR_OK) return rc;                                                                \
+        conv3x3_stream_kernel<KC, MODE><<<grid, CONV_THREADS, smem, stream>>>(tx, tw, p);            \
+    }
+    const bool bare = !p.scale && !p.stats;
+    if (p.ksplit > 1) AESR_STREAM(OUT_SAME)                     // split-K: raw accumulators, the epilogue runs in splitk_finish
+    else if (bare && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode == MUL_NONE) AESR_STREAM(OUT_SAME)
+    else if (bare && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode != MUL_NONE) AESR_STREAM(LEAN_SAME_MUL)
+    else if (bare && p.out_mode == OUT_SAME_MAXPOOL2 && p.mul_mode == MUL_NONE) AESR_STREAM(OUT_SAME_MAXPOOL2)
+    else AESR_STREAM(-1)
+#undef AESR_STREAM
     rc = check_launch("conv3x3_stream");
     if (rc != AESR_OK || p.ksplit == 1) return rc;
     const size_t npix = static_cast<size_t>(p.N) * p.H * p.W;

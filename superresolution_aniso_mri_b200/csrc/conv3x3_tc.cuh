@@ -1214,7 +1214,7 @@ struct StreamSmem {
     }
 };
 
-template <int KC>
+template <int KC, int MODE>        // MODE: -1 = run-time epilogue, else a compiled-in lean epilogue (OUT_SAME, OUT_SAME_MAXPOOL2, ConvLean)
 __global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                       const __grid_constant__ ConvParams p) {
@@ -1302,6 +1302,7 @@ conv3x3_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
                 mbar_wait(&bars.tmem_full[eset], acc_phase);
                 tc_fence_after();
                 if (ksplit > 1) conv_epilogue_splitk(p, tmem_base + eset * p.BN, &bars.tmem_empty[eset], t, sp);
+                else if (MODE >= 0) conv_epilogue_lean<MODE>(p, bars, tmem_base + eset * p.BN, &bars.tmem_empty[eset], t);
                 else conv_epilogue_tile(p, bars, tmem_base + eset * p.BN, &bars.tmem_empty[eset], t);
                 acc_phase ^= 1;
             }
