@@ -472,6 +472,32 @@ def run_ours(a):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = slices_per_step * a.steps / (float(e2e_ms.item()) * 1e-3)
 
+    # ---- platform ceiling of the host-buffer path: every rank copies one step's download volume device -> pinned host AT ONCE
+    #      (one cudaMemcpyAsync per copy, tools/d2h_probe.py); e2e cannot exceed aggregate GB/s / bytes per slice
+    d2h_ceiling = None
+    if pipe is not None:
+        nb = max(d2h_bytes // 4, 1)
+        src_d = torch.empty(nb, device=dev)
+        dst_h = torch.empty(nb).pin_memory()
+        for _ in range(2):
+            dst_h.copy_(src_d, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            dst_h.copy_(src_d, non_blocking=True)
+        c1.record()
+        barrier()
+        cms = torch.tensor([c0.elapsed_time(c1) / 5], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(cms, op=dist.ReduceOp.MAX)
+        agg = world * d2h_bytes / (float(cms.item()) * 1e-3) / 1e9
+        d2h_ceiling = {"gbs_aggregate": agg, "gbs_per_gpu": agg / world, "ms_per_step_copy_alone": float(cms.item()),
+                       "slices_per_s": slices_per_step / (float(cms.item()) * 1e-3),
+                       "note": "all %d ranks copying one step's download (%d MB each) device->pinned host at once, nothing else "
+                               "running: the host-buffer rate cannot exceed this whatever the pipeline does" % (world, d2h_bytes >> 20)}
+        del src_d, dst_h
+
     # ---- roofline of the dominant kernel family (tcgen05 conv3x3), timed per launch with CUDA events, untimed pass
     roof = None
     parity = None
@@ -594,6 +620,7 @@ def run_ours(a):
                                      "whole HR volumes" if pipe is not None else
                                      "one call per step, pageable host tensor in, CPU tensor out (the reference's return type)")},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "parity": parity,
+                "e2e_platform_ceiling": d2h_ceiling,
                 "cpu_baseline": {"value": cpu_rate, "unit": "slices/s", "cores": cores, "kind": "port", "sample": cpu_desc}}
         if a.workload == "dhcp202":
             line["ms_per_call"] = {"device_resident": ms_total / a.steps, "host_in_host_out": float(e2e_ms.item()) / a.steps,
