@@ -33,6 +33,11 @@ int aesr_probe_umma_pattern(long long* cycles, int BN, int kc, int T, int iters,
  * test_wait instead of try_wait, bit 2: three waiting warps).  cycles[0] = total cycles for `iters` round trips. */
 int aesr_probe_sync(long long* cycles, int iters, int mode, void* stream);
 
+/* Diagnostic: TMEM read rate and shuffle rate.  `nwarps` (4, 8, 12, 16) warps per CTA each issue `iters` x 4 loads of 16
+ * accumulator columns (2 KB per warp instruction) from their lane quarter (mode 0), `iters` x 64 fp32 shuffles (mode 1) or both
+ * (mode 2); cycles[b] = SM cycles of the slowest warp of CTA b; sink = any device buffer of >= 512 floats (never written). */
+int aesr_probe_tmem_ld(long long* cycles, int nwarps, int iters, int mode, int grid, float* sink, void* stream);
+
 /* Diagnostic: device time per kernel of a CUDA graph holding a chain of `n_kernels` dependent launches (`ctas` CTAs of 128
  * threads, each spinning `spin_cycles`), with (`pdl` = 1) or without programmatic dependent launch; HOST pointer result. */
 int aesr_probe_launch_gap(float* us_per_kernel, int n_kernels, int ctas, int spin_cycles, int pdl, int replays);

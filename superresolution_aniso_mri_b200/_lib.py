@@ -73,6 +73,7 @@ _PROBE_SIGNATURES = {
     "aesr_probe_umma_rate": (I, [P, I, I, I, I, I, I, I, I, I, P]),
     "aesr_probe_umma_pattern": (I, [P, I, I, I, I, I, I, I, I, P]),
     "aesr_probe_sync": (I, [P, I, I, P]),
+    "aesr_probe_tmem_ld": (I, [P, I, I, I, I, P, P]),
 }
 _probe_lib = None
 

@@ -8,6 +8,7 @@
 
 #include "../../include/aesr_b200.h"
 #include "conv3x3_tc.cuh"
+#include "conv3x3_fold.cuh"
 #include "elementwise.cuh"
 #include "eval_kernels.cuh"
 #include "lpips_kernels.cuh"
@@ -313,10 +314,12 @@ int halo_pick_bn(int Cin, int Cout) {
 // 6 = AESR_WGRAD_NO_FOLD weight gradient of Cin = 32 layers with one MMA per tap instead of one per filter row.
 // 7 = AESR_WGRAD_CTAS cap on the CTAs of a weight-gradient launch (each CTA ends with Cout x Cin x taps atomics).
 // 8 = AESR_NO_SPLITK streamed conv kernel without split-K (A/B measurements).
-int g_tune[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+// 9 = AESR_FOLD 32 -> 32 layers on conv3x3_fold_kernel (horizontal taps folded into N = 96; measured SLOWER than the tap-by-tap
+//     halo kernel, profiles/r08_fold_sweep.txt: kept as an opt-in experiment with its tests).
+int g_tune[10] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 int tune(int key) {
-    static const char* names[9] = {"AESR_CONV_DEBUG", "AESR_CONV_T", "AESR_CONV_NBUF", "AESR_CONV_STAGES", "AESR_HEAD_MMA",
-                                   "AESR_STEM_CUDA_CORES", "AESR_WGRAD_NO_FOLD", "AESR_WGRAD_CTAS", "AESR_NO_SPLITK"};
+    static const char* names[10] = {"AESR_CONV_DEBUG", "AESR_CONV_T", "AESR_CONV_NBUF", "AESR_CONV_STAGES", "AESR_HEAD_MMA",
+                                    "AESR_STEM_CUDA_CORES", "AESR_WGRAD_NO_FOLD", "AESR_WGRAD_CTAS", "AESR_NO_SPLITK", "AESR_FOLD"};
     if (g_tune[key] < 0) g_tune[key] = getenv(names[key]) ? atoi(getenv(names[key])) : 0;
     return g_tune[key];
 }
@@ -355,6 +358,61 @@ void halo_pick_T(int BN, int Cin, int tiles_y, int extra, int* T_out, int* stage
     *T_out = 1;
     *stages_out = 2;
     *nbuf_out = (512 / BN) >= 4 ? 4 : 2;
+}
+
+// 32 -> 32 layers: horizontal taps folded into N = 96 (conv3x3_fold.cuh).  Returns -1 when the launch is not one of the
+// compiled-in epilogue combinations (FOLD_NOT_APPLICABLE: the caller then takes the tap-by-tap halo kernel).
+constexpr int FOLD_NOT_APPLICABLE = 1;
+int launch_fold(const void* x, const void* w, ConvParams p, int He, int We, cudaStream_t stream) {
+    const bool plain = p.mul_mode == MUL_NONE && p.stats == nullptr && p.out2 == nullptr;
+    int mode = -1;
+    if (plain && p.out_mode == OUT_SAME) mode = OUT_SAME;
+    else if (plain && p.out_mode == OUT_AVGPOOL2) mode = OUT_AVGPOOL2;
+    else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode != MUL_NONE && !p.stats) mode = LEAN_SAME_MUL;
+    else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode != MUL_NONE && p.stats && p.stats_sum_only) mode = LEAN_SAME_MUL_SUM;
+    else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode == MUL_NONE && p.stats && !p.stats_sum_only) mode = LEAN_SAME_STATS;
+    if (mode < 0) return FOLD_NOT_APPLICABLE;
+    p.BN = 32;
+    p.n_blocks = 1;
+    p.tiles_x = (We + FOLD_VALID_W - 1) / FOLD_VALID_W;
+    p.tiles_y = (He + FOLD_TILE_H - 1) / FOLD_TILE_H;
+    // T M-tiles per TMA box / commit and nbuf TMEM buffers of T accumulators: T * nbuf * 96 <= 512 columns
+    int T = 1, nbuf = FOLD_MAX_BUF;
+    const int forced = tune(1), forced_nbuf = tune(2), stage_cap = tune(3);
+    if (forced == 2 && p.tiles_y >= 2) { T = 2; nbuf = 2; }
+    // T = 1: at least one buffer per epilogue set (a set may only wait on a buffer use whose predecessor it has seen complete)
+    if (T == 1 && forced_nbuf >= CONV_EPI_SETS && forced_nbuf <= FOLD_MAX_BUF) nbuf = forced_nbuf;
+    int stages = CONV_MAX_STAGES;
+    if (stage_cap >= 2 && stage_cap < stages) stages = stage_cap;
+    p.T = T;
+    p.nbuf = nbuf;
+    p.stiles_y = (p.tiles_y + T - 1) / T;
+    p.num_stages = stages;
+    const int st_total = p.N * p.tiles_x * p.stiles_y;
+    p.num_tiles = st_total;
+    CUtensorMap tx, tw;
+    int rc = make_act_tmap(&tx, x, p.N, p.H, p.W, 32, FOLD_KC, FOLD_TILE_W, FOLD_TILE_H * T + 2);
+    if (rc != AESR_OK) return rc;
+    rc = make_wgt_tmap(&tw, w, 9 * 32, 32, FOLD_KC, FOLD_N);
+    if (rc != AESR_OK) return rc;
+    const int grid = st_total < g_sm_count ? st_total : g_sm_count;
+    const int smem = fold_total_bytes(T, stages);
+#define AESR_FOLD(MODE)                                                                              \
+    case MODE: {                                                                                     \
+        static int configured = 0;                                                                   \
+        rc = set_max_smem(conv3x3_fold_kernel<MODE>, &configured);                                   \
+        if (rc != AESR_OK) return rc;                                                                \
+        conv3x3_fold_kernel<MODE><<<grid, CONV_THREADS, smem, stream>>>(tx, tw, p);                  \
+    } break;
+    switch (mode) {
+        AESR_FOLD(OUT_SAME)
+        AESR_FOLD(OUT_AVGPOOL2)
+        AESR_FOLD(LEAN_SAME_MUL)
+        AESR_FOLD(LEAN_SAME_MUL_SUM)
+        AESR_FOLD(LEAN_SAME_STATS)
+    }
+#undef AESR_FOLD
+    return check_launch("conv3x3_fold");
 }
 
 template <int KC>
@@ -437,7 +495,7 @@ int aesr_init(int device) {
 const char* aesr_last_error(void) { return g_err; }
 
 int aesr_set_tuning(int key, int value) {
-    if (key < 0 || key > 8 || value < 0) return fail(AESR_ERR_INVALID, "set_tuning: key %d value %d", key, value);
+    if (key < 0 || key > 9 || value < 0) return fail(AESR_ERR_INVALID, "set_tuning: key %d value %d", key, value);
     g_tune[key] = value;
     return AESR_OK;
 }
@@ -534,6 +592,10 @@ int conv3x3_dispatch(const void* x, const void* w_packed, const float* bias, con
     }
     if (out_mode == OUT_SHUFFLE2_HEAD && !halo)
         return fail(AESR_ERR_INVALID, "conv3x3_up2_head_fwd: Cin=%d: the 128-row folded bank must fit the resident-filter kernel", Cin);
+    if (halo && Cin == 32 && Cout == 32 && algo == AESR_ALGO_AUTO && tune(9) == 1) {
+        rc = launch_fold(x, w_packed, p, He, We, s);
+        if (rc != FOLD_NOT_APPLICABLE) return rc;
+    }
     if (halo) return KC == 64 ? launch_halo<64>(x, w_packed, head_w16, p, s) : launch_halo<32>(x, w_packed, head_w16, p, s);
     return KC == 64 ? launch_stream<64>(x, w_packed, p, s) : launch_stream<32>(x, w_packed, p, s);
 }
@@ -853,6 +915,15 @@ int aesr_probe_umma_pattern(long long* cycles, int BN, int kc, int T, int iters,
         umma_pattern_probe_kernel<32><<<grid, 576, smem, s>>>(cycles, BN, T, iters, variant, lag, fill_random);
     }
     return check_launch("umma_pattern_probe");
+}
+
+int aesr_probe_tmem_ld(long long* cycles, int nwarps, int iters, int mode, int grid, float* sink, void* stream) {
+    int rc = ensure_init();
+    if (rc != AESR_OK) return rc;
+    if (!cycles || !sink || nwarps < 4 || nwarps > 16 || nwarps % 4 || iters <= 0 || mode < 0 || mode > 2 || grid < 1 || grid > 1024)
+        return fail(AESR_ERR_INVALID, "probe_tmem_ld: bad arguments");
+    tmem_ld_probe_kernel<<<grid, 32 * nwarps, 0, static_cast<cudaStream_t>(stream)>>>(cycles, iters, mode, sink);
+    return check_launch("tmem_ld_probe");
 }
 
 int aesr_probe_sync(long long* cycles, int iters, int mode, void* stream) {

@@ -292,6 +292,63 @@ __global__ void __launch_bounds__(128, 1) sync_probe_kernel(long long* __restric
     }
 }
 
+// TMEM read-rate / shuffle-rate probe (diagnostic): `nwarps` warps (multiple of 4: warp w reads TMEM lane quarter w % 4) each
+// issue `iters` x 4 back-to-back loads of 16 accumulator columns (tcgen05.ld.32x32b.x16 = 2 KB per warp instruction), one
+// tcgen05.wait::ld per four loads; mode 1: 64 fp32 shuffles (shfl.sync.down) per iteration instead; mode 2: both.
+// cycles[0] = SM cycles of the slowest warp from a common start to its end.  Answers: is the TMEM read path 64 B/clk per SM
+// or per lane quarter (a 96-column accumulator is 48 KB per tile), and what do 64 shuffles per tile and warp cost?
+__global__ void __launch_bounds__(512, 1) tmem_ld_probe_kernel(long long* __restrict__ cycles, int iters, int mode,
+                                                               float* __restrict__ sink) {
+    __shared__ uint32_t tmem_ptr;
+    __shared__ long long t_end[16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) tmem_alloc(&tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t base = tmem_ptr + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    float acc = static_cast<float>(lane);
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+        if (mode != 1) {
+            uint32_t r0[16], r1[16], r2[16], r3[16];
+            const uint32_t c = static_cast<uint32_t>((i * 64 + (warp >> 2) * 128) & 448);
+            tmem_ld_32x32b_x16(base + c, r0);
+            tmem_ld_32x32b_x16(base + c + 16, r1);
+            tmem_ld_32x32b_x16(base + c + 32, r2);
+            tmem_ld_32x32b_x16(base + c + 48, r3);
+            tmem_ld_wait();
+            acc += __uint_as_float(r0[0] ^ r1[5] ^ r2[9] ^ r3[15]);
+        }
+        if (mode != 0) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = acc + static_cast<float>(j);
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += __shfl_down_sync(0xffffffffu, v[(j + 1) & 15], 1);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc += v[j];
+        }
+    }
+    const long long t1 = clock64();
+    if (lane == 0) t_end[warp] = t1 - t0;
+    if (acc == 123.456f) sink[threadIdx.x] = acc;
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long m = 0;
+        for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) m = t_end[w] > m ? t_end[w] : m;
+        cycles[blockIdx.x] = m;
+    }
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_ptr, 512);
+    }
+}
+
 // Launch-gap probe: a chain of dependent kernels of `ctas` CTAs x 128 threads, each spinning `spin` clock cycles after the
 // programmatic-dependency wait (griddepcontrol.wait is a no-op for a launch without the attribute).
 __global__ void launch_gap_probe_kernel(int* sink, int spin) {

@@ -159,6 +159,7 @@ HEAD_ON_TENSOR_CORES = os.environ.get("AESR_HEAD_TC", "0") != "0"
 
 
 TUNE_CONV_DEBUG, TUNE_CONV_T, TUNE_CONV_NBUF, TUNE_CONV_STAGES, TUNE_HEAD_MMA = range(5)
+TUNE_FOLD = 9
 
 
 def set_tuning(key: int, value: int) -> None:
