@@ -153,8 +153,8 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias: Optional[torch.Tensor
 
 
 # Decoder head conv inside the fused tail: False (default) = CUDA cores, fp32 activations and filter; True = tensor cores
-# (activations written back to tensor memory as a 16-bit A operand).  Measured equal within 1 % on B200 (the tile is
-# bound by reading its 64 KB accumulator out of TMEM either way, profiles/README.md), so the more exact one is the default.
+# (activations written back to tensor memory as a 16-bit A operand).  Measured equal within a few % on B200 (the tensor-core
+# variant is bound by the latency of its two-phase epilogue), so the more exact one is the default.
 HEAD_ON_TENSOR_CORES = os.environ.get("AESR_HEAD_TC", "0") != "0"
 
 
