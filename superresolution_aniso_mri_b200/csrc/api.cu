@@ -121,6 +121,22 @@ int make_wgt_tmap(CUtensorMap* m, const void* ptr, int rows, int Cin, int KC, in
     return AESR_OK;
 }
 
+// 16-bit NHWC output (or a strided view of it) as a 4-D tensor {C, W, H, N} with explicit byte strides {W, H, N}; box = one
+// 16-channel chunk of a 16 x 8 pixel tile (32-byte rows, SWIZZLE_32B) or, box_c = 32, its 64-byte rows (SWIZZLE_64B): the
+// TMA-store epilogues of the halo kernel.
+int make_out_tmap(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, size_t sw, size_t sh, size_t sn, int box_c = 16) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)sw, (cuuint64_t)sh, (cuuint64_t)sn};
+    cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)CONV_TILE_W, (cuuint32_t)CONV_TILE_H, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(AESR_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed: %d", (int)r);
+    return AESR_OK;
+}
+
 template <bool FP16>
 __global__ void pack_conv3x3_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cout, int Cin,
                                            int transpose_flip) {
@@ -316,10 +332,12 @@ int halo_pick_bn(int Cin, int Cout) {
 // 8 = AESR_NO_SPLITK streamed conv kernel without split-K (A/B measurements).
 // 9 = AESR_FOLD 32 -> 32 layers on conv3x3_fold_kernel (horizontal taps folded into N = 96; measured SLOWER than the tap-by-tap
 //     halo kernel, profiles/r08_fold_sweep.txt: kept as an opt-in experiment with its tests).
-int g_tune[10] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+// 10 = AESR_NO_TMA_STORE inference epilogues with per-thread global stores instead of staged TMA stores (A/B measurements).
+int g_tune[11] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 int tune(int key) {
-    static const char* names[10] = {"AESR_CONV_DEBUG", "AESR_CONV_T", "AESR_CONV_NBUF", "AESR_CONV_STAGES", "AESR_HEAD_MMA",
-                                    "AESR_STEM_CUDA_CORES", "AESR_WGRAD_NO_FOLD", "AESR_WGRAD_CTAS", "AESR_NO_SPLITK", "AESR_FOLD"};
+    static const char* names[11] = {"AESR_CONV_DEBUG", "AESR_CONV_T", "AESR_CONV_NBUF", "AESR_CONV_STAGES", "AESR_HEAD_MMA",
+                                    "AESR_STEM_CUDA_CORES", "AESR_WGRAD_NO_FOLD", "AESR_WGRAD_CTAS", "AESR_NO_SPLITK", "AESR_FOLD",
+                                    "AESR_NO_TMA_STORE"};
     if (g_tune[key] < 0) g_tune[key] = getenv(names[key]) ? atoi(getenv(names[key])) : 0;
     return g_tune[key];
 }
@@ -329,7 +347,7 @@ int tune(int key) {
 // epilogue), T as large as that allows; the activation ring must still hold >= 3 stages next to the resident filter
 // bank (2 * kchunks for multi-chunk layers, 2 for T = 1).
 template <int KC>
-void halo_pick_T(int BN, int Cin, int tiles_y, int extra, int* T_out, int* stages_out, int* nbuf_out) {
+void halo_pick_T(int BN, int Cin, int tiles_y, int extra, int* T_out, int* stages_out, int* nbuf_out, bool staged = false) {
     using S = HaloSmem<KC>;
     const int kchunks = Cin / KC;
     const int forced = tune(1), forced_nbuf = tune(2), stage_cap = tune(3);
@@ -346,7 +364,9 @@ void halo_pick_T(int BN, int Cin, int tiles_y, int extra, int* T_out, int* stage
             int stages = CONV_MAX_STAGES;
             if (stage_cap >= 2 && stage_cap < stages) stages = stage_cap;
             while (stages > 1 && S::total_bytes(BN, Cin, T, stages) + extra > g_max_smem_optin) --stages;
-            const int need = (T == 1) ? 2 : (kchunks > 1 ? 2 * kchunks : 3);
+            // (with the TMA-store staging behind the tail two stages of a T = 2 super-tile measure like three,
+            //  profiles/r01i: dec.2 0.364 vs 0.369 ms, and beat T = 1 with more stages)
+            const int need = (T == 1) ? 2 : (kchunks > 1 ? 2 * kchunks : (staged ? 2 : 3));
             if (S::total_bytes(BN, Cin, T, stages) + extra <= g_max_smem_optin && (stages >= need || T == 1)) {
                 *T_out = T;
                 *stages_out = stages;
@@ -425,7 +445,30 @@ int launch_halo(const void* x, const void* w, const void* head_w16, ConvParams p
     const bool head_mma = p.out_mode == OUT_SHUFFLE2_HEAD && !head_tc && tune(4) != 0;
     p.head_smem = head_tc ? HEAD_SMEM_BYTES : head_mma ? HEAD_MMA_SMEM_BYTES : 0;
     int T = 1, stages = 2, nbuf = 2;
-    halo_pick_T<KC>(p.BN, p.Cin, p.tiles_y, p.head_smem, &T, &stages, &nbuf);
+    // inference instantiations (output stage compiled in, no training extras) vs the fully dynamic one
+    const bool plain = p.mul_mode == MUL_NONE && p.stats == nullptr && p.out2 == nullptr;
+    // TMA-store epilogue (conv3x3_tc.cuh conv_epilogue_lean): 4 epilogue sets x st_bufs x 4 KB behind the tail; two buffers per
+    // set when >= 3 activation stages still fit next to them, else one
+    // BN >= 64 only: the 32-column layers' short epilogue sits on the MMA -> epilogue -> MMA latency chain and the two named
+    // barriers per chunk lengthen it (dec.8 437 -> 457 us with staged stores, profiles/r09_layer_times_tma_store.txt)
+    const bool head_cc = p.out_mode == OUT_SHUFFLE2_HEAD && !head_tc && !head_mma;      // CUDA-core head: one 8 KB store per tile
+    const bool tma_st = ((plain && (p.out_mode == OUT_SAME || p.out_mode == OUT_SHUFFLE2) && p.BN >= 64) || head_cc) && tune(10) != 1;
+    p.st_bufs = 0;
+    p.st_bytes = head_cc ? 2 * CONV_ST_CHUNK_BYTES : CONV_ST_CHUNK_BYTES;
+    int staging = 0;
+    if (tma_st) {
+        for (int bufs = 2; bufs >= 1; --bufs) {
+            staging = CONV_EPI_SETS * bufs * p.st_bytes + 1024;           // + alignment of the staging area to 1024 bytes
+            halo_pick_T<KC>(p.BN, p.Cin, p.tiles_y, p.head_smem + staging, &T, &stages, &nbuf, true);
+            p.st_bufs = bufs;
+            if (stages >= 3 || bufs == 1) break;
+        }
+        if (S::total_bytes(p.BN, p.Cin, T, stages) + p.head_smem + staging > g_max_smem_optin || stages < 2) {
+            p.st_bufs = 0;                     // no room (largest resident banks): per-thread stores
+            staging = 0;
+        }
+    }
+    if (p.st_bufs == 0) halo_pick_T<KC>(p.BN, p.Cin, p.tiles_y, p.head_smem, &T, &stages, &nbuf);
     p.T = T;
     p.nbuf = nbuf;
     p.stiles_y = (p.tiles_y + T - 1) / T;
@@ -445,23 +488,47 @@ int launch_halo(const void* x, const void* w, const void* head_w16, ConvParams p
     int per_nb = g_sm_count / p.n_blocks;
     if (per_nb < 1) per_nb = 1;
     if (per_nb > st_total) per_nb = st_total;
-    const int smem = S::total_bytes(p.BN, p.Cin, T, stages) + p.head_smem;
+    const int smem = S::total_bytes(p.BN, p.Cin, T, stages) + p.head_smem + staging;
     const int grid = per_nb * p.n_blocks;
-    // inference instantiations (output stage compiled in, no training extras) vs the fully dynamic one
-    const bool plain = p.mul_mode == MUL_NONE && p.stats == nullptr && p.out2 == nullptr;
-#define AESR_HALO(MODE)                                                                              \
+    ConvOutMaps om;
+    memset(&om, 0, sizeof(om));
+    if (p.st_bufs > 0) {
+        if (p.out_mode == OUT_SHUFFLE2_HEAD) {
+            // fp32 [N,H,W,16] patches as a 16-bit tensor of 32 "channels": one 64-byte row per low-res pixel
+            rc = make_out_tmap(&om.m[0], p.out, p.N, p.H, p.W, 32, 64, static_cast<size_t>(p.W) * 64, static_cast<size_t>(p.H) * p.W * 64, 32);
+            if (rc != AESR_OK) return rc;
+        } else if (p.out_mode == OUT_SAME) {
+            const size_t C = static_cast<size_t>(p.Cout);
+            rc = make_out_tmap(&om.m[0], p.out, p.N, p.H, p.W, p.Cout, C * 2, p.W * C * 2, static_cast<size_t>(p.H) * p.W * C * 2);
+            if (rc != AESR_OK) return rc;
+        } else {
+            // depth-to-space: phase ph = 2a+b of low-res pixel (y,x) is hi-res pixel (2y+a, 2x+b) of the [N,2H,2W,C] output
+            const size_t C = static_cast<size_t>(p.Cout >> 2), W2 = 2 * static_cast<size_t>(p.W), H2 = 2 * static_cast<size_t>(p.H);
+            for (int ph = 0; ph < 4; ++ph) {
+                const uint16_t* base = static_cast<const uint16_t*>(p.out) + ((ph >> 1) * W2 + (ph & 1)) * C;
+                rc = make_out_tmap(&om.m[ph], base, p.N, p.H, p.W, static_cast<int>(C), 2 * C * 2, 2 * W2 * C * 2, H2 * W2 * C * 2);
+                if (rc != AESR_OK) return rc;
+            }
+        }
+    }
+#define AESR_HALO_T(MODE, TM)                                                                        \
     {                                                                                                \
         static int configured = 0;                                                                   \
-        rc = set_max_smem(conv3x3_halo_kernel<KC, MODE>, &configured);                               \
+        rc = set_max_smem(conv3x3_halo_kernel<KC, MODE, TM>, &configured);                           \
         if (rc != AESR_OK) return rc;                                                                \
-        conv3x3_halo_kernel<KC, MODE><<<grid, CONV_THREADS, smem, stream>>>(tx, tw, th, p);          \
+        conv3x3_halo_kernel<KC, MODE, TM><<<grid, CONV_THREADS, smem, stream>>>(tx, tw, th, om, p);  \
+    }
+#define AESR_HALO(MODE) AESR_HALO_T(MODE, false)
+#define AESR_HALO_ST(MODE)                                                                           \
+    {                                                                                                \
+        if (p.st_bufs > 0) AESR_HALO_T(MODE, true) else AESR_HALO_T(MODE, false)                     \
     }
     if (head_tc) AESR_HALO(OUT_SHUFFLE2_HEAD_TC)
     else if (head_mma) AESR_HALO(OUT_SHUFFLE2_HEAD_MMA)
-    else if (p.out_mode == OUT_SHUFFLE2_HEAD) AESR_HALO(OUT_SHUFFLE2_HEAD)
-    else if (plain && p.out_mode == OUT_SAME) AESR_HALO(OUT_SAME)
+    else if (p.out_mode == OUT_SHUFFLE2_HEAD) AESR_HALO_ST(OUT_SHUFFLE2_HEAD)
+    else if (plain && p.out_mode == OUT_SAME) AESR_HALO_ST(OUT_SAME)
     else if (plain && p.out_mode == OUT_AVGPOOL2) AESR_HALO(OUT_AVGPOOL2)
-    else if (plain && p.out_mode == OUT_SHUFFLE2) AESR_HALO(OUT_SHUFFLE2)
+    else if (plain && p.out_mode == OUT_SHUFFLE2) AESR_HALO_ST(OUT_SHUFFLE2)
     else if (plain && p.out_mode == OUT_SAME_F32) AESR_HALO(OUT_SAME_F32)
     // training instantiations (conv3x3_tc.cuh ConvLean): no eval-BatchNorm affine, no second output except the max-pool
     else if (!p.scale && p.out_mode == OUT_SAME_MAXPOOL2 && p.mul_mode == MUL_NONE && !p.stats) AESR_HALO(OUT_SAME_MAXPOOL2)
@@ -469,6 +536,8 @@ int launch_halo(const void* x, const void* w, const void* head_w16, ConvParams p
     else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode != MUL_NONE && p.stats && p.stats_sum_only) AESR_HALO(LEAN_SAME_MUL_SUM)
     else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode == MUL_NONE && p.stats && !p.stats_sum_only) AESR_HALO(LEAN_SAME_STATS)
     else AESR_HALO(-1)
+#undef AESR_HALO_ST
+#undef AESR_HALO_T
 #undef AESR_HALO
     return check_launch("conv3x3_halo");
 }
@@ -495,7 +564,7 @@ int aesr_init(int device) {
 const char* aesr_last_error(void) { return g_err; }
 
 int aesr_set_tuning(int key, int value) {
-    if (key < 0 || key > 9 || value < 0) return fail(AESR_ERR_INVALID, "set_tuning: key %d value %d", key, value);
+    if (key < 0 || key > 10 || value < 0) return fail(AESR_ERR_INVALID, "set_tuning: key %d value %d", key, value);
     g_tune[key] = value;
     return AESR_OK;
 }

@@ -69,6 +69,10 @@ struct ConvParams {
     int T, stiles_y;        // halo kernel: M-tiles stacked vertically per super-tile, super-tile rows per image
     int head_smem;          // bytes reserved behind the filter bank for the 16 x 32 head filter block (0 or 1024)
     int nbuf;               // halo kernel: TMEM buffers (super-tiles in flight between the MMA issuer and the epilogue), 2..4
+    int st_bufs;            // halo kernel, OUT_SAME / OUT_SHUFFLE2 / OUT_SHUFFLE2_HEAD inference epilogues: staging buffers per epilogue
+                            // set for TMA stores (1 or 2; 4 KB = a 16-channel chunk of a tile, 8 KB = a tile of head patches);
+                            // 0 = per-thread global stores
+    int st_bytes;           // bytes of one staging buffer
     int fp16;               // 1: activations / weights are fp16, 0: bf16
     int debug;              // profiling only (AESR_CONV_DEBUG): bit0 = skip the MMAs, bit1 = skip the activation TMA loads
     // epilogue
@@ -113,6 +117,14 @@ constexpr int HALO_H = CONV_TILE_H + 2;     // 18
 constexpr int HALO_W = CONV_TILE_W + 2;     // 10
 constexpr int CONV_TAIL_BYTES = 256 + 5 * 512 * 4;   // barriers + tmem ptr + per-channel epilogue constants + BN statistics
                                                      // (s_stats: [2 passes][2][Cout], Cout <= 256 when statistics are taken)
+
+// Output tensor maps of the TMA-store epilogue: [0] = the NHWC output (OUT_SAME); OUT_SHUFFLE2: [ph] = the strided view of the
+// hi-res output that holds phase ph = 2a+b, i.e. pixels (2y+a, 2x+b), as a {C, W, H, N} tensor of the LOW-res extents.
+struct ConvOutMaps {
+    CUtensorMap m[4];
+};
+constexpr int CONV_ST_CHUNK_BYTES = CONV_TILE_M * 32;      // one 16-channel chunk of a tile: 128 pixels x 32 bytes
+constexpr int CONV_ST_BAR0 = 8;                             // named barriers 8..11: one per epilogue set
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi, int fp16) {
     if (fp16) {
@@ -511,9 +523,23 @@ __host__ __device__ constexpr int lean_out(int mode) { return mode >= 16 ? OUT_S
 __host__ __device__ constexpr bool lean_mul(int mode) { return mode == LEAN_SAME_MUL || mode == LEAN_SAME_MUL_SUM; }
 __host__ __device__ constexpr bool lean_stats(int mode) { return mode == LEAN_SAME_STATS || mode == LEAN_SAME_MUL_SUM; }
 
-template <int KMODE>
+// TMA-store path (p.st_bufs > 0; OUT_SAME / OUT_SHUFFLE2 without training extras): the 16-channel chunk of the tile goes to a
+// 4 KB staging buffer of the epilogue set (row = TMEM lane = pixel, 32 bytes) and ONE elected thread stores it with
+// cp.async.bulk.tensor (box {16 ch, 8, 16, 1}, clipped at the image bounds by the hardware) instead of 128 threads x 2 STG.128.
+// Measured (profiles/r09_store_cost_stage_isolation.txt): the per-thread global stores cost the 64 / 128-column layers 14-29 %
+// (dec.2 0.317 -> 0.246 ms, dec.6 0.540 -> 0.387 ms without them) although the epilogue warps mostly WAIT for the MMAs there;
+// the same bytes written to shared memory instead cost ~nothing (dec.2 0.250, dec.6 0.392 ms).  Global stores enter the
+// sub-partition's MIO queue, which the MMA issuer (warp 1) shares with epilogue warps 5, 9, 13, 17; ncu shows the issuer
+// stalled on mio_throttle at its UTCHMMAs (profiles/r08_halo_issuer_stalls.txt).
+//   st_set: this set's staging buffers, st_k: running chunk count of this thread's set (buffer = st_k % st_bufs),
+//   st_elect: this thread issues (and owns the bulk groups of) the set's stores.
+// TMAST is a compile-time property of the kernel instantiation: with the staged path only behind a run-time flag the 32-column
+// OUT_SAME instantiation (which never takes it) got 4 % slower (dec.8 0.449 -> 0.468 ms, same box).
+template <int KMODE, bool TMAST = false>
 __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
-                                                   uint64_t* tmem_empty_bar, const TileCoord& t) {
+                                                   uint64_t* tmem_empty_bar, const TileCoord& t,
+                                                   const ConvOutMaps* omaps = nullptr, uint8_t* st_set = nullptr,
+                                                   uint32_t* st_k = nullptr, bool st_elect = false, int eset = 0) {
     constexpr int MODE = lean_out(KMODE);
     constexpr bool WITH_MUL = lean_mul(KMODE), WITH_STATS = lean_stats(KMODE);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -644,6 +670,31 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) o4[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
             }
+        } else if (TMAST && (KMODE == OUT_SAME || KMODE == OUT_SHUFFLE2)) {
+            const uint4 p0 = pack8(v, fp16), p1 = pack8(v + 8, fp16);
+            const uint32_t k = *st_k;
+            uint8_t* buf = st_set + (p.st_bufs == 2 ? (k & 1u) : 0u) * p.st_bytes;
+            // the store that last used this buffer (chunk k - st_bufs) has been read out of shared memory
+            if (st_elect) {
+                if (p.st_bufs == 2) bulk_wait_group_read<1>();
+                else bulk_wait_group_read<0>();
+            }
+            named_bar_sync(CONV_ST_BAR0 + eset, 128);
+            const int sw = (row >> 2) & 1;             // CU_TENSOR_MAP_SWIZZLE_32B (buffer 1024-byte aligned): conflict-free
+            sts_u4(buf + row * 32 + 16 * sw, p0);
+            sts_u4(buf + row * 32 + 16 * (sw ^ 1), p1);
+            fence_proxy_async();                 // generic-proxy writes -> visible to the async proxy (TMA)
+            named_bar_sync(CONV_ST_BAR0 + eset, 128);
+            if (st_elect && !(p.debug & 4)) {
+                if (KMODE == OUT_SAME) {
+                    tma_store_4d(&omaps->m[0], buf, cg, t.x0, t.y0, t.n);
+                } else {
+                    const int ph = cg / Cpix;
+                    tma_store_4d(&omaps->m[ph], buf, cg - ph * Cpix, t.x0, t.y0, t.n);
+                }
+                bulk_commit_group();
+            }
+            *st_k = k + 1;
         } else if ((MODE == OUT_SAME || MODE == OUT_SHUFFLE2 || MODE == OUT_SAME_MAXPOOL2) && p.BN >= 64) {
             // Lane pairs (x, x+1) trade halves so that every store instruction writes whole 32-byte sectors: lane 2i
             // holds pixel P's channels [c0, c0+16) = 16-byte halves A0 A1, lane 2i+1 pixel P+1's B0 B1.  Stored directly
@@ -710,8 +761,10 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
 // profiles/r02f_head_scalar_vs_packed.txt): a 3-operand FFMA occupies the fp32 pipe for two cycles per warp just like an
 // FFMA2, so the packed form is the pipe's full rate and 576 x 2 cycles per tile and scheduler is this epilogue's floor.
 constexpr int HEAD_EPI_CW = 4;
+template <bool TMAST>
 __device__ __forceinline__ void conv_epilogue_head_tile(const ConvParams& p, const ConvBarriers& bars, uint32_t tmem_acc,
-                                                        uint64_t* tmem_empty_bar, const TileCoord& t) {
+                                                        uint64_t* tmem_empty_bar, const TileCoord& t, const ConvOutMaps* omaps,
+                                                        uint8_t* st_set, uint32_t* st_k, bool st_elect, int eset) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3;
     const int row = q * 32 + lane;
@@ -773,7 +826,31 @@ __device__ __forceinline__ void conv_epilogue_head_tile(const ConvParams& p, con
             }
         }
     }
-    if (inb && !(p.debug & 4)) {
+    if (TMAST) {
+        // the tile's 128 patches (64 bytes each) through the set's staging buffer and ONE TMA store (see conv_epilogue_lean):
+        // the per-thread stores cost this layer 14 % (1.073 -> 0.918 ms without them, profiles/r01u)
+        const uint32_t k = *st_k;
+        uint8_t* buf = st_set + (p.st_bufs == 2 ? (k & 1u) : 0u) * p.st_bytes;
+        if (st_elect) {
+            if (p.st_bufs == 2) bulk_wait_group_read<1>();
+            else bulk_wait_group_read<0>();
+        }
+        named_bar_sync(CONV_ST_BAR0 + eset, 128);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 f = make_float4(hp2[4 * i].x + hp2[4 * i].y, hp2[4 * i + 1].x + hp2[4 * i + 1].y,
+                                         hp2[4 * i + 2].x + hp2[4 * i + 2].y, hp2[4 * i + 3].x + hp2[4 * i + 3].y);
+            sts_u4(buf + row * 64 + 16 * (i ^ ((row >> 1) & 3)),      // CU_TENSOR_MAP_SWIZZLE_64B (buffer 1024-byte aligned): conflict-free
+                   make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w)));
+        }
+        fence_proxy_async();
+        named_bar_sync(CONV_ST_BAR0 + eset, 128);
+        if (st_elect && !(p.debug & 4)) {
+            tma_store_4d(&omaps->m[0], buf, 0, t.x0, t.y0, t.n);
+            bulk_commit_group();
+        }
+        *st_k = k + 1;
+    } else if (inb && !(p.debug & 4)) {
         float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) +
                                               ((static_cast<size_t>(t.n) * p.H + y) * p.W + x) * 16);
 #pragma unroll
@@ -998,10 +1075,11 @@ __host__ __device__ constexpr uint32_t halo_tmem_cols(int T, int BN, int nbuf) {
     return (c <= 32) ? 32 : (c <= 64) ? 64 : (c <= 128) ? 128 : (c <= 256) ? 256 : 512;
 }
 
-template <int KC, int MODE>        // MODE: -1 = run-time epilogue, OUT_* = that output stage compiled in
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+template <int KC, int MODE, bool TMAST = false>   // MODE: -1 = run-time epilogue, OUT_* = that output stage compiled in; TMAST:
+__global__ void __launch_bounds__(CONV_THREADS, 1)  // staged TMA stores (OUT_SAME / OUT_SHUFFLE2 / OUT_SHUFFLE2_HEAD, p.st_bufs >= 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                    const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ ConvParams p) {
+                    const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ ConvOutMaps omaps,
+                    const __grid_constant__ ConvParams p) {
     using S = HaloSmem<KC>;
     constexpr uint32_t LAYOUT = (KC == 64) ? UMMA_LAYOUT_SW128 : UMMA_LAYOUT_SW64;
     constexpr uint32_t ROW_BYTES = S::ROW_BYTES;
@@ -1159,6 +1237,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int nsets = (nbuf * T < CONV_EPI_SETS) ? nbuf * T : CONV_EPI_SETS;       // 2 or 4
         int i = 0, buf = 0;
         uint32_t buf_phase = 0, head_uses = 0;
+        // TMA-store staging of this set (behind the tail), the set's issuing thread, its running chunk count
+        uint8_t* st_set = a_smem + num_stages * a_stage + ((CONV_TAIL_BYTES + 1023) & ~1023) + eset * p.st_bufs * p.st_bytes;
+        const bool st_elect = ((warp - CONV_FIRST_EPI_WARP) & 3) == 0 && lane == 0;
+        uint32_t st_k = 0;
         const uint64_t h_tmpl = make_smem_desc(smem_u32(h_smem), 8 * 64, UMMA_LAYOUT_SW64);
         const uint32_t hdesc_lo = static_cast<uint32_t>(h_tmpl), hdesc_hi = static_cast<uint32_t>(h_tmpl >> 32);
         if (MODE == OUT_SHUFFLE2_HEAD_TC) mbar_wait(bars.b_full, 0);       // the head filter block landed with the bank
@@ -1185,9 +1267,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     } else if (MODE == OUT_SHUFFLE2_HEAD_MMA) {
                         conv_epilogue_head_mma_tile(p, bars, acc, &bars.tmem_empty[buf], tc, reinterpret_cast<const uint2*>(h_smem));
                     } else if (MODE == OUT_SHUFFLE2_HEAD) {
-                        conv_epilogue_head_tile(p, bars, acc, &bars.tmem_empty[buf], tc);
+                        conv_epilogue_head_tile<TMAST>(p, bars, acc, &bars.tmem_empty[buf], tc, &omaps, st_set, &st_k, st_elect, eset);
                     }
-                    else if (MODE >= 0) conv_epilogue_lean<MODE>(p, bars, acc, &bars.tmem_empty[buf], tc);
+                    else if (MODE >= 0) conv_epilogue_lean<MODE, TMAST>(p, bars, acc, &bars.tmem_empty[buf], tc, &omaps, st_set, &st_k, st_elect, eset);
                     else conv_epilogue_tile(p, bars, acc, &bars.tmem_empty[buf], tc);
                 } else {                       // M-tile below the image: nothing to read, release the buffer
                     tc_fence_before();
@@ -1197,6 +1279,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             }
             if (++buf == nbuf) { buf = 0; buf_phase ^= 1; }
         }
+        if (TMAST && st_elect) bulk_wait_group_all();             // stores issued by this thread
     }
     conv_teardown<(MODE < 0) || lean_stats(MODE)>(p, bars, tmem_base, tmem_cols);
 }
