@@ -452,7 +452,13 @@ int launch_halo(const void* x, const void* w, const void* head_w16, ConvParams p
     // BN >= 64 only: the 32-column layers' short epilogue sits on the MMA -> epilogue -> MMA latency chain and the two named
     // barriers per chunk lengthen it (dec.8 437 -> 457 us with staged stores, profiles/r09_layer_times_tma_store.txt)
     const bool head_cc = p.out_mode == OUT_SHUFFLE2_HEAD && !head_tc && !head_mma;      // CUDA-core head: one 8 KB store per tile
-    const bool tma_st = ((plain && (p.out_mode == OUT_SAME || p.out_mode == OUT_SHUFFLE2) && p.BN >= 64) || head_cc) && tune(10) != 1;
+    // training instantiations with an OUT_SAME-layout main output (ConvLean variants, max-pool second output) take it as well
+    const bool lean_train = !p.scale && ((p.out_mode == OUT_SAME_MAXPOOL2 && p.mul_mode == MUL_NONE && !p.stats) ||
+                                         (p.out_mode == OUT_SAME && !p.out2 && (p.mul_mode != MUL_NONE || p.stats) &&
+                                          !(p.mul_mode == MUL_NONE && p.stats && p.stats_sum_only) &&
+                                          !(p.mul_mode != MUL_NONE && p.stats && !p.stats_sum_only)));
+    const bool tma_st = (((plain && (p.out_mode == OUT_SAME || p.out_mode == OUT_SHUFFLE2)) || lean_train) && p.BN >= 64 || head_cc) &&
+                        tune(10) != 1;
     p.st_bufs = 0;
     p.st_bytes = head_cc ? 2 * CONV_ST_CHUNK_BYTES : CONV_ST_CHUNK_BYTES;
     int staging = 0;
@@ -497,7 +503,7 @@ int launch_halo(const void* x, const void* w, const void* head_w16, ConvParams p
             // fp32 [N,H,W,16] patches as a 16-bit tensor of 32 "channels": one 64-byte row per low-res pixel
             rc = make_out_tmap(&om.m[0], p.out, p.N, p.H, p.W, 32, 64, static_cast<size_t>(p.W) * 64, static_cast<size_t>(p.H) * p.W * 64, 32);
             if (rc != AESR_OK) return rc;
-        } else if (p.out_mode == OUT_SAME) {
+        } else if (p.out_mode == OUT_SAME || p.out_mode == OUT_SAME_MAXPOOL2) {
             const size_t C = static_cast<size_t>(p.Cout);
             rc = make_out_tmap(&om.m[0], p.out, p.N, p.H, p.W, p.Cout, C * 2, p.W * C * 2, static_cast<size_t>(p.H) * p.W * C * 2);
             if (rc != AESR_OK) return rc;
@@ -531,10 +537,10 @@ int launch_halo(const void* x, const void* w, const void* head_w16, ConvParams p
     else if (plain && p.out_mode == OUT_SHUFFLE2) AESR_HALO_ST(OUT_SHUFFLE2)
     else if (plain && p.out_mode == OUT_SAME_F32) AESR_HALO(OUT_SAME_F32)
     // training instantiations (conv3x3_tc.cuh ConvLean): no eval-BatchNorm affine, no second output except the max-pool
-    else if (!p.scale && p.out_mode == OUT_SAME_MAXPOOL2 && p.mul_mode == MUL_NONE && !p.stats) AESR_HALO(OUT_SAME_MAXPOOL2)
-    else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode != MUL_NONE && !p.stats) AESR_HALO(LEAN_SAME_MUL)
-    else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode != MUL_NONE && p.stats && p.stats_sum_only) AESR_HALO(LEAN_SAME_MUL_SUM)
-    else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode == MUL_NONE && p.stats && !p.stats_sum_only) AESR_HALO(LEAN_SAME_STATS)
+    else if (!p.scale && p.out_mode == OUT_SAME_MAXPOOL2 && p.mul_mode == MUL_NONE && !p.stats) AESR_HALO_ST(OUT_SAME_MAXPOOL2)
+    else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode != MUL_NONE && !p.stats) AESR_HALO_ST(LEAN_SAME_MUL)
+    else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode != MUL_NONE && p.stats && p.stats_sum_only) AESR_HALO_ST(LEAN_SAME_MUL_SUM)
+    else if (!p.scale && p.out_mode == OUT_SAME && !p.out2 && p.mul_mode == MUL_NONE && p.stats && !p.stats_sum_only) AESR_HALO_ST(LEAN_SAME_STATS)
     else AESR_HALO(-1)
 #undef AESR_HALO_ST
 #undef AESR_HALO_T

@@ -670,7 +670,7 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
 #pragma unroll
                 for (int j4 = 0; j4 < 4; ++j4) o4[j4] = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
             }
-        } else if (TMAST && (KMODE == OUT_SAME || KMODE == OUT_SHUFFLE2)) {
+        } else if (TMAST && (MODE == OUT_SAME || MODE == OUT_SAME_MAXPOOL2 || MODE == OUT_SHUFFLE2)) {
             const uint4 p0 = pack8(v, fp16), p1 = pack8(v + 8, fp16);
             const uint32_t k = *st_k;
             uint8_t* buf = st_set + (p.st_bufs == 2 ? (k & 1u) : 0u) * p.st_bytes;
@@ -686,7 +686,7 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
             fence_proxy_async();                 // generic-proxy writes -> visible to the async proxy (TMA)
             named_bar_sync(CONV_ST_BAR0 + eset, 128);
             if (st_elect && !(p.debug & 4)) {
-                if (KMODE == OUT_SAME) {
+                if (MODE != OUT_SHUFFLE2) {
                     tma_store_4d(&omaps->m[0], buf, cg, t.x0, t.y0, t.n);
                 } else {
                     const int ph = cg / Cpix;
