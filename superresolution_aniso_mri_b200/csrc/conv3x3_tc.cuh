@@ -550,6 +550,7 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
     const int y = t.y0 + py, x = t.x0 + px;
     const bool inb = (y < H) && (x < W);
     const float neg_slope = (p.act == ACT_LEAKY) ? p.slope : (p.act == ACT_RELU) ? 0.f : 1.f;
+    const float2 slope2 = make_float2(neg_slope, neg_slope);
     const uint32_t t_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
     const bool affine = p.scale != nullptr;
     // element offset of this thread's pixel (channel 0) in the output tensor
@@ -591,15 +592,20 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
             }
             if (p.debug & 64) continue;
             // act(a) = max(a, a * neg_slope): neg_slope = 1 (identity), 0.01 (LeakyReLU), 0 (ReLU) -- branch-free
+            // packed fp32x2 adds / multiplies (same roundings, half the issue slots: the epilogue warps of sub-partition 1 share
+            // their scheduler with the MMA issuer)
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 b = lds_f4(bars.s_bias + cg + 4 * j4);
-                const float a0 = __uint_as_float(raw[j4 * 4 + 0]) + b.x, a1 = __uint_as_float(raw[j4 * 4 + 1]) + b.y;
-                const float a2 = __uint_as_float(raw[j4 * 4 + 2]) + b.z, a3 = __uint_as_float(raw[j4 * 4 + 3]) + b.w;
-                v[j4 * 4 + 0] = fmaxf(a0, a0 * neg_slope);
-                v[j4 * 4 + 1] = fmaxf(a1, a1 * neg_slope);
-                v[j4 * 4 + 2] = fmaxf(a2, a2 * neg_slope);
-                v[j4 * 4 + 3] = fmaxf(a3, a3 * neg_slope);
+                const float2 a01 = __fadd2_rn(make_float2(__uint_as_float(raw[j4 * 4 + 0]), __uint_as_float(raw[j4 * 4 + 1])),
+                                              make_float2(b.x, b.y));
+                const float2 a23 = __fadd2_rn(make_float2(__uint_as_float(raw[j4 * 4 + 2]), __uint_as_float(raw[j4 * 4 + 3])),
+                                              make_float2(b.z, b.w));
+                const float2 s01 = __fmul2_rn(a01, slope2), s23 = __fmul2_rn(a23, slope2);
+                v[j4 * 4 + 0] = fmaxf(a01.x, s01.x);
+                v[j4 * 4 + 1] = fmaxf(a01.y, s01.y);
+                v[j4 * 4 + 2] = fmaxf(a23.x, s23.x);
+                v[j4 * 4 + 3] = fmaxf(a23.y, s23.y);
             }
         }
         if (WITH_MUL) {
@@ -641,10 +647,9 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
                 const float4 sc = lds_f4(bars.s_scale + cg + 4 * j4), sh = lds_f4(bars.s_shift + cg + 4 * j4);
-                v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], sc.x, sh.x);
-                v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], sc.y, sh.y);
-                v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], sc.z, sh.z);
-                v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], sc.w, sh.w);
+                const float2 r01 = __ffma2_rn(make_float2(v[j4 * 4 + 0], v[j4 * 4 + 1]), make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+                const float2 r23 = __ffma2_rn(make_float2(v[j4 * 4 + 2], v[j4 * 4 + 3]), make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+                v[j4 * 4 + 0] = r01.x; v[j4 * 4 + 1] = r01.y; v[j4 * 4 + 2] = r23.x; v[j4 * 4 + 3] = r23.y;
             }
         }
         size_t off;
