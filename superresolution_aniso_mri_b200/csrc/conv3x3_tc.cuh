@@ -1202,15 +1202,36 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                             const uint32_t d_tmem = d_tmem0 + t * p.BN;
                             const uint32_t a_lo = a_stage_lo + t * kTile16;
                             if (elect_one_sync()) {
-                                uint32_t b_lo = b_kc;
+                                if (KC == 64) {
+                                    // filter rows rolled, the 3 x 4 MMAs of a row unrolled: with all 9 taps unrolled the 2 x 36
+                                    // descriptor pairs exceed the 63 uniform registers and ptxas spills them through vector registers
+                                    // (156 MOV.SPILL / R2UR.FILL and 176 R2UR between the UTCHMMAs of a tile).  Same box: 64->64
+                                    // pooled 210 -> 183 us, 128->128 274 -> 214 us, dec.2 / dec.6 -3 % (profiles/r09_issuer_loop_ab.txt);
+                                    // the KC = 32 loop (18 pairs, 9 spill moves) is 2-3 % FASTER fully unrolled and stays so.
+                                    uint32_t b_lo = b_kc, a_row = a_lo;
+#pragma unroll 1
+                                    for (int dy = 0; dy < 3; ++dy) {
 #pragma unroll
-                                for (int tap = 0; tap < 9; ++tap) {
-                                    const uint32_t a_tap = a_lo + ((tap / 3) * HALO_W + (tap % 3)) * kRow16;
+                                        for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
-                                    for (int k = 0; k < KC / 16; ++k)
-                                        umma_f16_split(d_tmem, a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
-                                                       (tap | k) != 0 ? 1u : static_cast<uint32_t>(kc != 0));
-                                    b_lo += b_tap16;
+                                            for (int k = 0; k < KC / 16; ++k)
+                                                umma_f16_split(d_tmem, a_row + dx * kRow16 + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
+                                                               (dy | dx | k) != 0 ? 1u : static_cast<uint32_t>(kc != 0));
+                                            b_lo += b_tap16;
+                                        }
+                                        a_row += HALO_W * kRow16;
+                                    }
+                                } else {
+                                    uint32_t b_lo = b_kc;
+#pragma unroll
+                                    for (int tap = 0; tap < 9; ++tap) {
+                                        const uint32_t a_tap = a_lo + ((tap / 3) * HALO_W + (tap % 3)) * kRow16;
+#pragma unroll
+                                        for (int k = 0; k < KC / 16; ++k)
+                                            umma_f16_split(d_tmem, a_tap + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc,
+                                                           (tap | k) != 0 ? 1u : static_cast<uint32_t>(kc != 0));
+                                        b_lo += b_tap16;
+                                    }
                                 }
                             }
                             __syncwarp();
