@@ -507,6 +507,29 @@ __global__ void splitk_finish_kernel(const float* __restrict__ ws, int ksplit, s
     }
 }
 
+// 2x2 pooling of 16 per-lane values over the lanes {l, l^1, l^8, l^9} of a window (x neighbour, y neighbour; tile origins are
+// even), transposed: each round a lane keeps half of its values, sends the other half to its partner and combines what it
+// receives -- 8 + 4 shuffles instead of 2 x 16 (shuffles are MIO instructions like the issuer's tcgen05.mma).  On return r[0..3]
+// = the window's sums (maxima) of channels 8 * (lane & 1) + 4 * ((lane >> 3) & 1) + 0..3: the four lanes of a window hold its
+// 16 channels.  Same association as summing the x pair first: bit-identical to the straightforward version.
+template <bool IS_MAX>
+__device__ __forceinline__ void pool2x2_transposed(const float (&v)[16], int lane, float (&r)[4]) {
+    const bool hx = lane & 1, hy = lane & 8;
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float keep = hx ? v[8 + j] : v[j], send = hx ? v[j] : v[8 + j];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        a[j] = IS_MAX ? fmaxf(keep, recv) : keep + recv;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float keep = hy ? a[4 + j] : a[j], send = hy ? a[j] : a[4 + j];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+        r[j] = IS_MAX ? fmaxf(keep, recv) : keep + recv;
+    }
+}
+
 // Lean epilogue of the inference output stages (OUT_SAME, OUT_AVGPOOL2, OUT_SHUFFLE2, OUT_SAME_F32; no training extras): 16 accumulator
 // columns per TMEM load, so that 16 values + addresses + the role's loop state stay far below the 96 registers a
 // 576-thread CTA allows (the 32-column generic epilogue spills its loop state, ncu: LDL stalls in every tile).
@@ -565,7 +588,7 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
         Cpix = p.Cout;
         const int Ho = H >> 1, Wo = W >> 1, yo = y >> 1, xo = x >> 1;
         pix = (static_cast<size_t>(t.n) * Ho + yo) * Wo + xo;
-        store = ((px | py) & 1) == 0 && yo < Ho && xo < Wo;
+        store = yo < Ho && xo < Wo;             // all four lanes of a window store 4 channels each (pool2x2_transposed)
     } else {                                    // OUT_SHUFFLE2: phase offset added per chunk
         Cpix = p.Cout >> 2;
         pix = (static_cast<size_t>(t.n) * 2 * H + 2 * y) * (2 * W) + 2 * x;
@@ -654,15 +677,12 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
         }
         size_t off;
         if (MODE == OUT_AVGPOOL2) {
-            // 2x2 window = lanes {l, l^1, l^8} (x neighbour, y neighbour): tile origins are even.
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float a = v[j];
-                a += __shfl_xor_sync(0xffffffffu, a, 1);
-                a += __shfl_xor_sync(0xffffffffu, a, 8);
-                v[j] = a * 0.25f;
-            }
-            off = pix * Cpix + cg;
+            float r[4];
+            pool2x2_transposed<false>(v, lane, r);
+            if (store)
+                *reinterpret_cast<uint2*>(out16 + pix * Cpix + cg + 8 * (lane & 1) + 4 * ((lane >> 3) & 1)) =
+                    make_uint2(pack2(r[0] * 0.25f, r[1] * 0.25f, fp16), pack2(r[2] * 0.25f, r[3] * 0.25f, fp16));
+            continue;
         } else if (MODE == OUT_SHUFFLE2) {
             const int ph = cg / Cpix, ch = cg - ph * Cpix;
             off = (pix + static_cast<size_t>(ph >> 1) * (2 * W) + (ph & 1)) * Cpix + ch;
@@ -731,21 +751,13 @@ __device__ __forceinline__ void conv_epilogue_lean(const ConvParams& p, const Co
             o4[1] = pack8(v + 8, fp16);
         }
         if (MODE == OUT_SAME_MAXPOOL2) {
-            // 2x2 window = lanes {l, l^1, l^8} (x neighbour, y neighbour): tile origins are even.
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float a = v[j];
-                a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
-                a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 8));
-                v[j] = a;
-            }
+            float r[4];
+            pool2x2_transposed<true>(v, lane, r);
             const int Ho = H >> 1, Wo = W >> 1, yo = y >> 1, xo = x >> 1;
-            if (((px | py) & 1) == 0 && yo < Ho && xo < Wo && !(p.debug & 4)) {
-                uint4* o4 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out2) +
-                                                     ((static_cast<size_t>(t.n) * Ho + yo) * Wo + xo) * Cpix + cg);
-                o4[0] = pack8(v, fp16);
-                o4[1] = pack8(v + 8, fp16);
-            }
+            if (yo < Ho && xo < Wo && !(p.debug & 4))
+                *reinterpret_cast<uint2*>(static_cast<uint16_t*>(p.out2) + ((static_cast<size_t>(t.n) * Ho + yo) * Wo + xo) * Cpix + cg +
+                                          8 * (lane & 1) + 4 * ((lane >> 3) & 1)) =
+                    make_uint2(pack2(r[0], r[1], fp16), pack2(r[2], r[3], fp16));
         }
     }
 }
