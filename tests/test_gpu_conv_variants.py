@@ -1,7 +1,8 @@
-"""GPU tier: conv3x3_fold_kernel (32 -> 32 layers, horizontal taps folded into N = 96; csrc/conv3x3_fold.cuh) against torch fp32
-on 16-bit-rounded operands and against the tap-by-tap halo kernel on the same inputs.  Reference layers: enc.3, dec.8, dec.10
-(/root/reference/networks/acai_vanilla.py:55,92,94).  Tolerance: a few output ulps of the 16-bit storage type, as for the
-other conv kernels (tests/test_gpu_parity.py)."""
+"""GPU tier: variants of the tcgen05 conv kernels against each other and against torch fp32 on 16-bit-rounded operands.
+* conv3x3_fold_kernel (32 -> 32 layers, horizontal taps folded into N = 96; csrc/conv3x3_fold.cuh; opt-in) against torch fp32 and the
+  tap-by-tap halo kernel.  Reference layers: enc.3, dec.8, dec.10 (/root/reference/networks/acai_vanilla.py:55,92,94).
+* TMA-store epilogues (staged cp.async.bulk.tensor stores) against per-thread global stores: bit-identical.
+Tolerance of the torch comparisons: a few output ulps of the 16-bit storage type, as for the other conv kernels (tests/test_gpu_parity.py)."""
 import numpy as np
 import pytest
 import torch
@@ -124,3 +125,58 @@ def _fold_training_epilogues(dev, ops, dt):
     for k, sl in enumerate((slice(0, 3), slice(3, 4))):
         assert torch.allclose(s2[64 * k:64 * k + 32].cpu(), ya[sl].sum(dim=(0, 2, 3)), rtol=2e-3, atol=5e-2)
         assert torch.allclose(s2[64 * k + 32:64 * k + 64].cpu(), (ya[sl] ** 2).sum(dim=(0, 2, 3)), rtol=2e-3, atol=5e-2)
+
+
+# ------------------------------------------------------------------------------------------------ TMA-store epilogues
+# cin, cout (GEMM N), n, h, w, mode (0 same, 5 depth-to-space), affine: staged cp.async.bulk.tensor stores (clipped at the image
+# bounds by the hardware) against per-thread global stores (aesr_set_tuning key 10) -- the same values, so bit-identical.
+TMA_STORE_CASES = [(64, 64, 3, 32, 32, 0, True), (64, 64, 2, 65, 33, 0, True), (32, 64, 2, 65, 65, 0, False), (64, 128, 2, 32, 32, 0, False),
+                   (128, 128, 2, 17, 9, 0, False), (128, 64, 1, 1, 1, 0, True), (64, 128, 3, 20, 12, 5, False), (64, 128, 1, 1, 1, 5, False),
+                   (32, 128, 2, 55, 55, 5, False), (64, 64, 149, 32, 32, 0, True), (64, 128, 40, 37, 29, 5, False)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("case", TMA_STORE_CASES)
+def test_tma_store_epilogue_equals_per_thread_stores(dev, case, dtype):
+    from superresolution_aniso_mri_b200 import ops
+    cin, cout, n, h, w, mode, affine = case
+    if dtype == torch.bfloat16 and n > 3:
+        pytest.skip("bf16 covered on the small cases")
+    g = torch.Generator().manual_seed(cin + cout + h * 7 + w)
+    x = torch.randn(n, h, w, cin, generator=g).to(dtype).to(dev)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) / np.sqrt(cin * 9)).to(dev)
+    cb = cout // 4 if mode == 5 else cout
+    b = (torch.randn(cb, generator=g) * 0.1).to(dev)
+    sc = (torch.rand(cb, generator=g) + 0.5).to(dev) if affine else None
+    sh = (torch.randn(cb, generator=g) * 0.1).to(dev) if affine else None
+    wp = ops.pack_conv3x3_weight(wt, dtype=dtype)
+    shape = ops.conv_out_shape(n, h, w, cout, mode)
+    got = torch.full(shape, 7.0, dtype=dtype, device=dev)
+    ops.conv3x3(x, wp, b, act=1, scale=sc, shift=sh, out_mode=mode, out=got, algo=1)
+    want = torch.full(shape, 7.0, dtype=dtype, device=dev)
+    try:
+        ops.set_tuning(10, 1)
+        ops.conv3x3(x, wp, b, act=1, scale=sc, shift=sh, out_mode=mode, out=want, algo=1)
+    finally:
+        ops.set_tuning(10, 0)
+    assert torch.equal(got, want)
+    assert not torch.any(got == 7.0) or torch.equal(got == 7.0, want == 7.0)       # every element written (7.0 is not a plausible value)
+
+
+def test_tma_store_head_patches_equal_per_thread_stores(dev):
+    """dec.12 + head: the tile's 128 patches through one 8 KB TMA store against 128 threads x 4 STG.128."""
+    from superresolution_aniso_mri_b200 import ops
+    dt = torch.float16
+    for n, h, w in ((2, 64, 64), (3, 20, 12), (1, 1, 1), (1, 17, 9), (40, 33, 31)):
+        g = torch.Generator().manual_seed(n + h + w)
+        x = torch.randn(n, h, w, 32, generator=g).to(dt).to(dev)
+        wp = ops.pack_conv3x3_weight_up2fold((torch.randn(32, 32, 3, 3, generator=g) / 17).to(dev), dtype=dt)
+        b = (torch.randn(32, generator=g) * 0.1).to(dev)
+        w9c = (torch.randn(9, 32, generator=g) / 17).contiguous()
+        got = ops.conv3x3_up2_head(x, wp, b, w9c)
+        try:
+            ops.set_tuning(10, 1)
+            want = ops.conv3x3_up2_head(x, wp, b, w9c)
+        finally:
+            ops.set_tuning(10, 0)
+        assert torch.equal(got, want)
