@@ -72,7 +72,8 @@ const char* aesr_last_error(void);
  * variant (1 CUDA cores, 2 one tf32 term; AESR_STEM_CUDA_CORES), 6 = weight gradient without the dx fold
  * (AESR_WGRAD_NO_FOLD), 7 = cap on the CTAs of a weight-gradient launch (AESR_WGRAD_CTAS), 8 = no split-K (AESR_NO_SPLITK),
  * 9 = 32 -> 32 layers on the horizontal-tap-fold kernel (AESR_FOLD; opt-in experiment, slower), 10 = per-thread global stores
- * instead of the staged TMA stores of the conv epilogues (AESR_NO_TMA_STORE, A/B measurements).  value 0 = automatic. */
+ * instead of the staged TMA stores of the conv epilogues (AESR_NO_TMA_STORE, A/B measurements), 11 = head_gather with
+ * thread-staged windows instead of TMA loads (AESR_HEAD_GATHER_NO_TMA).  value 0 = automatic. */
 int aesr_set_tuning(int key, int value);
 int aesr_sm_count(void);
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */

@@ -333,11 +333,12 @@ int halo_pick_bn(int Cin, int Cout) {
 // 9 = AESR_FOLD 32 -> 32 layers on conv3x3_fold_kernel (horizontal taps folded into N = 96; measured SLOWER than the tap-by-tap
 //     halo kernel, profiles/r08_fold_sweep.txt: kept as an opt-in experiment with its tests).
 // 10 = AESR_NO_TMA_STORE inference epilogues with per-thread global stores instead of staged TMA stores (A/B measurements).
-int g_tune[11] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+// 11 = AESR_HEAD_GATHER_NO_TMA head_gather with thread-staged windows instead of TMA loads (A/B measurements).
+int g_tune[12] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
 int tune(int key) {
-    static const char* names[11] = {"AESR_CONV_DEBUG", "AESR_CONV_T", "AESR_CONV_NBUF", "AESR_CONV_STAGES", "AESR_HEAD_MMA",
+    static const char* names[12] = {"AESR_CONV_DEBUG", "AESR_CONV_T", "AESR_CONV_NBUF", "AESR_CONV_STAGES", "AESR_HEAD_MMA",
                                     "AESR_STEM_CUDA_CORES", "AESR_WGRAD_NO_FOLD", "AESR_WGRAD_CTAS", "AESR_NO_SPLITK", "AESR_FOLD",
-                                    "AESR_NO_TMA_STORE"};
+                                    "AESR_NO_TMA_STORE", "AESR_HEAD_GATHER_NO_TMA"};
     if (g_tune[key] < 0) g_tune[key] = getenv(names[key]) ? atoi(getenv(names[key])) : 0;
     return g_tune[key];
 }
@@ -570,7 +571,7 @@ int aesr_init(int device) {
 const char* aesr_last_error(void) { return g_err; }
 
 int aesr_set_tuning(int key, int value) {
-    if (key < 0 || key > 10 || value < 0) return fail(AESR_ERR_INVALID, "set_tuning: key %d value %d", key, value);
+    if (key < 0 || key > 11 || value < 0) return fail(AESR_ERR_INVALID, "set_tuning: key %d value %d", key, value);
     g_tune[key] = value;
     return AESR_OK;
 }
@@ -718,8 +719,40 @@ int aesr_head_gather(const float* partial, const float* bias, float* out, const 
     if ((out_image_stride & 1) || (reinterpret_cast<uintptr_t>(out) & 7))
         return fail(AESR_ERR_INVALID, "head_gather: output images must be 8-byte aligned (even stride)");
     if (static_cast<size_t>(h) * w > (1u << 28)) return fail(AESR_ERR_INVALID, "head_gather: image too large");
-    const dim3 grid((w + HG_TW - 1) / HG_TW, (h + HG_TH - 1) / HG_TH, N < 65535 ? N : 65535);
+    dim3 grid((w + HG_TW - 1) / HG_TW, (h + HG_TH - 1) / HG_TH, N < 65535 ? N : 65535);
     if (grid.y > 65535) return fail(AESR_ERR_INVALID, "head_gather: image too tall");
+    if (tune(11) != 1 && !(reinterpret_cast<uintptr_t>(partial) & 15)) {
+        // TMA version: fp32 [N,h,w,16] as {16, w, h, N}, one (8+2) x (32+2) window of patches per load, zero fill outside the image;
+        // each block walks through the images of its window position (double-buffered loads): ~5 resident blocks per SM
+        CUtensorMap tm;
+        cuuint64_t dims[4] = {16, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)N};
+        cuuint64_t strides[3] = {64, (cuuint64_t)w * 64, (cuuint64_t)h * w * 64};
+        cuuint32_t box[4] = {16, (cuuint32_t)(HG_TW + 2), (cuuint32_t)(HG_TH + 2), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = g_encode_tiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(partial), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(AESR_ERR_CUDA, "cuTensorMapEncodeTiled(head patches) failed: %d", (int)r);
+        static int configured = 0;
+        {
+            int dev = 0;
+            CUDA_TRY(cudaGetDevice(&dev));
+            const int bit = 1 << (dev & 31);
+            if (!(configured & bit)) {
+                CUDA_TRY(cudaFuncSetAttribute(head_gather_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HGT_SMEM_BYTES));
+                configured |= bit;
+            }
+        }
+        const int per_pos = grid.x * grid.y;
+        int gz = (5 * g_sm_count + per_pos - 1) / per_pos;
+        if (gz < 1) gz = 1;
+        if (gz > N) gz = N;
+        if (gz > 65535) gz = 65535;
+        grid.z = gz;
+        head_gather_tma_kernel<<<grid, 256, HGT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+            tm, bias, out, out_index, N, h, w, out_image_stride, apply_sigmoid);
+        return check_launch("head_gather_tma");
+    }
     head_gather_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         partial, bias, out, out_index, N, h, w, out_image_stride, apply_sigmoid);
     return check_launch("head_gather");

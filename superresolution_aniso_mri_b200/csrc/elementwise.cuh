@@ -513,6 +513,81 @@ head_gather_kernel(const float* __restrict__ part, const float* __restrict__ bia
     }
 }
 
+// head gather, TMA version: the (8+2) x (32+2) window of 64-byte patches of a block comes in by ONE cp.async.bulk.tensor load
+// (box {16 floats, 34, 10, 1}, SWIZZLE_64B, zero fill outside the image = the missing neighbours of border pixels), double-buffered
+// over the images a block walks through, so nothing is staged by the threads (the version above spends ~27 of its ~150
+// instructions per low-res pixel on LDG.128 + 4 scalar STS per patch, and 16 scalar LDS on reading it back).  A thread reads whole
+// 16-byte patch rows: 12 LDS.128, conflict-free under the 64-byte swizzle (the 8 lanes of a quarter warp hit 8 distinct 16-byte
+// slots).  Same summation order as head_gather_kernel: bit-identical output.
+constexpr int HGT_WIN_BYTES = (HG_TH + 2) * (HG_TW + 2) * 64;                   // 21760
+constexpr int HGT_BUF_BYTES = ((HGT_WIN_BYTES + 1023) / 1024) * 1024;           // 22528
+constexpr int HGT_SMEM_BYTES = 1024 + 2 * HGT_BUF_BYTES + 64;
+__device__ __forceinline__ float4 hgt_row(const uint8_t* win, int r, int c) {    // patch r of the window, patch row c (4 floats)
+    return lds_f4(reinterpret_cast<const float*>(win + r * 64 + 16 * (c ^ ((r >> 1) & 3))));
+}
+__global__ void __launch_bounds__(256)
+head_gather_tma_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ bias_ptr, float* __restrict__ out,
+                       const int* __restrict__ out_index, int N, int h, int w, size_t out_image_stride, int apply_sigmoid) {
+    extern __shared__ uint8_t hgt_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(hgt_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * HGT_BUF_BYTES);
+    const float bias = __ldg(bias_ptr);
+    const int W = 2 * w;
+    const int x0 = blockIdx.x * HG_TW, y0 = blockIdx.y * HG_TH;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int xl = x0 + tx, yl = y0 + ty;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap);
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    int n = blockIdx.z;
+    if (threadIdx.x == 0 && n < N) {
+        mbar_arrive_expect_tx(&full[0], HGT_WIN_BYTES);
+        tma_load_4d(smem, &tmap, &full[0], 0, x0 - 1, y0 - 1, n);
+    }
+    constexpr int ROW = HG_TW + 2;
+    const int r0 = (ty + 1) * ROW + tx + 1;                      // this thread's own patch in the window
+    for (int it = 0; n < N; n += gridDim.z, ++it) {
+        const int b = it & 1;
+        if (threadIdx.x == 0 && n + static_cast<int>(gridDim.z) < N) {          // the other buffer was read in iteration it - 1
+            mbar_arrive_expect_tx(&full[b ^ 1], HGT_WIN_BYTES);
+            tma_load_4d(smem + (b ^ 1) * HGT_BUF_BYTES, &tmap, &full[b ^ 1], 0, x0 - 1, y0 - 1, n + gridDim.z);
+        }
+        mbar_wait(&full[b], (it >> 1) & 1);
+        if (xl < w && yl < h) {
+            const uint8_t* win = smem + b * HGT_BUF_BYTES;
+            // own rows 1, 2; the neighbours' rows / columns that overlap this pixel's 2x2 outputs (patch origin (2y-1, 2x-1))
+            const float4 o1 = hgt_row(win, r0, 1), o2 = hgt_row(win, r0, 2);
+            const float4 u3 = hgt_row(win, r0 - ROW, 3), d0 = hgt_row(win, r0 + ROW, 0);
+            const float4 l1 = hgt_row(win, r0 - 1, 1), l2 = hgt_row(win, r0 - 1, 2);
+            const float4 q1 = hgt_row(win, r0 + 1, 1), q2 = hgt_row(win, r0 + 1, 2);
+            const float4 ul = hgt_row(win, r0 - ROW - 1, 3), ur = hgt_row(win, r0 - ROW + 1, 3);
+            const float4 dl = hgt_row(win, r0 + ROW - 1, 0), dr = hgt_row(win, r0 + ROW + 1, 0);
+            float r[4];
+            // (a, b) = (0,0): own [1][1], up [3][1], left [1][3], up-left [3][3]   (same order as head_gather_kernel)
+            r[0] = ((bias + o1.y) + u3.y + l1.w) + ul.w;
+            r[1] = ((bias + o1.z) + u3.z + q1.x) + ur.x;        // (0,1): own [1][2], up [3][2], right [1][0], up-right [3][0]
+            r[2] = ((bias + o2.y) + d0.y + l2.w) + dl.w;        // (1,0): own [2][1], down [0][1], left [2][3], down-left [0][3]
+            r[3] = ((bias + o2.z) + d0.z + q2.x) + dr.x;        // (1,1): own [2][2], down [0][2], right [2][0], down-right [0][0]
+            if (apply_sigmoid) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float s = 1.f / (1.f + __expf(-r[i]));
+                    r[i] = fminf(fmaxf(s, 0.f), 1.f);
+                }
+            }
+            const size_t slot = out_index ? static_cast<size_t>(__ldg(out_index + n)) : static_cast<size_t>(n);
+            float* o = out + slot * out_image_stride + static_cast<size_t>(2 * yl) * W + 2 * xl;
+            *reinterpret_cast<float2*>(o) = make_float2(r[0], r[1]);
+            *reinterpret_cast<float2*>(o + W) = make_float2(r[2], r[3]);
+        }
+        __syncthreads();                                         // the window may be refilled
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // latent interpolation + layout change
 //   z    fp32 NCHW [*, C, HW]  (public latent layout)
