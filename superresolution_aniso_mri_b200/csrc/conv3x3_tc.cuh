@@ -551,9 +551,9 @@ __host__ __device__ constexpr bool lean_stats(int mode) { return mode == LEAN_SA
 // cp.async.bulk.tensor (box {16 ch, 8, 16, 1}, clipped at the image bounds by the hardware) instead of 128 threads x 2 STG.128.
 // Measured (profiles/r09_store_cost_stage_isolation.txt): the per-thread global stores cost the 64 / 128-column layers 14-29 %
 // (dec.2 0.317 -> 0.246 ms, dec.6 0.540 -> 0.387 ms without them) although the epilogue warps mostly WAIT for the MMAs there;
-// the same bytes written to shared memory instead cost ~nothing (dec.2 0.250, dec.6 0.392 ms).  Global stores enter the
-// sub-partition's MIO queue, which the MMA issuer (warp 1) shares with epilogue warps 5, 9, 13, 17; ncu shows the issuer
-// stalled on mio_throttle at its UTCHMMAs (profiles/r08_halo_issuer_stalls.txt).
+// the same bytes written to shared memory instead cost ~nothing (dec.2 0.250, dec.6 0.392 ms).  ncu shows the MMA issuer
+// stalled on mio_throttle at its UTCHMMAs (profiles/r08_halo_issuer_stalls.txt); staging only the warps of the issuer's
+// sub-partition is not enough (per-thread stores from the other three quarters still cost 10-20 %, r10 record).
 //   st_set: this set's staging buffers, st_k: running chunk count of this thread's set (buffer = st_k % st_bufs),
 //   st_elect: this thread issues (and owns the bulk groups of) the set's stores.
 // TMAST is a compile-time property of the kernel instantiation: with the staged path only behind a run-time flag the 32-column
