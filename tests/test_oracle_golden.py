@@ -238,6 +238,21 @@ def test_ssim_psnr_properties():
     f = O._uniform_filter_reflect(a.astype(np.float64), 7)
     p = np.pad(a.astype(np.float64), 3, mode="symmetric")
     assert abs(f[10, 20] - p[10:17, 20:27].mean()) < 1e-12 and abs(f[0, 0] - p[0:7, 0:7].mean()) < 1e-12
+    # ... and against scipy.ndimage.uniform_filter itself: the one numerical component scikit-image's structural_similarity
+    # delegates to (its own code is the ~15 lines of arithmetic ssim_slice restates), on even / odd / tiny sizes
+    import scipy.ndimage
+    for shape in ((64, 64), (37, 53), (9, 8), (7, 7), (220, 220)):
+        img = rng.rand(*shape)
+        np.testing.assert_allclose(O._uniform_filter_reflect(img, 7), scipy.ndimage.uniform_filter(img, size=7), rtol=0, atol=1e-13)
+    # the whole metric with scipy's filter in place of the restated one
+    x, y = a.astype(np.float64), b.astype(np.float64)
+    uf = lambda v: scipy.ndimage.uniform_filter(v, size=7)      # noqa: E731
+    ux, uy, uxx, uyy, uxy = uf(x), uf(y), uf(x * x), uf(y * y), uf(x * y)
+    cn = 49.0 / 48.0
+    vx, vy, vxy = cn * (uxx - ux * ux), cn * (uyy - uy * uy), cn * (uxy - ux * uy)
+    C1, C2 = (0.01 * 2.0) ** 2, (0.03 * 2.0) ** 2
+    S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+    assert abs(S[3:-3, 3:-3].mean() - s) < 1e-12
 
 
 def test_vif_oracle_against_reference_golden(golden):
